@@ -1,0 +1,119 @@
+/*
+ * rnerf_b200.h -- C ABI of the B200-native refractive rendering hot path.
+ *
+ * The reference (alexkeroro86/SampleNeRFRO) has no FFI layer: the path sits behind Python call
+ * signatures and is lowered by XLA.  Each entry point below names the reference function
+ * (file:line under /root/reference) whose arithmetic it replaces; INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host; arrays
+ *     are row-major, contiguous, fp32 unless stated; indices are int32.
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on that stream, do not
+ *     allocate, do not synchronise.
+ *   - return value: 0 = ok, <0 = invalid argument (RNERF_E_*), >0 = cudaError_t.  rnerf_last_error()
+ *     returns a thread-local message for the last non-zero return.
+ *   - python floats of the reference (nmin, nmax, near, far) cross the ABI as double and are rounded
+ *     to fp32 at the same point the reference rounds them.
+ *
+ * Path record ("bent sample"): 12 floats per (ray, march step), [B][S][12]:
+ *     0..2 ray_pos   3 ray_dist   4..6 ray_dir (safe-l2-normalised)   7 idx_data (n)
+ *     8..10 idx_grad (grad n)     11 |v| (safe norm of the un-normalised direction state)
+ *   i.e. the five arrays PathSampler.__call__ returns (rnerf/eikonal_utils.py:118-124), interleaved.
+ */
+#ifndef RNERF_B200_H_
+#define RNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNERF_ABI_VERSION 1
+#define RNERF_PATH_STRIDE 12
+
+#define RNERF_E_NULL   (-1)  /* null pointer */
+#define RNERF_E_SHAPE  (-2)  /* bad size / unsupported shape */
+#define RNERF_E_ALIGN  (-3)  /* pointer not 16-byte aligned */
+#define RNERF_E_ARCH   (-4)  /* device is not sm_100 */
+
+int rnerf_abi_version(void);
+const char* rnerf_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t rnerf_launch_count(void);
+
+/* ---- a1: rnerf/ior_utils.py:327-363 conv3d_normal -- normalised ws^3 Gaussian, edge padding ---- */
+int rnerf_grid_blur(const float* n_in, float* n_out, const int ndim_host[3], int ws, double sigma, void* stream);
+
+/* ---- a2: rnerf/ior_utils.py:161,165-172 VoxMLP.setup/_compute_grad -- table[G^3][4] = (n, dn/dx, dn/dy, dn/dz) */
+int rnerf_grid_table(const float* n, const int ndim_host[3], const double nmin_host[3], const double nmax_host[3],
+                     float* table, void* stream);
+
+/* ---- a3: rnerf/ior_utils.py:188-223 VoxMLP._linear3 -- out[N][4] */
+int rnerf_grid_lookup(const float* table, const int ndim_host[3], const double nmin_host[3],
+                      const double nmax_host[3], const float* pts, int64_t n_pts, float* out, void* stream);
+
+/* ---- a5/a6: rnerf/eikonal_utils.py:30-49,101-124 OneEikonalStep + PathSampler (radiance stage) ----
+ * step_size = (far - near) / (S - 1) (rnerf/models.py:121-122).  path: [B][S][12] records. */
+int rnerf_march_fwd(const float* table, const int ndim_host[3], const double nmin_host[3],
+                    const double nmax_host[3], const float* origins, const float* viewdirs, int64_t n_rays,
+                    double near, double far, int n_steps, float* path, void* stream);
+
+/* ---- a7: rnerf/models.py:240-247 coarse selection; jitter[Nc] int32 march-step indices ---- */
+int rnerf_select(const float* path, int64_t n_rays, int n_steps, const int32_t* jitter, int n_coarse,
+                 float* pos_c, float* dir_c, float* t_c, float* grad_c, void* stream);
+
+/* ---- a8+a9: rnerf/model_utils.py:187-214 pos_enc + :30-90 NerfMLP, fused, bf16 tcgen05 ----
+ * rnerf_encmlp_pack converts the 12 Flax Dense layers ([in,out] kernels, [out] biases; creation order
+ * Dense_0..11 of model_utils.py:65-89) into the device image the kernel streams with TMA.
+ * kernels_host/biases_host: host arrays of 12 device pointers.  packed: rnerf_encmlp_packed_bytes(). */
+size_t rnerf_encmlp_packed_bytes(void);
+int rnerf_encmlp_pack(const float* const* kernels_host, const float* const* biases_host, void* packed, void* stream);
+/* raw_out[M][4] = (raw_rgb[3], raw_sigma).  pos/dir: [M][3].  M arbitrary (tail rows are masked). */
+int rnerf_encmlp_fwd(const void* packed, const float* pos, const float* dir, int64_t n_samples, float* raw_out,
+                     void* stream);
+/* debug/parity variant: also dumps every layer's post-activation output as bf16, layer_out[L][M][256]
+ * (L = 10: Dense_0..7, bottleneck, cond layer (first 128 cols)). */
+int rnerf_encmlp_fwd_debug(const void* packed, const float* pos, const float* dir, int64_t n_samples,
+                           float* raw_out, uint16_t* layer_out, void* stream);
+
+/* ---- a10: rnerf/model_utils.py:93-140 MLP as bkgd_mlp (27->128->128->128(+27)->128->3), fp32 ----
+ * w: the 5 Dense kernels then the 5 biases, concatenated fp32 ([in,out] row-major each).
+ * dirs: [B][3] unit directions (encoded in-kernel, pos_enc deg 0..4).  raw_out: [B][3]. */
+size_t rnerf_bkgd_weight_floats(void);
+int rnerf_bkgd_mlp_fwd(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
+                       float* raw_out, void* stream);
+
+/* ---- a11+a12: rnerf/models.py:334-338 activations + rnerf/model_utils.py:247-309 volumetric_rendering ----
+ * raw: [B][Ns][4]; t: [B][Ns]; dirs: [B][Ns][3]; bkgd_raw: [B][3] or NULL (rgb_bkgd=None);
+ * mask: [B][Ns] fp32 or NULL.  Outputs (any may be NULL except comp_rgb): comp_rgb[B][3], distance[B],
+ * acc[B], weights[B][Ns], alpha[B][Ns], trans[B], trans_rgb_bkgd[B][3]. */
+int rnerf_composite_fwd(const float* raw, const float* t, const float* dirs, const float* bkgd_raw,
+                        const float* mask, int64_t n_rays, int n_samples, int white_bkgd, double rgb_padding,
+                        double sigma_bias, float* comp_rgb, float* distance, float* acc, float* weights,
+                        float* alpha, float* trans, float* trans_rgb_bkgd, void* stream);
+/* backward of the above wrt raw and bkgd_raw, from d(comp_rgb)[B][3], d(trans)[B], d(trans_rgb_bkgd)[B][3]
+ * (any may be NULL = zero).  d_raw: [B][Ns][4]; d_bkgd_raw: [B][3] or NULL. */
+int rnerf_composite_bwd(const float* raw, const float* t, const float* dirs, const float* bkgd_raw,
+                        const float* mask, int64_t n_rays, int n_samples, int white_bkgd, double rgb_padding,
+                        double sigma_bias, const float* d_comp_rgb, const float* d_trans,
+                        const float* d_trans_rgb_bkgd, float* d_raw, float* d_bkgd_raw, void* stream);
+
+/* ---- a13+a14: rnerf/model_utils.py:312-374 sorted_piecewise_constant_pdf + :377-435 sample_pdf ----
+ * t_c/weights_c: [B][Nc] coarse distances / compositing weights (the kernel forms the mid-point bins and
+ * uses weights[1:-1]); u: [Nf] (u_per_ray=0) or [B][Nf] sorted CDF positions in [0,1).
+ * Outputs: t_f[B][Nc+Nf], pos_f/dir_f/grad_f [B][Nc+Nf][3]. */
+int rnerf_resample(const float* path, int64_t n_rays, int n_steps, const float* t_c, const float* weights_c,
+                   int n_coarse, const float* u, int u_per_ray, int n_fine, float* t_f, float* pos_f, float* dir_f,
+                   float* grad_f, void* stream);
+
+/* ---- a15: rnerf/models.py:498-503 bd_cut_dist mask: reverse-cumsum(inside bbox) > 0 ---- */
+int rnerf_bbox_tail_mask(const float* pos, int64_t n_rays, int n_samples, const double lo_host[3],
+                         const double hi_host[3], float* mask, float* inv_mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNERF_B200_H_ */

@@ -1,0 +1,702 @@
+"""CPU restatement (torch-CPU, IEEE fp32 per op; fp64 switch) of SampleNeRFRO's refractive
+rendering hot path.  TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+Every function cites the reference lines (relative to /root/reference) it follows.
+
+PINNING STATUS: the reference ships no tests / golden vectors for this path
+and its arithmetic lives in jax==0.2.22 / flax==0.3.6, which are not installable here.  The oracle is
+pinned instead by executing the reference's *own source files* under a numpy-backed jax/flax shim
+(tests/golden/make_reference_goldens.py -> tests/golden/ref_*.npz, checked in
+tests/test_oracle_vs_reference.py) and by analytic known-answer tests (tests/test_oracle_kat.py).
+
+Conventions
+  * all arrays are torch CPU tensors; `dt` is torch.float32 (default) or torch.float64.
+  * Python-float constants of the reference (step_size, nmin, ndelta, ...) are rounded to `dt` at the
+    point of use, exactly like jnp weak-typed scalars.
+  * elementwise expressions are written in the reference's association order; 3-vector sums are
+    (x+y)+z.  With fp32 this makes the march bit-reproducible by the CUDA kernel (which uses
+    non-contracted __fmul_rn/__fadd_rn in the same order).
+  * stochastic inputs (`jitter`, `u`) are explicit arguments (JAX threefry streams cannot be
+    reproduced without JAX).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+F32 = torch.float32
+F64 = torch.float64
+
+
+class Rays(NamedTuple):  # rnerf/utils.py:67
+    origins: torch.Tensor
+    directions: torch.Tensor
+    viewdirs: torch.Tensor
+    radii: torch.Tensor
+
+
+def _c(v: float, dt) -> torch.Tensor:
+    """A Python scalar rounded to dt (jnp weak-type behaviour)."""
+    return torch.tensor(float(v), dtype=dt)
+
+
+def as_t(x, dt=F32) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(dt)
+    return torch.as_tensor(np.asarray(x), dtype=dt)
+
+
+# ----------------------------------------------------------------------------------------------
+# a1. grid preparation  (train.py:209-225, rnerf/ior_utils.py:327-363)
+# ----------------------------------------------------------------------------------------------
+_RI_033_KEYS = ("glass", "wineglass", "pen", "torus_skydome-bkgd_cycles", "dolphin", "lighthouse", "yellow")
+
+
+def ior_scale_for_config(cfg_name: str) -> float:
+    """train.py:220 -- scene-name string matching picks the refractive-index scale."""
+    return 0.33 if any(k in cfg_name for k in _RI_033_KEYS) else 0.5
+
+
+def ior_rescale(data: np.ndarray, cfg_name: str) -> np.ndarray:
+    """train.py:223 -- (data - 1) * ri / 0.33 + 1, evaluated in numpy float64 as the reference does."""
+    ri = ior_scale_for_config(cfg_name)
+    return (np.asarray(data, dtype=np.float64) - 1.0) * ri / 0.33 + 1.0
+
+
+def gaussian_kernel3d(ws: int, s: float, dt=F32) -> torch.Tensor:
+    """rnerf/ior_utils.py:345-348 -- normalised 3-D Gaussian of side ws."""
+    hws = ws // 2
+    a = torch.linspace(-hws, hws, ws, dtype=dt)
+    xx, yy, zz = torch.meshgrid(a, a, a, indexing="xy")
+    k = torch.exp(-(xx ** 2 + yy ** 2 + zz ** 2) / (2.0 * s ** 2))
+    return k / k.sum()
+
+
+def conv3d_normal(grid, ndim: Sequence[int], ws: int, s: float, dt=F32) -> torch.Tensor:
+    """rnerf/ior_utils.py:327-363 -- edge-padded 'VALID' correlation with the Gaussian kernel.
+    Returns [G^3, 1]."""
+    hws = ws // 2
+    data = as_t(grid, dt).reshape(1, 1, ndim[0], ndim[1], ndim[2])
+    data = F.pad(data, (hws,) * 6, mode="replicate")
+    k = gaussian_kernel3d(ws, s, dt).reshape(1, 1, ws, ws, ws)
+    out = F.conv3d(data, k)
+    return out.reshape(-1, 1)
+
+
+def compute_ndelta(ndim, nmin, nmax) -> List[float]:
+    """rnerf/ior_utils.py:140-144 (python doubles)."""
+    return [(nmax[i] - nmin[i]) / (ndim[i] - 1.0) for i in range(3)]
+
+
+# ----------------------------------------------------------------------------------------------
+# a2. gradient table  (rnerf/ior_utils.py:161,165-172)
+# ----------------------------------------------------------------------------------------------
+def compute_grad(grid, ndim, nmin, nmax, dt=F32) -> torch.Tensor:
+    nd = compute_ndelta(ndim, nmin, nmax)
+    g = as_t(grid, dt).reshape(1, 1, ndim[0], ndim[1], ndim[2])
+    p = F.pad(g, (1,) * 6, mode="replicate")[0, 0]
+    dx = (p[2:, 1:-1, 1:-1] - p[:-2, 1:-1, 1:-1]) / _c(2 * nd[0], dt)
+    dy = (p[1:-1, 2:, 1:-1] - p[1:-1, :-2, 1:-1]) / _c(2 * nd[1], dt)
+    dz = (p[1:-1, 1:-1, 2:] - p[1:-1, 1:-1, :-2]) / _c(2 * nd[2], dt)
+    return torch.stack([dx, dy, dz], dim=-1).reshape(-1, 3)
+
+
+def build_table(grid, ndim, nmin, nmax, dt=F32) -> torch.Tensor:
+    """VoxMLP.setup: data = concat(n, grad n) -> [G^3, 4]."""
+    g = as_t(grid, dt).reshape(-1, 1)
+    return torch.cat([g, compute_grad(g, ndim, nmin, nmax, dt)], dim=-1).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# a3. trilinear lookup  (rnerf/ior_utils.py:188-223)
+# ----------------------------------------------------------------------------------------------
+def linear3(table: torch.Tensor, ndim, nmin, nmax, pts: torch.Tensor) -> torch.Tensor:
+    dt = table.dtype
+    nd = compute_ndelta(ndim, nmin, nmax)
+    x = (pts[..., 0] - _c(nmin[0], dt)) / _c(nd[0], dt)
+    y = (pts[..., 1] - _c(nmin[1], dt)) / _c(nd[1], dt)
+    z = (pts[..., 2] - _c(nmin[2], dt)) / _c(nd[2], dt)
+    xf, yf, zf = torch.floor(x), torch.floor(y), torch.floor(z)
+    # (x - x0) / (x1 - x0) with x1 - x0 == 1
+    xd = (x - xf)[..., None]
+    yd = (y - yf)[..., None]
+    zd = (z - zf)[..., None]
+    x0 = xf.long(); y0 = yf.long(); z0 = zf.long()
+    x1 = x0 + 1; y1 = y0 + 1; z1 = z0 + 1
+    x0 = x0.clamp(0, ndim[0] - 1); x1 = x1.clamp(0, ndim[0] - 1)
+    y0 = y0.clamp(0, ndim[1] - 1); y1 = y1.clamp(0, ndim[1] - 1)
+    z0 = z0.clamp(0, ndim[2] - 1); z1 = z1.clamp(0, ndim[2] - 1)
+    sx, sy = ndim[1] * ndim[2], ndim[2]
+
+    def at(ix, iy, iz):
+        return table[sx * ix + sy * iy + iz]
+
+    one = _c(1.0, dt)
+    c00 = at(x0, y0, z0) * (one - xd) + at(x1, y0, z0) * xd
+    c01 = at(x0, y0, z1) * (one - xd) + at(x1, y0, z1) * xd
+    c10 = at(x0, y1, z0) * (one - xd) + at(x1, y1, z0) * xd
+    c11 = at(x0, y1, z1) * (one - xd) + at(x1, y1, z1) * xd
+    c0 = c00 * (one - yd) + c10 * yd
+    c1 = c01 * (one - yd) + c11 * yd
+    return c0 * (one - zd) + c1 * zd
+
+
+# ----------------------------------------------------------------------------------------------
+# math helpers  (rnerf/math_utils.py:6-20)
+# ----------------------------------------------------------------------------------------------
+def sumsq3(x: torch.Tensor) -> torch.Tensor:
+    return (x[..., 0:1] * x[..., 0:1] + x[..., 1:2] * x[..., 1:2]) + x[..., 2:3] * x[..., 2:3]
+
+
+def safe_l2_norm(x, eps=1e-6):
+    return torch.sqrt(torch.maximum(sumsq3(x), _c(eps, x.dtype)))
+
+
+def safe_l2_normalize(x, eps=1e-6):
+    return x / safe_l2_norm(x, eps)
+
+
+def safe_log(x, eps=1e-6):
+    return torch.log(torch.maximum(x, _c(eps, x.dtype)))
+
+
+# ----------------------------------------------------------------------------------------------
+# a8. encodings  (rnerf/model_utils.py:187-214, 218-245)
+# ----------------------------------------------------------------------------------------------
+def pos_enc(x: torch.Tensor, min_deg: int, max_deg: int, legacy_posenc_order=False) -> torch.Tensor:
+    if min_deg == max_deg:
+        return x
+    dt = x.dtype
+    scales = torch.tensor([2 ** i for i in range(min_deg, max_deg)], dtype=dt)
+    half_pi = _c(0.5 * math.pi, dt)
+    if legacy_posenc_order:
+        xb = x[..., None, :] * scales[:, None]
+        four = torch.sin(torch.stack([xb, xb + half_pi], -2)).reshape(*x.shape[:-1], -1)
+    else:
+        xb = (x[..., None, :] * scales[:, None]).reshape(*x.shape[:-1], -1)
+        four = torch.sin(torch.cat([xb, xb + half_pi], dim=-1))
+    return torch.cat([x, four], dim=-1)
+
+
+def cosine_easing_window(min_freq_log2, max_freq_log2, num_bands, alpha, dt=F32):
+    bands = torch.linspace(min_freq_log2, max_freq_log2, num_bands, dtype=dt)
+    x = torch.clamp(as_t(alpha, dt) - bands, 0.0, 1.0)
+    return 0.5 * (1 + torch.cos(math.pi * x + math.pi))
+
+
+def annealed_pos_enc(x, min_deg, max_deg, alpha):
+    if min_deg == max_deg:
+        return x
+    dt = x.dtype
+    scales = torch.tensor([2 ** i for i in range(min_deg, max_deg)], dtype=dt)
+    xb = x[..., None, :] * scales[:, None]
+    window = cosine_easing_window(min_deg, max_deg - 1, len(scales), alpha, dt)[:, None]
+    half_pi = _c(0.5 * math.pi, dt)
+    four = torch.cat([torch.sin(xb) * window, torch.sin(xb + half_pi) * window], dim=-1)
+    return four.reshape(*x.shape[:-1], -1)
+
+
+# ----------------------------------------------------------------------------------------------
+# a9/a10. MLPs  (rnerf/model_utils.py:30-90, 93-140).  Params: {"Dense_i": {"kernel": [in,out], "bias": [out]}}
+# ----------------------------------------------------------------------------------------------
+def _bf16r(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+def dense(p, x, emulate_bf16=False):
+    k, b = p["kernel"], p["bias"]
+    if emulate_bf16:
+        return _bf16r(x) @ _bf16r(k) + b
+    return x @ k + b
+
+
+def nerf_mlp(params: Dict, x: torch.Tensor, condition: Optional[torch.Tensor], net_depth=8, skip_layer=4,
+             net_depth_condition=1, emulate_bf16=False, return_layers=False):
+    """NerfMLP.__call__ (rnerf/model_utils.py:42-90).  x [B,Ns,F], condition [B,Ns,C] (per-sample, T10)."""
+    num_samples = x.shape[1]
+    x = x.reshape(-1, x.shape[-1])
+    inputs = x
+    layers = []
+    li = 0
+    for i in range(net_depth):
+        x = torch.relu(dense(params[f"Dense_{li}"], x, emulate_bf16)); li += 1
+        layers.append(x)
+        if i % skip_layer == 0 and i > 0:
+            x = torch.cat([x, inputs], dim=-1)
+    raw_sigma = dense(params[f"Dense_{li}"], x, emulate_bf16).reshape(-1, num_samples, 1); li += 1
+    if condition is not None:
+        bottleneck = dense(params[f"Dense_{li}"], x, emulate_bf16); li += 1
+        layers.append(bottleneck)
+        condition = condition.reshape(-1, condition.shape[-1])
+        x = torch.cat([bottleneck, condition], dim=-1)
+        for i in range(net_depth_condition):
+            x = torch.relu(dense(params[f"Dense_{li}"], x, emulate_bf16)); li += 1
+            layers.append(x)
+    raw_rgb = dense(params[f"Dense_{li}"], x, emulate_bf16).reshape(-1, num_samples, 3)
+    if return_layers:
+        return raw_rgb, raw_sigma, layers
+    return raw_rgb, raw_sigma
+
+
+def small_mlp(params: Dict, x: torch.Tensor, net_depth=4, skip_layer=2):
+    """MLP.__call__ without condition (rnerf/model_utils.py:105-140); bkgd_mlp / so3_mlp."""
+    num_samples = x.shape[1]
+    x = x.reshape(-1, x.shape[-1])
+    inputs = x
+    li = 0
+    for i in range(net_depth):
+        x = torch.relu(dense(params[f"Dense_{li}"], x)); li += 1
+        if i % skip_layer == 0 and i > 0:
+            x = torch.cat([x, inputs], dim=-1)
+    out = dense(params[f"Dense_{li}"], x)
+    return out.reshape(-1, num_samples, out.shape[-1])
+
+
+def glorot_uniform(gen: torch.Generator, fan_in: int, fan_out: int, dt=F32) -> torch.Tensor:
+    a = math.sqrt(6.0 / (fan_in + fan_out))
+    return ((torch.rand(fan_in, fan_out, generator=gen, dtype=torch.float64) * 2 - 1) * a).to(dt)
+
+
+def init_nerf_mlp(gen, in_dim=63, cond_dim=27, width=256, depth=8, skip=4, wc=128, bias_scale=0.0, dt=F32):
+    """Layer creation order of rnerf/model_utils.py:65-89: Dense_0..7 trunk, 8 sigma, 9 bottleneck, 10 cond, 11 rgb."""
+    p = {}
+    d_in = in_dim
+    li = 0
+
+    def mk(i, o):
+        return {"kernel": glorot_uniform(gen, i, o, dt),
+                "bias": ((torch.rand(o, generator=gen, dtype=torch.float64) * 2 - 1) * bias_scale).to(dt)}
+
+    for i in range(depth):
+        p[f"Dense_{li}"] = mk(d_in, width); li += 1
+        d_in = width
+        if i % skip == 0 and i > 0:
+            d_in = width + in_dim
+    p[f"Dense_{li}"] = mk(d_in, 1); li += 1
+    p[f"Dense_{li}"] = mk(d_in, width); li += 1
+    p[f"Dense_{li}"] = mk(width + cond_dim, wc); li += 1
+    p[f"Dense_{li}"] = mk(wc, 3)
+    return p
+
+
+def init_small_mlp(gen, in_dim=27, width=128, depth=4, skip=2, out_dim=3, bias_scale=0.0, out_std=None, dt=F32):
+    p = {}
+    d_in = in_dim
+    li = 0
+
+    def mk(i, o):
+        return {"kernel": glorot_uniform(gen, i, o, dt),
+                "bias": ((torch.rand(o, generator=gen, dtype=torch.float64) * 2 - 1) * bias_scale).to(dt)}
+
+    for i in range(depth):
+        p[f"Dense_{li}"] = mk(d_in, width); li += 1
+        d_in = width
+        if i % skip == 0 and i > 0:
+            d_in = width + in_dim
+    p[f"Dense_{li}"] = mk(d_in, out_dim)
+    if out_std is not None:
+        p[f"Dense_{li}"]["kernel"] = (torch.randn(d_in, out_dim, generator=gen, dtype=torch.float64) * out_std).to(dt)
+    return p
+
+
+def init_variables(seed=0, bias_scale=0.0, dt=F32) -> Dict:
+    """Param tree with the reference's names."""
+    gen = torch.Generator().manual_seed(seed)
+    return {"params": {
+        "coarse_mlp": init_nerf_mlp(gen, bias_scale=bias_scale, dt=dt),
+        "fine_mlp": init_nerf_mlp(gen, bias_scale=bias_scale, dt=dt),
+        "bkgd_mlp": init_small_mlp(gen, bias_scale=bias_scale, dt=dt),
+        "path_sampler": {"scan": {"idx_model": {"so3_mlp": init_small_mlp(gen, in_dim=60, out_std=1e-5, dt=dt)}}},
+    }}
+
+
+# ----------------------------------------------------------------------------------------------
+# a4. so3 rotation of grad n ("all" stage)  (rnerf/ior_utils.py:225-267, 282-312)
+# ----------------------------------------------------------------------------------------------
+def rodrigues_grad(raw: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
+    theta = safe_l2_norm(raw)
+    e = raw / theta
+    a = safe_l2_norm(grad)
+    v = grad / a
+    cross = torch.linalg.cross(e, v, dim=-1)
+    ev = (e * v).sum(-1, keepdim=True)
+    return a * (torch.cos(theta) * v + torch.sin(theta) * cross + (1 - torch.cos(theta)) * ev * e)
+
+
+# ----------------------------------------------------------------------------------------------
+# a5/a6. eikonal march  (rnerf/eikonal_utils.py:30-49, 101-124)
+# ----------------------------------------------------------------------------------------------
+def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, num_steps: int,
+          stage="radiance", so3_params=None, annealed_alpha=1.0):
+    """PathSampler.__call__.  Returns ray_pos[B,S,3], ray_dir[B,S,3], ray_dist[B,S], idx_data[B,S,1],
+    idx_grad[B,S,3].  `num_steps` = S = Nc*P, step_size = (far-near)/(S-1) (rnerf/models.py:121-122)."""
+    dt = table.dtype
+    step = _c((far - near) / (num_steps - 1), dt)
+    o = as_t(origins, dt); d = as_t(viewdirs, dt)
+    B = o.shape[0]
+    rp = o + _c(near, dt) * d
+    rd = d.clone()
+    rt = _c(near, dt) * torch.ones(B, 1, dtype=dt)
+    pos = torch.empty(B, num_steps, 3, dtype=dt); dirs = torch.empty(B, num_steps, 3, dtype=dt)
+    dist = torch.empty(B, num_steps, dtype=dt)
+    idx_data = torch.empty(B, num_steps, 1, dtype=dt); idx_grad = torch.empty(B, num_steps, 3, dtype=dt)
+    for k in range(num_steps):
+        ret = linear3(table, ndim, nmin, nmax, rp)
+        n, g = ret[:, :1], ret[:, 1:]
+        pos[:, k] = rp; dirs[:, k] = rd; dist[:, k] = rt[:, 0]
+        idx_data[:, k] = n; idx_grad[:, k] = g
+        if stage.startswith("all"):
+            raw = small_mlp(so3_params, annealed_pos_enc(rp[:, None], 0, 10, annealed_alpha * 10))[:, 0]
+            pred = rodrigues_grad(raw, g)
+            gn = torch.sqrt(sumsq3(g))
+            g_used = torch.where(gn > 1e-3, pred, g)
+        else:
+            g_used = g
+        nrp = rp + step / n * rd
+        nrd = rd + step * g_used
+        rt = rt + torch.sqrt(sumsq3(rp - nrp))
+        rp, rd = nrp, nrd
+    return pos, safe_l2_normalize(dirs), dist, idx_data, idx_grad
+
+
+# ----------------------------------------------------------------------------------------------
+# a12. compositing  (rnerf/model_utils.py:247-309)
+# ----------------------------------------------------------------------------------------------
+def volumetric_rendering(rgb, density, t_vals, dirs, white_bkgd, rgb_bkgd, mask_bbox=None):
+    dt = rgb.dtype
+    t_dists = torch.cat([t_vals[..., 1:] - t_vals[..., :-1],
+                         torch.full_like(t_vals[..., :1], 1e-3)], -1)
+    delta = t_dists * torch.sqrt(sumsq3(dirs))[..., 0]
+    density_delta = density[..., 0] * delta
+    if mask_bbox is not None:
+        density_delta = density_delta * mask_bbox.to(dt)
+    alpha = 1 - torch.exp(-density_delta)
+    trans = torch.exp(-torch.cat([torch.zeros_like(density_delta[..., :1]),
+                                  torch.cumsum(density_delta, dim=-1)], dim=-1))
+    weights = alpha * trans[..., :-1]
+    if rgb_bkgd is not None:
+        comp_rgb = (weights[..., None] * rgb).sum(dim=-2) + trans[..., -1:] * rgb_bkgd
+    else:
+        comp_rgb = (weights[..., None] * rgb).sum(dim=-2)
+        rgb_bkgd = torch.ones(*trans[..., -1:].shape[:-1], 3, dtype=dt)
+    acc = weights.sum(dim=-1)
+    distance = (weights * t_vals).sum(dim=-1) / acc
+    # jnp.nan_to_num(distance, jnp.inf): the 2nd positional arg is `copy` -> NaN->0, +-inf->+-max (T12)
+    distance = torch.nan_to_num(distance)
+    distance = torch.minimum(torch.maximum(distance, t_vals[:, 0]), t_vals[:, -1])
+    if white_bkgd:
+        comp_rgb = comp_rgb + (1.0 - acc[..., None])
+    return comp_rgb, distance, acc, weights, alpha, trans[..., -1:], trans[..., -1:] * rgb_bkgd.detach()
+
+
+# ----------------------------------------------------------------------------------------------
+# a13. PDF sampling  (rnerf/model_utils.py:312-374)
+# ----------------------------------------------------------------------------------------------
+def deterministic_u(num_samples: int, dt=F32) -> torch.Tensor:
+    """model_utils.py:354-356: linspace(0, 1 - finfo(float32).eps, N)."""
+    eps = float(np.finfo(np.float32).eps)
+    return torch.linspace(0.0, 1.0 - eps, num_samples, dtype=dt)
+
+
+def stratified_u(noise: torch.Tensor) -> torch.Tensor:
+    """model_utils.py:343-352 given noise ~ U[0, s - eps) of shape [B, N]."""
+    n = noise.shape[-1]
+    eps = float(np.finfo(np.float32).eps)
+    s = 1 / n
+    u = torch.arange(n, dtype=noise.dtype) * s + noise
+    return torch.minimum(u, _c(1.0 - eps, noise.dtype))
+
+
+def sorted_piecewise_constant_pdf(bins, weights, u, chunk=2048):
+    """bins [B,Nb+1], weights [B,Nb], u [B,N] or [N]."""
+    dt = bins.dtype
+    eps = 1e-5
+    weight_sum = weights.sum(dim=-1, keepdim=True)
+    padding = torch.clamp(_c(eps, dt) - weight_sum, min=0)
+    weights = weights + padding / weights.shape[-1]
+    weight_sum = weight_sum + padding
+    pdf = weights / weight_sum
+    cdf = torch.clamp(torch.cumsum(pdf[..., :-1], dim=-1), max=1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf, torch.ones_like(cdf[..., :1])], dim=-1)
+    if u.dim() == 1:
+        u = u[None].expand(bins.shape[0], -1)
+    out = torch.empty_like(u)
+    for s0 in range(0, bins.shape[0], chunk):
+        sl = slice(s0, s0 + chunk)
+        uu, cc, bb = u[sl], cdf[sl], bins[sl]
+        mask = uu[..., None, :] >= cc[..., :, None]
+
+        def find_interval(x):
+            x0 = torch.where(mask, x[..., None], x[..., :1, None]).max(dim=-2).values
+            x1 = torch.where(~mask, x[..., None], x[..., -1:, None]).min(dim=-2).values
+            return x0, x1
+
+        b0, b1 = find_interval(bb)
+        c0, c1 = find_interval(cc)
+        t = torch.clamp(torch.nan_to_num((uu - c0) / (c1 - c0), nan=0.0), 0, 1)
+        out[sl] = b0 + t * (b1 - b0)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# a14. hierarchical resampling along the marched path  (rnerf/model_utils.py:377-435)
+# ----------------------------------------------------------------------------------------------
+def sample_pdf(bins, weights, ray_pos, ray_dir, ray_dist, idx_grad, u, jitter):
+    z_fine = sorted_piecewise_constant_pdf(bins, weights, u)
+    z = torch.sort(torch.cat([ray_dist[:, jitter], z_fine], dim=-1), dim=-1).values
+    z = z.detach()
+    # searchsorted(side="left") into [0, 0..S-1, S-1]  ==  max(#{ray_dist < z} - 1, 0)   (T14)
+    cnt = torch.searchsorted(ray_dist.contiguous(), z.contiguous(), right=False)
+    idx = torch.clamp(cnt - 1, min=0)
+    ii = idx[..., None].expand(-1, -1, 3)
+    rd = torch.gather(ray_dir.detach(), 1, ii)
+    ro = torch.gather(ray_pos.detach(), 1, ii)
+    zz = torch.gather(ray_dist.detach(), 1, idx)
+    pos = ro + rd * (z - zz)[..., None]
+    grads = torch.gather(idx_grad.detach(), 1, ii)
+    return z, pos, rd, grads
+
+
+# ----------------------------------------------------------------------------------------------
+# a11. activations (rnerf/models.py:334-338)
+# ----------------------------------------------------------------------------------------------
+def rgb_act(raw, rgb_padding=0.001):
+    return torch.sigmoid(raw) * (1 + 2 * rgb_padding) - rgb_padding
+
+
+def sigma_act(raw, sigma_bias=-1.0):
+    return F.softplus(raw + sigma_bias)
+
+
+# ----------------------------------------------------------------------------------------------
+# a15. bbox of the bd_cut_dist passes (rnerf/models.py:479-497)
+# ----------------------------------------------------------------------------------------------
+def bd_cut_bbox(cfg_name: str, nmin, nmax):
+    if "pen" in cfg_name:
+        lo, hi = list(nmin), list(nmax); hi[1] -= 0.6
+    elif "ball" in cfg_name:
+        lo, hi = [-1, 0.03597, -1], [1, 2.03597, 1]
+    elif "glass" in cfg_name:
+        lo, hi = list(nmin), list(nmax); hi[1] -= 0.7
+    else:
+        raise NotImplementedError()
+    return lo, hi
+
+
+def inside_bbox(pos, lo, hi):
+    m = torch.ones(pos.shape[:-1], dtype=torch.bool)
+    for a in range(3):
+        m = m & (pos[..., a] >= lo[a]) & (pos[..., a] <= hi[a])
+    return m
+
+
+# ----------------------------------------------------------------------------------------------
+# a16. NerfModel.__call__  (rnerf/models.py:219-535)
+# ----------------------------------------------------------------------------------------------
+class ModelCfg(NamedTuple):
+    ndim: Sequence[int]
+    nmin: Sequence[float]
+    nmax: Sequence[float]
+    near: float = 2.0
+    far: float = 6.0
+    num_coarse_samples: int = 64
+    num_fine_samples: int = 128
+    num_path_samples: int = 12
+    min_deg_point: int = 0
+    max_deg_point: int = 10
+    deg_view: int = 4
+    white_bkgd: bool = False
+    use_mask_bbox: bool = False
+    bd_cut_dist: Optional[float] = None
+    cfg_name: str = "example"
+    stage: str = "radiance"
+    use_online_sparsity: bool = False
+    use_fine_sparsity: bool = False
+    rgb_padding: float = 0.001
+    sigma_bias: float = -1.0
+
+
+def default_jitter(cfg: ModelCfg, offsets=None) -> torch.Tensor:
+    """rnerf/models.py:240-242: arange(0, S, P) (+ randint[0,P) supplied by the caller)."""
+    j = torch.arange(0, cfg.num_coarse_samples * cfg.num_path_samples, cfg.num_path_samples)
+    if offsets is not None:
+        j = j + torch.as_tensor(offsets, dtype=torch.long)
+    return j
+
+
+def nerf_model_apply(variables: Dict, table: torch.Tensor, cfg: ModelCfg, rays: Rays, jitter: torch.Tensor,
+                     u: torch.Tensor, annealed_alpha=1.0, emulate_bf16=False, debug=False):
+    """Returns (ret, loss_sp[, dbg]) like model.apply.  `u`: [Nf] or [B,Nf] CDF positions."""
+    P = variables["params"]
+    dt = table.dtype
+    S = cfg.num_coarse_samples * cfg.num_path_samples
+    so3 = P["path_sampler"]["scan"]["idx_model"]["so3_mlp"] if cfg.stage.startswith("all") else None
+    ray_pos, ray_dir, ray_dist, idx_data, idx_grad = march(
+        table, cfg.ndim, cfg.nmin, cfg.nmax, rays.origins, rays.viewdirs, cfg.near, cfg.far, S,
+        stage=cfg.stage, so3_params=so3, annealed_alpha=annealed_alpha)
+    ray_dist = ray_dist.detach()
+    jitter = torch.as_tensor(jitter, dtype=torch.long)
+    pos_c, dir_c, t_c = ray_pos[:, jitter], ray_dir[:, jitter], ray_dist[:, jitter]
+    grad_c = idx_grad[:, jitter]
+
+    def bbox_mask(pos):
+        if not cfg.use_mask_bbox:
+            return None
+        return inside_bbox(pos, cfg.nmin, cfg.nmax)
+
+    samples_enc = pos_enc(pos_c, cfg.min_deg_point, cfg.max_deg_point)
+    viewdirs_enc = pos_enc(dir_c, 0, cfg.deg_view)
+    raw_bkgd = small_mlp(P["bkgd_mlp"], viewdirs_enc[:, -1:])[:, 0]
+    raw_rgb, raw_sigma = nerf_mlp(P["coarse_mlp"], samples_enc, viewdirs_enc, emulate_bf16=emulate_bf16)
+    rgb = rgb_act(raw_rgb, cfg.rgb_padding)
+    bkgd = rgb_act(raw_bkgd, cfg.rgb_padding)
+    sigma = sigma_act(raw_sigma, cfg.sigma_bias)
+    comp_rgb, dist, acc, weights, alpha, trans, trans_rgb_bkgd = volumetric_rendering(
+        rgb, sigma, t_c, dir_c, cfg.white_bkgd, bkgd, bbox_mask(pos_c))
+    loss_sp = torch.zeros((), dtype=dt)
+    if cfg.use_online_sparsity:
+        m = (torch.sqrt(sumsq3(grad_c))[..., 0] > 1e-6).to(dt)
+        loss_sp = (m * safe_log(alpha)).sum() / (m.sum() + 1)
+    ret = [(comp_rgb, dist, acc, trans, trans_rgb_bkgd)]
+    dbg = {"ray_pos": ray_pos, "ray_dir": ray_dir, "ray_dist": ray_dist, "idx_data": idx_data,
+           "idx_grad": idx_grad, "ray_pos_c": pos_c, "weights_c": weights, "raw_rgb_c": raw_rgb,
+           "raw_sigma_c": raw_sigma, "bkgd": bkgd}
+    if cfg.num_fine_samples > 0:
+        t_mid = 0.5 * (t_c[..., 1:] + t_c[..., :-1])
+        t_f, pos_f, dir_f, grad_f = sample_pdf(t_mid, weights[..., 1:-1], ray_pos, ray_dir, ray_dist, idx_grad,
+                                               u, jitter)
+        samples_enc = pos_enc(pos_f, cfg.min_deg_point, cfg.max_deg_point)
+        viewdirs_enc = pos_enc(dir_f, 0, cfg.deg_view)
+        raw_rgb, raw_sigma = nerf_mlp(P["fine_mlp"], samples_enc, viewdirs_enc, emulate_bf16=emulate_bf16)
+        rgb = rgb_act(raw_rgb, cfg.rgb_padding)
+        sigma = sigma_act(raw_sigma, cfg.sigma_bias)
+        comp_rgb, dist, acc, _w, alpha, trans, trans_rgb_bkgd = volumetric_rendering(
+            rgb, sigma, t_f, dir_f, cfg.white_bkgd, bkgd, bbox_mask(pos_f))
+        if cfg.bd_cut_dist is not None:
+            assert not cfg.use_mask_bbox
+            lo, hi = bd_cut_bbox(cfg.cfg_name, cfg.nmin, cfg.nmax)
+            inside = inside_bbox(pos_f, lo, hi).to(dt)
+            m = (torch.flip(torch.cumsum(torch.flip(inside, [1]), dim=-1), [1]) > 0.0).to(dt)
+            trans = volumetric_rendering(rgb, sigma, t_f, dir_f, cfg.white_bkgd, None, m)[5]
+            trb = volumetric_rendering(rgb, sigma, t_f, dir_f, cfg.white_bkgd, bkgd, 1.0 - m)[0]
+            trans_rgb_bkgd = trans * trb
+        if cfg.use_online_sparsity and cfg.use_fine_sparsity:
+            m = (torch.sqrt(sumsq3(grad_f))[..., 0] > 1e-6).to(dt)
+            loss_sp = loss_sp + (m * safe_log(alpha)).sum() / (m.sum() + 1)
+        ret.append((comp_rgb, dist, acc, trans, trans_rgb_bkgd))
+        dbg.update({"t_f": t_f, "pos_f": pos_f, "dir_f": dir_f, "grad_f": grad_f, "raw_rgb_f": raw_rgb,
+                    "raw_sigma_f": raw_sigma})
+    if debug:
+        return ret, loss_sp, dbg
+    return ret, loss_sp
+
+
+def forward_envmap(variables, viewdirs, deg_view=4, rgb_padding=0.001):
+    """NerfModel.forward_envmap (rnerf/models.py:181-191)."""
+    enc = pos_enc(viewdirs, 0, deg_view)
+    raw = small_mlp(variables["params"]["bkgd_mlp"], enc[:, None])[:, 0]
+    return rgb_act(raw, rgb_padding)
+
+
+# ----------------------------------------------------------------------------------------------
+# a17. training loss  (train.py:75-162, radiance stage)
+# ----------------------------------------------------------------------------------------------
+def tree_leaves(tree) -> List[torch.Tensor]:
+    out = []
+    if isinstance(tree, dict):
+        for k in tree:
+            out += tree_leaves(tree[k])
+    else:
+        out.append(tree)
+    return out
+
+
+def train_loss(variables, table, cfg: ModelCfg, rays: Rays, pixels, env_viewdirs, jitter, u, annealed_alpha,
+               bg_weight=0.025, bg_smooth_weight=1.0, weight_decay_mult=0.0, emulate_bf16=False):
+    dt = table.dtype
+    ret, _ = nerf_model_apply(variables, table, cfg, rays, jitter, u, annealed_alpha, emulate_bf16=emulate_bf16)
+    rgb, _, _, trans, trans_rgb_bkgd = ret[-1]
+    px = pixels[..., :3]
+    loss = ((rgb - px) ** 2).mean()
+    gate = 1.0 if annealed_alpha > 0 else 0.0
+    if bg_weight > 0:
+        mask_bg = (trans > 0.5).to(dt)
+        loss_bg = gate * (mask_bg * torch.abs(trans_rgb_bkgd - px)).sum() / (mask_bg.sum() + 1)
+    else:
+        loss_bg = torch.zeros((), dtype=dt)
+    rgb_c = ret[0][0]
+    loss_c = ((rgb_c - px) ** 2).mean()
+    if bg_smooth_weight > 0:
+        ps = env_viewdirs.shape[0]
+        env = forward_envmap(variables, env_viewdirs.reshape(-1, 3), cfg.deg_view, cfg.rgb_padding).reshape(ps, ps, -1)
+        # train.py:130 adds the two flattened (equal-length) difference vectors elementwise, then means
+        loss_bg_smooth = gate * torch.mean(0.5 * ((env[1:, :] - env[:-1, :]) ** 2).reshape(-1)
+                                           + 0.5 * ((env[:, 1:] - env[:, :-1]) ** 2).reshape(-1))
+    else:
+        loss_bg_smooth = torch.zeros((), dtype=dt)
+    leaves = tree_leaves(variables)
+    weight_l2 = sum((z ** 2).sum() for z in leaves) / sum(z.numel() for z in leaves)
+    total = loss + loss_c + bg_weight * loss_bg + bg_smooth_weight * loss_bg_smooth + weight_decay_mult * weight_l2
+    stats = {"loss": loss, "loss_c": loss_c, "loss_bg": bg_weight * loss_bg, "loss_bg_smooth": loss_bg_smooth,
+             "weight_l2": weight_l2, "psnr": -10.0 * torch.log(loss) / math.log(10.0),
+             "psnr_c": -10.0 * torch.log(loss_c) / math.log(10.0)}
+    return total, stats
+
+
+def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1, lr_start_steps=0):
+    """rnerf/utils.py:490-528."""
+    if lr_delay_steps > 0:
+        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0), 1))
+    else:
+        delay_rate = 1.0
+    start_rate = min(max(step - lr_start_steps, 0), 1)
+    t = min(max(max(step - lr_start_steps, 0) / (max_steps - lr_start_steps), 0), 1)
+    log_lerp = math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+    return start_rate * delay_rate * log_lerp
+
+
+# ----------------------------------------------------------------------------------------------
+# ray generation (rnerf/datasets.py:216-242 blender, :486-518 opencv) -- only to make synthetic rays
+# ----------------------------------------------------------------------------------------------
+def generate_rays(camtoworld: np.ndarray, h: int, w: int, focal: float, use_pixel_centers=True,
+                  opencv_K: Optional[np.ndarray] = None) -> Rays:
+    pc = 0.5 if use_pixel_centers else 0.0
+    if opencv_K is None:
+        x, y = np.meshgrid(np.arange(w, dtype=np.float32) + pc, np.arange(h, dtype=np.float32) + pc, indexing="xy")
+        cam = np.stack([(x - w * 0.5) / focal, -(y - h * 0.5) / focal, -np.ones_like(x)], axis=-1)
+    else:
+        x, y = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32), indexing="xy")
+        K = opencv_K
+        cam = np.stack([(x - K[0][2] + pc) / K[0][0], (y - K[1][2] + pc) / K[1][1], np.ones_like(x)], axis=-1)
+    c2w = np.asarray(camtoworld, dtype=np.float32)
+    directions = (cam[..., None, :] * c2w[None, None, :3, :3]).sum(axis=-1)
+    origins = np.broadcast_to(c2w[None, None, :3, -1], directions.shape)
+    viewdirs = directions / np.linalg.norm(directions, axis=-1, keepdims=True)
+    dx = np.sqrt(np.sum((directions[:-1, :, :] - directions[1:, :, :]) ** 2, -1))
+    dx = np.concatenate([dx, dx[-2:-1, :]], 0)
+    radii = dx[..., None] * 2 / np.sqrt(12)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return Rays(t(origins), t(directions), t(viewdirs), t(radii))
+
+
+# ----------------------------------------------------------------------------------------------
+# a18. mip helpers for curved rays -- DEAD on the live path (T8); restated behind this flag only
+# (rnerf/mip.py:26-57,116-175)
+# ----------------------------------------------------------------------------------------------
+def expected_sin(x, x_var):
+    y = torch.exp(-0.5 * x_var) * torch.sin(x)
+    y_var = torch.clamp(0.5 * (1 - torch.exp(-2 * x_var) * torch.cos(2 * x)) - y ** 2, min=0)
+    return y, y_var
+
+
+def integrated_pos_enc(mean, var_diag, min_deg, max_deg):
+    """mip.integrated_pos_enc with diag=True (rnerf/mip.py:143-175)."""
+    dt = mean.dtype
+    scales = torch.tensor([2 ** i for i in range(min_deg, max_deg)], dtype=dt)
+    y = (mean[..., None, :] * scales[:, None]).reshape(*mean.shape[:-1], -1)
+    y_var = (var_diag[..., None, :] * scales[:, None] ** 2).reshape(*mean.shape[:-1], -1)
+    return expected_sin(torch.cat([y, y + 0.5 * math.pi], dim=-1), torch.cat([y_var] * 2, dim=-1))[0]

@@ -1,0 +1,123 @@
+// Background MLP (a10): model_utils.MLP(net_width=128, net_depth=4, skip_layer=2) on pos_enc(dir, 0, 4)
+// (rnerf/model_utils.py:93-140, rnerf/models.py:116-118,303).  fp32 on CUDA cores: one evaluation per RAY
+// (56 448 MAC) against 256 radiance-MLP evaluations per ray (152 M MAC), so this stage is <0.1 % of the work
+// and stays in full precision.
+//   Dense_0: 27->128  Dense_1: 128->128  Dense_2: 128->128, then concat(x, inputs) -> 155
+//   Dense_3: 155->128  Dense_4: 128->3 (no activation)
+#include "common.cuh"
+
+namespace rnerf {
+
+constexpr int BK_R = 32;        // rays per block
+constexpr int BK_PITCH = 36;    // floats per feature row (R + 4: conflict-free float4 column stores)
+constexpr int BK_W = 128;
+constexpr int BK_IN = 27;
+constexpr int BK_K0 = 0;
+constexpr int BK_K1 = BK_K0 + 27 * 128;
+constexpr int BK_K2 = BK_K1 + 128 * 128;
+constexpr int BK_K3 = BK_K2 + 128 * 128;
+constexpr int BK_K4 = BK_K3 + 155 * 128;
+constexpr int BK_B0 = BK_K4 + 128 * 3;
+constexpr int BK_B1 = BK_B0 + 128;
+constexpr int BK_B2 = BK_B1 + 128;
+constexpr int BK_B3 = BK_B2 + 128;
+constexpr int BK_B4 = BK_B3 + 128;
+constexpr int BK_TOTAL = BK_B4 + 3;
+
+// acc[r] += sum_k W[k][j] * in[k][r]
+__device__ __forceinline__ void dense_accum(float (&acc)[BK_R], const float* __restrict__ W, int K, int j,
+                                            const float* __restrict__ in) {
+  for (int k = 0; k < K; ++k) {
+    const float w = __ldg(W + k * BK_W + j);
+    const float4* row = reinterpret_cast<const float4*>(in + k * BK_PITCH);
+#pragma unroll
+    for (int r4 = 0; r4 < BK_R / 4; ++r4) {
+      float4 a = row[r4];
+      acc[4 * r4 + 0] = fmaf(a.x, w, acc[4 * r4 + 0]);
+      acc[4 * r4 + 1] = fmaf(a.y, w, acc[4 * r4 + 1]);
+      acc[4 * r4 + 2] = fmaf(a.z, w, acc[4 * r4 + 2]);
+      acc[4 * r4 + 3] = fmaf(a.w, w, acc[4 * r4 + 3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_relu(const float (&acc)[BK_R], float bias, float* __restrict__ out_row) {
+  float4* o = reinterpret_cast<float4*>(out_row);
+#pragma unroll
+  for (int r4 = 0; r4 < BK_R / 4; ++r4)
+    o[r4] = make_float4(fmaxf(acc[4 * r4] + bias, 0.f), fmaxf(acc[4 * r4 + 1] + bias, 0.f),
+                        fmaxf(acc[4 * r4 + 2] + bias, 0.f), fmaxf(acc[4 * r4 + 3] + bias, 0.f));
+}
+
+__global__ void __launch_bounds__(BK_W) bkgd_mlp_kernel(const float* __restrict__ w, const float* __restrict__ dirs,
+                                                        int64_t n_rays, int64_t dir_stride, float* __restrict__ raw_out) {
+  __shared__ __align__(16) float X[BK_W * BK_PITCH];
+  __shared__ __align__(16) float Y[BK_W * BK_PITCH];
+  __shared__ __align__(16) float E[BK_IN * BK_PITCH];
+  const int j = threadIdx.x;
+  const int64_t ray0 = blockIdx.x * (int64_t)BK_R;
+  // pos_enc(dir, 0, 4): [x(3), sin(2^k x) k-major (12), sin(2^k x + pi/2) k-major (12)]  (model_utils.py:204-214)
+  for (int e = j; e < BK_IN * BK_R; e += BK_W) {
+    const int r = e % BK_R, f = e / BK_R;
+    const int64_t ray = min(ray0 + r, n_rays - 1);
+    const float* d = dirs + ray * dir_stride;
+    float v;
+    if (f < 3) {
+      v = __ldg(d + f);
+    } else {
+      const int q = (f - 3) % 12, k = q / 3, c = q % 3;
+      float xb = mul(__ldg(d + c), (float)(1 << k));
+      if (f >= 15) xb = add(xb, 1.57079632679489661923f);
+      v = sinf(xb);
+    }
+    E[f * BK_PITCH + r] = v;
+  }
+  __syncthreads();
+  float acc[BK_R];
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+  dense_accum(acc, w + BK_K0, BK_IN, j, E);
+  store_relu(acc, __ldg(w + BK_B0 + j), X + j * BK_PITCH);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+  dense_accum(acc, w + BK_K1, BK_W, j, X);
+  store_relu(acc, __ldg(w + BK_B1 + j), Y + j * BK_PITCH);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+  dense_accum(acc, w + BK_K2, BK_W, j, Y);
+  __syncthreads();
+  store_relu(acc, __ldg(w + BK_B2 + j), X + j * BK_PITCH);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+  dense_accum(acc, w + BK_K3, BK_W, j, X);                       // rows 0..127: layer-2 output
+  dense_accum(acc, w + BK_K3 + BK_W * BK_W, BK_IN, j, E);        // rows 128..154: the skip-concatenated inputs
+  store_relu(acc, __ldg(w + BK_B3 + j), Y + j * BK_PITCH);
+  __syncthreads();
+  if (j < 3 * BK_R) {
+    const int r = j % BK_R, c = j / BK_R;
+    float o = 0.f;
+    for (int k = 0; k < BK_W; ++k) o = fmaf(Y[k * BK_PITCH + r], __ldg(w + BK_K4 + k * 3 + c), o);
+    o += __ldg(w + BK_B4 + c);
+    if (ray0 + r < n_rays) raw_out[(ray0 + r) * 3 + c] = o;
+  }
+}
+
+}  // namespace rnerf
+
+using namespace rnerf;
+
+extern "C" size_t rnerf_bkgd_weight_floats(void) { return (size_t)BK_TOTAL; }
+
+extern "C" int rnerf_bkgd_mlp_fwd(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
+                                  float* raw_out, void* stream) {
+  RNERF_REQUIRE(n_rays >= 0 && dir_stride_floats >= 3, RNERF_E_SHAPE, "rnerf_bkgd_mlp_fwd: bad sizes");
+  if (n_rays == 0) return 0;
+  RNERF_REQUIRE_PTR(w); RNERF_REQUIRE_PTR(dirs); RNERF_REQUIRE_PTR(raw_out);
+  bkgd_mlp_kernel<<<(unsigned)((n_rays + BK_R - 1) / BK_R), BK_W, 0, (cudaStream_t)stream>>>(w, dirs, n_rays,
+                                                                                            dir_stride_floats, raw_out);
+  count_launch();
+  return check_launch("rnerf_bkgd_mlp_fwd");
+}

@@ -1,0 +1,124 @@
+// IoR grid preparation and lookup: Gaussian prefilter (a1), (n, grad n) table (a2), trilinear lookup (a3).
+#include <math.h>
+#include "common.cuh"
+
+namespace rnerf {
+
+#define RNERF_MAX_BLUR_WS 11
+__constant__ float c_blur[RNERF_MAX_BLUR_WS * RNERF_MAX_BLUR_WS * RNERF_MAX_BLUR_WS];
+
+// conv3d_normal (rnerf/ior_utils.py:327-363): edge padding + 'VALID' correlation == clamp-to-edge taps.
+__global__ void __launch_bounds__(256) blur_kernel(const float* __restrict__ in, float* __restrict__ out, int gx, int gy,
+                                                   int gz, int ws) {
+  const int64_t total = (int64_t)gx * gy * gz;
+  const int hws = ws / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int z = (int)(i % gz);
+    int y = (int)((i / gz) % gy);
+    int x = (int)(i / ((int64_t)gz * gy));
+    float acc = 0.f;
+    int t = 0;
+    for (int a = 0; a < ws; ++a) {
+      int xx = min(max(x + a - hws, 0), gx - 1);
+      for (int b = 0; b < ws; ++b) {
+        int yy = min(max(y + b - hws, 0), gy - 1);
+        const float* row = in + ((int64_t)xx * gy + yy) * gz;
+        for (int c = 0; c < ws; ++c, ++t) {
+          int zz = min(max(z + c - hws, 0), gz - 1);
+          acc = fmaf(c_blur[t], __ldg(row + zz), acc);
+        }
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+// VoxMLP._compute_grad (rnerf/ior_utils.py:165-172): central differences on the edge-padded grid / (2*ndelta).
+__global__ void __launch_bounds__(256) table_kernel(const float* __restrict__ n, float4* __restrict__ table, GridGeom g) {
+  const int64_t total = (int64_t)g.gx * g.gy * g.gz;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int z = (int)(i % g.gz);
+    int y = (int)((i / g.gz) % g.gy);
+    int x = (int)(i / ((int64_t)g.gz * g.gy));
+    const int64_t sx = (int64_t)g.gy * g.gz, sy = g.gz;
+    int xm = max(x - 1, 0), xp = min(x + 1, g.gx - 1);
+    int ym = max(y - 1, 0), yp = min(y + 1, g.gy - 1);
+    int zm = max(z - 1, 0), zp = min(z + 1, g.gz - 1);
+    float dx = divf(sub(__ldg(n + sx * xp + sy * y + z), __ldg(n + sx * xm + sy * y + z)), g.two_ndelta[0]);
+    float dy = divf(sub(__ldg(n + sx * x + sy * yp + z), __ldg(n + sx * x + sy * ym + z)), g.two_ndelta[1]);
+    float dz = divf(sub(__ldg(n + sx * x + sy * y + zp), __ldg(n + sx * x + sy * y + zm)), g.two_ndelta[2]);
+    table[i] = make_float4(__ldg(n + i), dx, dy, dz);
+  }
+}
+
+__global__ void __launch_bounds__(256) lookup_kernel(const float4* __restrict__ table, GridGeom g,
+                                                     const float* __restrict__ pts, int64_t n_pts,
+                                                     float4* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  out[i] = trilinear(table, g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+}
+
+static int grid_blocks(int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = 148 * 32;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace rnerf
+
+using namespace rnerf;
+
+extern "C" int rnerf_grid_blur(const float* n_in, float* n_out, const int ndim[3], int ws, double sigma, void* stream) {
+  RNERF_REQUIRE_PTR(n_in); RNERF_REQUIRE_PTR(n_out); RNERF_REQUIRE_PTR(ndim);
+  RNERF_REQUIRE(ws >= 1 && ws <= RNERF_MAX_BLUR_WS && (ws & 1), RNERF_E_SHAPE, "rnerf_grid_blur: ws=%d unsupported (odd, <=%d)", ws,
+                RNERF_MAX_BLUR_WS);
+  RNERF_REQUIRE(n_in != n_out, RNERF_E_SHAPE, "rnerf_grid_blur: in-place blur is not supported");
+  // kernel weights in fp32 like the reference: linspace(-hws,hws,ws), exp(-(x^2+y^2+z^2)/(2 s^2)) / sum
+  static thread_local float k[RNERF_MAX_BLUR_WS * RNERF_MAX_BLUR_WS * RNERF_MAX_BLUR_WS];
+  const int hws = ws / 2;
+  const float two_s2 = (float)(2.0 * sigma * sigma);
+  float sum = 0.f;
+  int t = 0;
+  for (int a = 0; a < ws; ++a)
+    for (int b = 0; b < ws; ++b)
+      for (int c = 0; c < ws; ++c, ++t) {
+        float xa = (float)(a - hws), xb = (float)(b - hws), xc = (float)(c - hws);
+        k[t] = expf(-((xa * xa + xb * xb) + xc * xc) / two_s2);
+        sum += k[t];
+      }
+  for (int i = 0; i < t; ++i) k[i] = k[i] / sum;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_blur, k, sizeof(float) * t, 0, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { set_error("rnerf_grid_blur: %s", cudaGetErrorString(e)); return (int)e; }
+  const int64_t total = (int64_t)ndim[0] * ndim[1] * ndim[2];
+  blur_kernel<<<grid_blocks(total, 256), 256, 0, st>>>(n_in, n_out, ndim[0], ndim[1], ndim[2], ws);
+  count_launch();
+  return check_launch("rnerf_grid_blur");
+}
+
+extern "C" int rnerf_grid_table(const float* n, const int ndim[3], const double nmin[3], const double nmax[3],
+                                float* table, void* stream) {
+  RNERF_REQUIRE_PTR(n); RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
+  RNERF_REQUIRE(ndim[0] >= 2 && ndim[1] >= 2 && ndim[2] >= 2, RNERF_E_SHAPE, "rnerf_grid_table: ndim must be >= 2");
+  RNERF_REQUIRE(aligned16(table), RNERF_E_ALIGN, "rnerf_grid_table: table must be 16-byte aligned");
+  GridGeom g = make_geom(ndim, nmin, nmax);
+  const int64_t total = (int64_t)ndim[0] * ndim[1] * ndim[2];
+  table_kernel<<<grid_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(n, (float4*)table, g);
+  count_launch();
+  return check_launch("rnerf_grid_table");
+}
+
+extern "C" int rnerf_grid_lookup(const float* table, const int ndim[3], const double nmin[3], const double nmax[3],
+                                 const float* pts, int64_t n_pts, float* out, void* stream) {
+  RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
+  if (n_pts == 0) return 0;
+  RNERF_REQUIRE_PTR(pts); RNERF_REQUIRE_PTR(out);
+  RNERF_REQUIRE(n_pts > 0, RNERF_E_SHAPE, "rnerf_grid_lookup: n_pts < 0");
+  RNERF_REQUIRE(aligned16(table) && aligned16(out), RNERF_E_ALIGN, "rnerf_grid_lookup: table/out must be 16-byte aligned");
+  GridGeom g = make_geom(ndim, nmin, nmax);
+  lookup_kernel<<<(unsigned)((n_pts + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)table, g, pts, n_pts,
+                                                                                    (float4*)out);
+  count_launch();
+  return check_launch("rnerf_grid_lookup");
+}

@@ -1,0 +1,235 @@
+"""Thin torch-tensor wrappers over the C ABI (include/rnerf_b200.h).
+
+PyTorch owns the device buffers and the stream; every op below is one call into librnerf_b200.so.
+There is no alternative implementation: without the library (or a CUDA tensor) these raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Dbl3, Int3, check
+
+PATH_STRIDE = 12
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.RnerfError(f"{name}: expected a CUDA tensor (the rendering path has no CPU implementation)")
+    if t.dtype != dtype:
+        raise _lib.RnerfError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.RnerfError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _geom(ndim, nmin, nmax):
+    return Int3(*[int(v) for v in ndim]), Dbl3(*[float(v) for v in nmin]), Dbl3(*[float(v) for v in nmax])
+
+
+# ---------------------------------------------------------------- grid (a1, a2, a3)
+def grid_blur(n: torch.Tensor, ndim: Sequence[int], ws: int, sigma: float) -> torch.Tensor:
+    """conv3d_normal (rnerf/ior_utils.py:327-363).  n: [G^3] or [G^3,1] fp32 -> [G^3,1]."""
+    n = _chk(n.reshape(-1), "n")
+    out = torch.empty_like(n)
+    nd = Int3(*[int(v) for v in ndim])
+    check(_lib.load().rnerf_grid_blur(_p(n), _p(out), nd, int(ws), float(sigma), _stream()), "rnerf_grid_blur")
+    return out.reshape(-1, 1)
+
+
+def grid_table(n: torch.Tensor, ndim, nmin, nmax) -> torch.Tensor:
+    """VoxMLP.setup (rnerf/ior_utils.py:161): [G^3,4] = (n, grad n)."""
+    n = _chk(n.reshape(-1), "n")
+    table = torch.empty(n.numel(), 4, device=n.device, dtype=torch.float32)
+    nd, lo, hi = _geom(ndim, nmin, nmax)
+    check(_lib.load().rnerf_grid_table(_p(n), nd, lo, hi, _p(table), _stream()), "rnerf_grid_table")
+    return table
+
+
+def grid_lookup(table: torch.Tensor, ndim, nmin, nmax, pts: torch.Tensor) -> torch.Tensor:
+    """VoxMLP._linear3 (rnerf/ior_utils.py:188-223).  pts [N,3] -> [N,4]."""
+    _chk(table, "table"); pts = _chk(pts, "pts")
+    out = torch.empty(pts.shape[0], 4, device=pts.device, dtype=torch.float32)
+    nd, lo, hi = _geom(ndim, nmin, nmax)
+    check(_lib.load().rnerf_grid_lookup(_p(table), nd, lo, hi, _p(pts), pts.shape[0], _p(out), _stream()),
+          "rnerf_grid_lookup")
+    return out
+
+
+# ---------------------------------------------------------------- march (a5, a6) / select (a7)
+def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n_steps: int,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124), radiance stage.  Returns path [B,S,12]."""
+    _chk(table, "table"); origins = _chk(origins, "origins"); viewdirs = _chk(viewdirs, "viewdirs")
+    B = origins.shape[0]
+    if out is None:
+        out = torch.empty(B, n_steps, PATH_STRIDE, device=origins.device, dtype=torch.float32)
+    else:
+        _chk(out, "out")
+        assert out.shape == (B, n_steps, PATH_STRIDE)
+    nd, lo, hi = _geom(ndim, nmin, nmax)
+    check(_lib.load().rnerf_march_fwd(_p(table), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near), float(far),
+                                      int(n_steps), _p(out), _stream()), "rnerf_march_fwd")
+    return out
+
+
+def path_views(path: torch.Tensor):
+    """(ray_pos, ray_dir, ray_dist, idx_data, idx_grad) views of a path, as PathSampler returns them."""
+    return path[..., 0:3], path[..., 4:7], path[..., 3], path[..., 7:8], path[..., 8:11]
+
+
+def select(path: torch.Tensor, jitter: torch.Tensor, want_grad: bool = False):
+    """rnerf/models.py:243-247: gather the coarse samples at march-step indices `jitter` (int32 [Nc])."""
+    _chk(path, "path"); jitter = _chk(jitter, "jitter", torch.int32)
+    B, S, _ = path.shape
+    Nc = jitter.numel()
+    dev = path.device
+    pos = torch.empty(B, Nc, 3, device=dev); dirs = torch.empty(B, Nc, 3, device=dev); t = torch.empty(B, Nc, device=dev)
+    grad = torch.empty(B, Nc, 3, device=dev) if want_grad else None
+    check(_lib.load().rnerf_select(_p(path), B, S, _p(jitter), Nc, _p(pos), _p(dirs), _p(t), _p(grad), _stream()),
+          "rnerf_select")
+    return pos, dirs, t, grad
+
+
+# ---------------------------------------------------------------- encoding-fused radiance MLP (a8, a9)
+def nerf_mlp_layer_list(p: Dict) -> Tuple[list, list]:
+    ks, bs = [], []
+    for i in range(12):
+        d = p[f"Dense_{i}"]
+        ks.append(_chk(d["kernel"], f"Dense_{i}.kernel")); bs.append(_chk(d["bias"], f"Dense_{i}.bias"))
+    expect = [(63, 256)] + [(256, 256)] * 4 + [(319, 256)] + [(256, 256)] * 2 + [(256, 1), (256, 256), (283, 128), (128, 3)]
+    for i, (k, e) in enumerate(zip(ks, expect)):
+        if tuple(k.shape) != e:
+            raise _lib.RnerfError(f"Dense_{i}.kernel has shape {tuple(k.shape)}, the sm_100a kernel is built for {e} "
+                                  "(net_depth=8, net_width=256, skip_layer=4, condition 1x128, deg 10/4)")
+    return ks, bs
+
+
+def encmlp_pack(p: Dict, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pack the 12 Flax Dense layers of a NerfMLP into the pre-swizzled bf16 image the kernel streams."""
+    ks, bs = nerf_mlp_layer_list(p)
+    lib = _lib.load()
+    nbytes = lib.rnerf_encmlp_packed_bytes()
+    if out is None:
+        out = torch.empty(nbytes, device=ks[0].device, dtype=torch.uint8)
+    kp = (C.c_void_p * 12)(*[k.data_ptr() for k in ks])
+    bp = (C.c_void_p * 12)(*[b.data_ptr() for b in bs])
+    check(lib.rnerf_encmlp_pack(kp, bp, _p(out), _stream()), "rnerf_encmlp_pack")
+    return out
+
+
+def encmlp_fwd(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tensor, debug_layers: bool = False):
+    """pos_enc + NerfMLP.  pos/dirs [M,3] (or [B,Ns,3]) -> raw [M,4] = (raw_rgb, raw_sigma)."""
+    _chk(packed, "packed", torch.uint8)
+    pos = _chk(pos, "pos").reshape(-1, 3); dirs = _chk(dirs, "dirs").reshape(-1, 3)
+    M = pos.shape[0]
+    raw = torch.empty(M, 4, device=pos.device, dtype=torch.float32)
+    lib = _lib.load()
+    if debug_layers:
+        layers = torch.zeros(10, M, 256, device=pos.device, dtype=torch.bfloat16)
+        check(lib.rnerf_encmlp_fwd_debug(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(layers), _stream()),
+              "rnerf_encmlp_fwd_debug")
+        return raw, layers
+    check(lib.rnerf_encmlp_fwd(_p(packed), _p(pos), _p(dirs), M, _p(raw), _stream()), "rnerf_encmlp_fwd")
+    return raw
+
+
+# ---------------------------------------------------------------- background MLP (a10)
+def bkgd_pack(p: Dict) -> torch.Tensor:
+    ks = [_chk(p[f"Dense_{i}"]["kernel"], f"bkgd Dense_{i}.kernel") for i in range(5)]
+    bs = [_chk(p[f"Dense_{i}"]["bias"], f"bkgd Dense_{i}.bias") for i in range(5)]
+    expect = [(27, 128), (128, 128), (128, 128), (155, 128), (128, 3)]
+    for i, (k, e) in enumerate(zip(ks, expect)):
+        if tuple(k.shape) != e:
+            raise _lib.RnerfError(f"bkgd Dense_{i}.kernel has shape {tuple(k.shape)}, expected {e}")
+    w = torch.cat([k.reshape(-1) for k in ks] + [b.reshape(-1) for b in bs]).contiguous()
+    assert w.numel() == _lib.load().rnerf_bkgd_weight_floats()
+    return w
+
+
+def bkgd_mlp_fwd(w: torch.Tensor, dirs: torch.Tensor, n_rays: int, stride_floats: int = 3, offset_floats: int = 0):
+    """bkgd_mlp(pos_enc(dir)) -> raw [B,3].  `dirs` may be a larger array read with a ray stride (e.g. the
+    last coarse sample of a [B,Nc,3] array: offset (Nc-1)*3, stride Nc*3)."""
+    _chk(w, "w"); _chk(dirs, "dirs")
+    out = torch.empty(n_rays, 3, device=dirs.device, dtype=torch.float32)
+    ptr = C.c_void_p(dirs.data_ptr() + 4 * offset_floats)
+    check(_lib.load().rnerf_bkgd_mlp_fwd(_p(w), ptr, n_rays, stride_floats, _p(out), _stream()), "rnerf_bkgd_mlp_fwd")
+    return out
+
+
+# ---------------------------------------------------------------- compositing (a11, a12)
+def composite_fwd(raw, t, dirs, bkgd_raw=None, mask=None, white_bkgd=False, rgb_padding=0.001, sigma_bias=-1.0,
+                  want_weights=True, want_alpha=False):
+    """activations + volumetric_rendering (rnerf/models.py:334-349, rnerf/model_utils.py:247-309).
+    raw [B,Ns,4], t [B,Ns], dirs [B,Ns,3] -> dict(comp_rgb, distance, acc, weights, alpha, trans, trans_rgb_bkgd)."""
+    raw = _chk(raw, "raw"); t = _chk(t, "t"); dirs = _chk(dirs, "dirs")
+    B, Ns = t.shape
+    dev = t.device
+    o = {"comp_rgb": torch.empty(B, 3, device=dev), "distance": torch.empty(B, device=dev),
+         "acc": torch.empty(B, device=dev), "trans": torch.empty(B, 1, device=dev),
+         "trans_rgb_bkgd": torch.empty(B, 3, device=dev),
+         "weights": torch.empty(B, Ns, device=dev) if want_weights else None,
+         "alpha": torch.empty(B, Ns, device=dev) if want_alpha else None}
+    if bkgd_raw is not None:
+        _chk(bkgd_raw, "bkgd_raw")
+    if mask is not None:
+        _chk(mask, "mask")
+    check(_lib.load().rnerf_composite_fwd(_p(raw), _p(t), _p(dirs), _p(bkgd_raw), _p(mask), B, Ns, int(white_bkgd),
+                                          float(rgb_padding), float(sigma_bias), _p(o["comp_rgb"]), _p(o["distance"]),
+                                          _p(o["acc"]), _p(o["weights"]), _p(o["alpha"]), _p(o["trans"]),
+                                          _p(o["trans_rgb_bkgd"]), _stream()), "rnerf_composite_fwd")
+    return o
+
+
+def composite_bwd(raw, t, dirs, bkgd_raw, mask, d_comp_rgb, d_trans, d_trb, white_bkgd=False, rgb_padding=0.001,
+                  sigma_bias=-1.0):
+    raw = _chk(raw, "raw"); t = _chk(t, "t"); dirs = _chk(dirs, "dirs")
+    B, Ns = t.shape
+    d_raw = torch.empty(B, Ns, 4, device=t.device)
+    d_bk = torch.empty(B, 3, device=t.device) if bkgd_raw is not None else None
+    for nm, x in (("d_comp_rgb", d_comp_rgb), ("d_trans", d_trans), ("d_trb", d_trb)):
+        if x is not None:
+            _chk(x, nm)
+    check(_lib.load().rnerf_composite_bwd(_p(raw), _p(t), _p(dirs), _p(bkgd_raw), _p(mask), B, Ns, int(white_bkgd),
+                                          float(rgb_padding), float(sigma_bias), _p(d_comp_rgb), _p(d_trans), _p(d_trb),
+                                          _p(d_raw), _p(d_bk), _stream()), "rnerf_composite_bwd")
+    return d_raw, d_bk
+
+
+# ---------------------------------------------------------------- resampling (a13, a14)
+def resample(path, t_c, weights_c, u, n_fine: int, want_grad: bool = False):
+    """sorted_piecewise_constant_pdf + sample_pdf (rnerf/model_utils.py:312-435).
+    u: [Nf] (shared) or [B,Nf] sorted CDF positions.  Returns t_f [B,Nc+Nf], pos_f, dir_f, grad_f."""
+    _chk(path, "path"); t_c = _chk(t_c, "t_c"); weights_c = _chk(weights_c, "weights_c"); u = _chk(u, "u")
+    B, S, _ = path.shape
+    Nc = t_c.shape[1]
+    per_ray = 1 if u.dim() == 2 else 0
+    assert u.shape[-1] == n_fine and (not per_ray or u.shape[0] == B)
+    Nt = Nc + n_fine
+    dev = path.device
+    t_f = torch.empty(B, Nt, device=dev); pos_f = torch.empty(B, Nt, 3, device=dev); dir_f = torch.empty(B, Nt, 3, device=dev)
+    grad_f = torch.empty(B, Nt, 3, device=dev) if want_grad else None
+    check(_lib.load().rnerf_resample(_p(path), B, S, _p(t_c), _p(weights_c), Nc, _p(u), per_ray, n_fine, _p(t_f),
+                                     _p(pos_f), _p(dir_f), _p(grad_f), _stream()), "rnerf_resample")
+    return t_f, pos_f, dir_f, grad_f
+
+
+def bbox_tail_mask(pos: torch.Tensor, lo, hi):
+    """rnerf/models.py:498-503: mask = reverse-cumsum(inside bbox) > 0; returns (mask, 1 - mask) [B,Ns]."""
+    pos = _chk(pos, "pos")
+    B, Ns, _ = pos.shape
+    m = torch.empty(B, Ns, device=pos.device); im = torch.empty(B, Ns, device=pos.device)
+    check(_lib.load().rnerf_bbox_tail_mask(_p(pos), B, Ns, Dbl3(*[float(v) for v in lo]), Dbl3(*[float(v) for v in hi]),
+                                           _p(m), _p(im), _stream()), "rnerf_bbox_tail_mask")
+    return m, im

@@ -1,0 +1,208 @@
+"""Per-kernel parity: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rnerf_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scene(cuda_lib):
+    n, ndim, nmin, nmax = H.sphere_grid(G=40, ws=3, sigma=1.0)
+    table = O.build_table(n, ndim, nmin, nmax)
+    return {"n": n, "ndim": ndim, "nmin": nmin, "nmax": nmax, "table": table, "table_cu": table.cuda().contiguous()}
+
+
+def test_grid_table_bit_exact(cuda_lib, scene):
+    from samplenerfro_b200 import ops
+    t = ops.grid_table(scene["n"].cuda(), scene["ndim"], scene["nmin"], scene["nmax"]).cpu()
+    assert torch.equal(t, scene["table"]), f"max abs diff {(t - scene['table']).abs().max()}"
+
+
+@pytest.mark.parametrize("ws,sigma", [(3, 1.0), (5, 3.0), (9, 3.0)])
+def test_grid_blur(cuda_lib, ws, sigma):
+    from samplenerfro_b200 import ops
+    G = 24
+    n0, ndim, _, _ = H.sphere_grid(G=G, ws=0)
+    ref = O.conv3d_normal(n0, ndim, ws, sigma)
+    out = ops.grid_blur(n0.cuda(), ndim, ws, sigma).cpu()
+    assert (out - ref).abs().max().item() < 2e-6   # same taps, different fp32 summation order
+
+
+def test_lookup_bit_exact(cuda_lib, scene):
+    from samplenerfro_b200 import ops
+    gen = torch.Generator().manual_seed(1)
+    pts = (torch.rand(5001, 3, generator=gen) * 2 - 1) * 1.9   # includes points outside the box (clamp-to-edge)
+    pts[:8] = torch.tensor(scene["nmin"]) + torch.arange(8)[:, None] * 0.0769231  # voxel corners / edges
+    ref = O.linear3(scene["table"], scene["ndim"], scene["nmin"], scene["nmax"], pts)
+    out = ops.grid_lookup(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], pts.cuda()).cpu()
+    assert torch.equal(out, ref), f"max abs diff {(out - ref).abs().max()}"
+
+
+@pytest.mark.parametrize("B,S,near,far", [(1000, 96, 2.0, 6.0), (257, 768, 2.0, 6.0), (33, 1536, 0.2, 12.0), (1, 7, 2.0, 6.0)])
+def test_march_bit_exact(cuda_lib, scene, B, S, near, far):
+    """Bent sample positions: north_star asks 1e-4 relative; the kernel reproduces the fp32 oracle bit for bit."""
+    from samplenerfro_b200 import ops
+    o, d = H.random_rays(B, seed=B)
+    pos, dirs, dist, n, g = O.march(scene["table"], scene["ndim"], scene["nmin"], scene["nmax"], o, d, near, far, S)
+    path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), near, far, S).cpu()
+    rp, rd, rt, idn, idg = ops.path_views(path)
+    bent = (dirs[:, -1] - d).abs().max().item()
+    assert B < 100 or bent > 1e-3, "test scene does not bend any ray"
+    for name, a, b in (("ray_pos", rp, pos), ("ray_dir", rd, dirs), ("ray_dist", rt, dist), ("idx_data", idn, n),
+                       ("idx_grad", idg, g)):
+        assert torch.equal(a, b), f"{name}: max rel diff {H.rel_err(a, b):.3e}"
+
+
+def test_march_constant_grid_kat(cuda_lib):
+    """n == n0 -> straight ray, p_k = o + near d + k (step/n0) d, direction unchanged."""
+    from samplenerfro_b200 import ops
+    G, n0, S = 8, 1.25, 64
+    ndim, nmin, nmax = [G] * 3, [-1.0] * 3, [1.0] * 3
+    table = ops.grid_table(torch.full((G ** 3,), n0, device="cuda"), ndim, nmin, nmax)
+    o, d = H.random_rays(64, seed=3)
+    path = ops.march(table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, S).cpu().double()
+    step = 4.0 / (S - 1)
+    k = torch.arange(S, dtype=torch.float64)[None, :, None]
+    expect = o.double()[:, None] + 2.0 * d.double()[:, None] + k * (step / n0) * d.double()[:, None]
+    assert (path[..., 0:3] - expect).abs().max().item() < 2e-5
+    assert (path[..., 3] - (2.0 + k[..., 0] * step / n0)).abs().max().item() < 2e-5
+    assert (path[..., 4:7] - d.double()[:, None]).abs().max().item() < 1e-6
+    assert (path[..., 7] - n0).abs().max().item() < 1e-6 and path[..., 8:11].abs().max().item() == 0.0
+
+
+def test_select(cuda_lib, scene):
+    from samplenerfro_b200 import ops
+    o, d = H.random_rays(100, seed=5)
+    path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), 2.0, 6.0, 96)
+    jit = (torch.arange(0, 96, 12) + torch.randint(0, 12, (8,), generator=torch.Generator().manual_seed(0))).int()
+    pos, dirs, t, grad = ops.select(path, jit.cuda(), want_grad=True)
+    pc = path.cpu()
+    assert torch.equal(pos.cpu(), pc[:, jit.long(), 0:3]) and torch.equal(dirs.cpu(), pc[:, jit.long(), 4:7])
+    assert torch.equal(t.cpu(), pc[:, jit.long(), 3]) and torch.equal(grad.cpu(), pc[:, jit.long(), 8:11])
+
+
+def _composite_inputs(B, Ns, seed):
+    gen = torch.Generator().manual_seed(seed)
+    raw = torch.randn(B, Ns, 4, generator=gen) * 2
+    raw[..., 3] = raw[..., 3] * 3 + 1
+    t = 2 + torch.sort(torch.rand(B, Ns, generator=gen) * 4, dim=-1).values
+    dirs = torch.randn(B, Ns, 3, generator=gen)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    bk = torch.randn(B, 3, generator=gen)
+    return raw, t, dirs, bk
+
+
+@pytest.mark.parametrize("B,Ns,use_mask,use_bkgd", [(301, 64, False, True), (77, 192, True, True), (5, 50, False, False),
+                                                     (16, 1, False, True)])
+def test_composite_fwd(cuda_lib, B, Ns, use_mask, use_bkgd):
+    from samplenerfro_b200 import ops
+    raw, t, dirs, bk = _composite_inputs(B, Ns, B + Ns)
+    raw[0, :, 3] = -60.0   # sigma == 0 -> acc == 0 -> distance NaN -> 0 -> clipped to t_0 (T12)
+    mask = (torch.rand(B, Ns, generator=torch.Generator().manual_seed(9)) > 0.3).float() if use_mask else None
+    ref = O.volumetric_rendering(O.rgb_act(raw[..., :3]), O.sigma_act(raw[..., 3:4]), t, dirs, False,
+                                 O.rgb_act(bk) if use_bkgd else None, mask)
+    o = ops.composite_fwd(raw.cuda(), t.cuda(), dirs.cuda(), bk.cuda() if use_bkgd else None,
+                          mask.cuda() if use_mask else None, want_alpha=True)
+    names = ["comp_rgb", "distance", "acc", "weights", "alpha", "trans", "trans_rgb_bkgd"]
+    for nm, r in zip(names, ref):
+        got = o[nm].cpu()
+        assert (got - r).abs().max().item() < 3e-6 * max(1.0, r.abs().max().item()), (nm, (got - r).abs().max().item())
+    assert o["distance"][0].item() == t[0, 0].item()
+    assert (o["acc"].cpu() + o["trans"].cpu()[:, 0] - 1).abs().max().item() < 1e-5  # acc + T_end == 1 (telescoping)
+
+
+@pytest.mark.parametrize("B,Ns,use_mask", [(64, 64, False), (33, 192, True)])
+def test_composite_bwd(cuda_lib, B, Ns, use_mask):
+    from samplenerfro_b200 import ops
+    raw, t, dirs, bk = _composite_inputs(B, Ns, 100 + Ns)
+    gen = torch.Generator().manual_seed(2)
+    mask = (torch.rand(B, Ns, generator=gen) > 0.3).float() if use_mask else None
+    g_rgb, g_tr, g_trb = torch.randn(B, 3, generator=gen), torch.randn(B, 1, generator=gen), torch.randn(B, 3, generator=gen)
+    raw64 = raw.double().requires_grad_(True); bk64 = bk.double().requires_grad_(True)
+    ref = O.volumetric_rendering(O.rgb_act(raw64[..., :3]), O.sigma_act(raw64[..., 3:4]), t.double(), dirs.double(),
+                                 False, O.rgb_act(bk64), mask.double() if use_mask else None)
+    loss = (ref[0] * g_rgb.double()).sum() + (ref[5] * g_tr.double()).sum() + (ref[6] * g_trb.double()).sum()
+    loss.backward()
+    d_raw, d_bk = ops.composite_bwd(raw.cuda(), t.cuda(), dirs.cuda(), bk.cuda(), mask.cuda() if use_mask else None,
+                                    g_rgb.cuda(), g_tr.reshape(-1).contiguous().cuda(), g_trb.cuda())
+    assert H.rel_err(d_raw, raw64.grad) < 2e-5, H.rel_err(d_raw, raw64.grad)
+    assert H.rel_err(d_bk, bk64.grad) < 2e-5, H.rel_err(d_bk, bk64.grad)
+
+
+@pytest.mark.parametrize("B,randomized", [(200, False), (129, True)])
+def test_resample(cuda_lib, scene, B, randomized):
+    from samplenerfro_b200 import ops
+    S, Nc, P, Nf = 768, 64, 12, 128
+    o, d = H.random_rays(B, seed=11)
+    path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), 2.0, 6.0, S)
+    gen = torch.Generator().manual_seed(4)
+    jit = torch.arange(0, S, P) + torch.randint(0, P, (Nc,), generator=gen)
+    w = torch.rand(B, Nc, generator=gen) ** 4
+    w[0] = 0.0            # all-zero weights -> eps padding branch
+    w[1, 10:] = 0.0       # cdf plateau at 1
+    rp, rd, rt, _, rg = [x.contiguous() for x in ops.path_views(path.cpu())]
+    t_c = rt[:, jit]
+    if randomized:
+        u = O.stratified_u(torch.rand(B, Nf, generator=gen) * (1 / Nf - float(np.finfo(np.float32).eps)))
+    else:
+        u = O.deterministic_u(Nf)
+    t_mid = 0.5 * (t_c[..., 1:] + t_c[..., :-1])
+    z, pos, dirs, grads = O.sample_pdf(t_mid, w[..., 1:-1], rp, rd, rt, rg, u, jit)
+    t_f, pos_f, dir_f, grad_f = ops.resample(path, t_c.cuda().contiguous(), w.cuda(), u.cuda(), Nf, want_grad=True)
+    assert (t_f.cpu() - z).abs().max().item() < 4e-6, (t_f.cpu() - z).abs().max().item()
+    # march-step choice is discontinuous in z: compare rows where both picked the same step (all but a few ulp-ties)
+    same = (dir_f.cpu() == dirs).all(dim=-1)
+    assert same.float().mean().item() > 0.999, same.float().mean().item()
+    assert (pos_f.cpu() - pos)[same].abs().max().item() < 1e-5
+    assert torch.equal(grad_f.cpu()[same], grads[same])
+    assert (pos_f.cpu() - pos).abs().max().item() < 1e-4   # even at a tie the extrapolated point is continuous
+
+
+def test_bkgd_mlp(cuda_lib):
+    from samplenerfro_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    p = O.init_small_mlp(gen, bias_scale=0.1)
+    B, Nc = 1000, 4
+    d = torch.randn(B, Nc, 3, generator=gen)
+    d = d / d.norm(dim=-1, keepdim=True)
+    ref = O.small_mlp(p, O.pos_enc(d[:, -1:], 0, 4))[:, 0]
+    w = ops.bkgd_pack(H.to_cuda_params(p))
+    out = ops.bkgd_mlp_fwd(w, d.cuda().contiguous(), B, stride_floats=Nc * 3, offset_floats=(Nc - 1) * 3).cpu()
+    assert (out - ref).abs().max().item() < 2e-5, (out - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("M", [128, 1000, 148 * 128 + 77, 60000])
+def test_encmlp_vs_bf16_oracle(cuda_lib, M):
+    """Per-layer outputs vs an oracle that rounds operands to bf16 at the same points (fp32 accumulate).
+    Stated bf16 tolerance: 2 bf16 ulps (2^-7 relative to the layer's max magnitude) per layer output."""
+    from samplenerfro_b200 import ops
+    gen = torch.Generator().manual_seed(M)
+    p = O.init_nerf_mlp(gen, bias_scale=0.1)
+    pos = (torch.rand(M, 3, generator=gen) * 2 - 1) * 3.0
+    dirs = torch.randn(M, 3, generator=gen)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    packed = ops.encmlp_pack(H.to_cuda_params(p))
+    raw, layers = ops.encmlp_fwd(packed, pos.cuda(), dirs.cuda(), debug_layers=True)
+    torch.cuda.synchronize()
+    raw2 = ops.encmlp_fwd(packed, pos.cuda(), dirs.cuda())
+    assert torch.equal(raw, raw2), "debug and production launches disagree"
+    n_chk = min(M, 4096)
+    sel = torch.randperm(M, generator=gen)[:n_chk]
+    rgb_ref, sig_ref, lay_ref = O.nerf_mlp(p, O.pos_enc(pos[sel][:, None], 0, 10), O.pos_enc(dirs[sel][:, None], 0, 4),
+                                           emulate_bf16=True, return_layers=True)
+    layers = layers.float().cpu()
+    for li, ref in enumerate(lay_ref):
+        got = layers[li, sel, :ref.shape[1]]
+        tol = 2.0 ** -7 * ref.abs().max().item()
+        assert (got - ref).abs().max().item() <= tol, (li, (got - ref).abs().max().item(), tol)
+    ref = torch.cat([rgb_ref[:, 0], sig_ref[:, 0]], dim=-1)
+    err = (raw.cpu()[sel] - ref).abs().max().item()
+    assert err < 2.0 ** -7 * ref.abs().max().item(), err
+    # and against the true fp32 MLP: bf16 compute stays within ~1 % of the output scale
+    rgb32, sig32 = O.nerf_mlp(p, O.pos_enc(pos[sel][:, None], 0, 10), O.pos_enc(dirs[sel][:, None], 0, 4))
+    ref32 = torch.cat([rgb32[:, 0], sig32[:, 0]], dim=-1)
+    assert (raw.cpu()[sel] - ref32).abs().max().item() < 0.03 * ref32.abs().max().item()
