@@ -148,12 +148,20 @@ def linear3(table: torch.Tensor, ndim, nmin, nmax, pts: torch.Tensor) -> torch.T
 # ----------------------------------------------------------------------------------------------
 # math helpers  (rnerf/math_utils.py:6-20)
 # ----------------------------------------------------------------------------------------------
+def _sqrt(x: torch.Tensor) -> torch.Tensor:
+    """Correctly rounded sqrt.  torch's CPU fp32 sqrt (MKL VML) is off by one ulp in ~0.7 % of cases; XLA's CPU
+    sqrt and CUDA's sqrt.rn.f32 are IEEE, so the oracle takes the fp64 root and rounds once."""
+    if x.dtype == torch.float32:
+        return torch.sqrt(x.double()).to(torch.float32)
+    return torch.sqrt(x)
+
+
 def sumsq3(x: torch.Tensor) -> torch.Tensor:
     return (x[..., 0:1] * x[..., 0:1] + x[..., 1:2] * x[..., 1:2]) + x[..., 2:3] * x[..., 2:3]
 
 
 def safe_l2_norm(x, eps=1e-6):
-    return torch.sqrt(torch.maximum(sumsq3(x), _c(eps, x.dtype)))
+    return _sqrt(torch.maximum(sumsq3(x), _c(eps, x.dtype)))
 
 
 def safe_l2_normalize(x, eps=1e-6):
@@ -352,13 +360,13 @@ def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n
         if stage.startswith("all"):
             raw = small_mlp(so3_params, annealed_pos_enc(rp[:, None], 0, 10, annealed_alpha * 10))[:, 0]
             pred = rodrigues_grad(raw, g)
-            gn = torch.sqrt(sumsq3(g))
+            gn = _sqrt(sumsq3(g))
             g_used = torch.where(gn > 1e-3, pred, g)
         else:
             g_used = g
         nrp = rp + step / n * rd
         nrd = rd + step * g_used
-        rt = rt + torch.sqrt(sumsq3(rp - nrp))
+        rt = rt + _sqrt(sumsq3(rp - nrp))
         rp, rd = nrp, nrd
     return pos, safe_l2_normalize(dirs), dist, idx_data, idx_grad
 
@@ -370,7 +378,7 @@ def volumetric_rendering(rgb, density, t_vals, dirs, white_bkgd, rgb_bkgd, mask_
     dt = rgb.dtype
     t_dists = torch.cat([t_vals[..., 1:] - t_vals[..., :-1],
                          torch.full_like(t_vals[..., :1], 1e-3)], -1)
-    delta = t_dists * torch.sqrt(sumsq3(dirs))[..., 0]
+    delta = t_dists * _sqrt(sumsq3(dirs))[..., 0]
     density_delta = density[..., 0] * delta
     if mask_bbox is not None:
         density_delta = density_delta * mask_bbox.to(dt)
@@ -559,7 +567,7 @@ def nerf_model_apply(variables: Dict, table: torch.Tensor, cfg: ModelCfg, rays: 
         rgb, sigma, t_c, dir_c, cfg.white_bkgd, bkgd, bbox_mask(pos_c))
     loss_sp = torch.zeros((), dtype=dt)
     if cfg.use_online_sparsity:
-        m = (torch.sqrt(sumsq3(grad_c))[..., 0] > 1e-6).to(dt)
+        m = (_sqrt(sumsq3(grad_c))[..., 0] > 1e-6).to(dt)
         loss_sp = (m * safe_log(alpha)).sum() / (m.sum() + 1)
     ret = [(comp_rgb, dist, acc, trans, trans_rgb_bkgd)]
     dbg = {"ray_pos": ray_pos, "ray_dir": ray_dir, "ray_dist": ray_dist, "idx_data": idx_data,
@@ -585,7 +593,7 @@ def nerf_model_apply(variables: Dict, table: torch.Tensor, cfg: ModelCfg, rays: 
             trb = volumetric_rendering(rgb, sigma, t_f, dir_f, cfg.white_bkgd, bkgd, 1.0 - m)[0]
             trans_rgb_bkgd = trans * trb
         if cfg.use_online_sparsity and cfg.use_fine_sparsity:
-            m = (torch.sqrt(sumsq3(grad_f))[..., 0] > 1e-6).to(dt)
+            m = (_sqrt(sumsq3(grad_f))[..., 0] > 1e-6).to(dt)
             loss_sp = loss_sp + (m * safe_log(alpha)).sum() / (m.sum() + 1)
         ret.append((comp_rgb, dist, acc, trans, trans_rgb_bkgd))
         dbg.update({"t_f": t_f, "pos_f": pos_f, "dir_f": dir_f, "grad_f": grad_f, "raw_rgb_f": raw_rgb,

@@ -1,0 +1,124 @@
+"""Autograd boundary: one torch.autograd.Function per CUDA stage.  PyTorch only records the graph between
+the stages; every forward and backward body is a call into librnerf_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+
+def _mlp_param_list(p: Dict, n: int):
+    out = []
+    for i in range(n):
+        out += [p[f"Dense_{i}"]["kernel"], p[f"Dense_{i}"]["bias"]]
+    return out
+
+
+def _needs_grad(p: Dict) -> bool:
+    return torch.is_grad_enabled() and any(t.requires_grad for d in p.values() for t in d.values())
+
+
+# ----------------------------------------------------------------------------- radiance MLP (a8 + a9)
+class _RadianceMLP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, name, packed, pos, dirs, *params):
+        M = pos.shape[0] * pos.shape[1]
+        raw, saved = ops.encmlp_fwd_train(packed, pos, dirs)
+        ctx.model, ctx.name, ctx.shape = model, name, pos.shape
+        ctx.save_for_backward(packed, pos, dirs, saved, *params)
+        return raw.view(pos.shape[0], pos.shape[1], 4)
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        packed, pos, dirs, saved, *params = ctx.saved_tensors
+        grads = ops.encmlp_bwd(packed, pos, dirs, saved, d_raw.contiguous().view(-1, 4), params)
+        return (None, None, None, None, None, *grads)
+
+
+def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
+    """pos_enc + NerfMLP on [B,Ns,3] positions / per-sample directions -> raw [B,Ns,4]."""
+    p = variables["params"][name]
+    packed = model._packed(variables, name)
+    if _needs_grad(p):
+        return _RadianceMLP.apply(model, name, packed, pos, dirs, *_mlp_param_list(p, 12))
+    with torch.no_grad():
+        return ops.encmlp_fwd(packed, pos, dirs).view(pos.shape[0], pos.shape[1], 4)
+
+
+# ----------------------------------------------------------------------------- background MLP (a10)
+class _BkgdMLP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, dirs, n_rays, stride, offset, *params):
+        ctx.geom = (n_rays, stride, offset)
+        ctx.save_for_backward(w, dirs, *params)
+        return ops.bkgd_mlp_fwd(w, dirs, n_rays, stride, offset)
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        w, dirs, *params = ctx.saved_tensors
+        n_rays, stride, offset = ctx.geom
+        grads = ops.bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw.contiguous(), params)
+        return (None, None, None, None, None, *grads)
+
+
+def bkgd_raw(model, variables: Dict, dir_c: torch.Tensor, n_rays: int, n_coarse: int) -> torch.Tensor:
+    """raw_bkgd = bkgd_mlp(pos_enc(ray_dir_c[:, -1])) (rnerf/models.py:303)."""
+    p = variables["params"]["bkgd_mlp"]
+    w = model._packed(variables, "bkgd_mlp")
+    stride, offset = n_coarse * 3, (n_coarse - 1) * 3
+    if _needs_grad(p):
+        return _BkgdMLP.apply(w, dir_c, n_rays, stride, offset, *_mlp_param_list(p, 5))
+    with torch.no_grad():
+        return ops.bkgd_mlp_fwd(w, dir_c, n_rays, stride, offset)
+
+
+def bkgd_color(model, variables: Dict, viewdirs: torch.Tensor) -> torch.Tensor:
+    """NerfModel.forward_envmap (rnerf/models.py:181-191): widened sigmoid of bkgd_mlp(pos_enc(dir))."""
+    p = variables["params"]["bkgd_mlp"]
+    w = model._packed(variables, "bkgd_mlp")
+    n = viewdirs.shape[0]
+    if _needs_grad(p):
+        raw = _BkgdMLP.apply(w, viewdirs, n, 3, 0, *_mlp_param_list(p, 5))
+    else:
+        with torch.no_grad():
+            raw = ops.bkgd_mlp_fwd(w, viewdirs, n, 3, 0)
+    return torch.sigmoid(raw) * (1 + 2 * model.rgb_padding) - model.rgb_padding
+
+
+# ----------------------------------------------------------------------------- compositing (a11 + a12)
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias):
+        o = ops.composite_fwd(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias, want_weights=True)
+        ctx.cfg = (white_bkgd, rgb_padding, sigma_bias, bkgd_raw is not None, mask is not None)
+        ctx.save_for_backward(raw, t, dirs, bkgd_raw if bkgd_raw is not None else raw.new_empty(0),
+                              mask if mask is not None else raw.new_empty(0))
+        outs = (o["comp_rgb"], o["distance"], o["acc"], o["weights"], o["trans"], o["trans_rgb_bkgd"])
+        ctx.mark_non_differentiable(o["distance"], o["acc"], o["weights"])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_rgb, _d_dist, _d_acc, _d_w, d_trans, d_trb):
+        raw, t, dirs, bk, mask = ctx.saved_tensors
+        white_bkgd, rgb_padding, sigma_bias, has_bk, has_mask = ctx.cfg
+        d_raw, d_bk = ops.composite_bwd(raw, t, dirs, bk if has_bk else None, mask if has_mask else None,
+                                        None if d_rgb is None else d_rgb.contiguous(),
+                                        None if d_trans is None else d_trans.contiguous().view(-1),
+                                        None if d_trb is None else d_trb.contiguous(),
+                                        white_bkgd, rgb_padding, sigma_bias)
+        return d_raw, None, None, (d_bk if has_bk else None), None, None, None, None
+
+
+def composite(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias, want_weights=True, want_alpha=False):
+    """activations + volumetric_rendering -> dict.  Differentiable wrt raw / bkgd_raw through comp_rgb, trans and
+    trans_rgb_bkgd (the outputs train.py's loss reads); distance / acc / weights are not differentiated."""
+    if torch.is_grad_enabled() and (raw.requires_grad or (bkgd_raw is not None and bkgd_raw.requires_grad)):
+        rgb, dist, acc, w, trans, trb = _Composite.apply(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias)
+        return {"comp_rgb": rgb, "distance": dist, "acc": acc, "weights": w, "alpha": None, "trans": trans,
+                "trans_rgb_bkgd": trb}
+    with torch.no_grad():
+        return ops.composite_fwd(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias,
+                                 want_weights=want_weights, want_alpha=want_alpha)

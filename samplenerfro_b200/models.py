@@ -1,0 +1,274 @@
+"""Host-side mirror of rnerf/models.py for the refractive rendering path.
+
+`construct_nerf(key, example_batch, args, ndim, nmin, nmax, grid) -> (model, variables)` and
+`model.apply(variables, key_0, key_1, rays, randomized[, annealed_alpha]) -> (ret, loss_sp)` keep the
+reference's signatures (rnerf/models.py:219,538); everything between the ray batch and the returned
+`ret = [(rgb, distance, acc, trans, trans_rgb_bkgd)_coarse, (...)_fine]` runs in hand-written sm_100a kernels
+reached through the C ABI (`ops`).  PyTorch holds the tensors and, for training, the autograd graph
+boundary (`autograd.py`).
+
+Differences from the reference that a caller can see:
+  * PRNG keys are plain integers (or None); the stochastic inputs they produce -- the coarse-sample jitter
+    (rnerf/models.py:240-242) and the stratified CDF positions (rnerf/model_utils.py:343-352) -- can also be
+    passed explicitly as `jitter=` / `u=` for reproducible parity tests.
+  * `variables["params"]` holds torch CUDA tensors under the Flax names (coarse_mlp/Dense_0.. etc.).
+  * `apply(..., debug=True)` additionally returns the bent path (the "per-ray sample positions out" of the
+    commented debug variant, rnerf/models.py:362-365, rnerf/utils.py:385-388).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .utils import Rays
+
+_EPS32 = float(np.finfo(np.float32).eps)
+
+
+def _glorot_uniform(gen: torch.Generator, fan_in: int, fan_out: int, device) -> torch.Tensor:
+    a = math.sqrt(6.0 / (fan_in + fan_out))
+    return ((torch.rand(fan_in, fan_out, generator=gen, dtype=torch.float64) * 2 - 1) * a).to(torch.float32).to(device)
+
+
+def _dense(gen, i, o, device, kernel=None):
+    return {"kernel": kernel if kernel is not None else _glorot_uniform(gen, i, o, device),
+            "bias": torch.zeros(o, dtype=torch.float32, device=device)}
+
+
+def init_nerf_mlp_params(gen, device, in_dim=63, cond_dim=27, width=256, depth=8, skip=4, width_cond=128) -> Dict:
+    """Parameters of model_utils.NerfMLP in Flax creation order (rnerf/model_utils.py:65-89):
+    Dense_0..7 trunk, Dense_8 sigma, Dense_9 bottleneck, Dense_10 condition, Dense_11 rgb."""
+    p, d_in, li = {}, in_dim, 0
+    for i in range(depth):
+        p[f"Dense_{li}"] = _dense(gen, d_in, width, device); li += 1
+        d_in = width + in_dim if (i % skip == 0 and i > 0) else width
+    p[f"Dense_{li}"] = _dense(gen, d_in, 1, device); li += 1
+    p[f"Dense_{li}"] = _dense(gen, d_in, width, device); li += 1
+    p[f"Dense_{li}"] = _dense(gen, width + cond_dim, width_cond, device); li += 1
+    p[f"Dense_{li}"] = _dense(gen, width_cond, 3, device)
+    return p
+
+
+def init_small_mlp_params(gen, device, in_dim=27, width=128, depth=4, skip=2, out_dim=3, out_std=None) -> Dict:
+    """Parameters of model_utils.MLP (rnerf/model_utils.py:93-140) as used for bkgd_mlp / so3_mlp."""
+    p, d_in, li = {}, in_dim, 0
+    for i in range(depth):
+        p[f"Dense_{li}"] = _dense(gen, d_in, width, device); li += 1
+        d_in = width + in_dim if (i % skip == 0 and i > 0) else width
+    k = None
+    if out_std is not None:  # jax.nn.initializers.normal(stddev=1e-5) (rnerf/ior_utils.py:151)
+        k = (torch.randn(d_in, out_dim, generator=gen, dtype=torch.float64) * out_std).to(torch.float32).to(device)
+    p[f"Dense_{li}"] = _dense(gen, d_in, out_dim, device, k)
+    return p
+
+
+class NerfModel:
+    """Nerf NN Model with both coarse and fine MLPs, sampled along eikonal-bent rays (rnerf/models.py:42-535)."""
+
+    def __init__(self, *, ndim, nmin, nmax, grid, stage="radiance", use_fine_sparsity=False, use_online_sparsity=False,
+                 num_coarse_samples=64, num_fine_samples=128, use_viewdirs=True, sh_deg=-1, near=2.0, far=6.0,
+                 noise_std=None, net_depth=8, net_width=256, net_depth_condition=1, net_width_condition=128,
+                 net_activation="relu", skip_layer=4, num_rgb_channels=3, num_sigma_channels=1, white_bkgd=False,
+                 min_deg_point=0, max_deg_point=10, deg_view=4, lindisp=False, rgb_activation="sigmoid",
+                 sigma_activation="softplus", legacy_posenc_order=False, rgb_padding=0.001, sigma_bias=-1.0,
+                 num_path_samples=8, sh_direnc_deg=-1, use_mask_bbox=False, bd_cut_dist=None, cfg_name=None,
+                 use_random_choice=True, device=None):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.ndim, self.nmin, self.nmax = [int(v) for v in ndim], [float(v) for v in nmin], [float(v) for v in nmax]
+        self.stage = stage
+        self.use_fine_sparsity, self.use_online_sparsity = use_fine_sparsity, use_online_sparsity
+        self.num_coarse_samples, self.num_fine_samples = int(num_coarse_samples), int(num_fine_samples)
+        self.near, self.far = float(near), float(far)
+        self.white_bkgd = bool(white_bkgd)
+        self.rgb_padding, self.sigma_bias = float(rgb_padding), float(sigma_bias)
+        self.num_path_samples = int(num_path_samples)
+        self.use_mask_bbox, self.bd_cut_dist, self.cfg_name = bool(use_mask_bbox), bd_cut_dist, cfg_name or ""
+        self.use_random_choice = bool(use_random_choice)
+        self.deg_view, self.min_deg_point, self.max_deg_point = deg_view, min_deg_point, max_deg_point
+        # The sm_100a kernels are specialised for the one architecture every shipped config uses
+        # (flag defaults rnerf/utils.py:138-181); anything else is rejected loudly rather than approximated.
+        unsupported = []
+        if (net_depth, net_width, net_depth_condition, net_width_condition, skip_layer) != (8, 256, 1, 128, 4):
+            unsupported.append("net_depth/net_width/net_depth_condition/net_width_condition/skip_layer != 8/256/1/128/4")
+        if (min_deg_point, max_deg_point, deg_view) != (0, 10, 4):
+            unsupported.append("min_deg_point/max_deg_point/deg_view != 0/10/4")
+        if not use_viewdirs: unsupported.append("use_viewdirs=False")
+        if sh_deg >= 0 or sh_direnc_deg > 0: unsupported.append("spherical-harmonics encodings (sh_deg/sh_direnc_deg)")
+        if legacy_posenc_order: unsupported.append("legacy_posenc_order=True")
+        if lindisp: unsupported.append("lindisp=True")
+        if noise_std is not None: unsupported.append("noise_std")
+        if (str(net_activation), str(rgb_activation), str(sigma_activation)) != ("relu", "sigmoid", "softplus"):
+            unsupported.append("activations other than relu/sigmoid/softplus")
+        if (num_rgb_channels, num_sigma_channels) != (3, 1): unsupported.append("num_rgb_channels/num_sigma_channels != 3/1")
+        if stage.startswith("all") or stage.startswith("ior"):
+            unsupported.append(f"stage={stage!r} (only the radiance stage is built; SURVEY section 8(f) rank 1)")
+        if self.num_fine_samples <= 0: unsupported.append("num_fine_samples <= 0")
+        if unsupported:
+            raise NotImplementedError("rnerf_b200 kernels do not cover: " + "; ".join(unsupported))
+        # VoxMLP.setup (rnerf/ior_utils.py:161): (n, grad n) table, built once on the device
+        g = torch.as_tensor(np.asarray(grid, dtype=np.float32) if not isinstance(grid, torch.Tensor) else grid)
+        g = g.to(self.device, torch.float32).reshape(-1).contiguous()
+        if g.numel() != self.ndim[0] * self.ndim[1] * self.ndim[2]:
+            raise ValueError("grid size does not match ndim")
+        self.table = ops.grid_table(g, self.ndim, self.nmin, self.nmax)
+        self.num_march_steps = self.num_coarse_samples * self.num_path_samples  # rnerf/models.py:121
+        self._pack_cache: Dict[str, Any] = {}
+
+    # ------------------------------------------------------------------ parameters
+    def init(self, key, device=None) -> Dict:
+        """Random-init variables with the reference's tree names."""
+        device = device or self.device
+        gen = torch.Generator().manual_seed(int(key) if key is not None else 0)
+        return {"params": {
+            "coarse_mlp": init_nerf_mlp_params(gen, device),
+            "fine_mlp": init_nerf_mlp_params(gen, device),
+            "bkgd_mlp": init_small_mlp_params(gen, device),
+            "path_sampler": {"scan": {"idx_model": {"so3_mlp": init_small_mlp_params(gen, device, in_dim=60, out_std=1e-5)}}},
+        }}
+
+    def _packed(self, variables: Dict, name: str) -> torch.Tensor:
+        """Device image of one MLP's weights; repacked only when a parameter tensor changed."""
+        p = variables["params"][name]
+        sig = tuple((id(d["kernel"]), d["kernel"]._version, id(d["bias"]), d["bias"]._version) for d in p.values())
+        hit = self._pack_cache.get(name)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            buf = ops.bkgd_pack(p) if name == "bkgd_mlp" else ops.encmlp_pack(p, out=hit[1] if hit else None)
+        self._pack_cache[name] = (sig, buf)
+        return buf
+
+    # ------------------------------------------------------------------ stochastic inputs
+    def draw_jitter(self, key) -> torch.Tensor:
+        """rnerf/models.py:240-242: arange(0, S, P) + randint(key, [Nc], 0, P) (also at eval, T9)."""
+        j = torch.arange(0, self.num_march_steps, self.num_path_samples, dtype=torch.int32)
+        if self.use_random_choice:
+            gen = torch.Generator().manual_seed(int(key) if key is not None else 0)
+            j = j + torch.randint(0, self.num_path_samples, (self.num_coarse_samples,), generator=gen, dtype=torch.int32)
+        return j.to(self.device)
+
+    def draw_u(self, key, n_rays: int, randomized: bool) -> torch.Tensor:
+        """rnerf/model_utils.py:343-356: stratified (train) or linspace(0, 1-eps, Nf) (eval) CDF positions."""
+        nf = self.num_fine_samples
+        if not randomized:
+            return torch.linspace(0.0, 1.0 - _EPS32, nf, dtype=torch.float32, device=self.device)
+        gen = torch.Generator(device=self.device).manual_seed(int(key) if key is not None else 0)
+        s = 1.0 / nf
+        u = torch.arange(nf, device=self.device, dtype=torch.float32) * s
+        u = u + torch.rand(n_rays, nf, generator=gen, device=self.device) * (s - _EPS32)
+        return torch.clamp(u, max=1.0 - _EPS32).contiguous()
+
+    # ------------------------------------------------------------------ forward
+    def apply(self, variables: Dict, *args, method=None, **kwargs):
+        if method is not None:
+            fn = method if callable(method) else getattr(self, method)
+            if getattr(fn, "__self__", None) is self:
+                return fn(variables, *args, **kwargs)
+            return fn(self, variables, *args, **kwargs)
+        return self.__call__(variables, *args, **kwargs)
+
+    def forward_envmap(self, variables: Dict, viewdirs: torch.Tensor) -> torch.Tensor:
+        """rnerf/models.py:181-191."""
+        from . import autograd as ag
+        return ag.bkgd_color(self, variables, viewdirs.reshape(-1, 3).contiguous())
+
+    def _bd_bbox(self):
+        """Scene-name-selected bbox of the bd_cut_dist passes (rnerf/models.py:485-497)."""
+        if "pen" in self.cfg_name:
+            lo, hi = list(self.nmin), list(self.nmax); hi[1] -= 0.6
+        elif "ball" in self.cfg_name:
+            lo, hi = [-1, 0.03597, -1], [1, 2.03597, 1]
+        elif "glass" in self.cfg_name:
+            lo, hi = list(self.nmin), list(self.nmax); hi[1] -= 0.7
+        else:
+            raise NotImplementedError()
+        return lo, hi
+
+    def __call__(self, variables: Dict, rng_0, rng_1, rays: Rays, randomized: bool, annealed_alpha: float = 1.0, *,
+                 jitter: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None, debug: bool = False):
+        from . import autograd as ag
+        Nc, Nf, S = self.num_coarse_samples, self.num_fine_samples, self.num_march_steps
+        origins = rays.origins.to(self.device, torch.float32).contiguous()
+        viewdirs = rays.viewdirs.to(self.device, torch.float32).contiguous()   # T1: the unit viewdirs, not directions
+        B = origins.shape[0]
+        k0 = None if rng_0 is None else int(rng_0)
+        k1 = None if rng_1 is None else int(rng_1)
+        # --- bent-ray march: no trainable inputs in the radiance stage (T7) -> no autograd through it
+        with torch.no_grad():
+            path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S)
+            jit = self.draw_jitter(k0) if jitter is None else torch.as_tensor(jitter).to(self.device, torch.int32).contiguous()
+            pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=self.use_online_sparsity)
+            mask_c = self._bbox_mask(pos_c) if self.use_mask_bbox else None
+        # --- coarse pass
+        raw_bkgd = ag.bkgd_raw(self, variables, dir_c, B, Nc)                      # T11: dir at the last coarse sample
+        raw_c = ag.radiance_mlp(self, variables, "coarse_mlp", pos_c, dir_c)      # [B,Nc,4]
+        out_c = ag.composite(raw_c, t_c, dir_c, raw_bkgd, mask_c, self.white_bkgd, self.rgb_padding, self.sigma_bias,
+                             want_alpha=self.use_online_sparsity)
+        loss_sp = torch.zeros((), device=self.device)
+        if self.use_online_sparsity:
+            m = (grad_c.norm(dim=-1) > 1e-6).float()
+            loss_sp = (m * torch.log(torch.clamp(out_c["alpha"], min=1e-6))).sum() / (m.sum() + 1)
+        ret = [(out_c["comp_rgb"], out_c["distance"], out_c["acc"], out_c["trans"], out_c["trans_rgb_bkgd"])]
+        # --- hierarchical resampling along the bent path (stop-gradient in the reference)
+        with torch.no_grad():
+            uu = self.draw_u(k1, B, randomized) if u is None else torch.as_tensor(u).to(self.device, torch.float32).contiguous()
+            t_f, pos_f, dir_f, grad_f = ops.resample(path, t_c, out_c["weights"].detach(), uu, Nf,
+                                                     want_grad=self.use_online_sparsity and self.use_fine_sparsity)
+            mask_f = self._bbox_mask(pos_f) if self.use_mask_bbox else None
+        # --- fine pass
+        raw_f = ag.radiance_mlp(self, variables, "fine_mlp", pos_f, dir_f)        # [B,Nc+Nf,4]
+        out_f = ag.composite(raw_f, t_f, dir_f, raw_bkgd, mask_f, self.white_bkgd, self.rgb_padding, self.sigma_bias,
+                             want_alpha=self.use_online_sparsity and self.use_fine_sparsity, want_weights=False)
+        trans, trb = out_f["trans"], out_f["trans_rgb_bkgd"]
+        if self.bd_cut_dist is not None:
+            # rnerf/models.py:479-524: transmittance up to the last in-box sample, colour behind it
+            assert not self.use_mask_bbox, "'use_mask_bbox' is true"
+            lo, hi = self._bd_bbox()
+            with torch.no_grad():
+                m, im = ops.bbox_tail_mask(pos_f, lo, hi)
+            trans = ag.composite(raw_f, t_f, dir_f, None, m, self.white_bkgd, self.rgb_padding, self.sigma_bias,
+                                 want_weights=False)["trans"]
+            behind = ag.composite(raw_f, t_f, dir_f, raw_bkgd, im, self.white_bkgd, self.rgb_padding, self.sigma_bias,
+                                  want_weights=False)["comp_rgb"]
+            trb = trans * behind
+        if self.use_online_sparsity and self.use_fine_sparsity:
+            m = (grad_f.norm(dim=-1) > 1e-6).float()
+            loss_sp = loss_sp + (m * torch.log(torch.clamp(out_f["alpha"], min=1e-6))).sum() / (m.sum() + 1)
+        ret.append((out_f["comp_rgb"], out_f["distance"], out_f["acc"], trans, trb))
+        if debug:
+            rp, rd, rt, idn, idg = ops.path_views(path)
+            dbg = {"path": path, "ray_pos": rp, "ray_dir": rd, "ray_dist": rt, "idx_data": idn, "idx_grad": idg,
+                   "ray_pos_c": pos_c, "jitter": jit, "u": uu, "t_c": t_c, "weights_c": out_c["weights"],
+                   "raw_c": raw_c, "raw_f": raw_f, "t_f": t_f, "pos_f": pos_f, "dir_f": dir_f, "raw_bkgd": raw_bkgd}
+            return ret, loss_sp, dbg
+        return ret, loss_sp
+
+    def _bbox_mask(self, pos: torch.Tensor) -> torch.Tensor:
+        """rnerf/models.py:260-271 small mask bbox: pos inside [nmin, nmax]."""
+        lo = torch.tensor(self.nmin, device=pos.device, dtype=torch.float32)
+        hi = torch.tensor(self.nmax, device=pos.device, dtype=torch.float32)
+        return ((pos >= lo) & (pos <= hi)).all(dim=-1).float().contiguous()
+
+
+def construct_nerf(key, example_batch, args, ndim, nmin, nmax, grid):
+    """Construct a Neural Radiance Field (rnerf/models.py:538-618).  Returns (model, init_variables)."""
+    if getattr(args, "sh_deg", -1) >= 0:
+        assert not args.use_viewdirs, "You can only use up to one of: SH or use_viewdirs."
+    gin_model = getattr(args, "gin_bindings", {}).get("NerfModel", {}) if hasattr(args, "gin_bindings") else {}
+    model = NerfModel(
+        min_deg_point=args.min_deg_point, max_deg_point=args.max_deg_point, deg_view=args.deg_view,
+        num_coarse_samples=args.num_coarse_samples, num_fine_samples=args.num_fine_samples,
+        use_viewdirs=args.use_viewdirs, sh_deg=args.sh_deg, near=args.near, far=args.far, noise_std=args.noise_std,
+        white_bkgd=args.white_bkgd, net_depth=args.net_depth, net_width=args.net_width,
+        net_depth_condition=args.net_depth_condition, net_width_condition=args.net_width_condition,
+        skip_layer=args.skip_layer, num_rgb_channels=args.num_rgb_channels, num_sigma_channels=args.num_sigma_channels,
+        lindisp=args.lindisp, net_activation=args.net_activation, rgb_activation=args.rgb_activation,
+        sigma_activation=args.sigma_activation, legacy_posenc_order=args.legacy_posenc_order,
+        ndim=ndim, nmin=nmin, nmax=nmax, grid=grid, stage=args.stage, num_path_samples=args.num_path_samples,
+        use_fine_sparsity=args.use_fine_sparsity, use_online_sparsity=args.use_online_sparsity,
+        sh_direnc_deg=args.sh_direnc_deg, cfg_name=args.config, **gin_model)
+    return model, model.init(key)

@@ -1,0 +1,198 @@
+"""Host-side mirror of the parts of rnerf/utils.py that sit either side of the hot path: the `Rays`
+container, flag defaults + YAML overlay, a gin-subset reader for the unchanged configs/*.gin, the chunked
+`render_image` driver, the learning-rate schedule and ray sharding.  (Reference: rnerf/utils.py.)
+"""
+from __future__ import annotations
+
+import ast
+import collections
+import dataclasses
+import math
+import os
+import re
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+
+import torch
+import yaml
+
+Rays = collections.namedtuple("Rays", ("origins", "directions", "viewdirs", "radii"))  # rnerf/utils.py:67
+
+
+def namedtuple_map(fn, tup):
+    """Apply `fn` to each element of `tup` and cast to `tup`'s namedtuple (rnerf/utils.py:70-72)."""
+    return type(tup)(*map(fn, tup))
+
+
+@dataclasses.dataclass
+class Config:
+    """gin-configurable `Config` of rnerf/utils.py:75-84."""
+    kernel_size: int = 3
+    kernel_sigma: float = 1.0
+    voxel_grid: str = "voxelize"
+    radiance_weight_name: Optional[str] = "radiance"
+    ior_weight_name: Optional[str] = "ior"
+    all_weight_name: Optional[str] = "all"
+
+
+# flag defaults of rnerf/utils.py:87-245 (define_flags); names unchanged
+FLAG_DEFAULTS: Dict[str, Any] = dict(
+    gin_file=None, gin_param=None, train_dir=None, stage_dir=None, data_dir=None, config=None,
+    dataset="blender", batching="single_image", white_bkgd=True, batch_size=1024, factor=4, spherify=False,
+    render_path=False, llffhold=8, use_pixel_centers=False, stage="radiance", skip_frames=1,
+    model="nerf", near=2.0, far=6.0, net_depth=8, net_width=256, net_depth_condition=1, net_width_condition=128,
+    weight_decay_mult=0.0, skip_layer=4, num_rgb_channels=3, num_sigma_channels=1, randomized=True,
+    min_deg_point=0, max_deg_point=10, deg_view=4, num_coarse_samples=64, num_fine_samples=128, use_viewdirs=True,
+    sh_deg=-1, sh_direnc_deg=-1, noise_std=None, lindisp=False, net_activation="relu", rgb_activation="sigmoid",
+    sigma_activation="softplus", legacy_posenc_order=False,
+    lr_init=5e-4, lr_final=5e-6, lr_delay_steps=2500, lr_delay_mult=0.01, grad_max_norm=0.0, grad_max_val=0.0,
+    max_steps=1000000, save_every=10000, print_every=100, render_every=5000, gc_every=10000, precrop_iters=0,
+    precrop_frac=0.5, num_path_samples=8, sparsity_weight=0.0, use_fine_sparsity=False, use_online_sparsity=True,
+    extra_batch_size=1024, normal_loss_weight=0.0, normal_smooth_weight=0.0, anneal_delay_steps=80000,
+    anneal_max_steps=160000, beta_weight=0.0, bg_weight=0.0, bg_smooth_weight=0.0, bg_patch_size=0,
+    eval_once=True, save_output=True, chunk=8192, eval_train=False,
+)
+
+
+class Flags:
+    """Stand-in for absl FLAGS: attribute access over the reference's flag names and defaults."""
+
+    def __init__(self, **overrides):
+        self.__dict__.update(FLAG_DEFAULTS)
+        unknown = set(overrides) - set(FLAG_DEFAULTS)
+        if unknown:
+            raise ValueError(f"Unknown flags {sorted(unknown)}")
+        self.__dict__.update(overrides)
+
+
+def update_flags(args: Flags, base_dir: Optional[str] = None) -> None:
+    """YAML overlay (rnerf/utils.py:248-257): `<config>.yaml` may only set flags that already exist."""
+    pth = args.config + ".yaml" if base_dir is None else os.path.join(base_dir, args.config + ".yaml")
+    with open(pth, "r") as fin:
+        configs = yaml.load(fin, Loader=yaml.FullLoader)
+    invalid_args = list(set(configs.keys()) - set(dir(args)) - set(args.__dict__))
+    if invalid_args:
+        raise ValueError(f"Invalid args {invalid_args} in {pth}.")
+    args.__dict__.update(configs)
+
+
+_GIN_LINE = re.compile(r"^\s*([A-Za-z_][\w]*)\.([A-Za-z_][\w]*)\s*=\s*(.+?)\s*$")
+
+
+def parse_gin(files: Optional[Iterable[str]] = None, bindings: Optional[Iterable[str]] = None) -> Dict[str, Dict[str, Any]]:
+    """The subset of gin the shipped configs use: `Name.attr = python-literal` lines and `#` comments
+    (rnerf/utils.py:267-270 calls gin.parse_config_files_and_bindings; gin-config is not installable here)."""
+    out: Dict[str, Dict[str, Any]] = collections.defaultdict(dict)
+    lines: List[str] = []
+    for f in files or []:
+        with open(f, "r") as fh:
+            lines += fh.read().splitlines()
+    for b in bindings or []:
+        lines += b.splitlines()
+    for raw in lines:
+        line = raw.split("#", 1)[0].strip() if "'" not in raw and '"' not in raw else _strip_comment(raw)
+        if not line:
+            continue
+        m = _GIN_LINE.match(line)
+        if not m:
+            raise ValueError(f"unsupported gin syntax: {raw!r}")
+        scope, attr, val = m.groups()
+        out[scope][attr] = ast.literal_eval(val)
+    return dict(out)
+
+
+def _strip_comment(raw: str) -> str:
+    quote = None
+    for i, ch in enumerate(raw):
+        if quote:
+            if ch == quote:
+                quote = None
+        elif ch in "'\"":
+            quote = ch
+        elif ch == "#":
+            return raw[:i].strip()
+    return raw.strip()
+
+
+def load_config(gin_files=None, gin_params=None):
+    """-> (Config, gin dict).  Mirrors rnerf/utils.py:267-270."""
+    g = parse_gin(gin_files, gin_params)
+    known = {f.name for f in dataclasses.fields(Config)}
+    bad = set(g.get("Config", {})) - known
+    if bad:
+        raise ValueError(f"Unknown Config bindings {sorted(bad)}")
+    return Config(**g.get("Config", {})), g
+
+
+def render_image(render_fn: Callable, rays: Rays, rng, normalize_disp: bool, chunk: int = 8192, world_size: int = 1,
+                 debug: bool = False):
+    """Render all the pixels of an image in `chunk`-ray pieces (rnerf/utils.py:331-389).
+
+    render_fn(key_0, key_1, chunk_rays) -> (ret, loss_sp) with ret[-1] = (rgb, distance, acc, trans, trans_rgb_bkgd).
+    Chunks are padded by edge replication to a multiple of `world_size` like the reference pads to the
+    device count (rnerf/utils.py:357-361).  Returns (rgb[H,W,3], distance[H,W,1], acc[H,W,1]).
+    """
+    height, width = rays[0].shape[:2]
+    num_rays = height * width
+    rays = namedtuple_map(lambda r: r.reshape((num_rays, -1)), rays)
+    key_0, key_1 = _split_key(rng)
+    results = []
+    for i in range(0, num_rays, chunk):
+        chunk_rays = namedtuple_map(lambda r: r[i:i + chunk], rays)
+        chunk_size = chunk_rays[0].shape[0]
+        rem = chunk_size % world_size
+        padding = world_size - rem if rem != 0 else 0
+        if padding:
+            chunk_rays = namedtuple_map(lambda r: torch.cat([r, r[-1:].expand(padding, -1)], dim=0), chunk_rays)
+        chunk_results = render_fn(key_0, key_1, chunk_rays)[0][-1]
+        results.append([x[:-padding] if padding else x for x in chunk_results])
+    rgb, distance, acc, trans, trans_rgb_bkgd = [torch.cat(r, dim=0) for r in zip(*results)]
+    if normalize_disp:
+        distance = (distance - distance.min()) / (distance.max() - distance.min())
+    return (rgb.reshape(height, width, -1), distance.reshape(height, width, -1), acc.reshape(height, width, -1))
+
+
+def _split_key(rng):
+    """jax.random.split(rng, 3)[1:] stand-in: two derived integer seeds."""
+    seed = int(rng) if rng is not None else 0
+    return (seed * 2654435761 + 1) % (2 ** 31), (seed * 2654435761 + 2) % (2 ** 31)
+
+
+def compute_psnr(mse):
+    """rnerf/utils.py:392-401."""
+    if isinstance(mse, torch.Tensor):
+        return -10.0 * torch.log(mse) / math.log(10.0)
+    return -10.0 * math.log(mse) / math.log(10.0)
+
+
+def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1, lr_start_steps=0):
+    """Log-linear decay with a sine warm-up (rnerf/utils.py:490-528)."""
+    if lr_delay_steps > 0:
+        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * math.sin(
+            0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+    else:
+        delay_rate = 1.0
+    start_rate = min(max(step - lr_start_steps, 0), 1)
+    t = min(max(max(step - lr_start_steps, 0) / (max_steps - lr_start_steps), 0.0), 1.0)
+    log_lerp = math.exp(math.log(lr_init) * (1 - t) + math.log(lr_final) * t)
+    return start_rate * delay_rate * log_lerp
+
+
+def shard_range(n: int, rank: int, world_size: int):
+    """Contiguous ray range of `rank` (reference: shard() reshapes to [n_dev, B/n_dev, ...], rnerf/utils.py:531-534)."""
+    per = n // world_size
+    return rank * per, (rank + 1) * per
+
+
+def load_mesh_pkl(path: str):
+    """mesh.pkl schema (voxelize_mesh.py:109-116; loader train.py:209-217) -> (data[G^3,1] float64, ndim, nmin, nmax)."""
+    import pickle
+    with open(path, "rb") as f:
+        mesh_dict = pickle.load(f)
+    if mesh_dict["extent"] > 0:
+        nmin = [-mesh_dict["extent"]] * 3
+        nmax = [mesh_dict["extent"]] * 3
+    else:
+        nmin = list(mesh_dict["min_point"])
+        nmax = list(mesh_dict["max_point"])
+    ndim = [mesh_dict["num_voxels"]] * 3
+    return mesh_dict["data"], ndim, nmin, nmax
