@@ -79,6 +79,11 @@ int rnerf_encmlp_fwd(const void* packed, const float* pos, const float* dir, int
 int rnerf_encmlp_fwd_debug(const void* packed, const float* pos, const float* dir, int64_t n_samples,
                            float* raw_out, uint16_t* layer_out, void* stream);
 
+/* development aid: same as rnerf_encmlp_fwd, plus clock64 stamps of CTA 0: prof[2 roles][10 layers][4] int64
+ * (role 0 = MMA issuer: wait-start, A-ready, issued; role 1 = epilogue: wait-start, acc-ready, done). */
+int rnerf_encmlp_fwd_profile(const void* packed, const float* pos, const float* dir, int64_t n_samples,
+                             float* raw_out, long long* prof, void* stream);
+
 /* ---- a10: rnerf/model_utils.py:93-140 MLP as bkgd_mlp (27->128->128->128(+27)->128->3), fp32 ----
  * w: the 5 Dense kernels then the 5 biases, concatenated fp32 ([in,out] row-major each).
  * dirs: [B][3] unit directions (encoded in-kernel, pos_enc deg 0..4).  raw_out: [B][3]. */

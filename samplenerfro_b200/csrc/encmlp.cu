@@ -222,6 +222,7 @@ struct EncMlpArgs {
   int64_t n_samples;
   float4* raw_out;
   __nv_bfloat16* layer_out;  // debug dump [10][M][256] or null
+  long long* prof;           // development aid: clock64 stamps of CTA 0, [2 roles][10 layers][4], or null
   int n_groups;              // ceil(n_samples / (128*NT))
 };
 
@@ -308,9 +309,12 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
       uint32_t phase = 0, ar_phase = 0;
       for (int g = 0; g < my_groups; ++g) {
         for (int l = 0; l < N_MMA_LAYERS; ++l) {
+          const bool prof = args.prof != nullptr && blockIdx.x == 0 && g == 0;
+          if (prof) args.prof[l * 4 + 0] = clock64();
           mbar_wait(bar_aready, ar_phase);  // A operand of layer l written (and accumulators drained)
           ar_phase ^= 1;
           tc_fence_after();
+          if (prof) args.prof[l * 4 + 1] = clock64();
           const int akb = layer_akb(l), nkb = akb + layer_has_e(l), nhn = layer_nh(l);
           for (int h = 0; h < nhn; ++h) {
             for (int kbi = 0; kbi < nkb; ++kbi) {
@@ -333,6 +337,7 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
               if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
           }
+          if (prof) args.prof[l * 4 + 2] = clock64();
         }
       }
     }
@@ -367,8 +372,11 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
         const float* bias = bias_all + l * 256;
         float r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
         // all n-halves of the layer must be complete before the in-place overwrite of the A operand
+        const bool prof = args.prof != nullptr && blockIdx.x == 0 && g == 0 && warp == 2 && lane == 0;
+        if (prof) args.prof[40 + l * 4 + 0] = clock64();
         for (int h = 0; h < nhn; ++h) { mbar_wait(bar_acc(h), acc_phase[h]); acc_phase[h] ^= 1; }
         tc_fence_after();
+        if (prof) args.prof[40 + l * 4 + 1] = clock64();
         for (int cg = 0; cg < nhn * 4; ++cg) {  // 32 accumulator columns at a time
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + cg * 32), v);
@@ -425,6 +433,7 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
           const float d0 = __ldg(args.dir + 3 * lrow), d1 = __ldg(args.dir + 3 * lrow + 1), d2 = __ldg(args.dir + 3 * lrow + 2);
           write_encoding<4>(e_blk, row, d0, d1, d2);
         }
+        if (prof) args.prof[40 + l * 4 + 2] = clock64();
         if (l == 9) {
           if (live) args.raw_out[srow] = make_float4(r_acc + headb.x, g_acc + headb.y, b_acc + headb.z, sigma_raw + headb.w);
           tc_fence_before();  // accumulators drained; the next group's layer 0 may overwrite them
@@ -486,7 +495,7 @@ extern "C" int rnerf_encmlp_pack(const float* const* kernels, const float* const
 }
 
 static int encmlp_fwd_impl(const void* packed, const float* pos, const float* dir, int64_t n_samples, float* raw_out,
-                           uint16_t* layer_out, void* stream) {
+                           uint16_t* layer_out, void* stream, long long* prof = nullptr) {
   RNERF_REQUIRE(n_samples >= 0, RNERF_E_SHAPE, "rnerf_encmlp_fwd: n_samples < 0");
   if (n_samples == 0) return 0;
   RNERF_REQUIRE_PTR(packed); RNERF_REQUIRE_PTR(pos); RNERF_REQUIRE_PTR(dir); RNERF_REQUIRE_PTR(raw_out);
@@ -494,7 +503,7 @@ static int encmlp_fwd_impl(const void* packed, const float* pos, const float* di
   RNERF_REQUIRE(layer_out == nullptr || aligned16(layer_out), RNERF_E_ALIGN, "rnerf_encmlp_fwd: layer_out must be 16-byte aligned");
   EncMlpArgs a;
   a.packed = (const uint8_t*)packed; a.pos = pos; a.dir = dir; a.n_samples = n_samples;
-  a.raw_out = (float4*)raw_out; a.layer_out = (__nv_bfloat16*)layer_out; a.n_groups = 0;
+  a.raw_out = (float4*)raw_out; a.layer_out = (__nv_bfloat16*)layer_out; a.prof = prof; a.n_groups = 0;
   if (n_samples <= 148 * 128) return launch_encmlp<1, 8>(a, (cudaStream_t)stream);
   return launch_encmlp<2, 4>(a, (cudaStream_t)stream);
 }
@@ -507,4 +516,10 @@ extern "C" int rnerf_encmlp_fwd(const void* packed, const float* pos, const floa
 extern "C" int rnerf_encmlp_fwd_debug(const void* packed, const float* pos, const float* dir, int64_t n_samples,
                                       float* raw_out, uint16_t* layer_out, void* stream) {
   return encmlp_fwd_impl(packed, pos, dir, n_samples, raw_out, layer_out, stream);
+}
+
+// development aid (not part of the reference-facing surface): per-layer clock64 stamps of CTA 0
+extern "C" int rnerf_encmlp_fwd_profile(const void* packed, const float* pos, const float* dir, int64_t n_samples,
+                                        float* raw_out, long long* prof, void* stream) {
+  return encmlp_fwd_impl(packed, pos, dir, n_samples, raw_out, nullptr, stream, prof);
 }

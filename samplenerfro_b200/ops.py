@@ -233,3 +233,14 @@ def bbox_tail_mask(pos: torch.Tensor, lo, hi):
     check(_lib.load().rnerf_bbox_tail_mask(_p(pos), B, Ns, Dbl3(*[float(v) for v in lo]), Dbl3(*[float(v) for v in hi]),
                                            _p(m), _p(im), _stream()), "rnerf_bbox_tail_mask")
     return m, im
+
+
+def encmlp_fwd_profile(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tensor):
+    """Development aid: forward + per-layer clock64 stamps of CTA 0 -> (raw, prof[2,10,4] int64)."""
+    pos = _chk(pos, "pos").reshape(-1, 3); dirs = _chk(dirs, "dirs").reshape(-1, 3)
+    M = pos.shape[0]
+    raw = torch.empty(M, 4, device=pos.device, dtype=torch.float32)
+    prof = torch.zeros(2, 10, 4, device=pos.device, dtype=torch.int64)
+    check(_lib.load().rnerf_encmlp_fwd_profile(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(prof), _stream()),
+          "rnerf_encmlp_fwd_profile")
+    return raw, prof
