@@ -12,8 +12,9 @@
 // warpgroup (128 threads, thread <-> sample row) per 128-row tile.  NT tiles (NT*128 samples) share every
 // weight chunk, which divides the L2->SM weight traffic by NT.
 //
-// Tile geometry: M = 128 rows per tile (UMMA_M = 128, cta_group::1), N = 128 per MMA (one "n-half" of a
-// 256-wide layer), K-chunk = 64 bf16 = one 128-byte swizzle row (4 x UMMA_K=16).
+// Tile geometry: M = 128 rows per tile (UMMA_M = 128, cta_group::1), N = the whole layer width per MMA (256, or
+// 128 for the condition layer) so that the A operand is read from shared memory once per K-step; activations are
+// [128 x 64] SWIZZLE_128B k-blocks, weights stream as [N x 32] SWIZZLE_64B chunks (2 x UMMA_K=16 each).
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -23,29 +24,36 @@ namespace rnerf {
 // network geometry (flag defaults rnerf/utils.py:138-157; identical in every shipped config)
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_M = 128;
-constexpr int KB = 64;                     // K elements per chunk / swizzle row
-constexpr int NH = 128;                    // N per MMA
-constexpr int CHUNK_BYTES = NH * KB * 2;   // 16384
+constexpr int KB = 64;                       // K elements per activation k-block (one 128-byte swizzle row)
+constexpr int KCH = 32;                      // K elements per weight chunk (one 64-byte swizzle row)
+constexpr int SUBS = KB / KCH;               // weight chunks per activation k-block
+constexpr int NMAX = 256;                    // widest layer = N of one MMA
+constexpr int SLOT_BYTES = NMAX * KCH * 2;   // 16384: one ring slot / packed chunk
 constexpr int ABLK_BYTES = TILE_M * KB * 2;  // 16384: one [128 x 64] bf16 activation k-block
-constexpr int N_MMA_LAYERS = 10;           // Dense_0..7, Dense_9 (bottleneck), Dense_10 (condition)
-constexpr int N_CHUNKS = 73;
+constexpr int N_MMA_LAYERS = 10;             // Dense_0..7, Dense_9 (bottleneck), Dense_10 (condition)
 constexpr int POS_ENC = 63, DIR_ENC = 27;
 
 // per MMA layer: number of A k-blocks taken from the activation buffer, whether the E (encoding) block is
-// appended, number of n-halves, ReLU, and the Flax Dense index it implements
+// appended, output width, ReLU, and the Flax Dense index it implements
 __host__ __device__ constexpr int layer_akb(int l) { return l == 0 ? 0 : 4; }
 __host__ __device__ constexpr int layer_has_e(int l) { return (l == 0 || l == 5 || l == 9) ? 1 : 0; }
-__host__ __device__ constexpr int layer_nh(int l) { return l == 9 ? 1 : 2; }
+__host__ __device__ constexpr int layer_n(int l) { return l == 9 ? 128 : 256; }
 __host__ __device__ constexpr int layer_relu(int l) { return l == 8 ? 0 : 1; }
 __host__ __device__ constexpr int layer_dense(int l) { return l < 8 ? l : l + 1; }   // 8->Dense_9, 9->Dense_10
-__host__ __device__ constexpr int layer_chunks(int l) { return (layer_akb(l) + layer_has_e(l)) * layer_nh(l); }
+__host__ __device__ constexpr int layer_chunks(int l) { return (layer_akb(l) + layer_has_e(l)) * SUBS; }
+__host__ __device__ constexpr int total_chunks() {
+  int c = 0;
+  for (int l = 0; l < N_MMA_LAYERS; ++l) c += layer_chunks(l);
+  return c;
+}
+constexpr int N_CHUNKS = total_chunks();     // 78
 
-// packed image: [chunks][fp32 tail]
+// packed image: [chunks, one slot each][fp32 tail]
 constexpr size_t PK_CHUNKS = 0;
-constexpr size_t PK_BIAS = (size_t)N_CHUNKS * CHUNK_BYTES;         // float bias[10][256]
+constexpr size_t PK_BIAS = (size_t)N_CHUNKS * SLOT_BYTES;          // float bias[10][256]
 constexpr size_t PK_WSIGMA = PK_BIAS + 10 * 256 * 4;               // float w_sigma[256] (bf16-rounded)
-constexpr size_t PK_WRGB = PK_WSIGMA + 256 * 4;                    // float4 w_rgb[128] (bf16-rounded, .w = 0)
-constexpr size_t PK_HEADB = PK_WRGB + 128 * 16;                    // float4 (b_r, b_g, b_b, b_sigma)
+constexpr size_t PK_WRGB = PK_WSIGMA + 256 * 4;                    // float w_rgb[3][128] (bf16-rounded, channel-major)
+constexpr size_t PK_HEADB = PK_WRGB + 3 * 128 * 4;                 // float4 (b_r, b_g, b_b, b_sigma)
 constexpr size_t PK_TOTAL = PK_HEADB + 16;
 
 // ------------------------------------------------------------------------------------------------
@@ -130,11 +138,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row atoms 1024 B apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) (=1, unused), SBO>>4 [32,46) (=64),
-//  version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64))
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) (=1, unused for
+// swizzled K-major), SBO>>4 [32,46), version=1 [46,48), layout_type [61,64)).
+//   A operand: K-major SWIZZLE_128B -- rows of 128 B (64 bf16), 8-row atoms 1024 B apart (layout_type 2)
+//   B operand: K-major SWIZZLE_64B  -- rows of  64 B (32 bf16), 8-row atoms  512 B apart (layout_type 4)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
 // cute::UMMA::InstrDescriptor for kind::f16: c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), K-major both,
 // N>>3 at [17,23), M>>4 at [24,29)
@@ -142,19 +154,33 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// byte offset of element (row, k) inside a [rows x 64] bf16 K-major SWIZZLE_128B block
+// byte offset of element (row, k) inside a [rows x 64] bf16 K-major SWIZZLE_128B block (Swizzle<3,4,3>)
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
 }
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+// byte offset of element (row, k) inside a [rows x 32] bf16 K-major SWIZZLE_64B block (Swizzle<2,4,3>:
+// address bits [4,6) ^= bits [7,9), i.e. the 16-byte unit index is xored with (row >> 1) & 3)
+__host__ __device__ __forceinline__ uint32_t sw64_offset(int row, int k) {
+  return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((k >> 3) ^ ((row >> 1) & 3)) & 3) << 4) + (k & 7) * 2);
 }
+
+// two fp32 -> packed bf16x2 (lo in bits [0,16)), optionally with ReLU fused into the conversion
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ------------------------------------------------------------------------------------------------
-// weight packing: Flax [in,out] fp32 kernels -> 73 pre-swizzled bf16 [128 n x 64 k] chunks + fp32 tail
+// weight packing: Flax [in,out] fp32 kernels -> pre-swizzled bf16 [N x 32] chunks + fp32 tail
 // ------------------------------------------------------------------------------------------------
 struct PackArgs {
   const float* kern[12];
@@ -162,39 +188,37 @@ struct PackArgs {
 };
 
 __global__ void __launch_bounds__(256) encmlp_pack_kernel(PackArgs a, uint8_t* __restrict__ packed) {
-  // chunk enumeration must match the MMA issuer: for layer, for n-half, for k-block (A blocks then E)
+  // chunk enumeration must match the MMA issuer: for layer, for k-block (A blocks then E), for 32-wide sub-chunk
   int c = blockIdx.x;
   if (c < N_CHUNKS) {
     int l = 0, rem = c;
     while (rem >= layer_chunks(l)) { rem -= layer_chunks(l); ++l; }
-    const int nkb = layer_akb(l) + layer_has_e(l);
-    const int nh = rem / nkb, kbi = rem % nkb;
+    const int kbi = rem / SUBS, sub = rem % SUBS;
     const bool is_e = kbi >= layer_akb(l);
     const int dense = layer_dense(l);
     const int in_dim = (l == 0) ? POS_ENC : (l == 5 ? 256 + POS_ENC : (l == 9 ? 256 + DIR_ENC : 256));
-    const int out_dim = (l == 9) ? 128 : 256;
+    const int out_dim = layer_n(l);
     const float* W = a.kern[dense];
-    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + PK_CHUNKS + (size_t)c * CHUNK_BYTES);
-    for (int e = threadIdx.x; e < NH * KB; e += blockDim.x) {
-      const int n = e / KB, k = e % KB;
-      const int kk = is_e ? (layer_akb(l) * KB + k) : (kbi * KB + k);
-      const int col = nh * NH + n;
-      float v = (kk < in_dim && col < out_dim) ? W[(size_t)kk * out_dim + col] : 0.f;
-      dst[sw128_offset(n, k) / 2] = __float2bfloat16_rn(v);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + PK_CHUNKS + (size_t)c * SLOT_BYTES);
+    for (int e = threadIdx.x; e < NMAX * KCH; e += blockDim.x) {
+      const int n = e / KCH, k = e % KCH;
+      const int kk = (is_e ? layer_akb(l) * KB : kbi * KB) + sub * KCH + k;
+      float v = (kk < in_dim && n < out_dim) ? W[(size_t)kk * out_dim + n] : 0.f;
+      dst[sw64_offset(n, k) / 2] = __float2bfloat16_rn(v);
     }
   } else {
     float* bias = reinterpret_cast<float*>(packed + PK_BIAS);
     for (int e = threadIdx.x; e < 10 * 256; e += blockDim.x) {
       const int l = e / 256, j = e % 256;
-      const int out_dim = (l == 9) ? 128 : 256;
-      bias[e] = j < out_dim ? a.bias[layer_dense(l)][j] : 0.f;
+      bias[e] = j < layer_n(l) ? a.bias[layer_dense(l)][j] : 0.f;
     }
     float* ws = reinterpret_cast<float*>(packed + PK_WSIGMA);
     for (int e = threadIdx.x; e < 256; e += blockDim.x) ws[e] = bf16_round(a.kern[8][e]);  // Dense_8: [256,1]
-    float4* wr = reinterpret_cast<float4*>(packed + PK_WRGB);
-    for (int e = threadIdx.x; e < 128; e += blockDim.x)                                      // Dense_11: [128,3]
-      wr[e] = make_float4(bf16_round(a.kern[11][e * 3]), bf16_round(a.kern[11][e * 3 + 1]),
-                          bf16_round(a.kern[11][e * 3 + 2]), 0.f);
+    float* wr = reinterpret_cast<float*>(packed + PK_WRGB);
+    for (int e = threadIdx.x; e < 3 * 128; e += blockDim.x) {                               // Dense_11: [128,3]
+      const int ch = e / 128, j = e % 128;
+      wr[e] = bf16_round(a.kern[11][j * 3 + ch]);
+    }
     if (threadIdx.x == 0)
       *reinterpret_cast<float4*>(packed + PK_HEADB) = make_float4(a.bias[11][0], a.bias[11][1], a.bias[11][2], a.bias[8][0]);
   }
@@ -208,11 +232,11 @@ struct SmemLayout {
   static constexpr uint32_t A_OFF = 0;                                   // [NT][4][16 KB] activation k-blocks
   static constexpr uint32_t E_OFF = A_OFF + NT * 4 * ABLK_BYTES;         // [NT][16 KB] encoding k-block
   static constexpr uint32_t W_OFF = E_OFF + NT * ABLK_BYTES;             // [NSTAGE][16 KB] weight ring
-  static constexpr uint32_t BAR_OFF = W_OFF + NSTAGE * CHUNK_BYTES;      // mbarriers (8 B each)
-  static constexpr uint32_t N_BARS = 2 * NSTAGE + 3;                     // full[], empty[], acc[2], a_ready
+  static constexpr uint32_t V_OFF = W_OFF + NSTAGE * SLOT_BYTES;         // 2 x 1 KB fp32: bias / head-weight slots
+  static constexpr uint32_t BAR_OFF = V_OFF + 2048;                      // mbarriers (8 B each)
+  static constexpr uint32_t N_BARS = 2 * NSTAGE + 2;                     // full[], empty[], acc, a_ready
   static constexpr uint32_t TMEM_SLOT = BAR_OFF + N_BARS * 8;
   static constexpr uint32_t BYTES = TMEM_SLOT + 16;
-  static constexpr uint32_t ALLOC = BYTES + 1024;                        // slack for manual 1024-B alignment
 };
 
 struct EncMlpArgs {
@@ -222,56 +246,150 @@ struct EncMlpArgs {
   int64_t n_samples;
   float4* raw_out;
   __nv_bfloat16* layer_out;  // debug dump [10][M][256] or null
-  long long* prof;           // development aid: clock64 stamps of CTA 0, [2 roles][10 layers][4], or null
+  long long* prof;           // development aid: clock64 stamps of CTA 0, [3][10][4], or null
   int n_groups;              // ceil(n_samples / (128*NT))
 };
 
 // pos_enc(x, 0, L) of one 3-vector into columns [0, 3+6L) of this thread's row of a swizzled k-block; the
 // remaining columns up to 64 are zero.  Feature order (non-legacy): x, sin(2^k x) k-major, sin(2^k x + pi/2).
+//
+// sin/cos(2^k x) come from one accurate sincosf(x) per channel followed by the double-angle recurrence
+// s' = 2 s c, c' = 1 - 2 s^2 (3 flops per octave instead of a full sinf).  The absolute error doubles per octave:
+// <= 2^9 * 1.2e-7 = 6e-5 at the top position octave -- below the reference's own error in the same feature
+// (it evaluates cos as sin(fl32(2^k x + pi/2)), off by up to ulp(3072)/2 = 1.2e-4) and ~30x below the bf16
+// quantisation step (2^-9 relative) the value is rounded to when it becomes an MMA operand.
 template <int L>
 __device__ __forceinline__ void write_encoding(uint8_t* blk, int row, float x0, float x1, float x2) {
   constexpr int NF = 3 + 6 * L;
+  float feat[64];
+  feat[0] = x0; feat[1] = x1; feat[2] = x2;
   const float xs[3] = {x0, x1, x2};
 #pragma unroll
-  for (int c8 = 0; c8 < 8; ++c8) {  // 8 columns (16 bytes) at a time
-    float v[8];
+  for (int ch = 0; ch < 3; ++ch) {
+    float s, c;
+    sincosf(xs[ch], &s, &c);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int f = c8 * 8 + j;
-      if (f < 3) {
-        v[j] = xs[f];
-      } else if (f < NF) {
-        const int q = (f - 3) % (3 * L), k = q / 3, ch = q % 3;
-        float xb = mul(xs[ch], (float)(1 << k));
-        if (f >= 3 + 3 * L) xb = add(xb, 1.57079632679489661923f);
-        v[j] = sinf(xb);
-      } else {
-        v[j] = 0.f;
-      }
+    for (int k = 0; k < L; ++k) {
+      feat[3 + 3 * k + ch] = s;
+      feat[3 + 3 * L + 3 * k + ch] = c;
+      const float s2 = s + s;
+      const float ns = s2 * c;
+      c = fmaf(-s2, s, 1.f);
+      s = ns;
     }
-    uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+#pragma unroll
+  for (int f = NF; f < 64; ++f) feat[f] = 0.f;
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) {  // 8 columns (16 bytes) at a time
+    uint4 o = make_uint4(pack_bf16(feat[c8 * 8 + 0], feat[c8 * 8 + 1]), pack_bf16(feat[c8 * 8 + 2], feat[c8 * 8 + 3]),
+                         pack_bf16(feat[c8 * 8 + 4], feat[c8 * 8 + 5]), pack_bf16(feat[c8 * 8 + 6], feat[c8 * 8 + 7]));
     *reinterpret_cast<uint4*>(blk + sw128_offset(row, c8 * 8)) = o;
   }
 }
 
-template <int NT, int NSTAGE>
+// 2 x fp32 packed add (SASS: FADD2)
+__device__ __forceinline__ void add2(uint32_t& x0, uint32_t& x1, float b0, float b1) {
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(x0), "r"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(x0), "=r"(x1) : "l"(c));
+}
+
+// Epilogue of one MMA layer for one sample row (thread): accumulators (TMEM) + bias -> [ReLU] -> bf16 ->
+// next layer's A operand (swizzled smem) and/or the fused heads.
+//   KIND 0: ReLU, write A            (Dense_0..6)
+//   KIND 1: ReLU, write A, sigma head (Dense_7 -> Dense_8)
+//   KIND 2: no activation, write A   (Dense_9 bottleneck)
+//   KIND 3: ReLU, rgb head only      (Dense_10 -> Dense_11), 128 columns
+struct EpiOut { float sigma, r, g, b; };
+
+template <int KIND, bool DUMP>
+__device__ __forceinline__ void epilogue_row(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ vslot,
+                                             uint8_t* __restrict__ a_row, uint32_t r7s, EpiOut& o,
+                                             __nv_bfloat16* __restrict__ dump_row) {
+  constexpr int NCG = (KIND == 3) ? 4 : 8;
+#pragma unroll 1
+  for (int cg2 = 0; cg2 < NCG; cg2 += 2) {   // 2 x 32 accumulator columns per iteration, both TMEM loads in flight
+    uint32_t v[2][32];
+    tmem_ld32(taddr + cg2 * 32, v[0]);
+    tmem_ld32(taddr + cg2 * 32 + 32, v[1]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int c0 = cg2 * 32 + half * 32;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + j4 * 4);
+        add2(v[half][4 * j4 + 0], v[half][4 * j4 + 1], b4.x, b4.y);
+        add2(v[half][4 * j4 + 2], v[half][4 * j4 + 3], b4.z, b4.w);
+        const float f0 = __uint_as_float(v[half][4 * j4 + 0]), f1 = __uint_as_float(v[half][4 * j4 + 1]);
+        const float f2 = __uint_as_float(v[half][4 * j4 + 2]), f3 = __uint_as_float(v[half][4 * j4 + 3]);
+        if (KIND == 2) { pk[2 * j4] = pack_bf16(f0, f1);      pk[2 * j4 + 1] = pack_bf16(f2, f3); }
+        else           { pk[2 * j4] = pack_bf16_relu(f0, f1); pk[2 * j4 + 1] = pack_bf16_relu(f2, f3); }
+      }
+      if (KIND == 1) {  // sigma head (Dense_8) on the bf16-rounded trunk output; weights in vslot[0..255]
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(vslot + c0 + j4 * 4);
+          o.sigma = fmaf(bf16_lo(pk[2 * j4]), w4.x, o.sigma);
+          o.sigma = fmaf(bf16_hi(pk[2 * j4]), w4.y, o.sigma);
+          o.sigma = fmaf(bf16_lo(pk[2 * j4 + 1]), w4.z, o.sigma);
+          o.sigma = fmaf(bf16_hi(pk[2 * j4 + 1]), w4.w, o.sigma);
+        }
+      }
+      if (KIND == 3) {  // rgb head (Dense_11) on the bf16-rounded condition-layer output
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 wr = *reinterpret_cast<const float4*>(vslot + c0 + j4 * 4);
+          const float4 wg = *reinterpret_cast<const float4*>(vslot + 128 + c0 + j4 * 4);
+          const float4 wb = *reinterpret_cast<const float4*>(vslot + 384 + c0 + j4 * 4);
+          const float h0 = bf16_lo(pk[2 * j4]), h1 = bf16_hi(pk[2 * j4]), h2 = bf16_lo(pk[2 * j4 + 1]), h3 = bf16_hi(pk[2 * j4 + 1]);
+          o.r = fmaf(h0, wr.x, o.r); o.r = fmaf(h1, wr.y, o.r); o.r = fmaf(h2, wr.z, o.r); o.r = fmaf(h3, wr.w, o.r);
+          o.g = fmaf(h0, wg.x, o.g); o.g = fmaf(h1, wg.y, o.g); o.g = fmaf(h2, wg.z, o.g); o.g = fmaf(h3, wg.w, o.g);
+          o.b = fmaf(h0, wb.x, o.b); o.b = fmaf(h1, wb.y, o.b); o.b = fmaf(h2, wb.z, o.b); o.b = fmaf(h3, wb.w, o.b);
+        }
+      } else {
+        // next layer's A operand: these 32 columns live in k-block cg2/2 at 16-byte units half*4 .. half*4+3,
+        // xor-swizzled with (row & 7)
+        uint8_t* blk = a_row + (cg2 >> 1) * ABLK_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(blk + ((uint32_t)((half * 4 + c) << 4) ^ r7s)) =
+              make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+      if (DUMP) {
+        if (dump_row != nullptr) {
+          uint4* dst = reinterpret_cast<uint4*>(dump_row + c0);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+template <int NT, int NSTAGE, bool DEBUG>
 __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpArgs args) {
   using SL = SmemLayout<NT, NSTAGE>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   auto bar_full = [&](int s) { return sbase + SL::BAR_OFF + 8u * s; };
   auto bar_empty = [&](int s) { return sbase + SL::BAR_OFF + 8u * (NSTAGE + s); };
-  auto bar_acc = [&](int h) { return sbase + SL::BAR_OFF + 8u * (2 * NSTAGE + h); };
-  const uint32_t bar_aready = sbase + SL::BAR_OFF + 8u * (2 * NSTAGE + 2);
+  const uint32_t bar_acc = sbase + SL::BAR_OFF + 8u * (2 * NSTAGE);
+  const uint32_t bar_aready = sbase + SL::BAR_OFF + 8u * (2 * NSTAGE + 1);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SL::TMEM_SLOT);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    mbar_init(bar_acc(0), 1);
-    mbar_init(bar_acc(1), 1);
+    mbar_init(bar_acc, 1);
     mbar_init(bar_aready, 4 * NT);  // one arrive per epilogue warp
     fence_barrier_init();
   }
@@ -287,56 +405,61 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
   const int my_groups = (args.n_groups > (int)blockIdx.x) ? (args.n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
-    // ===================== weight producer =====================
+    // ===================== weight producer (TMA bulk copies through an mbarrier ring) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int g = 0; g < my_groups; ++g) {
-        for (int c = 0; c < N_CHUNKS; ++c) {
-          mbar_wait(bar_empty(stage), phase ^ 1);
-          mbar_arrive_expect_tx(bar_full(stage), CHUNK_BYTES);
-          tma_bulk_g2s(sbase + SL::W_OFF + stage * CHUNK_BYTES, args.packed + PK_CHUNKS + (size_t)c * CHUNK_BYTES,
-                       CHUNK_BYTES, bar_full(stage));
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        int c = 0;
+        for (int l = 0; l < N_MMA_LAYERS; ++l) {
+          const uint32_t bytes = (uint32_t)layer_n(l) * KCH * 2;
+          for (int i = 0; i < layer_chunks(l); ++i, ++c) {
+            mbar_wait(bar_empty(stage), phase ^ 1);
+            mbar_arrive_expect_tx(bar_full(stage), bytes);
+            tma_bulk_g2s(sbase + SL::W_OFF + stage * SLOT_BYTES, args.packed + PK_CHUNKS + (size_t)c * SLOT_BYTES, bytes,
+                         bar_full(stage));
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_M, NH);
       int stage = 0;
       uint32_t phase = 0, ar_phase = 0;
       for (int g = 0; g < my_groups; ++g) {
         for (int l = 0; l < N_MMA_LAYERS; ++l) {
-          const bool prof = args.prof != nullptr && blockIdx.x == 0 && g == 0;
+          const bool prof = DEBUG && args.prof != nullptr && blockIdx.x == 0 && g == 0;
           if (prof) args.prof[l * 4 + 0] = clock64();
           mbar_wait(bar_aready, ar_phase);  // A operand of layer l written (and accumulators drained)
           ar_phase ^= 1;
           tc_fence_after();
           if (prof) args.prof[l * 4 + 1] = clock64();
-          const int akb = layer_akb(l), nkb = akb + layer_has_e(l), nhn = layer_nh(l);
-          for (int h = 0; h < nhn; ++h) {
-            for (int kbi = 0; kbi < nkb; ++kbi) {
+          const int akb = layer_akb(l), nkb = akb + layer_has_e(l);
+          const uint32_t idesc = make_idesc(TILE_M, layer_n(l));
+          for (int kbi = 0; kbi < nkb; ++kbi) {
+#pragma unroll
+            for (int sub = 0; sub < SUBS; ++sub) {
               mbar_wait(bar_full(stage), phase);
               tc_fence_after();
-              const uint32_t b_addr = sbase + SL::W_OFF + stage * CHUNK_BYTES;
+              const uint32_t b_addr = sbase + SL::W_OFF + stage * SLOT_BYTES;
 #pragma unroll
               for (int t = 0; t < NT; ++t) {
-                const uint32_t a_addr = (kbi < akb) ? (sbase + SL::A_OFF + (t * 4 + kbi) * ABLK_BYTES)
-                                                    : (sbase + SL::E_OFF + t * ABLK_BYTES);
-                const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + h * NH);
+                const uint32_t a_addr = ((kbi < akb) ? (sbase + SL::A_OFF + (t * 4 + kbi) * ABLK_BYTES)
+                                                     : (sbase + SL::E_OFF + t * ABLK_BYTES)) + sub * (KCH * 2);
+                const uint32_t d_addr = tmem_base + (uint32_t)(t * 256);
 #pragma unroll
-                for (int ks = 0; ks < KB / 16; ++ks) {
-                  umma_bf16(d_addr, make_sw128_desc(a_addr + ks * 32), make_sw128_desc(b_addr + ks * 32), idesc,
-                            (kbi > 0 || ks > 0) ? 1u : 0u);
+                for (int ks = 0; ks < KCH / 16; ++ks) {
+                  umma_bf16(d_addr, make_sw128_desc(a_addr + ks * 32), make_sw64_desc(b_addr + ks * 32), idesc,
+                            (kbi > 0 || sub > 0 || ks > 0) ? 1u : 0u);
                 }
               }
               umma_commit(bar_empty(stage));  // frees the weight slot once these MMAs have read it
-              if (kbi == nkb - 1) umma_commit(bar_acc(h));
               if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
           }
+          umma_commit(bar_acc);               // accumulators of layer l complete
           if (prof) args.prof[l * 4 + 2] = clock64();
         }
       }
@@ -346,13 +469,17 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
     const int t = (warp - 2) >> 2;               // tile handled by this warpgroup
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;               // row within the tile == TMEM lane
+    const int etid = threadIdx.x - 64;           // 0 .. 128*NT-1
     uint8_t* a_blk = smem + SL::A_OFF + t * 4 * ABLK_BYTES;
+    uint8_t* a_row = a_blk + (row >> 3) * 1024 + (row & 7) * 128;   // this row inside a SWIZZLE_128B k-block
+    const uint32_t r7s = (uint32_t)(row & 7) << 4;                   // xor mask of the 16-byte unit index
     uint8_t* e_blk = smem + SL::E_OFF + t * ABLK_BYTES;
+    float* vslot = reinterpret_cast<float*>(smem + SL::V_OFF);   // [2][256] fp32
     const float* bias_all = reinterpret_cast<const float*>(args.packed + PK_BIAS);
-    const float4* wsig4 = reinterpret_cast<const float4*>(args.packed + PK_WSIGMA);
-    const float4* wrgb = reinterpret_cast<const float4*>(args.packed + PK_WRGB);
+    const float* wsig_g = reinterpret_cast<const float*>(args.packed + PK_WSIGMA);
+    const float* wrgb_g = reinterpret_cast<const float*>(args.packed + PK_WRGB);
     const float4 headb = __ldg(reinterpret_cast<const float4*>(args.packed + PK_HEADB));
-    uint32_t acc_phase[2] = {0, 0};
+    uint32_t acc_phase = 0;
 
     for (int g = 0; g < my_groups; ++g) {
       const int64_t group = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
@@ -366,67 +493,35 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_aready);
 
-      float sigma_raw = 0.f;
+      EpiOut eo = {0.f, 0.f, 0.f, 0.f};
       for (int l = 0; l < N_MMA_LAYERS; ++l) {
-        const int nhn = layer_nh(l);
-        const float* bias = bias_all + l * 256;
-        float r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
-        // all n-halves of the layer must be complete before the in-place overwrite of the A operand
-        const bool prof = args.prof != nullptr && blockIdx.x == 0 && g == 0 && warp == 2 && lane == 0;
+        const bool prof = DEBUG && args.prof != nullptr && blockIdx.x == 0 && g == 0 && warp == 2 && lane == 0;
         if (prof) args.prof[40 + l * 4 + 0] = clock64();
-        for (int h = 0; h < nhn; ++h) { mbar_wait(bar_acc(h), acc_phase[h]); acc_phase[h] ^= 1; }
+        // stage this layer's bias (slot l&1) and, where a head follows, the head weights (free space of the slots)
+        // while the tensor core is busy.  The leading barrier makes sure no warp is still reading these slots in the
+        // previous layer's epilogue (the head weights reuse the other slot).
+        {
+          epi_bar_sync(128 * NT);
+          float* bs = vslot + (l & 1) * 256;
+          for (int j = etid; j < layer_n(l); j += 128 * NT) bs[j] = __ldg(bias_all + l * 256 + j);
+          if (l == 7) for (int j = etid; j < 256; j += 128 * NT) vslot[j] = __ldg(wsig_g + j);            // slot 0
+          if (l == 9) for (int j = etid; j < 384; j += 128 * NT)                                          // slot 0 + top of slot 1
+              vslot[j < 256 ? j : j + 128] = __ldg(wrgb_g + j);
+          epi_bar_sync(128 * NT);
+        }
+        const float* bias = vslot + (l & 1) * 256;
+        mbar_wait(bar_acc, acc_phase);   // every MMA of the layer done: accumulators final, A operand free
+        acc_phase ^= 1;
         tc_fence_after();
         if (prof) args.prof[40 + l * 4 + 1] = clock64();
-        for (int cg = 0; cg < nhn * 4; ++cg) {  // 32 accumulator columns at a time
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + cg * 32), v);
-          tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cg * 32) + j4);
-            f[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b4.x;
-            f[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b4.y;
-            f[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b4.z;
-            f[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b4.w;
-          }
-          if (layer_relu(l)) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-          if (l == 7) {  // sigma head (Dense_8) on the bf16-rounded trunk output
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w4 = __ldg(wsig4 + cg * 8 + j4);
-              sigma_raw = fmaf(bf16_round(f[4 * j4 + 0]), w4.x, sigma_raw);
-              sigma_raw = fmaf(bf16_round(f[4 * j4 + 1]), w4.y, sigma_raw);
-              sigma_raw = fmaf(bf16_round(f[4 * j4 + 2]), w4.z, sigma_raw);
-              sigma_raw = fmaf(bf16_round(f[4 * j4 + 3]), w4.w, sigma_raw);
-            }
-          }
-          if (l == 9) {  // rgb head (Dense_11) on the bf16-rounded condition-layer output
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float4 w4 = __ldg(wrgb + cg * 32 + j);
-              const float hb = bf16_round(f[j]);
-              r_acc = fmaf(hb, w4.x, r_acc); g_acc = fmaf(hb, w4.y, g_acc); b_acc = fmaf(hb, w4.z, b_acc);
-            }
-          } else {
-            // next layer's A operand: columns cg*32..+31 -> k-block cg/2, 16-byte chunks (cg&1)*4..+3
-            uint8_t* blk = a_blk + (cg >> 1) * ABLK_BYTES;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<uint4*>(blk + sw128_offset(row, (cg & 1) * 32 + c * 8)) =
-                  make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          }
-          if (args.layer_out && live) {
-            uint4* dst = reinterpret_cast<uint4*>(args.layer_out + ((size_t)l * args.n_samples + srow) * 256 + cg * 32);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          }
+        {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+          __nv_bfloat16* dump_row = nullptr;
+          if (DEBUG) dump_row = (args.layer_out && live) ? args.layer_out + ((size_t)l * args.n_samples + srow) * 256 : nullptr;
+          if (l == 7)      epilogue_row<1, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);
+          else if (l == 8) epilogue_row<2, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);
+          else if (l == 9) epilogue_row<3, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);
+          else             epilogue_row<0, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);
         }
         if (l == 8) {
           // condition input for Dense_10: pos_enc(dir, 0, 4) replaces the position encoding (last used by layer 5)
@@ -435,7 +530,7 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
         }
         if (prof) args.prof[40 + l * 4 + 2] = clock64();
         if (l == 9) {
-          if (live) args.raw_out[srow] = make_float4(r_acc + headb.x, g_acc + headb.y, b_acc + headb.z, sigma_raw + headb.w);
+          if (live) args.raw_out[srow] = make_float4(eo.r + headb.x, eo.g + headb.y, eo.b + headb.z, eo.sigma + headb.w);
           tc_fence_before();  // accumulators drained; the next group's layer 0 may overwrite them
         } else {
           tc_fence_before();
@@ -452,15 +547,16 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
   if (warp == 1) tmem_dealloc(tmem_base, 256 * NT);
 }
 
-template <int NT, int NSTAGE>
+template <int NT, int NSTAGE, bool DEBUG>
 static int launch_encmlp(const EncMlpArgs& a0, cudaStream_t st) {
   using SL = SmemLayout<NT, NSTAGE>;
+  static_assert(SL::BYTES <= 232448, "shared-memory budget exceeded");
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  auto kfn = encmlp_kernel<NT, NSTAGE>;
+  auto kfn = encmlp_kernel<NT, NSTAGE, DEBUG>;
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::BYTES);
     if (e != cudaSuccess) { set_error("rnerf_encmlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set[dev] = true;
   }
@@ -469,7 +565,7 @@ static int launch_encmlp(const EncMlpArgs& a0, cudaStream_t st) {
   EncMlpArgs a = a0;
   a.n_groups = (int)((a.n_samples + (int64_t)TILE_M * NT - 1) / ((int64_t)TILE_M * NT));
   const int grid = a.n_groups < n_sm ? a.n_groups : n_sm;
-  kfn<<<grid, 64 + 128 * NT, SL::ALLOC, st>>>(a);
+  kfn<<<grid, 64 + 128 * NT, SL::BYTES, st>>>(a);
   count_launch();
   return check_launch("rnerf_encmlp_fwd");
 }
@@ -504,8 +600,9 @@ static int encmlp_fwd_impl(const void* packed, const float* pos, const float* di
   EncMlpArgs a;
   a.packed = (const uint8_t*)packed; a.pos = pos; a.dir = dir; a.n_samples = n_samples;
   a.raw_out = (float4*)raw_out; a.layer_out = (__nv_bfloat16*)layer_out; a.prof = prof; a.n_groups = 0;
-  if (n_samples <= 148 * 128) return launch_encmlp<1, 8>(a, (cudaStream_t)stream);
-  return launch_encmlp<2, 4>(a, (cudaStream_t)stream);
+  const bool dbg = layer_out != nullptr || prof != nullptr;
+  if (n_samples <= 148 * 128) return dbg ? launch_encmlp<1, 8, true>(a, (cudaStream_t)stream) : launch_encmlp<1, 8, false>(a, (cudaStream_t)stream);
+  return dbg ? launch_encmlp<2, 4, true>(a, (cudaStream_t)stream) : launch_encmlp<2, 4, false>(a, (cudaStream_t)stream);
 }
 
 extern "C" int rnerf_encmlp_fwd(const void* packed, const float* pos, const float* dir, int64_t n_samples, float* raw_out,

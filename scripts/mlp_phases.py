@@ -20,3 +20,4 @@ for l in range(10):
     m = pr[0, l]; e = pr[1, l]
     print(f"{l:5d} | {m[1]-m[0]:8d} {m[2]-m[1]:8d} | {e[1]-e[0]:8d} {e[2]-e[1]:8d} | mma_start {m[0]-t0:8d} epi_done {e[2]-t0:8d}")
 print("group total cycles:", (pr[1, 9, 2] - t0).item())
+
