@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Generate golden vectors by EXECUTING THE REFERENCE'S OWN SOURCE FILES (/root/reference/rnerf/*.py, unmodified)
+under the numpy-backed jax/flax shim in tests/golden/_jaxshim.  Run in the build container only:
+
+    python tests/golden/make_reference_goldens.py
+
+writes tests/golden/ref_*.npz.  tests/test_oracle_vs_reference.py then pins the CPU oracle (oracle/rnerf_oracle.py)
+against these files.  The shim reproduces jax/flax *semantics* (32-bit types, Flax parameter naming, nn.scan,
+.at[].set, lax.fori_loop, the positional-argument quirk of jnp.nan_to_num); random draws are recorded and stored so
+the oracle receives the same jitter / u / noise.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_jaxshim"))
+sys.path.insert(0, "/root/reference")
+np.seterr(all="ignore")
+
+import jax  # noqa: E402  (the shim)
+import jax.numpy as jnp  # noqa: E402
+from rnerf import eikonal_utils, ior_utils, math_utils, model_utils, models, utils  # noqa: E402
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+def flatten(tree, prefix=""):
+    out = {}
+    for k, v in tree.items():
+        if isinstance(v, dict):
+            out.update(flatten(v, prefix + k + "/"))
+        else:
+            out[prefix + k] = np.asarray(v)
+    return out
+
+
+def sphere_grid(G, extent, radius, center=(0, 0, 0)):
+    lin = np.linspace(-extent, extent, G)
+    X, Y, Z = np.meshgrid(lin, lin, lin, indexing="ij")
+    r2 = (X - center[0]) ** 2 + (Y - center[1]) ** 2 + (Z - center[2]) ** 2
+    return np.where(r2 < radius ** 2, 1.33, 1.0).reshape(-1, 1)
+
+
+def rays_towards_box(B, seed, radius=4.0, extent=0.9, shift=(0, 0, 0)):
+    rs = np.random.RandomState(seed)
+    o = rs.normal(size=(B, 3)); o = o / np.linalg.norm(o, axis=-1, keepdims=True) * radius + np.array(shift)
+    tgt = rs.uniform(-extent, extent, size=(B, 3)) + np.array(shift)
+    d = tgt - o; d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    return f32(o), f32(d)
+
+
+def args_for(config, **kw):
+    a = types.SimpleNamespace(
+        net_activation="relu", rgb_activation="sigmoid", sigma_activation="softplus", sh_deg=-1, use_viewdirs=True,
+        num_rgb_channels=3, num_sigma_channels=1, min_deg_point=0, max_deg_point=10, deg_view=4, num_coarse_samples=64,
+        num_fine_samples=128, near=2.0, far=6.0, noise_std=None, white_bkgd=False, net_depth=8, net_width=256,
+        net_depth_condition=1, net_width_condition=128, skip_layer=4, lindisp=False, legacy_posenc_order=False,
+        stage="radiance", num_path_samples=12, use_fine_sparsity=False, use_online_sparsity=False, sh_direnc_deg=-1,
+        config=config, randomized=False)
+    a.__dict__.update(kw)
+    return a
+
+
+def run_model(name, config, G, extent, radius, center, ws, sigma, B, seed, near, far, P, ri_scale, bd_cut_dist=None,
+              randomized=False, shift=(0, 0, 0), bias_scale=0.1):
+    ndim, nmin, nmax = [G] * 3, [-extent] * 3, [extent] * 3
+    data = sphere_grid(G, extent, radius, center)
+    grid = ior_utils.conv3d_normal((data - 1.0) * ri_scale / 0.33 + 1.0, ndim, ws, sigma)       # train.py:223
+    o, d = rays_towards_box(B, seed, shift=shift)
+    rays = utils.Rays(origins=jnp.array(o), directions=jnp.array(d), viewdirs=jnp.array(d), radii=jnp.array(np.ones((B, 1))))
+    args = args_for(config, near=near, far=far, num_path_samples=P, randomized=randomized)
+    if bd_cut_dist is not None:
+        # gin would bind NerfModel.bd_cut_dist; without gin the class default is patched for this run
+        models.NerfModel.bd_cut_dist = bd_cut_dist
+        models.NerfModel.__dataclass_fields__["bd_cut_dist"].default = bd_cut_dist
+    example = {"rays": utils.namedtuple_map(lambda x: x[None], rays)}
+    import flax.linen as _nn
+    _nn._CTX["key"] = 0          # same parameter draw for every scene: the 5 MB weight file is stored once
+    model, variables = models.construct_nerf(jax.random.PRNGKey(seed), example, args, ndim=ndim, nmin=nmin, nmax=nmax,
+                                             grid=grid)
+    if bd_cut_dist is not None:
+        models.NerfModel.bd_cut_dist = None
+        models.NerfModel.__dataclass_fields__["bd_cut_dist"].default = None
+        if model.bd_cut_dist != bd_cut_dist:
+            object.__setattr__(model, "bd_cut_dist", bd_cut_dist)
+    # non-zero biases so every term is exercised (Flax initialises them to zero)
+    rs = np.random.RandomState(1234)
+    for mlp in ("coarse_mlp", "fine_mlp", "bkgd_mlp"):
+        for dn in variables["params"][mlp].values():
+            dn["bias"] = jnp.array(rs.uniform(-bias_scale, bias_scale, size=dn["bias"].shape))
+    jax.random.DRAWS.clear()
+    ret, loss_sp = model.apply(variables, jax.random.PRNGKey(11), jax.random.PRNGKey(12), rays, randomized)
+    draws = list(jax.random.DRAWS)
+    jitter_off = [v for k, v in draws if k == "randint"][0]
+    out = {"grid": f32(grid), "ndim": np.array(ndim), "nmin": np.array(nmin), "nmax": np.array(nmax),
+           "origins": o, "viewdirs": d, "near": near, "far": far, "num_path_samples": P, "config": config,
+           "jitter": np.arange(0, 64 * P, P) + np.asarray(jitter_off), "loss_sp": f32(loss_sp),
+           "bd_cut_dist": -1.0 if bd_cut_dist is None else bd_cut_dist}
+    if randomized:
+        un = [v for k, v in draws if k == "uniform"][0]
+        out["u_noise"] = f32(un)
+    for lvl, tup in enumerate(ret):
+        for nm, v in zip(("rgb", "distance", "acc", "trans", "trans_rgb_bkgd"), tup):
+            out[f"ret{lvl}_{nm}"] = f32(v)
+    # the bent path itself (PathSampler), through the model's own parameters
+    ps = eikonal_utils.PathSampler(near=near, far=far, stage="radiance", num_samples=64 * P,
+                                   step_size=(far - near) / (64 * P - 1), ndim=ndim, nmin=nmin, nmax=nmax, grid=grid)
+    pos, dirs, dist, idn, idg = ps.apply({"params": variables["params"]["path_sampler"]}, rays.origins, rays.viewdirs, 1.0)
+    out.update(path_pos=f32(pos), path_dir=f32(dirs), path_dist=f32(dist), path_n=f32(idn), path_grad=f32(idg))
+    params = {k: f32(v) for k, v in flatten(variables["params"]).items()}
+    ppath = os.path.join(HERE, "ref_params.npz")
+    if os.path.exists(ppath):
+        old = np.load(ppath)
+        assert all(np.array_equal(old[k], params[k]) for k in params), "parameter draw changed between scenes"
+    else:
+        np.savez_compressed(ppath, **params)
+    np.savez_compressed(os.path.join(HERE, f"ref_model_{name}.npz"), **out)
+    print(name, "rgb fine mean", out["ret1_rgb"].mean(), "bend", np.abs(out["path_dir"][:, -1] - d).max())
+
+
+def run_functions():
+    rs = np.random.RandomState(0)
+    out = {}
+    # encodings (rnerf/model_utils.py:187-245)
+    x = f32(rs.uniform(-3, 3, size=(5, 7, 3)))
+    out["enc_x"] = x
+    out["pos_enc_10"] = f32(model_utils.pos_enc(jnp.array(x), 0, 10))
+    out["pos_enc_4"] = f32(model_utils.pos_enc(jnp.array(x), 0, 4))
+    out["pos_enc_4_legacy"] = f32(model_utils.pos_enc(jnp.array(x), 0, 4, True))
+    out["annealed_enc_alpha3p5"] = f32(model_utils.annealed_pos_enc(jnp.array(x), 0, 10, 3.5))
+    # compositing (rnerf/model_utils.py:247-309)
+    B, Ns = 9, 40
+    rgb = f32(rs.uniform(size=(B, Ns, 3))); sig = f32(rs.uniform(size=(B, Ns, 1)) * 6); sig[0] = 0
+    t = f32(2 + np.sort(rs.uniform(size=(B, Ns)) * 4, axis=-1)); dirs = f32(rs.normal(size=(B, Ns, 3)))
+    bk = f32(rs.uniform(size=(B, 3))); mask = f32(rs.uniform(size=(B, Ns)) > 0.4)
+    out.update(vr_rgb=rgb, vr_sigma=sig, vr_t=t, vr_dirs=dirs, vr_bkgd=bk, vr_mask=mask)
+    for tag, kw in (("a", dict(white_bkgd=False, rgb_bkgd=jnp.array(bk))), ("b", dict(white_bkgd=True, rgb_bkgd=None)),
+                    ("c", dict(white_bkgd=False, rgb_bkgd=jnp.array(bk), mask_bbox=jnp.array(mask)))):
+        r = model_utils.volumetric_rendering(jnp.array(rgb), jnp.array(sig), jnp.array(t), jnp.array(dirs), **kw)
+        for nm, v in zip(("comp", "dist", "acc", "w", "alpha", "trans", "trb"), r):
+            out[f"vr_{tag}_{nm}"] = f32(v)
+    # pdf sampling (rnerf/model_utils.py:312-374)
+    B, Nb, N = 6, 63, 128
+    bins = f32(2 + np.sort(rs.uniform(size=(B, Nb)) * 4, axis=-1)); w = f32(rs.uniform(size=(B, Nb - 1)) ** 3 + 0.01)
+    w[0] = 0.0
+    out.update(pdf_bins=bins, pdf_w=w)
+    out["pdf_det"] = f32(model_utils.sorted_piecewise_constant_pdf(None, jnp.array(bins), jnp.array(w), N, False))
+    jax.random.DRAWS.clear()
+    out["pdf_rand"] = f32(model_utils.sorted_piecewise_constant_pdf(jax.random.PRNGKey(3), jnp.array(bins), jnp.array(w), N, True))
+    out["pdf_rand_noise"] = f32(jax.random.DRAWS[0][1])
+    # grid ops (rnerf/ior_utils.py:165-223, 327-363)
+    G = 10
+    ndim, nmin, nmax = [G, G, G], [-1.5, -1.0, -0.5], [1.5, 2.0, 0.75]
+    g0 = f32(1 + 0.5 * rs.uniform(size=(G ** 3, 1)))
+    out["grid_in"] = g0
+    out.update(grid_ndim=np.array(ndim), grid_nmin=np.array(nmin), grid_nmax=np.array(nmax))
+    for ws, s in ((3, 1.0), (5, 3.0)):
+        out[f"blur_{ws}"] = f32(ior_utils.conv3d_normal(g0, ndim, ws, s))
+    vm = ior_utils.VoxMLP(ndim=ndim, nmin=nmin, nmax=nmax, grid=jnp.array(g0))
+    vars_ = vm.init(jax.random.PRNGKey(0), jnp.array(f32(rs.uniform(-1, 1, size=(4, 3)))))
+    pts = f32(rs.uniform(-2.0, 2.5, size=(300, 3)))
+    out["lookup_pts"] = pts
+    out["grad_table"] = f32(vm.apply(vars_, method=vm._compute_grad))
+    out["lookup"] = f32(vm.apply(vars_, jnp.array(pts), method=vm._linear3))
+    # "all"-stage march: so3 MLP rotation of grad n inside every step (rnerf/eikonal_utils.py:34-39, ior_utils.py:282-312)
+    G = 16
+    ndim, nmin, nmax = [G] * 3, [-1.5] * 3, [1.5] * 3
+    grid = ior_utils.conv3d_normal((sphere_grid(G, 1.5, 0.8) - 1.0) * 0.5 / 0.33 + 1.0, ndim, 3, 1.0)
+    o, d = rays_towards_box(12, 5)
+    S = 96
+    ps = eikonal_utils.PathSampler(near=2.0, far=6.0, stage="all", num_samples=S, step_size=4.0 / (S - 1), ndim=ndim,
+                                   nmin=nmin, nmax=nmax, grid=grid)
+    v = ps.init(jax.random.PRNGKey(1), jnp.array(o), jnp.array(d), 0.7)
+    so3 = v["params"]["scan"]["idx_model"]["so3_mlp"]
+    so3["Dense_4"]["kernel"] = jnp.array(f32(rs.normal(size=so3["Dense_4"]["kernel"].shape) * 0.3))   # visible rotation
+    pos, dirs, dist, idn, idg = ps.apply(v, jnp.array(o), jnp.array(d), 0.7)
+    out.update(all_grid=f32(grid), all_o=o, all_d=d, all_pos=f32(pos), all_dir=f32(dirs), all_dist=f32(dist), all_grad=f32(idg))
+    for k, val in flatten(so3).items():
+        out["all_so3:" + k] = f32(val)
+    # math helpers (rnerf/math_utils.py:6-20)
+    z = f32(rs.normal(size=(20, 3))); z[0] = 0
+    out["mh_x"] = z
+    out["mh_normalize"] = f32(math_utils.safe_l2_normalize(jnp.array(z)))
+    out["mh_log"] = f32(math_utils.safe_log(jnp.array(np.abs(z))))
+    np.savez_compressed(os.path.join(HERE, "ref_functions.npz"), **out)
+    print("functions ok")
+
+
+if __name__ == "__main__":
+    if os.path.exists(os.path.join(HERE, "ref_params.npz")):
+        os.remove(os.path.join(HERE, "ref_params.npz"))
+    run_functions()
+    # config A shape (example.gin/yaml): near/far 2/6, P=12, blur 3/1, IoR scale 0.5
+    run_model("example", "example", G=20, extent=1.5, radius=0.8, center=(0, 0, 0), ws=3, sigma=1.0, B=24, seed=3,
+              near=2.0, far=6.0, P=12, ri_scale=0.5)
+    # training-mode sampling (randomized=True): stratified u
+    run_model("example_rand", "example", G=20, extent=1.5, radius=0.8, center=(0, 0, 0), ws=3, sigma=1.0, B=16, seed=4,
+              near=2.0, far=6.0, P=12, ri_scale=0.5, randomized=True)
+    # config D shape (ball.gin/yaml): near/far 0.2/12, P=24, blur 5/3, bd_cut_dist passes with the hard-coded ball box
+    run_model("ball", "ball", G=16, extent=2.0, radius=1.0, center=(0, 1.036, 0), ws=5, sigma=3.0, B=16, seed=5,
+              near=0.2, far=12.0, P=24, ri_scale=0.5, bd_cut_dist=6.0, shift=(0, 1.0, 0))
