@@ -3,11 +3,15 @@ rendering hot path.  TEST INFRASTRUCTURE ONLY -- never imported by the product p
 
 Every function cites the reference lines (relative to /root/reference) it follows.
 
-PINNING STATUS: the reference ships no tests / golden vectors for this path
-and its arithmetic lives in jax==0.2.22 / flax==0.3.6, which are not installable here.  The oracle is
-pinned instead by executing the reference's *own source files* under a numpy-backed jax/flax shim
-(tests/golden/make_reference_goldens.py -> tests/golden/ref_*.npz, checked in
-tests/test_oracle_vs_reference.py) and by analytic known-answer tests (tests/test_oracle_kat.py).
+PINNING STATUS: PINNED.  The reference ships no tests / golden vectors for this path and
+its arithmetic lives in jax==0.2.22 / flax==0.3.6 (requirements.txt:10,22,23), which are not installable here.
+The oracle is pinned against outputs of the reference's *own source files* (rnerf/models.py, model_utils.py,
+eikonal_utils.py, ior_utils.py, math_utils.py -- imported unmodified from /root/reference) executed under a
+numpy-backed jax/flax shim that reproduces JAX's 32-bit type semantics, Flax parameter naming and nn.scan
+(tests/golden/make_reference_goldens.py -> tests/golden/ref_*.npz).  tests/test_oracle_vs_reference.py checks the
+oracle against those fixtures (bent path bit-exact, full NerfModel.__call__ within fp32 summation-order
+tolerance, incl. the bd_cut_dist passes and the "all"-stage so3 rotation); tests/test_oracle_kat.py adds analytic
+known-answer tests.  What the shim cannot pin is XLA's own code generation (FMA contraction, reduction order).
 
 Conventions
   * all arrays are torch CPU tensors; `dt` is torch.float32 (default) or torch.float64.

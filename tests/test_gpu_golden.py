@@ -1,0 +1,82 @@
+"""CUDA path vs the committed golden fixtures, i.e. vs outputs of the reference's own source files
+(tests/golden/make_reference_goldens.py).  Through the C ABI; reads only tests/golden/*.npz."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import rnerf_test_helpers as H
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _params_cuda():
+    prm = np.load(os.path.join(G, "ref_params.npz"))
+    tree = {}
+    for k in prm.files:
+        node = tree
+        parts = k.split("/")
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+        node[parts[-1]] = torch.from_numpy(prm[k]).cuda().contiguous()
+    return {"params": tree}
+
+
+@pytest.mark.parametrize("name", ["example", "example_rand", "ball"])
+def test_model_apply_vs_reference_golden(cuda_lib, name):
+    from samplenerfro_b200 import models, ops, utils
+    d = np.load(os.path.join(G, f"ref_model_{name}.npz"))
+    ndim, nmin, nmax = d["ndim"].tolist(), d["nmin"].tolist(), d["nmax"].tolist()
+    bd = float(d["bd_cut_dist"])
+    args = utils.Flags(config=str(d["config"]), near=float(d["near"]), far=float(d["far"]),
+                       num_path_samples=int(d["num_path_samples"]), white_bkgd=False, use_online_sparsity=False)
+    if bd >= 0:
+        args.gin_bindings = {"NerfModel": {"bd_cut_dist": bd}}
+    model, _ = models.construct_nerf(0, None, args, ndim, nmin, nmax, d["grid"])
+    variables = _params_cuda()
+    o = torch.from_numpy(d["origins"]).cuda(); v = torch.from_numpy(d["viewdirs"]).cuda()
+    rays = utils.Rays(o, v, v, torch.ones(o.shape[0], 1, device="cuda"))
+    randomized = "u_noise" in d.files
+    u = None
+    if randomized:
+        noise = torch.from_numpy(d["u_noise"])
+        nf = noise.shape[-1]
+        u = torch.clamp(torch.arange(nf) * (1 / nf) + noise, max=1.0 - float(np.finfo(np.float32).eps)).float()
+    ret, loss_sp, dbg = model.apply(variables, 0, 0, rays, randomized, jitter=torch.from_numpy(d["jitter"]).int(), u=u,
+                                    debug=True)
+    # bent sample positions: bit-identical to the reference's nn.scan
+    for nm, key in (("ray_pos", "path_pos"), ("ray_dir", "path_dir"), ("ray_dist", "path_dist"), ("idx_grad", "path_grad")):
+        assert np.array_equal(dbg[nm].cpu().numpy(), d[key]), nm
+    assert np.array_equal(dbg["idx_data"].cpu().numpy(), d["path_n"])
+    for lvl in (0, 1):
+        rgb, dist, acc, trans, trb = [x.cpu() for x in ret[lvl]]
+        assert H.psnr(rgb, torch.from_numpy(d[f"ret{lvl}_rgb"])) >= 50.0, H.psnr(rgb, torch.from_numpy(d[f"ret{lvl}_rgb"]))
+        assert H.psnr(trb, torch.from_numpy(d[f"ret{lvl}_trans_rgb_bkgd"])) >= 50.0
+        assert np.abs(acc.numpy() - d[f"ret{lvl}_acc"]).max() < 5e-3
+        assert np.abs(trans.numpy() - d[f"ret{lvl}_trans"]).max() < 5e-3
+        assert np.abs(dist.numpy() - d[f"ret{lvl}_distance"]).max() < 3e-2
+
+
+def test_kernels_vs_reference_function_goldens(cuda_lib):
+    from samplenerfro_b200 import ops
+    fn = np.load(os.path.join(G, "ref_functions.npz"))
+    C = lambda k: torch.from_numpy(fn[k]).cuda().contiguous()
+    ndim, nmin, nmax = fn["grid_ndim"].tolist(), fn["grid_nmin"].tolist(), fn["grid_nmax"].tolist()
+    table = ops.grid_table(C("grid_in"), ndim, nmin, nmax)
+    assert np.array_equal(table[:, 1:].cpu().numpy(), fn["grad_table"])                       # _compute_grad
+    assert np.array_equal(ops.grid_lookup(table, ndim, nmin, nmax, C("lookup_pts")).cpu().numpy(), fn["lookup"])  # _linear3
+    assert np.abs(ops.grid_blur(C("grid_in"), ndim, 3, 1.0).cpu().numpy() - fn["blur_3"]).max() < 2e-6
+    assert np.abs(ops.grid_blur(C("grid_in"), ndim, 5, 3.0).cpu().numpy() - fn["blur_5"]).max() < 2e-6
+    # volumetric_rendering on pre-activated inputs: invert the activations to feed the fused kernel
+    rgb, sig = torch.from_numpy(fn["vr_rgb"]), torch.from_numpy(fn["vr_sigma"])
+    raw_rgb = torch.logit(((rgb + 0.001) / 1.002).double().clamp(1e-9, 1 - 1e-9)).float()
+    raw_sig = torch.where(sig > 0, torch.log(torch.expm1(sig.double().clamp_min(1e-30))).float() + 1.0, torch.full_like(sig, -80.0))
+    bk = torch.from_numpy(fn["vr_bkgd"]); raw_bk = torch.logit(((bk + 0.001) / 1.002).double()).float()
+    raw = torch.cat([raw_rgb, raw_sig], -1).cuda().contiguous()
+    for tag, kw in (("a", dict(bkgd_raw=raw_bk.cuda())), ("c", dict(bkgd_raw=raw_bk.cuda(), mask=C("vr_mask")))):
+        o = ops.composite_fwd(raw, C("vr_t"), C("vr_dirs"), want_alpha=True, **kw)
+        for nm, key in (("comp_rgb", "comp"), ("acc", "acc"), ("weights", "w"), ("alpha", "alpha"), ("trans", "trans"),
+                        ("trans_rgb_bkgd", "trb"), ("distance", "dist")):
+            assert np.abs(o[nm].cpu().numpy() - fn[f"vr_{tag}_{key}"]).max() < 2e-5, (tag, nm)
