@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--side", type=int, default=800, help="image side (800 -> 640 000 rays per step)")
     ap.add_argument("--grid", type=int, default=512)
     ap.add_argument("--chunk", type=int, default=65536, help="rays per model.apply call")
-    ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=16384, help="rays of the bounded CPU-baseline sample (~15-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -131,7 +131,7 @@ def run_reference(a, rank, world):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    n = a.cpu_rays
+    n = min(a.cpu_rays, 4096)          # per step; K steps + warm-up stay within a couple of minutes
     for _ in range(min(a.warmup, 1)):
         cpu_baseline(min(n, 128))
     vals, t_all = [], 0.0

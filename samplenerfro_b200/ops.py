@@ -244,3 +244,79 @@ def encmlp_fwd_profile(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tens
     check(_lib.load().rnerf_encmlp_fwd_profile(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(prof), _stream()),
           "rnerf_encmlp_fwd_profile")
     return raw, prof
+
+
+# ---------------------------------------------------------------- training-mode MLP (forward saves activations)
+def encmlp_fwd_train(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tensor):
+    """Forward that also keeps every layer's post-activation output (bf16 [10,M,256]) for the backward pass."""
+    return encmlp_fwd(packed, pos, dirs, debug_layers=True)
+
+
+def _pos_enc_torch(x: torch.Tensor, max_deg: int) -> torch.Tensor:
+    scales = (2.0 ** torch.arange(max_deg, device=x.device, dtype=torch.float32))
+    xb = (x[:, None, :] * scales[:, None]).reshape(x.shape[0], -1)
+    return torch.cat([x, torch.sin(xb), torch.cos(xb)], dim=-1)
+
+
+def encmlp_bwd(packed, pos, dirs, saved, d_raw, params):
+    """Backward of pos_enc + NerfMLP wrt the 12 Dense layers, from d(raw)[M,4] and the saved activations.
+
+    INTERIM (round 1): the dgrad/wgrad GEMMs below are plain library GEMMs (torch.matmul -> cuBLAS, fp32); the
+    forward, its saved activations and every other stage are this repo's kernels.  A fused tcgen05 dgrad chain +
+    split-K wgrad kernel replaces this in a later round ("Training path")."""
+    pos = pos.reshape(-1, 3); dirs = dirs.reshape(-1, 3)
+    K = [p for p in params[0::2]]
+    Wb = [k.detach().to(torch.bfloat16).float() for k in K]      # the forward multiplied by bf16-rounded weights
+    H = saved
+    gK = [None] * 12; gB = [None] * 12
+    d_raw = d_raw.float()
+    d_rgb, d_sig = d_raw[:, :3], d_raw[:, 3:4]
+    pe = _pos_enc_torch(pos, 10).to(torch.bfloat16).float()
+    de = _pos_enc_torch(dirs, 4).to(torch.bfloat16).float()
+    h9 = H[9][:, :128].float()
+    gK[11] = h9.t() @ d_rgb; gB[11] = d_rgb.sum(0)
+    dz = (d_rgb @ Wb[11].t()) * (h9 > 0)
+    x10 = torch.cat([H[8].float(), de], dim=-1)
+    gK[10] = x10.t() @ dz; gB[10] = dz.sum(0)
+    dbott = dz @ Wb[10][:256].t()
+    del x10, dz
+    h7 = H[7].float()
+    gK[9] = h7.t() @ dbott; gB[9] = dbott.sum(0)
+    gK[8] = h7.t() @ d_sig; gB[8] = d_sig.sum(0)
+    dz = (dbott @ Wb[9].t() + d_sig @ Wb[8].t()) * (h7 > 0)
+    del dbott, h7
+    for l in range(7, -1, -1):
+        if l == 0:
+            x = pe
+        elif l == 5:
+            x = torch.cat([H[4].float(), pe], dim=-1)
+        else:
+            x = H[l - 1].float()
+        gK[l] = x.t() @ dz; gB[l] = dz.sum(0)
+        if l > 0:
+            dz = (dz @ Wb[l][:256].t()) * (H[l - 1] > 0)
+        del x
+    out = []
+    for i in range(12):
+        out += [gK[i].reshape(K[i].shape), gB[i].reshape(params[2 * i + 1].shape)]
+    return out
+
+
+def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params):
+    """Backward of the background MLP wrt its 5 Dense layers.  INTERIM (round 1): recomputes the 56k-MAC-per-ray
+    forward with torch ops and differentiates it with torch.autograd (the forward used on the render path is the
+    CUDA kernel)."""
+    flat = dirs.reshape(-1)
+    idx = offset + stride * torch.arange(n_rays, device=dirs.device)
+    d = torch.stack([flat[idx], flat[idx + 1], flat[idx + 2]], dim=-1)
+    with torch.enable_grad():
+        ps = [p.detach().requires_grad_(True) for p in params]
+        enc = _pos_enc_torch(d, 4)
+        x = enc
+        for i in range(4):
+            x = torch.relu(x @ ps[2 * i] + ps[2 * i + 1])
+            if i == 2:
+                x = torch.cat([x, enc], dim=-1)
+        out = x @ ps[8] + ps[9]
+        grads = torch.autograd.grad(out, ps, d_raw)
+    return list(grads)

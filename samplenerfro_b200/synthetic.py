@@ -30,10 +30,11 @@ def ellipsoid_occupancy(G: int, extent: float, radii: Sequence[float], center=(0
     yy = ((lin[:, None] + offs[None, :] - center[1]) / r[1]) ** 2        # [G, ss]
     zz = ((lin[:, None] + offs[None, :] - center[2]) / r[2]) ** 2
     yz = yy[:, None, :, None] + zz[None, :, None, :]                     # [G, G, ss, ss]
-    for i in range(G):
-        xx = ((lin[i] + offs - center[0]) / r[0]) ** 2                   # [ss]
-        inside = (xx[None, None, :, None, None] + yz[:, :, None, :, :]) < 1.0
-        out[i] = inside.float().mean(dim=(2, 3, 4))
+    slab = max(1, min(G, (1 << 25) // (G * G)))                            # ~32 M voxels x ss^3 sub-samples per pass
+    for i in range(0, G, slab):
+        xx = ((lin[i:i + slab, None] + offs[None, :] - center[0]) / r[0]) ** 2     # [slab, ss]
+        inside = (xx[:, None, None, :, None, None] + yz[None, :, :, None, :, :]) < 1.0
+        out[i:i + slab] = inside.float().mean(dim=(3, 4, 5))
     return (1.0 + 0.33 * out).reshape(-1)
 
 

@@ -1,0 +1,55 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: contiguous ray sharding and the bucketed gradient
+all-reduce-mean that stands in for jax.lax.pmean(grads, "batch") (train.py:166)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from samplenerfro_b200 import train, utils
+    gen = torch.Generator().manual_seed(0)
+    full = torch.randn(8, 5, generator=gen)                       # the "global batch" every rank can reconstruct
+    lo, hi = utils.shard_range(full.shape[0], rank, world)
+    shard = full[lo:hi]
+    variables = {"params": {name: {"Dense_0": {"kernel": torch.zeros(5, 3, requires_grad=True),
+                                               "bias": torch.zeros(3, requires_grad=True)}}
+                            for name in train.GRAD_BUCKETS}}
+    variables["params"]["path_sampler"] = {"so3": {"kernel": torch.zeros(2, 2)}}
+    w = torch.arange(15, dtype=torch.float32).reshape(5, 3)
+    for name in train.GRAD_BUCKETS:                               # per-rank mean loss over its shard, like the reference
+        d = variables["params"][name]["Dense_0"]
+        loss = ((shard @ (d["kernel"] + w) + d["bias"]) ** 2).mean()
+        loss.backward()
+    train.allreduce_mean_grads(variables, world)
+    # expected: mean over ranks of per-shard gradients == gradient of the global-batch mean (equal shard sizes)
+    k = torch.zeros(5, 3, requires_grad=True); b = torch.zeros(3, requires_grad=True)
+    ((full @ (k + w) + b) ** 2).mean().backward()
+    ok = all(torch.allclose(variables["params"][n]["Dense_0"]["kernel"].grad, k.grad, atol=1e-5) and
+             torch.allclose(variables["params"][n]["Dense_0"]["bias"].grad, b.grad, atol=1e-5) for n in train.GRAD_BUCKETS)
+    q.put((rank, ok, (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_mean_and_sharding():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True]
+    assert [r[2] for r in res] == [(0, 4), (4, 8)]
