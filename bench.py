@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--side", type=int, default=800, help="image side (800 -> 640 000 rays per step)")
     ap.add_argument("--grid", type=int, default=512)
-    ap.add_argument("--chunk", type=int, default=65536, help="rays per model.apply call")
+    ap.add_argument("--chunk", type=int, default=128000, help="rays per model.apply call (5 chunks per 800x800 frame; one resident wave of the march kernel)")
     ap.add_argument("--cpu-rays", type=int, default=16384, help="rays of the bounded CPU-baseline sample (~15-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -17,9 +17,11 @@
  *     to fp32 at the same point the reference rounds them.
  *
  * Path record ("bent sample"): 12 floats per (ray, march step), [B][S][12]:
- *     0..2 ray_pos   3 ray_dist   4..6 ray_dir (safe-l2-normalised)   7 idx_data (n)
- *     8..10 idx_grad (grad n)     11 |v| (safe norm of the un-normalised direction state)
- *   i.e. the five arrays PathSampler.__call__ returns (rnerf/eikonal_utils.py:118-124), interleaved.
+ *     0..2 ray_pos   3 ray_dist   4..6 direction state v (UN-normalised)   7 idx_data (n)
+ *     8..10 idx_grad (grad n)     11 unused (0)
+ *   i.e. the arrays PathSampler.__call__ returns (rnerf/eikonal_utils.py:118-124), interleaved; ray_dir =
+ *   safe_l2_normalize(v) (rnerf/eikonal_utils.py:113) is applied by the readers (rnerf_select, rnerf_resample,
+ *   rnerf_path_dirs) to the records they use, with the same arithmetic, instead of at every march step.
  */
 #ifndef RNERF_B200_H_
 #define RNERF_B200_H_
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 1
+#define RNERF_ABI_VERSION 2
 #define RNERF_PATH_STRIDE 12
 
 #define RNERF_E_NULL   (-1)  /* null pointer */
@@ -51,15 +53,26 @@ int rnerf_grid_blur(const float* n_in, float* n_out, const int ndim_host[3], int
 int rnerf_grid_table(const float* n, const int ndim_host[3], const double nmin_host[3], const double nmax_host[3],
                      float* table, void* stream);
 
+/* ---- (no reference counterpart) brick map for the march: bricks[nbx*nby*nbz] (8^3-voxel bricks, x slowest) holds
+ * the common n of a homogeneous brick (all corners bit-equal, grad n == 0) or NaN.  Purely an access-skipping aid:
+ * lookups give bit-identical results with or without it. */
+int64_t rnerf_grid_brick_count(const int ndim_host[3]);
+int rnerf_grid_bricks(const float* table, const int ndim_host[3], float* bricks, void* stream);
+
 /* ---- a3: rnerf/ior_utils.py:188-223 VoxMLP._linear3 -- out[N][4] */
 int rnerf_grid_lookup(const float* table, const int ndim_host[3], const double nmin_host[3],
                       const double nmax_host[3], const float* pts, int64_t n_pts, float* out, void* stream);
 
 /* ---- a5/a6: rnerf/eikonal_utils.py:30-49,101-124 OneEikonalStep + PathSampler (radiance stage) ----
  * step_size = (far - near) / (S - 1) (rnerf/models.py:121-122).  path: [B][S][12] records. */
-int rnerf_march_fwd(const float* table, const int ndim_host[3], const double nmin_host[3],
-                    const double nmax_host[3], const float* origins, const float* viewdirs, int64_t n_rays,
-                    double near, double far, int n_steps, float* path, void* stream);
+int rnerf_march_fwd(const float* table, const float* bricks /* from rnerf_grid_bricks, or NULL */,
+                    const int ndim_host[3], const double nmin_host[3], const double nmax_host[3],
+                    const float* origins, const float* viewdirs, int64_t n_rays, double near, double far, int n_steps,
+                    float* path, void* stream);
+
+/* ray_dir[B][S][3] = safe_l2_normalize(v) of every record: the `ray_dir` array of PathSampler.__call__
+ * (rnerf/eikonal_utils.py:113), for callers that want the whole bent path (extract_mesh.py:178). */
+int rnerf_path_dirs(const float* path, int64_t n_rays, int n_steps, float* ray_dir, void* stream);
 
 /* ---- a7: rnerf/models.py:240-247 coarse selection; jitter[Nc] int32 march-step indices ---- */
 int rnerf_select(const float* path, int64_t n_rays, int n_steps, const int32_t* jitter, int n_coarse,

@@ -29,8 +29,11 @@ SIGNATURES = {
                                    C.c_void_p]),
     "rnerf_grid_lookup": (C.c_int, [c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                     c_i64, c_f32p, C.c_void_p]),
-    "rnerf_march_fwd": (C.c_int, [c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
+    "rnerf_grid_brick_count": (C.c_int64, [C.POINTER(C.c_int)]),
+    "rnerf_grid_bricks": (C.c_int, [c_f32p, C.POINTER(C.c_int), c_f32p, C.c_void_p]),
+    "rnerf_march_fwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                   c_f32p, c_i64, C.c_double, C.c_double, C.c_int, c_f32p, C.c_void_p]),
+    "rnerf_path_dirs": (C.c_int, [c_f32p, c_i64, C.c_int, c_f32p, C.c_void_p]),
     "rnerf_select": (C.c_int, [c_f32p, c_i64, C.c_int, C.c_void_p, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_encmlp_packed_bytes": (C.c_size_t, []),
     "rnerf_encmlp_pack": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
@@ -68,8 +71,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rnerf_abi_version() != 1:
-        raise RnerfError(f"ABI version mismatch: library reports {lib.rnerf_abi_version()}, binding expects 1")
+    if lib.rnerf_abi_version() != 2:
+        raise RnerfError(f"ABI version mismatch: library reports {lib.rnerf_abi_version()}, binding expects 2")
     _lib = lib
     return lib
 

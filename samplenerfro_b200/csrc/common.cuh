@@ -38,6 +38,10 @@ struct GridGeom {
   float two_ndelta[3];  // fp32(2 * ndelta_double)  (rnerf/ior_utils.py:169-171)
 };
 
+static inline bool grid_fits_int32(const int ndim[3]) {
+  return ndim[0] > 0 && ndim[1] > 0 && ndim[2] > 0 && (double)ndim[0] * ndim[1] * ndim[2] < 2147483648.0;
+}
+
 static inline GridGeom make_geom(const int ndim[3], const double nmin[3], const double nmax[3]) {
   GridGeom g;
   g.gx = ndim[0]; g.gy = ndim[1]; g.gz = ndim[2];
@@ -63,9 +67,17 @@ __device__ __forceinline__ float4 lerp4_ref(float4 a, float4 b, float omw, float
                      lerp_ref(a.w, b.w, omw, w));
 }
 
+// Brick map: the grid is cut into BRICK^3-voxel bricks; bricks[b] holds the common value c when every corner a
+// lookup inside the brick can touch (voxels [BRICK*b, BRICK*b + BRICK] per axis, clamped) has n == c bit-for-bit
+// and grad n == 0, and NaN otherwise.  In such a brick the 8 gathers are skipped; the lerp arithmetic is kept.
+constexpr int BRICK_LOG2 = 3;
+constexpr int BRICK = 1 << BRICK_LOG2;
+
 // VoxMLP._linear3 (rnerf/ior_utils.py:188-223): unclamped floor/frac, clamp-to-edge indices, x->y->z lerps.
+// `bricks` may be null (no skipping).  Results are bit-identical with and without the brick map: with all eight
+// corners equal to c the seven lerps collapse to three lerps of identical operands, and 0*(1-w) + 0*w == 0.
 __device__ __forceinline__ float4 trilinear(const float4* __restrict__ table, const GridGeom& g, float px, float py,
-                                            float pz) {
+                                            float pz, const float* __restrict__ bricks = nullptr) {
   float x = divf(sub(px, g.nmin[0]), g.ndelta[0]);
   float y = divf(sub(py, g.nmin[1]), g.ndelta[1]);
   float z = divf(sub(pz, g.nmin[2]), g.ndelta[2]);
@@ -76,8 +88,19 @@ __device__ __forceinline__ float4 trilinear(const float4* __restrict__ table, co
       z0 = (int)fminf(fmaxf(zf, -2.f), (float)g.gz);
   int x1 = min(max(x0 + 1, 0), g.gx - 1), y1 = min(max(y0 + 1, 0), g.gy - 1), z1 = min(max(z0 + 1, 0), g.gz - 1);
   x0 = min(max(x0, 0), g.gx - 1); y0 = min(max(y0, 0), g.gy - 1); z0 = min(max(z0, 0), g.gz - 1);
-  const int64_t sx = (int64_t)g.gy * g.gz, sy = g.gz;
-  const int64_t b00 = sx * x0 + sy * y0, b10 = sx * x1 + sy * y0, b01 = sx * x0 + sy * y1, b11 = sx * x1 + sy * y1;
+  if (bricks != nullptr) {
+    const int nby = (g.gy + BRICK - 1) >> BRICK_LOG2, nbz = (g.gz + BRICK - 1) >> BRICK_LOG2;
+    const float c = __ldg(bricks + ((x0 >> BRICK_LOG2) * nby + (y0 >> BRICK_LOG2)) * nbz + (z0 >> BRICK_LOG2));
+    if (c == c) {  // not NaN: homogeneous brick
+      const float oxd = sub(1.f, xd), oyd = sub(1.f, yd), ozd = sub(1.f, zd);
+      const float c00 = lerp_ref(c, c, oxd, xd);
+      const float c0 = lerp_ref(c00, c00, oyd, yd);
+      return make_float4(lerp_ref(c0, c0, ozd, zd), 0.f, 0.f, 0.f);
+    }
+  }
+  // 32-bit voxel indices: the host rejects grids with more than 2^31 voxels
+  const int sx = g.gy * g.gz, sy = g.gz;
+  const int b00 = sx * x0 + sy * y0, b10 = sx * x1 + sy * y0, b01 = sx * x0 + sy * y1, b11 = sx * x1 + sy * y1;
   float4 d000 = __ldg(table + b00 + z0), d100 = __ldg(table + b10 + z0);
   float4 d001 = __ldg(table + b00 + z1), d101 = __ldg(table + b10 + z1);
   float4 d010 = __ldg(table + b01 + z0), d110 = __ldg(table + b11 + z0);
@@ -90,6 +113,12 @@ __device__ __forceinline__ float4 trilinear(const float4* __restrict__ table, co
   float4 c0 = lerp4_ref(c00, c10, oyd, yd);
   float4 c1 = lerp4_ref(c01, c11, oyd, yd);
   return lerp4_ref(c0, c1, ozd, zd);
+}
+
+// safe_l2_normalize (rnerf/math_utils.py:6-12) of the direction state stored in a path record's 2nd float4
+__device__ __forceinline__ float3 path_dir(float4 rec1) {
+  const float vn = sqrtf(fmaxf(sumsq3(rec1.x, rec1.y, rec1.z), 1e-6f));
+  return make_float3(divf(rec1.x, vn), divf(rec1.y, vn), divf(rec1.z, vn));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -59,6 +59,27 @@ __global__ void __launch_bounds__(256) lookup_kernel(const float4* __restrict__ 
   out[i] = trilinear(table, g, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
 }
 
+// One thread per brick: homogeneous iff every voxel of [B*b, B*b + B] (clamped) equals the first bit-for-bit and
+// has a zero gradient.  The +1 halo covers the x1/y1/z1 corners of the last cell row of the brick.
+__global__ void __launch_bounds__(128) brick_kernel(const float4* __restrict__ table, GridGeom g, float* __restrict__ bricks,
+                                                    int nbx, int nby, int nbz) {
+  const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (b >= (int64_t)nbx * nby * nbz) return;
+  const int bz = (int)(b % nbz), by = (int)((b / nbz) % nby), bx = (int)(b / ((int64_t)nbz * nby));
+  const int x0 = bx * BRICK, y0 = by * BRICK, z0 = bz * BRICK;
+  const int x1 = min(x0 + BRICK, g.gx - 1), y1 = min(y0 + BRICK, g.gy - 1), z1 = min(z0 + BRICK, g.gz - 1);
+  const float4 first = __ldg(table + ((int64_t)x0 * g.gy + y0) * g.gz + z0);
+  bool ok = true;
+  for (int x = x0; x <= x1 && ok; ++x)
+    for (int y = y0; y <= y1 && ok; ++y)
+      for (int z = z0; z <= z1; ++z) {
+        const float4 v = __ldg(table + ((int64_t)x * g.gy + y) * g.gz + z);
+        if (__float_as_uint(v.x) != __float_as_uint(first.x) || v.y != 0.f || v.z != 0.f || v.w != 0.f) { ok = false; break; }
+      }
+  ok = ok && (first.x == first.x) && !isinf(first.x);
+  bricks[b] = ok ? first.x : __int_as_float(0x7fc00000);
+}
+
 static int grid_blocks(int64_t total, int threads) {
   int64_t b = (total + threads - 1) / threads;
   const int64_t cap = 148 * 32;
@@ -116,9 +137,27 @@ extern "C" int rnerf_grid_lookup(const float* table, const int ndim[3], const do
   RNERF_REQUIRE_PTR(pts); RNERF_REQUIRE_PTR(out);
   RNERF_REQUIRE(n_pts > 0, RNERF_E_SHAPE, "rnerf_grid_lookup: n_pts < 0");
   RNERF_REQUIRE(aligned16(table) && aligned16(out), RNERF_E_ALIGN, "rnerf_grid_lookup: table/out must be 16-byte aligned");
+  RNERF_REQUIRE(grid_fits_int32(ndim), RNERF_E_SHAPE, "rnerf_grid_lookup: grids with >= 2^31 voxels are not supported");
   GridGeom g = make_geom(ndim, nmin, nmax);
   lookup_kernel<<<(unsigned)((n_pts + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)table, g, pts, n_pts,
                                                                                     (float4*)out);
   count_launch();
   return check_launch("rnerf_grid_lookup");
+}
+
+extern "C" int64_t rnerf_grid_brick_count(const int ndim[3]) {
+  if (!ndim) return 0;
+  return (int64_t)((ndim[0] + BRICK - 1) / BRICK) * ((ndim[1] + BRICK - 1) / BRICK) * ((ndim[2] + BRICK - 1) / BRICK);
+}
+
+extern "C" int rnerf_grid_bricks(const float* table, const int ndim[3], float* bricks, void* stream) {
+  RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(bricks);
+  RNERF_REQUIRE(aligned16(table), RNERF_E_ALIGN, "rnerf_grid_bricks: table must be 16-byte aligned");
+  const double zero[3] = {0, 0, 0}, one[3] = {1, 1, 1};
+  GridGeom g = make_geom(ndim, zero, one);
+  const int nbx = (ndim[0] + BRICK - 1) / BRICK, nby = (ndim[1] + BRICK - 1) / BRICK, nbz = (ndim[2] + BRICK - 1) / BRICK;
+  const int64_t total = (int64_t)nbx * nby * nbz;
+  brick_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const float4*)table, g, bricks, nbx, nby, nbz);
+  count_launch();
+  return check_launch("rnerf_grid_bricks");
 }

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(MARCH_THREADS) march_kernel(const float4* __re
                                                               const float* __restrict__ origins,
                                                               const float* __restrict__ viewdirs, int64_t n_rays,
                                                               float near, float step, int n_steps,
-                                                              float4* __restrict__ path) {
+                                                              float4* __restrict__ path,
+                                                              const float* __restrict__ bricks) {
   __shared__ float4 stage[MARCH_THREADS / 32][32 * STAGE_PITCH];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp_ray0 = (blockIdx.x * (int64_t)MARCH_THREADS) + warp * 32;
@@ -42,11 +43,12 @@ __global__ void __launch_bounds__(MARCH_THREADS) march_kernel(const float4* __re
   for (int k0 = 0; k0 < n_steps; k0 += STEPS_PER_FLUSH) {
     const int nk = min(STEPS_PER_FLUSH, n_steps - k0);
     for (int kk = 0; kk < nk; ++kk) {
-      float4 c = trilinear(table, g, px, py, pz);  // (n, gx, gy, gz) at the pre-update position
-      float vn = sqrtf(fmaxf(sumsq3(vx, vy, vz), 1e-6f));
+      float4 c = trilinear(table, g, px, py, pz, bricks);  // (n, gx, gy, gz) at the pre-update position
+      // the direction is stored un-normalised; readers apply safe_l2_normalize (path_dir()) to the few records they
+      // use, which keeps 3 IEEE divides + 1 sqrt per step out of the march loop
       my_stage[kk * 3 + 0] = make_float4(px, py, pz, t);
-      my_stage[kk * 3 + 1] = make_float4(divf(vx, vn), divf(vy, vn), divf(vz, vn), c.x);
-      my_stage[kk * 3 + 2] = make_float4(c.y, c.z, c.w, vn);
+      my_stage[kk * 3 + 1] = make_float4(vx, vy, vz, c.x);
+      my_stage[kk * 3 + 2] = make_float4(c.y, c.z, c.w, 0.f);
       float s = divf(step, c.x);
       float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
       vx = add(vx, mul(step, c.y)); vy = add(vy, mul(step, c.z)); vz = add(vz, mul(step, c.w));
@@ -66,6 +68,15 @@ __global__ void __launch_bounds__(MARCH_THREADS) march_kernel(const float4* __re
   }
 }
 
+// ray_dir of every record, normalised: the array PathSampler returns (rnerf/eikonal_utils.py:113)
+__global__ void __launch_bounds__(256) path_dirs_kernel(const float4* __restrict__ path, int64_t n_rec,
+                                                        float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rec) return;
+  float3 d = path_dir(__ldg(path + i * 3 + 1));
+  out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
+}
+
 // rnerf/models.py:243-247: ray_pos[:, jitter] etc.
 __global__ void __launch_bounds__(256) select_kernel(const float4* __restrict__ path, int64_t n_rays, int n_steps,
                                                      const int32_t* __restrict__ jitter, int n_coarse,
@@ -80,7 +91,8 @@ __global__ void __launch_bounds__(256) select_kernel(const float4* __restrict__ 
   float4 a = __ldg(rec), b = __ldg(rec + 1);
   pos_c[3 * i] = a.x; pos_c[3 * i + 1] = a.y; pos_c[3 * i + 2] = a.z;
   t_c[i] = a.w;
-  dir_c[3 * i] = b.x; dir_c[3 * i + 1] = b.y; dir_c[3 * i + 2] = b.z;
+  const float3 dn = path_dir(b);
+  dir_c[3 * i] = dn.x; dir_c[3 * i + 1] = dn.y; dir_c[3 * i + 2] = dn.z;
   if (grad_c) {
     float4 c = __ldg(rec + 2);
     grad_c[3 * i] = c.x; grad_c[3 * i + 1] = c.y; grad_c[3 * i + 2] = c.z;
@@ -91,20 +103,21 @@ __global__ void __launch_bounds__(256) select_kernel(const float4* __restrict__ 
 
 using namespace rnerf;
 
-extern "C" int rnerf_march_fwd(const float* table, const int ndim[3], const double nmin[3], const double nmax[3],
-                               const float* origins, const float* viewdirs, int64_t n_rays, double near, double far,
-                               int n_steps, float* path, void* stream) {
+extern "C" int rnerf_march_fwd(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
+                               const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
+                               double near, double far, int n_steps, float* path, void* stream) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_fwd: n_rays < 0");
   RNERF_REQUIRE(n_steps >= 2, RNERF_E_SHAPE, "rnerf_march_fwd: n_steps must be >= 2 (step = (far-near)/(S-1))");
   if (n_rays == 0) return 0;
   RNERF_REQUIRE_PTR(origins); RNERF_REQUIRE_PTR(viewdirs); RNERF_REQUIRE_PTR(path);
   RNERF_REQUIRE(aligned16(table) && aligned16(path), RNERF_E_ALIGN, "rnerf_march_fwd: table/path must be 16-byte aligned");
+  RNERF_REQUIRE(grid_fits_int32(ndim), RNERF_E_SHAPE, "rnerf_march_fwd: grids with >= 2^31 voxels are not supported");
   GridGeom g = make_geom(ndim, nmin, nmax);
   const float step = (float)((far - near) / (n_steps - 1));
   const unsigned blocks = (unsigned)((n_rays + MARCH_THREADS - 1) / MARCH_THREADS);
   march_kernel<<<blocks, MARCH_THREADS, 0, (cudaStream_t)stream>>>((const float4*)table, g, origins, viewdirs, n_rays,
-                                                                   (float)near, step, n_steps, (float4*)path);
+                                                                   (float)near, step, n_steps, (float4*)path, bricks);
   count_launch();
   return check_launch("rnerf_march_fwd");
 }
@@ -121,4 +134,15 @@ extern "C" int rnerf_select(const float* path, int64_t n_rays, int n_steps, cons
                                                                                   grad_c);
   count_launch();
   return check_launch("rnerf_select");
+}
+
+extern "C" int rnerf_path_dirs(const float* path, int64_t n_rays, int n_steps, float* ray_dir, void* stream) {
+  RNERF_REQUIRE(n_rays >= 0 && n_steps > 0, RNERF_E_SHAPE, "rnerf_path_dirs: bad sizes");
+  if (n_rays == 0) return 0;
+  RNERF_REQUIRE_PTR(path); RNERF_REQUIRE_PTR(ray_dir);
+  RNERF_REQUIRE(aligned16(path), RNERF_E_ALIGN, "rnerf_path_dirs: path must be 16-byte aligned");
+  const int64_t n = n_rays * n_steps;
+  path_dirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)path, n, ray_dir);
+  count_launch();
+  return check_launch("rnerf_path_dirs");
 }

@@ -107,11 +107,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const float4* _
       if (__ldg(&rec0[mid * 3].w) < zv) lo = mid + 1; else hi = mid;
     }
     const int idx = max(lo - 1, 0);
-    const float4 a = __ldg(rec0 + idx * 3), b = __ldg(rec0 + idx * 3 + 1), c = __ldg(rec0 + idx * 3 + 2);
-    const float dz = zv - a.w;
+    const float4 a = __ldg(rec0 + idx * 3), c = __ldg(rec0 + idx * 3 + 2);
+    const float3 b = path_dir(__ldg(rec0 + idx * 3 + 1));
+    const float dz = sub(zv, a.w);
     const int64_t o = ray * nt + m;
     t_f[o] = zv;
-    pos_f[3 * o] = a.x + b.x * dz; pos_f[3 * o + 1] = a.y + b.y * dz; pos_f[3 * o + 2] = a.z + b.z * dz;
+    pos_f[3 * o] = add(a.x, mul(b.x, dz)); pos_f[3 * o + 1] = add(a.y, mul(b.y, dz)); pos_f[3 * o + 2] = add(a.z, mul(b.z, dz));
     dir_f[3 * o] = b.x; dir_f[3 * o + 1] = b.y; dir_f[3 * o + 2] = b.z;
     if (grad_f) { grad_f[3 * o] = c.x; grad_f[3 * o + 1] = c.y; grad_f[3 * o + 2] = c.z; }
   }

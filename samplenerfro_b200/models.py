@@ -115,6 +115,7 @@ class NerfModel:
         if g.numel() != self.ndim[0] * self.ndim[1] * self.ndim[2]:
             raise ValueError("grid size does not match ndim")
         self.table = ops.grid_table(g, self.ndim, self.nmin, self.nmax)
+        self.bricks = ops.grid_bricks(self.table, self.ndim)   # access-skipping aid for the march (bit-identical results)
         self.num_march_steps = self.num_coarse_samples * self.num_path_samples  # rnerf/models.py:121
         self._pack_cache: Dict[str, Any] = {}
 
@@ -199,7 +200,8 @@ class NerfModel:
         k1 = None if rng_1 is None else int(rng_1)
         # --- bent-ray march: no trainable inputs in the radiance stage (T7) -> no autograd through it
         with torch.no_grad():
-            path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S)
+            path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S,
+                             bricks=self.bricks)
             jit = self.draw_jitter(k0) if jitter is None else torch.as_tensor(jitter).to(self.device, torch.int32).contiguous()
             pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=self.use_online_sparsity)
             mask_c = self._bbox_mask(pos_c) if self.use_mask_bbox else None

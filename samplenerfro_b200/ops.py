@@ -68,10 +68,23 @@ def grid_lookup(table: torch.Tensor, ndim, nmin, nmax, pts: torch.Tensor) -> tor
 
 
 # ---------------------------------------------------------------- march (a5, a6) / select (a7)
+def grid_bricks(table: torch.Tensor, ndim) -> torch.Tensor:
+    """Brick map of a (n, grad n) table: per 8^3-voxel brick the common n, or NaN if the brick is not homogeneous."""
+    _chk(table, "table")
+    lib = _lib.load()
+    nd = Int3(*[int(v) for v in ndim])
+    bricks = torch.empty(int(lib.rnerf_grid_brick_count(nd)), device=table.device, dtype=torch.float32)
+    check(lib.rnerf_grid_bricks(_p(table), nd, _p(bricks), _stream()), "rnerf_grid_bricks")
+    return bricks
+
+
 def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n_steps: int,
-          out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124), radiance stage.  Returns path [B,S,12]."""
+          out: Optional[torch.Tensor] = None, bricks: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124), radiance stage.  Returns path [B,S,12].
+    `bricks` (from grid_bricks) lets the kernel skip the gathers in homogeneous space; results are bit-identical."""
     _chk(table, "table"); origins = _chk(origins, "origins"); viewdirs = _chk(viewdirs, "viewdirs")
+    if bricks is not None:
+        _chk(bricks, "bricks")
     B = origins.shape[0]
     if out is None:
         out = torch.empty(B, n_steps, PATH_STRIDE, device=origins.device, dtype=torch.float32)
@@ -79,14 +92,24 @@ def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n
         _chk(out, "out")
         assert out.shape == (B, n_steps, PATH_STRIDE)
     nd, lo, hi = _geom(ndim, nmin, nmax)
-    check(_lib.load().rnerf_march_fwd(_p(table), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near), float(far),
-                                      int(n_steps), _p(out), _stream()), "rnerf_march_fwd")
+    check(_lib.load().rnerf_march_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
+                                      float(far), int(n_steps), _p(out), _stream()), "rnerf_march_fwd")
+    return out
+
+
+def path_dirs(path: torch.Tensor) -> torch.Tensor:
+    """ray_dir [B,S,3]: safe_l2_normalize of the direction state stored in every record."""
+    _chk(path, "path")
+    B, S, _ = path.shape
+    out = torch.empty(B, S, 3, device=path.device, dtype=torch.float32)
+    check(_lib.load().rnerf_path_dirs(_p(path), B, S, _p(out), _stream()), "rnerf_path_dirs")
     return out
 
 
 def path_views(path: torch.Tensor):
-    """(ray_pos, ray_dir, ray_dist, idx_data, idx_grad) views of a path, as PathSampler returns them."""
-    return path[..., 0:3], path[..., 4:7], path[..., 3], path[..., 7:8], path[..., 8:11]
+    """(ray_pos, ray_dir, ray_dist, idx_data, idx_grad) as PathSampler returns them: strided views of the path,
+    except ray_dir which is normalised on demand (the path stores the un-normalised direction state)."""
+    return path[..., 0:3], path_dirs(path), path[..., 3], path[..., 7:8], path[..., 8:11]
 
 
 def select(path: torch.Tensor, jitter: torch.Tensor, want_grad: bool = False):

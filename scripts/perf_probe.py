@@ -28,7 +28,7 @@ def timeit(fn, n=5, warm=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=512)
-    ap.add_argument("--rays", type=int, default=65536)
+    ap.add_argument("--rays", type=int, default=128000)
     ap.add_argument("--side", type=int, default=800)
     a = ap.parse_args()
     G = a.grid
@@ -51,8 +51,9 @@ def main():
     u = model.draw_u(2, B, False)
     pk_c = model._packed(variables, "coarse_mlp"); pk_f = model._packed(variables, "fine_mlp"); wb = model._packed(variables, "bkgd_mlp")
     res = {}
-    res["march"] = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, S, out=path))
+    res["march"] = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, S, out=path, bricks=model.bricks))
     pos_c, dir_c, t_c, _ = ops.select(path, jit)
+    res["march_nobricks"] = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, S, out=path))
     res["select"] = timeit(lambda: ops.select(path, jit))
     res["bkgd_mlp"] = timeit(lambda: ops.bkgd_mlp_fwd(wb, dir_c, B, Nc * 3, (Nc - 1) * 3))
     raw_b = ops.bkgd_mlp_fwd(wb, dir_c, B, Nc * 3, (Nc - 1) * 3)
@@ -70,7 +71,7 @@ def main():
     tot = 0
     for k, (mn, av) in res.items():
         extra = ""
-        if k == "march":
+        if k.startswith("march"):
             extra = f"  {B * (24 + 44 * S) / mn / 1e6:.0f} GB/s algorithmic"
         if k.startswith("encmlp"):
             M = B * (Nc if k.endswith("coarse") else Nc + Nf)

@@ -48,13 +48,31 @@ def test_march_bit_exact(cuda_lib, scene, B, S, near, far):
     from samplenerfro_b200 import ops
     o, d = H.random_rays(B, seed=B)
     pos, dirs, dist, n, g = O.march(scene["table"], scene["ndim"], scene["nmin"], scene["nmax"], o, d, near, far, S)
-    path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), near, far, S).cpu()
-    rp, rd, rt, idn, idg = ops.path_views(path)
+    path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), near, far, S)
+    rp, rd, rt, idn, idg = [x.cpu() for x in ops.path_views(path)]
     bent = (dirs[:, -1] - d).abs().max().item()
     assert B < 100 or bent > 1e-3, "test scene does not bend any ray"
     for name, a, b in (("ray_pos", rp, pos), ("ray_dir", rd, dirs), ("ray_dist", rt, dist), ("idx_data", idn, n),
                        ("idx_grad", idg, g)):
         assert torch.equal(a, b), f"{name}: max rel diff {H.rel_err(a, b):.3e}"
+
+
+def test_march_brick_skipping_is_bit_identical(cuda_lib):
+    """The brick map only skips gathers: the emitted path must not change by a single bit."""
+    from samplenerfro_b200 import ops
+    n, ndim, nmin, nmax = H.sphere_grid(G=72, radius=0.6, ws=5, sigma=3.0)
+    table = ops.grid_table(n.cuda(), ndim, nmin, nmax)
+    bricks = ops.grid_bricks(table, ndim)
+    homog = torch.isfinite(bricks).float().mean().item()
+    assert 0.3 < homog < 0.99, homog                       # the scene has both kinds of bricks
+    vals = bricks[torch.isfinite(bricks)].unique()
+    assert vals.numel() >= 2                               # vacuum (n = 1) and the object's core (n = 1.5)
+    o, d = H.random_rays(3000, seed=9, target_extent=1.4)
+    o[:50] *= 3.0                                          # some rays never enter the grid (clamp-to-edge lookups)
+    a = ops.march(table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768)
+    b = ops.march(table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768, bricks=bricks)
+    assert torch.equal(a, b)
+    assert (a[:, -1, 4:7].cpu() - d).abs().max() > 1e-2    # and rays do bend
 
 
 def test_march_constant_grid_kat(cuda_lib):
@@ -81,7 +99,7 @@ def test_select(cuda_lib, scene):
     jit = (torch.arange(0, 96, 12) + torch.randint(0, 12, (8,), generator=torch.Generator().manual_seed(0))).int()
     pos, dirs, t, grad = ops.select(path, jit.cuda(), want_grad=True)
     pc = path.cpu()
-    assert torch.equal(pos.cpu(), pc[:, jit.long(), 0:3]) and torch.equal(dirs.cpu(), pc[:, jit.long(), 4:7])
+    assert torch.equal(pos.cpu(), pc[:, jit.long(), 0:3]) and torch.equal(dirs.cpu(), ops.path_dirs(path).cpu()[:, jit.long()])
     assert torch.equal(t.cpu(), pc[:, jit.long(), 3]) and torch.equal(grad.cpu(), pc[:, jit.long(), 8:11])
 
 
@@ -141,7 +159,7 @@ def _resample_setup(scene, B, randomized, weights_fn):
     gen = torch.Generator().manual_seed(4)
     jit = torch.arange(0, S, P) + torch.randint(0, P, (Nc,), generator=gen)
     w = weights_fn(torch.rand(B, Nc, generator=gen))
-    rp, rd, rt, _, rg = [x.contiguous() for x in ops.path_views(path.cpu())]
+    rp, rd, rt, _, rg = [x.cpu().contiguous() for x in ops.path_views(path)]
     t_c = rt[:, jit].contiguous()
     if randomized:
         u = O.stratified_u(torch.rand(B, Nf, generator=gen) * (1 / Nf - float(np.finfo(np.float32).eps)))
