@@ -263,7 +263,7 @@ def encmlp_fwd_profile(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tens
     pos = _chk(pos, "pos").reshape(-1, 3); dirs = _chk(dirs, "dirs").reshape(-1, 3)
     M = pos.shape[0]
     raw = torch.empty(M, 4, device=pos.device, dtype=torch.float32)
-    prof = torch.zeros(3, 10, 4, device=pos.device, dtype=torch.int64)
+    prof = torch.zeros(8, 10, 4, device=pos.device, dtype=torch.int64)
     check(_lib.load().rnerf_encmlp_fwd_profile(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(prof), _stream()),
           "rnerf_encmlp_fwd_profile")
     return raw, prof

@@ -226,7 +226,7 @@ def test_bkgd_mlp(cuda_lib):
     assert (out - ref).abs().max().item() < 2e-5, (out - ref).abs().max().item()
 
 
-@pytest.mark.parametrize("M", [128, 1000, 148 * 128 + 77, 60000])
+@pytest.mark.parametrize("M", [128, 1000, 148 * 128 + 77, 60000, 74 * 512 * 3 + 333])
 def test_encmlp_vs_bf16_oracle(cuda_lib, M):
     """Per-layer outputs vs an oracle that rounds operands to bf16 at the same points (fp32 accumulate).
     Stated bf16 tolerance: 2 bf16 ulps (2^-7 relative to the layer's max magnitude) per layer output."""
@@ -240,7 +240,9 @@ def test_encmlp_vs_bf16_oracle(cuda_lib, M):
     raw, layers = ops.encmlp_fwd(packed, pos.cuda(), dirs.cuda(), debug_layers=True)
     torch.cuda.synchronize()
     raw2 = ops.encmlp_fwd(packed, pos.cuda(), dirs.cuda())
-    assert torch.equal(raw, raw2), "debug and production launches disagree"
+    # the production launch may be the CTA-pair kernel, which accumulates the k-blocks in a different order
+    # (bf16 rounding of an activation can flip -> same 2-ulp tolerance as against the oracle)
+    assert (raw - raw2).abs().max().item() <= 2.0 ** -7 * raw.abs().max().item(), "debug and production launches disagree"
     n_chk = min(M, 4096)
     sel = torch.randperm(M, generator=gen)[:n_chk]
     rgb_ref, sig_ref, lay_ref = O.nerf_mlp(p, O.pos_enc(pos[sel][:, None], 0, 10), O.pos_enc(dirs[sel][:, None], 0, 4),
@@ -253,6 +255,8 @@ def test_encmlp_vs_bf16_oracle(cuda_lib, M):
     ref = torch.cat([rgb_ref[:, 0], sig_ref[:, 0]], dim=-1)
     err = (raw.cpu()[sel] - ref).abs().max().item()
     assert err < 2.0 ** -7 * ref.abs().max().item(), err
+    err2 = (raw2.cpu()[sel] - ref).abs().max().item()
+    assert err2 < 2.0 ** -7 * ref.abs().max().item(), err2
     # and against the true fp32 MLP: bf16 compute stays within ~1 % of the output scale
     rgb32, sig32 = O.nerf_mlp(p, O.pos_enc(pos[sel][:, None], 0, 10), O.pos_enc(dirs[sel][:, None], 0, 4))
     ref32 = torch.cat([rgb32[:, 0], sig32[:, 0]], dim=-1)
