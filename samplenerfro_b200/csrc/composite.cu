@@ -53,6 +53,9 @@ __device__ __forceinline__ SampleEval eval_sample(const CompositeArgs& a, int64_
   return s;
 }
 
+// MAXC > 0: the ray's samples (<= 32*MAXC) are evaluated up front so that all their loads are in flight together,
+// then the dependent scan runs over registers; MAXC == 0 streams chunks of 32 (any Ns).
+template <int MAXC>
 __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a, float* __restrict__ comp_rgb,
                                                             float* __restrict__ distance, float* __restrict__ acc_out,
                                                             float* __restrict__ weights, float* __restrict__ alpha_out,
@@ -63,10 +66,9 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a, flo
   const int64_t base = ray * a.n_samples;
   float carry = 0.f;  // sum of dd over previous chunks
   float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f, swt = 0.f;
-  for (int i0 = 0; i0 < a.n_samples; i0 += 32) {
+  auto chunk = [&](int i0, const SampleEval& s) {
     const int i = i0 + lane;
     const bool valid = i < a.n_samples;
-    SampleEval s = eval_sample(a, base, i, valid);
     float incl = warp_incl_scan(s.dd, lane);
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = 0.f;
@@ -79,6 +81,16 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a, flo
       sr += w * s.r; sg += w * s.g; sb += w * s.b; sw += w; swt += w * s.tval;
     }
     carry += __shfl_sync(0xffffffffu, incl, 31);
+  };
+  if (MAXC > 0) {
+    SampleEval ev[MAXC > 0 ? MAXC : 1];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) ev[c] = eval_sample(a, base, c * 32 + lane, c * 32 + lane < a.n_samples);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c * 32 < a.n_samples) chunk(c * 32, ev[c]);
+  } else {
+    for (int i0 = 0; i0 < a.n_samples; i0 += 32) chunk(i0, eval_sample(a, base, i0 + lane, i0 + lane < a.n_samples));
   }
   sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sw = warp_sum(sw); swt = warp_sum(swt);
   if (lane == 0) {
@@ -246,8 +258,12 @@ extern "C" int rnerf_composite_fwd(const float* raw, const float* t, const float
   if (rc) return rc;
   RNERF_REQUIRE_PTR(comp_rgb);
   const int wpb = 4;
-  composite_fwd_kernel<<<(unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      a, comp_rgb, distance, acc, weights, alpha, trans, trans_rgb_bkgd);
+  const unsigned grid = (unsigned)((n_rays + wpb - 1) / wpb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_samples <= 64)       composite_fwd_kernel<2><<<grid, wpb * 32, 0, st>>>(a, comp_rgb, distance, acc, weights, alpha, trans, trans_rgb_bkgd);
+  else if (n_samples <= 192) composite_fwd_kernel<6><<<grid, wpb * 32, 0, st>>>(a, comp_rgb, distance, acc, weights, alpha, trans, trans_rgb_bkgd);
+  else if (n_samples <= 256) composite_fwd_kernel<8><<<grid, wpb * 32, 0, st>>>(a, comp_rgb, distance, acc, weights, alpha, trans, trans_rgb_bkgd);
+  else                       composite_fwd_kernel<0><<<grid, wpb * 32, 0, st>>>(a, comp_rgb, distance, acc, weights, alpha, trans, trans_rgb_bkgd);
   count_launch();
   return check_launch("rnerf_composite_fwd");
 }

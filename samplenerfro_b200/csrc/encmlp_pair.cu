@@ -202,6 +202,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
           const uint32_t ph = (c / PAIR_NSLOT) & 1;
           const uint32_t bytes = (uint32_t)(layer_n(c_pair_stream[i].layer) / 2) * KB * 2;
           mbar_wait_cluster(bar_empty(s), ph ^ 1);
+          if (args.prof != nullptr && blockIdx.x == 0 && g == 1 && c_pair_stream[i].layer == 3)
+            args.prof[256 + (i - pair_layer_first(3))] = clock64();     // slot free -> TMA issued (leader CTA)
           mbar_arrive_expect_tx(bar_full(s), bytes);
           tma_bulk_g2s(sbase + SL::W_OFF + s * PAIR_HALF_BYTES,
                        args.packed + PK_PAIR + (size_t)i * PAIR_CHUNK_STRIDE + rank * PAIR_HALF_BYTES, bytes, bar_full(s));
@@ -250,8 +252,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
                 const bool first_consumer = (ch.cons == 3) ? (j == 0) : true;
                 const bool last_consumer = (ch.cons == 3) ? (j == 1) : true;
                 if (first_consumer) {
+                  const bool pw = prof && l == 3 && j == 0;     // layer 3, P0: stamps for each of the 4 chunks
+                  if (pw) args.prof[240 + i * 4 + 0] = clock64();
                   mbar_wait(bar_full(s), ph);
+                  if (pw) args.prof[240 + i * 4 + 1] = clock64();
                   mbar_wait_cluster(bar_pfull(s), ph);
+                  if (pw) args.prof[240 + i * 4 + 2] = clock64();
                   tc_fence_after();
                 }
                 const uint32_t a_addr = (ch.src < 4) ? (sbase + SL::A_OFF + (j * 4 + ch.src) * ABLK_BYTES)

@@ -20,7 +20,7 @@ constexpr int STEPS_PER_FLUSH = 4;                     // 4 records = 12 float4 
 constexpr int F4_PER_FLUSH = STEPS_PER_FLUSH * 3;      // 12
 constexpr int STAGE_PITCH = F4_PER_FLUSH + 1;          // +1 float4 pad: conflict-free column writes
 
-__global__ void __launch_bounds__(MARCH_THREADS) march_kernel(const float4* __restrict__ table, GridGeom g,
+__global__ void __launch_bounds__(MARCH_THREADS, 8) march_kernel(const float4* __restrict__ table, GridGeom g,
                                                               const float* __restrict__ origins,
                                                               const float* __restrict__ viewdirs, int64_t n_rays,
                                                               float near, float step, int n_steps,
@@ -40,29 +40,48 @@ __global__ void __launch_bounds__(MARCH_THREADS) march_kernel(const float4* __re
   float4* my_stage = &stage[warp][lane * STAGE_PITCH];
   const int rays_here = (int)min((int64_t)32, n_rays - warp_ray0);
 
+  // one eikonal step: emit the record of the current state, then advance it
+  auto one_step = [&](int kk) {
+    float4 c = trilinear(table, g, px, py, pz, bricks);  // (n, gx, gy, gz) at the pre-update position
+    // the direction is stored un-normalised; readers apply safe_l2_normalize (path_dir()) to the few records they
+    // use, which keeps 3 IEEE divides + 1 sqrt per step out of the march loop
+    my_stage[kk * 3 + 0] = make_float4(px, py, pz, t);
+    my_stage[kk * 3 + 1] = make_float4(vx, vy, vz, c.x);
+    my_stage[kk * 3 + 2] = make_float4(c.y, c.z, c.w, 0.f);
+    float s = divf(step, c.x);
+    float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
+    vx = add(vx, mul(step, c.y)); vy = add(vy, mul(step, c.z)); vz = add(vz, mul(step, c.w));
+    t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
+    px = nx; py = ny; pz = nz;
+  };
+
   for (int k0 = 0; k0 < n_steps; k0 += STEPS_PER_FLUSH) {
     const int nk = min(STEPS_PER_FLUSH, n_steps - k0);
-    for (int kk = 0; kk < nk; ++kk) {
-      float4 c = trilinear(table, g, px, py, pz, bricks);  // (n, gx, gy, gz) at the pre-update position
-      // the direction is stored un-normalised; readers apply safe_l2_normalize (path_dir()) to the few records they
-      // use, which keeps 3 IEEE divides + 1 sqrt per step out of the march loop
-      my_stage[kk * 3 + 0] = make_float4(px, py, pz, t);
-      my_stage[kk * 3 + 1] = make_float4(vx, vy, vz, c.x);
-      my_stage[kk * 3 + 2] = make_float4(c.y, c.z, c.w, 0.f);
-      float s = divf(step, c.x);
-      float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
-      vx = add(vx, mul(step, c.y)); vy = add(vy, mul(step, c.z)); vz = add(vz, mul(step, c.w));
-      t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
-      px = nx; py = ny; pz = nz;
+    if (nk == STEPS_PER_FLUSH) {
+#pragma unroll
+      for (int kk = 0; kk < STEPS_PER_FLUSH; ++kk) one_step(kk);
+    } else {
+      for (int kk = 0; kk < nk; ++kk) one_step(kk);
     }
     __syncwarp();
     // cooperative flush: element e -> (ray e / n4, float4 e % n4); consecutive lanes write consecutive bytes
-    const int n4 = nk * 3;
-    const int total4 = rays_here * n4;
-    for (int e = lane; e < total4; e += 32) {
-      const int r = e / n4, j = e - r * n4;
-      float4 v = stage[warp][r * STAGE_PITCH + j];
-      __stcs(path + ((warp_ray0 + r) * (int64_t)n_steps + k0) * 3 + j, v);
+    float4* wbase = path + (warp_ray0 * (int64_t)n_steps + k0) * 3;   // one 64-bit base per flush, 32-bit offsets below
+    const int ray_stride4 = n_steps * 3;                               // float4 units between consecutive rays
+    if (nk == STEPS_PER_FLUSH && rays_here == 32) {
+      // common case: compile-time trip count and divisor (e / 12 is a multiply-shift)
+#pragma unroll
+      for (int it = 0; it < F4_PER_FLUSH; ++it) {
+        const int e = it * 32 + lane;
+        const int r = e / F4_PER_FLUSH, j = e - r * F4_PER_FLUSH;
+        __stcs(wbase + r * ray_stride4 + j, stage[warp][r * STAGE_PITCH + j]);
+      }
+    } else {
+      const int n4 = nk * 3;
+      const int total4 = rays_here * n4;
+      for (int e = lane; e < total4; e += 32) {
+        const int r = e / n4, j = e - r * n4;
+        __stcs(wbase + r * ray_stride4 + j, stage[warp][r * STAGE_PITCH + j]);
+      }
     }
     __syncwarp();
   }

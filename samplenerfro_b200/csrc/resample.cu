@@ -15,6 +15,8 @@ namespace rnerf {
 constexpr int RS_MAX_COARSE = 128;
 constexpr int RS_MAX_FINE = 256;
 constexpr int RS_WARPS = 4;
+constexpr int RS_L1_STRIDE = 32;
+constexpr int RS_MAX_L1 = 64;            // first-level table covers n_steps <= 2048; longer paths use the plain search
 
 struct ResampleSmem {
   float tc[RS_MAX_COARSE];
@@ -22,6 +24,7 @@ struct ResampleSmem {
   float cdf[RS_MAX_COARSE];
   float z[RS_MAX_FINE];
   float merged[RS_MAX_COARSE + RS_MAX_FINE];
+  float tk[RS_MAX_L1];   // ray_dist at every RS_L1_STRIDE-th march step (first level of the step search)
 };
 
 __global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const float4* __restrict__ path, int64_t n_rays,
@@ -97,11 +100,26 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const float4* _
     s.merged[j + lo] = v;
   }
   __syncwarp();
-  // nearest march step strictly below, then linear extrapolation
+  // nearest march step strictly below, then linear extrapolation.  ray_dist is increasing along the path, so the
+  // count of steps with ray_dist < z is found in two levels: a 32-stride table staged in shared memory (one strided
+  // load per lane), then 5 probes inside the 32-step segment instead of 10-11 over the whole path.
   const float4* rec0 = path + ray * (int64_t)n_steps * 3;
+  const int n1 = (n_steps + RS_L1_STRIDE - 1) / RS_L1_STRIDE;
+  const bool two_level = n1 <= RS_MAX_L1;
+  if (two_level) {
+    for (int i = lane; i < n1; i += 32) s.tk[i] = __ldg(&rec0[(i * RS_L1_STRIDE) * 3].w);
+    __syncwarp();
+  }
   for (int m = lane; m < nt; m += 32) {
     const float zv = s.merged[m];
     int lo = 0, hi = n_steps;  // count of ray_dist < z
+    if (two_level) {
+      int a = 0, b = n1;       // number of table entries < z
+      while (a < b) { int mid = (a + b) >> 1; if (s.tk[mid] < zv) a = mid + 1; else b = mid; }
+      // entries [0, a) are < z, entry a (if any) is >= z: the count lies in ((a-1)*32, a*32]
+      lo = a == 0 ? 0 : (a - 1) * RS_L1_STRIDE + 1;
+      hi = a == 0 ? 0 : min(a * RS_L1_STRIDE, n_steps);
+    }
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
       if (__ldg(&rec0[mid * 3].w) < zv) lo = mid + 1; else hi = mid;

@@ -33,3 +33,8 @@ for rank in range(2):
     done = [pr[160 + rank * 16 + w].item() - base for w in range(16)]
     print(f"  rank {rank} acc-seen tile0 warps:", acc[:8], " tile1:", acc[8:])
     print(f"  rank {rank} epi-done tile0 warps:", done[:8], " tile1:", done[8:])
+print("layer 3 / P0 weight waits (leader clock64, relative to the MMA thread's aready stamp of layer 3 P0):")
+ref = mma[3, 0, 1].item()
+for i in range(4):
+    w = pr[240 + i * 4: 240 + i * 4 + 3]
+    print(f"  chunk {i}: TMA issued at {pr[256 + i].item() - ref:7d} | wait begins {w[0].item() - ref:7d}  full(local) {w[1].item() - ref:7d}  pfull(peer) {w[2].item() - ref:7d}")
