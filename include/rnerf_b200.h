@@ -92,6 +92,23 @@ int rnerf_encmlp_fwd(const void* packed, const float* pos, const float* dir, int
 int rnerf_encmlp_fwd_debug(const void* packed, const float* pos, const float* dir, int64_t n_samples,
                            float* raw_out, uint16_t* layer_out, void* stream);
 
+/* ---- a17 (train.py:164-165 differentiates the MLPs): training forward + backward of pos_enc + NerfMLP ----
+ * rnerf_encmlp_fwd_train additionally saves layer_out[10][M][256] (bf16 post-activation outputs of Dense_0..7,
+ * Dense_9, Dense_10) and enc_out[2][M][64] (bf16 pos_enc / dir_enc rows, zero padded).
+ * rnerf_mlp_dgrad: fused tcgen05 chain producing dz_out[10][M][256] (bf16 gradient wrt every layer's pre-activation)
+ *   from d_raw[M][4]; dgrad_packed comes from rnerf_mlp_dgrad_pack (transposed weight image, rebuilt when weights change).
+ * rnerf_mlp_wgrad: gw[kx_valid][n] += x[:, :x_cols]^T dz (fp32, accumulating), gb[n] += column sums of dz (or NULL).
+ * rnerf_mlp_head_grad: out[644] += (gW11[128][3], gb11[3], gW8[256], gb8) from d_raw and the saved activations. */
+int rnerf_encmlp_fwd_train(const void* packed, const float* pos, const float* dir, int64_t n_samples, float* raw_out,
+                           uint16_t* layer_out, uint16_t* enc_out, void* stream);
+size_t rnerf_mlp_dgrad_packed_bytes(void);
+int rnerf_mlp_dgrad_pack(const float* const* kernels_host, void* dgrad_packed, void* stream);
+int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed, const uint16_t* layer_out, const float* d_raw,
+                    int64_t n_samples, uint16_t* dz_out, void* stream);
+int rnerf_mlp_wgrad(const uint16_t* x, int ldx, int x_cols, int kx_valid, const uint16_t* dz, int n, int64_t n_samples,
+                    float* gw, float* gb, void* stream);
+int rnerf_mlp_head_grad(const uint16_t* layer_out, const float* d_raw, int64_t n_samples, float* out, void* stream);
+
 /* development aid: same as rnerf_encmlp_fwd, plus clock64 stamps of CTA 0: prof[2 roles][10 layers][4] int64
  * (role 0 = MMA issuer: wait-start, A-ready, issued; role 1 = epilogue: wait-start, acc-ready, done). */
 int rnerf_encmlp_fwd_profile(const void* packed, const float* pos, const float* dir, int64_t n_samples,

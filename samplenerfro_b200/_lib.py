@@ -40,6 +40,12 @@ SIGNATURES = {
     "rnerf_encmlp_fwd": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_encmlp_fwd_debug": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p, C.c_void_p]),
     "rnerf_encmlp_fwd_profile": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p, C.c_void_p]),
+    "rnerf_encmlp_fwd_train": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rnerf_mlp_dgrad_packed_bytes": (C.c_size_t, []),
+    "rnerf_mlp_dgrad_pack": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "rnerf_mlp_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_i64, C.c_void_p, C.c_void_p]),
+    "rnerf_mlp_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, c_i64, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_mlp_head_grad": (C.c_int, [C.c_void_p, c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_bkgd_weight_floats": (C.c_size_t, []),
     "rnerf_bkgd_mlp_fwd": (C.c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, C.c_void_p]),
     "rnerf_composite_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,

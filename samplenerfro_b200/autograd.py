@@ -26,15 +26,15 @@ class _RadianceMLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, name, packed, pos, dirs, *params):
         M = pos.shape[0] * pos.shape[1]
-        raw, saved = ops.encmlp_fwd_train(packed, pos, dirs)
+        raw, (layers, enc) = ops.encmlp_fwd_train(packed, pos, dirs)
         ctx.model, ctx.name, ctx.shape = model, name, pos.shape
-        ctx.save_for_backward(packed, pos, dirs, saved, *params)
+        ctx.save_for_backward(packed, pos, dirs, layers, enc, *params)
         return raw.view(pos.shape[0], pos.shape[1], 4)
 
     @staticmethod
     def backward(ctx, d_raw):
-        packed, pos, dirs, saved, *params = ctx.saved_tensors
-        grads = ops.encmlp_bwd(packed, pos, dirs, saved, d_raw.contiguous().view(-1, 4), params)
+        packed, pos, dirs, layers, enc, *params = ctx.saved_tensors
+        grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc), d_raw.contiguous().view(-1, 4), params)
         return (None, None, None, None, None, *grads)
 
 

@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
       const int64_t lrow = live ? srow : (args.n_samples - 1);
       const float p0 = __ldg(args.pos + 3 * lrow), p1 = __ldg(args.pos + 3 * lrow + 1), p2 = __ldg(args.pos + 3 * lrow + 2);
       // ---- layer-0 A operand: pos_enc(pos, 0, 10) ----
-      write_encoding<10>(e_blk, row, p0, p1, p2);
+      write_encoding<10>(e_blk, row, p0, p1, p2,
+                         (DEBUG && args.enc_out && live) ? reinterpret_cast<uint4*>(args.enc_out + (size_t)srow * 64) : nullptr);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_aready);
@@ -328,7 +329,8 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
         if (l == 8) {
           // condition input for Dense_10: pos_enc(dir, 0, 4) replaces the position encoding (last used by layer 5)
           const float d0 = __ldg(args.dir + 3 * lrow), d1 = __ldg(args.dir + 3 * lrow + 1), d2 = __ldg(args.dir + 3 * lrow + 2);
-          write_encoding<4>(e_blk, row, d0, d1, d2);
+          write_encoding<4>(e_blk, row, d0, d1, d2,
+                            (DEBUG && args.enc_out && live) ? reinterpret_cast<uint4*>(args.enc_out + ((size_t)args.n_samples + srow) * 64) : nullptr);
         }
         if (prof) args.prof[40 + l * 4 + 2] = clock64();
         if (l == 9) {
@@ -405,7 +407,7 @@ static bool use_pair_kernel() {
 }
 
 static int encmlp_fwd_impl(const void* packed, const float* pos, const float* dir, int64_t n_samples, float* raw_out,
-                           uint16_t* layer_out, void* stream, long long* prof = nullptr) {
+                           uint16_t* layer_out, void* stream, long long* prof = nullptr, uint16_t* enc_out = nullptr) {
   RNERF_REQUIRE(n_samples >= 0, RNERF_E_SHAPE, "rnerf_encmlp_fwd: n_samples < 0");
   if (n_samples == 0) return 0;
   RNERF_REQUIRE_PTR(packed); RNERF_REQUIRE_PTR(pos); RNERF_REQUIRE_PTR(dir); RNERF_REQUIRE_PTR(raw_out);
@@ -413,7 +415,7 @@ static int encmlp_fwd_impl(const void* packed, const float* pos, const float* di
   RNERF_REQUIRE(layer_out == nullptr || aligned16(layer_out), RNERF_E_ALIGN, "rnerf_encmlp_fwd: layer_out must be 16-byte aligned");
   EncMlpArgs a;
   a.packed = (const uint8_t*)packed; a.pos = pos; a.dir = dir; a.n_samples = n_samples;
-  a.raw_out = (float4*)raw_out; a.layer_out = (__nv_bfloat16*)layer_out; a.prof = prof; a.n_groups = 0;
+  a.raw_out = (float4*)raw_out; a.layer_out = (__nv_bfloat16*)layer_out; a.enc_out = (__nv_bfloat16*)enc_out; a.prof = prof; a.n_groups = 0;
   if (prof != nullptr && layer_out == nullptr && n_samples >= 74 * 512 && getenv("RNERF_PROFILE_PAIR") != nullptr)
     return launch_encmlp_pair(a, (cudaStream_t)stream);
   const bool dbg = layer_out != nullptr || prof != nullptr;
@@ -436,4 +438,13 @@ extern "C" int rnerf_encmlp_fwd_debug(const void* packed, const float* pos, cons
 extern "C" int rnerf_encmlp_fwd_profile(const void* packed, const float* pos, const float* dir, int64_t n_samples,
                                         float* raw_out, long long* prof, void* stream) {
   return encmlp_fwd_impl(packed, pos, dir, n_samples, raw_out, nullptr, stream, prof);
+}
+
+// training forward: saves every layer's post-activation output (bf16 [10][M][256]) and the two encodings
+// (bf16 [2][M][64]) for rnerf_mlp_dgrad / rnerf_mlp_wgrad
+extern "C" int rnerf_encmlp_fwd_train(const void* packed, const float* pos, const float* dir, int64_t n_samples,
+                                      float* raw_out, uint16_t* layer_out, uint16_t* enc_out, void* stream) {
+  RNERF_REQUIRE_PTR(layer_out); RNERF_REQUIRE_PTR(enc_out);
+  RNERF_REQUIRE(aligned16(enc_out), RNERF_E_ALIGN, "rnerf_encmlp_fwd_train: enc_out must be 16-byte aligned");
+  return encmlp_fwd_impl(packed, pos, dir, n_samples, raw_out, layer_out, stream, nullptr, enc_out);
 }

@@ -1,0 +1,530 @@
+// Backward of the radiance MLP (a17: train.py:164-165 differentiates NerfMLP, rnerf/model_utils.py:30-90).
+//
+//   mlp_dgrad_kernel  fused chain of data gradients on tcgen05/TMEM: for a 128-row tile the gradient wrt every
+//                     layer's pre-activation (dZ_l) is produced layer by layer, dZ_l -> (x W_l^T) -> ReLU mask ->
+//                     dZ_{l-1}, with the bf16 A operand living in shared memory exactly like the forward; each dZ_l
+//                     is also streamed to HBM once (bf16) for the weight-gradient pass.  ReLU masks come from the
+//                     forward's saved activations, prefetched as 256-bit row masks while the MMAs run.
+//   mlp_wgrad_kernel  dW_l = X_l^T dZ_l, reduction over the sample rows: both operands are read in their natural
+//                     row-major layout as MN-major UMMA operands; each CTA owns a slab of rows and accumulates the
+//                     whole [K_l x N_l] block in TMEM (2 x 256 columns), then adds it to the fp32 gradient with
+//                     red.global.add; the bias gradient (column sums of dZ_l) is taken from the staged tiles.
+//   mlp_head_grad_kernel  the two skinny heads (Dense_8: 256->1, Dense_11: 128->3) on CUDA cores.
+//
+// Layer numbering: "MMA layer" l = 0..9 as in the forward (Dense_0..7, Dense_9 bottleneck, Dense_10 condition);
+// H[l] = saved post-activation output of MMA layer l ([M][256] bf16), dZ[l] = gradient wrt its pre-activation.
+#include "umma.cuh"
+
+namespace rnerf {
+
+// ------------------------------------------------------------------------------------------------
+// dgrad chain
+// ------------------------------------------------------------------------------------------------
+constexpr int DG_GEMMS = 9;                       // d = 0: Dense_10[:256]^T (K = 128), d = 1: Dense_9^T, d >= 2: Dense_(9-d)^T
+__host__ __device__ constexpr int dg_dense(int d) { return d == 0 ? 10 : (d == 1 ? 9 : 9 - d); }
+__host__ __device__ constexpr int dg_k(int d) { return d == 0 ? 128 : 256; }           // GEMM K = width of the layer's output
+__host__ __device__ constexpr int dg_chunks(int d) { return dg_k(d) / KCH; }           // [256 x 32] SWIZZLE_64B chunks
+constexpr int DG_NCHUNK = 4 + 8 * 8;              // 68
+constexpr size_t DG_PACKED_BYTES = (size_t)DG_NCHUNK * SLOT_BYTES;
+
+struct DgradPackArgs { const float* kern[12]; };
+
+// chunk c of GEMM d: rows r = input feature kin (0..255), 32 columns = output features n0..n0+31 of the layer:
+// B[kin][n] = W[kin][n], i.e. plain row slices of the Flax [in,out] kernel (only its first 256 rows matter).
+__global__ void __launch_bounds__(256) dgrad_pack_kernel(DgradPackArgs a, uint8_t* __restrict__ packed) {
+  int c = blockIdx.x, d = 0;
+  while (c >= dg_chunks(d)) { c -= dg_chunks(d); ++d; }
+  const int out_dim = dg_k(d);
+  const float* W = a.kern[dg_dense(d)];
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + (size_t)blockIdx.x * SLOT_BYTES);
+  for (int e = threadIdx.x; e < NMAX * KCH; e += blockDim.x) {
+    const int r = e / KCH, k = e % KCH;
+    dst[sw64_offset(r, k) / 2] = __float2bfloat16_rn(W[(size_t)r * out_dim + c * KCH + k]);
+  }
+}
+
+template <int NT, int NSTAGE>
+struct DgradSmem {
+  static constexpr uint32_t A_OFF = 0;                                   // [NT][4][16 KB] dZ k-blocks
+  static constexpr uint32_t W_OFF = A_OFF + NT * 4 * ABLK_BYTES;         // [NSTAGE][16 KB] weight ring
+  static constexpr uint32_t H_OFF = W_OFF + NSTAGE * SLOT_BYTES;         // w_sigma[256] + w_rgb[3][128] fp32
+  static constexpr uint32_t BAR_OFF = H_OFF + (256 + 384) * 4;
+  static constexpr uint32_t N_BARS = 2 * NSTAGE + 2;
+  static constexpr uint32_t TMEM_SLOT = BAR_OFF + N_BARS * 8;
+  static constexpr uint32_t BYTES = TMEM_SLOT + 16;
+};
+
+struct DgradArgs {
+  const uint8_t* packed;        // dgrad weight image (dgrad_pack_kernel)
+  const float* head_w;          // w_sigma[256] then w_rgb[3][128], bf16-rounded fp32 (forward image tail)
+  const __nv_bfloat16* H;       // [10][M][256] saved activations
+  const float4* d_raw;          // [M] (d rgb_raw[3], d sigma_raw)
+  __nv_bfloat16* dZ;            // [10][M][256] out
+  int64_t n_samples;
+  int n_groups;
+};
+
+// 256-bit ReLU mask of one saved activation row (H > 0  <=>  bf16 bits != 0 after ReLU)
+__device__ __forceinline__ void load_row_mask(const __nv_bfloat16* __restrict__ hrow, uint32_t (&mask)[8]) {
+  const uint4* p = reinterpret_cast<const uint4*>(hrow);
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {            // 4 x 16 bytes = 32 bf16 per mask word
+      const uint4 v = __ldg(p + w * 4 + q4);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        m |= ((u[i] & 0xFFFFu) != 0u ? 1u : 0u) << (q4 * 8 + i * 2);
+        m |= ((u[i] >> 16) != 0u ? 1u : 0u) << (q4 * 8 + i * 2 + 1);
+      }
+    }
+    mask[w] = m;
+  }
+}
+
+template <int NT, int NSTAGE>
+__global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const DgradArgs args) {
+  using SL = DgradSmem<NT, NSTAGE>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar_full = [&](int s) { return sbase + SL::BAR_OFF + 8u * s; };
+  auto bar_empty = [&](int s) { return sbase + SL::BAR_OFF + 8u * (NSTAGE + s); };
+  const uint32_t bar_acc = sbase + SL::BAR_OFF + 8u * (2 * NSTAGE);
+  const uint32_t bar_aready = sbase + SL::BAR_OFF + 8u * (2 * NSTAGE + 1);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SL::TMEM_SLOT);
+  float* head_s = reinterpret_cast<float*>(smem + SL::H_OFF);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_aready, 4 * NT);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(sbase + SL::TMEM_SLOT, 256 * NT); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 256 + 384; i += blockDim.x) head_s[i] = __ldg(args.head_w + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_groups = (args.n_groups > (int)blockIdx.x) ? (args.n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const size_t layer_stride = (size_t)args.n_samples * 256;
+
+  if (warp == 0) {
+    if (lane == 0) {   // weight producer
+      int stage = 0; uint32_t phase = 0;
+      for (int g = 0; g < my_groups; ++g)
+        for (int c = 0; c < DG_NCHUNK; ++c) {
+          mbar_wait(bar_empty(stage), phase ^ 1);
+          mbar_arrive_expect_tx(bar_full(stage), SLOT_BYTES);
+          tma_bulk_g2s(sbase + SL::W_OFF + stage * SLOT_BYTES, args.packed + (size_t)c * SLOT_BYTES, SLOT_BYTES, bar_full(stage));
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // MMA issuer
+      constexpr uint32_t idesc = make_idesc(TILE_M, 256);
+      int stage = 0; uint32_t phase = 0, ar_phase = 0;
+      for (int g = 0; g < my_groups; ++g)
+        for (int d = 0; d < DG_GEMMS; ++d) {
+          mbar_wait(bar_aready, ar_phase); ar_phase ^= 1;
+          tc_fence_after();
+          const int nkb = dg_k(d) / KB;
+          for (int kbi = 0; kbi < nkb; ++kbi)
+#pragma unroll
+            for (int sub = 0; sub < SUBS; ++sub) {
+              mbar_wait(bar_full(stage), phase);
+              tc_fence_after();
+              const uint32_t b_addr = sbase + SL::W_OFF + stage * SLOT_BYTES;
+#pragma unroll
+              for (int t = 0; t < NT; ++t) {
+                const uint32_t a_addr = sbase + SL::A_OFF + (t * 4 + kbi) * ABLK_BYTES + sub * (KCH * 2);
+#pragma unroll
+                for (int ks = 0; ks < KCH / 16; ++ks)
+                  umma_bf16(tmem_base + (uint32_t)(t * 256), make_sw128_desc(a_addr + ks * 32), make_sw64_desc(b_addr + ks * 32),
+                            idesc, (kbi > 0 || sub > 0 || ks > 0) ? 1u : 0u);
+              }
+              umma_commit(bar_empty(stage));
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+          umma_commit(bar_acc);
+        }
+    }
+  } else {
+    // epilogue warpgroups: thread <-> sample row
+    const int t = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane;
+    uint8_t* a_row = smem + SL::A_OFF + t * 4 * ABLK_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+    const uint32_t r7s = (uint32_t)(row & 7) << 4;
+    const float* w_sigma = head_s;
+    const float* w_rgb = head_s + 256;
+    uint32_t acc_phase = 0;
+    auto signal_ready = [&]() {
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_aready);
+    };
+    for (int g = 0; g < my_groups; ++g) {
+      const int64_t group = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
+      const int64_t srow = (group * NT + t) * TILE_M + row;
+      const bool live = srow < args.n_samples;
+      const int64_t lrow = live ? srow : (args.n_samples - 1);
+      const float4 draw = live ? __ldg(args.d_raw + lrow) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // ---- prologue: rgb head (Dense_11) backward + ReLU of the condition layer -> dZ[9] (128 columns)
+      {
+        const uint4* h9 = reinterpret_cast<const uint4*>(args.H + 9 * layer_stride + (size_t)lrow * 256);
+        uint4* out = reinterpret_cast<uint4*>(args.dZ + 9 * layer_stride + (size_t)lrow * 256);
+#pragma unroll 1
+        for (int c8 = 0; c8 < 16; ++c8) {         // 8 columns per 16-byte unit
+          const uint4 hv = __ldg(h9 + c8);
+          const uint32_t hu[4] = {hv.x, hv.y, hv.z, hv.w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j0 = c8 * 8 + i * 2;
+            float g0 = draw.x * w_rgb[j0] + draw.y * w_rgb[128 + j0] + draw.z * w_rgb[256 + j0];
+            float g1 = draw.x * w_rgb[j0 + 1] + draw.y * w_rgb[128 + j0 + 1] + draw.z * w_rgb[256 + j0 + 1];
+            if ((hu[i] & 0xFFFFu) == 0u) g0 = 0.f;
+            if ((hu[i] >> 16) == 0u) g1 = 0.f;
+            pk[i] = pack_bf16(g0, g1);
+          }
+          const uint4 o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(a_row + (c8 >> 3) * ABLK_BYTES + ((uint32_t)((c8 & 7) << 4) ^ r7s)) = o;
+          if (live) out[c8] = o;
+        }
+      }
+      signal_ready();
+      for (int d = 0; d < DG_GEMMS; ++d) {
+        const int lo = 8 - d;                       // MMA layer whose dZ this GEMM produces
+        uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (d >= 1) load_row_mask(args.H + (size_t)lo * layer_stride + (size_t)lrow * 256, mask);   // hidden under the MMAs
+        mbar_wait(bar_acc, acc_phase); acc_phase ^= 1;
+        tc_fence_after();
+        __nv_bfloat16* out_row = args.dZ + (size_t)lo * layer_stride + (size_t)lrow * 256;
+#pragma unroll 1
+        for (int cg = 0; cg < 8; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + cg * 32), v);
+          tmem_ld_wait();
+          uint32_t mk = 0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) if (w == cg) mk = mask[w];     // select, keeps mask[] in registers
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+            if (d == 1) {   // the sigma head (Dense_8) also feeds h7: dh7 += d_sigma * w_sigma
+              f0 = fmaf(draw.w, w_sigma[cg * 32 + 2 * j], f0);
+              f1 = fmaf(draw.w, w_sigma[cg * 32 + 2 * j + 1], f1);
+            }
+            if (d >= 1) {
+              if (!((mk >> (2 * j)) & 1u)) f0 = 0.f;
+              if (!((mk >> (2 * j + 1)) & 1u)) f1 = 0.f;
+            }
+            pk[j] = pack_bf16(f0, f1);
+          }
+          if (d < DG_GEMMS - 1) {
+            uint8_t* blk = a_row + (cg >> 1) * ABLK_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(blk + ((uint32_t)(((cg & 1) * 4 + c) << 4) ^ r7s)) =
+                  make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          }
+          if (live) {
+            uint4* o = reinterpret_cast<uint4*>(out_row + cg * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          }
+        }
+        if (d < DG_GEMMS - 1) signal_ready(); else tc_fence_before();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256 * NT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// heads + bias gradients of the skinny layers (CUDA cores)
+//   gW11[j][c] = sum_m H9[m][j] d_rgb[m][c]   gb11[c] = sum_m d_rgb[m][c]
+//   gW8[j]     = sum_m H7[m][j] d_sig[m]      gb8     = sum_m d_sig[m]
+// out: float[128*3 + 3 + 256 + 1], accumulated with atomics (zeroed by the caller)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mlp_head_grad_kernel(const __nv_bfloat16* __restrict__ H, const float4* __restrict__ d_raw,
+                                                            int64_t n_samples, int rows_per_block, float* __restrict__ out) {
+  const size_t layer_stride = (size_t)n_samples * 256;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m1 = min(m0 + rows_per_block, n_samples);
+  const int j = threadIdx.x;            // column 0..255
+  float a_sig = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f, s_s = 0.f;
+  for (int64_t m = m0; m < m1; ++m) {
+    const float4 d = __ldg(d_raw + m);
+    a_sig = fmaf(__bfloat162float(H[7 * layer_stride + m * 256 + j]), d.w, a_sig);
+    if (j < 128) {
+      const float h = __bfloat162float(H[9 * layer_stride + m * 256 + j]);
+      a_r = fmaf(h, d.x, a_r); a_g = fmaf(h, d.y, a_g); a_b = fmaf(h, d.z, a_b);
+    }
+    if (j == 0) { s_r += d.x; s_g += d.y; s_b += d.z; s_s += d.w; }
+  }
+  if (j < 128) { atomicAdd(out + j * 3, a_r); atomicAdd(out + j * 3 + 1, a_g); atomicAdd(out + j * 3 + 2, a_b); }
+  atomicAdd(out + 387 + j, a_sig);
+  if (j == 0) { atomicAdd(out + 384, s_r); atomicAdd(out + 385, s_g); atomicAdd(out + 386, s_b); atomicAdd(out + 643, s_s); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: G[Kx x N] += X[rows][Kx]^T  dZ[rows][N]   (MN-major operands, reduction over rows), gb[N] += colsum(dZ)
+// One CTA = one slab of rows; accumulators: Kx/128 M-blocks x N columns of TMEM.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 64;                           // rows (GEMM K) per pipeline stage
+constexpr int WG_STAGES = 3;
+constexpr int WG_STAGE_BYTES = WG_ROWS * 256 * 2 * 2; // X tile [64 x 256] + dZ tile [64 x 256] bf16 = 64 KB
+constexpr int WG_THREADS = 64 + 256;                  // warp 0: MMA, warp 1: spare, warps 2-9: loaders/epilogue
+
+struct WgradSmem {
+  static constexpr uint32_t ST_OFF = 0;
+  static constexpr uint32_t BAR_OFF = WG_STAGES * WG_STAGE_BYTES;
+  static constexpr uint32_t TMEM_SLOT = BAR_OFF + (2 * WG_STAGES + 1) * 8;
+  static constexpr uint32_t BYTES = TMEM_SLOT + 16;
+};
+
+struct WgradArgs {
+  const __nv_bfloat16* X;     // [M][ldx] rows; the first kx columns are used
+  const __nv_bfloat16* dZ;    // [M][256]
+  int ldx, kx, x_cols;        // kx in {128, 256}: gradient rows (UMMA M blocks of 128); x_cols <= kx real columns of X, rest zero
+  int n;                      // 128 or 256 columns of dZ
+  int64_t n_samples;
+  int rows_per_cta;           // multiple of WG_ROWS
+  float* gW;                  // [kx_valid][n] fp32, accumulated
+  int kx_valid;               // rows of gW actually written (e.g. 63 of 64)
+  float* gb;                  // [n] fp32 or null, accumulated
+};
+
+// MN-major SWIZZLE_128B descriptor: 64 MN-elements (128 B) contiguous per K-row, 8 K-rows per 1024-byte atom;
+// LBO = byte distance between MN-atoms, SBO = byte distance between groups of 8 K-rows.
+__device__ __forceinline__ uint64_t make_mn_sw128_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {   // both operands MN-major (bits 15, 16)
+  return make_idesc(m, n) | (1u << 15) | (1u << 16);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;     // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Tile layout in a stage: [operand (X, dZ)][k-group kb = 0..7][MN-atom mm = 0..3][8 rows x 128 B], i.e. for a row r
+// (= GEMM K index) and column c: atom (kb = r/8, mm = c/64), row-in-atom kk = r%8, 16-byte unit (c%64)/8 ^ kk.
+__global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArgs a) {
+  using SL = WgradSmem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto bar_full = [&](int s) { return sbase + SL::BAR_OFF + 8u * s; };
+  auto bar_empty = [&](int s) { return sbase + SL::BAR_OFF + 8u * (WG_STAGES + s); };
+  const uint32_t bar_done = sbase + SL::BAR_OFF + 8u * (2 * WG_STAGES);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SL::TMEM_SLOT);
+  const int n_mblk = a.kx / 128;                    // M-blocks of the gradient (1 or 2)
+  const int m_rows = 128;                           // UMMA M
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(bar_full(s), 256); mbar_init(bar_empty(s), 1); }
+    mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(sbase + SL::TMEM_SLOT, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t row0 = (int64_t)blockIdx.x * a.rows_per_cta;
+  const int64_t row1 = min(row0 + a.rows_per_cta, a.n_samples);
+  const int n_steps = row1 > row0 ? (int)((row1 - row0 + WG_ROWS - 1) / WG_ROWS) : 0;
+  const int xatoms = a.kx / 64, zatoms = a.n / 64;  // MN-atoms per K-group
+
+  if (warp == 0) {
+    if (lane == 0 && n_steps > 0) {
+      const uint32_t idesc = make_idesc_mn(m_rows, a.n);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < n_steps; ++it) {
+        mbar_wait(bar_full(stage), phase);
+        tc_fence_after();
+        const uint32_t xs = sbase + SL::ST_OFF + stage * WG_STAGE_BYTES;
+        const uint32_t zs = xs + WG_ROWS * 256 * 2;
+        for (int mb = 0; mb < n_mblk; ++mb)
+#pragma unroll
+          for (int ks = 0; ks < WG_ROWS / 16; ++ks) {
+            // K-step = 16 rows = 2 k-groups; A: MN-atoms 2*mb, 2*mb+1 of the X tile; B: all n/64 atoms of the dZ tile
+            const uint64_t ad = make_mn_sw128_desc(xs + (2 * ks) * xatoms * 1024 + mb * 2 * 1024, 1024, xatoms * 1024);
+            const uint64_t bd = make_mn_sw128_desc(zs + (2 * ks) * zatoms * 1024, 1024, zatoms * 1024);
+            umma_bf16(tmem_base + (uint32_t)(mb * 256), ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+        umma_commit(bar_empty(stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(bar_done);
+    }
+  } else if (warp >= 2) {
+    // ---- loaders: 256 threads copy one stage (rows x {X, dZ}) with 16-byte cp.async into the swizzled MN-major tiles
+    const int tid = threadIdx.x - 64;
+    float colsum = 0.f;                        // thread tid owns dZ column tid (if < n)
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < n_steps; ++it) {
+      mbar_wait(bar_empty(stage), phase ^ 1);
+      uint8_t* xs = smem + SL::ST_OFF + stage * WG_STAGE_BYTES;
+      uint8_t* zs = xs + WG_ROWS * 256 * 2;
+      const int64_t rbase = row0 + (int64_t)it * WG_ROWS;
+      const int xunits = a.kx / 8, zunits = a.n / 8;     // 16-byte units per row
+      for (int e = tid; e < WG_ROWS * xunits; e += 256) {
+        const int r = e / xunits, u = e % xunits;
+        const int64_t gr = rbase + r;
+        const uint32_t off = (uint32_t)(((r >> 3) * xatoms + (u >> 3)) * 1024 + (r & 7) * 128 + (((u & 7) ^ (r & 7)) << 4));
+        const bool in_x = u * 8 < a.x_cols;
+        cp_async16(smem_u32(xs + off), a.X + (size_t)min(gr, a.n_samples - 1) * a.ldx + (in_x ? u * 8 : 0), gr < row1 && in_x);
+      }
+      for (int e = tid; e < WG_ROWS * zunits; e += 256) {
+        const int r = e / zunits, u = e % zunits;
+        const int64_t gr = rbase + r;
+        const uint32_t off = (uint32_t)(((r >> 3) * zatoms + (u >> 3)) * 1024 + (r & 7) * 128 + (((u & 7) ^ (r & 7)) << 4));
+        cp_async16(smem_u32(zs + off), a.dZ + (size_t)min(gr, a.n_samples - 1) * 256 + u * 8, gr < row1);
+      }
+      cp_async_commit_wait_all();
+      // bias gradient: column sums of the dZ tile, read back from the staged tile (own writes + others' after the barrier
+      // would need a sync; use the global values instead: one coalesced 2-byte read per row)
+      if (a.gb != nullptr && tid < a.n) {
+        for (int r = 0; r < WG_ROWS; ++r) {
+          const int64_t gr = rbase + r;
+          if (gr < row1) colsum += __bfloat162float(a.dZ[(size_t)gr * 256 + tid]);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_full(stage));
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (a.gb != nullptr && tid < a.n && n_steps > 0) atomicAdd(a.gb + tid, colsum);
+    // ---- epilogue: accumulators -> red.global.add into gW.  TMEM lane = gradient row (X column) within the M-block.
+    if (n_steps > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      const int q = warp & 3, wg = (warp - 2) >> 2;       // two warpgroups split the columns
+      const int lrow = q * 32 + lane;
+      for (int mb = 0; mb < n_mblk; ++mb) {
+        const int grow = mb * 128 + lrow;
+        const bool ok = lrow < m_rows && grow < a.kx_valid;
+        for (int cg = wg; cg < a.n / 32; cg += 2) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * 256 + cg * 32), v);
+          tmem_ld_wait();
+          if (ok) {
+            float* dst = a.gW + (size_t)grow * a.n + cg * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace rnerf
+
+using namespace rnerf;
+
+extern "C" size_t rnerf_mlp_dgrad_packed_bytes(void) { return DG_PACKED_BYTES; }
+
+extern "C" int rnerf_mlp_dgrad_pack(const float* const* kernels, void* packed, void* stream) {
+  RNERF_REQUIRE_PTR(kernels); RNERF_REQUIRE_PTR(packed);
+  RNERF_REQUIRE(aligned16(packed), RNERF_E_ALIGN, "rnerf_mlp_dgrad_pack: packed must be 16-byte aligned");
+  DgradPackArgs a;
+  for (int i = 0; i < 12; ++i) {
+    if (!kernels[i]) { set_error("rnerf_mlp_dgrad_pack: null kernel %d", i); return RNERF_E_NULL; }
+    a.kern[i] = kernels[i];
+  }
+  dgrad_pack_kernel<<<DG_NCHUNK, 256, 0, (cudaStream_t)stream>>>(a, (uint8_t*)packed);
+  count_launch();
+  return check_launch("rnerf_mlp_dgrad_pack");
+}
+
+extern "C" int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed, const uint16_t* saved_h, const float* d_raw,
+                               int64_t n_samples, uint16_t* dz_out, void* stream) {
+  RNERF_REQUIRE(n_samples >= 0, RNERF_E_SHAPE, "rnerf_mlp_dgrad: n_samples < 0");
+  if (n_samples == 0) return 0;
+  RNERF_REQUIRE_PTR(dgrad_packed); RNERF_REQUIRE_PTR(fwd_packed); RNERF_REQUIRE_PTR(saved_h); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(dz_out);
+  RNERF_REQUIRE(aligned16(dgrad_packed) && aligned16(saved_h) && aligned16(d_raw) && aligned16(dz_out), RNERF_E_ALIGN,
+                "rnerf_mlp_dgrad: buffers must be 16-byte aligned");
+  constexpr int NT = 2, NSTAGE = 4;
+  using SL = DgradSmem<NT, NSTAGE>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto kfn = mlp_dgrad_kernel<NT, NSTAGE>;
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::BYTES);
+    if (e != cudaSuccess) { set_error("rnerf_mlp_dgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set[dev] = true;
+  }
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  DgradArgs a;
+  a.packed = (const uint8_t*)dgrad_packed;
+  a.head_w = reinterpret_cast<const float*>((const uint8_t*)fwd_packed + PK_WSIGMA);
+  a.H = (const __nv_bfloat16*)saved_h; a.d_raw = (const float4*)d_raw; a.dZ = (__nv_bfloat16*)dz_out;
+  a.n_samples = n_samples;
+  a.n_groups = (int)((n_samples + TILE_M * NT - 1) / (TILE_M * NT));
+  const int grid = a.n_groups < n_sm ? a.n_groups : n_sm;
+  kfn<<<grid, 64 + 128 * NT, SL::BYTES, (cudaStream_t)stream>>>(a);
+  count_launch();
+  return check_launch("rnerf_mlp_dgrad");
+}
+
+extern "C" int rnerf_mlp_head_grad(const uint16_t* saved_h, const float* d_raw, int64_t n_samples, float* out, void* stream) {
+  if (n_samples <= 0) return 0;
+  RNERF_REQUIRE_PTR(saved_h); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(out);
+  const int rows_per_block = 256;
+  const unsigned grid = (unsigned)((n_samples + rows_per_block - 1) / rows_per_block);
+  mlp_head_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)saved_h, (const float4*)d_raw, n_samples,
+                                                                rows_per_block, out);
+  count_launch();
+  return check_launch("rnerf_mlp_head_grad");
+}
+
+extern "C" int rnerf_mlp_wgrad(const uint16_t* x, int ldx, int x_cols, int kx_valid, const uint16_t* dz, int n, int64_t n_samples,
+                               float* gw, float* gb, void* stream) {
+  if (n_samples <= 0) return 0;
+  RNERF_REQUIRE_PTR(x); RNERF_REQUIRE_PTR(dz); RNERF_REQUIRE_PTR(gw);
+  RNERF_REQUIRE(x_cols >= 8 && x_cols <= 256 && (x_cols % 8) == 0 && x_cols <= ldx && (ldx % 8) == 0 && kx_valid >= 1 && kx_valid <= x_cols,
+                RNERF_E_SHAPE, "rnerf_mlp_wgrad: x_cols must be a multiple of 8 in [8,256] (got %d, ldx %d, valid %d)", x_cols, ldx, kx_valid);
+  const int kx = x_cols <= 128 ? 128 : 256;
+  RNERF_REQUIRE(n == 128 || n == 256, RNERF_E_SHAPE, "rnerf_mlp_wgrad: n must be 128 or 256");
+  RNERF_REQUIRE(aligned16(x) && aligned16(dz), RNERF_E_ALIGN, "rnerf_mlp_wgrad: x/dz must be 16-byte aligned");
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradSmem::BYTES);
+    if (e != cudaSuccess) { set_error("rnerf_mlp_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set[dev] = true;
+  }
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  WgradArgs a;
+  a.X = (const __nv_bfloat16*)x; a.dZ = (const __nv_bfloat16*)dz; a.ldx = ldx; a.kx = kx; a.x_cols = x_cols; a.kx_valid = kx_valid; a.n = n;
+  a.n_samples = n_samples; a.gW = gw; a.gb = gb;
+  int64_t per = (n_samples + n_sm - 1) / n_sm;
+  per = (per + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+  a.rows_per_cta = (int)per;
+  const unsigned grid = (unsigned)((n_samples + per - 1) / per);
+  mlp_wgrad_kernel<<<grid, WG_THREADS, WgradSmem::BYTES, (cudaStream_t)stream>>>(a);
+  count_launch();
+  return check_launch("rnerf_mlp_wgrad");
+}

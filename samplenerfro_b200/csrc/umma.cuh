@@ -192,7 +192,8 @@ struct EncMlpArgs {
   const float* dir;
   int64_t n_samples;
   float4* raw_out;
-  __nv_bfloat16* layer_out;  // debug dump [10][M][256] or null
+  __nv_bfloat16* layer_out;  // debug / training dump [10][M][256] or null
+  __nv_bfloat16* enc_out;    // training dump of the encodings [2][M][64] (pos_enc, dir_enc) or null
   long long* prof;           // development aid: clock64 stamps of CTA 0, [3][10][4], or null
   int n_groups;              // ceil(n_samples / (128*NT))
 };
@@ -206,7 +207,8 @@ struct EncMlpArgs {
 // (it evaluates cos as sin(fl32(2^k x + pi/2)), off by up to ulp(3072)/2 = 1.2e-4) and ~30x below the bf16
 // quantisation step (2^-9 relative) the value is rounded to when it becomes an MMA operand.
 template <int L>
-__device__ __forceinline__ void write_encoding(uint8_t* blk, int row, float x0, float x1, float x2) {
+__device__ __forceinline__ void write_encoding(uint8_t* blk, int row, float x0, float x1, float x2,
+                                               uint4* __restrict__ gout = nullptr /* optional [8] copy of the row to global */) {
   constexpr int NF = 3 + 6 * L;
   float feat[64];
   feat[0] = x0; feat[1] = x1; feat[2] = x2;
@@ -232,6 +234,7 @@ __device__ __forceinline__ void write_encoding(uint8_t* blk, int row, float x0, 
     uint4 o = make_uint4(pack_bf16(feat[c8 * 8 + 0], feat[c8 * 8 + 1]), pack_bf16(feat[c8 * 8 + 2], feat[c8 * 8 + 3]),
                          pack_bf16(feat[c8 * 8 + 4], feat[c8 * 8 + 5]), pack_bf16(feat[c8 * 8 + 6], feat[c8 * 8 + 7]));
     *reinterpret_cast<uint4*>(blk + sw128_offset(row, c8 * 8)) = o;
+    if (gout != nullptr) gout[c8] = o;
   }
 }
 

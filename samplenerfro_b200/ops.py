@@ -269,60 +269,76 @@ def encmlp_fwd_profile(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tens
     return raw, prof
 
 
-# ---------------------------------------------------------------- training-mode MLP (forward saves activations)
+# ---------------------------------------------------------------- training-mode MLP: forward with saved activations, backward
 def encmlp_fwd_train(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tensor):
-    """Forward that also keeps every layer's post-activation output (bf16 [10,M,256]) for the backward pass."""
-    return encmlp_fwd(packed, pos, dirs, debug_layers=True)
+    """Forward that keeps what the backward kernels need: every layer's post-activation output (bf16 [10,M,256])
+    and the two encodings (bf16 [2,M,64]).  Returns (raw [M,4], (layers, enc))."""
+    _chk(packed, "packed", torch.uint8)
+    pos = _chk(pos, "pos").reshape(-1, 3); dirs = _chk(dirs, "dirs").reshape(-1, 3)
+    M = pos.shape[0]
+    raw = torch.empty(M, 4, device=pos.device, dtype=torch.float32)
+    layers = torch.empty(10, M, 256, device=pos.device, dtype=torch.bfloat16)
+    enc = torch.empty(2, M, 64, device=pos.device, dtype=torch.bfloat16)
+    check(_lib.load().rnerf_encmlp_fwd_train(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(layers), _p(enc), _stream()),
+          "rnerf_encmlp_fwd_train")
+    return raw, (layers, enc)
+
+
+def mlp_dgrad_pack(kernels) -> torch.Tensor:
+    """Transposed-weight image for the dgrad chain (rebuilt whenever the weights change)."""
+    lib = _lib.load()
+    out = torch.empty(lib.rnerf_mlp_dgrad_packed_bytes(), device=kernels[0].device, dtype=torch.uint8)
+    kp = (C.c_void_p * 12)(*[_chk(k, "kernel").data_ptr() for k in kernels])
+    check(lib.rnerf_mlp_dgrad_pack(kp, _p(out), _stream()), "rnerf_mlp_dgrad_pack")
+    return out
+
+
+def mlp_wgrad(x: torch.Tensor, x_cols: int, kx_valid: int, dz: torch.Tensor, n: int, gw: torch.Tensor,
+              gb: Optional[torch.Tensor]) -> None:
+    """gw[kx_valid, n] += x[:, :x_cols]^T dz[:, :n];  gb[n] += colsum(dz[:, :n]).  x: bf16 [M, ldx], dz: bf16 [M, 256]."""
+    assert x.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16 and x.is_contiguous() and dz.is_contiguous()
+    assert gw.dtype == torch.float32 and gw.is_contiguous() and gw.shape == (kx_valid, n)
+    M = x.shape[0]
+    check(_lib.load().rnerf_mlp_wgrad(_p(x), x.shape[1], int(x_cols), int(kx_valid), _p(dz), int(n), M, _p(gw), _p(gb), _stream()),
+          "rnerf_mlp_wgrad")
+
+
+def encmlp_bwd(packed, pos, dirs, saved, d_raw, params):
+    """Backward of pos_enc + NerfMLP wrt the 12 Dense layers: fused tcgen05 dgrad chain (dZ of every layer), then one
+    MN-major tcgen05 wgrad per layer (+ the two skinny heads on CUDA cores).  Returns [gK0, gb0, ..., gK11, gb11]."""
+    layers, enc = saved
+    M = layers.shape[1]
+    lib = _lib.load()
+    K = [p for p in params[0::2]]
+    dev = layers.device
+    d_raw = _chk(d_raw.contiguous(), "d_raw")
+    dgp = mlp_dgrad_pack(K)
+    dz = torch.empty(10, M, 256, device=dev, dtype=torch.bfloat16)
+    check(lib.rnerf_mlp_dgrad(_p(dgp), _p(packed), _p(layers), _p(d_raw), M, _p(dz), _stream()), "rnerf_mlp_dgrad")
+    gK = [torch.zeros_like(k) for k in K]
+    gB = [torch.zeros_like(b) for b in params[1::2]]
+    mlp_wgrad(enc[0], 64, 63, dz[0], 256, gK[0], gB[0])
+    for l in (1, 2, 3, 4, 6, 7):
+        mlp_wgrad(layers[l - 1], 256, 256, dz[l], 256, gK[l], gB[l])
+    mlp_wgrad(layers[4], 256, 256, dz[5], 256, gK[5][:256], gB[5])
+    mlp_wgrad(enc[0], 64, 63, dz[5], 256, gK[5][256:], None)
+    mlp_wgrad(layers[7], 256, 256, dz[8], 256, gK[9], gB[9])
+    mlp_wgrad(layers[8], 256, 256, dz[9], 128, gK[10][:256], gB[10])
+    mlp_wgrad(enc[1], 32, 27, dz[9], 128, gK[10][256:], None)
+    heads = torch.zeros(644, device=dev, dtype=torch.float32)
+    check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(heads), _stream()), "rnerf_mlp_head_grad")
+    gK[11] = heads[:384].view(128, 3); gB[11] = heads[384:387]
+    gK[8] = heads[387:643].view(256, 1); gB[8] = heads[643:644]
+    out = []
+    for i in range(12):
+        out += [gK[i], gB[i]]
+    return out
 
 
 def _pos_enc_torch(x: torch.Tensor, max_deg: int) -> torch.Tensor:
     scales = (2.0 ** torch.arange(max_deg, device=x.device, dtype=torch.float32))
     xb = (x[:, None, :] * scales[:, None]).reshape(x.shape[0], -1)
     return torch.cat([x, torch.sin(xb), torch.cos(xb)], dim=-1)
-
-
-def encmlp_bwd(packed, pos, dirs, saved, d_raw, params):
-    """Backward of pos_enc + NerfMLP wrt the 12 Dense layers, from d(raw)[M,4] and the saved activations.
-
-    INTERIM (round 1): the dgrad/wgrad GEMMs below are plain library GEMMs (torch.matmul -> cuBLAS, fp32); the
-    forward, its saved activations and every other stage are this repo's kernels.  A fused tcgen05 dgrad chain +
-    split-K wgrad kernel replaces this in a later round ("Training path")."""
-    pos = pos.reshape(-1, 3); dirs = dirs.reshape(-1, 3)
-    K = [p for p in params[0::2]]
-    Wb = [k.detach().to(torch.bfloat16).float() for k in K]      # the forward multiplied by bf16-rounded weights
-    H = saved
-    gK = [None] * 12; gB = [None] * 12
-    d_raw = d_raw.float()
-    d_rgb, d_sig = d_raw[:, :3], d_raw[:, 3:4]
-    pe = _pos_enc_torch(pos, 10).to(torch.bfloat16).float()
-    de = _pos_enc_torch(dirs, 4).to(torch.bfloat16).float()
-    h9 = H[9][:, :128].float()
-    gK[11] = h9.t() @ d_rgb; gB[11] = d_rgb.sum(0)
-    dz = (d_rgb @ Wb[11].t()) * (h9 > 0)
-    x10 = torch.cat([H[8].float(), de], dim=-1)
-    gK[10] = x10.t() @ dz; gB[10] = dz.sum(0)
-    dbott = dz @ Wb[10][:256].t()
-    del x10, dz
-    h7 = H[7].float()
-    gK[9] = h7.t() @ dbott; gB[9] = dbott.sum(0)
-    gK[8] = h7.t() @ d_sig; gB[8] = d_sig.sum(0)
-    dz = (dbott @ Wb[9].t() + d_sig @ Wb[8].t()) * (h7 > 0)
-    del dbott, h7
-    for l in range(7, -1, -1):
-        if l == 0:
-            x = pe
-        elif l == 5:
-            x = torch.cat([H[4].float(), pe], dim=-1)
-        else:
-            x = H[l - 1].float()
-        gK[l] = x.t() @ dz; gB[l] = dz.sum(0)
-        if l > 0:
-            dz = (dz @ Wb[l][:256].t()) * (H[l - 1] > 0)
-        del x
-    out = []
-    for i in range(12):
-        out += [gK[i].reshape(K[i].shape), gB[i].reshape(params[2 * i + 1].shape)]
-    return out
 
 
 def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params):
