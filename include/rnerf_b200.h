@@ -121,6 +121,10 @@ size_t rnerf_bkgd_weight_floats(void);
 int rnerf_bkgd_mlp_fwd(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
                        float* raw_out, void* stream);
 
+/* backward of the above wrt the 5 Dense layers: gw (same flat layout as w, fp32) is ACCUMULATED into; d_raw: [B][3]. */
+int rnerf_bkgd_mlp_bwd(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
+                       const float* d_raw, float* gw, void* stream);
+
 /* ---- a11+a12: rnerf/models.py:334-338 activations + rnerf/model_utils.py:247-309 volumetric_rendering ----
  * raw: [B][Ns][4]; t: [B][Ns]; dirs: [B][Ns][3]; bkgd_raw: [B][3] or NULL (rgb_bkgd=None);
  * mask: [B][Ns] fp32 or NULL.  Outputs (any may be NULL except comp_rgb): comp_rgb[B][3], distance[B],

@@ -48,6 +48,7 @@ SIGNATURES = {
     "rnerf_mlp_head_grad": (C.c_int, [C.c_void_p, c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_bkgd_weight_floats": (C.c_size_t, []),
     "rnerf_bkgd_mlp_fwd": (C.c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, C.c_void_p]),
+    "rnerf_bkgd_mlp_bwd": (C.c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_composite_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,
                                       C.c_double, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_composite_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,

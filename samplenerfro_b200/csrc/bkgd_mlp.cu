@@ -105,6 +105,149 @@ __global__ void __launch_bounds__(BK_W) bkgd_mlp_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Backward of the background MLP (train.py differentiates bkgd_mlp through comp_rgb and the env-map smoothness term):
+// the forward is recomputed per 32-ray tile with every layer's activations kept in shared memory, then the chain
+//   dz_l = (K_{l+1} dz_{l+1}) * relu'(h_l),  gK_l += X_l^T dz_l,  gb_l += sum_r dz_l
+// runs layer by layer; weight gradients are accumulated into `gw` (same flat layout as `w`) with red.global.add.
+// ---------------------------------------------------------------------------------------------------------
+// acc[r] += sum_j W[i][j] * in[j][r]   (thread i reads row i of a row-major [rows][ld] matrix: transposed use of K)
+__device__ __forceinline__ void dense_accum_t(float (&acc)[BK_R], const float* __restrict__ W, int ld, int ncols, int i,
+                                              const float* __restrict__ in) {
+  const float* wrow = W + (size_t)i * ld;
+  for (int j = 0; j < ncols; ++j) {
+    const float w = __ldg(wrow + j);
+    const float4* row = reinterpret_cast<const float4*>(in + j * BK_PITCH);
+#pragma unroll
+    for (int r4 = 0; r4 < BK_R / 4; ++r4) {
+      float4 a = row[r4];
+      acc[4 * r4 + 0] = fmaf(a.x, w, acc[4 * r4 + 0]);
+      acc[4 * r4 + 1] = fmaf(a.y, w, acc[4 * r4 + 1]);
+      acc[4 * r4 + 2] = fmaf(a.z, w, acc[4 * r4 + 2]);
+      acc[4 * r4 + 3] = fmaf(a.w, w, acc[4 * r4 + 3]);
+    }
+  }
+}
+
+// gK[k][j] += sum_r X[k][r] * dz[j][r] for k < K (thread j holds dz[j][:] in registers); gb[j] += sum_r dz[j][r]
+__device__ __forceinline__ void wgrad_rows(const float (&dz)[BK_R], const float* __restrict__ X, int K, int j, int ld_out,
+                                           float* __restrict__ gK) {
+  for (int k = 0; k < K; ++k) {
+    const float4* row = reinterpret_cast<const float4*>(X + k * BK_PITCH);
+    float s = 0.f;
+#pragma unroll
+    for (int r4 = 0; r4 < BK_R / 4; ++r4) {
+      float4 a = row[r4];
+      s = fmaf(a.x, dz[4 * r4 + 0], s); s = fmaf(a.y, dz[4 * r4 + 1], s);
+      s = fmaf(a.z, dz[4 * r4 + 2], s); s = fmaf(a.w, dz[4 * r4 + 3], s);
+    }
+    atomicAdd(gK + (size_t)k * ld_out + j, s);
+  }
+}
+
+__global__ void __launch_bounds__(BK_W) bkgd_mlp_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dirs,
+                                                            int64_t n_rays, int64_t dir_stride, const float* __restrict__ d_raw,
+                                                            float* __restrict__ gw) {
+  extern __shared__ __align__(16) float sm[];
+  float* E = sm;                               // [27][36]
+  float* Hs = E + BK_IN * BK_PITCH;            // [4][128][36]  post-activation outputs of Dense_0..3
+  float* D = Hs + 4 * BK_W * BK_PITCH;         // [128][36]     current dz
+  const int j = threadIdx.x;
+  const int64_t ray0 = blockIdx.x * (int64_t)BK_R;
+  for (int e = j; e < BK_IN * BK_R; e += BK_W) {
+    const int r = e % BK_R, f = e / BK_R;
+    const int64_t ray = min(ray0 + r, n_rays - 1);
+    const float* d = dirs + ray * dir_stride;
+    float v;
+    if (f < 3) {
+      v = __ldg(d + f);
+    } else {
+      const int q = (f - 3) % 12, k = q / 3, c = q % 3;
+      float xb = mul(__ldg(d + c), (float)(1 << k));
+      if (f >= 15) xb = add(xb, 1.57079632679489661923f);
+      v = sinf(xb);
+    }
+    E[f * BK_PITCH + r] = v;
+  }
+  __syncthreads();
+  float acc[BK_R];
+  // ---- forward recompute, keeping h0..h3
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+  dense_accum(acc, w + BK_K0, BK_IN, j, E);
+  store_relu(acc, __ldg(w + BK_B0 + j), Hs + (0 * BK_W + j) * BK_PITCH);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+  dense_accum(acc, w + BK_K1, BK_W, j, Hs);
+  store_relu(acc, __ldg(w + BK_B1 + j), Hs + (1 * BK_W + j) * BK_PITCH);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+  dense_accum(acc, w + BK_K2, BK_W, j, Hs + 1 * BK_W * BK_PITCH);
+  store_relu(acc, __ldg(w + BK_B2 + j), Hs + (2 * BK_W + j) * BK_PITCH);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+  dense_accum(acc, w + BK_K3, BK_W, j, Hs + 2 * BK_W * BK_PITCH);
+  dense_accum(acc, w + BK_K3 + BK_W * BK_W, BK_IN, j, E);
+  store_relu(acc, __ldg(w + BK_B3 + j), Hs + (3 * BK_W + j) * BK_PITCH);
+  __syncthreads();
+  // ---- output layer Dense_4 (128 -> 3): thread j = hidden unit
+  float dy[3][BK_R];
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) {
+    const bool live = ray0 + r < n_rays;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dy[c][r] = live ? __ldg(d_raw + (ray0 + r) * 3 + c) : 0.f;
+  }
+  {
+    const float* h3 = Hs + (3 * BK_W + j) * BK_PITCH;
+    const float k0 = __ldg(w + BK_K4 + j * 3), k1 = __ldg(w + BK_K4 + j * 3 + 1), k2 = __ldg(w + BK_K4 + j * 3 + 2);
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < BK_R; ++r) {
+      const float h = h3[r];
+      g0 = fmaf(h, dy[0][r], g0); g1 = fmaf(h, dy[1][r], g1); g2 = fmaf(h, dy[2][r], g2);
+      acc[r] = h > 0.f ? (k0 * dy[0][r] + k1 * dy[1][r] + k2 * dy[2][r]) : 0.f;     // dz3[j][r]
+    }
+    atomicAdd(gw + BK_K4 + j * 3, g0); atomicAdd(gw + BK_K4 + j * 3 + 1, g1); atomicAdd(gw + BK_K4 + j * 3 + 2, g2);
+    if (j < 3) {
+      float sb = 0.f;
+#pragma unroll
+      for (int r = 0; r < BK_R; ++r) sb += (j == 0 ? dy[0][r] : (j == 1 ? dy[1][r] : dy[2][r]));
+      atomicAdd(gw + BK_B4 + j, sb);
+    }
+  }
+  // ---- hidden layers 3 -> 0: acc[] holds dz_l[j][:]
+  for (int l = 3; l >= 0; --l) {
+    float sb = 0.f;
+#pragma unroll
+    for (int r = 0; r < BK_R; ++r) sb += acc[r];
+    atomicAdd(gw + (l == 3 ? BK_B3 : (l == 2 ? BK_B2 : (l == 1 ? BK_B1 : BK_B0))) + j, sb);
+    const float* Kl = w + (l == 3 ? BK_K3 : (l == 2 ? BK_K2 : (l == 1 ? BK_K1 : BK_K0)));
+    float* gKl = gw + (l == 3 ? BK_K3 : (l == 2 ? BK_K2 : (l == 1 ? BK_K1 : BK_K0)));
+    if (l == 0) {
+      wgrad_rows(acc, E, BK_IN, j, BK_W, gKl);                                   // X_0 = encoding
+      break;
+    }
+    wgrad_rows(acc, Hs + (l - 1) * BK_W * BK_PITCH, BK_W, j, BK_W, gKl);         // X_l = h_{l-1} ...
+    if (l == 3) wgrad_rows(acc, E, BK_IN, j, BK_W, gKl + BK_W * BK_W);           // ... and the skip-concatenated encoding
+    // publish dz_l, then dh_{l-1}[i][r] = sum_j K_l[i][j] dz_l[j][r]
+    float4* drow = reinterpret_cast<float4*>(D + j * BK_PITCH);
+#pragma unroll
+    for (int r4 = 0; r4 < BK_R / 4; ++r4) drow[r4] = make_float4(acc[4 * r4], acc[4 * r4 + 1], acc[4 * r4 + 2], acc[4 * r4 + 3]);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
+    dense_accum_t(acc, Kl, BK_W, BK_W, j, D);
+    const float* hprev = Hs + ((l - 1) * BK_W + j) * BK_PITCH;
+#pragma unroll
+    for (int r = 0; r < BK_R; ++r) acc[r] = hprev[r] > 0.f ? acc[r] : 0.f;
+    __syncthreads();      // everyone has read D before the next layer overwrites it
+  }
+}
+
 }  // namespace rnerf
 
 using namespace rnerf;
@@ -120,4 +263,24 @@ extern "C" int rnerf_bkgd_mlp_fwd(const float* w, const float* dirs, int64_t n_r
                                                                                             dir_stride_floats, raw_out);
   count_launch();
   return check_launch("rnerf_bkgd_mlp_fwd");
+}
+
+extern "C" int rnerf_bkgd_mlp_bwd(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
+                                  const float* d_raw, float* gw, void* stream) {
+  RNERF_REQUIRE(n_rays >= 0 && dir_stride_floats >= 3, RNERF_E_SHAPE, "rnerf_bkgd_mlp_bwd: bad sizes");
+  if (n_rays == 0) return 0;
+  RNERF_REQUIRE_PTR(w); RNERF_REQUIRE_PTR(dirs); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(gw);
+  const size_t smem = (size_t)(BK_IN + 5 * BK_W) * BK_PITCH * sizeof(float);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(bkgd_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("rnerf_bkgd_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set[dev] = true;
+  }
+  bkgd_mlp_bwd_kernel<<<(unsigned)((n_rays + BK_R - 1) / BK_R), BK_W, smem, (cudaStream_t)stream>>>(w, dirs, n_rays,
+                                                                                                   dir_stride_floats, d_raw, gw);
+  count_launch();
+  return check_launch("rnerf_bkgd_mlp_bwd");
 }
