@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
   const int n_mblk = a.kx / 128;                    // M-blocks of the gradient (1 or 2)
   const int m_rows = 128;                           // UMMA M
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(bar_full(s), 256); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
@@ -372,16 +372,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
       umma_commit(bar_done);
     }
   } else if (warp >= 2) {
-    // ---- loaders: 256 threads copy one stage (rows x {X, dZ}) with 16-byte cp.async into the swizzled MN-major tiles
+    // ---- loaders: 256 threads copy one stage (rows x {X, dZ}) with 16-byte cp.async into the swizzled MN-major tiles.
+    // Software pipeline: the copies of stage `it` are issued before the wait on stage `it-1`, so one stage of loads is
+    // always in flight behind the one being published.
     const int tid = threadIdx.x - 64;
     float colsum = 0.f;                        // thread tid owns dZ column tid (if < n)
-    int stage = 0; uint32_t phase = 0;
-    for (int it = 0; it < n_steps; ++it) {
-      mbar_wait(bar_empty(stage), phase ^ 1);
+    const int xunits = a.kx / 8, zunits = a.n / 8;     // 16-byte units per row
+    auto issue = [&](int it, int stage) {
       uint8_t* xs = smem + SL::ST_OFF + stage * WG_STAGE_BYTES;
       uint8_t* zs = xs + WG_ROWS * 256 * 2;
       const int64_t rbase = row0 + (int64_t)it * WG_ROWS;
-      const int xunits = a.kx / 8, zunits = a.n / 8;     // 16-byte units per row
       for (int e = tid; e < WG_ROWS * xunits; e += 256) {
         const int r = e / xunits, u = e % xunits;
         const int64_t gr = rbase + r;
@@ -395,18 +395,38 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
         const uint32_t off = (uint32_t)(((r >> 3) * zatoms + (u >> 3)) * 1024 + (r & 7) * 128 + (((u & 7) ^ (r & 7)) << 4));
         cp_async16(smem_u32(zs + off), a.dZ + (size_t)min(gr, a.n_samples - 1) * 256 + u * 8, gr < row1);
       }
-      cp_async_commit_wait_all();
-      // bias gradient: column sums of the dZ tile, read back from the staged tile (own writes + others' after the barrier
-      // would need a sync; use the global values instead: one coalesced 2-byte read per row)
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // publish a completed stage: all 256 loaders' copies have landed (named barrier), bias gradient from the staged dZ
+    // tile (column tid: element (r, tid) sits in atom (r/8, tid/64), row r%8, unit ((tid%64)/8) ^ (r%8)), then one arrive
+    auto publish = [&](int stage) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (a.gb != nullptr && tid < a.n) {
+        const uint8_t* zs = smem + SL::ST_OFF + stage * WG_STAGE_BYTES + WG_ROWS * 256 * 2;
+        const int mm = tid >> 6, u = (tid & 63) >> 3, w = tid & 7;
+#pragma unroll 8
         for (int r = 0; r < WG_ROWS; ++r) {
-          const int64_t gr = rbase + r;
-          if (gr < row1) colsum += __bfloat162float(a.dZ[(size_t)gr * 256 + tid]);
+          const uint32_t off = (uint32_t)(((r >> 3) * zatoms + mm) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4) + w * 2);
+          colsum += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(zs + off));
         }
       }
       fence_proxy_async();
-      mbar_arrive(bar_full(stage));
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // every loader has fenced its writes (and read its column)
+      if (tid == 0) mbar_arrive(bar_full(stage));
+    };
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < n_steps; ++it) {
+      mbar_wait(bar_empty(stage), phase ^ 1);
+      issue(it, stage);
+      if (it > 0) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group: stage it-1 is complete
+        publish(stage == 0 ? WG_STAGES - 1 : stage - 1);
+      }
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (n_steps > 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      publish(stage == 0 ? WG_STAGES - 1 : stage - 1);
     }
     if (a.gb != nullptr && tid < a.n && n_steps > 0) atomicAdd(a.gb + tid, colsum);
     // ---- epilogue: accumulators -> red.global.add into gW.  TMEM lane = gradient row (X column) within the M-block.
