@@ -240,12 +240,16 @@ def main():
         sampler.start()
         l0 = _lib.launch_count()
         record["on"] = with_events
+        if with_events:      # `ncu --profile-from-start off` captures exactly the timed region (no-op otherwise)
+            torch.cuda.cudart().cudaProfilerStart()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
+        if with_events:
+            torch.cuda.cudart().cudaProfilerStop()
         record["on"] = False
         sampler.stop_flag = True
         sampler.join()

@@ -354,173 +354,3 @@ def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params):
     for k, b in zip(ks, bs):
         out += [k, b]
     return out
-
-
-# ---------------------------------------------------------------- compositing (a11, a12)
-def composite_fwd(raw, t, dirs, bkgd_raw=None, mask=None, white_bkgd=False, rgb_padding=0.001, sigma_bias=-1.0,
-                  want_weights=True, want_alpha=False):
-    """activations + volumetric_rendering (rnerf/models.py:334-349, rnerf/model_utils.py:247-309).
-    raw [B,Ns,4], t [B,Ns], dirs [B,Ns,3] -> dict(comp_rgb, distance, acc, weights, alpha, trans, trans_rgb_bkgd)."""
-    raw = _chk(raw, "raw"); t = _chk(t, "t"); dirs = _chk(dirs, "dirs")
-    B, Ns = t.shape
-    dev = t.device
-    o = {"comp_rgb": torch.empty(B, 3, device=dev), "distance": torch.empty(B, device=dev),
-         "acc": torch.empty(B, device=dev), "trans": torch.empty(B, 1, device=dev),
-         "trans_rgb_bkgd": torch.empty(B, 3, device=dev),
-         "weights": torch.empty(B, Ns, device=dev) if want_weights else None,
-         "alpha": torch.empty(B, Ns, device=dev) if want_alpha else None}
-    if bkgd_raw is not None:
-        _chk(bkgd_raw, "bkgd_raw")
-    if mask is not None:
-        _chk(mask, "mask")
-    check(_lib.load().rnerf_composite_fwd(_p(raw), _p(t), _p(dirs), _p(bkgd_raw), _p(mask), B, Ns, int(white_bkgd),
-                                          float(rgb_padding), float(sigma_bias), _p(o["comp_rgb"]), _p(o["distance"]),
-                                          _p(o["acc"]), _p(o["weights"]), _p(o["alpha"]), _p(o["trans"]),
-                                          _p(o["trans_rgb_bkgd"]), _stream()), "rnerf_composite_fwd")
-    return o
-
-
-def composite_bwd(raw, t, dirs, bkgd_raw, mask, d_comp_rgb, d_trans, d_trb, white_bkgd=False, rgb_padding=0.001,
-                  sigma_bias=-1.0):
-    raw = _chk(raw, "raw"); t = _chk(t, "t"); dirs = _chk(dirs, "dirs")
-    B, Ns = t.shape
-    d_raw = torch.empty(B, Ns, 4, device=t.device)
-    d_bk = torch.empty(B, 3, device=t.device) if bkgd_raw is not None else None
-    for nm, x in (("d_comp_rgb", d_comp_rgb), ("d_trans", d_trans), ("d_trb", d_trb)):
-        if x is not None:
-            _chk(x, nm)
-    check(_lib.load().rnerf_composite_bwd(_p(raw), _p(t), _p(dirs), _p(bkgd_raw), _p(mask), B, Ns, int(white_bkgd),
-                                          float(rgb_padding), float(sigma_bias), _p(d_comp_rgb), _p(d_trans), _p(d_trb),
-                                          _p(d_raw), _p(d_bk), _stream()), "rnerf_composite_bwd")
-    return d_raw, d_bk
-
-
-# ---------------------------------------------------------------- resampling (a13, a14)
-def resample(path, t_c, weights_c, u, n_fine: int, want_grad: bool = False):
-    """sorted_piecewise_constant_pdf + sample_pdf (rnerf/model_utils.py:312-435).
-    u: [Nf] (shared) or [B,Nf] sorted CDF positions.  Returns t_f [B,Nc+Nf], pos_f, dir_f, grad_f."""
-    _chk(path, "path"); t_c = _chk(t_c, "t_c"); weights_c = _chk(weights_c, "weights_c"); u = _chk(u, "u")
-    B, S, _ = path.shape
-    Nc = t_c.shape[1]
-    per_ray = 1 if u.dim() == 2 else 0
-    assert u.shape[-1] == n_fine and (not per_ray or u.shape[0] == B)
-    Nt = Nc + n_fine
-    dev = path.device
-    t_f = torch.empty(B, Nt, device=dev); pos_f = torch.empty(B, Nt, 3, device=dev); dir_f = torch.empty(B, Nt, 3, device=dev)
-    grad_f = torch.empty(B, Nt, 3, device=dev) if want_grad else None
-    check(_lib.load().rnerf_resample(_p(path), B, S, _p(t_c), _p(weights_c), Nc, _p(u), per_ray, n_fine, _p(t_f),
-                                     _p(pos_f), _p(dir_f), _p(grad_f), _stream()), "rnerf_resample")
-    return t_f, pos_f, dir_f, grad_f
-
-
-def bbox_tail_mask(pos: torch.Tensor, lo, hi):
-    """rnerf/models.py:498-503: mask = reverse-cumsum(inside bbox) > 0; returns (mask, 1 - mask) [B,Ns]."""
-    pos = _chk(pos, "pos")
-    B, Ns, _ = pos.shape
-    m = torch.empty(B, Ns, device=pos.device); im = torch.empty(B, Ns, device=pos.device)
-    check(_lib.load().rnerf_bbox_tail_mask(_p(pos), B, Ns, Dbl3(*[float(v) for v in lo]), Dbl3(*[float(v) for v in hi]),
-                                           _p(m), _p(im), _stream()), "rnerf_bbox_tail_mask")
-    return m, im
-
-
-def encmlp_fwd_profile(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tensor):
-    """Development aid: forward + per-layer clock64 stamps of CTA 0 -> (raw, prof[2,10,4] int64)."""
-    pos = _chk(pos, "pos").reshape(-1, 3); dirs = _chk(dirs, "dirs").reshape(-1, 3)
-    M = pos.shape[0]
-    raw = torch.empty(M, 4, device=pos.device, dtype=torch.float32)
-    prof = torch.zeros(8, 10, 4, device=pos.device, dtype=torch.int64)
-    check(_lib.load().rnerf_encmlp_fwd_profile(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(prof), _stream()),
-          "rnerf_encmlp_fwd_profile")
-    return raw, prof
-
-
-# ---------------------------------------------------------------- training-mode MLP: forward with saved activations, backward
-def encmlp_fwd_train(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tensor):
-    """Forward that keeps what the backward kernels need: every layer's post-activation output (bf16 [10,M,256])
-    and the two encodings (bf16 [2,M,64]).  Returns (raw [M,4], (layers, enc))."""
-    _chk(packed, "packed", torch.uint8)
-    pos = _chk(pos, "pos").reshape(-1, 3); dirs = _chk(dirs, "dirs").reshape(-1, 3)
-    M = pos.shape[0]
-    raw = torch.empty(M, 4, device=pos.device, dtype=torch.float32)
-    layers = torch.empty(10, M, 256, device=pos.device, dtype=torch.bfloat16)
-    enc = torch.empty(2, M, 64, device=pos.device, dtype=torch.bfloat16)
-    check(_lib.load().rnerf_encmlp_fwd_train(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(layers), _p(enc), _stream()),
-          "rnerf_encmlp_fwd_train")
-    return raw, (layers, enc)
-
-
-def mlp_dgrad_pack(kernels) -> torch.Tensor:
-    """Transposed-weight image for the dgrad chain (rebuilt whenever the weights change)."""
-    lib = _lib.load()
-    out = torch.empty(lib.rnerf_mlp_dgrad_packed_bytes(), device=kernels[0].device, dtype=torch.uint8)
-    kp = (C.c_void_p * 12)(*[_chk(k, "kernel").data_ptr() for k in kernels])
-    check(lib.rnerf_mlp_dgrad_pack(kp, _p(out), _stream()), "rnerf_mlp_dgrad_pack")
-    return out
-
-
-def mlp_wgrad(x: torch.Tensor, x_cols: int, kx_valid: int, dz: torch.Tensor, n: int, gw: torch.Tensor,
-              gb: Optional[torch.Tensor]) -> None:
-    """gw[kx_valid, n] += x[:, :x_cols]^T dz[:, :n];  gb[n] += colsum(dz[:, :n]).  x: bf16 [M, ldx], dz: bf16 [M, 256]."""
-    assert x.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16 and x.is_contiguous() and dz.is_contiguous()
-    assert gw.dtype == torch.float32 and gw.is_contiguous() and gw.shape == (kx_valid, n)
-    M = x.shape[0]
-    check(_lib.load().rnerf_mlp_wgrad(_p(x), x.shape[1], int(x_cols), int(kx_valid), _p(dz), int(n), M, _p(gw), _p(gb), _stream()),
-          "rnerf_mlp_wgrad")
-
-
-def encmlp_bwd(packed, pos, dirs, saved, d_raw, params):
-    """Backward of pos_enc + NerfMLP wrt the 12 Dense layers: fused tcgen05 dgrad chain (dZ of every layer), then one
-    MN-major tcgen05 wgrad per layer (+ the two skinny heads on CUDA cores).  Returns [gK0, gb0, ..., gK11, gb11]."""
-    layers, enc = saved
-    M = layers.shape[1]
-    lib = _lib.load()
-    K = [p for p in params[0::2]]
-    dev = layers.device
-    d_raw = _chk(d_raw.contiguous(), "d_raw")
-    dgp = mlp_dgrad_pack(K)
-    dz = torch.empty(10, M, 256, device=dev, dtype=torch.bfloat16)
-    check(lib.rnerf_mlp_dgrad(_p(dgp), _p(packed), _p(layers), _p(d_raw), M, _p(dz), _stream()), "rnerf_mlp_dgrad")
-    gK = [torch.zeros_like(k) for k in K]
-    gB = [torch.zeros_like(b) for b in params[1::2]]
-    mlp_wgrad(enc[0], 64, 63, dz[0], 256, gK[0], gB[0])
-    for l in (1, 2, 3, 4, 6, 7):
-        mlp_wgrad(layers[l - 1], 256, 256, dz[l], 256, gK[l], gB[l])
-    mlp_wgrad(layers[4], 256, 256, dz[5], 256, gK[5][:256], gB[5])
-    mlp_wgrad(enc[0], 64, 63, dz[5], 256, gK[5][256:], None)
-    mlp_wgrad(layers[7], 256, 256, dz[8], 256, gK[9], gB[9])
-    mlp_wgrad(layers[8], 256, 256, dz[9], 128, gK[10][:256], gB[10])
-    mlp_wgrad(enc[1], 32, 27, dz[9], 128, gK[10][256:], None)
-    heads = torch.zeros(644, device=dev, dtype=torch.float32)
-    check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(heads), _stream()), "rnerf_mlp_head_grad")
-    gK[11] = heads[:384].view(128, 3); gB[11] = heads[384:387]
-    gK[8] = heads[387:643].view(256, 1); gB[8] = heads[643:644]
-    out = []
-    for i in range(12):
-        out += [gK[i], gB[i]]
-    return out
-
-
-def _pos_enc_torch(x: torch.Tensor, max_deg: int) -> torch.Tensor:
-    scales = (2.0 ** torch.arange(max_deg, device=x.device, dtype=torch.float32))
-    xb = (x[:, None, :] * scales[:, None]).reshape(x.shape[0], -1)
-    return torch.cat([x, torch.sin(xb), torch.cos(xb)], dim=-1)
-
-
-def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params):
-    """Backward of the background MLP wrt its 5 Dense layers.  INTERIM (round 1): recomputes the 56k-MAC-per-ray
-    forward with torch ops and differentiates it with torch.autograd (the forward used on the render path is the
-    CUDA kernel)."""
-    flat = dirs.reshape(-1)
-    idx = offset + stride * torch.arange(n_rays, device=dirs.device)
-    d = torch.stack([flat[idx], flat[idx + 1], flat[idx + 2]], dim=-1)
-    with torch.enable_grad():
-        ps = [p.detach().requires_grad_(True) for p in params]
-        enc = _pos_enc_torch(d, 4)
-        x = enc
-        for i in range(4):
-            x = torch.relu(x @ ps[2 * i] + ps[2 * i + 1])
-            if i == 2:
-                x = torch.cat([x, enc], dim=-1)
-        out = x @ ps[8] + ps[9]
-        grads = torch.autograd.grad(out, ps, d_raw)
-    return list(grads)
