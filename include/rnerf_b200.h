@@ -16,12 +16,16 @@
  *   - python floats of the reference (nmin, nmax, near, far) cross the ABI as double and are rounded
  *     to fp32 at the same point the reference rounds them.
  *
- * Path record ("bent sample"): 12 floats per (ray, march step), [B][S][12]:
+ * Path record ("bent sample"): rec_floats = 12 ("full") or 8 ("compact") floats per (ray, march step),
+ * [B][S][rec_floats]:
  *     0..2 ray_pos   3 ray_dist   4..6 direction state v (UN-normalised)   7 idx_data (n)
- *     8..10 idx_grad (grad n)     11 unused (0)
+ *     8..10 idx_grad (grad n)     11 unused (0)                            <- full records only
  *   i.e. the arrays PathSampler.__call__ returns (rnerf/eikonal_utils.py:118-124), interleaved; ray_dir =
  *   safe_l2_normalize(v) (rnerf/eikonal_utils.py:113) is applied by the readers (rnerf_select, rnerf_resample,
  *   rnerf_path_dirs) to the records they use, with the same arithmetic, instead of at every march step.
+ *   Compact records drop idx_grad, which on the render/train path is only read by the online-sparsity term
+ *   (rnerf/models.py:351-357; off in every shipped config) and by the debug outputs.
+ *   t_col [B][S] is an optional dense copy of ray_dist that lets rnerf_resample search in shared memory.
  */
 #ifndef RNERF_B200_H_
 #define RNERF_B200_H_
@@ -33,8 +37,9 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 2
-#define RNERF_PATH_STRIDE 12
+#define RNERF_ABI_VERSION 3
+#define RNERF_PATH_STRIDE 12         /* full records */
+#define RNERF_PATH_STRIDE_COMPACT 8
 
 #define RNERF_E_NULL   (-1)  /* null pointer */
 #define RNERF_E_SHAPE  (-2)  /* bad size / unsupported shape */
@@ -64,18 +69,20 @@ int rnerf_grid_lookup(const float* table, const int ndim_host[3], const double n
                       const double nmax_host[3], const float* pts, int64_t n_pts, float* out, void* stream);
 
 /* ---- a5/a6: rnerf/eikonal_utils.py:30-49,101-124 OneEikonalStep + PathSampler (radiance stage) ----
- * step_size = (far - near) / (S - 1) (rnerf/models.py:121-122).  path: [B][S][12] records. */
+ * step_size = (far - near) / (S - 1) (rnerf/models.py:121-122).  path: [B][S][rec_floats] records; t_col: [B][S]
+ * or NULL.  The first call for a new voxel pitch (ndelta) runs a one-off exhaustive check of the constant-divisor
+ * division used for the grid coordinates and synchronises `stream` once; later calls are asynchronous. */
 int rnerf_march_fwd(const float* table, const float* bricks /* from rnerf_grid_bricks, or NULL */,
                     const int ndim_host[3], const double nmin_host[3], const double nmax_host[3],
                     const float* origins, const float* viewdirs, int64_t n_rays, double near, double far, int n_steps,
-                    float* path, void* stream);
+                    int rec_floats, float* path, float* t_col, void* stream);
 
 /* ray_dir[B][S][3] = safe_l2_normalize(v) of every record: the `ray_dir` array of PathSampler.__call__
  * (rnerf/eikonal_utils.py:113), for callers that want the whole bent path (extract_mesh.py:178). */
-int rnerf_path_dirs(const float* path, int64_t n_rays, int n_steps, float* ray_dir, void* stream);
+int rnerf_path_dirs(const float* path, int rec_floats, int64_t n_rays, int n_steps, float* ray_dir, void* stream);
 
 /* ---- a7: rnerf/models.py:240-247 coarse selection; jitter[Nc] int32 march-step indices ---- */
-int rnerf_select(const float* path, int64_t n_rays, int n_steps, const int32_t* jitter, int n_coarse,
+int rnerf_select(const float* path, int rec_floats, int64_t n_rays, int n_steps, const int32_t* jitter, int n_coarse,
                  float* pos_c, float* dir_c, float* t_c, float* grad_c, void* stream);
 
 /* ---- a8+a9: rnerf/model_utils.py:187-214 pos_enc + :30-90 NerfMLP, fused, bf16 tcgen05 ----
@@ -143,10 +150,11 @@ int rnerf_composite_bwd(const float* raw, const float* t, const float* dirs, con
 /* ---- a13+a14: rnerf/model_utils.py:312-374 sorted_piecewise_constant_pdf + :377-435 sample_pdf ----
  * t_c/weights_c: [B][Nc] coarse distances / compositing weights (the kernel forms the mid-point bins and
  * uses weights[1:-1]); u: [Nf] (u_per_ray=0) or [B][Nf] sorted CDF positions in [0,1).
- * Outputs: t_f[B][Nc+Nf], pos_f/dir_f/grad_f [B][Nc+Nf][3]. */
-int rnerf_resample(const float* path, int64_t n_rays, int n_steps, const float* t_c, const float* weights_c,
-                   int n_coarse, const float* u, int u_per_ray, int n_fine, float* t_f, float* pos_f, float* dir_f,
-                   float* grad_f, void* stream);
+ * path/rec_floats/t_col as written by rnerf_march_fwd (t_col may be NULL: the search then probes the records).
+ * Outputs: t_f[B][Nc+Nf], pos_f/dir_f/grad_f [B][Nc+Nf][3] (grad_f needs full records; may be NULL). */
+int rnerf_resample(const float* path, int rec_floats, const float* t_col, int64_t n_rays, int n_steps, const float* t_c,
+                   const float* weights_c, int n_coarse, const float* u, int u_per_ray, int n_fine, float* t_f,
+                   float* pos_f, float* dir_f, float* grad_f, void* stream);
 
 /* ---- a15: rnerf/models.py:498-503 bd_cut_dist mask: reverse-cumsum(inside bbox) > 0 ---- */
 int rnerf_bbox_tail_mask(const float* pos, int64_t n_rays, int n_samples, const double lo_host[3],

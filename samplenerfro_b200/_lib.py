@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librnerf_b200.so")
+# RNERF_LIB: development aid for A/B runs of two builds of the same sources (never a different implementation)
+LIB_PATH = os.environ.get("RNERF_LIB") or os.path.join(_HERE, "librnerf_b200.so")
 
 _lib: Optional[C.CDLL] = None
 
@@ -32,9 +33,9 @@ SIGNATURES = {
     "rnerf_grid_brick_count": (C.c_int64, [C.POINTER(C.c_int)]),
     "rnerf_grid_bricks": (C.c_int, [c_f32p, C.POINTER(C.c_int), c_f32p, C.c_void_p]),
     "rnerf_march_fwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
-                                  c_f32p, c_i64, C.c_double, C.c_double, C.c_int, c_f32p, C.c_void_p]),
-    "rnerf_path_dirs": (C.c_int, [c_f32p, c_i64, C.c_int, c_f32p, C.c_void_p]),
-    "rnerf_select": (C.c_int, [c_f32p, c_i64, C.c_int, C.c_void_p, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+                                  c_f32p, c_i64, C.c_double, C.c_double, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_path_dirs": (C.c_int, [c_f32p, C.c_int, c_i64, C.c_int, c_f32p, C.c_void_p]),
+    "rnerf_select": (C.c_int, [c_f32p, C.c_int, c_i64, C.c_int, C.c_void_p, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_encmlp_packed_bytes": (C.c_size_t, []),
     "rnerf_encmlp_pack": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "rnerf_encmlp_fwd": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p]),
@@ -53,7 +54,7 @@ SIGNATURES = {
                                       C.c_double, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_composite_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,
                                       C.c_double, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
-    "rnerf_resample": (C.c_int, [c_f32p, c_i64, C.c_int, c_f32p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p,
+    "rnerf_resample": (C.c_int, [c_f32p, C.c_int, c_f32p, c_i64, C.c_int, c_f32p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, c_f32p,
                                  c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_bbox_tail_mask": (C.c_int, [c_f32p, c_i64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                        c_f32p, C.c_void_p]),
@@ -78,8 +79,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rnerf_abi_version() != 2:
-        raise RnerfError(f"ABI version mismatch: library reports {lib.rnerf_abi_version()}, binding expects 2")
+    if lib.rnerf_abi_version() != 3:
+        raise RnerfError(f"ABI version mismatch: library reports {lib.rnerf_abi_version()}, binding expects 3")
     _lib = lib
     return lib
 

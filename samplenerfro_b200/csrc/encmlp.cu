@@ -416,6 +416,7 @@ static int encmlp_fwd_impl(const void* packed, const float* pos, const float* di
   EncMlpArgs a;
   a.packed = (const uint8_t*)packed; a.pos = pos; a.dir = dir; a.n_samples = n_samples;
   a.raw_out = (float4*)raw_out; a.layer_out = (__nv_bfloat16*)layer_out; a.enc_out = (__nv_bfloat16*)enc_out; a.prof = prof; a.n_groups = 0;
+  { const char* d = getenv("RNERF_PAIR_DEBUG"); a.dbg = d ? atoi(d) : 0; }
   if (prof != nullptr && layer_out == nullptr && n_samples >= 74 * 512 && getenv("RNERF_PROFILE_PAIR") != nullptr)
     return launch_encmlp_pair(a, (cudaStream_t)stream);
   const bool dbg = layer_out != nullptr || prof != nullptr;

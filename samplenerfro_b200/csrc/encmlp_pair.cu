@@ -19,6 +19,7 @@
 //   empty[s]  (both)    multicast tcgen05.commit after the slot's last consumer
 //   acc[j]    (both)    multicast tcgen05.commit after tile pair j's K-loop
 //   aready[j] (leader)  16 arrivals: the 8 epilogue warps of tile j in both CTAs (the peer's arrive remotely)
+#include <stdlib.h>
 #include "umma.cuh"
 
 namespace rnerf {
@@ -109,12 +110,24 @@ template <int KIND>
 __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ hw,
                                               uint8_t* __restrict__ a_row, uint32_t r7s, int col0, EpiOut& o) {
   constexpr int NCG = (KIND == 3) ? 2 : 4;
+#ifdef RNERF_PAIR_PIPELINED_LD
+  // two TMEM loads in flight: group cg+1 is fetched while group cg is converted and stored
+  uint32_t vv[2][32];
+  tmem_ld32(taddr, vv[0]);
+#pragma unroll
+  for (int cg = 0; cg < NCG; ++cg) {
+    const int c0 = col0 + cg * 32;          // first of these 32 columns within the layer
+    uint32_t (&v)[32] = vv[cg & 1];
+    tmem_ld_wait();
+    if (cg + 1 < NCG) tmem_ld32(taddr + (cg + 1) * 32, vv[(cg + 1) & 1]);
+#else
 #pragma unroll 1
   for (int cg = 0; cg < NCG; ++cg) {
     const int c0 = col0 + cg * 32;          // first of these 32 columns within the layer
     uint32_t v[32];
     tmem_ld32(taddr + cg * 32, v);
     tmem_ld_wait();
+#endif
     uint32_t pk[16];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
@@ -254,9 +267,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
                 if (first_consumer) {
                   const bool pw = prof && l == 3 && j == 0;     // layer 3, P0: stamps for each of the 4 chunks
                   if (pw) args.prof[240 + i * 4 + 0] = clock64();
-                  mbar_wait(bar_full(s), ph);
+                  if (!(args.dbg & 4)) mbar_wait(bar_full(s), ph);
                   if (pw) args.prof[240 + i * 4 + 1] = clock64();
-                  mbar_wait_cluster(bar_pfull(s), ph);
+                  if (!(args.dbg & 2)) mbar_wait_cluster(bar_pfull(s), ph);
                   if (pw) args.prof[240 + i * 4 + 2] = clock64();
                   tc_fence_after();
                 }
@@ -405,6 +418,10 @@ int launch_encmlp_pair(const EncMlpArgs& a0, cudaStream_t st) {
   a.n_groups = (int)((a.n_samples + 511) / 512);
   int pairs = n_sm / 2;
   if (a.n_groups < pairs) pairs = a.n_groups;
+  if (const char* lim = getenv("RNERF_PAIR_LIMIT")) {       // development aid: run on fewer SM pairs
+    const int l = atoi(lim);
+    if (l > 0 && l < pairs) pairs = l;
+  }
   encmlp_pair_kernel<<<2 * pairs, PAIR_THREADS, PairSmem::BYTES, st>>>(a);
   count_launch();
   return check_launch("rnerf_encmlp_fwd(pair)");

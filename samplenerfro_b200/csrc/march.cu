@@ -7,26 +7,143 @@
 //
 // All state arithmetic uses non-contracted fp32 ops in the reference's association order, so the
 // emitted path is bit-identical to the fp32 oracle.
+//
+// Path layouts (rec_floats):
+//   12 "full"     (pos3, t | v3, n | grad3, 0)  every array PathSampler returns (debug / online-sparsity consumers)
+//    8 "compact"  (pos3, t | v3, n)             what select + resample read on the render/train path of every
+//                                               shipped config (idx_grad is only consumed by the sparsity term)
+// plus an optional dense t column [B][S] (ray_dist) that lets the resampler search in shared memory.
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <mutex>
 #include "common.cuh"
 
 namespace rnerf {
 
 // One thread per ray; a warp is a bundle of 32 consecutive rays (adjacent pixels -> adjacent voxels, so
-// the 8 float4 gathers of a warp land in few cache lines and the grid stays L1/L2 resident).  Records are
+// the gathers of a warp land in few cache lines and the brick map / grid stay L1/L2 resident).  Records are
 // staged through shared memory so that the global stores of a warp are sector-complete and contiguous:
-// STEPS_PER_FLUSH steps x 48 B = 192 B contiguous per ray, all 32 lanes active in every store.
+// STEPS_PER_FLUSH steps x 32 (48) B = 128 (192) B contiguous per ray, all 32 lanes active in every store.
 constexpr int MARCH_THREADS = 128;
-constexpr int STEPS_PER_FLUSH = 4;                     // 4 records = 12 float4 per ray per flush
-constexpr int F4_PER_FLUSH = STEPS_PER_FLUSH * 3;      // 12
-constexpr int STAGE_PITCH = F4_PER_FLUSH + 1;          // +1 float4 pad: conflict-free column writes
+constexpr int STEPS_PER_FLUSH = 4;
+constexpr int T_FLUSH = 16;              // the dense t column is flushed every 16 steps: 64 B (2 full sectors) per ray
 
-__global__ void __launch_bounds__(MARCH_THREADS, 8) march_kernel(const float4* __restrict__ table, GridGeom g,
+struct MarchGeom {
+  GridGeom g;
+  float rdelta[3];   // reciprocal of ndelta, exhaustively verified for the 3-instruction exact division (else unused)
+  int nby, nbz;      // brick grid (y, z extents)
+};
+
+// ---- exact division by a constant ------------------------------------------------------------------------------
+// q = a*y; r = fma(-q, d, a); q' = fma(r, y, q) with y ~ 1/d equals the correctly rounded a/d for MOST (d, a) but not
+// provably all, so a divisor is only used this way after the sequence has been compared with __fdiv_rn for every one
+// of the 2^23 significands of a (verify_recip_kernel).  With no under/overflow in q, r, q' -- guaranteed by the
+// exponent guards in fast_coords() and recip_for() -- the sequence commutes with scaling a by powers of two, so one
+// binade of a covers all of them.
+__device__ __forceinline__ float div_by_const(float a, float d, float y) {
+  const float q = __fmul_rn(a, y);
+  const float r = __fmaf_rn(-q, d, a);
+  return __fmaf_rn(r, y, q);
+}
+
+__global__ void __launch_bounds__(256) verify_recip_kernel(float d, float y, int* __restrict__ bad) {
+  const uint32_t m = blockIdx.x * 256u + threadIdx.x;          // 2^23 significands
+  const float a = __uint_as_float(0x3f800000u | m);
+  if (__float_as_uint(div_by_const(a, d, y)) != __float_as_uint(__fdiv_rn(a, d))) atomicOr(bad, 1);
+}
+
+// returns the verified reciprocal of d, or 0 if the fast sequence must not be used for this divisor
+static float recip_for(float d, cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<uint32_t, float> cache;
+  uint32_t key;
+  memcpy(&key, &d, 4);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  float y = 0.f;
+  if (d == d && fabsf(d) >= 0x1p-30f && fabsf(d) <= 0x1p30f) {
+    const float cand = (float)(1.0 / (double)d);
+    int* bad = nullptr;
+    int host_bad = 1;
+    if (cudaMalloc(&bad, sizeof(int)) == cudaSuccess) {
+      cudaMemsetAsync(bad, 0, sizeof(int), st);
+      verify_recip_kernel<<<(1u << 23) / 256, 256, 0, st>>>(d, cand, bad);
+      count_launch();
+      if (cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)
+        host_bad = 1;
+      cudaFree(bad);
+    }
+    if (!host_bad) y = cand;
+  }
+  cache[key] = y;
+  return y;
+}
+
+// grid coordinates x = (p - nmin) / ndelta of VoxMLP._linear3 (rnerf/ior_utils.py:201-203)
+template <bool FAST>
+__device__ __forceinline__ void grid_coords(const MarchGeom& mg, float px, float py, float pz, float& x, float& y, float& z) {
+  const float ax = sub(px, mg.g.nmin[0]), ay = sub(py, mg.g.nmin[1]), az = sub(pz, mg.g.nmin[2]);
+  if (FAST) {
+    x = div_by_const(ax, mg.g.ndelta[0], mg.rdelta[0]);
+    y = div_by_const(ay, mg.g.ndelta[1], mg.rdelta[1]);
+    z = div_by_const(az, mg.g.ndelta[2], mg.rdelta[2]);
+    const float lo = fminf(fminf(fabsf(ax), fabsf(ay)), fabsf(az)), hi = fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fabsf(az));
+    if (lo >= 0x1p-60f && hi <= 0x1p60f) return;     // false for zeros, subnormals, huge values and NaN
+  }
+  x = divf(ax, mg.g.ndelta[0]); y = divf(ay, mg.g.ndelta[1]); z = divf(az, mg.g.ndelta[2]);
+}
+
+// VoxMLP._linear3 at p (same arithmetic as trilinear() in common.cuh; index clamps done in float, which gives the same
+// integers: xf is integer-valued, so clamp(int(xf), 0, G-1) == int(clamp(xf, 0, G-1)), and the +1 corner likewise)
+template <bool FAST>
+__device__ __forceinline__ float4 march_lookup(const float4* __restrict__ table, const MarchGeom& mg,
+                                               const float* __restrict__ bricks, float px, float py, float pz) {
+  float x, y, z;
+  grid_coords<FAST>(mg, px, py, pz, x, y, z);
+  const float xf = floorf(x), yf = floorf(y), zf = floorf(z);
+  const float xd = sub(x, xf), yd = sub(y, yf), zd = sub(z, zf);
+  const float oxd = sub(1.f, xd), oyd = sub(1.f, yd), ozd = sub(1.f, zd);
+  const float mx = (float)(mg.g.gx - 1), my = (float)(mg.g.gy - 1), mz = (float)(mg.g.gz - 1);
+  const int x0 = (int)fminf(fmaxf(xf, 0.f), mx), y0 = (int)fminf(fmaxf(yf, 0.f), my), z0 = (int)fminf(fmaxf(zf, 0.f), mz);
+  if (bricks != nullptr) {
+    const float c = __ldg(bricks + ((x0 >> BRICK_LOG2) * mg.nby + (y0 >> BRICK_LOG2)) * mg.nbz + (z0 >> BRICK_LOG2));
+    if (c == c) {  // not NaN: homogeneous brick -- the lerps of eight equal corners, gradients exactly 0
+      const float c00 = lerp_ref(c, c, oxd, xd);
+      const float c0 = lerp_ref(c00, c00, oyd, yd);
+      return make_float4(lerp_ref(c0, c0, ozd, zd), 0.f, 0.f, 0.f);
+    }
+  }
+  const int x1 = (int)fminf(fmaxf(add(xf, 1.f), 0.f), mx), y1 = (int)fminf(fmaxf(add(yf, 1.f), 0.f), my),
+            z1 = (int)fminf(fmaxf(add(zf, 1.f), 0.f), mz);
+  const int sx = mg.g.gy * mg.g.gz, sy = mg.g.gz;
+  const int b00 = sx * x0 + sy * y0, b10 = sx * x1 + sy * y0, b01 = sx * x0 + sy * y1, b11 = sx * x1 + sy * y1;
+  const float4 d000 = __ldg(table + b00 + z0), d100 = __ldg(table + b10 + z0);
+  const float4 d001 = __ldg(table + b00 + z1), d101 = __ldg(table + b10 + z1);
+  const float4 d010 = __ldg(table + b01 + z0), d110 = __ldg(table + b11 + z0);
+  const float4 d011 = __ldg(table + b01 + z1), d111 = __ldg(table + b11 + z1);
+  const float4 c00 = lerp4_ref(d000, d100, oxd, xd);
+  const float4 c01 = lerp4_ref(d001, d101, oxd, xd);
+  const float4 c10 = lerp4_ref(d010, d110, oxd, xd);
+  const float4 c11 = lerp4_ref(d011, d111, oxd, xd);
+  const float4 c0 = lerp4_ref(c00, c10, oyd, yd);
+  const float4 c1 = lerp4_ref(c01, c11, oyd, yd);
+  return lerp4_ref(c0, c1, ozd, zd);
+}
+
+template <int RECF4, bool FAST>
+__global__ void __launch_bounds__(MARCH_THREADS, 8) march_kernel(const float4* __restrict__ table, const MarchGeom mg,
                                                               const float* __restrict__ origins,
                                                               const float* __restrict__ viewdirs, int64_t n_rays,
                                                               float near, float step, int n_steps,
-                                                              float4* __restrict__ path,
-                                                              const float* __restrict__ bricks) {
-  __shared__ float4 stage[MARCH_THREADS / 32][32 * STAGE_PITCH];
+                                                              float4* __restrict__ path, float* __restrict__ t_col,
+                                                              const float* __restrict__ bricks, int dbg) {
+  constexpr int F4_PER_FLUSH = STEPS_PER_FLUSH * RECF4;   // float4 per ray per flush: 8 (compact) / 12 (full)
+  constexpr int PITCH = F4_PER_FLUSH + 1;                  // +1 float4 pad: conflict-free column writes
+  __shared__ float4 stage[MARCH_THREADS / 32][32 * PITCH];
+  __shared__ float tstage[MARCH_THREADS / 32][T_FLUSH * 32];        // ray_dist of the last <= 16 steps, [step][lane]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp_ray0 = (blockIdx.x * (int64_t)MARCH_THREADS) + warp * 32;
   if (warp_ray0 >= n_rays) return;
@@ -37,19 +154,40 @@ __global__ void __launch_bounds__(MARCH_THREADS, 8) march_kernel(const float4* _
   float vx = viewdirs[3 * rr], vy = viewdirs[3 * rr + 1], vz = viewdirs[3 * rr + 2];
   float px = add(ox, mul(near, vx)), py = add(oy, mul(near, vy)), pz = add(oz, mul(near, vz));
   float t = near;
-  float4* my_stage = &stage[warp][lane * STAGE_PITCH];
+  float4* my_stage = &stage[warp][lane * PITCH];
   const int rays_here = (int)min((int64_t)32, n_rays - warp_ray0);
+  const int ray_stride4 = n_steps * RECF4;                            // float4 units between consecutive rays
+  const bool t_vec = t_col != nullptr && (n_steps & 3) == 0 && (reinterpret_cast<uintptr_t>(t_col) & 15u) == 0;
+  float* ts = tstage[warp];
+  const bool want_t = t_col != nullptr && !(dbg & 2);
+
+  // cooperative flush mapping, fixed per thread: element e = it*32 + lane -> (ray e / F4, float4 e % F4)
+  //   compact (F4 = 8):  ray = it*4 + (lane >> 3), unit = lane & 7                   -> one (smem, global) base pair
+  //   full    (F4 = 12): 96 = 8 rays x 12 units, so the pattern repeats every 3 iterations -> three base pairs
+  constexpr int NBASE = (RECF4 == 2) ? 1 : 3;
+  constexpr int RAYS_PER_ROUND = (RECF4 == 2) ? 4 : 8;                // rays covered by NBASE iterations
+  int s_off[NBASE], g_off[NBASE];
+#pragma unroll
+  for (int m = 0; m < NBASE; ++m) {
+    const int e = m * 32 + lane, r = e / F4_PER_FLUSH, j = e - r * F4_PER_FLUSH;
+    s_off[m] = r * PITCH + j;
+    g_off[m] = r * ray_stride4 + j;
+  }
+  const float4* s_rd = stage[warp];
+  float4* g_wr = path + warp_ray0 * (int64_t)ray_stride4;             // advanced by F4_PER_FLUSH per flush
+  const int round_stride4 = RAYS_PER_ROUND * ray_stride4;
 
   // one eikonal step: emit the record of the current state, then advance it
-  auto one_step = [&](int kk) {
-    float4 c = trilinear(table, g, px, py, pz, bricks);  // (n, gx, gy, gz) at the pre-update position
+  auto one_step = [&](int kk, int trow) {
+    const float4 c = march_lookup<FAST>(table, mg, bricks, px, py, pz);  // (n, gx, gy, gz) at the pre-update position
     // the direction is stored un-normalised; readers apply safe_l2_normalize (path_dir()) to the few records they
     // use, which keeps 3 IEEE divides + 1 sqrt per step out of the march loop
-    my_stage[kk * 3 + 0] = make_float4(px, py, pz, t);
-    my_stage[kk * 3 + 1] = make_float4(vx, vy, vz, c.x);
-    my_stage[kk * 3 + 2] = make_float4(c.y, c.z, c.w, 0.f);
-    float s = divf(step, c.x);
-    float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
+    my_stage[kk * RECF4 + 0] = make_float4(px, py, pz, t);
+    my_stage[kk * RECF4 + 1] = make_float4(vx, vy, vz, c.x);
+    if (RECF4 == 3) my_stage[kk * RECF4 + 2] = make_float4(c.y, c.z, c.w, 0.f);
+    ts[(trow + kk) * 32 + lane] = t;
+    const float s = divf(step, c.x);
+    const float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
     vx = add(vx, mul(step, c.y)); vy = add(vy, mul(step, c.z)); vz = add(vz, mul(step, c.w));
     t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
     px = nx; py = ny; pz = nz;
@@ -57,47 +195,73 @@ __global__ void __launch_bounds__(MARCH_THREADS, 8) march_kernel(const float4* _
 
   for (int k0 = 0; k0 < n_steps; k0 += STEPS_PER_FLUSH) {
     const int nk = min(STEPS_PER_FLUSH, n_steps - k0);
+    const int trow = k0 & (T_FLUSH - 1);
     if (nk == STEPS_PER_FLUSH) {
 #pragma unroll
-      for (int kk = 0; kk < STEPS_PER_FLUSH; ++kk) one_step(kk);
+      for (int kk = 0; kk < STEPS_PER_FLUSH; ++kk) one_step(kk, trow);
     } else {
-      for (int kk = 0; kk < nk; ++kk) one_step(kk);
+#pragma unroll
+      for (int kk = 0; kk < STEPS_PER_FLUSH; ++kk)
+        if (kk < nk) one_step(kk, trow);
     }
     __syncwarp();
-    // cooperative flush: element e -> (ray e / n4, float4 e % n4); consecutive lanes write consecutive bytes
-    float4* wbase = path + (warp_ray0 * (int64_t)n_steps + k0) * 3;   // one 64-bit base per flush, 32-bit offsets below
-    const int ray_stride4 = n_steps * 3;                               // float4 units between consecutive rays
-    if (nk == STEPS_PER_FLUSH && rays_here == 32) {
-      // common case: compile-time trip count and divisor (e / 12 is a multiply-shift)
+    if (want_t && (trow + nk == T_FLUSH || k0 + nk >= n_steps)) {
+      // dense t column: lanes 4r..4r+3 write the 16 staged steps of ray r as four float4 (64 B, sector-complete)
+      const int filled = trow + nk, kbase = k0 - trow;
+      float* tb = t_col + warp_ray0 * (int64_t)n_steps + kbase;
+      if (filled == T_FLUSH && t_vec) {
 #pragma unroll
-      for (int it = 0; it < F4_PER_FLUSH; ++it) {
-        const int e = it * 32 + lane;
-        const int r = e / F4_PER_FLUSH, j = e - r * F4_PER_FLUSH;
-        __stcs(wbase + r * ray_stride4 + j, stage[warp][r * STAGE_PITCH + j]);
+        for (int it = 0; it < T_FLUSH / 4; ++it) {
+          const int e = it * 32 + lane, r = e >> 2, q = e & 3;
+          if (r < rays_here)
+            __stcs(reinterpret_cast<float4*>(tb + r * n_steps + 4 * q),
+                   make_float4(ts[(4 * q) * 32 + r], ts[(4 * q + 1) * 32 + r], ts[(4 * q + 2) * 32 + r], ts[(4 * q + 3) * 32 + r]));
+        }
+      } else {
+        for (int e = lane; e < rays_here * filled; e += 32) {
+          const int r = e / filled, j = e - r * filled;
+          tb[r * n_steps + j] = ts[j * 32 + r];
+        }
+      }
+    }
+    if (dbg & 1) {
+    } else if (nk == STEPS_PER_FLUSH && rays_here == 32) {
+      // common case: fixed trip count, per-thread offsets, one 64-bit base advanced per round
+      float4* g = g_wr;
+      const float4* sp = s_rd;
+#pragma unroll
+      for (int round = 0; round < 32 / RAYS_PER_ROUND; ++round) {
+#pragma unroll
+        for (int m = 0; m < NBASE; ++m) {
+          if (dbg & 4) g[g_off[m]] = sp[s_off[m]]; else __stcs(g + g_off[m], sp[s_off[m]]);
+        }
+        g += round_stride4;
+        sp += RAYS_PER_ROUND * PITCH;
       }
     } else {
-      const int n4 = nk * 3;
+      const int n4 = nk * RECF4;
       const int total4 = rays_here * n4;
       for (int e = lane; e < total4; e += 32) {
         const int r = e / n4, j = e - r * n4;
-        __stcs(wbase + r * ray_stride4 + j, stage[warp][r * STAGE_PITCH + j]);
+        __stcs(g_wr + r * ray_stride4 + j, s_rd[r * PITCH + j]);
       }
     }
+    g_wr += F4_PER_FLUSH;
     __syncwarp();
   }
 }
 
 // ray_dir of every record, normalised: the array PathSampler returns (rnerf/eikonal_utils.py:113)
-__global__ void __launch_bounds__(256) path_dirs_kernel(const float4* __restrict__ path, int64_t n_rec,
+__global__ void __launch_bounds__(256) path_dirs_kernel(const float4* __restrict__ path, int recf4, int64_t n_rec,
                                                         float* __restrict__ out) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_rec) return;
-  float3 d = path_dir(__ldg(path + i * 3 + 1));
+  float3 d = path_dir(__ldg(path + i * recf4 + 1));
   out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z;
 }
 
 // rnerf/models.py:243-247: ray_pos[:, jitter] etc.
-__global__ void __launch_bounds__(256) select_kernel(const float4* __restrict__ path, int64_t n_rays, int n_steps,
+__global__ void __launch_bounds__(256) select_kernel(const float4* __restrict__ path, int recf4, int64_t n_rays, int n_steps,
                                                      const int32_t* __restrict__ jitter, int n_coarse,
                                                      float* __restrict__ pos_c, float* __restrict__ dir_c,
                                                      float* __restrict__ t_c, float* __restrict__ grad_c) {
@@ -106,7 +270,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float4* __restrict__ 
   int64_t r = i / n_coarse;
   int j = (int)(i % n_coarse);
   int k = min(max(__ldg(jitter + j), 0), n_steps - 1);
-  const float4* rec = path + (r * n_steps + k) * 3;
+  const float4* rec = path + (r * n_steps + k) * recf4;
   float4 a = __ldg(rec), b = __ldg(rec + 1);
   pos_c[3 * i] = a.x; pos_c[3 * i + 1] = a.y; pos_c[3 * i + 2] = a.z;
   t_c[i] = a.w;
@@ -122,46 +286,73 @@ __global__ void __launch_bounds__(256) select_kernel(const float4* __restrict__ 
 
 using namespace rnerf;
 
+// RNERF_MARCH_DIV=ieee forces IEEE divisions for the grid coordinates (results are identical either way)
+static bool fast_div_enabled() {
+  const char* e = getenv("RNERF_MARCH_DIV");      // read per call so that a test can compare both modes in one process
+  return !(e != nullptr && strcmp(e, "ieee") == 0);
+}
+
 extern "C" int rnerf_march_fwd(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
                                const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
-                               double near, double far, int n_steps, float* path, void* stream) {
+                               double near, double far, int n_steps, int rec_floats, float* path, float* t_col,
+                               void* stream) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_fwd: n_rays < 0");
   RNERF_REQUIRE(n_steps >= 2, RNERF_E_SHAPE, "rnerf_march_fwd: n_steps must be >= 2 (step = (far-near)/(S-1))");
+  RNERF_REQUIRE(rec_floats == 8 || rec_floats == 12, RNERF_E_SHAPE, "rnerf_march_fwd: rec_floats must be 8 (compact) or 12 (full)");
   if (n_rays == 0) return 0;
   RNERF_REQUIRE_PTR(origins); RNERF_REQUIRE_PTR(viewdirs); RNERF_REQUIRE_PTR(path);
   RNERF_REQUIRE(aligned16(table) && aligned16(path), RNERF_E_ALIGN, "rnerf_march_fwd: table/path must be 16-byte aligned");
   RNERF_REQUIRE(grid_fits_int32(ndim), RNERF_E_SHAPE, "rnerf_march_fwd: grids with >= 2^31 voxels are not supported");
-  GridGeom g = make_geom(ndim, nmin, nmax);
+  RNERF_REQUIRE((double)n_steps * 12 * 32 < 2147483648.0, RNERF_E_SHAPE, "rnerf_march_fwd: n_steps too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  MarchGeom mg;
+  mg.g = make_geom(ndim, nmin, nmax);
+  mg.nby = (ndim[1] + BRICK - 1) >> BRICK_LOG2;
+  mg.nbz = (ndim[2] + BRICK - 1) >> BRICK_LOG2;
+  bool fast = fast_div_enabled();
+  for (int i = 0; i < 3; ++i) {
+    mg.rdelta[i] = fast ? recip_for(mg.g.ndelta[i], st) : 0.f;
+    fast = fast && mg.rdelta[i] != 0.f;
+  }
   const float step = (float)((far - near) / (n_steps - 1));
+  const char* dbg_env = getenv("RNERF_MARCH_DEBUG");   // development aid: 1 = no record stores, 2 = no t stores, 4 = plain stores
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
   const unsigned blocks = (unsigned)((n_rays + MARCH_THREADS - 1) / MARCH_THREADS);
-  march_kernel<<<blocks, MARCH_THREADS, 0, (cudaStream_t)stream>>>((const float4*)table, g, origins, viewdirs, n_rays,
-                                                                   (float)near, step, n_steps, (float4*)path, bricks);
+#define RNERF_MARCH_LAUNCH(R, F)                                                                                       \
+  march_kernel<R, F><<<blocks, MARCH_THREADS, 0, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
+                                                       step, n_steps, (float4*)path, t_col, bricks, dbg)
+  if (rec_floats == 8) { if (fast) RNERF_MARCH_LAUNCH(2, true); else RNERF_MARCH_LAUNCH(2, false); }
+  else                 { if (fast) RNERF_MARCH_LAUNCH(3, true); else RNERF_MARCH_LAUNCH(3, false); }
+#undef RNERF_MARCH_LAUNCH
   count_launch();
   return check_launch("rnerf_march_fwd");
 }
 
-extern "C" int rnerf_select(const float* path, int64_t n_rays, int n_steps, const int32_t* jitter, int n_coarse,
-                            float* pos_c, float* dir_c, float* t_c, float* grad_c, void* stream) {
+extern "C" int rnerf_select(const float* path, int rec_floats, int64_t n_rays, int n_steps, const int32_t* jitter,
+                            int n_coarse, float* pos_c, float* dir_c, float* t_c, float* grad_c, void* stream) {
   RNERF_REQUIRE(n_rays >= 0 && n_steps > 0 && n_coarse > 0, RNERF_E_SHAPE, "rnerf_select: bad sizes");
+  RNERF_REQUIRE(rec_floats == 8 || rec_floats == 12, RNERF_E_SHAPE, "rnerf_select: rec_floats must be 8 or 12");
+  RNERF_REQUIRE(grad_c == nullptr || rec_floats == 12, RNERF_E_SHAPE, "rnerf_select: grad_c needs the full (12-float) path records");
   if (n_rays == 0) return 0;
   RNERF_REQUIRE_PTR(path); RNERF_REQUIRE_PTR(jitter); RNERF_REQUIRE_PTR(pos_c); RNERF_REQUIRE_PTR(dir_c); RNERF_REQUIRE_PTR(t_c);
   RNERF_REQUIRE(aligned16(path), RNERF_E_ALIGN, "rnerf_select: path must be 16-byte aligned");
   int64_t total = n_rays * n_coarse;
-  select_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)path, n_rays, n_steps,
-                                                                                  jitter, n_coarse, pos_c, dir_c, t_c,
-                                                                                  grad_c);
+  select_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)path, rec_floats / 4, n_rays,
+                                                                                  n_steps, jitter, n_coarse, pos_c, dir_c,
+                                                                                  t_c, grad_c);
   count_launch();
   return check_launch("rnerf_select");
 }
 
-extern "C" int rnerf_path_dirs(const float* path, int64_t n_rays, int n_steps, float* ray_dir, void* stream) {
+extern "C" int rnerf_path_dirs(const float* path, int rec_floats, int64_t n_rays, int n_steps, float* ray_dir, void* stream) {
   RNERF_REQUIRE(n_rays >= 0 && n_steps > 0, RNERF_E_SHAPE, "rnerf_path_dirs: bad sizes");
+  RNERF_REQUIRE(rec_floats == 8 || rec_floats == 12, RNERF_E_SHAPE, "rnerf_path_dirs: rec_floats must be 8 or 12");
   if (n_rays == 0) return 0;
   RNERF_REQUIRE_PTR(path); RNERF_REQUIRE_PTR(ray_dir);
   RNERF_REQUIRE(aligned16(path), RNERF_E_ALIGN, "rnerf_path_dirs: path must be 16-byte aligned");
   const int64_t n = n_rays * n_steps;
-  path_dirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)path, n, ray_dir);
+  path_dirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)path, rec_floats / 4, n, ray_dir);
   count_launch();
   return check_launch("rnerf_path_dirs");
 }

@@ -17,6 +17,7 @@ constexpr int RS_MAX_FINE = 256;
 constexpr int RS_WARPS = 4;
 constexpr int RS_L1_STRIDE = 32;
 constexpr int RS_MAX_L1 = 64;            // first-level table covers n_steps <= 2048; longer paths use the plain search
+constexpr int RS_MAX_TROW = 4096;        // longest path whose t column is staged in shared memory (dynamic smem)
 
 struct ResampleSmem {
   float tc[RS_MAX_COARSE];
@@ -27,13 +28,18 @@ struct ResampleSmem {
   float tk[RS_MAX_L1];   // ray_dist at every RS_L1_STRIDE-th march step (first level of the step search)
 };
 
-__global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const float4* __restrict__ path, int64_t n_rays,
+// `t_col` (optional): the dense ray_dist column [B][S] written by the march.  When present (and S <= RS_MAX_TROW) the
+// ray's column is staged in shared memory with coalesced loads and the step search never touches global memory;
+// otherwise the search probes the strided t field of the path records.
+__global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const float4* __restrict__ path, int recf4,
+                                                                 const float* __restrict__ t_col, int64_t n_rays,
                                                                  int n_steps, const float* __restrict__ t_c,
                                                                  const float* __restrict__ w_c, int nc,
                                                                  const float* __restrict__ u, int u_per_ray, int nf,
                                                                  float* __restrict__ t_f, float* __restrict__ pos_f,
                                                                  float* __restrict__ dir_f, float* __restrict__ grad_f) {
   __shared__ ResampleSmem sm[RS_WARPS];
+  extern __shared__ __align__(16) float trow_all[];      // [RS_WARPS][n_steps] when t_col is staged
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ray = blockIdx.x * (int64_t)RS_WARPS + warp;
   if (ray >= n_rays) return;
@@ -103,17 +109,33 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const float4* _
   // nearest march step strictly below, then linear extrapolation.  ray_dist is increasing along the path, so the
   // count of steps with ray_dist < z is found in two levels: a 32-stride table staged in shared memory (one strided
   // load per lane), then 5 probes inside the 32-step segment instead of 10-11 over the whole path.
-  const float4* rec0 = path + ray * (int64_t)n_steps * 3;
+  const float4* rec0 = path + ray * (int64_t)n_steps * recf4;
   const int n1 = (n_steps + RS_L1_STRIDE - 1) / RS_L1_STRIDE;
-  const bool two_level = n1 <= RS_MAX_L1;
-  if (two_level) {
-    for (int i = lane; i < n1; i += 32) s.tk[i] = __ldg(&rec0[(i * RS_L1_STRIDE) * 3].w);
+  const bool staged = t_col != nullptr;          // host passes t_col only when the dynamic smem was sized for it
+  const bool two_level = !staged && n1 <= RS_MAX_L1;
+  float* trow = trow_all + warp * n_steps;
+  if (staged) {
+    const float* tr = t_col + ray * (int64_t)n_steps;
+    if ((n_steps & 3) == 0 && (reinterpret_cast<uintptr_t>(t_col) & 15u) == 0) {
+      for (int i = lane; i < (n_steps >> 2); i += 32)
+        reinterpret_cast<float4*>(trow)[i] = __ldcs(reinterpret_cast<const float4*>(tr) + i);
+    } else {
+      for (int i = lane; i < n_steps; i += 32) trow[i] = __ldcs(tr + i);
+    }
+    __syncwarp();
+  } else if (two_level) {
+    for (int i = lane; i < n1; i += 32) s.tk[i] = __ldg(&rec0[(i * RS_L1_STRIDE) * recf4].w);
     __syncwarp();
   }
   for (int m = lane; m < nt; m += 32) {
     const float zv = s.merged[m];
     int lo = 0, hi = n_steps;  // count of ray_dist < z
-    if (two_level) {
+    if (staged) {
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (trow[mid] < zv) lo = mid + 1; else hi = mid;
+      }
+    } else if (two_level) {
       int a = 0, b = n1;       // number of table entries < z
       while (a < b) { int mid = (a + b) >> 1; if (s.tk[mid] < zv) a = mid + 1; else b = mid; }
       // entries [0, a) are < z, entry a (if any) is >= z: the count lies in ((a-1)*32, a*32]
@@ -122,11 +144,13 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const float4* _
     }
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
-      if (__ldg(&rec0[mid * 3].w) < zv) lo = mid + 1; else hi = mid;
+      if (__ldg(&rec0[mid * recf4].w) < zv) lo = mid + 1; else hi = mid;
     }
     const int idx = max(lo - 1, 0);
-    const float4 a = __ldg(rec0 + idx * 3), c = __ldg(rec0 + idx * 3 + 2);
-    const float3 b = path_dir(__ldg(rec0 + idx * 3 + 1));
+    const float4 a = __ldg(rec0 + idx * recf4);
+    const float3 b = path_dir(__ldg(rec0 + idx * recf4 + 1));
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grad_f) c = __ldg(rec0 + idx * recf4 + 2);
     const float dz = sub(zv, a.w);
     const int64_t o = ray * nt + m;
     t_f[o] = zv;
@@ -140,10 +164,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32) resample_kernel(const float4* _
 
 using namespace rnerf;
 
-extern "C" int rnerf_resample(const float* path, int64_t n_rays, int n_steps, const float* t_c, const float* weights_c,
-                              int n_coarse, const float* u, int u_per_ray, int n_fine, float* t_f, float* pos_f,
-                              float* dir_f, float* grad_f, void* stream) {
+extern "C" int rnerf_resample(const float* path, int rec_floats, const float* t_col, int64_t n_rays, int n_steps,
+                              const float* t_c, const float* weights_c, int n_coarse, const float* u, int u_per_ray,
+                              int n_fine, float* t_f, float* pos_f, float* dir_f, float* grad_f, void* stream) {
   RNERF_REQUIRE(n_rays >= 0 && n_steps > 0, RNERF_E_SHAPE, "rnerf_resample: bad sizes");
+  RNERF_REQUIRE(rec_floats == 8 || rec_floats == 12, RNERF_E_SHAPE, "rnerf_resample: rec_floats must be 8 or 12");
+  RNERF_REQUIRE(grad_f == nullptr || rec_floats == 12, RNERF_E_SHAPE, "rnerf_resample: grad_f needs the full (12-float) path records");
   RNERF_REQUIRE(n_coarse >= 3 && n_coarse <= RS_MAX_COARSE, RNERF_E_SHAPE, "rnerf_resample: n_coarse=%d unsupported (3..%d)",
                 n_coarse, RS_MAX_COARSE);
   RNERF_REQUIRE(n_fine >= 1 && n_fine <= RS_MAX_FINE, RNERF_E_SHAPE, "rnerf_resample: n_fine=%d unsupported (1..%d)", n_fine,
@@ -152,8 +178,21 @@ extern "C" int rnerf_resample(const float* path, int64_t n_rays, int n_steps, co
   RNERF_REQUIRE_PTR(path); RNERF_REQUIRE_PTR(t_c); RNERF_REQUIRE_PTR(weights_c); RNERF_REQUIRE_PTR(u);
   RNERF_REQUIRE_PTR(t_f); RNERF_REQUIRE_PTR(pos_f); RNERF_REQUIRE_PTR(dir_f);
   RNERF_REQUIRE(aligned16(path), RNERF_E_ALIGN, "rnerf_resample: path must be 16-byte aligned");
-  resample_kernel<<<(unsigned)((n_rays + RS_WARPS - 1) / RS_WARPS), RS_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      (const float4*)path, n_rays, n_steps, t_c, weights_c, n_coarse, u, u_per_ray, n_fine, t_f, pos_f, dir_f, grad_f);
+  const bool staged = t_col != nullptr && n_steps <= RS_MAX_TROW;
+  const size_t dyn = staged ? (size_t)RS_WARPS * n_steps * sizeof(float) : 0;
+  if (dyn > 24 * 1024) {   // static 17 KB + dynamic must be opted into above 48 KB
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_WARPS * RS_MAX_TROW * 4);
+      if (e != cudaSuccess) { set_error("rnerf_resample: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+      attr_set[dev] = true;
+    }
+  }
+  resample_kernel<<<(unsigned)((n_rays + RS_WARPS - 1) / RS_WARPS), RS_WARPS * 32, dyn, (cudaStream_t)stream>>>(
+      (const float4*)path, rec_floats / 4, staged ? t_col : nullptr, n_rays, n_steps, t_c, weights_c, n_coarse, u, u_per_ray,
+      n_fine, t_f, pos_f, dir_f, grad_f);
   count_launch();
   return check_launch("rnerf_resample");
 }

@@ -196,6 +196,7 @@ struct EncMlpArgs {
   __nv_bfloat16* enc_out;    // training dump of the encodings [2][M][64] (pos_enc, dir_enc) or null
   long long* prof;           // development aid: clock64 stamps of CTA 0, [3][10][4], or null
   int n_groups;              // ceil(n_samples / (128*NT))
+  int dbg;                   // development aid (timing experiments only; results are wrong when set)
 };
 
 // pos_enc(x, 0, L) of one 3-vector into columns [0, 3+6L) of this thread's row of a swizzled k-block; the

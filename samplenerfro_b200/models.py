@@ -200,8 +200,11 @@ class NerfModel:
         k1 = None if rng_1 is None else int(rng_1)
         # --- bent-ray march: no trainable inputs in the radiance stage (T7) -> no autograd through it
         with torch.no_grad():
+            # idx_grad is only read by the sparsity term and the debug outputs: every shipped config marches with
+            # compact (pos, t | v, n) records
+            need_grad = debug or self.use_online_sparsity
             path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S,
-                             bricks=self.bricks)
+                             bricks=self.bricks, compact=not need_grad)
             jit = self.draw_jitter(k0) if jitter is None else torch.as_tensor(jitter).to(self.device, torch.int32).contiguous()
             pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=self.use_online_sparsity)
             mask_c = self._bbox_mask(pos_c) if self.use_mask_bbox else None
@@ -243,7 +246,7 @@ class NerfModel:
         ret.append((out_f["comp_rgb"], out_f["distance"], out_f["acc"], trans, trb))
         if debug:
             rp, rd, rt, idn, idg = ops.path_views(path)
-            dbg = {"path": path, "ray_pos": rp, "ray_dir": rd, "ray_dist": rt, "idx_data": idn, "idx_grad": idg,
+            dbg = {"path": path.rec, "ray_pos": rp, "ray_dir": rd, "ray_dist": rt, "idx_data": idn, "idx_grad": idg,
                    "ray_pos_c": pos_c, "jitter": jit, "u": uu, "t_c": t_c, "weights_c": out_c["weights"],
                    "raw_c": raw_c, "raw_f": raw_f, "t_f": t_f, "pos_f": pos_f, "dir_f": dir_f, "raw_bkgd": raw_bkgd}
             return ret, loss_sp, dbg

@@ -6,7 +6,7 @@ There is no alternative implementation: without the library (or a CUDA tensor) t
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, NamedTuple, Optional, Sequence, Tuple
 
 import torch
 
@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import Dbl3, Int3, check
 
 PATH_STRIDE = 12
+PATH_STRIDE_COMPACT = 8
 
 
 def _stream() -> C.c_void_p:
@@ -78,49 +79,77 @@ def grid_bricks(table: torch.Tensor, ndim) -> torch.Tensor:
     return bricks
 
 
+class BentPath(NamedTuple):
+    """The marched path: interleaved records [B,S,12] (full) or [B,S,8] (compact, no idx_grad) and the dense
+    ray_dist column [B,S] (or None).  Layout: include/rnerf_b200.h."""
+    rec: torch.Tensor
+    t: Optional[torch.Tensor]
+
+    @property
+    def compact(self) -> bool:
+        return self.rec.shape[-1] == PATH_STRIDE_COMPACT
+
+
 def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n_steps: int,
-          out: Optional[torch.Tensor] = None, bricks: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124), radiance stage.  Returns path [B,S,12].
-    `bricks` (from grid_bricks) lets the kernel skip the gathers in homogeneous space; results are bit-identical."""
+          out: Optional[BentPath] = None, bricks: Optional[torch.Tensor] = None, compact: bool = False,
+          t_col: bool = True) -> BentPath:
+    """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124), radiance stage.  Returns the BentPath.
+    `bricks` (from grid_bricks) lets the kernel skip the gathers in homogeneous space; results are bit-identical.
+    `compact` drops idx_grad from the records (8 instead of 12 floats per step)."""
     _chk(table, "table"); origins = _chk(origins, "origins"); viewdirs = _chk(viewdirs, "viewdirs")
     if bricks is not None:
         _chk(bricks, "bricks")
     B = origins.shape[0]
+    W = PATH_STRIDE_COMPACT if compact else PATH_STRIDE
     if out is None:
-        out = torch.empty(B, n_steps, PATH_STRIDE, device=origins.device, dtype=torch.float32)
+        rec = torch.empty(B, n_steps, W, device=origins.device, dtype=torch.float32)
+        out = BentPath(rec, torch.empty(B, n_steps, device=origins.device, dtype=torch.float32) if t_col else None)
     else:
-        _chk(out, "out")
-        assert out.shape == (B, n_steps, PATH_STRIDE)
+        _chk(out.rec, "out.rec")
+        assert out.rec.shape == (B, n_steps, W)
+        if out.t is not None:
+            _chk(out.t, "out.t")
+            assert out.t.shape == (B, n_steps)
     nd, lo, hi = _geom(ndim, nmin, nmax)
     check(_lib.load().rnerf_march_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
-                                      float(far), int(n_steps), _p(out), _stream()), "rnerf_march_fwd")
+                                      float(far), int(n_steps), W, _p(out.rec), _p(out.t), _stream()), "rnerf_march_fwd")
     return out
 
 
-def path_dirs(path: torch.Tensor) -> torch.Tensor:
+def _rec(path) -> torch.Tensor:
+    rec = path.rec if isinstance(path, BentPath) else path
+    _chk(rec, "path")
+    if rec.dim() != 3 or rec.shape[-1] not in (PATH_STRIDE, PATH_STRIDE_COMPACT):
+        raise _lib.RnerfError(f"path records must be [B,S,12] or [B,S,8], got {tuple(rec.shape)}")
+    return rec
+
+
+def path_dirs(path) -> torch.Tensor:
     """ray_dir [B,S,3]: safe_l2_normalize of the direction state stored in every record."""
-    _chk(path, "path")
-    B, S, _ = path.shape
-    out = torch.empty(B, S, 3, device=path.device, dtype=torch.float32)
-    check(_lib.load().rnerf_path_dirs(_p(path), B, S, _p(out), _stream()), "rnerf_path_dirs")
+    rec = _rec(path)
+    B, S, W = rec.shape
+    out = torch.empty(B, S, 3, device=rec.device, dtype=torch.float32)
+    check(_lib.load().rnerf_path_dirs(_p(rec), W, B, S, _p(out), _stream()), "rnerf_path_dirs")
     return out
 
 
-def path_views(path: torch.Tensor):
-    """(ray_pos, ray_dir, ray_dist, idx_data, idx_grad) as PathSampler returns them: strided views of the path,
-    except ray_dir which is normalised on demand (the path stores the un-normalised direction state)."""
-    return path[..., 0:3], path_dirs(path), path[..., 3], path[..., 7:8], path[..., 8:11]
+def path_views(path):
+    """(ray_pos, ray_dir, ray_dist, idx_data, idx_grad) as PathSampler returns them: strided views of the records,
+    except ray_dir which is normalised on demand (the path stores the un-normalised direction state).  idx_grad is
+    None for compact records."""
+    rec = _rec(path)
+    return rec[..., 0:3], path_dirs(rec), rec[..., 3], rec[..., 7:8], (rec[..., 8:11] if rec.shape[-1] == PATH_STRIDE else None)
 
 
-def select(path: torch.Tensor, jitter: torch.Tensor, want_grad: bool = False):
+def select(path, jitter: torch.Tensor, want_grad: bool = False):
     """rnerf/models.py:243-247: gather the coarse samples at march-step indices `jitter` (int32 [Nc])."""
-    _chk(path, "path"); jitter = _chk(jitter, "jitter", torch.int32)
-    B, S, _ = path.shape
+    rec = _rec(path); jitter = _chk(jitter, "jitter", torch.int32)
+    B, S, W = rec.shape
     Nc = jitter.numel()
-    dev = path.device
+    dev = rec.device
     pos = torch.empty(B, Nc, 3, device=dev); dirs = torch.empty(B, Nc, 3, device=dev); t = torch.empty(B, Nc, device=dev)
     grad = torch.empty(B, Nc, 3, device=dev) if want_grad else None
-    check(_lib.load().rnerf_select(_p(path), B, S, _p(jitter), Nc, _p(pos), _p(dirs), _p(t), _p(grad), _stream()),
+    check(_lib.load().rnerf_select(_p(rec), W, B, S, _p(jitter), Nc, _p(pos), _p(dirs), _p(t), _p(grad), _stream()),
           "rnerf_select")
     return pos, dirs, t, grad
 
@@ -234,17 +263,20 @@ def composite_bwd(raw, t, dirs, bkgd_raw, mask, d_comp_rgb, d_trans, d_trb, whit
 def resample(path, t_c, weights_c, u, n_fine: int, want_grad: bool = False):
     """sorted_piecewise_constant_pdf + sample_pdf (rnerf/model_utils.py:312-435).
     u: [Nf] (shared) or [B,Nf] sorted CDF positions.  Returns t_f [B,Nc+Nf], pos_f, dir_f, grad_f."""
-    _chk(path, "path"); t_c = _chk(t_c, "t_c"); weights_c = _chk(weights_c, "weights_c"); u = _chk(u, "u")
-    B, S, _ = path.shape
+    rec = _rec(path); t_c = _chk(t_c, "t_c"); weights_c = _chk(weights_c, "weights_c"); u = _chk(u, "u")
+    tcol = path.t if isinstance(path, BentPath) else None
+    if tcol is not None:
+        _chk(tcol, "path.t")
+    B, S, W = rec.shape
     Nc = t_c.shape[1]
     per_ray = 1 if u.dim() == 2 else 0
     assert u.shape[-1] == n_fine and (not per_ray or u.shape[0] == B)
     Nt = Nc + n_fine
-    dev = path.device
+    dev = rec.device
     t_f = torch.empty(B, Nt, device=dev); pos_f = torch.empty(B, Nt, 3, device=dev); dir_f = torch.empty(B, Nt, 3, device=dev)
     grad_f = torch.empty(B, Nt, 3, device=dev) if want_grad else None
-    check(_lib.load().rnerf_resample(_p(path), B, S, _p(t_c), _p(weights_c), Nc, _p(u), per_ray, n_fine, _p(t_f),
-                                     _p(pos_f), _p(dir_f), _p(grad_f), _stream()), "rnerf_resample")
+    check(_lib.load().rnerf_resample(_p(rec), W, _p(tcol), B, S, _p(t_c), _p(weights_c), Nc, _p(u), per_ray, n_fine,
+                                     _p(t_f), _p(pos_f), _p(dir_f), _p(grad_f), _stream()), "rnerf_resample")
     return t_f, pos_f, dir_f, grad_f
 
 

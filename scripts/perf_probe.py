@@ -46,14 +46,16 @@ def main():
     r0 = (a.side * a.side - B) // 2
     o = flat.origins[r0:r0 + B].cuda().contiguous(); d = flat.viewdirs[r0:r0 + B].cuda().contiguous()
     S, Nc, Nf = 768, 64, 128
-    path = torch.empty(B, S, 12, device="cuda")
+    path = ops.BentPath(torch.empty(B, S, 8, device="cuda"), torch.empty(B, S, device="cuda"))
+    path_full = ops.BentPath(torch.empty(B, S, 12, device="cuda"), torch.empty(B, S, device="cuda"))
     jit = model.draw_jitter(1)
     u = model.draw_u(2, B, False)
     pk_c = model._packed(variables, "coarse_mlp"); pk_f = model._packed(variables, "fine_mlp"); wb = model._packed(variables, "bkgd_mlp")
     res = {}
-    res["march"] = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, S, out=path, bricks=model.bricks))
+    res["march_full"] = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, S, out=path_full, bricks=model.bricks))
+    res["march_nobricks"] = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, S, out=path, compact=True))
+    res["march"] = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, S, out=path, bricks=model.bricks, compact=True))
     pos_c, dir_c, t_c, _ = ops.select(path, jit)
-    res["march_nobricks"] = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, S, out=path))
     res["select"] = timeit(lambda: ops.select(path, jit))
     res["bkgd_mlp"] = timeit(lambda: ops.bkgd_mlp_fwd(wb, dir_c, B, Nc * 3, (Nc - 1) * 3))
     raw_b = ops.bkgd_mlp_fwd(wb, dir_c, B, Nc * 3, (Nc - 1) * 3)
@@ -72,7 +74,8 @@ def main():
     for k, (mn, av) in res.items():
         extra = ""
         if k.startswith("march"):
-            extra = f"  {B * (24 + 44 * S) / mn / 1e6:.0f} GB/s algorithmic"
+            wr = B * S * ((48 if k == "march_full" else 32) + 4)
+            extra = f"  {B * (24 + 44 * S) / mn / 1e6:.0f} GB/s algorithmic (reference arrays), {wr / mn / 1e6:.0f} GB/s written"
         if k.startswith("encmlp"):
             M = B * (Nc if k.endswith("coarse") else Nc + Nf)
             extra = f"  {2 * 593408 * M / mn / 1e9:.1f} TFLOP/s"

@@ -42,19 +42,43 @@ def test_lookup_bit_exact(cuda_lib, scene):
     assert torch.equal(out, ref), f"max abs diff {(out - ref).abs().max()}"
 
 
-@pytest.mark.parametrize("B,S,near,far", [(1000, 96, 2.0, 6.0), (257, 768, 2.0, 6.0), (33, 1536, 0.2, 12.0), (1, 7, 2.0, 6.0)])
-def test_march_bit_exact(cuda_lib, scene, B, S, near, far):
-    """Bent sample positions: north_star asks 1e-4 relative; the kernel reproduces the fp32 oracle bit for bit."""
+@pytest.mark.parametrize("compact", [False, True])
+@pytest.mark.parametrize("B,S,near,far", [(1000, 96, 2.0, 6.0), (257, 768, 2.0, 6.0), (33, 1536, 0.2, 12.0), (1, 7, 2.0, 6.0),
+                                          (70, 770, 2.0, 6.0)])
+def test_march_bit_exact(cuda_lib, scene, B, S, near, far, compact):
+    """Bent sample positions: north_star asks 1e-4 relative; the kernel reproduces the fp32 oracle bit for bit, with
+    full (12-float) and compact (8-float, no idx_grad) records, and the dense ray_dist column equals the records'."""
     from samplenerfro_b200 import ops
     o, d = H.random_rays(B, seed=B)
     pos, dirs, dist, n, g = O.march(scene["table"], scene["ndim"], scene["nmin"], scene["nmax"], o, d, near, far, S)
-    path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), near, far, S)
-    rp, rd, rt, idn, idg = [x.cpu() for x in ops.path_views(path)]
+    path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), near, far, S,
+                     compact=compact)
+    assert path.rec.shape == (B, S, 8 if compact else 12)
+    rp, rd, rt, idn, idg = [None if x is None else x.cpu() for x in ops.path_views(path)]
     bent = (dirs[:, -1] - d).abs().max().item()
     assert B < 100 or bent > 1e-3, "test scene does not bend any ray"
-    for name, a, b in (("ray_pos", rp, pos), ("ray_dir", rd, dirs), ("ray_dist", rt, dist), ("idx_data", idn, n),
-                       ("idx_grad", idg, g)):
+    checks = [("ray_pos", rp, pos), ("ray_dir", rd, dirs), ("ray_dist", rt, dist), ("idx_data", idn, n),
+              ("t_col", path.t.cpu(), dist)]
+    if not compact:
+        checks.append(("idx_grad", idg, g))
+    for name, a, b in checks:
         assert torch.equal(a, b), f"{name}: max rel diff {H.rel_err(a, b):.3e}"
+
+
+def test_march_constant_divisor_division_is_exact(cuda_lib, scene, monkeypatch):
+    """The grid coordinates (p - nmin)/ndelta use a 3-instruction division by the (exhaustively verified) constant
+    ndelta; forcing IEEE divisions must not change a bit.  Rays starting exactly on / next to nmin exercise the
+    zero / tiny-numerator guard."""
+    from samplenerfro_b200 import ops
+    o, d = H.random_rays(2000, seed=21)
+    o[:8] = torch.tensor(scene["nmin"]) - 2.0 * d[:8]       # p0 = o + near*d lands on the grid corner
+    o[8:16, 0] = scene["nmin"][0] - 2.0 * d[8:16, 0] + 1e-30
+    args = (scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), 2.0, 6.0, 768)
+    a = ops.march(*args, compact=True)
+    monkeypatch.setenv("RNERF_MARCH_DIV", "ieee")
+    b = ops.march(*args, compact=True)
+    monkeypatch.delenv("RNERF_MARCH_DIV")
+    assert torch.equal(a.rec, b.rec) and torch.equal(a.t, b.t)
 
 
 def test_march_brick_skipping_is_bit_identical(cuda_lib):
@@ -71,8 +95,10 @@ def test_march_brick_skipping_is_bit_identical(cuda_lib):
     o[:50] *= 3.0                                          # some rays never enter the grid (clamp-to-edge lookups)
     a = ops.march(table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768)
     b = ops.march(table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768, bricks=bricks)
-    assert torch.equal(a, b)
-    assert (a[:, -1, 4:7].cpu() - d).abs().max() > 1e-2    # and rays do bend
+    assert torch.equal(a.rec, b.rec) and torch.equal(a.t, b.t)
+    c = ops.march(table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768, bricks=bricks, compact=True)
+    assert torch.equal(c.rec, a.rec[..., :8]) and torch.equal(c.t, a.t)   # compact records = the first 8 floats
+    assert (a.rec[:, -1, 4:7].cpu() - d).abs().max() > 1e-2    # and rays do bend
 
 
 def test_march_constant_grid_kat(cuda_lib):
@@ -82,7 +108,7 @@ def test_march_constant_grid_kat(cuda_lib):
     ndim, nmin, nmax = [G] * 3, [-1.0] * 3, [1.0] * 3
     table = ops.grid_table(torch.full((G ** 3,), n0, device="cuda"), ndim, nmin, nmax)
     o, d = H.random_rays(64, seed=3)
-    path = ops.march(table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, S).cpu().double()
+    path = ops.march(table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, S).rec.cpu().double()
     step = 4.0 / (S - 1)
     k = torch.arange(S, dtype=torch.float64)[None, :, None]
     expect = o.double()[:, None] + 2.0 * d.double()[:, None] + k * (step / n0) * d.double()[:, None]
@@ -98,9 +124,15 @@ def test_select(cuda_lib, scene):
     path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), 2.0, 6.0, 96)
     jit = (torch.arange(0, 96, 12) + torch.randint(0, 12, (8,), generator=torch.Generator().manual_seed(0))).int()
     pos, dirs, t, grad = ops.select(path, jit.cuda(), want_grad=True)
-    pc = path.cpu()
+    pc = path.rec.cpu()
     assert torch.equal(pos.cpu(), pc[:, jit.long(), 0:3]) and torch.equal(dirs.cpu(), ops.path_dirs(path).cpu()[:, jit.long()])
     assert torch.equal(t.cpu(), pc[:, jit.long(), 3]) and torch.equal(grad.cpu(), pc[:, jit.long(), 8:11])
+    cpath = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), 2.0, 6.0, 96,
+                      compact=True)
+    pos2, dirs2, t2, _ = ops.select(cpath, jit.cuda())
+    assert torch.equal(pos2, pos) and torch.equal(dirs2, dirs) and torch.equal(t2, t)
+    with pytest.raises(Exception):
+        ops.select(cpath, jit.cuda(), want_grad=True)       # compact records carry no idx_grad
 
 
 def _composite_inputs(B, Ns, seed):
@@ -151,9 +183,9 @@ def test_composite_bwd(cuda_lib, B, Ns, use_mask):
     assert H.rel_err(d_bk, bk64.grad) < 2e-5, H.rel_err(d_bk, bk64.grad)
 
 
-def _resample_setup(scene, B, randomized, weights_fn):
+def _resample_setup(scene, B, randomized, weights_fn, S=768, P=12):
     from samplenerfro_b200 import ops
-    S, Nc, P, Nf = 768, 64, 12, 128
+    Nc, Nf = 64, 128
     o, d = H.random_rays(B, seed=11)
     path = ops.march(scene["table_cu"], scene["ndim"], scene["nmin"], scene["nmax"], o.cuda(), d.cuda(), 2.0, 6.0, S)
     gen = torch.Generator().manual_seed(4)
@@ -184,6 +216,26 @@ def test_resample(cuda_lib, scene, B, randomized):
     assert (pos_f.cpu() - pos)[same].abs().max().item() < 3e-5
     assert torch.equal(grad_f.cpu()[same], grads[same])
     assert (pos_f.cpu() - pos).abs().max().item() < 2e-4   # even at a tie the extrapolated point is continuous
+    # the three search variants (t column staged in smem / strided two-level / compact records) agree bit for bit
+    strided = ops.resample(ops.BentPath(path.rec, None), t_c.cuda(), w.cuda(), u.cuda(), Nf, want_grad=True)
+    compact = ops.resample(ops.BentPath(path.rec[..., :8].contiguous(), path.t), t_c.cuda(), w.cuda(), u.cuda(), Nf)
+    for a, b in zip((t_f, pos_f, dir_f, grad_f), strided):
+        assert torch.equal(a, b)
+    for a, b in zip((t_f, pos_f, dir_f), compact[:3]):
+        assert torch.equal(a, b)
+
+
+def test_resample_long_path(cuda_lib, scene):
+    """S = 1536 (ball/glass/pen configs): the staged t column needs 24 KB of dynamic shared memory per CTA."""
+    from samplenerfro_b200 import ops
+    path, (rp, rd, rt, rg), jit, t_c, w, u, Nf = _resample_setup(scene, 96, False, lambda r: 0.05 + r, S=1536, P=24)
+    t_mid = 0.5 * (t_c[..., 1:] + t_c[..., :-1])
+    z, pos, dirs, grads = O.sample_pdf(t_mid, w[..., 1:-1], rp, rd, rt, rg, u, jit)
+    t_f, pos_f, dir_f, _ = ops.resample(path, t_c.cuda(), w.cuda(), u.cuda(), Nf)
+    assert (t_f.cpu() - z).abs().max().item() < 2e-5
+    same = (dir_f.cpu() == dirs).all(dim=-1)
+    assert same.float().mean().item() > 0.995
+    assert (pos_f.cpu() - pos)[same].abs().max().item() < 3e-5
 
 
 def test_resample_degenerate_pdf(cuda_lib, scene):

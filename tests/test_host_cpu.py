@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rnerf_abi_version() == 2
+    assert lib.rnerf_abi_version() == 3
     assert lib.rnerf_encmlp_packed_bytes() > 1_000_000 and lib.rnerf_bkgd_weight_floats() == 56448 + 515
 
 
@@ -31,15 +31,15 @@ def test_abi_argument_validation_without_gpu():
     from samplenerfro_b200 import _lib
     lib = _lib.load()
     nd = _lib.Int3(4, 4, 4); lo = _lib.Dbl3(0, 0, 0); hi = _lib.Dbl3(1, 1, 1)
-    rc = lib.rnerf_march_fwd(None, None, nd, lo, hi, None, None, 10, 2.0, 6.0, 768, None, None)
+    rc = lib.rnerf_march_fwd(None, None, nd, lo, hi, None, None, 10, 2.0, 6.0, 768, 12, None, None, None)
     assert rc == -1 and b"null" in lib.rnerf_last_error()
-    rc = lib.rnerf_march_fwd(C.c_void_p(16), None, nd, lo, hi, C.c_void_p(16), C.c_void_p(16), 10, 2.0, 6.0, 1, C.c_void_p(16), None)
+    rc = lib.rnerf_march_fwd(C.c_void_p(16), None, nd, lo, hi, C.c_void_p(16), C.c_void_p(16), 10, 2.0, 6.0, 1, 12, C.c_void_p(16), None, None)
     assert rc == -2 and b"n_steps" in lib.rnerf_last_error()
-    rc = lib.rnerf_resample(C.c_void_p(16), 4, 768, C.c_void_p(16), C.c_void_p(16), 2, C.c_void_p(16), 0, 128,
+    rc = lib.rnerf_resample(C.c_void_p(16), 12, None, 4, 768, C.c_void_p(16), C.c_void_p(16), 2, C.c_void_p(16), 0, 128,
                             C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), None, None)
     assert rc == -2
     assert lib.rnerf_encmlp_fwd(None, None, None, 0, None, None) == 0      # empty input is a no-op
-    assert lib.rnerf_march_fwd(C.c_void_p(16), None, nd, lo, hi, None, None, 0, 2.0, 6.0, 768, None, None) == 0
+    assert lib.rnerf_march_fwd(C.c_void_p(16), None, nd, lo, hi, None, None, 0, 2.0, 6.0, 768, 12, None, None, None) == 0
 
 
 def test_ops_refuse_cpu_tensors():
