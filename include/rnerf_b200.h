@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 3
+#define RNERF_ABI_VERSION 4
 #define RNERF_PATH_STRIDE 12         /* full records */
 #define RNERF_PATH_STRIDE_COMPACT 8
 
@@ -105,7 +105,8 @@ int rnerf_encmlp_fwd_debug(const void* packed, const float* pos, const float* di
  * rnerf_mlp_dgrad: fused tcgen05 chain producing dz_out[10][M][256] (bf16 gradient wrt every layer's pre-activation)
  *   from d_raw[M][4]; dgrad_packed comes from rnerf_mlp_dgrad_pack (transposed weight image, rebuilt when weights change).
  * rnerf_mlp_wgrad: gw[kx_valid][n] += x[:, :x_cols]^T dz (fp32, accumulating), gb[n] += column sums of dz (or NULL).
- * rnerf_mlp_head_grad: out[644] += (gW11[128][3], gb11[3], gW8[256], gb8) from d_raw and the saved activations. */
+ * rnerf_mlp_head_grad: out_rgb_head[387] += (gW11[128][3], gb11[3]), out_sigma_head[257] += (gW8[256], gb8) from d_raw
+ *   and the saved activations (each pair laid out like the Flax (kernel, bias) of Dense_11 / Dense_8). */
 int rnerf_encmlp_fwd_train(const void* packed, const float* pos, const float* dir, int64_t n_samples, float* raw_out,
                            uint16_t* layer_out, uint16_t* enc_out, void* stream);
 size_t rnerf_mlp_dgrad_packed_bytes(void);
@@ -114,7 +115,8 @@ int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed, const uint
                     int64_t n_samples, uint16_t* dz_out, void* stream);
 int rnerf_mlp_wgrad(const uint16_t* x, int ldx, int x_cols, int kx_valid, const uint16_t* dz, int n, int64_t n_samples,
                     float* gw, float* gb, void* stream);
-int rnerf_mlp_head_grad(const uint16_t* layer_out, const float* d_raw, int64_t n_samples, float* out, void* stream);
+int rnerf_mlp_head_grad(const uint16_t* layer_out, const float* d_raw, int64_t n_samples, float* out_rgb_head,
+                        float* out_sigma_head, void* stream);
 
 /* development aid: same as rnerf_encmlp_fwd, plus clock64 stamps of CTA 0: prof[2 roles][10 layers][4] int64
  * (role 0 = MMA issuer: wait-start, A-ready, issued; role 1 = epilogue: wait-start, acc-ready, done). */
@@ -155,6 +157,19 @@ int rnerf_composite_bwd(const float* raw, const float* t, const float* dirs, con
 int rnerf_resample(const float* path, int rec_floats, const float* t_col, int64_t n_rays, int n_steps, const float* t_c,
                    const float* weights_c, int n_coarse, const float* u, int u_per_ray, int n_fine, float* t_f,
                    float* pos_f, float* dir_f, float* grad_f, void* stream);
+
+/* ---- a17: train.py:166-183 gradient clipping + optax.adam (train.py:312-317) on a flat fp32 parameter arena ----
+ * hyper (device, 10 floats): lr, b1, b2, eps, 1-b1^t, 1-b2^t, gradient scale, weight-decay coefficient
+ * (2 weight_decay_mult / numel: the closed-form gradient of train.py:146-150's weight_l2 term), grad_max_val,
+ * grad_max_norm (0 = off).  Per-step scalars are read from device memory so a captured CUDA graph of the step can be
+ * replayed.  The effective gradient is clamp(gscale * grad + wd * theta, +-grad_max_val) * min(1, grad_max_norm /
+ * (1e-7 + sqrt(*norm_sq))); rnerf_grad_sumsq accumulates that squared norm (before the norm factor) into out_accum.
+ * rnerf_sumsq: out_accum[0] += sum x^2 (the weight_l2 statistic). */
+int rnerf_sumsq(const float* x, int64_t n, float* out_accum, void* stream);
+int rnerf_grad_sumsq(const float* grad, const float* theta /* or NULL */, int64_t n, const float* hyper, float* out_accum,
+                     void* stream);
+int rnerf_adam_step(float* theta, const float* grad, float* mu, float* nu, int64_t n, const float* hyper,
+                    const float* norm_sq /* or NULL */, void* stream);
 
 /* ---- a15: rnerf/models.py:498-503 bd_cut_dist mask: reverse-cumsum(inside bbox) > 0 ---- */
 int rnerf_bbox_tail_mask(const float* pos, int64_t n_rays, int n_samples, const double lo_host[3],

@@ -46,7 +46,10 @@ SIGNATURES = {
     "rnerf_mlp_dgrad_pack": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "rnerf_mlp_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_i64, C.c_void_p, C.c_void_p]),
     "rnerf_mlp_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, c_i64, c_f32p, c_f32p, C.c_void_p]),
-    "rnerf_mlp_head_grad": (C.c_int, [C.c_void_p, c_f32p, c_i64, c_f32p, C.c_void_p]),
+    "rnerf_mlp_head_grad": (C.c_int, [C.c_void_p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_sumsq": (C.c_int, [c_f32p, c_i64, c_f32p, C.c_void_p]),
+    "rnerf_grad_sumsq": (C.c_int, [c_f32p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_adam_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_bkgd_weight_floats": (C.c_size_t, []),
     "rnerf_bkgd_mlp_fwd": (C.c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, C.c_void_p]),
     "rnerf_bkgd_mlp_bwd": (C.c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_f32p, C.c_void_p]),
@@ -79,8 +82,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rnerf_abi_version() != 3:
-        raise RnerfError(f"ABI version mismatch: library reports {lib.rnerf_abi_version()}, binding expects 3")
+    if lib.rnerf_abi_version() != 4:
+        raise RnerfError(f"ABI version mismatch: library reports {lib.rnerf_abi_version()}, binding expects 4")
     _lib = lib
     return lib
 

@@ -22,20 +22,29 @@ def _needs_grad(p: Dict) -> bool:
 
 
 # ----------------------------------------------------------------------------- radiance MLP (a8 + a9)
+def _sink(model, name):
+    """Gradient views of a flat parameter arena (train.ParamArena) the backward kernels accumulate into directly,
+    or None: the gradients are then returned to autograd as fresh tensors."""
+    sinks = getattr(model, "_grad_sink", None)
+    return None if sinks is None else sinks.get(name)
+
+
 class _RadianceMLP(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, name, packed, pos, dirs, *params):
-        M = pos.shape[0] * pos.shape[1]
+    def forward(ctx, sink, packed, pos, dirs, *params):
         raw, (layers, enc) = ops.encmlp_fwd_train(packed, pos, dirs)
-        ctx.model, ctx.name, ctx.shape = model, name, pos.shape
+        ctx.sink = sink
         ctx.save_for_backward(packed, pos, dirs, layers, enc, *params)
         return raw.view(pos.shape[0], pos.shape[1], 4)
 
     @staticmethod
     def backward(ctx, d_raw):
         packed, pos, dirs, layers, enc, *params = ctx.saved_tensors
-        grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc), d_raw.contiguous().view(-1, 4), params)
-        return (None, None, None, None, None, *grads)
+        grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc), d_raw.contiguous().view(-1, 4), params,
+                               grad_out=ctx.sink)
+        if ctx.sink is not None:        # already accumulated into the arena's .grad views
+            return (None,) * (4 + len(params))
+        return (None, None, None, None, *grads)
 
 
 def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
@@ -43,7 +52,7 @@ def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: tor
     p = variables["params"][name]
     packed = model._packed(variables, name)
     if _needs_grad(p):
-        return _RadianceMLP.apply(model, name, packed, pos, dirs, *_mlp_param_list(p, 12))
+        return _RadianceMLP.apply(_sink(model, name), packed, pos, dirs, *_mlp_param_list(p, 12))
     with torch.no_grad():
         return ops.encmlp_fwd(packed, pos, dirs).view(pos.shape[0], pos.shape[1], 4)
 
@@ -51,8 +60,9 @@ def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: tor
 # ----------------------------------------------------------------------------- background MLP (a10)
 class _BkgdMLP(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, w, dirs, n_rays, stride, offset, *params):
+    def forward(ctx, sink, w, dirs, n_rays, stride, offset, *params):
         ctx.geom = (n_rays, stride, offset)
+        ctx.sink = sink
         ctx.save_for_backward(w, dirs, *params)
         return ops.bkgd_mlp_fwd(w, dirs, n_rays, stride, offset)
 
@@ -60,8 +70,10 @@ class _BkgdMLP(torch.autograd.Function):
     def backward(ctx, d_raw):
         w, dirs, *params = ctx.saved_tensors
         n_rays, stride, offset = ctx.geom
-        grads = ops.bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw.contiguous(), params)
-        return (None, None, None, None, None, *grads)
+        grads = ops.bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw.contiguous(), params, gw_out=ctx.sink)
+        if ctx.sink is not None:
+            return (None,) * (6 + len(params))
+        return (None, None, None, None, None, None, *grads)
 
 
 def bkgd_raw(model, variables: Dict, dir_c: torch.Tensor, n_rays: int, n_coarse: int) -> torch.Tensor:
@@ -70,7 +82,7 @@ def bkgd_raw(model, variables: Dict, dir_c: torch.Tensor, n_rays: int, n_coarse:
     w = model._packed(variables, "bkgd_mlp")
     stride, offset = n_coarse * 3, (n_coarse - 1) * 3
     if _needs_grad(p):
-        return _BkgdMLP.apply(w, dir_c, n_rays, stride, offset, *_mlp_param_list(p, 5))
+        return _BkgdMLP.apply(_sink(model, "bkgd_mlp"), w, dir_c, n_rays, stride, offset, *_mlp_param_list(p, 5))
     with torch.no_grad():
         return ops.bkgd_mlp_fwd(w, dir_c, n_rays, stride, offset)
 
@@ -81,7 +93,7 @@ def bkgd_color(model, variables: Dict, viewdirs: torch.Tensor) -> torch.Tensor:
     w = model._packed(variables, "bkgd_mlp")
     n = viewdirs.shape[0]
     if _needs_grad(p):
-        raw = _BkgdMLP.apply(w, viewdirs, n, 3, 0, *_mlp_param_list(p, 5))
+        raw = _BkgdMLP.apply(_sink(model, "bkgd_mlp"), w, viewdirs, n, 3, 0, *_mlp_param_list(p, 5))
     else:
         with torch.no_grad():
             raw = ops.bkgd_mlp_fwd(w, viewdirs, n, 3, 0)

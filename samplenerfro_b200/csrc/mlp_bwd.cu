@@ -252,10 +252,12 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
 // heads + bias gradients of the skinny layers (CUDA cores)
 //   gW11[j][c] = sum_m H9[m][j] d_rgb[m][c]   gb11[c] = sum_m d_rgb[m][c]
 //   gW8[j]     = sum_m H7[m][j] d_sig[m]      gb8     = sum_m d_sig[m]
-// out: float[128*3 + 3 + 256 + 1], accumulated with atomics (zeroed by the caller)
+// out_rgb: float[128*3 + 3] = (gW11, gb11), out_sig: float[256 + 1] = (gW8, gb8) -- the Flax (kernel, bias) pairs of
+// Dense_11 / Dense_8 as they sit in a flat parameter arena; accumulated with atomics (zeroed by the caller)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mlp_head_grad_kernel(const __nv_bfloat16* __restrict__ H, const float4* __restrict__ d_raw,
-                                                            int64_t n_samples, int rows_per_block, float* __restrict__ out) {
+                                                            int64_t n_samples, int rows_per_block,
+                                                            float* __restrict__ out, float* __restrict__ out_sig) {
   const size_t layer_stride = (size_t)n_samples * 256;
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t m1 = min(m0 + rows_per_block, n_samples);
@@ -271,8 +273,8 @@ __global__ void __launch_bounds__(256) mlp_head_grad_kernel(const __nv_bfloat16*
     if (j == 0) { s_r += d.x; s_g += d.y; s_b += d.z; s_s += d.w; }
   }
   if (j < 128) { atomicAdd(out + j * 3, a_r); atomicAdd(out + j * 3 + 1, a_g); atomicAdd(out + j * 3 + 2, a_b); }
-  atomicAdd(out + 387 + j, a_sig);
-  if (j == 0) { atomicAdd(out + 384, s_r); atomicAdd(out + 385, s_g); atomicAdd(out + 386, s_b); atomicAdd(out + 643, s_s); }
+  atomicAdd(out_sig + j, a_sig);
+  if (j == 0) { atomicAdd(out + 384, s_r); atomicAdd(out + 385, s_g); atomicAdd(out + 386, s_b); atomicAdd(out_sig + 256, s_s); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -377,23 +379,39 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
     // always in flight behind the one being published.
     const int tid = threadIdx.x - 64;
     float colsum = 0.f;                        // thread tid owns dZ column tid (if < n)
-    const int xunits = a.kx / 8, zunits = a.n / 8;     // 16-byte units per row
+    // 16-byte units per row: 16 or 32 -- powers of two, so the per-unit index math below is shifts and masks
+    const int xshift = a.kx == 256 ? 5 : 4, zshift = a.n == 256 ? 5 : 4;
+    const int xunits = 1 << xshift, zunits = 1 << zshift;
+    // Each loader owns one 16-byte unit column (u) of either operand and walks down the rows in steps of 256/units
+    // (8 or 16): r & 7 is then fixed per thread, so the swizzled destination is a constant plus a per-row stride.
+    const int xu = tid & (xunits - 1), xr0 = tid >> xshift, xrs = 256 >> xshift;
+    const int zu = tid & (zunits - 1), zr0 = tid >> zshift, zrs = 256 >> zshift;
+    const uint32_t xoff0 = (uint32_t)(((xr0 >> 3) * xatoms + (xu >> 3)) * 1024 + (xr0 & 7) * 128 + (((xu & 7) ^ (xr0 & 7)) << 4));
+    const uint32_t zoff0 = (uint32_t)(((zr0 >> 3) * zatoms + (zu >> 3)) * 1024 + (zr0 & 7) * 128 + (((zu & 7) ^ (zr0 & 7)) << 4));
+    const uint32_t xdstep = (uint32_t)((xrs >> 3) * xatoms * 1024), zdstep = (uint32_t)((zrs >> 3) * zatoms * 1024);
+    const bool in_x = xu * 8 < a.x_cols;
+    const int64_t last = a.n_samples - 1;
     auto issue = [&](int it, int stage) {
-      uint8_t* xs = smem + SL::ST_OFF + stage * WG_STAGE_BYTES;
-      uint8_t* zs = xs + WG_ROWS * 256 * 2;
+      const uint32_t xs = sbase + SL::ST_OFF + stage * WG_STAGE_BYTES;
+      const uint32_t zs = xs + WG_ROWS * 256 * 2;
       const int64_t rbase = row0 + (int64_t)it * WG_ROWS;
-      for (int e = tid; e < WG_ROWS * xunits; e += 256) {
-        const int r = e / xunits, u = e % xunits;
-        const int64_t gr = rbase + r;
-        const uint32_t off = (uint32_t)(((r >> 3) * xatoms + (u >> 3)) * 1024 + (r & 7) * 128 + (((u & 7) ^ (r & 7)) << 4));
-        const bool in_x = u * 8 < a.x_cols;
-        cp_async16(smem_u32(xs + off), a.X + (size_t)min(gr, a.n_samples - 1) * a.ldx + (in_x ? u * 8 : 0), gr < row1 && in_x);
+      {
+        uint32_t dst = xs + xoff0;
+        const __nv_bfloat16* colp = a.X + (in_x ? xu * 8 : 0);
+#pragma unroll 4
+        for (int r = xr0; r < WG_ROWS; r += xrs, dst += xdstep) {
+          const int64_t gr = rbase + r;
+          cp_async16(dst, colp + (size_t)min(gr, last) * a.ldx, gr < row1 && in_x);
+        }
       }
-      for (int e = tid; e < WG_ROWS * zunits; e += 256) {
-        const int r = e / zunits, u = e % zunits;
-        const int64_t gr = rbase + r;
-        const uint32_t off = (uint32_t)(((r >> 3) * zatoms + (u >> 3)) * 1024 + (r & 7) * 128 + (((u & 7) ^ (r & 7)) << 4));
-        cp_async16(smem_u32(zs + off), a.dZ + (size_t)min(gr, a.n_samples - 1) * 256 + u * 8, gr < row1);
+      {
+        uint32_t dst = zs + zoff0;
+        const __nv_bfloat16* colp = a.dZ + zu * 8;
+#pragma unroll 4
+        for (int r = zr0; r < WG_ROWS; r += zrs, dst += zdstep) {
+          const int64_t gr = rbase + r;
+          cp_async16(dst, colp + (size_t)min(gr, last) * 256, gr < row1);
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -507,13 +525,14 @@ extern "C" int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed,
   return check_launch("rnerf_mlp_dgrad");
 }
 
-extern "C" int rnerf_mlp_head_grad(const uint16_t* saved_h, const float* d_raw, int64_t n_samples, float* out, void* stream) {
+extern "C" int rnerf_mlp_head_grad(const uint16_t* saved_h, const float* d_raw, int64_t n_samples, float* out_rgb_head,
+                                   float* out_sigma_head, void* stream) {
   if (n_samples <= 0) return 0;
-  RNERF_REQUIRE_PTR(saved_h); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(out);
+  RNERF_REQUIRE_PTR(saved_h); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(out_rgb_head); RNERF_REQUIRE_PTR(out_sigma_head);
   const int rows_per_block = 256;
   const unsigned grid = (unsigned)((n_samples + rows_per_block - 1) / rows_per_block);
   mlp_head_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)saved_h, (const float4*)d_raw, n_samples,
-                                                                rows_per_block, out);
+                                                                rows_per_block, out_rgb_head, out_sigma_head);
   count_launch();
   return check_launch("rnerf_mlp_head_grad");
 }

@@ -118,6 +118,8 @@ class NerfModel:
         self.bricks = ops.grid_bricks(self.table, self.ndim)   # access-skipping aid for the march (bit-identical results)
         self.num_march_steps = self.num_coarse_samples * self.num_path_samples  # rnerf/models.py:121
         self._pack_cache: Dict[str, Any] = {}
+        self._grad_sink = None       # set by train.train_step: backward kernels accumulate into a ParamArena
+        self._theta_flat = None
 
     # ------------------------------------------------------------------ parameters
     def init(self, key, device=None) -> Dict:
@@ -134,6 +136,9 @@ class NerfModel:
     def _packed(self, variables: Dict, name: str) -> torch.Tensor:
         """Device image of one MLP's weights; repacked only when a parameter tensor changed."""
         p = variables["params"][name]
+        flat = getattr(self, "_theta_flat", None)
+        if name == "bkgd_mlp" and flat is not None and p["Dense_0"]["kernel"].data_ptr() == flat[name].data_ptr():
+            return flat[name]      # the arena bucket IS the background kernels' weight image (train.ParamArena)
         sig = tuple((id(d["kernel"]), d["kernel"]._version, id(d["bias"]), d["bias"]._version) for d in p.values())
         hit = self._pack_cache.get(name)
         if hit is not None and hit[0] == sig:
@@ -144,13 +149,13 @@ class NerfModel:
         return buf
 
     # ------------------------------------------------------------------ stochastic inputs
-    def draw_jitter(self, key) -> torch.Tensor:
+    def draw_jitter(self, key, host: bool = False) -> torch.Tensor:
         """rnerf/models.py:240-242: arange(0, S, P) + randint(key, [Nc], 0, P) (also at eval, T9)."""
         j = torch.arange(0, self.num_march_steps, self.num_path_samples, dtype=torch.int32)
         if self.use_random_choice:
             gen = torch.Generator().manual_seed(int(key) if key is not None else 0)
             j = j + torch.randint(0, self.num_path_samples, (self.num_coarse_samples,), generator=gen, dtype=torch.int32)
-        return j.to(self.device)
+        return j if host else j.to(self.device)
 
     def draw_u(self, key, n_rays: int, randomized: bool) -> torch.Tensor:
         """rnerf/model_utils.py:343-356: stratified (train) or linspace(0, 1-eps, Nf) (eval) CDF positions."""

@@ -335,9 +335,11 @@ def mlp_wgrad(x: torch.Tensor, x_cols: int, kx_valid: int, dz: torch.Tensor, n: 
           "rnerf_mlp_wgrad")
 
 
-def encmlp_bwd(packed, pos, dirs, saved, d_raw, params):
+def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None):
     """Backward of pos_enc + NerfMLP wrt the 12 Dense layers: fused tcgen05 dgrad chain (dZ of every layer), then one
-    MN-major tcgen05 wgrad per layer (+ the two skinny heads on CUDA cores).  Returns [gK0, gb0, ..., gK11, gb11]."""
+    MN-major tcgen05 wgrad per layer (+ the two skinny heads on CUDA cores).  Returns [gK0, gb0, ..., gK11, gb11].
+    `grad_out`: optional list of 24 fp32 tensors (same order) the kernels ACCUMULATE into -- the gradient views of a
+    flat parameter arena, where every (kernel, bias) pair is contiguous; fresh zero buffers otherwise."""
     layers, enc = saved
     M = layers.shape[1]
     lib = _lib.load()
@@ -347,8 +349,21 @@ def encmlp_bwd(packed, pos, dirs, saved, d_raw, params):
     dgp = mlp_dgrad_pack(K)
     dz = torch.empty(10, M, 256, device=dev, dtype=torch.bfloat16)
     check(lib.rnerf_mlp_dgrad(_p(dgp), _p(packed), _p(layers), _p(d_raw), M, _p(dz), _stream()), "rnerf_mlp_dgrad")
-    gK = [torch.zeros_like(k) for k in K]
-    gB = [torch.zeros_like(b) for b in params[1::2]]
+    if grad_out is not None:
+        gK, gB = list(grad_out[0::2]), list(grad_out[1::2])
+        for g in gK + gB:
+            _chk(g, "grad_out")
+        contiguous_pairs = all(gB[i].data_ptr() == gK[i].data_ptr() + 4 * gK[i].numel() for i in (8, 11))
+    else:
+        contiguous_pairs = False
+    if not contiguous_pairs:
+        heads = torch.zeros(644, device=dev, dtype=torch.float32)
+        head_rgb, head_sig = heads[:387], heads[387:]
+    if grad_out is None:
+        gK = [torch.zeros_like(k) for k in K]
+        gB = [torch.zeros_like(b) for b in params[1::2]]
+        gK[11], gB[11] = head_rgb[:384].view(128, 3), head_rgb[384:387]
+        gK[8], gB[8] = head_sig[:256].view(256, 1), head_sig[256:257]
     mlp_wgrad(enc[0], 64, 63, dz[0], 256, gK[0], gB[0])
     for l in (1, 2, 3, 4, 6, 7):
         mlp_wgrad(layers[l - 1], 256, 256, dz[l], 256, gK[l], gB[l])
@@ -357,21 +372,26 @@ def encmlp_bwd(packed, pos, dirs, saved, d_raw, params):
     mlp_wgrad(layers[7], 256, 256, dz[8], 256, gK[9], gB[9])
     mlp_wgrad(layers[8], 256, 256, dz[9], 128, gK[10][:256], gB[10])
     mlp_wgrad(enc[1], 32, 27, dz[9], 128, gK[10][256:], None)
-    heads = torch.zeros(644, device=dev, dtype=torch.float32)
-    check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(heads), _stream()), "rnerf_mlp_head_grad")
-    gK[11] = heads[:384].view(128, 3); gB[11] = heads[384:387]
-    gK[8] = heads[387:643].view(256, 1); gB[8] = heads[643:644]
+    if contiguous_pairs:      # (kernel, bias) of Dense_11 / Dense_8 are adjacent in the arena: accumulate in place
+        check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(gK[11]), _p(gK[8]), _stream()), "rnerf_mlp_head_grad")
+    else:
+        check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(head_rgb), _p(head_sig), _stream()), "rnerf_mlp_head_grad")
+        if grad_out is not None:
+            gK[11].add_(head_rgb[:384].view(128, 3)); gB[11].add_(head_rgb[384:387])
+            gK[8].add_(head_sig[:256].view(256, 1)); gB[8].add_(head_sig[256:257])
     out = []
     for i in range(12):
         out += [gK[i], gB[i]]
     return out
 
 
-def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params):
+def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params, gw_out=None):
     """Backward of the background MLP wrt its 5 Dense layers (CUDA: forward recompute per 32-ray tile + chain rule,
-    weight gradients accumulated with atomics).  Returns [gK0, gb0, ..., gK4, gb4]."""
+    weight gradients accumulated with atomics).  Returns [gK0, gb0, ..., gK4, gb4] (views of `gw_out`, a flat fp32
+    buffer laid out like `w` that is ACCUMULATED into, when given)."""
     _chk(w, "w"); _chk(dirs, "dirs"); d_raw = _chk(d_raw.contiguous(), "d_raw")
-    gw = torch.zeros_like(w)
+    gw = torch.zeros_like(w) if gw_out is None else _chk(gw_out, "gw_out")
+    assert gw.numel() == w.numel()
     ptr = C.c_void_p(dirs.data_ptr() + 4 * offset)
     check(_lib.load().rnerf_bkgd_mlp_bwd(_p(w), ptr, n_rays, stride, _p(d_raw), _p(gw), _stream()), "rnerf_bkgd_mlp_bwd")
     shapes = [(27, 128), (128, 128), (128, 128), (155, 128), (128, 3)]
@@ -386,3 +406,34 @@ def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params):
     for k, b in zip(ks, bs):
         out += [k, b]
     return out
+
+
+# ---------------------------------------------------------------- optimiser on a flat parameter arena (a17)
+HYPER_FLOATS = 10   # lr, b1, b2, eps, 1-b1^t, 1-b2^t, gscale, wd_coef, grad_max_val, grad_max_norm (include/rnerf_b200.h)
+
+
+def sumsq(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[0] += sum(x^2) over a flat fp32 buffer (out: 1-element fp32, zero-initialised when not given)."""
+    x = _chk(x.reshape(-1), "x")
+    out = torch.zeros(1, device=x.device, dtype=torch.float32) if out is None else _chk(out, "out")
+    check(_lib.load().rnerf_sumsq(_p(x), x.numel(), _p(out), _stream()), "rnerf_sumsq")
+    return out
+
+
+def grad_sumsq(grad: torch.Tensor, theta: Optional[torch.Tensor], hyper: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[0] += squared norm of the effective (scaled, decayed, value-clipped) gradient (train.py:176-180)."""
+    grad = _chk(grad, "grad"); hyper = _chk(hyper, "hyper"); _chk(out, "out")
+    assert hyper.numel() >= HYPER_FLOATS
+    check(_lib.load().rnerf_grad_sumsq(_p(grad), _p(theta), grad.numel(), _p(hyper), _p(out), _stream()), "rnerf_grad_sumsq")
+    return out
+
+
+def adam_step(theta: torch.Tensor, grad: torch.Tensor, mu: torch.Tensor, nu: torch.Tensor, hyper: torch.Tensor,
+              norm_sq: Optional[torch.Tensor] = None) -> None:
+    """In-place optax.adam update of theta[:n] (n = grad.numel()) with the scalars in the device array `hyper`."""
+    for nm, t in (("theta", theta), ("grad", grad), ("mu", mu), ("nu", nu), ("hyper", hyper)):
+        _chk(t, nm)
+    n = grad.numel()
+    assert theta.numel() >= n and mu.numel() == n and nu.numel() == n and hyper.numel() >= HYPER_FLOATS
+    check(_lib.load().rnerf_adam_step(_p(theta), _p(grad), _p(mu), _p(nu), n, _p(hyper), _p(norm_sq), _stream()),
+          "rnerf_adam_step")

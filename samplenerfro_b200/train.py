@@ -28,26 +28,180 @@ def tree_leaves(tree) -> List[torch.Tensor]:
     return out
 
 
+class ParamArena:
+    """Every leaf of the variables tree as a view of ONE flat fp32 buffer, trainable buckets first
+    (fine_mlp | coarse_mlp | bkgd_mlp | frozen rest), with a same-layout gradient buffer whose views are pre-installed
+    as the leaves' `.grad`.  One memset zeroes all gradients, one NCCL call per bucket reduces them in place (no
+    flatten/unflatten copies), one kernel applies Adam, one kernel gives the weight_l2 statistic.  Inside a bucket the
+    leaves follow Flax order (Dense_i kernel, bias), except bkgd_mlp which is laid out (kernels..., biases...): that is
+    the background kernels' weight image, so the bucket itself is passed to them and no packing step exists."""
+
+    def __init__(self, variables: Dict):
+        params = variables["params"]
+
+        def walk(d, out):
+            for k in d:
+                if isinstance(d[k], dict):
+                    walk(d[k], out)
+                else:
+                    out.append((d, k))
+            return out
+
+        groups = []                                   # (bucket name, [(container dict, key), ...])
+        for name in GRAD_BUCKETS:
+            if name == "bkgd_mlp":
+                layers = [params[name][f"Dense_{i}"] for i in range(len(params[name]))]
+                groups.append((name, [(lay, leaf) for leaf in ("kernel", "bias") for lay in layers]))
+            else:
+                groups.append((name, walk(params[name], [])))
+        frozen = []
+        for name in params:
+            if name not in GRAD_BUCKETS:
+                walk(params[name], frozen)
+        groups.append(("frozen", frozen))
+        dev = groups[0][1][0][0][groups[0][1][0][1]].device
+        self.numel = sum(d[k].numel() for _, ents in groups for d, k in ents)   # true leaf count (weight_l2 denominator)
+        self.bucket_range: Dict[str, tuple] = {}
+        off, layout = 0, []
+        for name, ents in groups:
+            off = (off + 3) // 4 * 4                                            # 16-byte aligned bucket starts
+            if name == "frozen":
+                self.n_train = off
+            lo = off
+            for d, k in ents:
+                layout.append((d, k, off, name))
+                off += d[k].numel()
+            self.bucket_range[name] = (lo, off)
+        total = (off + 3) // 4 * 4
+        self.theta = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(self.n_train, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for d, k, o, name in layout:
+                t = d[k]
+                view = self.theta[o:o + t.numel()].view(t.shape)
+                view.copy_(t)
+                view = view.detach()
+                if name != "frozen":
+                    view.requires_grad_(True)
+                    view.grad = self.grad[o:o + t.numel()].view(t.shape)
+                d[k] = view
+        self.sinks: Dict[str, Any] = {}
+        for name in ("fine_mlp", "coarse_mlp"):
+            p = params[name]
+            self.sinks[name] = [p[f"Dense_{i}"][leaf].grad for i in range(len(p)) for leaf in ("kernel", "bias")]
+        lo, hi = self.bucket_range["bkgd_mlp"]
+        self.sinks["bkgd_mlp"] = self.grad[lo:hi]
+        self.theta_flat = {"bkgd_mlp": self.theta[lo:hi]}
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+    def bucket_grads(self) -> List[torch.Tensor]:
+        return [self.grad[self.bucket_range[n][0]:self.bucket_range[n][1]] for n in GRAD_BUCKETS]
+
+    def allreduce_mean(self, world_size: int, group=None) -> None:
+        """jax.lax.pmean(grads, "batch") (train.py:166): one in-place all-reduce per bucket view, then one scale."""
+        if world_size <= 1:
+            return
+        import torch.distributed as dist
+        works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in self.bucket_grads()]
+        for w in works:
+            w.wait()
+        self.grad.mul_(1.0 / world_size)
+
+    def weight_l2(self) -> torch.Tensor:
+        """mean(theta^2) over every leaf (train.py:146-150) -- one kernel over the arena (padding is zero)."""
+        from . import ops
+        if self.theta.is_cuda:
+            return ops.sumsq(self.theta)[0] / self.numel
+        return (self.theta ** 2).sum() / self.numel
+
+
+class _PinnedRing:
+    """Host -> device staging of small per-step values without a stream synchronisation: a few pinned slots, each
+    guarded by an event so a slot is not rewritten while its copy may still be in flight."""
+
+    def __init__(self, shape, dtype, device, slots: int = 4):
+        self.cuda = torch.device(device).type == "cuda"
+        self.bufs = [torch.zeros(shape, dtype=dtype) for _ in range(slots)]
+        if self.cuda:
+            self.bufs = [b.pin_memory() for b in self.bufs]
+        self.events: List[Any] = [None] * slots
+        self.i = 0
+
+    def push(self, src: torch.Tensor, dst: torch.Tensor) -> None:
+        if not self.cuda:
+            dst.copy_(src)
+            return
+        i = self.i
+        self.i = (i + 1) % len(self.bufs)
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        self.bufs[i].copy_(src)
+        dst.copy_(self.bufs[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+
+
+class ArenaAdam:
+    """optax.adam(lr) with the reference's clipping (train.py:169-181) as one kernel over the arena; the per-step scalars
+    are staged in pinned memory and copied to a device array so a captured graph of the step can be replayed."""
+
+    def __init__(self, arena: ParamArena, args):
+        from . import ops
+        self.arena, self.b1, self.b2, self.eps = arena, 0.9, 0.999, 1e-8
+        dev = arena.theta.device
+        self.mu = torch.zeros_like(arena.grad)
+        self.nu = torch.zeros_like(arena.grad)
+        self.hyper = torch.zeros(ops.HYPER_FLOATS, device=dev, dtype=torch.float32)
+        self.ring = _PinnedRing((ops.HYPER_FLOATS,), torch.float32, dev)
+        self.norm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.count = 0                               # optax's own step counter (bias correction)
+        self.wd_coef = 2.0 * float(args.weight_decay_mult) / arena.numel
+        self.grad_max_val, self.grad_max_norm = float(args.grad_max_val), float(args.grad_max_norm)
+
+    def stage_hyper(self, lr: float) -> None:
+        """Host -> device copy of this step's scalars (outside any captured graph)."""
+        t = self.count + 1
+        self.ring.push(torch.tensor([lr, self.b1, self.b2, self.eps, 1.0 - self.b1 ** t, 1.0 - self.b2 ** t, 1.0,
+                                     self.wd_coef, self.grad_max_val, self.grad_max_norm], dtype=torch.float32), self.hyper)
+
+    def apply(self) -> None:
+        """The device part of the update (capturable): optional global-norm pass, then the fused Adam kernel."""
+        from . import ops
+        norm = None
+        if self.grad_max_norm > 0:
+            self.norm_sq.zero_()
+            norm = ops.grad_sumsq(self.arena.grad, self.arena.theta, self.hyper, self.norm_sq)
+        ops.adam_step(self.arena.theta, self.arena.grad, self.mu, self.nu, self.hyper, norm)
+
+    def step(self, lr: float) -> None:
+        self.stage_hyper(lr)
+        self.apply()
+        self.count += 1
+
+
 @dataclasses.dataclass
 class TrainState:
     """flax.training.train_state.TrainState stand-in: step, params (the variables tree), optimiser state."""
     step: int
     params: Dict
     opt: Any = None
+    arena: Optional[ParamArena] = None
+    graphs: Dict = dataclasses.field(default_factory=dict)
 
     @staticmethod
     def create(variables: Dict, args) -> "TrainState":
-        trainable = []
-        for name in GRAD_BUCKETS:                       # radiance stage: path_sampler gets optax.set_to_zero (T7)
-            trainable += tree_leaves(variables["params"][name])
-        for p in trainable:
-            p.requires_grad_(True)
-        opt = torch.optim.Adam(trainable, lr=args.lr_init, betas=(0.9, 0.999), eps=1e-8)   # optax.adam defaults
-        return TrainState(step=0, params=variables, opt=opt)
+        """Re-homes the variables into a ParamArena (the tree keeps its names; leaves become views) and attaches the
+        fused Adam.  Radiance stage: path_sampler gets optax.set_to_zero (T7) -> it sits in the frozen tail."""
+        arena = ParamArena(variables)
+        return TrainState(step=0, params=variables, opt=ArenaAdam(arena, args), arena=arena)
 
 
-def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None):
-    """train.py:75-162, radiance stage.  Returns (total, stats)."""
+def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, arena: Optional[ParamArena] = None):
+    """train.py:75-162, radiance stage.  Returns (total, stats).  With `arena`, the weight_l2 term is a statistic only:
+    its closed-form gradient is applied by the optimiser kernel (ArenaAdam)."""
     annealed_alpha = float(batch["annealed_alpha"])
     rays = batch["rays"]
     ret, loss_sp = model.apply(variables, key_0, key_1, rays, args.randomized, annealed_alpha, jitter=jitter, u=u)
@@ -70,8 +224,12 @@ def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None):
                                            + 0.5 * ((env[:, 1:] - env[:, :-1]) ** 2).reshape(-1))
     else:
         loss_bg_smooth = torch.zeros((), device=rgb.device)
-    leaves = tree_leaves(variables)
-    weight_l2 = sum((z ** 2).sum() for z in leaves) / sum(z.numel() for z in leaves)
+    if arena is not None:
+        with torch.no_grad():
+            weight_l2 = arena.weight_l2()
+    else:
+        leaves = tree_leaves(variables)
+        weight_l2 = sum((z ** 2).sum() for z in leaves) / sum(z.numel() for z in leaves)
     total = (loss + loss_c + args.bg_weight * loss_bg + args.bg_smooth_weight * loss_bg_smooth
              + args.weight_decay_mult * weight_l2)
     stats = {"loss": loss.detach(), "psnr": utils.compute_psnr(loss.detach()), "loss_c": loss_c.detach(),
@@ -106,15 +264,18 @@ def allreduce_mean_grads(variables: Dict, world_size: int, group=None) -> None:
             off += n
 
 
-def train_step(model, rng, state: TrainState, batch: Dict, args=None, world_size: int = 1, group=None,
-               jitter=None, u=None):
-    """One optimisation step (train.py:58-183)."""
-    args = args if args is not None else batch["args"]
-    key_0, key_1 = utils._split_key(rng)
-    state.opt.zero_grad(set_to_none=True)
-    total, stats = loss_fn(model, state.params, batch, args, key_0, key_1, jitter=jitter, u=u)
-    total.backward()
-    allreduce_mean_grads(state.params, world_size, group)
+def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_size, group, jitter, u):
+    """Device work of one optimisation step: zero grads, loss forward/backward (gradients land in the arena),
+    gradient + stats all-reduce, fused Adam.  No host synchronisation: capturable in a CUDA graph."""
+    arena = state.arena
+    arena.zero_grad()
+    model._grad_sink, model._theta_flat = arena.sinks, arena.theta_flat
+    try:
+        total, stats = loss_fn(model, state.params, batch, args, key_0, key_1, jitter=jitter, u=u, arena=arena)
+        total.backward()
+    finally:
+        model._grad_sink = None
+    arena.allreduce_mean(world_size, group)
     if world_size > 1:
         import torch.distributed as dist
         keys = [k for k, v in stats.items() if torch.is_tensor(v)]
@@ -122,21 +283,92 @@ def train_step(model, rng, state: TrainState, batch: Dict, args=None, world_size
         dist.all_reduce(packed, group=group)                      # pmean(stats), train.py:167
         for k, v in zip(keys, packed / world_size):
             stats[k] = v
-    if args.grad_max_val > 0:
-        for p in tree_leaves(state.params):
-            if p.grad is not None:
-                p.grad.clamp_(-args.grad_max_val, args.grad_max_val)
-    if args.grad_max_norm > 0:
-        gs = [p.grad for p in tree_leaves(state.params) if p.grad is not None]
-        norm = torch.sqrt(sum((g ** 2).sum() for g in gs))
-        mult = torch.clamp(args.grad_max_norm / (1e-7 + norm), max=1.0)
-        for g in gs:
-            g.mul_(mult)
+    state.opt.apply()
+    return stats
+
+
+class _GraphedStep:
+    """The whole training step captured once in a CUDA graph and replayed: the step is ~100 kernels of a few
+    microseconds to a few hundred each, so eager launches from Python (about 15 ms of host time at 4096 rays) would
+    bound it.  Static input buffers are refreshed before every replay; per-step scalars go through ArenaAdam.hyper."""
+
+    def __init__(self, model, state, batch, args, world_size, group):
+        dev = state.arena.theta.device
+        rays = batch["rays"]
+        B = rays.origins.shape[0]
+        self.rays = utils.Rays(*[torch.empty_like(r, device=dev).contiguous() for r in rays])
+        self.pixels = torch.empty_like(batch["pixels"], device=dev)
+        self.env = None
+        if "env_rays" in batch and batch["env_rays"] is not None:
+            self.env = utils.Rays(*[torch.empty_like(r, device=dev).contiguous() for r in batch["env_rays"]])
+        self.jitter = torch.zeros(model.num_coarse_samples, device=dev, dtype=torch.int32)
+        self.jitter_ring = _PinnedRing((model.num_coarse_samples,), torch.int32, dev)
+        self.u = (torch.zeros(B, model.num_fine_samples, device=dev) if args.randomized
+                  else model.draw_u(None, B, False))
+        self.static_batch = {"rays": self.rays, "pixels": self.pixels, "env_rays": self.env,
+                             "annealed_alpha": float(batch["annealed_alpha"])}
+        self.load(model, batch, 0, 0, args)
+        self.graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            self.stats = _step_body(model, state, self.static_batch, args, None, None, world_size, group, self.jitter, self.u)
+        model._pack_cache.clear()
+
+    def load(self, model, batch, key_0, key_1, args):
+        for dst, src in zip(self.rays, batch["rays"]):
+            dst.copy_(src, non_blocking=True)
+        self.pixels.copy_(batch["pixels"], non_blocking=True)
+        if self.env is not None:
+            for dst, src in zip(self.env, batch["env_rays"]):
+                dst.copy_(src, non_blocking=True)
+        self.jitter_ring.push(model.draw_jitter(key_0, host=True), self.jitter)
+        if args.randomized:
+            self.u.copy_(model.draw_u(key_1, self.u.shape[0], True))
+
+    def replay(self):
+        self.graph.replay()
+        return dict(self.stats)
+
+
+def _graph_key(batch, args, world_size):
+    env = batch.get("env_rays")
+    return (tuple(batch["rays"].origins.shape), tuple(batch["pixels"].shape),
+            None if env is None else tuple(env.viewdirs.shape), float(batch["annealed_alpha"]) > 0,
+            bool(args.randomized), int(world_size))
+
+
+def train_step(model, rng, state: TrainState, batch: Dict, args=None, world_size: int = 1, group=None,
+               jitter=None, u=None, use_graph: Optional[bool] = None, graph_after: int = 2):
+    """One optimisation step (train.py:58-183).  After `graph_after` eager steps with a given batch shape the step is
+    captured in a CUDA graph and replayed from then on (`use_graph=False` keeps it eager; explicit `jitter`/`u`
+    also do).  Returned stats are device tensors: reading them is the caller's synchronisation point."""
+    args = args if args is not None else batch["args"]
+    key_0, key_1 = utils._split_key(rng)
     lr = utils.learning_rate_decay(state.step, args.lr_init, args.lr_final, args.max_steps, args.lr_delay_steps,
                                    args.lr_delay_mult)
-    for gparam in state.opt.param_groups:
-        gparam["lr"] = lr
-    state.opt.step()
+    on_cuda = state.arena.theta.is_cuda
+    if use_graph is None:
+        use_graph = on_cuda and jitter is None and u is None
+    state.opt.stage_hyper(lr)
+    stats = None
+    if use_graph:
+        key = _graph_key(batch, args, world_size)
+        slot = state.graphs.get(key)
+        if isinstance(slot, _GraphedStep):
+            slot.load(model, batch, key_0, key_1, args)
+            stats = slot.replay()
+        elif isinstance(slot, int) and slot >= graph_after:
+            slot = _GraphedStep(model, state, batch, args, world_size, group)
+            state.graphs[key] = slot
+            slot.load(model, batch, key_0, key_1, args)
+            stats = slot.replay()
+        else:
+            state.graphs[key] = (slot or 0) + 1
+    if stats is None:
+        stats = _step_body(model, state, batch, args, key_0, key_1, world_size, group, jitter, u)
+    model._pack_cache.clear()          # the weights changed under the packed images
+    state.opt.count += 1
     state.step += 1
     stats["lr"] = lr
+    stats["annealing_rate"] = float(batch["annealed_alpha"])
     return state, stats, (int(rng) + 1 if rng is not None else 1)

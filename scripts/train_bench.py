@@ -10,6 +10,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--batch", type=int, default=4096, help="global batch (rays per step over all GPUs)")
 ap.add_argument("--grid", type=int, default=512)
+ap.add_argument("--eager", action="store_true", help="no CUDA-graph capture of the step")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -47,23 +48,28 @@ def barrier():
 rng = 0
 state.step = 3000
 for _ in range(a.warmup):
-    state, stats, rng = train.train_step(model, rng, state, batch, args, world_size=world)
+    state, stats, rng = train.train_step(model, rng, state, batch, args, world_size=world, use_graph=False if a.eager else None)
 barrier()
 l0 = _lib.launch_count()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
+torch.cuda.cudart().cudaProfilerStart()
+tc0 = time.perf_counter()
 e0.record()
 for _ in range(a.steps):
-    state, stats, rng = train.train_step(model, rng, state, batch, args, world_size=world)
+    state, stats, rng = train.train_step(model, rng, state, batch, args, world_size=world, use_graph=False if a.eager else None)
 e1.record()
+cpu_issue_ms = (time.perf_counter() - tc0) * 1e3 / a.steps
 barrier()
+torch.cuda.cudart().cudaProfilerStop()
 ms = e0.elapsed_time(e1)
 if world > 1:
     t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
 if rank == 0:
     print(json.dumps({"metric": "training rays/sec (fwd+bwd+allreduce+Adam)", "value": a.batch * a.steps / (ms * 1e-3),
                       "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-                      "scaling": "strong", "global_batch": a.batch, "gpu_launches": int(_lib.launch_count() - l0),
-                      "loss": float(stats["loss"]), "config": "ship_skydome training step, S=768, G=%d, 64+192 samples, "
+                      "scaling": "strong", "global_batch": a.batch, "cuda_graph": not a.eager, "gpu_launches": int(_lib.launch_count() - l0),
+                      "loss": float(stats["loss"]), "cpu_issue_ms_per_step": cpu_issue_ms, "config": "ship_skydome training step, S=768, G=%d, 64+192 samples, "
                       "bg_weight 0.025, bg_smooth 1.0 on a 128x128 env patch" % G}))
 if world > 1:
     dist.destroy_process_group()

@@ -163,3 +163,76 @@ def test_train_step_uses_no_library_gemm_for_the_radiance_mlps(cuda_lib):
     n0 = _lib.launch_count()
     ops.encmlp_bwd(packed, pos, dirs, saved, torch.randn(M, 4, device="cuda"), params)
     assert _lib.launch_count() - n0 == 1 + 1 + 12 + 1      # dgrad pack, dgrad chain, 12 wgrad GEMMs, heads
+
+
+def test_fused_adam_matches_torch_adam(cuda_lib):
+    """ArenaAdam (one kernel over the flat arena, optax.adam semantics) vs torch.optim.Adam on the same gradients,
+    with and without the reference's value / norm clipping (train.py:169-181) and the weight-decay term."""
+    from samplenerfro_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    n = 100_003
+    for clip_val, clip_norm, wd in ((0.0, 0.0, 0.0), (0.02, 0.5, 1e-3)):
+        theta0 = torch.randn(n, generator=gen).cuda()
+        theta, ref = theta0.clone(), theta0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+        mu, nu = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        nsq = torch.zeros(1, device="cuda")
+        for t in range(1, 6):
+            g = (torch.randn(n, generator=gen) * 0.05).cuda()
+            lr = 1e-3 * t
+            hyper = torch.tensor([lr, 0.9, 0.999, 1e-8, 1 - 0.9 ** t, 1 - 0.999 ** t, 1.0, wd, clip_val, clip_norm]).cuda()
+            norm = None
+            if clip_norm > 0:
+                nsq.zero_()
+                norm = ops.grad_sumsq(g, theta, hyper, nsq)
+            ops.adam_step(theta, g, mu, nu, hyper, norm)
+            ge = g + wd * ref.detach()
+            if clip_val > 0:
+                ge = ge.clamp(-clip_val, clip_val)
+            if clip_norm > 0:
+                ge = ge * torch.clamp(clip_norm / (1e-7 + ge.norm()), max=1.0)
+                assert abs(nsq.sqrt().item() / (ge.norm().item() / min(1.0, clip_norm / (1e-7 + (g + wd * ref.detach()).clamp(-clip_val, clip_val).norm().item()))) - 1) < 1e-4
+            ref.grad = ge
+            for gparam in opt.param_groups:
+                gparam["lr"] = lr
+            opt.step()
+            assert (theta - ref.detach()).abs().max().item() < 2e-6, (clip_val, t)
+    x = torch.randn(70_001, generator=gen).cuda()
+    assert abs(ops.sumsq(x).item() / (x.double() ** 2).sum().item() - 1) < 1e-5
+
+
+def test_graph_replayed_step_equals_eager_step(cuda_lib):
+    """One step replayed from the captured CUDA graph vs the same step run eagerly from the same parameters, optimiser
+    state and seeds: same loss, same gradients (up to the summation order of the atomics in the weight-gradient
+    kernels).  Parameters after Adam are only compared through the gradients: m/sqrt(v) amplifies rounding noise of
+    near-zero gradients to O(lr), so a direct comparison would be ill-conditioned."""
+    from samplenerfro_b200 import train, utils
+    model, variables, args, _, o, d, env, pixels, gen = _setup(B=128, bias=0.02)
+    args.lr_delay_steps = 0
+    B = o.shape[0]
+    state = train.TrainState.create(variables, args)
+    batch = {"rays": utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(B, 1).cuda()), "pixels": pixels.cuda(),
+             "env_rays": utils.Rays(env.cuda(), env.cuda(), env.cuda(), env.cuda()[..., :1]), "annealed_alpha": 0.5}
+    rng = 0
+    state.step = 10
+    for _ in range(2):
+        state, stats, rng = train.train_step(model, rng, state, batch, args)
+    snap = (state.arena.theta.clone(), state.opt.mu.clone(), state.opt.nu.clone(), state.opt.count, state.step, rng)
+    state, stats, _ = train.train_step(model, rng, state, batch, args)          # third call: capture + replay
+    assert any(isinstance(v, train._GraphedStep) for v in state.graphs.values())
+    g_graph, th_graph = state.arena.grad.clone(), state.arena.theta.clone()
+    st_graph = {k: float(v) for k, v in stats.items() if torch.is_tensor(v)}
+    state.arena.theta.copy_(snap[0]); state.opt.mu.copy_(snap[1]); state.opt.nu.copy_(snap[2])
+    state.opt.count, state.step = snap[3], snap[4]
+    model._pack_cache.clear()
+    state, stats, _ = train.train_step(model, snap[5], state, batch, args, use_graph=False)
+    g_eager, th_eager = state.arena.grad.clone(), state.arena.theta.clone()
+    for k, v in st_graph.items():
+        assert abs(v - float(stats[k])) <= 1e-5 * max(1.0, abs(v)), (k, v, float(stats[k]))
+    rel = ((g_graph - g_eager).norm() / g_eager.norm()).item()
+    assert rel < 1e-3, rel
+    assert (th_graph - snap[0]).abs().max().item() > 0 and (th_eager - snap[0]).abs().max().item() > 0
+    # a fourth call replays the same graph object (no re-capture) and keeps counting steps
+    n_graphs = len(state.graphs)
+    state, stats, _ = train.train_step(model, 7, state, batch, args)
+    assert len(state.graphs) == n_graphs and state.step == snap[4] + 2 and state.opt.count == snap[3] + 2

@@ -53,3 +53,42 @@ def test_two_rank_gradient_mean_and_sharding():
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]
     assert [r[2] for r in res] == [(0, 4), (4, 8)]
+
+
+def _arena_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from samplenerfro_b200 import models, train, utils
+    gen = torch.Generator().manual_seed(0)
+    V = {"params": {"coarse_mlp": models.init_nerf_mlp_params(gen, "cpu"), "fine_mlp": models.init_nerf_mlp_params(gen, "cpu"),
+                    "bkgd_mlp": models.init_small_mlp_params(gen, "cpu"),
+                    "path_sampler": {"so3_mlp": models.init_small_mlp_params(gen, "cpu", in_dim=60, out_std=1e-5)}}}
+    state = train.TrainState.create(V, utils.Flags())
+    arena = state.arena
+    # each rank's "loss": (rank+1) * sum of every trainable leaf  ->  gradient (rank+1) everywhere, mean 1.5 at N=2
+    loss = sum(p.sum() for n in train.GRAD_BUCKETS for p in train.tree_leaves(V["params"][n])) * (rank + 1)
+    loss.backward()
+    arena.allreduce_mean(world)
+    lo, hi = arena.bucket_range["bkgd_mlp"]
+    ok = bool(torch.allclose(arena.grad[:arena.bucket_range["coarse_mlp"][1]], torch.full((1,), 1.5)))
+    ok = ok and bool(torch.allclose(arena.grad[lo:hi], torch.full((1,), 1.5)))
+    ok = ok and V["params"]["fine_mlp"]["Dense_5"]["kernel"].grad.data_ptr() == arena.sinks["fine_mlp"][10].data_ptr()
+    ok = ok and V["params"]["path_sampler"]["so3_mlp"]["Dense_0"]["kernel"].grad is None
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_arena_allreduce():
+    """ParamArena: gradients accumulate into the flat buffer's views and the per-bucket in-place all-reduce-mean over
+    gloo equals pmean (train.py:166)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True]
