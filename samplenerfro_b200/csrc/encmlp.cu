@@ -176,7 +176,8 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, const float* __rest
 __device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 template <int NT, int NSTAGE, bool DEBUG>
-__global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpArgs args) {
+__global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpArgs args,
+                                                                  const __grid_constant__ CUtensorMap tm_layers) {
   using SL = SmemLayout<NT, NSTAGE>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -317,14 +318,23 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
         acc_phase ^= 1;
         tc_fence_after();
         if (prof) args.prof[40 + l * 4 + 1] = clock64();
+        // Activation dump (training / parity): layers 0..8 leave this warp's 32 rows of the tile in shared memory as the
+        // next layer's A operand, so the dump is 4 TMA tensor stores per warp (one per 64-column k-block, fully
+        // coalesced, no LSU traffic) instead of per-thread 16-byte stores that touch 32 lines per instruction.
+        // The stores issued after the previous layer must have finished reading the tile before it is overwritten.
+        const bool dump = DEBUG && args.layer_out != nullptr;
+        if (dump) {
+          if (lane == 0) bulk_wait_read();
+          __syncwarp();
+        }
         {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
           __nv_bfloat16* dump_row = nullptr;
-          if (DEBUG) dump_row = (args.layer_out && live) ? args.layer_out + ((size_t)l * args.n_samples + srow) * 256 : nullptr;
-          if (l == 7)      epilogue_row<1, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);
-          else if (l == 8) epilogue_row<2, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);
-          else if (l == 9) epilogue_row<3, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);
-          else             epilogue_row<0, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);
+          if (DEBUG) dump_row = (args.layer_out && live && l == 9) ? args.layer_out + ((size_t)l * args.n_samples + srow) * 256 : nullptr;
+          if (l == 7)      epilogue_row<1, false>(taddr, bias, vslot, a_row, r7s, eo, nullptr);
+          else if (l == 8) epilogue_row<2, false>(taddr, bias, vslot, a_row, r7s, eo, nullptr);
+          else if (l == 9) epilogue_row<3, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);   // no smem copy: direct stores
+          else             epilogue_row<0, false>(taddr, bias, vslot, a_row, r7s, eo, nullptr);
         }
         if (l == 8) {
           // condition input for Dense_10: pos_enc(dir, 0, 4) replaces the position encoding (last used by layer 5)
@@ -340,10 +350,20 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_aready);
+          if (lane == 0) {
+            mbar_arrive(bar_aready);
+            const int64_t wrow0 = (group * NT + t) * TILE_M + q * 32;     // first sample row of this warp
+            if (dump && wrow0 < args.n_samples) {
+              const uint32_t src = sbase + SL::A_OFF + t * 4 * ABLK_BYTES + q * 4096;
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) tma_store_3d(&tm_layers, src + kb * ABLK_BYTES, kb * KB, (int)wrow0, l);
+              bulk_commit();
+            }
+          }
         }
       }
     }
+    if (DEBUG && args.layer_out != nullptr && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -369,7 +389,13 @@ static int launch_encmlp(const EncMlpArgs& a0, cudaStream_t st) {
   EncMlpArgs a = a0;
   a.n_groups = (int)((a.n_samples + (int64_t)TILE_M * NT - 1) / ((int64_t)TILE_M * NT));
   const int grid = a.n_groups < n_sm ? a.n_groups : n_sm;
-  kfn<<<grid, 64 + 128 * NT, SL::BYTES, st>>>(a);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (DEBUG && a.layer_out != nullptr) {
+    int rc = make_rows_tmap(&tm, a.layer_out, a.n_samples, N_MMA_LAYERS);
+    if (rc) return rc;
+  }
+  kfn<<<grid, 64 + 128 * NT, SL::BYTES, st>>>(a, tm);
   count_launch();
   return check_launch("rnerf_encmlp_fwd");
 }

@@ -64,28 +64,36 @@ struct DgradArgs {
   int n_groups;
 };
 
-// 256-bit ReLU mask of one saved activation row (H > 0  <=>  bf16 bits != 0 after ReLU)
-__device__ __forceinline__ void load_row_mask(const __nv_bfloat16* __restrict__ hrow, uint32_t (&mask)[8]) {
-  const uint4* p = reinterpret_cast<const uint4*>(hrow);
+// ReLU masks of 32 consecutive saved activation rows (H > 0  <=>  bf16 bits != 0 after ReLU), loaded warp-cooperatively:
+// lane i reads the 16-byte unit i of a row, so one load instruction covers one full 512-byte row (4 lines) instead of
+// 32 different rows.  The bits are exchanged with ballots: mask[p] bit i of the row's owner (lane r <-> row wrow0 + r)
+// says whether column 8 i + p is active.
+__device__ __forceinline__ void load_row_masks(const __nv_bfloat16* __restrict__ Hl, int64_t wrow0, int64_t n_samples,
+                                               int lane, uint32_t (&mask)[8]) {
+#pragma unroll 1
+  for (int r0 = 0; r0 < 32; r0 += 4) {
+    uint4 v[4];
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    uint32_t m = 0;
+    for (int k = 0; k < 4; ++k) {
+      const int64_t row = min(wrow0 + r0 + k, n_samples - 1);
+      v[k] = __ldg(reinterpret_cast<const uint4*>(Hl + (size_t)row * 256) + lane);
+    }
 #pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {            // 4 x 16 bytes = 32 bf16 per mask word
-      const uint4 v = __ldg(p + w * 4 + q4);
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        m |= ((u[i] & 0xFFFFu) != 0u ? 1u : 0u) << (q4 * 8 + i * 2);
-        m |= ((u[i] >> 16) != 0u ? 1u : 0u) << (q4 * 8 + i * 2 + 1);
+      for (int p = 0; p < 8; ++p) {
+        const bool on = (p & 1) ? ((u[p >> 1] >> 16) != 0u) : ((u[p >> 1] & 0xFFFFu) != 0u);
+        const uint32_t bal = __ballot_sync(0xffffffffu, on);
+        if (lane == r0 + k) mask[p] = bal;
       }
     }
-    mask[w] = m;
   }
 }
 
 template <int NT, int NSTAGE>
-__global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const DgradArgs args) {
+__global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const DgradArgs args,
+                                                                     const __grid_constant__ CUtensorMap tm_dz) {
   using SL = DgradSmem<NT, NSTAGE>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -161,57 +169,66 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
     const float* w_sigma = head_s;
     const float* w_rgb = head_s + 256;
     uint32_t acc_phase = 0;
-    auto signal_ready = [&]() {
-      tc_fence_before();
-      fence_proxy_async();
+    // Every dZ tile is left in shared memory (it is the next GEMM's A operand) and streamed to HBM from there by the
+    // TMA engine: 4 tensor stores per warp and layer (one per 64-column k-block of the warp's 32 rows).
+    const uint32_t a_warp = sbase + SL::A_OFF + t * 4 * ABLK_BYTES + q * 4096;
+    auto store_tile = [&](int64_t wrow0, int layer, int nkb) {     // lane 0 only, after fence + __syncwarp
+      if (wrow0 < args.n_samples) {
+        for (int kb = 0; kb < nkb; ++kb) tma_store_3d(&tm_dz, a_warp + kb * ABLK_BYTES, kb * KB, (int)wrow0, layer);
+        bulk_commit();
+      }
+    };
+    auto tile_free = [&]() {                                       // previous stores have finished reading the tile
+      if (lane == 0) bulk_wait_read();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_aready);
     };
     for (int g = 0; g < my_groups; ++g) {
       const int64_t group = (int64_t)blockIdx.x + (int64_t)g * gridDim.x;
-      const int64_t srow = (group * NT + t) * TILE_M + row;
+      const int64_t wrow0 = (group * NT + t) * TILE_M + q * 32;
+      const int64_t srow = wrow0 + lane;
       const bool live = srow < args.n_samples;
       const int64_t lrow = live ? srow : (args.n_samples - 1);
       const float4 draw = live ? __ldg(args.d_raw + lrow) : make_float4(0.f, 0.f, 0.f, 0.f);
       // ---- prologue: rgb head (Dense_11) backward + ReLU of the condition layer -> dZ[9] (128 columns)
       {
-        const uint4* h9 = reinterpret_cast<const uint4*>(args.H + 9 * layer_stride + (size_t)lrow * 256);
-        uint4* out = reinterpret_cast<uint4*>(args.dZ + 9 * layer_stride + (size_t)lrow * 256);
+        uint32_t m9[8];
+        load_row_masks(args.H + 9 * layer_stride, wrow0, args.n_samples, lane, m9);    // columns >= 128 are ignored
+        tile_free();
 #pragma unroll 1
         for (int c8 = 0; c8 < 16; ++c8) {         // 8 columns per 16-byte unit
-          const uint4 hv = __ldg(h9 + c8);
-          const uint32_t hu[4] = {hv.x, hv.y, hv.z, hv.w};
           uint32_t pk[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int j0 = c8 * 8 + i * 2;
             float g0 = draw.x * w_rgb[j0] + draw.y * w_rgb[128 + j0] + draw.z * w_rgb[256 + j0];
             float g1 = draw.x * w_rgb[j0 + 1] + draw.y * w_rgb[128 + j0 + 1] + draw.z * w_rgb[256 + j0 + 1];
-            if ((hu[i] & 0xFFFFu) == 0u) g0 = 0.f;
-            if ((hu[i] >> 16) == 0u) g1 = 0.f;
+            if (!((m9[2 * i] >> c8) & 1u)) g0 = 0.f;
+            if (!((m9[2 * i + 1] >> c8) & 1u)) g1 = 0.f;
             pk[i] = pack_bf16(g0, g1);
           }
-          const uint4 o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(a_row + (c8 >> 3) * ABLK_BYTES + ((uint32_t)((c8 & 7) << 4) ^ r7s)) = o;
-          if (live) out[c8] = o;
+          *reinterpret_cast<uint4*>(a_row + (c8 >> 3) * ABLK_BYTES + ((uint32_t)((c8 & 7) << 4) ^ r7s)) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
-      signal_ready();
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar_aready); store_tile(wrow0, 9, 2); }
       for (int d = 0; d < DG_GEMMS; ++d) {
         const int lo = 8 - d;                       // MMA layer whose dZ this GEMM produces
         uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (d >= 1) load_row_mask(args.H + (size_t)lo * layer_stride + (size_t)lrow * 256, mask);   // hidden under the MMAs
+        if (d >= 1) load_row_masks(args.H + (size_t)lo * layer_stride, wrow0, args.n_samples, lane, mask);   // hidden under the MMAs
         mbar_wait(bar_acc, acc_phase); acc_phase ^= 1;
         tc_fence_after();
-        __nv_bfloat16* out_row = args.dZ + (size_t)lo * layer_stride + (size_t)lrow * 256;
+        tile_free();
 #pragma unroll 1
         for (int cg = 0; cg < 8; ++cg) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + cg * 32), v);
           tmem_ld_wait();
-          uint32_t mk = 0;
+          uint32_t mk[8];                           // bit (j >> 2) of mk[p]: column cg*32 + 8*(j >> 2) + p
 #pragma unroll
-          for (int w = 0; w < 8; ++w) if (w == cg) mk = mask[w];     // select, keeps mask[] in registers
+          for (int p = 0; p < 8; ++p) mk[p] = mask[p] >> (cg * 4);
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -221,27 +238,27 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
               f1 = fmaf(draw.w, w_sigma[cg * 32 + 2 * j + 1], f1);
             }
             if (d >= 1) {
-              if (!((mk >> (2 * j)) & 1u)) f0 = 0.f;
-              if (!((mk >> (2 * j + 1)) & 1u)) f1 = 0.f;
+              if (!((mk[(2 * j) & 7] >> (j >> 2)) & 1u)) f0 = 0.f;
+              if (!((mk[(2 * j + 1) & 7] >> (j >> 2)) & 1u)) f1 = 0.f;
             }
             pk[j] = pack_bf16(f0, f1);
           }
-          if (d < DG_GEMMS - 1) {
-            uint8_t* blk = a_row + (cg >> 1) * ABLK_BYTES;
+          uint8_t* blk = a_row + (cg >> 1) * ABLK_BYTES;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<uint4*>(blk + ((uint32_t)(((cg & 1) * 4 + c) << 4) ^ r7s)) =
-                  make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          }
-          if (live) {
-            uint4* o = reinterpret_cast<uint4*>(out_row + cg * 32);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) o[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          }
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(blk + ((uint32_t)(((cg & 1) * 4 + c) << 4) ^ r7s)) =
+                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         }
-        if (d < DG_GEMMS - 1) signal_ready(); else tc_fence_before();
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (d < DG_GEMMS - 1) mbar_arrive(bar_aready);
+          store_tile(wrow0, lo, 4);
+        }
       }
     }
+    if (lane == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -281,9 +298,10 @@ __global__ void __launch_bounds__(256) mlp_head_grad_kernel(const __nv_bfloat16*
 // wgrad: G[Kx x N] += X[rows][Kx]^T  dZ[rows][N]   (MN-major operands, reduction over rows), gb[N] += colsum(dZ)
 // One CTA = one slab of rows; accumulators: Kx/128 M-blocks x N columns of TMEM.
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_ROWS = 64;                           // rows (GEMM K) per pipeline stage
-constexpr int WG_STAGES = 3;
-constexpr int WG_STAGE_BYTES = WG_ROWS * 256 * 2 * 2; // X tile [64 x 256] + dZ tile [64 x 256] bf16 = 64 KB
+constexpr int WG_ROWS = 32;                           // rows (GEMM K) per pipeline stage
+constexpr int WG_STAGES = 6;
+constexpr int WG_DEPTH = 4;                           // stages of loads kept in flight (128 KB per SM: the kernel is HBM-bound)
+constexpr int WG_STAGE_BYTES = WG_ROWS * 256 * 2 * 2; // X tile [32 x 256] + dZ tile [32 x 256] bf16 = 32 KB
 constexpr int WG_THREADS = 64 + 256;                  // warp 0: MMA, warp 1: spare, warps 2-9: loaders/epilogue
 
 struct WgradSmem {
@@ -432,19 +450,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
       asm volatile("bar.sync 1, 256;" ::: "memory");     // every loader has fenced its writes (and read its column)
       if (tid == 0) mbar_arrive(bar_full(stage));
     };
+    // Software pipeline: stage `it` is issued WG_DEPTH - 1 stages ahead of the one being published, so WG_DEPTH - 1
+    // stages of loads are always in flight behind it.
+    auto wait_pending = [&](int n) {     // at most n of this thread's cp.async groups still pending
+      switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+      }
+    };
+    static_assert(WG_DEPTH == 4 && WG_DEPTH <= WG_STAGES, "wait_pending covers depths up to 4");
     int stage = 0; uint32_t phase = 0;
     for (int it = 0; it < n_steps; ++it) {
       mbar_wait(bar_empty(stage), phase ^ 1);
       issue(it, stage);
-      if (it > 0) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group: stage it-1 is complete
-        publish(stage == 0 ? WG_STAGES - 1 : stage - 1);
+      if (it >= WG_DEPTH - 1) {
+        wait_pending(WG_DEPTH - 1);                          // stage it - (WG_DEPTH-1) has landed
+        publish((it - (WG_DEPTH - 1)) % WG_STAGES);
       }
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-    if (n_steps > 0) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      publish(stage == 0 ? WG_STAGES - 1 : stage - 1);
+    {
+      const int pending = n_steps < WG_DEPTH - 1 ? n_steps : WG_DEPTH - 1;
+      for (int j = 0; j < pending; ++j) {
+        wait_pending(pending - 1 - j);
+        publish((n_steps - pending + j) % WG_STAGES);
+      }
     }
     if (a.gb != nullptr && tid < a.n && n_steps > 0) atomicAdd(a.gb + tid, colsum);
     // ---- epilogue: accumulators -> red.global.add into gW.  TMEM lane = gradient row (X column) within the M-block.
@@ -452,6 +484,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
       mbar_wait(bar_done, 0);
       tc_fence_after();
       const int q = warp & 3, wg = (warp - 2) >> 2;       // two warpgroups split the columns
+      const bool vec_ok = (reinterpret_cast<uintptr_t>(a.gW) & 15u) == 0;   // a.n is a multiple of 128
       const int lrow = q * 32 + lane;
       for (int mb = 0; mb < n_mblk; ++mb) {
         const int grow = mb * 128 + lrow;
@@ -462,8 +495,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
           tmem_ld_wait();
           if (ok) {
             float* dst = a.gW + (size_t)grow * a.n + cg * 32;
+            if (vec_ok) {      // 16-byte aligned gradient rows: 8 vector reductions instead of 32 scalar ones
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -520,7 +561,10 @@ extern "C" int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed,
   a.n_samples = n_samples;
   a.n_groups = (int)((n_samples + TILE_M * NT - 1) / (TILE_M * NT));
   const int grid = a.n_groups < n_sm ? a.n_groups : n_sm;
-  kfn<<<grid, 64 + 128 * NT, SL::BYTES, (cudaStream_t)stream>>>(a);
+  CUtensorMap tm;
+  int rc = make_rows_tmap(&tm, dz_out, n_samples, N_MMA_LAYERS);
+  if (rc) return rc;
+  kfn<<<grid, 64 + 128 * NT, SL::BYTES, (cudaStream_t)stream>>>(a, tm);
   count_launch();
   return check_launch("rnerf_mlp_dgrad");
 }

@@ -1,5 +1,6 @@
 // tcgen05 / TMEM / TMA / mbarrier PTX wrappers and the network geometry shared by the enc+MLP kernels (sm_100a).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -104,6 +105,24 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+
+// TMA engine tensor store shared -> global through a CUtensorMap (SASS: UTMASTG); completion tracked by bulk groups.
+// The source tile must have been made visible to the async proxy (fence.proxy.async) by its writers.
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk stores have finished READING shared memory (the tile may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed entirely
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Host: tensor map of a bf16 activation dump [layers][M][256] (row-major) whose box is one warp's share of a
+// SWIZZLE_128B k-block: 64 columns x 32 rows.  Rows beyond M are clipped by the TMA engine.  Returns 0 or a
+// negative/CUDA error code (message via set_error).
+int make_rows_tmap(CUtensorMap* out, const void* base, int64_t n_rows, int n_layers);
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

@@ -32,8 +32,8 @@ class ParamArena:
     """Every leaf of the variables tree as a view of ONE flat fp32 buffer, trainable buckets first
     (fine_mlp | coarse_mlp | bkgd_mlp | frozen rest), with a same-layout gradient buffer whose views are pre-installed
     as the leaves' `.grad`.  One memset zeroes all gradients, one NCCL call per bucket reduces them in place (no
-    flatten/unflatten copies), one kernel applies Adam, one kernel gives the weight_l2 statistic.  Inside a bucket the
-    leaves follow Flax order (Dense_i kernel, bias), except bkgd_mlp which is laid out (kernels..., biases...): that is
+    flatten/unflatten copies), one kernel applies Adam, one kernel gives the weight_l2 statistic (padding stays zero).
+    Inside a bucket the leaves follow Flax order (Dense_i kernel, bias), except bkgd_mlp which is laid out (kernels..., biases...): that is
     the background kernels' weight image, so the bucket itself is passed to them and no packing step exists."""
 
     def __init__(self, variables: Dict):
@@ -69,6 +69,7 @@ class ParamArena:
                 self.n_train = off
             lo = off
             for d, k in ents:
+                off = (off + 3) // 4 * 4          # 16-byte aligned leaves: the wgrad kernel reduces with red.v4.f32
                 layout.append((d, k, off, name))
                 off += d[k].numel()
             self.bucket_range[name] = (lo, off)
@@ -90,6 +91,7 @@ class ParamArena:
             p = params[name]
             self.sinks[name] = [p[f"Dense_{i}"][leaf].grad for i in range(len(p)) for leaf in ("kernel", "bias")]
         lo, hi = self.bucket_range["bkgd_mlp"]
+        assert hi - lo == sum(d[k].numel() for d, k in groups[GRAD_BUCKETS.index("bkgd_mlp")][1]), "bkgd bucket must be dense"
         self.sinks["bkgd_mlp"] = self.grad[lo:hi]
         self.theta_flat = {"bkgd_mlp": self.theta[lo:hi]}
 
