@@ -193,6 +193,10 @@ class TrainState:
     arena: Optional[ParamArena] = None
     graphs: Dict = dataclasses.field(default_factory=dict)
 
+    def replayed_kernel_launches(self) -> int:
+        """Kernels of this library launched through graph replays so far (the eager ones are in _lib.launch_count())."""
+        return sum(g.kernels_per_replay * g.replays for g in self.graphs.values() if isinstance(g, _GraphedStep))
+
     @staticmethod
     def create(variables: Dict, args) -> "TrainState":
         """Re-homes the variables into a ParamArena (the tree keeps its names; leaves become views) and attaches the
@@ -310,10 +314,14 @@ class _GraphedStep:
         self.static_batch = {"rays": self.rays, "pixels": self.pixels, "env_rays": self.env,
                              "annealed_alpha": float(batch["annealed_alpha"])}
         self.load(model, batch, 0, 0, args)
+        from . import _lib
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        l0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.stats = _step_body(model, state, self.static_batch, args, None, None, world_size, group, self.jitter, self.u)
+        self.kernels_per_replay = _lib.launch_count() - l0     # this library's kernel nodes in the captured graph
+        self.replays = 0
         model._pack_cache.clear()
 
     def load(self, model, batch, key_0, key_1, args):
@@ -329,6 +337,7 @@ class _GraphedStep:
 
     def replay(self):
         self.graph.replay()
+        self.replays += 1
         return dict(self.stats)
 
 
@@ -374,3 +383,21 @@ def train_step(model, rng, state: TrainState, batch: Dict, args=None, world_size
     stats["lr"] = lr
     stats["annealing_rate"] = float(batch["annealed_alpha"])
     return state, stats, (int(rng) + 1 if rng is not None else 1)
+
+
+def shutdown_distributed(state: Optional[TrainState] = None) -> None:
+    """Tear down in the order NCCL needs: captured graphs that contain all-reduce nodes keep the communicator busy, so
+    they are released (and the device drained) BEFORE the process group is destroyed; destroying the group first
+    blocks forever (seen on 2 x B200, NCCL 2.28)."""
+    import gc
+    import torch.distributed as dist
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if state is not None:
+        state.graphs.clear()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()

@@ -32,7 +32,7 @@ def grads_of(rays, px, uu, ws):
     batch = {"rays": rays, "pixels": px, "annealed_alpha": 0.5}
     total, _ = train.loss_fn(model, variables, batch, args, 1, 2, jitter=model.draw_jitter(5), u=uu)
     total.backward()
-    train.allreduce_mean_grads(variables, ws)
+    state.arena.allreduce_mean(ws)
     return variables, state, model, batch
 
 
@@ -54,4 +54,15 @@ if rank == 0:
     print(f"world={world} worst relative gradient difference vs single-GPU full batch: {worst:.3e}; params identical after step: {same}")
     assert worst < 2e-2, worst      # bf16 forward: shard order changes tile composition, not the math
 assert same
-dist.destroy_process_group()
+# graph mode: two eager steps, then the captured step (NCCL all-reduces inside the CUDA graph) replayed three times
+for i in range(5):
+    state, stats, _ = train.train_step(model, i + 1, state, batch, args, world_size=world)
+torch.cuda.synchronize()
+captured = any(isinstance(v, train._GraphedStep) for v in state.graphs.values())
+ref = state.arena.theta.clone(); dist.broadcast(ref, 0)
+same_g = torch.equal(ref, state.arena.theta)
+loss = float(stats["loss"])
+if rank == 0:
+    print(f"graph-captured step with in-graph NCCL: captured={captured}, params identical on all ranks: {same_g}, loss {loss:.5f}")
+assert captured and same_g and np.isfinite(loss)
+train.shutdown_distributed(state)

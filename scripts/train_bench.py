@@ -50,7 +50,7 @@ state.step = 3000
 for _ in range(a.warmup):
     state, stats, rng = train.train_step(model, rng, state, batch, args, world_size=world, use_graph=False if a.eager else None)
 barrier()
-l0 = _lib.launch_count()
+l0 = _lib.launch_count() + state.replayed_kernel_launches()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 import time
 torch.cuda.cudart().cudaProfilerStart()
@@ -68,8 +68,8 @@ if world > 1:
 if rank == 0:
     print(json.dumps({"metric": "training rays/sec (fwd+bwd+allreduce+Adam)", "value": a.batch * a.steps / (ms * 1e-3),
                       "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-                      "scaling": "strong", "global_batch": a.batch, "cuda_graph": not a.eager, "gpu_launches": int(_lib.launch_count() - l0),
+                      "scaling": "strong", "global_batch": a.batch, "cuda_graph": not a.eager, "gpu_launches": int(_lib.launch_count() + state.replayed_kernel_launches() - l0),
                       "loss": float(stats["loss"]), "cpu_issue_ms_per_step": cpu_issue_ms, "config": "ship_skydome training step, S=768, G=%d, 64+192 samples, "
                       "bg_weight 0.025, bg_smooth 1.0 on a 128x128 env patch" % G}))
 if world > 1:
-    dist.destroy_process_group()
+    train.shutdown_distributed(state)
