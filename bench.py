@@ -28,6 +28,10 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 FLOP_PER_SAMPLE = 2 * 593408          # un-padded MACs of NerfMLP
+# DRAM traffic of the enc+MLP kernel from its `ncu --set full` capture (profiles/r1a_encmlp_pair_kernel_ncu_summary.txt:
+# dram__bytes_read 102.95 MB + dram__bytes_write 37.99 MB for a 4 194 304-sample launch) = 33.6 B/sample, against
+# 40 B/sample algorithmic (24 B pos+dir in, 16 B raw out; part of the input is still L2-resident from its producer)
+MLP_DRAM_BYTES_PER_SAMPLE = (102.945536e6 + 37.994752e6) / 4194304
 NC, NF, P = 64, 128, 12
 S = NC * P
 NEAR, FAR = 2.0, 6.0
@@ -272,11 +276,13 @@ def main():
         peaks = json.load(open(pk_path))
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     ach_tf = FLOP_PER_SAMPLE * mlp_samples / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-    roofline = {"kernel": "encmlp_kernel (pos_enc + NerfMLP, tcgen05)", "bound": "tensor", "achieved": ach_tf,
+    roofline = {"kernel": "encmlp_pair_kernel (pos_enc + NerfMLP, tcgen05 cta_group::2)", "bound": "tensor", "achieved": ach_tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                 if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
-                "share_of_step": mlp_ms / ms, "launches": len(mlp_ev), "traffic": None}
+                "share_of_step": mlp_ms / ms, "launches": len(mlp_ev),
+                "traffic": MLP_DRAM_BYTES_PER_SAMPLE * mlp_samples / max(1, len(mlp_ev)),
+                "traffic_unit": "bytes per launch (ncu dram bytes per sample x samples per launch)"}
     e2e_ms, _, _ = timed(render_e2e, a.steps, max(1, a.warmup - 1))
     h2d = sum(t.numel() * 4 for t in host)
     d2h = out_host.numel() * 4

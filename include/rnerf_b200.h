@@ -77,6 +77,17 @@ int rnerf_march_fwd(const float* table, const float* bricks /* from rnerf_grid_b
                     const float* origins, const float* viewdirs, int64_t n_rays, double near, double far, int n_steps,
                     int rec_floats, float* path, float* t_col, void* stream);
 
+/* ---- a4 + a5/a6, "all" stage: rnerf/ior_utils.py:269-312 VoxMLP.__call__ (so3_mlp on annealed_pos_enc(p, 0, 10,
+ * alpha*10), Rodrigues rotation of grad n) inside rnerf/eikonal_utils.py:30-49 (grad = where(|grad n| > 1e-3, pred,
+ * grad n)).  so3_w: the 5 Dense kernels of so3_mlp ([in,out] row-major: 60x128, 128x128, 128x128, 188x128, 128x3) then
+ * the 5 biases, fp32, rnerf_so3_weight_floats() values.  so3_window_host[10]: cosine-easing window per octave
+ * (rnerf/model_utils.py:222-245 at alpha * 10).  Outputs as rnerf_march_fwd (idx_grad is the un-rotated grad n). */
+size_t rnerf_so3_weight_floats(void);
+int rnerf_march_all_fwd(const float* table, const float* bricks, const int ndim_host[3], const double nmin_host[3],
+                        const double nmax_host[3], const float* origins, const float* viewdirs, int64_t n_rays,
+                        double near, double far, int n_steps, int rec_floats, const float* so3_w,
+                        const double so3_window_host[10], float* path, float* t_col, void* stream);
+
 /* ray_dir[B][S][3] = safe_l2_normalize(v) of every record: the `ray_dir` array of PathSampler.__call__
  * (rnerf/eikonal_utils.py:113), for callers that want the whole bent path (extract_mesh.py:178). */
 int rnerf_path_dirs(const float* path, int rec_floats, int64_t n_rays, int n_steps, float* ray_dir, void* stream);

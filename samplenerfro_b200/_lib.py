@@ -34,6 +34,10 @@ SIGNATURES = {
     "rnerf_grid_bricks": (C.c_int, [c_f32p, C.POINTER(C.c_int), c_f32p, C.c_void_p]),
     "rnerf_march_fwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                   c_f32p, c_i64, C.c_double, C.c_double, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_so3_weight_floats": (C.c_size_t, []),
+    "rnerf_march_all_fwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
+                                      c_f32p, c_i64, C.c_double, C.c_double, C.c_int, C.c_int, c_f32p, C.POINTER(C.c_double),
+                                      c_f32p, c_f32p, C.c_void_p]),
     "rnerf_path_dirs": (C.c_int, [c_f32p, C.c_int, c_i64, C.c_int, c_f32p, C.c_void_p]),
     "rnerf_select": (C.c_int, [c_f32p, C.c_int, c_i64, C.c_int, C.c_void_p, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_encmlp_packed_bytes": (C.c_size_t, []),

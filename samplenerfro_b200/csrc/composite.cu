@@ -13,9 +13,15 @@
 
 namespace rnerf {
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-// jax.nn.softplus(x) = logaddexp(x, 0)
-__device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+// The kernels were issue-bound (88 % issue-slot utilisation at 35 % of HBM peak, profiles/r1a_composite_*): the
+// activations dominated the instruction count.  They now use the SFU forms (ex2.approx / rcp.approx / lg2.approx, each
+// <= 2^-21 relative): their errors enter the outputs multiplied by weights that sum to <= 1, so the composited values
+// move by < 1e-6 absolute.  alpha = 1 - exp(-sigma delta) keeps the accurate expf: there an error of the exponential is
+// NOT scaled down (alpha ~ 0 in empty space) and would accumulate over the samples of a ray.
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// jax.nn.softplus(x) = logaddexp(x, 0) = max(x, 0) + log(1 + exp(-|x|))
+__device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
+__device__ __forceinline__ float trans_exp(float x) { return __expf(x); }   // transmittance: relative error only
 
 struct CompositeArgs {
   const float4* raw;   // [B][Ns] (r,g,b,sigma) raw
@@ -72,7 +78,7 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a, flo
     float incl = warp_incl_scan(s.dd, lane);
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = 0.f;
-    float T = expf(-(carry + excl));
+    float T = trans_exp(-(carry + excl));
     float al = 1.f - expf(-s.dd);
     float w = al * T;
     if (valid) {
@@ -94,7 +100,7 @@ __global__ void __launch_bounds__(128) composite_fwd_kernel(CompositeArgs a, flo
   }
   sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sw = warp_sum(sw); swt = warp_sum(swt);
   if (lane == 0) {
-    const float Tend = expf(-carry);
+    const float Tend = trans_exp(-carry);
     float br = 1.f, bg = 1.f, bb = 1.f;  // rgb_bkgd=None -> ones (model_utils.py:301)
     if (a.bkgd_raw) {
       br = sigmoidf_(a.bkgd_raw[3 * ray]) * a.rgb_scale - a.rgb_pad;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeArgs a, con
     float incl = warp_incl_scan(s.dd, lane);
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = 0.f;
-    float T = expf(-(carry + excl));
+    float T = trans_exp(-(carry + excl));
     float w = (1.f - expf(-s.dd)) * T;
     tot += w * (gr * s.r + gg * s.g + gb * s.b);
     totw += w;
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeArgs a, con
   }
   tot = warp_sum(tot);
   totw = warp_sum(totw);
-  const float Tend = expf(-carry);
+  const float Tend = trans_exp(-carry);
   // gradient flowing into T_N: comp_rgb bkgd term, trans, trans_rgb_bkgd (bkgd stop-grad)
   float gT = 0.f;
   if (a.bkgd_raw) gT += gr * br + gg * bg + gb * bb;
@@ -171,8 +177,8 @@ __global__ void __launch_bounds__(128) composite_bwd_kernel(CompositeArgs a, con
     float incl = warp_incl_scan(s.dd, lane);
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = 0.f;
-    float T = expf(-(carry + excl));
-    float Tn = expf(-(carry + incl));
+    float T = trans_exp(-(carry + excl));
+    float Tn = trans_exp(-(carry + incl));
     float w = (1.f - expf(-s.dd)) * T;
     float gc = gr * s.r + gg * s.g + gb * s.b;
     float pre = warp_incl_scan(w * gc, lane);

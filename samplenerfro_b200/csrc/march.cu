@@ -133,13 +133,127 @@ __device__ __forceinline__ float4 march_lookup(const float4* __restrict__ table,
   return lerp4_ref(c0, c1, ozd, zd);
 }
 
-template <int RECF4, bool FAST>
-__global__ void __launch_bounds__(MARCH_THREADS, 8) march_kernel(const float4* __restrict__ table, const MarchGeom mg,
+// ---- "all" stage (a4): so3_mlp inside every eikonal step -------------------------------------------------------------
+// VoxMLP.__call__ (rnerf/ior_utils.py:269-312): raw = so3_mlp(annealed_pos_enc(p, 0, 10, alpha*10)); theta = |raw|_safe,
+// e = raw/theta, a = |grad n|_safe, v = grad n / a; pred = a (cos(theta) v + sin(theta) e x v + (1 - cos(theta)) (e.v) e);
+// OneEikonalStep (rnerf/eikonal_utils.py:34-35) then uses where(|grad n| > 1e-3, pred, grad n).
+// so3_mlp = model_utils.MLP(net_width=128, net_depth=4, skip_layer=2, 3 outputs): 60 -> 128 -> 128 -> 128 (+60) -> 128 -> 3.
+//
+// The `where` makes the MLP irrelevant wherever |grad n| <= 1e-3 (everywhere but the blurred object boundary), so a warp
+// only evaluates it at steps where one of its 32 rays needs it.  The evaluation is warp-cooperative in fp32 (the result
+// steers the ray, so no reduced-precision operands): activations live in shared memory as [feature][ray]; lane l owns
+// output neurons l, l+32, l+64, l+96 of a hidden layer for all 32 rays (128 accumulators), reads the weight row with
+// coalesced loads (the 260 KB of weights stay L2-resident) and the activations with broadcast LDS.128.
+constexpr int SO3_IN = 60, SO3_W = 128, SO3_PITCH = 36;     // pitch: 16-byte aligned rows, 4-way conflicts on the (rare) writes
+constexpr int SO3_OFF_W1 = SO3_IN * SO3_W, SO3_OFF_W2 = SO3_OFF_W1 + SO3_W * SO3_W, SO3_OFF_W3 = SO3_OFF_W2 + SO3_W * SO3_W,
+              SO3_OFF_W4 = SO3_OFF_W3 + (SO3_W + SO3_IN) * SO3_W, SO3_OFF_B = SO3_OFF_W4 + SO3_W * 3,
+              SO3_FLOATS = SO3_OFF_B + 4 * SO3_W + 3;
+constexpr int SO3_SMEM_PER_WARP = (SO3_IN + SO3_W) * SO3_PITCH * 4;   // X[60][36] + H[128][36] fp32 = 27 072 B
+
+struct So3Args {
+  const float* w;        // kernels W0..W4 ([in][out] row-major) then biases b0..b4, fp32, SO3_FLOATS
+  float window[10];      // cosine-easing window of annealed_pos_enc (rnerf/model_utils.py:236-245) per octave
+};
+
+// acc[m][r] += sum_k W[k][lane + 32 m] * in[k][r]
+__device__ __forceinline__ void so3_accumulate(float (&acc)[4][32], const float* __restrict__ W, const float* in, int K, int lane) {
+#pragma unroll 2
+  for (int k = 0; k < K; ++k) {
+    const float* wr = W + k * SO3_W + lane;
+    const float w0 = __ldg(wr), w1 = __ldg(wr + 32), w2 = __ldg(wr + 64), w3 = __ldg(wr + 96);
+    const float4* xr = reinterpret_cast<const float4*>(in + k * SO3_PITCH);
+#pragma unroll
+    for (int r4 = 0; r4 < 8; ++r4) {
+      const float4 x = xr[r4];
+      acc[0][4 * r4] = fmaf(w0, x.x, acc[0][4 * r4]); acc[0][4 * r4 + 1] = fmaf(w0, x.y, acc[0][4 * r4 + 1]);
+      acc[0][4 * r4 + 2] = fmaf(w0, x.z, acc[0][4 * r4 + 2]); acc[0][4 * r4 + 3] = fmaf(w0, x.w, acc[0][4 * r4 + 3]);
+      acc[1][4 * r4] = fmaf(w1, x.x, acc[1][4 * r4]); acc[1][4 * r4 + 1] = fmaf(w1, x.y, acc[1][4 * r4 + 1]);
+      acc[1][4 * r4 + 2] = fmaf(w1, x.z, acc[1][4 * r4 + 2]); acc[1][4 * r4 + 3] = fmaf(w1, x.w, acc[1][4 * r4 + 3]);
+      acc[2][4 * r4] = fmaf(w2, x.x, acc[2][4 * r4]); acc[2][4 * r4 + 1] = fmaf(w2, x.y, acc[2][4 * r4 + 1]);
+      acc[2][4 * r4 + 2] = fmaf(w2, x.z, acc[2][4 * r4 + 2]); acc[2][4 * r4 + 3] = fmaf(w2, x.w, acc[2][4 * r4 + 3]);
+      acc[3][4 * r4] = fmaf(w3, x.x, acc[3][4 * r4]); acc[3][4 * r4 + 1] = fmaf(w3, x.y, acc[3][4 * r4 + 1]);
+      acc[3][4 * r4 + 2] = fmaf(w3, x.z, acc[3][4 * r4 + 2]); acc[3][4 * r4 + 3] = fmaf(w3, x.w, acc[3][4 * r4 + 3]);
+    }
+  }
+}
+
+// raw = so3_mlp(annealed_pos_enc(p)) for the warp's 32 rays; every lane participates, returns this lane's ray's raw[3]
+__device__ __forceinline__ void so3_eval(const So3Args& a, float* scratch, int lane, float px, float py, float pz,
+                                         float& r0, float& r1, float& r2) {
+  float* X = scratch;                          // [60][36]
+  float* Hs = scratch + SO3_IN * SO3_PITCH;    // [128][36]
+  const float xs[3] = {px, py, pz};
+  const float half_pi = 1.57079632679489661923f;
+  float sc = 1.f;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {               // feature index k*6 + c (sin), k*6 + 3 + c (sin(x + pi/2)), times window[k]
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xb = mul(xs[c], sc);
+      X[(k * 6 + c) * SO3_PITCH + lane] = mul(sinf(xb), a.window[k]);
+      X[(k * 6 + 3 + c) * SO3_PITCH + lane] = mul(sinf(add(xb, half_pi)), a.window[k]);
+    }
+    sc *= 2.f;
+  }
+  __syncwarp();
+  const float* bias = a.w + SO3_OFF_B;
+  float acc[4][32];
+  auto finish = [&](const float* b) {          // bias + ReLU, in-place hand-over through Hs
+    __syncwarp();                              // every lane has finished reading the layer input
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float bj = __ldg(b + lane + 32 * m);
+      float* row = Hs + (lane + 32 * m) * SO3_PITCH;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) row[r] = fmaxf(acc[m][r] + bj, 0.f);
+    }
+    __syncwarp();
+  };
+  auto clear = [&]() {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int r = 0; r < 32; ++r) acc[m][r] = 0.f;
+  };
+  clear(); so3_accumulate(acc, a.w, X, SO3_IN, lane); finish(bias);                                   // Dense_0
+  clear(); so3_accumulate(acc, a.w + SO3_OFF_W1, Hs, SO3_W, lane); finish(bias + SO3_W);              // Dense_1
+  clear(); so3_accumulate(acc, a.w + SO3_OFF_W2, Hs, SO3_W, lane); finish(bias + 2 * SO3_W);          // Dense_2, then concat(x, inputs)
+  clear(); so3_accumulate(acc, a.w + SO3_OFF_W3, Hs, SO3_W, lane);
+  so3_accumulate(acc, a.w + SO3_OFF_W3 + SO3_W * SO3_W, X, SO3_IN, lane); finish(bias + 3 * SO3_W);   // Dense_3 on [h, inputs]
+  const float* W4 = a.w + SO3_OFF_W4;
+  const float* b4 = bias + 4 * SO3_W;
+  r0 = __ldg(b4); r1 = __ldg(b4 + 1); r2 = __ldg(b4 + 2);
+#pragma unroll 4
+  for (int k = 0; k < SO3_W; ++k) {            // Dense_4: this lane's own ray
+    const float h = Hs[k * SO3_PITCH + lane];
+    r0 = fmaf(h, __ldg(W4 + 3 * k), r0); r1 = fmaf(h, __ldg(W4 + 3 * k + 1), r1); r2 = fmaf(h, __ldg(W4 + 3 * k + 2), r2);
+  }
+  __syncwarp();
+}
+
+// Rodrigues rotation of grad n by raw (rnerf/ior_utils.py:300-306); safe_l2_norm = sqrt(max(sum sq, 1e-6))
+__device__ __forceinline__ void so3_rotate(float r0, float r1, float r2, float& gx, float& gy, float& gz) {
+  const float theta = sqrtf(fmaxf(sumsq3(r0, r1, r2), 1e-6f));
+  const float ex = divf(r0, theta), ey = divf(r1, theta), ez = divf(r2, theta);
+  const float an = sqrtf(fmaxf(sumsq3(gx, gy, gz), 1e-6f));
+  const float vx = divf(gx, an), vy = divf(gy, an), vz = divf(gz, an);
+  const float ct = cosf(theta), st = sinf(theta);
+  const float cx = sub(mul(ey, vz), mul(ez, vy)), cy = sub(mul(ez, vx), mul(ex, vz)), cz = sub(mul(ex, vy), mul(ey, vx));
+  const float ev = add(add(mul(ex, vx), mul(ey, vy)), mul(ez, vz));
+  const float omc = mul(sub(1.f, ct), ev);
+  gx = mul(an, add(add(mul(ct, vx), mul(st, cx)), mul(omc, ex)));
+  gy = mul(an, add(add(mul(ct, vy), mul(st, cy)), mul(omc, ey)));
+  gz = mul(an, add(add(mul(ct, vz), mul(st, cz)), mul(omc, ez)));
+}
+
+template <int RECF4, bool FAST, bool SO3>
+__global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 1 : 8) march_kernel(const float4* __restrict__ table, const MarchGeom mg,
                                                               const float* __restrict__ origins,
                                                               const float* __restrict__ viewdirs, int64_t n_rays,
                                                               float near, float step, int n_steps,
                                                               float4* __restrict__ path, float* __restrict__ t_col,
-                                                              const float* __restrict__ bricks, int dbg) {
+                                                              const float* __restrict__ bricks, int dbg, const So3Args so3) {
+  extern __shared__ __align__(16) float so3_scratch[];     // SO3 only: SO3_SMEM_PER_WARP bytes per warp
   constexpr int F4_PER_FLUSH = STEPS_PER_FLUSH * RECF4;   // float4 per ray per flush: 8 (compact) / 12 (full)
   constexpr int PITCH = F4_PER_FLUSH + 1;                  // +1 float4 pad: conflict-free column writes
   __shared__ float4 stage[MARCH_THREADS / 32][32 * PITCH];
@@ -186,9 +300,18 @@ __global__ void __launch_bounds__(MARCH_THREADS, 8) march_kernel(const float4* _
     my_stage[kk * RECF4 + 1] = make_float4(vx, vy, vz, c.x);
     if (RECF4 == 3) my_stage[kk * RECF4 + 2] = make_float4(c.y, c.z, c.w, 0.f);
     ts[(trow + kk) * 32 + lane] = t;
+    float gx = c.y, gy = c.z, gz = c.w;
+    if (SO3) {
+      const bool act = sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;     // jnp.linalg.norm(idx_grad) > 1e-3
+      if (__any_sync(0xffffffffu, act)) {
+        float r0, r1, r2;
+        so3_eval(so3, so3_scratch + warp * (SO3_SMEM_PER_WARP / 4), lane, px, py, pz, r0, r1, r2);
+        if (act) so3_rotate(r0, r1, r2, gx, gy, gz);
+      }
+    }
     const float s = divf(step, c.x);
     const float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
-    vx = add(vx, mul(step, c.y)); vy = add(vy, mul(step, c.z)); vz = add(vz, mul(step, c.w));
+    vx = add(vx, mul(step, gx)); vy = add(vy, mul(step, gy)); vz = add(vz, mul(step, gz));
     t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
     px = nx; py = ny; pz = nz;
   };
@@ -292,10 +415,10 @@ static bool fast_div_enabled() {
   return !(e != nullptr && strcmp(e, "ieee") == 0);
 }
 
-extern "C" int rnerf_march_fwd(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
-                               const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
-                               double near, double far, int n_steps, int rec_floats, float* path, float* t_col,
-                               void* stream) {
+static int march_impl(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
+                      const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
+                      double near, double far, int n_steps, int rec_floats, const float* so3_w,
+                      const double* so3_window, float* path, float* t_col, void* stream) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_fwd: n_rays < 0");
   RNERF_REQUIRE(n_steps >= 2, RNERF_E_SHAPE, "rnerf_march_fwd: n_steps must be >= 2 (step = (far-near)/(S-1))");
@@ -319,14 +442,58 @@ extern "C" int rnerf_march_fwd(const float* table, const float* bricks, const in
   const char* dbg_env = getenv("RNERF_MARCH_DEBUG");   // development aid: 1 = no record stores, 2 = no t stores, 4 = plain stores
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   const unsigned blocks = (unsigned)((n_rays + MARCH_THREADS - 1) / MARCH_THREADS);
-#define RNERF_MARCH_LAUNCH(R, F)                                                                                       \
-  march_kernel<R, F><<<blocks, MARCH_THREADS, 0, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
-                                                       step, n_steps, (float4*)path, t_col, bricks, dbg)
-  if (rec_floats == 8) { if (fast) RNERF_MARCH_LAUNCH(2, true); else RNERF_MARCH_LAUNCH(2, false); }
-  else                 { if (fast) RNERF_MARCH_LAUNCH(3, true); else RNERF_MARCH_LAUNCH(3, false); }
+  So3Args so3;
+  memset(&so3, 0, sizeof(so3));
+  size_t dyn = 0;
+  if (so3_w != nullptr) {
+    so3.w = so3_w;
+    for (int k = 0; k < 10; ++k) so3.window[k] = (float)so3_window[k];
+    dyn = (size_t)(MARCH_THREADS / 32) * SO3_SMEM_PER_WARP;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      cudaError_t e = cudaSuccess;
+      e = cudaFuncSetAttribute(march_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(march_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(march_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(march_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      if (e != cudaSuccess) { set_error("rnerf_march_all_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+      attr_set[dev] = true;
+    }
+  }
+#define RNERF_MARCH_LAUNCH(R, F, A)                                                                                       \
+  march_kernel<R, F, A><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
+                                                            step, n_steps, (float4*)path, t_col, bricks, dbg, so3)
+  if (so3_w == nullptr) {
+    if (rec_floats == 8) { if (fast) RNERF_MARCH_LAUNCH(2, true, false); else RNERF_MARCH_LAUNCH(2, false, false); }
+    else                 { if (fast) RNERF_MARCH_LAUNCH(3, true, false); else RNERF_MARCH_LAUNCH(3, false, false); }
+  } else {
+    if (rec_floats == 8) { if (fast) RNERF_MARCH_LAUNCH(2, true, true); else RNERF_MARCH_LAUNCH(2, false, true); }
+    else                 { if (fast) RNERF_MARCH_LAUNCH(3, true, true); else RNERF_MARCH_LAUNCH(3, false, true); }
+  }
 #undef RNERF_MARCH_LAUNCH
   count_launch();
-  return check_launch("rnerf_march_fwd");
+  return check_launch(so3_w ? "rnerf_march_all_fwd" : "rnerf_march_fwd");
+}
+
+extern "C" int rnerf_march_fwd(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
+                               const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
+                               double near, double far, int n_steps, int rec_floats, float* path, float* t_col,
+                               void* stream) {
+  return march_impl(table, bricks, ndim, nmin, nmax, origins, viewdirs, n_rays, near, far, n_steps, rec_floats, nullptr,
+                    nullptr, path, t_col, stream);
+}
+
+extern "C" size_t rnerf_so3_weight_floats(void) { return SO3_FLOATS; }
+
+extern "C" int rnerf_march_all_fwd(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
+                                   const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
+                                   double near, double far, int n_steps, int rec_floats, const float* so3_w,
+                                   const double so3_window[10], float* path, float* t_col, void* stream) {
+  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(so3_window);
+  return march_impl(table, bricks, ndim, nmin, nmax, origins, viewdirs, n_rays, near, far, n_steps, rec_floats, so3_w,
+                    so3_window, path, t_col, stream);
 }
 
 extern "C" int rnerf_select(const float* path, int rec_floats, int64_t n_rays, int n_steps, const int32_t* jitter,

@@ -104,8 +104,8 @@ class NerfModel:
         if (str(net_activation), str(rgb_activation), str(sigma_activation)) != ("relu", "sigmoid", "softplus"):
             unsupported.append("activations other than relu/sigmoid/softplus")
         if (num_rgb_channels, num_sigma_channels) != (3, 1): unsupported.append("num_rgb_channels/num_sigma_channels != 3/1")
-        if stage.startswith("all") or stage.startswith("ior"):
-            unsupported.append(f"stage={stage!r} (only the radiance stage is built; SURVEY section 8(f) rank 1)")
+        if stage.startswith("ior"):
+            unsupported.append(f"stage={stage!r} (the IoR-fitting stage is not built; SURVEY section 8(f) rank 1)")
         if self.num_fine_samples <= 0: unsupported.append("num_fine_samples <= 0")
         if unsupported:
             raise NotImplementedError("rnerf_b200 kernels do not cover: " + "; ".join(unsupported))
@@ -147,6 +147,23 @@ class NerfModel:
             buf = ops.bkgd_pack(p) if name == "bkgd_mlp" else ops.encmlp_pack(p, out=hit[1] if hit else None)
         self._pack_cache[name] = (sig, buf)
         return buf
+
+    def so3_window(self, annealed_alpha: float) -> List[float]:
+        """cosine_easing_window(0, 9, 10, annealed_alpha * 10) of annealed_pos_enc (rnerf/model_utils.py:222-245), in
+        fp32 like the reference evaluates it."""
+        bands = torch.linspace(0.0, 9.0, 10, dtype=torch.float32)
+        x = torch.clamp(torch.tensor(float(annealed_alpha) * 10, dtype=torch.float32) - bands, 0.0, 1.0)
+        return [float(v) for v in 0.5 * (1 + torch.cos(math.pi * x + math.pi))]
+
+    def _so3_packed(self, variables: Dict) -> torch.Tensor:
+        p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+        sig = tuple((id(d["kernel"]), d["kernel"]._version, id(d["bias"]), d["bias"]._version) for d in p.values())
+        hit = self._pack_cache.get("so3_mlp")
+        if hit is None or hit[0] != sig:
+            with torch.no_grad():
+                hit = (sig, ops.so3_pack(p))
+            self._pack_cache["so3_mlp"] = hit
+        return hit[1]
 
     # ------------------------------------------------------------------ stochastic inputs
     def draw_jitter(self, key, host: bool = False) -> torch.Tensor:
@@ -208,8 +225,14 @@ class NerfModel:
             # idx_grad is only read by the sparsity term and the debug outputs: every shipped config marches with
             # compact (pos, t | v, n) records
             need_grad = debug or self.use_online_sparsity
+            so3 = None
+            if self.stage.startswith("all"):     # a4: so3_mlp rotates grad n inside every step (inference only)
+                if torch.is_grad_enabled() and any(t.requires_grad for d in variables["params"]["path_sampler"]["scan"][
+                        "idx_model"]["so3_mlp"].values() for t in d.values()):
+                    raise NotImplementedError("training the 'all' stage (adjoint of the S-step scan wrt so3_mlp) is not built")
+                so3 = (self._so3_packed(variables), self.so3_window(annealed_alpha))
             path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S,
-                             bricks=self.bricks, compact=not need_grad)
+                             bricks=self.bricks, compact=not need_grad, so3=so3)
             jit = self.draw_jitter(k0) if jitter is None else torch.as_tensor(jitter).to(self.device, torch.int32).contiguous()
             pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=self.use_online_sparsity)
             mask_c = self._bbox_mask(pos_c) if self.use_mask_bbox else None

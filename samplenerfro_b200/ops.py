@@ -90,12 +90,28 @@ class BentPath(NamedTuple):
         return self.rec.shape[-1] == PATH_STRIDE_COMPACT
 
 
+def so3_pack(p: Dict) -> torch.Tensor:
+    """so3_mlp parameters (model_utils.MLP 60 -> 128 x4 (+60 after layer 2) -> 3, rnerf/ior_utils.py:147-152) as the flat
+    fp32 image rnerf_march_all_fwd reads: the 5 kernels, then the 5 biases."""
+    ks = [_chk(p[f"Dense_{i}"]["kernel"], f"so3 Dense_{i}.kernel") for i in range(5)]
+    bs = [_chk(p[f"Dense_{i}"]["bias"], f"so3 Dense_{i}.bias") for i in range(5)]
+    expect = [(60, 128), (128, 128), (128, 128), (188, 128), (128, 3)]
+    for i, (k, e) in enumerate(zip(ks, expect)):
+        if tuple(k.shape) != e:
+            raise _lib.RnerfError(f"so3 Dense_{i}.kernel has shape {tuple(k.shape)}, expected {e}")
+    w = torch.cat([k.reshape(-1) for k in ks] + [b.reshape(-1) for b in bs]).contiguous()
+    assert w.numel() == _lib.load().rnerf_so3_weight_floats()
+    return w
+
+
 def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n_steps: int,
           out: Optional[BentPath] = None, bricks: Optional[torch.Tensor] = None, compact: bool = False,
-          t_col: bool = True) -> BentPath:
-    """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124), radiance stage.  Returns the BentPath.
+          t_col: bool = True, so3: Optional[Tuple[torch.Tensor, Sequence[float]]] = None) -> BentPath:
+    """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124).  Returns the BentPath.
     `bricks` (from grid_bricks) lets the kernel skip the gathers in homogeneous space; results are bit-identical.
-    `compact` drops idx_grad from the records (8 instead of 12 floats per step)."""
+    `compact` drops idx_grad from the records (8 instead of 12 floats per step).
+    `so3` = (so3_pack(...) weights, 10 window values): the "all" stage, where every step rotates grad n by the so3_mlp
+    prediction wherever |grad n| > 1e-3 (rnerf/eikonal_utils.py:34-35); None = radiance stage."""
     _chk(table, "table"); origins = _chk(origins, "origins"); viewdirs = _chk(viewdirs, "viewdirs")
     if bricks is not None:
         _chk(bricks, "bricks")
@@ -111,6 +127,15 @@ def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n
             _chk(out.t, "out.t")
             assert out.t.shape == (B, n_steps)
     nd, lo, hi = _geom(ndim, nmin, nmax)
+    if so3 is not None:
+        w, window = so3
+        _chk(w, "so3 weights")
+        assert len(window) == 10
+        win = (C.c_double * 10)(*[float(v) for v in window])
+        check(_lib.load().rnerf_march_all_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
+                                              float(far), int(n_steps), W, _p(w), win, _p(out.rec), _p(out.t), _stream()),
+              "rnerf_march_all_fwd")
+        return out
     check(_lib.load().rnerf_march_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
                                       float(far), int(n_steps), W, _p(out.rec), _p(out.t), _stream()), "rnerf_march_fwd")
     return out

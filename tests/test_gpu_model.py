@@ -114,10 +114,44 @@ def test_unsupported_configs_fail_loudly(cuda_lib, example_scene):
     with pytest.raises(NotImplementedError):
         models.construct_nerf(0, None, _flags(net_width=128), ndim, nmin, nmax, n)
     with pytest.raises(NotImplementedError):
-        models.construct_nerf(0, None, _flags(stage="all"), ndim, nmin, nmax, n)
+        models.construct_nerf(0, None, _flags(stage="ior"), ndim, nmin, nmax, n)
 
 
 def test_cpu_tensors_are_rejected(cuda_lib):
     from samplenerfro_b200 import ops, _lib
     with pytest.raises(_lib.RnerfError):
         ops.grid_table(torch.ones(8), [2, 2, 2], [0.0] * 3, [1.0] * 3)
+
+
+def test_all_stage_model_matches_oracle(cuda_lib):
+    """stage="all" end to end (march with the so3 rotation -> coarse -> resample -> fine) vs the oracle, with so3 weights
+    large enough to bend the rays visibly, annealed_alpha = 0.6."""
+    from samplenerfro_b200 import models, utils
+    n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
+    args = _flags(stage="all")
+    model, variables = models.construct_nerf(5, None, args, ndim, nmin, nmax, n)
+    so3 = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+    gen = torch.Generator().manual_seed(3)
+    so3["Dense_4"]["kernel"].copy_((torch.randn(128, 3, generator=gen) * 0.05).cuda())
+    so3["Dense_4"]["bias"].copy_((torch.randn(3, generator=gen) * 0.2).cuda())
+    o, d = H.random_rays(64, seed=11)
+    jitter = model.draw_jitter(2)
+    u = O.deterministic_u(128)
+    with torch.no_grad():
+        ret, _, dbg = model.apply(variables, 0, 0, utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(64, 1).cuda()), False, 0.6,
+                                  jitter=jitter, u=u, debug=True)
+
+    def cv(t):
+        return {k: cv(v) for k, v in t.items()} if isinstance(t, dict) else t.detach().cpu()
+
+    cfg = O.ModelCfg(ndim=ndim, nmin=nmin, nmax=nmax, cfg_name="example", stage="all")
+    oret, _, odbg = O.nerf_model_apply(cv(variables), O.build_table(n, ndim, nmin, nmax), cfg, O.Rays(o, d, d, torch.ones(64, 1)),
+                                       jitter.cpu().long(), u, annealed_alpha=0.6, debug=True)
+    scale = odbg["ray_pos"].abs().max().item()
+    assert (dbg["ray_pos"].cpu() - odbg["ray_pos"]).abs().max().item() < 1e-4 * scale
+    plain_model, _ = models.construct_nerf(5, None, _flags(), ndim, nmin, nmax, n)
+    with torch.no_grad():
+        _, _, pdbg = plain_model.apply(variables, 0, 0, utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(64, 1).cuda()), False,
+                                       jitter=jitter, u=u, debug=True)
+    assert (pdbg["ray_pos"] - dbg["ray_pos"]).abs().max().item() > 1e-3      # the rotation changed the paths
+    assert H.psnr(ret[1][0], oret[1][0]) >= 50.0

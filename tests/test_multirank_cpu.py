@@ -70,8 +70,10 @@ def _arena_worker(rank, world, port, q):
     loss.backward()
     arena.allreduce_mean(world)
     lo, hi = arena.bucket_range["bkgd_mlp"]
-    ok = bool(torch.allclose(arena.grad[:arena.bucket_range["coarse_mlp"][1]], torch.full((1,), 1.5)))
-    ok = ok and bool(torch.allclose(arena.grad[lo:hi], torch.full((1,), 1.5)))
+    leaves = [p for n in train.GRAD_BUCKETS for p in train.tree_leaves(V["params"][n])]
+    ok = all(bool(torch.allclose(p.grad, torch.full((1,), 1.5))) for p in leaves)
+    ok = ok and bool(torch.allclose(arena.grad[lo:hi], torch.full((1,), 1.5)))          # the bkgd bucket is dense
+    ok = ok and abs(arena.grad.sum().item() - 1.5 * sum(p.numel() for p in leaves)) < 1.0   # padding stayed zero
     ok = ok and V["params"]["fine_mlp"]["Dense_5"]["kernel"].grad.data_ptr() == arena.sinks["fine_mlp"][10].data_ptr()
     ok = ok and V["params"]["path_sampler"]["so3_mlp"]["Dense_0"]["kernel"].grad is None
     q.put((rank, ok))
