@@ -182,6 +182,15 @@ int rnerf_grad_sumsq(const float* grad, const float* theta /* or NULL */, int64_
 int rnerf_adam_step(float* theta, const float* grad, float* mu, float* nu, int64_t n, const float* hyper,
                     const float* norm_sq /* or NULL */, void* stream);
 
+/* ---- rnerf/datasets.py:216-242 (Blender) / :486-518 (OpenCV) _generate_rays for image rows
+ * [row0, row0 + n_rows) of one camera.  camtoworld_host: the 3x4 pose, row-major (rounded to fp32 like the reference's
+ * arrays).  Blender: focal = fx (fy, cx, cy unused).  Outputs [n_rows*W][3] (radii [n_rows*W]); any may be NULL. */
+int rnerf_generate_rays(const double camtoworld_host[12], int height, int width, int opencv, double fx, double fy,
+                        double cx, double cy, int use_pixel_centers, int row0, int n_rows, float* origins,
+                        float* directions, float* viewdirs, float* radii, void* stream);
+/* out_accum[0] += sum (a - b)^2: the image mse behind compute_psnr (rnerf/utils.py:392-401) */
+int rnerf_sq_err(const float* a, const float* b, int64_t n, float* out_accum, void* stream);
+
 /* ---- a15: rnerf/models.py:498-503 bd_cut_dist mask: reverse-cumsum(inside bbox) > 0 ---- */
 int rnerf_bbox_tail_mask(const float* pos, int64_t n_rays, int n_samples, const double lo_host[3],
                          const double hi_host[3], float* mask, float* inv_mask, void* stream);

@@ -51,6 +51,9 @@ SIGNATURES = {
     "rnerf_mlp_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_i64, C.c_void_p, C.c_void_p]),
     "rnerf_mlp_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, c_i64, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_mlp_head_grad": (C.c_int, [C.c_void_p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_generate_rays": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                      C.c_double, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_sq_err": (C.c_int, [c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_sumsq": (C.c_int, [c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_grad_sumsq": (C.c_int, [c_f32p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_adam_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),

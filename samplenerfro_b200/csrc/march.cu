@@ -139,11 +139,11 @@ __device__ __forceinline__ float4 march_lookup(const float4* __restrict__ table,
 // OneEikonalStep (rnerf/eikonal_utils.py:34-35) then uses where(|grad n| > 1e-3, pred, grad n).
 // so3_mlp = model_utils.MLP(net_width=128, net_depth=4, skip_layer=2, 3 outputs): 60 -> 128 -> 128 -> 128 (+60) -> 128 -> 3.
 //
-// The `where` makes the MLP irrelevant wherever |grad n| <= 1e-3 (everywhere but the blurred object boundary), so a warp
-// only evaluates it at steps where one of its 32 rays needs it.  The evaluation is warp-cooperative in fp32 (the result
-// steers the ray, so no reduced-precision operands): activations live in shared memory as [feature][ray]; lane l owns
-// output neurons l, l+32, l+64, l+96 of a hidden layer for all 32 rays (128 accumulators), reads the weight row with
-// coalesced loads (the 260 KB of weights stay L2-resident) and the activations with broadcast LDS.128.
+// The `where` makes the MLP irrelevant wherever |grad n| <= 1e-3 (everywhere but the blurred object boundary), so a CTA
+// only evaluates it at steps where one of its 128 rays needs it.  The evaluation is fp32 on the CUDA cores (the result
+// steers the ray, so no reduced-precision operands): per warp the activations of its 32 rays live in shared memory as
+// [feature][ray]; lane l owns output neurons l, l+32, l+64, l+96 of a hidden layer for all 32 rays (128 accumulators)
+// and reads the activations with broadcast LDS.128.
 constexpr int SO3_IN = 60, SO3_W = 128, SO3_PITCH = 36;     // pitch: 16-byte aligned rows, 4-way conflicts on the (rare) writes
 constexpr int SO3_OFF_W1 = SO3_IN * SO3_W, SO3_OFF_W2 = SO3_OFF_W1 + SO3_W * SO3_W, SO3_OFF_W3 = SO3_OFF_W2 + SO3_W * SO3_W,
               SO3_OFF_W4 = SO3_OFF_W3 + (SO3_W + SO3_IN) * SO3_W, SO3_OFF_B = SO3_OFF_W4 + SO3_W * 3,
@@ -155,80 +155,136 @@ struct So3Args {
   float window[10];      // cosine-easing window of annealed_pos_enc (rnerf/model_utils.py:236-245) per octave
 };
 
-// acc[m][r] += sum_k W[k][lane + 32 m] * in[k][r]
-__device__ __forceinline__ void so3_accumulate(float (&acc)[4][32], const float* __restrict__ W, const float* in, int K, int lane) {
-#pragma unroll 2
-  for (int k = 0; k < K; ++k) {
-    const float* wr = W + k * SO3_W + lane;
-    const float w0 = __ldg(wr), w1 = __ldg(wr + 32), w2 = __ldg(wr + 64), w3 = __ldg(wr + 96);
-    const float4* xr = reinterpret_cast<const float4*>(in + k * SO3_PITCH);
-#pragma unroll
-    for (int r4 = 0; r4 < 8; ++r4) {
-      const float4 x = xr[r4];
-      acc[0][4 * r4] = fmaf(w0, x.x, acc[0][4 * r4]); acc[0][4 * r4 + 1] = fmaf(w0, x.y, acc[0][4 * r4 + 1]);
-      acc[0][4 * r4 + 2] = fmaf(w0, x.z, acc[0][4 * r4 + 2]); acc[0][4 * r4 + 3] = fmaf(w0, x.w, acc[0][4 * r4 + 3]);
-      acc[1][4 * r4] = fmaf(w1, x.x, acc[1][4 * r4]); acc[1][4 * r4 + 1] = fmaf(w1, x.y, acc[1][4 * r4 + 1]);
-      acc[1][4 * r4 + 2] = fmaf(w1, x.z, acc[1][4 * r4 + 2]); acc[1][4 * r4 + 3] = fmaf(w1, x.w, acc[1][4 * r4 + 3]);
-      acc[2][4 * r4] = fmaf(w2, x.x, acc[2][4 * r4]); acc[2][4 * r4 + 1] = fmaf(w2, x.y, acc[2][4 * r4 + 1]);
-      acc[2][4 * r4 + 2] = fmaf(w2, x.z, acc[2][4 * r4 + 2]); acc[2][4 * r4 + 3] = fmaf(w2, x.w, acc[2][4 * r4 + 3]);
-      acc[3][4 * r4] = fmaf(w3, x.x, acc[3][4 * r4]); acc[3][4 * r4 + 1] = fmaf(w3, x.y, acc[3][4 * r4 + 1]);
-      acc[3][4 * r4 + 2] = fmaf(w3, x.z, acc[3][4 * r4 + 2]); acc[3][4 * r4 + 3] = fmaf(w3, x.w, acc[3][4 * r4 + 3]);
-    }
-  }
+// The four hidden-layer kernels are contiguous in the weight image: one [504][128] fp32 matrix (60 + 128 + 128 + 188
+// rows).  It is streamed through a 3-slot shared-memory ring in chunks of <= 16 rows that never straddle a segment
+// (a segment = the rows multiplying one input block): S0 = Dense_0 x X, S1 = Dense_1 x H, S2 = Dense_2 x H,
+// S3a = Dense_3[:128] x H, S3b = Dense_3[128:] x X (the skip concat [h, inputs]).  All 128 threads of the CTA copy a chunk
+// with cp.async (coalesced, two chunks in flight), so the weights cross L2 -> SM once per CTA evaluation instead of
+// once per warp, and the FMA loop reads them with conflict-free LDS instead of waiting on L2 latency.
+constexpr int SO3_CH = 16;                                   // rows per chunk
+constexpr int SO3_NCHUNK = 4 + 8 + 8 + 8 + 4;                // 32
+constexpr int SO3_RING_SLOTS = 3;
+constexpr int SO3_RING_FLOATS = SO3_RING_SLOTS * SO3_CH * SO3_W;
+constexpr int SO3_SMEM_BYTES = (MARCH_THREADS / 32) * SO3_SMEM_PER_WARP + SO3_RING_FLOATS * 4;
+
+struct So3Chunk { int row0, rows, in_k0, in_is_x, last_of_layer; };
+__device__ __forceinline__ So3Chunk so3_chunk(int c) {
+  // segment starts (chunks): S0 0..3, S1 4..11, S2 12..19, S3a 20..27, S3b 28..31; weight-row starts 0, 60, 188, 316, 444
+  So3Chunk k;
+  int seg, j;
+  if (c < 4) { seg = 0; j = c; } else if (c < 12) { seg = 1; j = c - 4; } else if (c < 20) { seg = 2; j = c - 12; }
+  else if (c < 28) { seg = 3; j = c - 20; } else { seg = 4; j = c - 28; }
+  const int seg_row0 = seg == 0 ? 0 : (seg == 1 ? 60 : (seg == 2 ? 188 : (seg == 3 ? 316 : 444)));
+  const int seg_rows = (seg == 0 || seg == 4) ? 60 : 128;
+  k.in_k0 = j * SO3_CH;
+  k.row0 = seg_row0 + k.in_k0;
+  k.rows = min(SO3_CH, seg_rows - k.in_k0);
+  k.in_is_x = (seg == 0 || seg == 4);
+  k.last_of_layer = (seg != 3) && (k.in_k0 + k.rows == seg_rows);     // S3a continues into S3b
+  return k;
 }
 
-// raw = so3_mlp(annealed_pos_enc(p)) for the warp's 32 rays; every lane participates, returns this lane's ray's raw[3]
-__device__ __forceinline__ void so3_eval(const So3Args& a, float* scratch, int lane, float px, float py, float pz,
-                                         float& r0, float& r1, float& r2) {
+// raw = so3_mlp(annealed_pos_enc(p)) for the CTA's 128 rays.  EVERY thread of the CTA must call this (block barriers
+// inside); warps without an active ray (`warp_on` false) only help copying the weights.
+__device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, int warp, int lane, bool warp_on, float px, float py,
+                                         float pz, float& r0, float& r1, float& r2) {
+  float* scratch = dyn_smem + warp * (SO3_SMEM_PER_WARP / 4);
   float* X = scratch;                          // [60][36]
   float* Hs = scratch + SO3_IN * SO3_PITCH;    // [128][36]
-  const float xs[3] = {px, py, pz};
-  const float half_pi = 1.57079632679489661923f;
-  float sc = 1.f;
+  float* ring = dyn_smem + (MARCH_THREADS / 32) * (SO3_SMEM_PER_WARP / 4);
+  const int tid = warp * 32 + lane;
+  auto issue = [&](int c) {
+    const So3Chunk k = so3_chunk(c);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (c % SO3_RING_SLOTS) * SO3_CH * SO3_W);
+    const float* src = a.w + (size_t)k.row0 * SO3_W;
 #pragma unroll
-  for (int k = 0; k < 10; ++k) {               // feature index k*6 + c (sin), k*6 + 3 + c (sin(x + pi/2)), times window[k]
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float xb = mul(xs[c], sc);
-      X[(k * 6 + c) * SO3_PITCH + lane] = mul(sinf(xb), a.window[k]);
-      X[(k * 6 + 3 + c) * SO3_PITCH + lane] = mul(sinf(add(xb, half_pi)), a.window[k]);
+    for (int i = 0; i < 4; ++i) {              // 512 16-byte units per chunk, 4 per thread
+      const int u = tid + i * MARCH_THREADS, r = u >> 5;
+      const int sz = r < k.rows ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + u * 16), "l"(src + (r < k.rows ? u * 4 : 0)), "r"(sz)
+                   : "memory");
     }
-    sc *= 2.f;
-  }
-  __syncwarp();
-  const float* bias = a.w + SO3_OFF_B;
-  float acc[4][32];
-  auto finish = [&](const float* b) {          // bias + ReLU, in-place hand-over through Hs
-    __syncwarp();                              // every lane has finished reading the layer input
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  issue(1);
+  if (warp_on) {
+    const float xs[3] = {px, py, pz};
+    const float half_pi = 1.57079632679489661923f;
+    float sc = 1.f;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const float bj = __ldg(b + lane + 32 * m);
-      float* row = Hs + (lane + 32 * m) * SO3_PITCH;
+    for (int k = 0; k < 10; ++k) {             // feature index k*6 + c (sin), k*6 + 3 + c (sin(x + pi/2)), times window[k]
 #pragma unroll
-      for (int r = 0; r < 32; ++r) row[r] = fmaxf(acc[m][r] + bj, 0.f);
+      for (int c = 0; c < 3; ++c) {
+        const float xb = mul(xs[c], sc);
+        X[(k * 6 + c) * SO3_PITCH + lane] = mul(sinf(xb), a.window[k]);
+        X[(k * 6 + 3 + c) * SO3_PITCH + lane] = mul(sinf(add(xb, half_pi)), a.window[k]);
+      }
+      sc *= 2.f;
     }
     __syncwarp();
-  };
-  auto clear = [&]() {
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-#pragma unroll
-      for (int r = 0; r < 32; ++r) acc[m][r] = 0.f;
-  };
-  clear(); so3_accumulate(acc, a.w, X, SO3_IN, lane); finish(bias);                                   // Dense_0
-  clear(); so3_accumulate(acc, a.w + SO3_OFF_W1, Hs, SO3_W, lane); finish(bias + SO3_W);              // Dense_1
-  clear(); so3_accumulate(acc, a.w + SO3_OFF_W2, Hs, SO3_W, lane); finish(bias + 2 * SO3_W);          // Dense_2, then concat(x, inputs)
-  clear(); so3_accumulate(acc, a.w + SO3_OFF_W3, Hs, SO3_W, lane);
-  so3_accumulate(acc, a.w + SO3_OFF_W3 + SO3_W * SO3_W, X, SO3_IN, lane); finish(bias + 3 * SO3_W);   // Dense_3 on [h, inputs]
-  const float* W4 = a.w + SO3_OFF_W4;
-  const float* b4 = bias + 4 * SO3_W;
-  r0 = __ldg(b4); r1 = __ldg(b4 + 1); r2 = __ldg(b4 + 2);
-#pragma unroll 4
-  for (int k = 0; k < SO3_W; ++k) {            // Dense_4: this lane's own ray
-    const float h = Hs[k * SO3_PITCH + lane];
-    r0 = fmaf(h, __ldg(W4 + 3 * k), r0); r1 = fmaf(h, __ldg(W4 + 3 * k + 1), r1); r2 = fmaf(h, __ldg(W4 + 3 * k + 2), r2);
   }
-  __syncwarp();
+  const float* bias = a.w + SO3_OFF_B;
+  float acc[4][32];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int r = 0; r < 32; ++r) acc[m][r] = 0.f;
+  int layer = 0;
+#pragma unroll 1
+  for (int c = 0; c < SO3_NCHUNK; ++c) {
+    if (c + 1 < SO3_NCHUNK) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                           // chunk c has landed for everyone; slot (c+2)%3 is no longer being read
+    if (c + 2 < SO3_NCHUNK) issue(c + 2);
+    const So3Chunk k = so3_chunk(c);
+    if (warp_on) {
+      const float* wbuf = ring + (c % SO3_RING_SLOTS) * SO3_CH * SO3_W + lane;
+      const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_PITCH;
+#pragma unroll 2
+      for (int r = 0; r < k.rows; ++r) {
+        const float w0 = wbuf[r * SO3_W], w1 = wbuf[r * SO3_W + 32], w2 = wbuf[r * SO3_W + 64], w3 = wbuf[r * SO3_W + 96];
+        const float4* xr = reinterpret_cast<const float4*>(in + r * SO3_PITCH);
+#pragma unroll
+        for (int r4 = 0; r4 < 8; ++r4) {
+          const float4 x = xr[r4];
+          acc[0][4 * r4] = fmaf(w0, x.x, acc[0][4 * r4]); acc[0][4 * r4 + 1] = fmaf(w0, x.y, acc[0][4 * r4 + 1]);
+          acc[0][4 * r4 + 2] = fmaf(w0, x.z, acc[0][4 * r4 + 2]); acc[0][4 * r4 + 3] = fmaf(w0, x.w, acc[0][4 * r4 + 3]);
+          acc[1][4 * r4] = fmaf(w1, x.x, acc[1][4 * r4]); acc[1][4 * r4 + 1] = fmaf(w1, x.y, acc[1][4 * r4 + 1]);
+          acc[1][4 * r4 + 2] = fmaf(w1, x.z, acc[1][4 * r4 + 2]); acc[1][4 * r4 + 3] = fmaf(w1, x.w, acc[1][4 * r4 + 3]);
+          acc[2][4 * r4] = fmaf(w2, x.x, acc[2][4 * r4]); acc[2][4 * r4 + 1] = fmaf(w2, x.y, acc[2][4 * r4 + 1]);
+          acc[2][4 * r4 + 2] = fmaf(w2, x.z, acc[2][4 * r4 + 2]); acc[2][4 * r4 + 3] = fmaf(w2, x.w, acc[2][4 * r4 + 3]);
+          acc[3][4 * r4] = fmaf(w3, x.x, acc[3][4 * r4]); acc[3][4 * r4 + 1] = fmaf(w3, x.y, acc[3][4 * r4 + 1]);
+          acc[3][4 * r4 + 2] = fmaf(w3, x.z, acc[3][4 * r4 + 2]); acc[3][4 * r4 + 3] = fmaf(w3, x.w, acc[3][4 * r4 + 3]);
+        }
+      }
+      if (k.last_of_layer) {                   // bias + ReLU, handed to the next layer in place through Hs
+        __syncwarp();                          // every lane has finished reading the layer input
+        const float* b = bias + layer * SO3_W;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float bj = __ldg(b + lane + 32 * m);
+          float* row = Hs + (lane + 32 * m) * SO3_PITCH;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) { row[r] = fmaxf(acc[m][r] + bj, 0.f); acc[m][r] = 0.f; }
+        }
+        __syncwarp();
+      }
+    }
+    if (k.last_of_layer) ++layer;
+  }
+  r0 = r1 = r2 = 0.f;
+  if (warp_on) {
+    const float* W4 = a.w + SO3_OFF_W4;
+    const float* b4 = bias + 4 * SO3_W;
+    r0 = __ldg(b4); r1 = __ldg(b4 + 1); r2 = __ldg(b4 + 2);
+#pragma unroll 4
+    for (int k = 0; k < SO3_W; ++k) {          // Dense_4: this lane's own ray
+      const float h = Hs[k * SO3_PITCH + lane];
+      r0 = fmaf(h, __ldg(W4 + 3 * k), r0); r1 = fmaf(h, __ldg(W4 + 3 * k + 1), r1); r2 = fmaf(h, __ldg(W4 + 3 * k + 2), r2);
+    }
+    __syncwarp();
+  }
 }
 
 // Rodrigues rotation of grad n by raw (rnerf/ior_utils.py:300-306); safe_l2_norm = sqrt(max(sum sq, 1e-6))
@@ -260,7 +316,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 1 : 8) march_kernel(const
   __shared__ float tstage[MARCH_THREADS / 32][T_FLUSH * 32];        // ray_dist of the last <= 16 steps, [step][lane]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp_ray0 = (blockIdx.x * (int64_t)MARCH_THREADS) + warp * 32;
-  if (warp_ray0 >= n_rays) return;
+  if (!SO3 && warp_ray0 >= n_rays) return;      // SO3: every warp stays for the block barriers of so3_eval
   const int64_t ray = warp_ray0 + lane;
   const bool live = ray < n_rays;
   const int64_t rr = live ? ray : (n_rays - 1);
@@ -302,10 +358,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 1 : 8) march_kernel(const
     ts[(trow + kk) * 32 + lane] = t;
     float gx = c.y, gy = c.z, gz = c.w;
     if (SO3) {
-      const bool act = sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;     // jnp.linalg.norm(idx_grad) > 1e-3
-      if (__any_sync(0xffffffffu, act)) {
+      const bool act = live && sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;     // jnp.linalg.norm(idx_grad) > 1e-3
+      if (__syncthreads_or(act)) {
         float r0, r1, r2;
-        so3_eval(so3, so3_scratch + warp * (SO3_SMEM_PER_WARP / 4), lane, px, py, pz, r0, r1, r2);
+        so3_eval(so3, so3_scratch, warp, lane, __any_sync(0xffffffffu, act), px, py, pz, r0, r1, r2);
         if (act) so3_rotate(r0, r1, r2, gx, gy, gz);
       }
     }
@@ -448,7 +504,7 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
   if (so3_w != nullptr) {
     so3.w = so3_w;
     for (int k = 0; k < 10; ++k) so3.window[k] = (float)so3_window[k];
-    dyn = (size_t)(MARCH_THREADS / 32) * SO3_SMEM_PER_WARP;
+    dyn = (size_t)SO3_SMEM_BYTES;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

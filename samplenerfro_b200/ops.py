@@ -462,3 +462,42 @@ def adam_step(theta: torch.Tensor, grad: torch.Tensor, mu: torch.Tensor, nu: tor
     assert theta.numel() >= n and mu.numel() == n and nu.numel() == n and hyper.numel() >= HYPER_FLOATS
     check(_lib.load().rnerf_adam_step(_p(theta), _p(grad), _p(mu), _p(nu), n, _p(hyper), _p(norm_sq), _stream()),
           "rnerf_adam_step")
+
+
+# ---------------------------------------------------------------- ray generation / image error
+def generate_rays(camtoworld, height: int, width: int, focal: Optional[float] = None, cam_mat=None,
+                  use_pixel_centers: bool = True, row0: int = 0, n_rows: Optional[int] = None, device="cuda",
+                  want_radii: bool = True):
+    """Dataset._generate_rays for one camera, on the device (rnerf/datasets.py:216-242 Blender when `focal` is given,
+    :486-518 OpenCV when `cam_mat` (3x3 intrinsics) is).  Returns (origins, directions, viewdirs, radii) with shapes
+    [n_rows, W, 3] / [n_rows, W, 1] for image rows [row0, row0 + n_rows)."""
+    import numpy as np
+    c2w = np.asarray(camtoworld, dtype=np.float64)[:3, :4]
+    pose = (C.c_double * 12)(*c2w.reshape(-1).tolist())
+    n_rows = height - row0 if n_rows is None else int(n_rows)
+    if (focal is None) == (cam_mat is None):
+        raise ValueError("give exactly one of focal (Blender camera) or cam_mat (OpenCV camera)")
+    if cam_mat is not None:
+        K = np.asarray(cam_mat, dtype=np.float64)
+        opencv, fx, fy, cx, cy = 1, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+    else:
+        opencv, fx, fy, cx, cy = 0, float(focal), float(focal), 0.0, 0.0
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.RnerfError("generate_rays: expected a CUDA device (there is no CPU implementation)")
+    o = torch.empty(n_rows, width, 3, device=dev); d = torch.empty(n_rows, width, 3, device=dev)
+    v = torch.empty(n_rows, width, 3, device=dev)
+    r = torch.empty(n_rows, width, 1, device=dev) if want_radii else None
+    with torch.cuda.device(dev):
+        check(_lib.load().rnerf_generate_rays(pose, int(height), int(width), opencv, fx, fy, cx, cy, int(use_pixel_centers),
+                                              int(row0), n_rows, _p(o), _p(d), _p(v), _p(r), _stream()), "rnerf_generate_rays")
+    return o, d, v, r
+
+
+def image_mse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """mean((a - b)^2) as a 0-d device tensor (compute_psnr's input, rnerf/utils.py:392-401)."""
+    a = _chk(a.reshape(-1), "a"); b = _chk(b.reshape(-1), "b")
+    assert a.numel() == b.numel()
+    out = torch.zeros(1, device=a.device, dtype=torch.float32)
+    check(_lib.load().rnerf_sq_err(_p(a), _p(b), a.numel(), _p(out), _stream()), "rnerf_sq_err")
+    return out[0] / a.numel()

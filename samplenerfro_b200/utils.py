@@ -196,3 +196,28 @@ def load_mesh_pkl(path: str):
         nmax = list(mesh_dict["max_point"])
     ndim = [mesh_dict["num_voxels"]] * 3
     return mesh_dict["data"], ndim, nmin, nmax
+
+
+def generate_rays(camtoworld, height: int, width: int, focal: Optional[float] = None, cam_mat=None,
+                  use_pixel_centers: bool = True, device="cuda") -> Rays:
+    """Rays of one camera built on the device: Dataset._generate_rays (rnerf/datasets.py:216-242 / :486-518) without
+    the host arrays and their host->device copy.  [H,W,.] fields like the reference's `rays` of one image."""
+    from . import ops
+    o, d, v, r = ops.generate_rays(camtoworld, height, width, focal=focal, cam_mat=cam_mat,
+                                   use_pixel_centers=use_pixel_centers, device=device)
+    return Rays(o, d, v, r)
+
+
+def render_view(render_fn: Callable, camtoworld, height: int, width: int, rng, focal: Optional[float] = None, cam_mat=None,
+                use_pixel_centers: bool = True, normalize_disp: bool = False, chunk: int = 8192, device="cuda"):
+    """render_image for a camera instead of a ray array: rays are generated on the device, chunk outputs are assembled
+    on the device -> (rgb[H,W,3], distance[H,W,1], acc[H,W,1]); only the pose crosses the host/device boundary."""
+    rays = generate_rays(camtoworld, height, width, focal=focal, cam_mat=cam_mat, use_pixel_centers=use_pixel_centers,
+                         device=device)
+    return render_image(render_fn, rays, rng, normalize_disp, chunk=chunk)
+
+
+def image_psnr(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """compute_psnr(mean((pred - target)^2)) with the reduction on the device (eval.py's per-image metric)."""
+    from . import ops
+    return compute_psnr(ops.image_mse(pred.contiguous(), target.contiguous()))

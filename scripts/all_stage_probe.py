@@ -5,7 +5,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from samplenerfro_b200 import models, ops, synthetic, utils  # noqa: E402
 
-ap = argparse.ArgumentParser(); ap.add_argument("--rays", type=int, default=65536); ap.add_argument("--grid", type=int, default=512)
+ap = argparse.ArgumentParser(); ap.add_argument("--rays", type=int, default=640000); ap.add_argument("--grid", type=int, default=512)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 G = a.grid
@@ -16,8 +16,8 @@ args = utils.Flags(config="ship_skydome", num_path_samples=12, white_bkgd=False,
 model, variables = models.construct_nerf(0, None, args, ndim, nmin, nmax, n)
 rays = synthetic.blender_rays(synthetic.camera_pose(0.7, 1.0, 4.03), 800, 800)
 flat = utils.namedtuple_map(lambda r: r.reshape(-1, r.shape[-1]), rays)
-idx = torch.linspace(0, 640000 - 1, a.rays).long()
-o = flat.origins[idx].to(dev).contiguous(); d = flat.viewdirs[idx].to(dev).contiguous()
+r0 = (640000 - a.rays) // 2          # a contiguous band of image rows: a warp / CTA holds adjacent pixels
+o = flat.origins[r0:r0 + a.rays].to(dev).contiguous(); d = flat.viewdirs[r0:r0 + a.rays].to(dev).contiguous()
 so3 = (model._so3_packed(variables), model.so3_window(1.0))
 
 
@@ -34,10 +34,18 @@ def timeit(fn, n=5):
 path = ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True)
 t_rad = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, out=path))
 t_all = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, out=path, so3=so3))
-full = ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=False)
-g = full.rec[..., 8:11].norm(dim=-1)
-act = (g > 1e-3).float()
-warp_act = act.reshape(-1, 32, 768).amax(dim=1)
-print(f"rays {a.rays}: radiance march {t_rad:.3f} ms, all-stage march {t_all:.3f} ms; steps with |grad n| > 1e-3: "
-      f"{100 * act.mean().item():.2f} % of ray-steps, {100 * warp_act.mean().item():.2f} % of warp-steps "
-      f"({act.sum().item() * 2 * 64896 / t_all / 1e9:.2f} TFLOP/s of useful so3 flops)")
+del path
+n_ray = n_warp = n_cta = 0.0
+for i in range(0, a.rays // 128 * 128, 65536):
+    j = min(i + 65536, a.rays // 128 * 128)
+    full = ops.march(model.table, ndim, nmin, nmax, o[i:j], d[i:j], 2.0, 6.0, 768, bricks=model.bricks, compact=False)
+    act = (full.rec[..., 8:11].norm(dim=-1) > 1e-3).float()
+    n_ray += act.sum().item()
+    n_warp += act.reshape(-1, 32, 768).amax(dim=1).sum().item()
+    n_cta += act.reshape(-1, 128, 768).amax(dim=1).sum().item()
+    del full, act
+tot = a.rays * 768
+print(f"rays {a.rays}: radiance march {t_rad:.3f} ms, all-stage march {t_all:.3f} ms; |grad n| > 1e-3 at {100 * n_ray / tot:.2f} % of "
+      f"ray-steps, {100 * n_warp * 32 / tot:.2f} % of warp-steps, {100 * n_cta * 128 / tot:.2f} % of CTA-steps = {n_cta:.0f} CTA "
+      f"evaluations -> {(t_all - t_rad) * 1e3 * 148 / max(n_cta, 1):.1f} us per evaluation per SM; "
+      f"{n_ray * 2 * 64896 / t_all / 1e9:.2f} TFLOP/s of useful so3 flops")
