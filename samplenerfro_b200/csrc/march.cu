@@ -139,16 +139,21 @@ __device__ __forceinline__ float4 march_lookup(const float4* __restrict__ table,
 // OneEikonalStep (rnerf/eikonal_utils.py:34-35) then uses where(|grad n| > 1e-3, pred, grad n).
 // so3_mlp = model_utils.MLP(net_width=128, net_depth=4, skip_layer=2, 3 outputs): 60 -> 128 -> 128 -> 128 (+60) -> 128 -> 3.
 //
-// The `where` makes the MLP irrelevant wherever |grad n| <= 1e-3 (everywhere but the blurred object boundary), so a CTA
-// only evaluates it at steps where one of its 128 rays needs it.  The evaluation is fp32 on the CUDA cores (the result
-// steers the ray, so no reduced-precision operands): per warp the activations of its 32 rays live in shared memory as
-// [feature][ray]; lane l owns output neurons l, l+32, l+64, l+96 of a hidden layer for all 32 rays (128 accumulators)
-// and reads the activations with broadcast LDS.128.
-constexpr int SO3_IN = 60, SO3_W = 128, SO3_PITCH = 36;     // pitch: 16-byte aligned rows, 4-way conflicts on the (rare) writes
+// The `where` makes the MLP irrelevant wherever |grad n| <= 1e-3 (everywhere but the blurred object boundary): a CTA
+// only evaluates it at steps where one of its 128 rays needs it, and only for those rays.  They are compacted (ballot +
+// per-warp counts) into columns of CTA-wide activation buffers [feature][ray] in shared memory, at most 64 per pass (two
+// groups of 32; more active rays -- rare -- take another pass), and processed by ALL four warps: thread t owns neurons
+// 2j, 2j+1 (j = t mod 64) for one half (t / 64) of every group's rays, i.e. 32 accumulators per group; the layer input is
+// read with broadcast LDS.128, the weights with LDS.64.  The 64-column buffers keep the CTA at 110 KB of shared memory
+// and ~170 registers, so two CTAs share an SM: one can march or evaluate while the other waits on a barrier or a load.
+// fp32 on the CUDA cores (the result steers the ray, so no reduced-precision operands).
+constexpr int SO3_IN = 60, SO3_W = 128;
+constexpr int SO3_COLS = 64;                                 // active rays per pass
+constexpr int SO3_RP = SO3_COLS + 4;                         // ray pitch of the activation buffers (16-byte aligned rows)
 constexpr int SO3_OFF_W1 = SO3_IN * SO3_W, SO3_OFF_W2 = SO3_OFF_W1 + SO3_W * SO3_W, SO3_OFF_W3 = SO3_OFF_W2 + SO3_W * SO3_W,
               SO3_OFF_W4 = SO3_OFF_W3 + (SO3_W + SO3_IN) * SO3_W, SO3_OFF_B = SO3_OFF_W4 + SO3_W * 3,
               SO3_FLOATS = SO3_OFF_B + 4 * SO3_W + 3;
-constexpr int SO3_SMEM_PER_WARP = (SO3_IN + SO3_W) * SO3_PITCH * 4;   // X[60][36] + H[128][36] fp32 = 27 072 B
+constexpr int SO3_ACT_FLOATS = (SO3_IN + SO3_W) * SO3_RP;    // X[60][68] + H[128][68]
 
 struct So3Args {
   const float* w;        // kernels W0..W4 ([in][out] row-major) then biases b0..b4, fp32, SO3_FLOATS
@@ -165,7 +170,7 @@ constexpr int SO3_CH = 16;                                   // rows per chunk
 constexpr int SO3_NCHUNK = 4 + 8 + 8 + 8 + 4;                // 32
 constexpr int SO3_RING_SLOTS = 3;
 constexpr int SO3_RING_FLOATS = SO3_RING_SLOTS * SO3_CH * SO3_W;
-constexpr int SO3_SMEM_BYTES = (MARCH_THREADS / 32) * SO3_SMEM_PER_WARP + SO3_RING_FLOATS * 4;
+constexpr int SO3_SMEM_BYTES = (SO3_ACT_FLOATS + SO3_RING_FLOATS) * 4 + 16;     // + per-warp active-ray counts
 
 struct So3Chunk { int row0, rows, in_k0, in_is_x, last_of_layer; };
 __device__ __forceinline__ So3Chunk so3_chunk(int c) {
@@ -184,14 +189,14 @@ __device__ __forceinline__ So3Chunk so3_chunk(int c) {
   return k;
 }
 
-// raw = so3_mlp(annealed_pos_enc(p)) for the CTA's 128 rays.  EVERY thread of the CTA must call this (block barriers
-// inside); warps without an active ray (`warp_on` false) only help copying the weights.
-__device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, int warp, int lane, bool warp_on, float px, float py,
+// raw = so3_mlp(annealed_pos_enc(p)) for the CTA's active rays.  EVERY thread of the CTA must call this (block barriers
+// inside); only threads with `act` get a result.
+__device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, int warp, int lane, bool act, float px, float py,
                                          float pz, float& r0, float& r1, float& r2) {
-  float* scratch = dyn_smem + warp * (SO3_SMEM_PER_WARP / 4);
-  float* X = scratch;                          // [60][36]
-  float* Hs = scratch + SO3_IN * SO3_PITCH;    // [128][36]
-  float* ring = dyn_smem + (MARCH_THREADS / 32) * (SO3_SMEM_PER_WARP / 4);
+  float* X = dyn_smem;                         // [60][132]
+  float* Hs = dyn_smem + SO3_IN * SO3_RP;      // [128][132]
+  float* ring = dyn_smem + SO3_ACT_FLOATS;
+  int* cnt = reinterpret_cast<int*>(ring + SO3_RING_FLOATS);
   const int tid = warp * 32 + lane;
   auto issue = [&](int c) {
     const So3Chunk k = so3_chunk(c);
@@ -208,82 +213,113 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, int 
   };
   issue(0);
   issue(1);
-  if (warp_on) {
-    const float xs[3] = {px, py, pz};
-    const float half_pi = 1.57079632679489661923f;
-    float sc = 1.f;
+  // ---- compaction: active ray -> column idx of the activation buffers
+  const unsigned bal = __ballot_sync(0xffffffffu, act);
+  if (lane == 0) cnt[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, n_act = 0;
 #pragma unroll
-    for (int k = 0; k < 10; ++k) {             // feature index k*6 + c (sin), k*6 + 3 + c (sin(x + pi/2)), times window[k]
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float xb = mul(xs[c], sc);
-        X[(k * 6 + c) * SO3_PITCH + lane] = mul(sinf(xb), a.window[k]);
-        X[(k * 6 + 3 + c) * SO3_PITCH + lane] = mul(sinf(add(xb, half_pi)), a.window[k]);
-      }
-      sc *= 2.f;
-    }
-    __syncwarp();
+  for (int w = 0; w < MARCH_THREADS / 32; ++w) {
+    const int c = cnt[w];
+    if (w < warp) base += c;
+    n_act += c;
   }
+  const int idx = base + __popc(bal & ((1u << lane) - 1u));
   const float* bias = a.w + SO3_OFF_B;
-  float acc[4][32];
-#pragma unroll
-  for (int m = 0; m < 4; ++m)
-#pragma unroll
-    for (int r = 0; r < 32; ++r) acc[m][r] = 0.f;
-  int layer = 0;
+  const int j = tid & 63, h = tid >> 6;        // neurons 2j, 2j+1; columns 16h .. 16h+15 of every group
+  r0 = r1 = r2 = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < SO3_NCHUNK; ++c) {
-    if (c + 1 < SO3_NCHUNK) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                           // chunk c has landed for everyone; slot (c+2)%3 is no longer being read
-    if (c + 2 < SO3_NCHUNK) issue(c + 2);
-    const So3Chunk k = so3_chunk(c);
-    if (warp_on) {
-      const float* wbuf = ring + (c % SO3_RING_SLOTS) * SO3_CH * SO3_W + lane;
-      const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_PITCH;
-#pragma unroll 2
-      for (int r = 0; r < k.rows; ++r) {
-        const float w0 = wbuf[r * SO3_W], w1 = wbuf[r * SO3_W + 32], w2 = wbuf[r * SO3_W + 64], w3 = wbuf[r * SO3_W + 96];
-        const float4* xr = reinterpret_cast<const float4*>(in + r * SO3_PITCH);
+  for (int col0 = 0; col0 < n_act; col0 += SO3_COLS) {
+    const int n_groups = (min(SO3_COLS, n_act - col0) + 31) >> 5;   // 1 or 2 groups of 32 columns (unused columns hold garbage)
+    const bool mine = act && idx >= col0 && idx < col0 + SO3_COLS;
+    const int col = idx - col0;
+    if (col0 > 0) {                            // another pass: everyone is done with the ring and Hs of the previous one
+      __syncthreads();
+      issue(0);
+      issue(1);
+    }
+    if (mine) {
+      const float xs[3] = {px, py, pz};
+      const float half_pi = 1.57079632679489661923f;
+      float sc = 1.f;
 #pragma unroll
-        for (int r4 = 0; r4 < 8; ++r4) {
-          const float4 x = xr[r4];
-          acc[0][4 * r4] = fmaf(w0, x.x, acc[0][4 * r4]); acc[0][4 * r4 + 1] = fmaf(w0, x.y, acc[0][4 * r4 + 1]);
-          acc[0][4 * r4 + 2] = fmaf(w0, x.z, acc[0][4 * r4 + 2]); acc[0][4 * r4 + 3] = fmaf(w0, x.w, acc[0][4 * r4 + 3]);
-          acc[1][4 * r4] = fmaf(w1, x.x, acc[1][4 * r4]); acc[1][4 * r4 + 1] = fmaf(w1, x.y, acc[1][4 * r4 + 1]);
-          acc[1][4 * r4 + 2] = fmaf(w1, x.z, acc[1][4 * r4 + 2]); acc[1][4 * r4 + 3] = fmaf(w1, x.w, acc[1][4 * r4 + 3]);
-          acc[2][4 * r4] = fmaf(w2, x.x, acc[2][4 * r4]); acc[2][4 * r4 + 1] = fmaf(w2, x.y, acc[2][4 * r4 + 1]);
-          acc[2][4 * r4 + 2] = fmaf(w2, x.z, acc[2][4 * r4 + 2]); acc[2][4 * r4 + 3] = fmaf(w2, x.w, acc[2][4 * r4 + 3]);
-          acc[3][4 * r4] = fmaf(w3, x.x, acc[3][4 * r4]); acc[3][4 * r4 + 1] = fmaf(w3, x.y, acc[3][4 * r4 + 1]);
-          acc[3][4 * r4 + 2] = fmaf(w3, x.z, acc[3][4 * r4 + 2]); acc[3][4 * r4 + 3] = fmaf(w3, x.w, acc[3][4 * r4 + 3]);
+      for (int k = 0; k < 10; ++k) {           // feature index k*6 + c (sin), k*6 + 3 + c (sin(x + pi/2)), times window[k]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float xb = mul(xs[c], sc);
+          X[(k * 6 + c) * SO3_RP + col] = mul(sinf(xb), a.window[k]);
+          X[(k * 6 + 3 + c) * SO3_RP + col] = mul(sinf(add(xb, half_pi)), a.window[k]);
+        }
+        sc *= 2.f;
+      }
+    }
+    float acc[2][2][16];
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int r = 0; r < 16; ++r) { acc[g][0][r] = 0.f; acc[g][1][r] = 0.f; }
+    int layer = 0;
+#pragma unroll 1
+    for (int c = 0; c < SO3_NCHUNK; ++c) {
+      if (c + 1 < SO3_NCHUNK) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                         // chunk c has landed for everyone; slot (c+2)%3 is no longer being read;
+                                               // activations written before this point (X, or Hs of the last layer) are visible
+      if (c + 2 < SO3_NCHUNK) issue(c + 2);
+      const So3Chunk k = so3_chunk(c);
+      const float* wbuf = ring + (c % SO3_RING_SLOTS) * SO3_CH * SO3_W + 2 * j;
+      const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_RP + 16 * h;
+#pragma unroll 4
+      for (int r = 0; r < k.rows; ++r) {
+        const float2 w = *reinterpret_cast<const float2*>(wbuf + r * SO3_W);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g < n_groups) {
+            const float4* xr = reinterpret_cast<const float4*>(in + r * SO3_RP + 32 * g);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 x = xr[q];
+              acc[g][0][4 * q] = fmaf(w.x, x.x, acc[g][0][4 * q]); acc[g][0][4 * q + 1] = fmaf(w.x, x.y, acc[g][0][4 * q + 1]);
+              acc[g][0][4 * q + 2] = fmaf(w.x, x.z, acc[g][0][4 * q + 2]); acc[g][0][4 * q + 3] = fmaf(w.x, x.w, acc[g][0][4 * q + 3]);
+              acc[g][1][4 * q] = fmaf(w.y, x.x, acc[g][1][4 * q]); acc[g][1][4 * q + 1] = fmaf(w.y, x.y, acc[g][1][4 * q + 1]);
+              acc[g][1][4 * q + 2] = fmaf(w.y, x.z, acc[g][1][4 * q + 2]); acc[g][1][4 * q + 3] = fmaf(w.y, x.w, acc[g][1][4 * q + 3]);
+            }
+          }
         }
       }
       if (k.last_of_layer) {                   // bias + ReLU, handed to the next layer in place through Hs
-        __syncwarp();                          // every lane has finished reading the layer input
-        const float* b = bias + layer * SO3_W;
+        __syncthreads();                       // every thread has finished reading the layer input
+        const float b0 = __ldg(bias + layer * SO3_W + 2 * j), b1 = __ldg(bias + layer * SO3_W + 2 * j + 1);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const float bj = __ldg(b + lane + 32 * m);
-          float* row = Hs + (lane + 32 * m) * SO3_PITCH;
+        for (int g = 0; g < 2; ++g) {
+          if (g < n_groups) {
+            float4* o0 = reinterpret_cast<float4*>(Hs + (2 * j) * SO3_RP + 32 * g + 16 * h);
+            float4* o1 = reinterpret_cast<float4*>(Hs + (2 * j + 1) * SO3_RP + 32 * g + 16 * h);
 #pragma unroll
-          for (int r = 0; r < 32; ++r) { row[r] = fmaxf(acc[m][r] + bj, 0.f); acc[m][r] = 0.f; }
+            for (int q = 0; q < 4; ++q) {
+              o0[q] = make_float4(fmaxf(acc[g][0][4 * q] + b0, 0.f), fmaxf(acc[g][0][4 * q + 1] + b0, 0.f),
+                                  fmaxf(acc[g][0][4 * q + 2] + b0, 0.f), fmaxf(acc[g][0][4 * q + 3] + b0, 0.f));
+              o1[q] = make_float4(fmaxf(acc[g][1][4 * q] + b1, 0.f), fmaxf(acc[g][1][4 * q + 1] + b1, 0.f),
+                                  fmaxf(acc[g][1][4 * q + 2] + b1, 0.f), fmaxf(acc[g][1][4 * q + 3] + b1, 0.f));
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 16; ++r) { acc[g][0][r] = 0.f; acc[g][1][r] = 0.f; }
         }
-        __syncwarp();
+        ++layer;
       }
     }
-    if (k.last_of_layer) ++layer;
-  }
-  r0 = r1 = r2 = 0.f;
-  if (warp_on) {
-    const float* W4 = a.w + SO3_OFF_W4;
-    const float* b4 = bias + 4 * SO3_W;
-    r0 = __ldg(b4); r1 = __ldg(b4 + 1); r2 = __ldg(b4 + 2);
+    __syncthreads();                           // Dense_3 output visible
+    if (mine) {
+      const float* W4 = a.w + SO3_OFF_W4;
+      const float* b4 = bias + 4 * SO3_W;
+      r0 = __ldg(b4); r1 = __ldg(b4 + 1); r2 = __ldg(b4 + 2);
 #pragma unroll 4
-    for (int k = 0; k < SO3_W; ++k) {          // Dense_4: this lane's own ray
-      const float h = Hs[k * SO3_PITCH + lane];
-      r0 = fmaf(h, __ldg(W4 + 3 * k), r0); r1 = fmaf(h, __ldg(W4 + 3 * k + 1), r1); r2 = fmaf(h, __ldg(W4 + 3 * k + 2), r2);
+      for (int k = 0; k < SO3_W; ++k) {        // Dense_4: this thread's own ray
+        const float hv = Hs[k * SO3_RP + col];
+        r0 = fmaf(hv, __ldg(W4 + 3 * k), r0); r1 = fmaf(hv, __ldg(W4 + 3 * k + 1), r1); r2 = fmaf(hv, __ldg(W4 + 3 * k + 2), r2);
+      }
     }
-    __syncwarp();
   }
 }
 
@@ -303,13 +339,13 @@ __device__ __forceinline__ void so3_rotate(float r0, float r1, float r2, float& 
 }
 
 template <int RECF4, bool FAST, bool SO3>
-__global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 1 : 8) march_kernel(const float4* __restrict__ table, const MarchGeom mg,
+__global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const float4* __restrict__ table, const MarchGeom mg,
                                                               const float* __restrict__ origins,
                                                               const float* __restrict__ viewdirs, int64_t n_rays,
                                                               float near, float step, int n_steps,
                                                               float4* __restrict__ path, float* __restrict__ t_col,
                                                               const float* __restrict__ bricks, int dbg, const So3Args so3) {
-  extern __shared__ __align__(16) float so3_scratch[];     // SO3 only: SO3_SMEM_PER_WARP bytes per warp
+  extern __shared__ __align__(16) float so3_scratch[];     // SO3 only: SO3_SMEM_BYTES
   constexpr int F4_PER_FLUSH = STEPS_PER_FLUSH * RECF4;   // float4 per ray per flush: 8 (compact) / 12 (full)
   constexpr int PITCH = F4_PER_FLUSH + 1;                  // +1 float4 pad: conflict-free column writes
   __shared__ float4 stage[MARCH_THREADS / 32][32 * PITCH];
@@ -361,7 +397,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 1 : 8) march_kernel(const
       const bool act = live && sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;     // jnp.linalg.norm(idx_grad) > 1e-3
       if (__syncthreads_or(act)) {
         float r0, r1, r2;
-        so3_eval(so3, so3_scratch, warp, lane, __any_sync(0xffffffffu, act), px, py, pz, r0, r1, r2);
+        so3_eval(so3, so3_scratch, warp, lane, act, px, py, pz, r0, r1, r2);
         if (act) so3_rotate(r0, r1, r2, gx, gy, gz);
       }
     }

@@ -155,3 +155,32 @@ def test_all_stage_model_matches_oracle(cuda_lib):
                                        jitter=jitter, u=u, debug=True)
     assert (pdbg["ray_pos"] - dbg["ray_pos"]).abs().max().item() > 1e-3      # the rotation changed the paths
     assert H.psnr(ret[1][0], oret[1][0]) >= 50.0
+
+
+def test_all_stage_march_many_active_rays_per_cta(cuda_lib):
+    """A bundle of nearly parallel rays crosses the object boundary at the same steps, so all 128 rays of a CTA need the
+    so3 MLP at once: exercises the multi-pass path of the compacted evaluation (64 columns per pass) and partial CTAs."""
+    from samplenerfro_b200 import models, ops
+    n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
+    gen = torch.Generator().manual_seed(5)
+    B = 300
+    o = torch.tensor([0.3, -3.9, 0.5]) + torch.randn(B, 3, generator=gen) * 0.01
+    d = -o + torch.randn(B, 3, generator=gen) * 0.02
+    d = d / d.norm(dim=-1, keepdim=True)
+    model, variables = models.construct_nerf(5, None, _flags(stage="all"), ndim, nmin, nmax, n)
+    so3 = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+    so3["Dense_4"]["kernel"].copy_((torch.randn(128, 3, generator=gen) * 0.05).cuda())
+    so3["Dense_4"]["bias"].copy_((torch.randn(3, generator=gen) * 0.2).cuda())
+    S = 768
+    path = ops.march(model.table, ndim, nmin, nmax, o.cuda().contiguous(), d.cuda().contiguous(), 2.0, 6.0, S, bricks=model.bricks,
+                     so3=(ops.so3_pack(so3), model.so3_window(0.8)))
+    pos, dirs, dist, nn, g = ops.path_views(path)
+    act = (g.norm(dim=-1) > 1e-3)
+    assert act[:128].sum(dim=0).max().item() > 64          # more active rays in one CTA-step than one pass holds
+    cpu = {k: {kk: vv.detach().cpu() for kk, vv in v.items()} for k, v in so3.items()}
+    opos, odir, odist, _, _ = O.march(O.build_table(n, ndim, nmin, nmax), ndim, nmin, nmax, o, d, 2.0, 6.0, S, stage="all",
+                                      so3_params=cpu, annealed_alpha=0.8)
+    scale = opos.abs().max().item()
+    assert (pos.cpu() - opos).abs().max().item() < 1e-4 * scale, (pos.cpu() - opos).abs().max().item()
+    assert (dirs.cpu() - odir).abs().max().item() < 1e-4
+    assert (dist.cpu() - odist).abs().max().item() < 1e-4 * odist.abs().max().item()
