@@ -206,6 +206,27 @@ def main():
 
     ops.encmlp_fwd = timed_encmlp
 
+    # the memory-bound stages, timed the same way (CUDA events around their launches inside the timed region) and
+    # reported against the measured HBM copy peak with the algorithmic bytes of SURVEY 8(d)
+    stage_ev = {"march": [], "composite": [], "resample": []}
+    orig_march, orig_comp, orig_resample = ops.march, ops.composite_fwd, ops.resample
+
+    def _timed(name, fn, nbytes):
+        def wrapper(*args, **kw):
+            if not record["on"]:
+                return fn(*args, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*args, **kw)
+            e1.record()
+            stage_ev[name].append((e0, e1, nbytes(args, kw)))
+            return out
+        return wrapper
+
+    ops.march = _timed("march", orig_march, lambda a_, k_: a_[4].shape[0] * (24 + 44 * a_[8]))                 # origins, n_steps
+    ops.composite_fwd = _timed("composite", orig_comp, lambda a_, k_: a_[1].shape[0] * (32 * a_[1].shape[1] + 36))   # t [B,Ns]
+    ops.resample = _timed("resample", orig_resample, lambda a_, k_: a_[1].shape[0] * ((63 + 62) * 4 + 192 * 80))     # t_c [B,Nc]
+
     def render_resident():
         """One frame with the rays already in HBM; outputs stay on the device."""
         outs = []
@@ -283,6 +304,14 @@ def main():
                 "share_of_step": mlp_ms / ms, "launches": len(mlp_ev),
                 "traffic": MLP_DRAM_BYTES_PER_SAMPLE * mlp_samples / max(1, len(mlp_ev)),
                 "traffic_unit": "bytes per launch (ncu dram bytes per sample x samples per launch)"}
+    hbm = float(peaks.get("hbm_gbs", 6500.0))
+    stage_roof = []
+    for name, evs in stage_ev.items():
+        t_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in evs)
+        nb = sum(b for _, _, b in evs)
+        if t_ms > 0:
+            stage_roof.append({"kernel": name, "bound": "hbm", "achieved": nb / (t_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                               "frac": nb / (t_ms * 1e-3) / 1e9 / hbm, "share_of_step": t_ms / ms, "launches": len(evs)})
     e2e_ms, _, _ = timed(render_e2e, a.steps, max(1, a.warmup - 1))
     h2d = sum(t.numel() * 4 for t in host)
     d2h = out_host.numel() * 4
@@ -297,7 +326,8 @@ def main():
                        "rays_per_step_per_gpu": n_total, "chunk": chunk,
                        "l2": f"inputs larger than L2: path {chunk * S * 36 / 2**20:.0f} MiB/chunk, table {G**3 * 16 / 2**20:.0f} MiB",
                        "parallelism": f"ray-sharded x{world}, no data-path collective"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "other_kernels": stage_roof}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         cpu_baseline(64)

@@ -447,6 +447,9 @@ static int encmlp_fwd_impl(const void* packed, const float* pos, const float* di
     return launch_encmlp_pair(a, (cudaStream_t)stream);
   const bool dbg = layer_out != nullptr || prof != nullptr;
   if (!dbg && n_samples >= 74 * 512 && use_pair_kernel()) return launch_encmlp_pair(a, (cudaStream_t)stream);
+  // training forward (activations + encodings saved): the pair kernel in TRAIN mode for large batches
+  if (layer_out != nullptr && enc_out != nullptr && prof == nullptr && n_samples >= 74 * 512 && use_pair_kernel())
+    return launch_encmlp_pair(a, (cudaStream_t)stream);
   if (n_samples <= 148 * 128) return dbg ? launch_encmlp<1, 8, true>(a, (cudaStream_t)stream) : launch_encmlp<1, 8, false>(a, (cudaStream_t)stream);
   return dbg ? launch_encmlp<2, 4, true>(a, (cudaStream_t)stream) : launch_encmlp<2, 4, false>(a, (cudaStream_t)stream);
 }

@@ -106,9 +106,10 @@ __device__ __forceinline__ void tile_bar_sync(int tile) { asm volatile("bar.sync
 
 // Epilogue of one layer for one row and one 128-column half (64 columns for the condition layer).
 //   KIND 0: ReLU, write A   1: + sigma partial   2: no activation, write A   3: ReLU, rgb partial only
-template <int KIND>
+template <int KIND, bool DUMP = false>
 __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ hw,
-                                              uint8_t* __restrict__ a_row, uint32_t r7s, int col0, EpiOut& o) {
+                                              uint8_t* __restrict__ a_row, uint32_t r7s, int col0, EpiOut& o,
+                                              __nv_bfloat16* __restrict__ dump_row = nullptr /* KIND 3 in training mode */) {
   constexpr int NCG = (KIND == 3) ? 2 : 4;
 #ifdef RNERF_PAIR_PIPELINED_LD
   // two TMEM loads in flight: group cg+1 is fetched while group cg is converted and stored
@@ -149,6 +150,13 @@ __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __res
         o.sigma = fmaf(bf16_hi(pk[2 * j4 + 1]), w4.w, o.sigma);
       }
     }
+    if (KIND == 3 && DUMP) {   // the condition layer leaves no shared-memory copy: its saved activations go out directly
+      if (dump_row != nullptr) {
+        uint4* dst = reinterpret_cast<uint4*>(dump_row + c0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
+    }
     if (KIND == 3) {  // rgb head (Dense_11): hw = w_rgb[3][128]
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
@@ -171,7 +179,12 @@ __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __res
   }
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) encmlp_pair_kernel(const EncMlpArgs args) {
+// TRAIN: additionally saves what the backward kernels need -- every layer's post-activation output (TMA tensor stores
+// of the swizzled shared-memory tiles, 2 k-blocks per warp and layer; the condition layer by direct stores) and the two
+// encodings -- into args.layer_out [10][M][256] / args.enc_out [2][M][64] (bf16).
+template <bool TRAIN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) encmlp_pair_kernel(const EncMlpArgs args,
+                                                                                                const __grid_constant__ CUtensorMap tm_layers) {
   using SL = PairSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -337,7 +350,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
       const int64_t lrow = live ? srow : (args.n_samples - 1);
       if (half == 0) {
         const float p0 = __ldg(args.pos + 3 * lrow), p1 = __ldg(args.pos + 3 * lrow + 1), p2 = __ldg(args.pos + 3 * lrow + 2);
-        write_encoding<10>(e_blk, row, p0, p1, p2);     // layer-0 A operand: pos_enc(pos, 0, 10)
+        write_encoding<10>(e_blk, row, p0, p1, p2,      // layer-0 A operand: pos_enc(pos, 0, 10)
+                           (TRAIN && live) ? reinterpret_cast<uint4*>(args.enc_out + (size_t)srow * 64) : nullptr);
       }
       signal_ready();
 
@@ -359,11 +373,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
           args.prof[200 + rank * 16 + ew] = (long long)gt;            // acc[t] of layer 2 observed by this warp
         }
+        if (TRAIN) {           // this warp's activation stores of the previous layer have finished reading the tile
+          if (lane == 0) bulk_wait_read();
+          __syncwarp();
+        }
         if (l == 9) {
+          if (TRAIN) tile_bar_sync(t);                    // ... and so have everybody else's: the scratch below overlaps their rows
           // rgb-head weights into the (now free) activation buffer
           for (int i = ttid; i < 384; i += 256) a_scratch[i] = __ldg(wrgb_g + i);
           tile_bar_sync(t);
-          pair_epilogue<3>(taddr_row + half * 64, bias_s, a_scratch, a_row, r7s, half * 64, eo);
+          pair_epilogue<3, TRAIN>(taddr_row + half * 64, bias_s, a_scratch, a_row, r7s, half * 64, eo,
+                                  (TRAIN && live) ? args.layer_out + ((size_t)9 * args.n_samples + srow) * 256 : nullptr);
           // combine the two column halves: half 1 parks its partial sums, half 0 adds and writes the row
           float4* part = reinterpret_cast<float4*>(a_scratch + 1024);
           if (half == 1) part[row] = make_float4(eo.r, eo.g, eo.b, eo.sigma);
@@ -382,7 +402,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
           if (l == 8 && half == 0) {
             // condition input for Dense_10: pos_enc(dir, 0, 4) replaces the position encoding
             const float d0 = __ldg(args.dir + 3 * lrow), d1 = __ldg(args.dir + 3 * lrow + 1), d2 = __ldg(args.dir + 3 * lrow + 2);
-            write_encoding<4>(e_blk, row, d0, d1, d2);
+            write_encoding<4>(e_blk, row, d0, d1, d2,
+                              (TRAIN && live) ? reinterpret_cast<uint4*>(args.enc_out + ((size_t)args.n_samples + srow) * 64) : nullptr);
           }
           if (prof) args.prof[80 + (l * 2 + t) * 4 + 2] = clock64();
           if (args.prof != nullptr && (blockIdx.x >> 1) == 0 && g == 1 && l == 2 && lane == 0) {
@@ -392,9 +413,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
             args.prof[160 + rank * 16 + ew] = (long long)gt;
           }
           signal_ready();
+          if (TRAIN && lane == 0) {
+            const int64_t wrow0 = group * 512 + t * 256 + (int64_t)rank * 128 + q * 32;     // first sample row of this warp
+            if (wrow0 < args.n_samples) {
+              const uint32_t src = sbase + SL::A_OFF + t * 4 * ABLK_BYTES + q * 4096;
+#pragma unroll
+              for (int kb = 0; kb < 2; ++kb)
+                tma_store_3d(&tm_layers, src + (half * 2 + kb) * ABLK_BYTES, (half * 2 + kb) * KB, (int)wrow0, l);
+              bulk_commit();
+            }
+          }
         }
       }
     }
+    if (TRAIN && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
@@ -408,7 +440,9 @@ int launch_encmlp_pair(const EncMlpArgs& a0, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(encmlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairSmem::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(encmlp_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairSmem::BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(encmlp_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairSmem::BYTES);
     if (e != cudaSuccess) { set_error("rnerf_encmlp_fwd: cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return (int)e; }
     attr_set[dev] = true;
   }
@@ -422,7 +456,16 @@ int launch_encmlp_pair(const EncMlpArgs& a0, cudaStream_t st) {
     const int l = atoi(lim);
     if (l > 0 && l < pairs) pairs = l;
   }
-  encmlp_pair_kernel<<<2 * pairs, PAIR_THREADS, PairSmem::BYTES, st>>>(a);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (a.layer_out != nullptr) {                        // training forward: activations + encodings are saved
+    if (a.enc_out == nullptr) { set_error("rnerf_encmlp_fwd(pair): layer_out given without enc_out"); return RNERF_E_NULL; }
+    int rc = make_rows_tmap(&tm, a.layer_out, a.n_samples, N_MMA_LAYERS);
+    if (rc) return rc;
+    encmlp_pair_kernel<true><<<2 * pairs, PAIR_THREADS, PairSmem::BYTES, st>>>(a, tm);
+  } else {
+    encmlp_pair_kernel<false><<<2 * pairs, PAIR_THREADS, PairSmem::BYTES, st>>>(a, tm);
+  }
   count_launch();
   return check_launch("rnerf_encmlp_fwd(pair)");
 }
