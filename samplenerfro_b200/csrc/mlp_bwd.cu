@@ -70,16 +70,17 @@ struct DgradArgs {
 // says whether column 8 i + p is active.
 __device__ __forceinline__ void load_row_masks(const __nv_bfloat16* __restrict__ Hl, int64_t wrow0, int64_t n_samples,
                                                int lane, uint32_t (&mask)[8]) {
+  constexpr int NB = 16;          // rows in flight: the loads are HBM-latency bound and must finish under one MMA phase
 #pragma unroll 1
-  for (int r0 = 0; r0 < 32; r0 += 4) {
-    uint4 v[4];
+  for (int r0 = 0; r0 < 32; r0 += NB) {
+    uint4 v[NB];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NB; ++k) {
       const int64_t row = min(wrow0 + r0 + k, n_samples - 1);
       v[k] = __ldg(reinterpret_cast<const uint4*>(Hl + (size_t)row * 256) + lane);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NB; ++k) {
       const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
@@ -275,23 +276,44 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
 __global__ void __launch_bounds__(256) mlp_head_grad_kernel(const __nv_bfloat16* __restrict__ H, const float4* __restrict__ d_raw,
                                                             int64_t n_samples, int rows_per_block,
                                                             float* __restrict__ out, float* __restrict__ out_sig) {
+  // 256 threads = 2 row streams x 128 column pairs: thread (s, p) reads columns 2p, 2p+1 of H7 (and of H9 when p < 64)
+  // as one 4-byte load per row, rows s, s+2, ... of the block's slab, four rows in flight.
   const size_t layer_stride = (size_t)n_samples * 256;
   const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t m1 = min(m0 + rows_per_block, n_samples);
-  const int j = threadIdx.x;            // column 0..255
-  float a_sig = 0.f, a_r = 0.f, a_g = 0.f, a_b = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f, s_s = 0.f;
-  for (int64_t m = m0; m < m1; ++m) {
-    const float4 d = __ldg(d_raw + m);
-    a_sig = fmaf(__bfloat162float(H[7 * layer_stride + m * 256 + j]), d.w, a_sig);
-    if (j < 128) {
-      const float h = __bfloat162float(H[9 * layer_stride + m * 256 + j]);
-      a_r = fmaf(h, d.x, a_r); a_g = fmaf(h, d.y, a_g); a_b = fmaf(h, d.z, a_b);
+  const int p = threadIdx.x & 127, s = threadIdx.x >> 7;
+  const uint32_t* H7 = reinterpret_cast<const uint32_t*>(H + 7 * layer_stride) + p;     // + m * 128 per row
+  const uint32_t* H9 = reinterpret_cast<const uint32_t*>(H + 9 * layer_stride) + p;
+  float sg0 = 0.f, sg1 = 0.f, r0 = 0.f, r1 = 0.f, g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
+  float s_r = 0.f, s_g = 0.f, s_b = 0.f, s_s = 0.f;
+  constexpr int U = 4;
+  for (int64_t m = m0 + s; m < m1; m += 2 * U) {
+    uint32_t h7[U], h9[U];
+    float4 d[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t mm = m + 2 * u;
+      const bool ok = mm < m1;
+      const int64_t mc = ok ? mm : m;
+      h7[u] = __ldg(H7 + (size_t)mc * 128);
+      h9[u] = p < 64 ? __ldg(H9 + (size_t)mc * 128) : 0u;
+      d[u] = ok ? __ldg(d_raw + mc) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (j == 0) { s_r += d.x; s_g += d.y; s_b += d.z; s_s += d.w; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      sg0 = fmaf(bf16_lo(h7[u]), d[u].w, sg0); sg1 = fmaf(bf16_hi(h7[u]), d[u].w, sg1);
+      const float a = bf16_lo(h9[u]), c = bf16_hi(h9[u]);
+      r0 = fmaf(a, d[u].x, r0); g0 = fmaf(a, d[u].y, g0); b0 = fmaf(a, d[u].z, b0);
+      r1 = fmaf(c, d[u].x, r1); g1 = fmaf(c, d[u].y, g1); b1 = fmaf(c, d[u].z, b1);
+      if (p == 0) { s_r += d[u].x; s_g += d[u].y; s_b += d[u].z; s_s += d[u].w; }
+    }
   }
-  if (j < 128) { atomicAdd(out + j * 3, a_r); atomicAdd(out + j * 3 + 1, a_g); atomicAdd(out + j * 3 + 2, a_b); }
-  atomicAdd(out_sig + j, a_sig);
-  if (j == 0) { atomicAdd(out + 384, s_r); atomicAdd(out + 385, s_g); atomicAdd(out + 386, s_b); atomicAdd(out_sig + 256, s_s); }
+  atomicAdd(out_sig + 2 * p, sg0); atomicAdd(out_sig + 2 * p + 1, sg1);
+  if (p < 64) {
+    atomicAdd(out + (2 * p) * 3, r0); atomicAdd(out + (2 * p) * 3 + 1, g0); atomicAdd(out + (2 * p) * 3 + 2, b0);
+    atomicAdd(out + (2 * p + 1) * 3, r1); atomicAdd(out + (2 * p + 1) * 3 + 1, g1); atomicAdd(out + (2 * p + 1) * 3 + 2, b1);
+  }
+  if (p == 0) { atomicAdd(out + 384, s_r); atomicAdd(out + 385, s_g); atomicAdd(out + 386, s_b); atomicAdd(out_sig + 256, s_s); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -573,7 +595,7 @@ extern "C" int rnerf_mlp_head_grad(const uint16_t* saved_h, const float* d_raw, 
                                    float* out_sigma_head, void* stream) {
   if (n_samples <= 0) return 0;
   RNERF_REQUIRE_PTR(saved_h); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(out_rgb_head); RNERF_REQUIRE_PTR(out_sigma_head);
-  const int rows_per_block = 256;
+  const int rows_per_block = 512;
   const unsigned grid = (unsigned)((n_samples + rows_per_block - 1) / rows_per_block);
   mlp_head_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)saved_h, (const float4*)d_raw, n_samples,
                                                                 rows_per_block, out_rgb_head, out_sigma_head);
