@@ -71,7 +71,8 @@ def test_full_size_march_sortedness_and_oracle_on_a_subset(ship):
     assert dt.max().item() <= step * 1.5 * 1.02 and dt.min().item() >= step / 1.5 * 0.98
     assert torch.equal(path.rec[..., 3], t)                                           # dense t column == record field
     n_rec = path.rec[..., 7]
-    assert n_rec.min().item() >= 1.0 - 1e-6 and n_rec.max().item() <= 1.5 + 1e-6
+    # the 729-tap fp32 blur of a constant region is the constant times the rounded kernel sum (1 - 2.7e-6 here)
+    assert n_rec.min().item() >= 1.0 - 2e-5 and n_rec.max().item() <= 1.5 + 2e-5
     # oracle on 24 rays that cross the object, with the device-built 512^3 table (its construction is parity-tested at
     # small sizes): bit-exact rows
     bent = ((path.rec[:, -1, 4:7] - flat.viewdirs).norm(dim=-1) > 1e-2).nonzero()[:, 0]
