@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 4
+#define RNERF_ABI_VERSION 5
 #define RNERF_PATH_STRIDE 12         /* full records */
 #define RNERF_PATH_STRIDE_COMPACT 8
 
@@ -190,6 +190,33 @@ int rnerf_generate_rays(const double camtoworld_host[12], int height, int width,
                         float* directions, float* viewdirs, float* radii, void* stream);
 /* out_accum[0] += sum (a - b)^2: the image mse behind compute_psnr (rnerf/utils.py:392-401) */
 int rnerf_sq_err(const float* a, const float* b, int64_t n, float* out_accum, void* stream);
+
+/* ---- training of the "all" stage -- what train.py:164 (jax.value_and_grad) differentiates when
+ * path_sampler is trainable (train.py:302-310).  The loss reaches the scan only through the coarse samples
+ * ray_pos[:, jitter] / ray_dir[:, jitter] (rnerf/models.py:243-244; ray_dist and the fine samples are stop_gradient,
+ * rnerf/eikonal_utils.py:120, rnerf/model_utils.py:406-411).
+ * rnerf_mlp_input_grad: gradient of pos_enc + NerfMLP wrt its inputs, d_pos[M][3] / d_dirs[M][3], from the dz_out of
+ *   rnerf_mlp_dgrad; wt from rnerf_mlp_input_grad_pack(Dense_0, Dense_5, Dense_10 kernels), rebuilt when they change.
+ * rnerf_bkgd_mlp_bwd_dirs: rnerf_bkgd_mlp_bwd that also writes d_dirs[B][3], the gradient wrt the encoded direction
+ *   (ray_dir_c[:, -1], rnerf/models.py:303).
+ * rnerf_march_all_bwd: reverse sweep of the scan (rnerf/eikonal_utils.py:30-49,75-82).  path/rec_floats: the records
+ *   written by rnerf_march_all_fwd for the same inputs; jitter[Nc]: strictly increasing march-step indices;
+ *   d_pos_c/d_dir_c: [B][Nc][3] loss gradients; so3_wt: rnerf_so3_transpose(so3_w).  g_so3 (layout of so3_w) is
+ *   ACCUMULATED into; d_origins/d_viewdirs [B][3] (gradients wrt the ray, not used by train.py) may be NULL. */
+size_t rnerf_mlp_input_grad_packed_floats(void);
+int rnerf_mlp_input_grad_pack(const float* dense0_kernel, const float* dense5_kernel, const float* dense10_kernel,
+                              float* wt, void* stream);
+int rnerf_mlp_input_grad(const uint16_t* dz, int64_t n_samples, const float* wt, const float* pos, const float* dirs,
+                         float* d_pos, float* d_dirs, void* stream);
+int rnerf_bkgd_mlp_bwd_dirs(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
+                            const float* d_raw, float* gw, float* d_dirs, void* stream);
+size_t rnerf_so3_transposed_floats(void);
+int rnerf_so3_transpose(const float* so3_w, float* so3_wt, void* stream);
+int rnerf_march_all_bwd(const float* table, const float* bricks, const int ndim_host[3], const double nmin_host[3],
+                        const double nmax_host[3], const float* path, int rec_floats, int64_t n_rays, double near,
+                        double far, int n_steps, const int32_t* jitter, int n_coarse, const float* d_pos_c,
+                        const float* d_dir_c, const float* so3_w, const float* so3_wt, const double so3_window_host[10],
+                        float* g_so3, float* d_origins, float* d_viewdirs, void* stream);
 
 /* ---- a15: rnerf/models.py:498-503 bd_cut_dist mask: reverse-cumsum(inside bbox) > 0 ---- */
 int rnerf_bbox_tail_mask(const float* pos, int64_t n_rays, int n_samples, const double lo_host[3],

@@ -60,6 +60,15 @@ SIGNATURES = {
     "rnerf_bkgd_weight_floats": (C.c_size_t, []),
     "rnerf_bkgd_mlp_fwd": (C.c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, C.c_void_p]),
     "rnerf_bkgd_mlp_bwd": (C.c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_bkgd_mlp_bwd_dirs": (C.c_int, [c_f32p, c_f32p, c_i64, c_i64, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_mlp_input_grad_packed_floats": (C.c_size_t, []),
+    "rnerf_mlp_input_grad_pack": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_mlp_input_grad": (C.c_int, [C.c_void_p, c_i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_so3_transposed_floats": (C.c_size_t, []),
+    "rnerf_so3_transpose": (C.c_int, [c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_march_all_bwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
+                                      C.c_int, c_i64, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, c_f32p, c_f32p,
+                                      c_f32p, c_f32p, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_composite_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,
                                       C.c_double, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_composite_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,
@@ -89,8 +98,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rnerf_abi_version() != 4:
-        raise RnerfError(f"ABI version mismatch: library reports {lib.rnerf_abi_version()}, binding expects 4")
+    if lib.rnerf_abi_version() != 5:
+        raise RnerfError(f"ABI version mismatch: library reports {lib.rnerf_abi_version()}, binding expects 5")
     _lib = lib
     return lib
 

@@ -40,11 +40,13 @@ class _RadianceMLP(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_raw):
         packed, pos, dirs, layers, enc, *params = ctx.saved_tensors
+        want_in = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]      # "all" stage: the samples depend on so3_mlp
         grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc), d_raw.contiguous().view(-1, 4), params,
-                               grad_out=ctx.sink)
+                               grad_out=ctx.sink, input_grads=want_in)
+        d_pos, d_dirs = grads.pop() if want_in else (None, None)
         if ctx.sink is not None:        # already accumulated into the arena's .grad views
-            return (None,) * (4 + len(params))
-        return (None, None, None, None, *grads)
+            return (None, None, d_pos, d_dirs) + (None,) * len(params)
+        return (None, None, d_pos, d_dirs, *grads)
 
 
 def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
@@ -70,10 +72,16 @@ class _BkgdMLP(torch.autograd.Function):
     def backward(ctx, d_raw):
         w, dirs, *params = ctx.saved_tensors
         n_rays, stride, offset = ctx.geom
-        grads = ops.bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw.contiguous(), params, gw_out=ctx.sink)
+        want_in = ctx.needs_input_grad[2]                                # "all" stage: ray_dir_c[:, -1] depends on so3_mlp
+        grads = ops.bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw.contiguous(), params, gw_out=ctx.sink,
+                                 want_d_dirs=want_in)
+        d_dirs = None
+        if want_in:
+            d_dirs = torch.zeros_like(dirs)
+            d_dirs.view(n_rays, -1)[:, offset:offset + 3] = grads.pop()
         if ctx.sink is not None:
-            return (None,) * (6 + len(params))
-        return (None, None, None, None, None, None, *grads)
+            return (None, None, d_dirs) + (None,) * (3 + len(params))
+        return (None, None, d_dirs, None, None, None, *grads)
 
 
 def bkgd_raw(model, variables: Dict, dir_c: torch.Tensor, n_rays: int, n_coarse: int) -> torch.Tensor:
@@ -98,6 +106,43 @@ def bkgd_color(model, variables: Dict, viewdirs: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():
             raw = ops.bkgd_mlp_fwd(w, viewdirs, n, 3, 0)
     return torch.sigmoid(raw) * (1 + 2 * model.rgb_padding) - model.rgb_padding
+
+
+# ----------------------------------------------------------------------------- "all"-stage march (a4-a7, trainable so3_mlp)
+class _MarchAll(torch.autograd.Function):
+    """PathSampler + coarse selection with so3_mlp in the loop.  Differentiable outputs: pos_c, dir_c (the only way a
+    loss reaches the scan: ray_dist is stop_gradient, rnerf/eikonal_utils.py:120, and so are the fine samples,
+    rnerf/model_utils.py:406-411).  Backward = the reverse sweep kernel (rnerf_march_all_bwd)."""
+
+    @staticmethod
+    def forward(ctx, model, sink, w, window, origins, viewdirs, jitter, compact, *params):
+        path = ops.march(model.table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
+                         model.num_march_steps, bricks=model.bricks, compact=compact, so3=(w, window))
+        pos_c, dir_c, t_c, _ = ops.select(path, jitter)
+        ctx.model, ctx.sink, ctx.window = model, sink, window
+        ctx.save_for_backward(w, path.rec, jitter)
+        ctx.mark_non_differentiable(t_c, path.rec, path.t)
+        return pos_c, dir_c, t_c, path.rec, path.t
+
+    @staticmethod
+    def backward(ctx, d_pos_c, d_dir_c, _dt, _drec, _dtcol):
+        w, rec, jitter = ctx.saved_tensors
+        m = ctx.model
+        z = lambda g: torch.zeros(rec.shape[0], jitter.numel(), 3, device=rec.device) if g is None else g
+        g, _, _ = ops.march_all_bwd(m.table, m.ndim, m.nmin, m.nmax, rec, m.near, m.far, jitter, z(d_pos_c), z(d_dir_c),
+                                    (w, ctx.window), bricks=m.bricks, g_so3=ctx.sink)
+        if ctx.sink is not None:
+            return (None,) * 18
+        return (None,) * 8 + tuple(ops.so3_unpack_views(g))
+
+
+def march_all(model, variables: Dict, origins, viewdirs, jitter, annealed_alpha: float, compact: bool):
+    """-> (BentPath, pos_c, dir_c, t_c) with autograd edges from pos_c / dir_c to so3_mlp."""
+    p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+    w = model._so3_packed(variables)
+    pos_c, dir_c, t_c, rec, t_col = _MarchAll.apply(model, _sink(model, "so3_mlp"), w, model.so3_window(annealed_alpha),
+                                                    origins, viewdirs, jitter, compact, *_mlp_param_list(p, 5))
+    return ops.BentPath(rec, t_col), pos_c, dir_c, t_c
 
 
 # ----------------------------------------------------------------------------- compositing (a11 + a12)

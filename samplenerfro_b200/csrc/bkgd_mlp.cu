@@ -147,7 +147,7 @@ __device__ __forceinline__ void wgrad_rows(const float (&dz)[BK_R], const float*
 
 __global__ void __launch_bounds__(BK_W) bkgd_mlp_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dirs,
                                                             int64_t n_rays, int64_t dir_stride, const float* __restrict__ d_raw,
-                                                            float* __restrict__ gw) {
+                                                            float* __restrict__ gw, float* __restrict__ d_dirs) {
   extern __shared__ __align__(16) float sm[];
   float* E = sm;                               // [27][36]
   float* Hs = E + BK_IN * BK_PITCH;            // [4][128][36]  post-activation outputs of Dense_0..3
@@ -219,6 +219,10 @@ __global__ void __launch_bounds__(BK_W) bkgd_mlp_bwd_kernel(const float* __restr
       atomicAdd(gw + BK_B4 + j, sb);
     }
   }
+  // gradient wrt the encoded direction (threads j < 27, "all" stage only): dE = K_3[128:]^T-part dz_3 + K_0 dz_0
+  float accE[BK_R];
+#pragma unroll
+  for (int r = 0; r < BK_R; ++r) accE[r] = 0.f;
   // ---- hidden layers 3 -> 0: acc[] holds dz_l[j][:]
   for (int l = 3; l >= 0; --l) {
     float sb = 0.f;
@@ -229,6 +233,33 @@ __global__ void __launch_bounds__(BK_W) bkgd_mlp_bwd_kernel(const float* __restr
     float* gKl = gw + (l == 3 ? BK_K3 : (l == 2 ? BK_K2 : (l == 1 ? BK_K1 : BK_K0)));
     if (l == 0) {
       wgrad_rows(acc, E, BK_IN, j, BK_W, gKl);                                   // X_0 = encoding
+      if (d_dirs == nullptr) break;
+      float4* drow0 = reinterpret_cast<float4*>(D + j * BK_PITCH);
+#pragma unroll
+      for (int r4 = 0; r4 < BK_R / 4; ++r4) drow0[r4] = make_float4(acc[4 * r4], acc[4 * r4 + 1], acc[4 * r4 + 2], acc[4 * r4 + 3]);
+      __syncthreads();
+      if (j < BK_IN) {
+        dense_accum_t(accE, Kl, BK_W, BK_W, j, D);
+        float* erow = Hs + j * BK_PITCH;                                         // h0 is no longer needed
+#pragma unroll
+        for (int r = 0; r < BK_R; ++r) erow[r] = accE[r];
+      }
+      __syncthreads();
+      // chain rule through pos_enc(dir, 0, 4): d dir_c = dE[c] + sum_k 2^k (cos(2^k d_c) dE[3+3k+c] + cos(2^k d_c + pi/2) dE[15+3k+c])
+      if (j < BK_R * 3) {
+        const int r = j / 3, c = j % 3;
+        if (ray0 + r < n_rays) {
+          const float x = __ldg(dirs + (ray0 + r) * dir_stride + c);
+          float g = Hs[c * BK_PITCH + r], sc = 1.f;
+          for (int k = 0; k < 4; ++k) {
+            const float xb = mul(x, sc);
+            g += sc * (cosf(xb) * Hs[(3 + 3 * k + c) * BK_PITCH + r] +
+                       cosf(add(xb, 1.57079632679489661923f)) * Hs[(15 + 3 * k + c) * BK_PITCH + r]);
+            sc *= 2.f;
+          }
+          d_dirs[(ray0 + r) * 3 + c] = g;
+        }
+      }
       break;
     }
     wgrad_rows(acc, Hs + (l - 1) * BK_W * BK_PITCH, BK_W, j, BK_W, gKl);         // X_l = h_{l-1} ...
@@ -238,6 +269,7 @@ __global__ void __launch_bounds__(BK_W) bkgd_mlp_bwd_kernel(const float* __restr
 #pragma unroll
     for (int r4 = 0; r4 < BK_R / 4; ++r4) drow[r4] = make_float4(acc[4 * r4], acc[4 * r4 + 1], acc[4 * r4 + 2], acc[4 * r4 + 3]);
     __syncthreads();
+    if (l == 3 && d_dirs != nullptr && j < BK_IN) dense_accum_t(accE, Kl + BK_W * BK_W, BK_W, BK_W, j, D);   // skip-concat rows
 #pragma unroll
     for (int r = 0; r < BK_R; ++r) acc[r] = 0.f;
     dense_accum_t(acc, Kl, BK_W, BK_W, j, D);
@@ -265,8 +297,8 @@ extern "C" int rnerf_bkgd_mlp_fwd(const float* w, const float* dirs, int64_t n_r
   return check_launch("rnerf_bkgd_mlp_fwd");
 }
 
-extern "C" int rnerf_bkgd_mlp_bwd(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
-                                  const float* d_raw, float* gw, void* stream) {
+static int bkgd_bwd_impl(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats, const float* d_raw,
+                         float* gw, float* d_dirs, void* stream) {
   RNERF_REQUIRE(n_rays >= 0 && dir_stride_floats >= 3, RNERF_E_SHAPE, "rnerf_bkgd_mlp_bwd: bad sizes");
   if (n_rays == 0) return 0;
   RNERF_REQUIRE_PTR(w); RNERF_REQUIRE_PTR(dirs); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(gw);
@@ -280,7 +312,18 @@ extern "C" int rnerf_bkgd_mlp_bwd(const float* w, const float* dirs, int64_t n_r
     attr_set[dev] = true;
   }
   bkgd_mlp_bwd_kernel<<<(unsigned)((n_rays + BK_R - 1) / BK_R), BK_W, smem, (cudaStream_t)stream>>>(w, dirs, n_rays,
-                                                                                                   dir_stride_floats, d_raw, gw);
+                                                                                                   dir_stride_floats, d_raw, gw, d_dirs);
   count_launch();
   return check_launch("rnerf_bkgd_mlp_bwd");
+}
+
+extern "C" int rnerf_bkgd_mlp_bwd(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
+                                  const float* d_raw, float* gw, void* stream) {
+  return bkgd_bwd_impl(w, dirs, n_rays, dir_stride_floats, d_raw, gw, nullptr, stream);
+}
+
+extern "C" int rnerf_bkgd_mlp_bwd_dirs(const float* w, const float* dirs, int64_t n_rays, int64_t dir_stride_floats,
+                                       const float* d_raw, float* gw, float* d_dirs, void* stream) {
+  RNERF_REQUIRE_PTR(d_dirs);
+  return bkgd_bwd_impl(w, dirs, n_rays, dir_stride_floats, d_raw, gw, d_dirs, stream);
 }

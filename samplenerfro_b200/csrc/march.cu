@@ -18,6 +18,7 @@
 #include <map>
 #include <mutex>
 #include "common.cuh"
+#include "march_common.cuh"
 
 namespace rnerf {
 
@@ -25,27 +26,8 @@ namespace rnerf {
 // the gathers of a warp land in few cache lines and the brick map / grid stay L1/L2 resident).  Records are
 // staged through shared memory so that the global stores of a warp are sector-complete and contiguous:
 // STEPS_PER_FLUSH steps x 32 (48) B = 128 (192) B contiguous per ray, all 32 lanes active in every store.
-constexpr int MARCH_THREADS = 128;
 constexpr int STEPS_PER_FLUSH = 4;
 constexpr int T_FLUSH = 16;              // the dense t column is flushed every 16 steps: 64 B (2 full sectors) per ray
-
-struct MarchGeom {
-  GridGeom g;
-  float rdelta[3];   // reciprocal of ndelta, exhaustively verified for the 3-instruction exact division (else unused)
-  int nby, nbz;      // brick grid (y, z extents)
-};
-
-// ---- exact division by a constant ------------------------------------------------------------------------------
-// q = a*y; r = fma(-q, d, a); q' = fma(r, y, q) with y ~ 1/d equals the correctly rounded a/d for MOST (d, a) but not
-// provably all, so a divisor is only used this way after the sequence has been compared with __fdiv_rn for every one
-// of the 2^23 significands of a (verify_recip_kernel).  With no under/overflow in q, r, q' -- guaranteed by the
-// exponent guards in fast_coords() and recip_for() -- the sequence commutes with scaling a by powers of two, so one
-// binade of a covers all of them.
-__device__ __forceinline__ float div_by_const(float a, float d, float y) {
-  const float q = __fmul_rn(a, y);
-  const float r = __fmaf_rn(-q, d, a);
-  return __fmaf_rn(r, y, q);
-}
 
 __global__ void __launch_bounds__(256) verify_recip_kernel(float d, float y, int* __restrict__ bad) {
   const uint32_t m = blockIdx.x * 256u + threadIdx.x;          // 2^23 significands
@@ -54,7 +36,7 @@ __global__ void __launch_bounds__(256) verify_recip_kernel(float d, float y, int
 }
 
 // returns the verified reciprocal of d, or 0 if the fast sequence must not be used for this divisor
-static float recip_for(float d, cudaStream_t st) {
+float recip_for(float d, cudaStream_t st) {
   static std::mutex mu;
   static std::map<uint32_t, float> cache;
   uint32_t key;
@@ -80,20 +62,6 @@ static float recip_for(float d, cudaStream_t st) {
   }
   cache[key] = y;
   return y;
-}
-
-// grid coordinates x = (p - nmin) / ndelta of VoxMLP._linear3 (rnerf/ior_utils.py:201-203)
-template <bool FAST>
-__device__ __forceinline__ void grid_coords(const MarchGeom& mg, float px, float py, float pz, float& x, float& y, float& z) {
-  const float ax = sub(px, mg.g.nmin[0]), ay = sub(py, mg.g.nmin[1]), az = sub(pz, mg.g.nmin[2]);
-  if (FAST) {
-    x = div_by_const(ax, mg.g.ndelta[0], mg.rdelta[0]);
-    y = div_by_const(ay, mg.g.ndelta[1], mg.rdelta[1]);
-    z = div_by_const(az, mg.g.ndelta[2], mg.rdelta[2]);
-    const float lo = fminf(fminf(fabsf(ax), fabsf(ay)), fabsf(az)), hi = fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fabsf(az));
-    if (lo >= 0x1p-60f && hi <= 0x1p60f) return;     // false for zeros, subnormals, huge values and NaN
-  }
-  x = divf(ax, mg.g.ndelta[0]); y = divf(ay, mg.g.ndelta[1]); z = divf(az, mg.g.ndelta[2]);
 }
 
 // VoxMLP._linear3 at p (same arithmetic as trilinear() in common.cuh; index clamps done in float, which gives the same
@@ -147,18 +115,9 @@ __device__ __forceinline__ float4 march_lookup(const float4* __restrict__ table,
 // read with broadcast LDS.128, the weights with LDS.64.  The 64-column buffers keep the CTA at 110 KB of shared memory
 // and ~170 registers, so two CTAs share an SM: one can march or evaluate while the other waits on a barrier or a load.
 // fp32 on the CUDA cores (the result steers the ray, so no reduced-precision operands).
-constexpr int SO3_IN = 60, SO3_W = 128;
 constexpr int SO3_COLS = 64;                                 // active rays per pass
 constexpr int SO3_RP = SO3_COLS + 4;                         // ray pitch of the activation buffers (16-byte aligned rows)
-constexpr int SO3_OFF_W1 = SO3_IN * SO3_W, SO3_OFF_W2 = SO3_OFF_W1 + SO3_W * SO3_W, SO3_OFF_W3 = SO3_OFF_W2 + SO3_W * SO3_W,
-              SO3_OFF_W4 = SO3_OFF_W3 + (SO3_W + SO3_IN) * SO3_W, SO3_OFF_B = SO3_OFF_W4 + SO3_W * 3,
-              SO3_FLOATS = SO3_OFF_B + 4 * SO3_W + 3;
 constexpr int SO3_ACT_FLOATS = (SO3_IN + SO3_W) * SO3_RP;    // X[60][68] + H[128][68]
-
-struct So3Args {
-  const float* w;        // kernels W0..W4 ([in][out] row-major) then biases b0..b4, fp32, SO3_FLOATS
-  float window[10];      // cosine-easing window of annealed_pos_enc (rnerf/model_utils.py:236-245) per octave
-};
 
 // The four hidden-layer kernels are contiguous in the weight image: one [504][128] fp32 matrix (60 + 128 + 128 + 188
 // rows).  It is streamed through a 3-slot shared-memory ring in chunks of <= 16 rows that never straddle a segment
@@ -507,6 +466,18 @@ static bool fast_div_enabled() {
   return !(e != nullptr && strcmp(e, "ieee") == 0);
 }
 
+bool rnerf::make_march_geom(const int ndim[3], const double nmin[3], const double nmax[3], cudaStream_t st, MarchGeom& mg) {
+  mg.g = make_geom(ndim, nmin, nmax);
+  mg.nby = (ndim[1] + BRICK - 1) >> BRICK_LOG2;
+  mg.nbz = (ndim[2] + BRICK - 1) >> BRICK_LOG2;
+  bool fast = fast_div_enabled();
+  for (int i = 0; i < 3; ++i) {
+    mg.rdelta[i] = fast ? recip_for(mg.g.ndelta[i], st) : 0.f;
+    fast = fast && mg.rdelta[i] != 0.f;
+  }
+  return fast;
+}
+
 static int march_impl(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
                       const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
                       double near, double far, int n_steps, int rec_floats, const float* so3_w,
@@ -522,14 +493,7 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
   RNERF_REQUIRE((double)n_steps * 12 * 32 < 2147483648.0, RNERF_E_SHAPE, "rnerf_march_fwd: n_steps too large");
   cudaStream_t st = (cudaStream_t)stream;
   MarchGeom mg;
-  mg.g = make_geom(ndim, nmin, nmax);
-  mg.nby = (ndim[1] + BRICK - 1) >> BRICK_LOG2;
-  mg.nbz = (ndim[2] + BRICK - 1) >> BRICK_LOG2;
-  bool fast = fast_div_enabled();
-  for (int i = 0; i < 3; ++i) {
-    mg.rdelta[i] = fast ? recip_for(mg.g.ndelta[i], st) : 0.f;
-    fast = fast && mg.rdelta[i] != 0.f;
-  }
+  const bool fast = make_march_geom(ndim, nmin, nmax, st, mg);
   const float step = (float)((far - near) / (n_steps - 1));
   const char* dbg_env = getenv("RNERF_MARCH_DEBUG");   // development aid: 1 = no record stores, 2 = no t stores, 4 = plain stores
   const int dbg = dbg_env ? atoi(dbg_env) : 0;

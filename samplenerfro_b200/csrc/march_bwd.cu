@@ -1,0 +1,538 @@
+// Adjoint of the "all"-stage eikonal march: gradients of a loss on the coarse samples (ray_pos_c, ray_dir_c) with
+// respect to so3_mlp.
+//
+// What the reference differentiates (train.py:164 jax.value_and_grad through nn.scan, rnerf/eikonal_utils.py:30-49,75-82):
+//     (n, g) = linear3(p_k);  G = where(|g| > 1e-3, rodrigues(so3_mlp(annealed_pos_enc(p_k)), g), g)
+//     p_{k+1} = p_k + step / n * v_k;    v_{k+1} = v_k + step * G
+// with ray_pos = p_k, ray_dir = safe_l2_normalize(v_k) read at the 64 coarse indices (rnerf/models.py:243-244); ray_dist is
+// stop_gradient (rnerf/eikonal_utils.py:120) and the fine samples are stop_gradient too (rnerf/model_utils.py:406-411), so
+// the coarse samples are the only way a loss reaches the scan.  The reverse sweep over k with adjoints (lp, lv) of
+// (p_{k+1}, v_{k+1}):
+//     lv_k = lv + step/n * lp                       dn = -(step/n^2) (v_k . lp)          dG = step * lv
+//     active ray:  (d raw, dg) = rodrigues^T(dG);   so3_mlp backward: parameter gradients += ..., dp_mlp = enc^T(dX)
+//     inactive:    dg = dG
+//     lp_k = lp + J^T (dn, dg) + dp_mlp             J = d linear3 / d p (the trilinear weights differentiated, floor/clamp
+//                                                       constant -- exactly what autodiff of rnerf/ior_utils.py:201-222 gives)
+// then the loss gradients of record k are added.  Nothing is saved by the forward march beyond the path records: p_k, v_k
+// are read back from them and the lookup / MLP forward are recomputed (bit-identical p_k => the same `active` set).
+//
+// One thread per ray, 128 rays per CTA, like the forward.  Steps at which a ray of the CTA is active evaluate so3_mlp
+// forward + backward cooperatively: the active rays are compacted into <= 32 columns of [feature][ray] buffers in
+// shared memory (all four hidden activations are kept for the ReLU masks and the weight gradients); thread t owns
+// neurons 2j, 2j+1 (j = t mod 64) for columns 16h .. 16h+15 (h = t / 64) in every GEMM of the chain:
+//     forward       acc[neuron][col] = sum_in  W [in][neuron]   A[in][col]
+//     input grad    acc[in][col]     = sum_out Wt[out][in]      dZ[out][col]      (Wt: transposed image, rnerf_so3_transpose)
+//     weight grad   gW[in][neuron]  += sum_col A[in][col] dZ[neuron][col]          (red.global.add.v2.f32 per row)
+// fp32 on the CUDA cores, like the forward (the gradient steers the ray).
+#include "march_common.cuh"
+
+namespace rnerf {
+
+constexpr int BW_COLS = 32;
+constexpr int BW_RP = BW_COLS + 4;                              // column pitch (rows stay 16-byte aligned)
+constexpr int BW_OFF_X = 0;                                     // X  [60][RP]   annealed encoding
+constexpr int BW_OFF_H = BW_OFF_X + SO3_IN * BW_RP;             // H  [4][128][RP] outputs of Dense_0..3 (post ReLU)
+constexpr int BW_OFF_D = BW_OFF_H + 4 * SO3_W * BW_RP;          // D  [128][RP]  dZ of the layer being processed
+constexpr int BW_OFF_DX = BW_OFF_D + SO3_W * BW_RP;             // DX [60][RP]   gradient wrt the encoding
+constexpr int BW_OFF_R = BW_OFF_DX + SO3_IN * BW_RP;            // R  [4][RP]    d raw (3 rows used)
+constexpr int BW_ACT_FLOATS = BW_OFF_R + 4 * BW_RP;
+constexpr int SO3T_OFF_0 = 0, SO3T_OFF_1 = SO3_W * SO3_IN, SO3T_OFF_2 = SO3T_OFF_1 + SO3_W * SO3_W,
+              SO3T_OFF_3A = SO3T_OFF_2 + SO3_W * SO3_W, SO3T_OFF_3B = SO3T_OFF_3A + SO3_W * SO3_W,
+              SO3T_FLOATS = SO3T_OFF_3B + SO3_W * SO3_IN;
+
+struct So3BwdArgs {
+  const float* w;        // forward image (So3Args::w)
+  const float* wt;       // transposed image: T0 [128][60], T1, T2, T3a [128][128], T3b [128][60]  (T_l[out][in] = W_l[in][out])
+  float* gw;             // gradient image, same layout as w, accumulated into
+  float window[10];
+};
+
+__global__ void __launch_bounds__(256) so3_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= SO3T_FLOATS) return;
+  int src;
+  if (i < SO3T_OFF_1)       { const int o = i / SO3_IN, k = i % SO3_IN; src = k * SO3_W + o; }
+  else if (i < SO3T_OFF_2)  { const int e = i - SO3T_OFF_1, o = e / SO3_W, k = e % SO3_W; src = SO3_OFF_W1 + k * SO3_W + o; }
+  else if (i < SO3T_OFF_3A) { const int e = i - SO3T_OFF_2, o = e / SO3_W, k = e % SO3_W; src = SO3_OFF_W2 + k * SO3_W + o; }
+  else if (i < SO3T_OFF_3B) { const int e = i - SO3T_OFF_3A, o = e / SO3_W, k = e % SO3_W; src = SO3_OFF_W3 + k * SO3_W + o; }
+  else                      { const int e = i - SO3T_OFF_3B, o = e / SO3_IN, k = e % SO3_IN; src = SO3_OFF_W3 + (SO3_W + k) * SO3_W + o; }
+  wt[i] = __ldg(w + src);
+}
+
+// ---- trilinear lookup with its derivative wrt p --------------------------------------------------------------------
+// c is computed with the forward's arithmetic (bit-identical n, grad n => the same active set); jx/jy/jz = dc/dp_x,y,z.
+template <bool FAST>
+__device__ __forceinline__ void lookup_with_jacobian(const float4* __restrict__ table, const MarchGeom& mg,
+                                                     const float* __restrict__ bricks, float px, float py, float pz, float4& c,
+                                                     float4& jx, float4& jy, float4& jz) {
+  float x, y, z;
+  grid_coords<FAST>(mg, px, py, pz, x, y, z);
+  const float xf = floorf(x), yf = floorf(y), zf = floorf(z);
+  const float xd = sub(x, xf), yd = sub(y, yf), zd = sub(z, zf);
+  const float oxd = sub(1.f, xd), oyd = sub(1.f, yd), ozd = sub(1.f, zd);
+  const float mx = (float)(mg.g.gx - 1), my = (float)(mg.g.gy - 1), mz = (float)(mg.g.gz - 1);
+  const int x0 = (int)fminf(fmaxf(xf, 0.f), mx), y0 = (int)fminf(fmaxf(yf, 0.f), my), z0 = (int)fminf(fmaxf(zf, 0.f), mz);
+  jx = jy = jz = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bricks != nullptr) {
+    const float b = __ldg(bricks + ((x0 >> BRICK_LOG2) * mg.nby + (y0 >> BRICK_LOG2)) * mg.nbz + (z0 >> BRICK_LOG2));
+    if (b == b) {            // homogeneous brick: eight equal corners -> zero derivative
+      const float c00 = lerp_ref(b, b, oxd, xd);
+      const float c0 = lerp_ref(c00, c00, oyd, yd);
+      c = make_float4(lerp_ref(c0, c0, ozd, zd), 0.f, 0.f, 0.f);
+      return;
+    }
+  }
+  const int x1 = (int)fminf(fmaxf(add(xf, 1.f), 0.f), mx), y1 = (int)fminf(fmaxf(add(yf, 1.f), 0.f), my),
+            z1 = (int)fminf(fmaxf(add(zf, 1.f), 0.f), mz);
+  const int sx = mg.g.gy * mg.g.gz, sy = mg.g.gz;
+  const int b00 = sx * x0 + sy * y0, b10 = sx * x1 + sy * y0, b01 = sx * x0 + sy * y1, b11 = sx * x1 + sy * y1;
+  const float4 d000 = __ldg(table + b00 + z0), d100 = __ldg(table + b10 + z0);
+  const float4 d001 = __ldg(table + b00 + z1), d101 = __ldg(table + b10 + z1);
+  const float4 d010 = __ldg(table + b01 + z0), d110 = __ldg(table + b11 + z0);
+  const float4 d011 = __ldg(table + b01 + z1), d111 = __ldg(table + b11 + z1);
+  const float4 c00 = lerp4_ref(d000, d100, oxd, xd);
+  const float4 c01 = lerp4_ref(d001, d101, oxd, xd);
+  const float4 c10 = lerp4_ref(d010, d110, oxd, xd);
+  const float4 c11 = lerp4_ref(d011, d111, oxd, xd);
+  const float4 c0 = lerp4_ref(c00, c10, oyd, yd);
+  const float4 c1 = lerp4_ref(c01, c11, oyd, yd);
+  c = lerp4_ref(c0, c1, ozd, zd);
+  const float ix = 1.f / mg.g.ndelta[0], iy = 1.f / mg.g.ndelta[1], iz = 1.f / mg.g.ndelta[2];
+#define RNERF_JAC(F)                                                                                                    \
+  {                                                                                                                     \
+    const float e00 = d100.F - d000.F, e01 = d101.F - d001.F, e10 = d110.F - d010.F, e11 = d111.F - d011.F;             \
+    jx.F = ((e00 * oyd + e10 * yd) * ozd + (e01 * oyd + e11 * yd) * zd) * ix;                                           \
+    jy.F = ((c10.F - c00.F) * ozd + (c11.F - c01.F) * zd) * iy;                                                         \
+    jz.F = (c1.F - c0.F) * iz;                                                                                          \
+  }
+  RNERF_JAC(x) RNERF_JAC(y) RNERF_JAC(z) RNERF_JAC(w)
+#undef RNERF_JAC
+}
+
+// ---- Rodrigues rotation (rnerf/ior_utils.py:300-306), reverse mode ------------------------------------------------------
+// pred = a (cos(th) v + sin(th) e x v + (1 - cos(th)) (e.v) e), th = |r|_safe, e = r/th, a = |g|_safe, v = g/a.
+// Given d pred, returns d r and d g.
+__device__ __forceinline__ void rodrigues_bwd(const float r[3], const float g[3], const float dp[3], float dr[3], float dg[3]) {
+  const float s_r = r[0] * r[0] + r[1] * r[1] + r[2] * r[2], s_g = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+  const float th = sqrtf(fmaxf(s_r, 1e-6f)), a = sqrtf(fmaxf(s_g, 1e-6f));
+  const float ith = 1.f / th, ia = 1.f / a;
+  const float e[3] = {r[0] * ith, r[1] * ith, r[2] * ith}, v[3] = {g[0] * ia, g[1] * ia, g[2] * ia};
+  const float ct = cosf(th), st = sinf(th);
+  const float c[3] = {e[1] * v[2] - e[2] * v[1], e[2] * v[0] - e[0] * v[2], e[0] * v[1] - e[1] * v[0]};
+  const float ev = e[0] * v[0] + e[1] * v[1] + e[2] * v[2];
+  const float omc = (1.f - ct) * ev;
+  float u[3], du[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { u[i] = ct * v[i] + st * c[i] + omc * e[i]; du[i] = a * dp[i]; }
+  float da = u[0] * dp[0] + u[1] * dp[1] + u[2] * dp[2];
+  const float e_du = e[0] * du[0] + e[1] * du[1] + e[2] * du[2];
+  const float d_ct = (v[0] * du[0] + v[1] * du[1] + v[2] * du[2]) - ev * e_du;
+  const float d_st = c[0] * du[0] + c[1] * du[1] + c[2] * du[2];
+  const float d_ev = (1.f - ct) * e_du;
+  const float dc[3] = {st * du[0], st * du[1], st * du[2]};
+  float de[3], dv[3];
+  // c = e x v:  de += v x dc,  dv += dc x e
+  de[0] = omc * du[0] + (v[1] * dc[2] - v[2] * dc[1]) + d_ev * v[0];
+  de[1] = omc * du[1] + (v[2] * dc[0] - v[0] * dc[2]) + d_ev * v[1];
+  de[2] = omc * du[2] + (v[0] * dc[1] - v[1] * dc[0]) + d_ev * v[2];
+  dv[0] = ct * du[0] + (dc[1] * e[2] - dc[2] * e[1]) + d_ev * e[0];
+  dv[1] = ct * du[1] + (dc[2] * e[0] - dc[0] * e[2]) + d_ev * e[1];
+  dv[2] = ct * du[2] + (dc[0] * e[1] - dc[1] * e[0]) + d_ev * e[2];
+  float d_th = -st * d_ct + ct * d_st;
+  d_th -= (e[0] * de[0] + e[1] * de[1] + e[2] * de[2]) * ith;
+  const float k_r = s_r > 1e-6f ? d_th : 0.f;          // d max(s, eps) / ds
+  da -= (v[0] * dv[0] + v[1] * dv[1] + v[2] * dv[2]) * ia;
+  const float k_g = s_g > 1e-6f ? da : 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    dr[i] = de[i] * ith + k_r * e[i];
+    dg[i] = dv[i] * ia + k_g * v[i];
+  }
+}
+
+// ---- building blocks of the cooperative MLP chain -----------------------------------------------------------------------
+// acc[n][c] += sum_{r < rows} W[r * wp + 2j + n] * In[r * RP + 16h + c]
+__device__ __forceinline__ void gemm_rows(float (&acc)[2][16], const float* __restrict__ W, int wp, int rows,
+                                          const float* __restrict__ In, int j, int h) {
+  const float* wq = W + 2 * j;
+  const float* in = In + 16 * h;
+#pragma unroll 8
+  for (int r = 0; r < rows; ++r) {
+    const float2 w = __ldg(reinterpret_cast<const float2*>(wq + r * wp));
+    const float4* xr = reinterpret_cast<const float4*>(in + r * BW_RP);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 x = xr[q];
+      acc[0][4 * q] = fmaf(w.x, x.x, acc[0][4 * q]);         acc[0][4 * q + 1] = fmaf(w.x, x.y, acc[0][4 * q + 1]);
+      acc[0][4 * q + 2] = fmaf(w.x, x.z, acc[0][4 * q + 2]); acc[0][4 * q + 3] = fmaf(w.x, x.w, acc[0][4 * q + 3]);
+      acc[1][4 * q] = fmaf(w.y, x.x, acc[1][4 * q]);         acc[1][4 * q + 1] = fmaf(w.y, x.y, acc[1][4 * q + 1]);
+      acc[1][4 * q + 2] = fmaf(w.y, x.z, acc[1][4 * q + 2]); acc[1][4 * q + 3] = fmaf(w.y, x.w, acc[1][4 * q + 3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[2][16]) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { acc[0][c] = 0.f; acc[1][c] = 0.f; }
+}
+
+// rows 2j, 2j+1 of a [.][RP] buffer, columns 16h .. 16h+15
+__device__ __forceinline__ void store_rows(const float (&acc)[2][16], float* buf, int j, int h) {
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    float4* o = reinterpret_cast<float4*>(buf + (2 * j + n) * BW_RP + 16 * h);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[n][4 * q], acc[n][4 * q + 1], acc[n][4 * q + 2], acc[n][4 * q + 3]);
+  }
+}
+
+__device__ __forceinline__ void relu_bias_store(float (&acc)[2][16], const float* __restrict__ bias, float* buf, int j, int h) {
+  const float b0 = __ldg(bias + 2 * j), b1 = __ldg(bias + 2 * j + 1);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { acc[0][c] = fmaxf(acc[0][c] + b0, 0.f); acc[1][c] = fmaxf(acc[1][c] + b1, 0.f); }
+  store_rows(acc, buf, j, h);
+}
+
+// dZ = dH where the saved activation is positive
+__device__ __forceinline__ void relu_mask(float (&acc)[2][16], const float* __restrict__ Hl, int j, int h) {
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    const float4* hr = reinterpret_cast<const float4*>(Hl + (2 * j + n) * BW_RP + 16 * h);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 x = hr[q];
+      acc[n][4 * q] = x.x > 0.f ? acc[n][4 * q] : 0.f;         acc[n][4 * q + 1] = x.y > 0.f ? acc[n][4 * q + 1] : 0.f;
+      acc[n][4 * q + 2] = x.z > 0.f ? acc[n][4 * q + 2] : 0.f; acc[n][4 * q + 3] = x.w > 0.f ? acc[n][4 * q + 3] : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// gb[2j + n] += sum_c dz[n][c];  gW[r][2j + n] += sum_c A[r][16h + c] dz[n][c]  for r < rows   (gW row pitch 128)
+__device__ __forceinline__ void bias_grad(const float (&dz)[2][16], float* gb, int j) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { s0 += dz[0][c]; s1 += dz[1][c]; }
+  red_add2(gb + 2 * j, s0, s1);
+}
+__device__ __forceinline__ void wgrad_rows(const float (&dz)[2][16], const float* __restrict__ A, int rows, float* gW, int j, int h) {
+  const float* in = A + 16 * h;
+  float* g = gW + 2 * j;
+#pragma unroll 2
+  for (int r = 0; r < rows; ++r) {
+    const float4* xr = reinterpret_cast<const float4*>(in + r * BW_RP);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 x = xr[q];
+      s0 = fmaf(x.x, dz[0][4 * q], s0); s0 = fmaf(x.y, dz[0][4 * q + 1], s0); s0 = fmaf(x.z, dz[0][4 * q + 2], s0); s0 = fmaf(x.w, dz[0][4 * q + 3], s0);
+      s1 = fmaf(x.x, dz[1][4 * q], s1); s1 = fmaf(x.y, dz[1][4 * q + 1], s1); s1 = fmaf(x.z, dz[1][4 * q + 2], s1); s1 = fmaf(x.w, dz[1][4 * q + 3], s1);
+    }
+    red_add2(g + r * SO3_W, s0, s1);
+  }
+}
+
+// so3_mlp forward + backward for the CTA's active rays.  EVERY thread of the CTA must call this (block barriers inside).
+// In (threads with `act`): position p, lookup gradient g, adjoint dG of the rotated gradient.
+// Out (threads with `act`): dg (adjoint of g), dp (adjoint of p through the encoding).  Parameter gradients -> a.gw.
+__device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int* cnt, int warp, int lane, bool act,
+                                            const float p[3], const float g[3], const float dG[3], float dg[3], float dp[3]) {
+  float* X = sm + BW_OFF_X;
+  float* H = sm + BW_OFF_H;
+  float* D = sm + BW_OFF_D;
+  float* DX = sm + BW_OFF_DX;
+  float* R = sm + BW_OFF_R;
+  const int tid = warp * 32 + lane;
+  const int j = tid & 63, h = tid >> 6;
+  const float* bias = a.w + SO3_OFF_B;
+  float* gbias = a.gw + SO3_OFF_B;
+  __syncthreads();                               // the previous evaluation has finished with cnt and the buffers
+  const unsigned bal = __ballot_sync(0xffffffffu, act);
+  if (lane == 0) cnt[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, n_act = 0;
+#pragma unroll
+  for (int w = 0; w < MARCH_THREADS / 32; ++w) {
+    const int c = cnt[w];
+    if (w < warp) base += c;
+    n_act += c;
+  }
+  const int idx = base + __popc(bal & ((1u << lane) - 1u));
+  constexpr int HL = SO3_W * BW_RP;              // floats per saved layer
+#pragma unroll 1
+  for (int col0 = 0; col0 < n_act; col0 += BW_COLS) {
+    const int n_here = min(BW_COLS, n_act - col0);
+    const bool mine = act && idx >= col0 && idx < col0 + BW_COLS;
+    const int col = idx - col0;
+    if (col0 > 0) __syncthreads();               // another pass: everyone is done with the buffers of the previous one
+    // unused columns are zeroed: their dZ stays exactly 0 through the chain, and 0 * (finite activation) adds nothing
+    if (tid < BW_COLS && tid >= n_here) {
+      for (int f = 0; f < SO3_IN; ++f) X[f * BW_RP + tid] = 0.f;
+      R[tid] = 0.f; R[BW_RP + tid] = 0.f; R[2 * BW_RP + tid] = 0.f;
+    }
+    if (mine) {
+      const float half_pi = 1.57079632679489661923f;
+      float sc = 1.f;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {             // feature k*6 + c = sin(2^k p_c) w_k, k*6 + 3 + c = sin(2^k p_c + pi/2) w_k
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float xb = mul(p[c], sc);
+          X[(k * 6 + c) * BW_RP + col] = mul(sinf(xb), a.window[k]);
+          X[(k * 6 + 3 + c) * BW_RP + col] = mul(sinf(add(xb, half_pi)), a.window[k]);
+        }
+        sc *= 2.f;
+      }
+    }
+    __syncthreads();
+    // ---- forward, keeping every hidden activation
+    float acc[2][16];
+    zero_acc(acc);
+    gemm_rows(acc, a.w, SO3_W, SO3_IN, X, j, h);
+    relu_bias_store(acc, bias, H, j, h);
+    __syncthreads();
+    zero_acc(acc);
+    gemm_rows(acc, a.w + SO3_OFF_W1, SO3_W, SO3_W, H, j, h);
+    relu_bias_store(acc, bias + SO3_W, H + HL, j, h);
+    __syncthreads();
+    zero_acc(acc);
+    gemm_rows(acc, a.w + SO3_OFF_W2, SO3_W, SO3_W, H + HL, j, h);
+    relu_bias_store(acc, bias + 2 * SO3_W, H + 2 * HL, j, h);
+    __syncthreads();
+    zero_acc(acc);
+    gemm_rows(acc, a.w + SO3_OFF_W3, SO3_W, SO3_W, H + 2 * HL, j, h);                 // skip concat [h, inputs]
+    gemm_rows(acc, a.w + SO3_OFF_W3 + SO3_W * SO3_W, SO3_W, SO3_IN, X, j, h);
+    relu_bias_store(acc, bias + 3 * SO3_W, H + 3 * HL, j, h);
+    __syncthreads();
+    const float* H4 = H + 3 * HL;
+    const float* W4 = a.w + SO3_OFF_W4;
+    // ---- Dense_4 + rotation, forward and reverse, by the ray's own thread
+    if (mine) {
+      const float* b4 = bias + 4 * SO3_W;
+      float r[3] = {__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2)};
+#pragma unroll 4
+      for (int k = 0; k < SO3_W; ++k) {
+        const float hv = H4[k * BW_RP + col];
+        r[0] = fmaf(hv, __ldg(W4 + 3 * k), r[0]); r[1] = fmaf(hv, __ldg(W4 + 3 * k + 1), r[1]); r[2] = fmaf(hv, __ldg(W4 + 3 * k + 2), r[2]);
+      }
+      float dr[3];
+      rodrigues_bwd(r, g, dG, dr, dg);
+      R[col] = dr[0]; R[BW_RP + col] = dr[1]; R[2 * BW_RP + col] = dr[2];
+    }
+    __syncthreads();
+    // ---- Dense_4 backward: dH4 = W4 d raw, masked; gW4 += H4 (x) d raw; gb4 += sum d raw
+    {
+      float gw4[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+      float w4[2][3];
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) w4[n][m] = __ldg(W4 + (2 * j + n) * 3 + m);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float r0 = R[16 * h + c], r1 = R[BW_RP + 16 * h + c], r2 = R[2 * BW_RP + 16 * h + c];
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const float hv = H4[(2 * j + n) * BW_RP + 16 * h + c];
+          acc[n][c] = hv > 0.f ? (w4[n][0] * r0 + w4[n][1] * r1 + w4[n][2] * r2) : 0.f;
+          gw4[n][0] = fmaf(hv, r0, gw4[n][0]); gw4[n][1] = fmaf(hv, r1, gw4[n][1]); gw4[n][2] = fmaf(hv, r2, gw4[n][2]);
+        }
+      }
+      float* g4 = a.gw + SO3_OFF_W4 + (2 * j) * 3;           // rows 2j, 2j+1 are 6 consecutive floats, 8-byte aligned
+      red_add2(g4, gw4[0][0], gw4[0][1]); red_add2(g4 + 2, gw4[0][2], gw4[1][0]); red_add2(g4 + 4, gw4[1][1], gw4[1][2]);
+      if (tid < 3) {
+        float s = 0.f;
+        for (int c = 0; c < BW_COLS; ++c) s += R[tid * BW_RP + c];
+        atomicAdd(gbias + 4 * SO3_W + tid, s);
+      }
+    }
+    // ---- Dense_3 (inputs [H3, X]): acc = dZ4
+    bias_grad(acc, gbias + 3 * SO3_W, j);
+    wgrad_rows(acc, H + 2 * HL, SO3_W, a.gw + SO3_OFF_W3, j, h);
+    wgrad_rows(acc, X, SO3_IN, a.gw + SO3_OFF_W3 + SO3_W * SO3_W, j, h);
+    store_rows(acc, D, j, h);
+    __syncthreads();
+    if (j < SO3_IN / 2) {                                    // gradient wrt the skip-concatenated encoding
+      float ax[2][16];
+      zero_acc(ax);
+      gemm_rows(ax, a.wt + SO3T_OFF_3B, SO3_IN, SO3_W, D, j, h);
+      store_rows(ax, DX, j, h);
+    }
+    zero_acc(acc);
+    gemm_rows(acc, a.wt + SO3T_OFF_3A, SO3_W, SO3_W, D, j, h);
+    relu_mask(acc, H + 2 * HL, j, h);                        // dZ3
+    __syncthreads();                                         // D has been read by everyone
+    // ---- Dense_2 (input H2)
+    bias_grad(acc, gbias + 2 * SO3_W, j);
+    wgrad_rows(acc, H + HL, SO3_W, a.gw + SO3_OFF_W2, j, h);
+    store_rows(acc, D, j, h);
+    __syncthreads();
+    zero_acc(acc);
+    gemm_rows(acc, a.wt + SO3T_OFF_2, SO3_W, SO3_W, D, j, h);
+    relu_mask(acc, H + HL, j, h);                            // dZ2
+    __syncthreads();
+    // ---- Dense_1 (input H1)
+    bias_grad(acc, gbias + SO3_W, j);
+    wgrad_rows(acc, H, SO3_W, a.gw + SO3_OFF_W1, j, h);
+    store_rows(acc, D, j, h);
+    __syncthreads();
+    zero_acc(acc);
+    gemm_rows(acc, a.wt + SO3T_OFF_1, SO3_W, SO3_W, D, j, h);
+    relu_mask(acc, H, j, h);                                 // dZ1
+    __syncthreads();
+    // ---- Dense_0 (input X)
+    bias_grad(acc, gbias, j);
+    wgrad_rows(acc, X, SO3_IN, a.gw, j, h);
+    store_rows(acc, D, j, h);
+    __syncthreads();
+    if (j < SO3_IN / 2) {
+      float ax[2][16];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {                          // continue from the skip part (own rows / columns)
+        const float4* o = reinterpret_cast<const float4*>(DX + (2 * j + n) * BW_RP + 16 * h);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float4 x = o[q]; ax[n][4 * q] = x.x; ax[n][4 * q + 1] = x.y; ax[n][4 * q + 2] = x.z; ax[n][4 * q + 3] = x.w; }
+      }
+      gemm_rows(ax, a.wt + SO3T_OFF_0, SO3_IN, SO3_W, D, j, h);
+      store_rows(ax, DX, j, h);
+    }
+    __syncthreads();
+    // ---- encoding backward: d/dp_c of sin(2^k p_c [+ pi/2]) w_k
+    if (mine) {
+      const float half_pi = 1.57079632679489661923f;
+      float sc = 1.f;
+      dp[0] = dp[1] = dp[2] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const float ws = a.window[k] * sc;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float xb = mul(p[c], sc);
+          dp[c] += ws * (cosf(xb) * DX[(k * 6 + c) * BW_RP + col] + cosf(add(xb, half_pi)) * DX[(k * 6 + 3 + c) * BW_RP + col]);
+        }
+        sc *= 2.f;
+      }
+    }
+  }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(MARCH_THREADS, 1) march_all_bwd_kernel(
+    const float4* __restrict__ table, const MarchGeom mg, const float* __restrict__ bricks, const float4* __restrict__ path,
+    int recf4, int64_t n_rays, float near, float step, int n_steps, const int32_t* __restrict__ jitter, int n_coarse,
+    const float* __restrict__ d_pos_c, const float* __restrict__ d_dir_c, const So3BwdArgs so3, float* __restrict__ d_origins,
+    float* __restrict__ d_viewdirs) {
+  extern __shared__ __align__(16) float sm[];
+  int* cnt = reinterpret_cast<int*>(sm + BW_ACT_FLOATS);
+  int16_t* kmap = reinterpret_cast<int16_t*>(cnt + 4);       // march step -> coarse sample index, or -1
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n_steps; i += MARCH_THREADS) kmap[i] = -1;
+  __syncthreads();
+  int k_last = 0;
+  for (int i = 0; i < n_coarse; ++i) k_last = max(k_last, min(max(__ldg(jitter + i), 0), n_steps - 1));
+  for (int i = tid; i < n_coarse; i += MARCH_THREADS) kmap[min(max(__ldg(jitter + i), 0), n_steps - 1)] = (int16_t)i;
+  __syncthreads();
+  const int64_t ray = blockIdx.x * (int64_t)MARCH_THREADS + tid;
+  const bool live = ray < n_rays;
+  const int64_t rr = live ? ray : (n_rays - 1);
+  const float4* rec = path + rr * (int64_t)n_steps * recf4;
+  float lp[3] = {0.f, 0.f, 0.f}, lv[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int k = k_last; k >= 0; --k) {
+    const float4 r0 = __ldg(rec + k * recf4), r1 = __ldg(rec + k * recf4 + 1);
+    const float p[3] = {r0.x, r0.y, r0.z}, v[3] = {r1.x, r1.y, r1.z};
+    if (k < k_last) {                            // transition k -> k+1, reverse
+      float4 c, jx, jy, jz;
+      lookup_with_jacobian<FAST>(table, mg, bricks, p[0], p[1], p[2], c, jx, jy, jz);
+      const float g[3] = {c.y, c.z, c.w};
+      const float hn = step / c.x;
+      const float dn = -(hn / c.x) * (v[0] * lp[0] + v[1] * lp[1] + v[2] * lp[2]);
+      const float dG[3] = {step * lv[0], step * lv[1], step * lv[2]};
+      float dg[3] = {dG[0], dG[1], dG[2]}, dpm[3] = {0.f, 0.f, 0.f};
+      const bool act = live && sqrtf(sumsq3(g[0], g[1], g[2])) > 1e-3f;     // the forward's test, on the same bits
+      if (__syncthreads_or(act)) so3_fwd_bwd(so3, sm, cnt, warp, lane, act, p, g, dG, dg, dpm);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) lv[i] = fmaf(hn, lp[i], lv[i]);
+      lp[0] += jx.x * dn + jx.y * dg[0] + jx.z * dg[1] + jx.w * dg[2] + dpm[0];
+      lp[1] += jy.x * dn + jy.y * dg[0] + jy.z * dg[1] + jy.w * dg[2] + dpm[1];
+      lp[2] += jz.x * dn + jz.y * dg[0] + jz.z * dg[1] + jz.w * dg[2] + dpm[2];
+    }
+    const int jc = kmap[k];
+    if (jc >= 0 && live) {                       // loss gradients of coarse sample jc = record k
+      const float* gp = d_pos_c + (ray * n_coarse + jc) * 3;
+      const float* gd = d_dir_c + (ray * n_coarse + jc) * 3;
+      const float s = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+      const float im = 1.f / sqrtf(fmaxf(s, 1e-6f));
+      const float d0 = v[0] * im, d1 = v[1] * im, d2 = v[2] * im;           // safe_l2_normalize (rnerf/math_utils.py:6-12)
+      const float g0 = __ldg(gd), g1 = __ldg(gd + 1), g2 = __ldg(gd + 2);
+      const float proj = s > 1e-6f ? (d0 * g0 + d1 * g1 + d2 * g2) : 0.f;
+      lv[0] += (g0 - d0 * proj) * im; lv[1] += (g1 - d1 * proj) * im; lv[2] += (g2 - d2 * proj) * im;
+      lp[0] += __ldg(gp); lp[1] += __ldg(gp + 1); lp[2] += __ldg(gp + 2);
+    }
+  }
+  if (live) {                                    // p_0 = o + near d, v_0 = d
+    if (d_origins != nullptr) { d_origins[3 * ray] = lp[0]; d_origins[3 * ray + 1] = lp[1]; d_origins[3 * ray + 2] = lp[2]; }
+    if (d_viewdirs != nullptr) {
+      d_viewdirs[3 * ray] = fmaf(near, lp[0], lv[0]); d_viewdirs[3 * ray + 1] = fmaf(near, lp[1], lv[1]);
+      d_viewdirs[3 * ray + 2] = fmaf(near, lp[2], lv[2]);
+    }
+  }
+}
+
+}  // namespace rnerf
+
+using namespace rnerf;
+
+extern "C" size_t rnerf_so3_transposed_floats(void) { return SO3T_FLOATS; }
+
+extern "C" int rnerf_so3_transpose(const float* so3_w, float* so3_wt, void* stream) {
+  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(so3_wt);
+  so3_transpose_kernel<<<(SO3T_FLOATS + 255) / 256, 256, 0, (cudaStream_t)stream>>>(so3_w, so3_wt);
+  count_launch();
+  return check_launch("rnerf_so3_transpose");
+}
+
+extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
+                                   const double nmax[3], const float* path, int rec_floats, int64_t n_rays, double near,
+                                   double far, int n_steps, const int32_t* jitter, int n_coarse, const float* d_pos_c,
+                                   const float* d_dir_c, const float* so3_w, const float* so3_wt,
+                                   const double so3_window[10], float* g_so3, float* d_origins, float* d_viewdirs,
+                                   void* stream) {
+  RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
+  RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_rays < 0");
+  RNERF_REQUIRE(n_steps >= 2 && n_steps <= 32767, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps must be in [2, 32767]");
+  RNERF_REQUIRE(n_coarse >= 1 && n_coarse <= n_steps, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_coarse must be in [1, n_steps]");
+  RNERF_REQUIRE(rec_floats == 8 || rec_floats == 12, RNERF_E_SHAPE, "rnerf_march_all_bwd: rec_floats must be 8 or 12");
+  if (n_rays == 0) return 0;
+  RNERF_REQUIRE_PTR(path); RNERF_REQUIRE_PTR(jitter); RNERF_REQUIRE_PTR(d_pos_c); RNERF_REQUIRE_PTR(d_dir_c);
+  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(so3_wt); RNERF_REQUIRE_PTR(so3_window); RNERF_REQUIRE_PTR(g_so3);
+  RNERF_REQUIRE(aligned16(table) && aligned16(path) && aligned16(so3_w) && aligned16(so3_wt) && aligned16(g_so3), RNERF_E_ALIGN,
+                "rnerf_march_all_bwd: table/path/so3 images must be 16-byte aligned");
+  RNERF_REQUIRE(grid_fits_int32(ndim), RNERF_E_SHAPE, "rnerf_march_all_bwd: grids with >= 2^31 voxels are not supported");
+  cudaStream_t st = (cudaStream_t)stream;
+  MarchGeom mg;
+  const bool fast = make_march_geom(ndim, nmin, nmax, st, mg);
+  const float step = (float)((far - near) / (n_steps - 1));
+  So3BwdArgs a;
+  a.w = so3_w; a.wt = so3_wt; a.gw = g_so3;
+  for (int k = 0; k < 10; ++k) a.window[k] = (float)so3_window[k];
+  const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 16 + (((size_t)n_steps * 2 + 15) & ~(size_t)15);
+  RNERF_REQUIRE(dyn <= 227 * 1024, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps too large for the step map in shared memory");
+  cudaError_t e = cudaFuncSetAttribute(march_all_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(march_all_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) { set_error("rnerf_march_all_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  const unsigned blocks = (unsigned)((n_rays + MARCH_THREADS - 1) / MARCH_THREADS);
+  if (fast)
+    march_all_bwd_kernel<true><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
+                                                                   n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
+                                                                   d_dir_c, a, d_origins, d_viewdirs);
+  else
+    march_all_bwd_kernel<false><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
+                                                                    n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
+                                                                    d_dir_c, a, d_origins, d_viewdirs);
+  count_launch();
+  return check_launch("rnerf_march_all_bwd");
+}

@@ -157,6 +157,9 @@ class NerfModel:
 
     def _so3_packed(self, variables: Dict) -> torch.Tensor:
         p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+        flat = getattr(self, "_theta_flat", None)
+        if flat is not None and "so3_mlp" in flat and p["Dense_0"]["kernel"].data_ptr() == flat["so3_mlp"].data_ptr():
+            return flat["so3_mlp"]     # the arena bucket IS the march kernels' weight image (train.ParamArena)
         sig = tuple((id(d["kernel"]), d["kernel"]._version, id(d["bias"]), d["bias"]._version) for d in p.values())
         hit = self._pack_cache.get("so3_mlp")
         if hit is None or hit[0] != sig:
@@ -221,20 +224,26 @@ class NerfModel:
         k0 = None if rng_0 is None else int(rng_0)
         k1 = None if rng_1 is None else int(rng_1)
         # --- bent-ray march: no trainable inputs in the radiance stage (T7) -> no autograd through it
+        # idx_grad is only read by the sparsity term and the debug outputs: every shipped config marches with
+        # compact (pos, t | v, n) records
+        need_grad = debug or self.use_online_sparsity
+        jit = self.draw_jitter(k0) if jitter is None else torch.as_tensor(jitter).to(self.device, torch.int32).contiguous()
+        so3_p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"] if self.stage.startswith("all") else None
+        if so3_p is not None and ag._needs_grad(so3_p):
+            # "all" stage, training: so3_mlp rotates grad n inside every step (a4) and is reached by the loss through the
+            # coarse samples; the reverse sweep of the scan is its own kernel
+            path, pos_c, dir_c, t_c = ag.march_all(self, variables, origins, viewdirs, jit, annealed_alpha, not need_grad)
+            grad_c = None
+            if self.use_online_sparsity:
+                with torch.no_grad():
+                    grad_c = ops.select(path, jit, want_grad=True)[3]
+        else:
+            with torch.no_grad():
+                so3 = (self._so3_packed(variables), self.so3_window(annealed_alpha)) if so3_p is not None else None
+                path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S,
+                                 bricks=self.bricks, compact=not need_grad, so3=so3)
+                pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=self.use_online_sparsity)
         with torch.no_grad():
-            # idx_grad is only read by the sparsity term and the debug outputs: every shipped config marches with
-            # compact (pos, t | v, n) records
-            need_grad = debug or self.use_online_sparsity
-            so3 = None
-            if self.stage.startswith("all"):     # a4: so3_mlp rotates grad n inside every step (inference only)
-                if torch.is_grad_enabled() and any(t.requires_grad for d in variables["params"]["path_sampler"]["scan"][
-                        "idx_model"]["so3_mlp"].values() for t in d.values()):
-                    raise NotImplementedError("training the 'all' stage (adjoint of the S-step scan wrt so3_mlp) is not built")
-                so3 = (self._so3_packed(variables), self.so3_window(annealed_alpha))
-            path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S,
-                             bricks=self.bricks, compact=not need_grad, so3=so3)
-            jit = self.draw_jitter(k0) if jitter is None else torch.as_tensor(jitter).to(self.device, torch.int32).contiguous()
-            pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=self.use_online_sparsity)
             mask_c = self._bbox_mask(pos_c) if self.use_mask_bbox else None
         # --- coarse pass
         raw_bkgd = ag.bkgd_raw(self, variables, dir_c, B, Nc)                      # T11: dir at the last coarse sample
@@ -249,7 +258,7 @@ class NerfModel:
         # --- hierarchical resampling along the bent path (stop-gradient in the reference)
         with torch.no_grad():
             uu = self.draw_u(k1, B, randomized) if u is None else torch.as_tensor(u).to(self.device, torch.float32).contiguous()
-            t_f, pos_f, dir_f, grad_f = ops.resample(path, t_c, out_c["weights"].detach(), uu, Nf,
+            t_f, pos_f, dir_f, grad_f = ops.resample(path, t_c.detach(), out_c["weights"].detach(), uu, Nf,
                                                      want_grad=self.use_online_sparsity and self.use_fine_sparsity)
             mask_f = self._bbox_mask(pos_f) if self.use_mask_bbox else None
         # --- fine pass

@@ -179,6 +179,56 @@ def select(path, jitter: torch.Tensor, want_grad: bool = False):
     return pos, dirs, t, grad
 
 
+def so3_unpack_views(g: torch.Tensor):
+    """Views of a flat so3 image (weights or gradients) in Flax order: [K0, b0, ..., K4, b4]."""
+    shapes = [(60, 128), (128, 128), (128, 128), (188, 128), (128, 3)]
+    ks, off = [], 0
+    for sh in shapes:
+        n = sh[0] * sh[1]
+        ks.append(g[off:off + n].view(sh)); off += n
+    out = []
+    for k, n in zip(ks, (128, 128, 128, 128, 3)):
+        out += [k, g[off:off + n]]; off += n
+    return out
+
+
+def so3_transpose(w: torch.Tensor) -> torch.Tensor:
+    """T_l[out][in] images of the four hidden so3 kernels (the adjoint's input-gradient GEMMs stream them row by row)."""
+    lib = _lib.load()
+    wt = torch.empty(lib.rnerf_so3_transposed_floats(), device=w.device, dtype=torch.float32)
+    check(lib.rnerf_so3_transpose(_p(_chk(w, "so3 weights")), _p(wt), _stream()), "rnerf_so3_transpose")
+    return wt
+
+
+def march_all_bwd(table, ndim, nmin, nmax, path, near: float, far: float, jitter: torch.Tensor, d_pos_c: torch.Tensor,
+                  d_dir_c: torch.Tensor, so3: Tuple[torch.Tensor, Sequence[float]], bricks: Optional[torch.Tensor] = None,
+                  g_so3: Optional[torch.Tensor] = None, want_ray_grads: bool = False):
+    """Reverse sweep of the "all"-stage scan (rnerf/eikonal_utils.py:30-49,75-82 under jax.value_and_grad, train.py:164):
+    from the loss gradients of the coarse samples, d_pos_c / d_dir_c [B,Nc,3] at march steps `jitter` (strictly
+    increasing), to the gradient of so3_mlp.  Returns (g_so3 [so3 image layout, accumulated into when given],
+    d_origins, d_viewdirs [B,3] or None)."""
+    rec = _rec(path); jitter = _chk(jitter, "jitter", torch.int32)
+    B, S, W = rec.shape
+    Nc = jitter.numel()
+    w, window = so3
+    _chk(w, "so3 weights"); _chk(table, "table")
+    d_pos_c = _chk(d_pos_c.contiguous(), "d_pos_c"); d_dir_c = _chk(d_dir_c.contiguous(), "d_dir_c")
+    assert d_pos_c.shape == (B, Nc, 3) and d_dir_c.shape == (B, Nc, 3) and len(window) == 10
+    if bricks is not None:
+        _chk(bricks, "bricks")
+    g = torch.zeros_like(w) if g_so3 is None else _chk(g_so3, "g_so3")
+    assert g.numel() == w.numel()
+    wt = so3_transpose(w)
+    d_o = torch.empty(B, 3, device=rec.device) if want_ray_grads else None
+    d_d = torch.empty(B, 3, device=rec.device) if want_ray_grads else None
+    nd, lo, hi = _geom(ndim, nmin, nmax)
+    win = (C.c_double * 10)(*[float(v) for v in window])
+    check(_lib.load().rnerf_march_all_bwd(_p(table), _p(bricks), nd, lo, hi, _p(rec), W, B, float(near), float(far), S,
+                                          _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), _p(w), _p(wt), win, _p(g), _p(d_o),
+                                          _p(d_d), _stream()), "rnerf_march_all_bwd")
+    return g, d_o, d_d
+
+
 # ---------------------------------------------------------------- encoding-fused radiance MLP (a8, a9)
 def nerf_mlp_layer_list(p: Dict) -> Tuple[list, list]:
     ks, bs = [], []
@@ -360,11 +410,22 @@ def mlp_wgrad(x: torch.Tensor, x_cols: int, kx_valid: int, dz: torch.Tensor, n: 
           "rnerf_mlp_wgrad")
 
 
-def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None):
+def mlp_input_grad_pack(k0: torch.Tensor, k5: torch.Tensor, k10: torch.Tensor) -> torch.Tensor:
+    """Transposed [640][64] fp32 image of the weight rows the encodings multiply (Dense_0, Dense_5[256:], Dense_10[256:])."""
+    lib = _lib.load()
+    wt = torch.empty(lib.rnerf_mlp_input_grad_packed_floats(), device=k0.device, dtype=torch.float32)
+    check(lib.rnerf_mlp_input_grad_pack(_p(_chk(k0, "Dense_0.kernel")), _p(_chk(k5, "Dense_5.kernel")),
+                                        _p(_chk(k10, "Dense_10.kernel")), _p(wt), _stream()), "rnerf_mlp_input_grad_pack")
+    return wt
+
+
+def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None, input_grads: bool = False):
     """Backward of pos_enc + NerfMLP wrt the 12 Dense layers: fused tcgen05 dgrad chain (dZ of every layer), then one
     MN-major tcgen05 wgrad per layer (+ the two skinny heads on CUDA cores).  Returns [gK0, gb0, ..., gK11, gb11].
     `grad_out`: optional list of 24 fp32 tensors (same order) the kernels ACCUMULATE into -- the gradient views of a
-    flat parameter arena, where every (kernel, bias) pair is contiguous; fresh zero buffers otherwise."""
+    flat parameter arena, where every (kernel, bias) pair is contiguous; fresh zero buffers otherwise.
+    `input_grads`: also return (d_pos, d_dirs), the gradients wrt the sample positions / directions ("all" stage), as
+    the last element of the returned list."""
     layers, enc = saved
     M = layers.shape[1]
     lib = _lib.load()
@@ -407,18 +468,32 @@ def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None):
     out = []
     for i in range(12):
         out += [gK[i], gB[i]]
+    if input_grads:
+        wt = mlp_input_grad_pack(K[0], K[5], K[10])
+        pos2, dirs2 = _chk(pos.reshape(-1, 3), "pos"), _chk(dirs.reshape(-1, 3), "dirs")
+        d_pos, d_dirs = torch.empty_like(pos2), torch.empty_like(dirs2)
+        check(lib.rnerf_mlp_input_grad(_p(dz), M, _p(wt), _p(pos2), _p(dirs2), _p(d_pos), _p(d_dirs), _stream()),
+              "rnerf_mlp_input_grad")
+        out.append((d_pos.view(pos.shape), d_dirs.view(dirs.shape)))
     return out
 
 
-def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params, gw_out=None):
+def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params, gw_out=None, want_d_dirs: bool = False):
     """Backward of the background MLP wrt its 5 Dense layers (CUDA: forward recompute per 32-ray tile + chain rule,
     weight gradients accumulated with atomics).  Returns [gK0, gb0, ..., gK4, gb4] (views of `gw_out`, a flat fp32
-    buffer laid out like `w` that is ACCUMULATED into, when given)."""
+    buffer laid out like `w` that is ACCUMULATED into, when given).  `want_d_dirs`: append d_dirs [n_rays,3], the gradient
+    wrt the input directions ("all" stage)."""
     _chk(w, "w"); _chk(dirs, "dirs"); d_raw = _chk(d_raw.contiguous(), "d_raw")
     gw = torch.zeros_like(w) if gw_out is None else _chk(gw_out, "gw_out")
     assert gw.numel() == w.numel()
     ptr = C.c_void_p(dirs.data_ptr() + 4 * offset)
-    check(_lib.load().rnerf_bkgd_mlp_bwd(_p(w), ptr, n_rays, stride, _p(d_raw), _p(gw), _stream()), "rnerf_bkgd_mlp_bwd")
+    d_dirs = None
+    if want_d_dirs:
+        d_dirs = torch.empty(n_rays, 3, device=w.device, dtype=torch.float32)
+        check(_lib.load().rnerf_bkgd_mlp_bwd_dirs(_p(w), ptr, n_rays, stride, _p(d_raw), _p(gw), _p(d_dirs), _stream()),
+              "rnerf_bkgd_mlp_bwd_dirs")
+    else:
+        check(_lib.load().rnerf_bkgd_mlp_bwd(_p(w), ptr, n_rays, stride, _p(d_raw), _p(gw), _stream()), "rnerf_bkgd_mlp_bwd")
     shapes = [(27, 128), (128, 128), (128, 128), (155, 128), (128, 3)]
     ks, off = [], 0
     for sh in shapes:
@@ -430,6 +505,8 @@ def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params, gw_out=None):
     out = []
     for k, b in zip(ks, bs):
         out += [k, b]
+    if want_d_dirs:
+        out.append(d_dirs)
     return out
 
 

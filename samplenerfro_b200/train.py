@@ -16,6 +16,7 @@ import torch
 from . import utils
 
 GRAD_BUCKETS = ("fine_mlp", "coarse_mlp", "bkgd_mlp")   # reverse order of backward completion
+ALL_STAGE_BUCKETS = GRAD_BUCKETS + ("path_sampler",)    # train.py:302-310: the "all" stage also trains so3_mlp
 
 
 def tree_leaves(tree) -> List[torch.Tensor]:
@@ -36,8 +37,9 @@ class ParamArena:
     Inside a bucket the leaves follow Flax order (Dense_i kernel, bias), except bkgd_mlp which is laid out (kernels..., biases...): that is
     the background kernels' weight image, so the bucket itself is passed to them and no packing step exists."""
 
-    def __init__(self, variables: Dict):
+    def __init__(self, variables: Dict, buckets=GRAD_BUCKETS):
         params = variables["params"]
+        self.buckets = tuple(buckets)
 
         def walk(d, out):
             for k in d:
@@ -48,15 +50,18 @@ class ParamArena:
             return out
 
         groups = []                                   # (bucket name, [(container dict, key), ...])
-        for name in GRAD_BUCKETS:
-            if name == "bkgd_mlp":
-                layers = [params[name][f"Dense_{i}"] for i in range(len(params[name]))]
+        flat_images = {"bkgd_mlp": ("bkgd_mlp", lambda: params["bkgd_mlp"]),
+                       "path_sampler": ("so3_mlp", lambda: params["path_sampler"]["scan"]["idx_model"]["so3_mlp"])}
+        for name in self.buckets:
+            if name in flat_images:       # laid out (kernels..., biases...): the kernels' own weight image
+                mlp = flat_images[name][1]()
+                layers = [mlp[f"Dense_{i}"] for i in range(len(mlp))]
                 groups.append((name, [(lay, leaf) for leaf in ("kernel", "bias") for lay in layers]))
             else:
                 groups.append((name, walk(params[name], [])))
         frozen = []
         for name in params:
-            if name not in GRAD_BUCKETS:
+            if name not in self.buckets:
                 walk(params[name], frozen)
         groups.append(("frozen", frozen))
         dev = groups[0][1][0][0][groups[0][1][0][1]].device
@@ -90,16 +95,19 @@ class ParamArena:
         for name in ("fine_mlp", "coarse_mlp"):
             p = params[name]
             self.sinks[name] = [p[f"Dense_{i}"][leaf].grad for i in range(len(p)) for leaf in ("kernel", "bias")]
-        lo, hi = self.bucket_range["bkgd_mlp"]
-        assert hi - lo == sum(d[k].numel() for d, k in groups[GRAD_BUCKETS.index("bkgd_mlp")][1]), "bkgd bucket must be dense"
-        self.sinks["bkgd_mlp"] = self.grad[lo:hi]
-        self.theta_flat = {"bkgd_mlp": self.theta[lo:hi]}
+        self.theta_flat = {}
+        for name in self.buckets:
+            if name in flat_images:
+                lo, hi = self.bucket_range[name]
+                assert hi - lo == sum(d[k].numel() for d, k in groups[self.buckets.index(name)][1]), f"{name} bucket must be dense"
+                self.sinks[flat_images[name][0]] = self.grad[lo:hi]
+                self.theta_flat[flat_images[name][0]] = self.theta[lo:hi]
 
     def zero_grad(self) -> None:
         self.grad.zero_()
 
     def bucket_grads(self) -> List[torch.Tensor]:
-        return [self.grad[self.bucket_range[n][0]:self.bucket_range[n][1]] for n in GRAD_BUCKETS]
+        return [self.grad[self.bucket_range[n][0]:self.bucket_range[n][1]] for n in self.buckets]
 
     def allreduce_mean(self, world_size: int, group=None) -> None:
         """jax.lax.pmean(grads, "batch") (train.py:166): one in-place all-reduce per bucket view, then one scale."""
@@ -200,8 +208,10 @@ class TrainState:
     @staticmethod
     def create(variables: Dict, args) -> "TrainState":
         """Re-homes the variables into a ParamArena (the tree keeps its names; leaves become views) and attaches the
-        fused Adam.  Radiance stage: path_sampler gets optax.set_to_zero (T7) -> it sits in the frozen tail."""
-        arena = ParamArena(variables)
+        fused Adam.  Radiance stage: path_sampler gets optax.set_to_zero (T7) -> it sits in the frozen tail; "all" stage
+        (train.py:302-310): so3_mlp is a fourth trainable bucket, laid out as the march kernels' weight image."""
+        stage = str(getattr(args, "stage", "radiance"))
+        arena = ParamArena(variables, ALL_STAGE_BUCKETS if stage.startswith("all") else GRAD_BUCKETS)
         return TrainState(step=0, params=variables, opt=ArenaAdam(arena, args), arena=arena)
 
 

@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rnerf_abi_version() == 4
+    assert lib.rnerf_abi_version() == 5
     assert lib.rnerf_encmlp_packed_bytes() > 1_000_000 and lib.rnerf_bkgd_weight_floats() == 56448 + 515
 
 
