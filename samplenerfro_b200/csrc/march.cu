@@ -120,16 +120,15 @@ constexpr int SO3_RP = SO3_COLS + 4;                         // ray pitch of the
 constexpr int SO3_ACT_FLOATS = (SO3_IN + SO3_W) * SO3_RP;    // X[60][68] + H[128][68]
 
 // The four hidden-layer kernels are contiguous in the weight image: one [504][128] fp32 matrix (60 + 128 + 128 + 188
-// rows).  It is streamed through a 3-slot shared-memory ring in chunks of <= 16 rows that never straddle a segment
-// (a segment = the rows multiplying one input block): S0 = Dense_0 x X, S1 = Dense_1 x H, S2 = Dense_2 x H,
-// S3a = Dense_3[:128] x H, S3b = Dense_3[128:] x X (the skip concat [h, inputs]).  All 128 threads of the CTA copy a chunk
-// with cp.async (coalesced, two chunks in flight), so the weights cross L2 -> SM once per CTA evaluation instead of
-// once per warp, and the FMA loop reads them with conflict-free LDS instead of waiting on L2 latency.
-constexpr int SO3_CH = 16;                                   // rows per chunk
+// rows).  It is streamed through the TMA-fed shared-memory ring of march_common.cuh in chunks of <= 16 rows that never
+// straddle a segment (a segment = the rows multiplying one input block): S0 = Dense_0 x X, S1 = Dense_1 x H,
+// S2 = Dense_2 x H, S3a = Dense_3[:128] x H, S3b = Dense_3[128:] x X (the skip concat [h, inputs]).  The weights cross
+// L2 -> SM once per CTA evaluation, n_slots - 1 chunks ahead of the FMA loop (also across evaluations: the stream is
+// periodic), and are read with conflict-free LDS.
 constexpr int SO3_NCHUNK = 4 + 8 + 8 + 8 + 4;                // 32
-constexpr int SO3_RING_SLOTS = 3;
-constexpr int SO3_RING_FLOATS = SO3_RING_SLOTS * SO3_CH * SO3_W;
-constexpr int SO3_SMEM_BYTES = (SO3_ACT_FLOATS + SO3_RING_FLOATS) * 4 + 16;     // + per-warp active-ray counts
+// dynamic shared memory: activations | per-warp active-ray counts (16 B) | mbarriers (128 B) | ring slots
+constexpr int SO3_OFF_CNT = SO3_ACT_FLOATS * 4, SO3_OFF_BARS = SO3_OFF_CNT + 16, SO3_OFF_RING = SO3_OFF_BARS + 8 * SO3_MAX_SLOTS;
+static size_t so3_smem_bytes(int n_slots) { return (size_t)SO3_OFF_RING + (size_t)n_slots * SO3_SLOT_FLOATS * 4; }
 
 struct So3Chunk { int row0, rows, in_k0, in_is_x, last_of_layer; };
 __device__ __forceinline__ So3Chunk so3_chunk(int c) {
@@ -148,30 +147,25 @@ __device__ __forceinline__ So3Chunk so3_chunk(int c) {
   return k;
 }
 
+struct So3FwdStream {
+  const float* w;
+  __device__ __forceinline__ void operator()(uint32_t g, const float*& src, uint32_t& bytes) const {
+    const So3Chunk k = so3_chunk((int)(g % (uint32_t)SO3_NCHUNK));
+    src = w + (size_t)k.row0 * SO3_W;
+    bytes = (uint32_t)k.rows * SO3_W * 4;
+  }
+};
+
 // raw = so3_mlp(annealed_pos_enc(p)) for the CTA's active rays.  EVERY thread of the CTA must call this (block barriers
 // inside); only threads with `act` get a result.
-__device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, int warp, int lane, bool act, float px, float py,
-                                         float pz, float& r0, float& r1, float& r2) {
-  float* X = dyn_smem;                         // [60][132]
-  float* Hs = dyn_smem + SO3_IN * SO3_RP;      // [128][132]
-  float* ring = dyn_smem + SO3_ACT_FLOATS;
-  int* cnt = reinterpret_cast<int*>(ring + SO3_RING_FLOATS);
+__device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3Ring& ring, int warp, int lane, bool act, float px,
+                                         float py, float pz, float& r0, float& r1, float& r2) {
+  float* X = dyn_smem;                         // [60][68]
+  float* Hs = dyn_smem + SO3_IN * SO3_RP;      // [128][68]
+  int* cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(dyn_smem) + SO3_OFF_CNT);
   const int tid = warp * 32 + lane;
-  auto issue = [&](int c) {
-    const So3Chunk k = so3_chunk(c);
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (c % SO3_RING_SLOTS) * SO3_CH * SO3_W);
-    const float* src = a.w + (size_t)k.row0 * SO3_W;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {              // 512 16-byte units per chunk, 4 per thread
-      const int u = tid + i * MARCH_THREADS, r = u >> 5;
-      const int sz = r < k.rows ? 16 : 0;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + u * 16), "l"(src + (r < k.rows ? u * 4 : 0)), "r"(sz)
-                   : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  issue(0);
-  issue(1);
+  const So3FwdStream stream{a.w};
+  ring_prime(ring, tid, stream);
   // ---- compaction: active ray -> column idx of the activation buffers
   const unsigned bal = __ballot_sync(0xffffffffu, act);
   if (lane == 0) cnt[warp] = __popc(bal);
@@ -192,11 +186,7 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, int 
     const int n_groups = (min(SO3_COLS, n_act - col0) + 31) >> 5;   // 1 or 2 groups of 32 columns (unused columns hold garbage)
     const bool mine = act && idx >= col0 && idx < col0 + SO3_COLS;
     const int col = idx - col0;
-    if (col0 > 0) {                            // another pass: everyone is done with the ring and Hs of the previous one
-      __syncthreads();
-      issue(0);
-      issue(1);
-    }
+    if (col0 > 0) __syncthreads();             // another pass: everyone is done with X and Hs of the previous one
     if (mine) {
       const float xs[3] = {px, py, pz};
       const float half_pi = 1.57079632679489661923f;
@@ -212,40 +202,37 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, int 
         sc *= 2.f;
       }
     }
-    float acc[2][2][16];
+    f32x2 acc[2][2][8];                        // [group][neuron][column pair]
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
-      for (int r = 0; r < 16; ++r) { acc[g][0][r] = 0.f; acc[g][1][r] = 0.f; }
+      for (int r = 0; r < 8; ++r) { acc[g][0][r] = 0ull; acc[g][1][r] = 0ull; }
     int layer = 0;
 #pragma unroll 1
     for (int c = 0; c < SO3_NCHUNK; ++c) {
-      if (c + 1 < SO3_NCHUNK) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();                         // chunk c has landed for everyone; slot (c+2)%3 is no longer being read;
-                                               // activations written before this point (X, or Hs of the last layer) are visible
-      if (c + 2 < SO3_NCHUNK) issue(c + 2);
+      // chunk c has landed; the barrier inside also makes the activations written before this point (X, or Hs of the
+      // last layer) visible
+      const float* wbuf = ring_acquire(ring, tid, stream) + 2 * j;
       const So3Chunk k = so3_chunk(c);
-      const float* wbuf = ring + (c % SO3_RING_SLOTS) * SO3_CH * SO3_W + 2 * j;
       const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_RP + 16 * h;
 #pragma unroll 4
       for (int r = 0; r < k.rows; ++r) {
         const float2 w = *reinterpret_cast<const float2*>(wbuf + r * SO3_W);
+        const f32x2 w0 = pack2(w.x, w.x), w1 = pack2(w.y, w.y);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < n_groups) {
-            const float4* xr = reinterpret_cast<const float4*>(in + r * SO3_RP + 32 * g);
+            const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(in + r * SO3_RP + 32 * g);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 x = xr[q];
-              acc[g][0][4 * q] = fmaf(w.x, x.x, acc[g][0][4 * q]); acc[g][0][4 * q + 1] = fmaf(w.x, x.y, acc[g][0][4 * q + 1]);
-              acc[g][0][4 * q + 2] = fmaf(w.x, x.z, acc[g][0][4 * q + 2]); acc[g][0][4 * q + 3] = fmaf(w.x, x.w, acc[g][0][4 * q + 3]);
-              acc[g][1][4 * q] = fmaf(w.y, x.x, acc[g][1][4 * q]); acc[g][1][4 * q + 1] = fmaf(w.y, x.y, acc[g][1][4 * q + 1]);
-              acc[g][1][4 * q + 2] = fmaf(w.y, x.z, acc[g][1][4 * q + 2]); acc[g][1][4 * q + 3] = fmaf(w.y, x.w, acc[g][1][4 * q + 3]);
+              const ulonglong2 x = xr[q];      // columns 4q, 4q+1 | 4q+2, 4q+3
+              acc[g][0][2 * q] = fma2(w0, x.x, acc[g][0][2 * q]); acc[g][0][2 * q + 1] = fma2(w0, x.y, acc[g][0][2 * q + 1]);
+              acc[g][1][2 * q] = fma2(w1, x.x, acc[g][1][2 * q]); acc[g][1][2 * q + 1] = fma2(w1, x.y, acc[g][1][2 * q + 1]);
             }
           }
         }
       }
+      ++ring.pos;
       if (k.last_of_layer) {                   // bias + ReLU, handed to the next layer in place through Hs
         __syncthreads();                       // every thread has finished reading the layer input
         const float b0 = __ldg(bias + layer * SO3_W + 2 * j), b1 = __ldg(bias + layer * SO3_W + 2 * j + 1);
@@ -256,14 +243,15 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, int 
             float4* o1 = reinterpret_cast<float4*>(Hs + (2 * j + 1) * SO3_RP + 32 * g + 16 * h);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              o0[q] = make_float4(fmaxf(acc[g][0][4 * q] + b0, 0.f), fmaxf(acc[g][0][4 * q + 1] + b0, 0.f),
-                                  fmaxf(acc[g][0][4 * q + 2] + b0, 0.f), fmaxf(acc[g][0][4 * q + 3] + b0, 0.f));
-              o1[q] = make_float4(fmaxf(acc[g][1][4 * q] + b1, 0.f), fmaxf(acc[g][1][4 * q + 1] + b1, 0.f),
-                                  fmaxf(acc[g][1][4 * q + 2] + b1, 0.f), fmaxf(acc[g][1][4 * q + 3] + b1, 0.f));
+              float a0, a1, a2, a3;
+              unpack2(acc[g][0][2 * q], a0, a1); unpack2(acc[g][0][2 * q + 1], a2, a3);
+              o0[q] = make_float4(fmaxf(a0 + b0, 0.f), fmaxf(a1 + b0, 0.f), fmaxf(a2 + b0, 0.f), fmaxf(a3 + b0, 0.f));
+              unpack2(acc[g][1][2 * q], a0, a1); unpack2(acc[g][1][2 * q + 1], a2, a3);
+              o1[q] = make_float4(fmaxf(a0 + b1, 0.f), fmaxf(a1 + b1, 0.f), fmaxf(a2 + b1, 0.f), fmaxf(a3 + b1, 0.f));
             }
           }
 #pragma unroll
-          for (int r = 0; r < 16; ++r) { acc[g][0][r] = 0.f; acc[g][1][r] = 0.f; }
+          for (int r = 0; r < 8; ++r) { acc[g][0][r] = 0ull; acc[g][1][r] = 0ull; }
         }
         ++layer;
       }
@@ -303,8 +291,9 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
                                                               const float* __restrict__ viewdirs, int64_t n_rays,
                                                               float near, float step, int n_steps,
                                                               float4* __restrict__ path, float* __restrict__ t_col,
-                                                              const float* __restrict__ bricks, int dbg, const So3Args so3) {
-  extern __shared__ __align__(16) float so3_scratch[];     // SO3 only: SO3_SMEM_BYTES
+                                                              const float* __restrict__ bricks, int dbg, const So3Args so3,
+                                                              int so3_slots) {
+  extern __shared__ __align__(16) float so3_scratch[];     // SO3 only: so3_smem_bytes(so3_slots)
   constexpr int F4_PER_FLUSH = STEPS_PER_FLUSH * RECF4;   // float4 per ray per flush: 8 (compact) / 12 (full)
   constexpr int PITCH = F4_PER_FLUSH + 1;                  // +1 float4 pad: conflict-free column writes
   __shared__ float4 stage[MARCH_THREADS / 32][32 * PITCH];
@@ -312,6 +301,12 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp_ray0 = (blockIdx.x * (int64_t)MARCH_THREADS) + warp * 32;
   if (!SO3 && warp_ray0 >= n_rays) return;      // SO3: every warp stays for the block barriers of so3_eval
+  So3Ring ring;
+  if (SO3) {
+    char* base = reinterpret_cast<char*>(so3_scratch);
+    ring_init(ring, reinterpret_cast<float*>(base + SO3_OFF_RING), base + SO3_OFF_BARS, so3_slots, threadIdx.x);
+    __syncthreads();
+  }
   const int64_t ray = warp_ray0 + lane;
   const bool live = ray < n_rays;
   const int64_t rr = live ? ray : (n_rays - 1);
@@ -356,7 +351,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
       const bool act = live && sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;     // jnp.linalg.norm(idx_grad) > 1e-3
       if (__syncthreads_or(act)) {
         float r0, r1, r2;
-        so3_eval(so3, so3_scratch, warp, lane, act, px, py, pz, r0, r1, r2);
+        so3_eval(so3, so3_scratch, ring, warp, lane, act, px, py, pz, r0, r1, r2);
         if (act) so3_rotate(r0, r1, r2, gx, gy, gz);
       }
     }
@@ -423,6 +418,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
     g_wr += F4_PER_FLUSH;
     __syncwarp();
   }
+  if (SO3) ring_drain(ring);                     // weight chunks fetched ahead for an evaluation that never came
 }
 
 // ray_dir of every record, normalised: the array PathSampler returns (rnerf/eikonal_utils.py:113)
@@ -501,26 +497,34 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
   So3Args so3;
   memset(&so3, 0, sizeof(so3));
   size_t dyn = 0;
+  int slots = 0;
   if (so3_w != nullptr) {
     so3.w = so3_w;
     for (int k = 0; k < 10; ++k) so3.window[k] = (float)so3_window[k];
-    dyn = (size_t)SO3_SMEM_BYTES;
-    static bool attr_set[64] = {false};
-    int dev = 0;
+    int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    // Small launches (a training batch) leave at most one CTA per SM: a deep ring (12 chunks = 96 KB in flight) hides
+    // the L2 latency alone.  Full frames keep two CTAs per SM (110 KB each) with a 4-slot ring and hide it with the
+    // other CTA.  RNERF_SO3_SLOTS overrides (development aid).
+    slots = blocks <= (unsigned)n_sm ? 13 : 4;
+    const char* se = getenv("RNERF_SO3_SLOTS");
+    if (se != nullptr && atoi(se) >= 2 && atoi(se) <= SO3_MAX_SLOTS) slots = atoi(se);
+    dyn = so3_smem_bytes(slots);
+    static size_t attr_set[64] = {0};
+    if (dev >= 0 && dev < 64 && attr_set[dev] < dyn) {
       cudaError_t e = cudaSuccess;
       e = cudaFuncSetAttribute(march_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(march_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(march_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(march_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       if (e != cudaSuccess) { set_error("rnerf_march_all_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-      attr_set[dev] = true;
+      attr_set[dev] = dyn;
     }
   }
 #define RNERF_MARCH_LAUNCH(R, F, A)                                                                                       \
   march_kernel<R, F, A><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
-                                                            step, n_steps, (float4*)path, t_col, bricks, dbg, so3)
+                                                            step, n_steps, (float4*)path, t_col, bricks, dbg, so3, slots)
   if (so3_w == nullptr) {
     if (rec_floats == 8) { if (fast) RNERF_MARCH_LAUNCH(2, true, false); else RNERF_MARCH_LAUNCH(2, false, false); }
     else                 { if (fast) RNERF_MARCH_LAUNCH(3, true, false); else RNERF_MARCH_LAUNCH(3, false, false); }

@@ -151,24 +151,64 @@ __device__ __forceinline__ void rodrigues_bwd(const float r[3], const float g[3]
 }
 
 // ---- building blocks of the cooperative MLP chain -----------------------------------------------------------------------
-// acc[n][c] += sum_{r < rows} W[r * wp + 2j + n] * In[r * RP + 16h + c]
-__device__ __forceinline__ void gemm_rows(float (&acc)[2][16], const float* __restrict__ W, int wp, int rows,
-                                          const float* __restrict__ In, int j, int h) {
-  const float* wq = W + 2 * j;
-  const float* in = In + 16 * h;
-#pragma unroll 8
-  for (int r = 0; r < rows; ++r) {
-    const float2 w = __ldg(reinterpret_cast<const float2*>(wq + r * wp));
-    const float4* xr = reinterpret_cast<const float4*>(in + r * BW_RP);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 x = xr[q];
-      acc[0][4 * q] = fmaf(w.x, x.x, acc[0][4 * q]);         acc[0][4 * q + 1] = fmaf(w.x, x.y, acc[0][4 * q + 1]);
-      acc[0][4 * q + 2] = fmaf(w.x, x.z, acc[0][4 * q + 2]); acc[0][4 * q + 3] = fmaf(w.x, x.w, acc[0][4 * q + 3]);
-      acc[1][4 * q] = fmaf(w.y, x.x, acc[1][4 * q]);         acc[1][4 * q + 1] = fmaf(w.y, x.y, acc[1][4 * q + 1]);
-      acc[1][4 * q + 2] = fmaf(w.y, x.z, acc[1][4 * q + 2]); acc[1][4 * q + 3] = fmaf(w.y, x.w, acc[1][4 * q + 3]);
+// Weight stream of one evaluation through the TMA ring (march_common.cuh), 72 chunks of <= 16 rows:
+//   0..31   the forward image, segments S0 (Dense_0 x X), S1, S2, S3a (Dense_3[:128] x H3), S3b (Dense_3[128:] x X)
+//   32..39  T3b [128][60]   40..47 T3a [128][128]   48..55 T2   56..63 T1   64..71 T0 [128][60]     (order of use)
+constexpr int BW_NCHUNK = 72;
+constexpr int BW_RING_SLOTS = 12;
+struct So3BwdStream {
+  const float* w;
+  const float* wt;
+  __device__ __forceinline__ void operator()(uint32_t g, const float*& src, uint32_t& bytes) const {
+    const int c = (int)(g % (uint32_t)BW_NCHUNK);
+    if (c < 32) {
+      int seg, i;
+      if (c < 4) { seg = 0; i = c; } else if (c < 12) { seg = 1; i = c - 4; } else if (c < 20) { seg = 2; i = c - 12; }
+      else if (c < 28) { seg = 3; i = c - 20; } else { seg = 4; i = c - 28; }
+      const int seg_row0 = seg == 0 ? 0 : (seg == 1 ? 60 : (seg == 2 ? 188 : (seg == 3 ? 316 : 444)));
+      const int seg_rows = (seg == 0 || seg == 4) ? 60 : 128;
+      src = w + (size_t)(seg_row0 + i * SO3_CH) * SO3_W;
+      bytes = (uint32_t)min(SO3_CH, seg_rows - i * SO3_CH) * SO3_W * 4;
+    } else {
+      const int b = (c - 32) >> 3, i = (c - 32) & 7;         // block in order of use, 8 chunks of 16 rows each
+      const int off = b == 0 ? SO3T_OFF_3B : (b == 1 ? SO3T_OFF_3A : (b == 2 ? SO3T_OFF_2 : (b == 3 ? SO3T_OFF_1 : SO3T_OFF_0)));
+      const int wp = (b == 0 || b == 4) ? SO3_IN : SO3_W;
+      src = wt + off + (size_t)i * SO3_CH * wp;
+      bytes = (uint32_t)SO3_CH * wp * 4;
     }
   }
+};
+
+// acc[n][c] += sum_{r < K} W[r][2j + n] * In[r][16h + c]: W ([K][wp], K <= 128) arrives as the next ceil(K/16) chunks of the
+// ring.  Every thread of the CTA runs the chunk loop (block barrier per chunk); `work` = this thread owns output rows.
+__device__ __forceinline__ void gemm_ring(float (&acc)[2][16], So3Ring& ring, int tid, const So3BwdStream& stream, int K, int wp,
+                                          const float* __restrict__ In, int j, int h, bool work) {
+  const float* in = In + 16 * h;
+  f32x2 a2[2][8];                                // column pairs (SASS: FFMA2)
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { a2[0][q] = pack2(acc[0][2 * q], acc[0][2 * q + 1]); a2[1][q] = pack2(acc[1][2 * q], acc[1][2 * q + 1]); }
+#pragma unroll 1
+  for (int k0 = 0; k0 < K; k0 += SO3_CH) {
+    const float* wq = ring_acquire(ring, tid, stream) + 2 * j;
+    const int rows = min(SO3_CH, K - k0);
+    if (work) {
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+        const float2 w = *reinterpret_cast<const float2*>(wq + r * wp);
+        const f32x2 w0 = pack2(w.x, w.x), w1 = pack2(w.y, w.y);
+        const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(in + (k0 + r) * BW_RP);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const ulonglong2 x = xr[q];
+          a2[0][2 * q] = fma2(w0, x.x, a2[0][2 * q]); a2[0][2 * q + 1] = fma2(w0, x.y, a2[0][2 * q + 1]);
+          a2[1][2 * q] = fma2(w1, x.x, a2[1][2 * q]); a2[1][2 * q + 1] = fma2(w1, x.y, a2[1][2 * q + 1]);
+        }
+      }
+    }
+    ++ring.pos;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { unpack2(a2[0][q], acc[0][2 * q], acc[0][2 * q + 1]); unpack2(a2[1][q], acc[1][2 * q], acc[1][2 * q + 1]); }
 }
 
 __device__ __forceinline__ void zero_acc(float (&acc)[2][16]) {
@@ -221,24 +261,29 @@ __device__ __forceinline__ void bias_grad(const float (&dz)[2][16], float* gb, i
 __device__ __forceinline__ void wgrad_rows(const float (&dz)[2][16], const float* __restrict__ A, int rows, float* gW, int j, int h) {
   const float* in = A + 16 * h;
   float* g = gW + 2 * j;
+  f32x2 d2[2][8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { d2[0][q] = pack2(dz[0][2 * q], dz[0][2 * q + 1]); d2[1][q] = pack2(dz[1][2 * q], dz[1][2 * q + 1]); }
 #pragma unroll 2
   for (int r = 0; r < rows; ++r) {
-    const float4* xr = reinterpret_cast<const float4*>(in + r * BW_RP);
-    float s0 = 0.f, s1 = 0.f;
+    const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(in + r * BW_RP);
+    f32x2 s0 = 0ull, s1 = 0ull;                  // (even columns, odd columns) partial sums
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 x = xr[q];
-      s0 = fmaf(x.x, dz[0][4 * q], s0); s0 = fmaf(x.y, dz[0][4 * q + 1], s0); s0 = fmaf(x.z, dz[0][4 * q + 2], s0); s0 = fmaf(x.w, dz[0][4 * q + 3], s0);
-      s1 = fmaf(x.x, dz[1][4 * q], s1); s1 = fmaf(x.y, dz[1][4 * q + 1], s1); s1 = fmaf(x.z, dz[1][4 * q + 2], s1); s1 = fmaf(x.w, dz[1][4 * q + 3], s1);
+      const ulonglong2 x = xr[q];
+      s0 = fma2(x.x, d2[0][2 * q], s0); s0 = fma2(x.y, d2[0][2 * q + 1], s0);
+      s1 = fma2(x.x, d2[1][2 * q], s1); s1 = fma2(x.y, d2[1][2 * q + 1], s1);
     }
-    red_add2(g + r * SO3_W, s0, s1);
+    float a, b, c, d;
+    unpack2(s0, a, b); unpack2(s1, c, d);
+    red_add2(g + r * SO3_W, a + b, c + d);
   }
 }
 
 // so3_mlp forward + backward for the CTA's active rays.  EVERY thread of the CTA must call this (block barriers inside).
 // In (threads with `act`): position p, lookup gradient g, adjoint dG of the rotated gradient.
 // Out (threads with `act`): dg (adjoint of g), dp (adjoint of p through the encoding).  Parameter gradients -> a.gw.
-__device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int* cnt, int warp, int lane, bool act,
+__device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int* cnt, So3Ring& ring, int warp, int lane, bool act,
                                             const float p[3], const float g[3], const float dG[3], float dg[3], float dp[3]) {
   float* X = sm + BW_OFF_X;
   float* H = sm + BW_OFF_H;
@@ -249,6 +294,8 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
   const int j = tid & 63, h = tid >> 6;
   const float* bias = a.w + SO3_OFF_B;
   float* gbias = a.gw + SO3_OFF_B;
+  const So3BwdStream stream{a.w, a.wt};
+  ring_prime(ring, tid, stream);
   __syncthreads();                               // the previous evaluation has finished with cnt and the buffers
   const unsigned bal = __ballot_sync(0xffffffffu, act);
   if (lane == 0) cnt[warp] = __popc(bal);
@@ -291,20 +338,17 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     // ---- forward, keeping every hidden activation
     float acc[2][16];
     zero_acc(acc);
-    gemm_rows(acc, a.w, SO3_W, SO3_IN, X, j, h);
+    gemm_ring(acc, ring, tid, stream, SO3_IN, SO3_W, X, j, h, true);
     relu_bias_store(acc, bias, H, j, h);
-    __syncthreads();
     zero_acc(acc);
-    gemm_rows(acc, a.w + SO3_OFF_W1, SO3_W, SO3_W, H, j, h);
+    gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, H, j, h, true);           // (the chunk barrier publishes H first)
     relu_bias_store(acc, bias + SO3_W, H + HL, j, h);
-    __syncthreads();
     zero_acc(acc);
-    gemm_rows(acc, a.w + SO3_OFF_W2, SO3_W, SO3_W, H + HL, j, h);
+    gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, H + HL, j, h, true);
     relu_bias_store(acc, bias + 2 * SO3_W, H + 2 * HL, j, h);
-    __syncthreads();
     zero_acc(acc);
-    gemm_rows(acc, a.w + SO3_OFF_W3, SO3_W, SO3_W, H + 2 * HL, j, h);                 // skip concat [h, inputs]
-    gemm_rows(acc, a.w + SO3_OFF_W3 + SO3_W * SO3_W, SO3_W, SO3_IN, X, j, h);
+    gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, H + 2 * HL, j, h, true);  // skip concat [h, inputs]
+    gemm_ring(acc, ring, tid, stream, SO3_IN, SO3_W, X, j, h, true);
     relu_bias_store(acc, bias + 3 * SO3_W, H + 3 * HL, j, h);
     __syncthreads();
     const float* H4 = H + 3 * HL;
@@ -355,14 +399,14 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     wgrad_rows(acc, X, SO3_IN, a.gw + SO3_OFF_W3 + SO3_W * SO3_W, j, h);
     store_rows(acc, D, j, h);
     __syncthreads();
-    if (j < SO3_IN / 2) {                                    // gradient wrt the skip-concatenated encoding
+    {                                                        // gradient wrt the skip-concatenated encoding
       float ax[2][16];
       zero_acc(ax);
-      gemm_rows(ax, a.wt + SO3T_OFF_3B, SO3_IN, SO3_W, D, j, h);
-      store_rows(ax, DX, j, h);
+      gemm_ring(ax, ring, tid, stream, SO3_W, SO3_IN, D, j, h, j < SO3_IN / 2);
+      if (j < SO3_IN / 2) store_rows(ax, DX, j, h);
     }
     zero_acc(acc);
-    gemm_rows(acc, a.wt + SO3T_OFF_3A, SO3_W, SO3_W, D, j, h);
+    gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, D, j, h, true);
     relu_mask(acc, H + 2 * HL, j, h);                        // dZ3
     __syncthreads();                                         // D has been read by everyone
     // ---- Dense_2 (input H2)
@@ -371,7 +415,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     store_rows(acc, D, j, h);
     __syncthreads();
     zero_acc(acc);
-    gemm_rows(acc, a.wt + SO3T_OFF_2, SO3_W, SO3_W, D, j, h);
+    gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, D, j, h, true);
     relu_mask(acc, H + HL, j, h);                            // dZ2
     __syncthreads();
     // ---- Dense_1 (input H1)
@@ -380,7 +424,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     store_rows(acc, D, j, h);
     __syncthreads();
     zero_acc(acc);
-    gemm_rows(acc, a.wt + SO3T_OFF_1, SO3_W, SO3_W, D, j, h);
+    gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, D, j, h, true);
     relu_mask(acc, H, j, h);                                 // dZ1
     __syncthreads();
     // ---- Dense_0 (input X)
@@ -388,16 +432,19 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     wgrad_rows(acc, X, SO3_IN, a.gw, j, h);
     store_rows(acc, D, j, h);
     __syncthreads();
-    if (j < SO3_IN / 2) {
+    {
       float ax[2][16];
+      zero_acc(ax);
+      if (j < SO3_IN / 2) {
 #pragma unroll
-      for (int n = 0; n < 2; ++n) {                          // continue from the skip part (own rows / columns)
-        const float4* o = reinterpret_cast<const float4*>(DX + (2 * j + n) * BW_RP + 16 * h);
+        for (int n = 0; n < 2; ++n) {                        // continue from the skip part (own rows / columns)
+          const float4* o = reinterpret_cast<const float4*>(DX + (2 * j + n) * BW_RP + 16 * h);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const float4 x = o[q]; ax[n][4 * q] = x.x; ax[n][4 * q + 1] = x.y; ax[n][4 * q + 2] = x.z; ax[n][4 * q + 3] = x.w; }
+          for (int q = 0; q < 4; ++q) { const float4 x = o[q]; ax[n][4 * q] = x.x; ax[n][4 * q + 1] = x.y; ax[n][4 * q + 2] = x.z; ax[n][4 * q + 3] = x.w; }
+        }
       }
-      gemm_rows(ax, a.wt + SO3T_OFF_0, SO3_IN, SO3_W, D, j, h);
-      store_rows(ax, DX, j, h);
+      gemm_ring(ax, ring, tid, stream, SO3_W, SO3_IN, D, j, h, j < SO3_IN / 2);
+      if (j < SO3_IN / 2) store_rows(ax, DX, j, h);
     }
     __syncthreads();
     // ---- encoding backward: d/dp_c of sin(2^k p_c [+ pi/2]) w_k
@@ -427,8 +474,11 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) march_all_bwd_kernel(
     float* __restrict__ d_viewdirs) {
   extern __shared__ __align__(16) float sm[];
   int* cnt = reinterpret_cast<int*>(sm + BW_ACT_FLOATS);
-  int16_t* kmap = reinterpret_cast<int16_t*>(cnt + 4);       // march step -> coarse sample index, or -1
+  float* ring_mem = sm + BW_ACT_FLOATS + 4 + 2 * BW_RING_SLOTS;          // after cnt (16 B) and the mbarriers (8 B each)
+  int16_t* kmap = reinterpret_cast<int16_t*>(ring_mem + BW_RING_SLOTS * SO3_SLOT_FLOATS);   // march step -> coarse sample, or -1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  So3Ring ring;
+  ring_init(ring, ring_mem, cnt + 4, BW_RING_SLOTS, tid);
   for (int i = tid; i < n_steps; i += MARCH_THREADS) kmap[i] = -1;
   __syncthreads();
   int k_last = 0;
@@ -453,7 +503,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) march_all_bwd_kernel(
       const float dG[3] = {step * lv[0], step * lv[1], step * lv[2]};
       float dg[3] = {dG[0], dG[1], dG[2]}, dpm[3] = {0.f, 0.f, 0.f};
       const bool act = live && sqrtf(sumsq3(g[0], g[1], g[2])) > 1e-3f;     // the forward's test, on the same bits
-      if (__syncthreads_or(act)) so3_fwd_bwd(so3, sm, cnt, warp, lane, act, p, g, dG, dg, dpm);
+      if (__syncthreads_or(act)) so3_fwd_bwd(so3, sm, cnt, ring, warp, lane, act, p, g, dG, dg, dpm);
 #pragma unroll
       for (int i = 0; i < 3; ++i) lv[i] = fmaf(hn, lp[i], lv[i]);
       lp[0] += jx.x * dn + jx.y * dg[0] + jx.z * dg[1] + jx.w * dg[2] + dpm[0];
@@ -473,6 +523,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) march_all_bwd_kernel(
       lp[0] += __ldg(gp); lp[1] += __ldg(gp + 1); lp[2] += __ldg(gp + 2);
     }
   }
+  ring_drain(ring);                              // weight chunks fetched ahead for an evaluation that never came
   if (live) {                                    // p_0 = o + near d, v_0 = d
     if (d_origins != nullptr) { d_origins[3 * ray] = lp[0]; d_origins[3 * ray + 1] = lp[1]; d_origins[3 * ray + 2] = lp[2]; }
     if (d_viewdirs != nullptr) {
@@ -519,7 +570,8 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   So3BwdArgs a;
   a.w = so3_w; a.wt = so3_wt; a.gw = g_so3;
   for (int k = 0; k < 10; ++k) a.window[k] = (float)so3_window[k];
-  const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 16 + (((size_t)n_steps * 2 + 15) & ~(size_t)15);
+  const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 16 + 8 * BW_RING_SLOTS + (size_t)BW_RING_SLOTS * SO3_SLOT_FLOATS * 4 +
+                     (((size_t)n_steps * 2 + 15) & ~(size_t)15);
   RNERF_REQUIRE(dyn <= 227 * 1024, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps too large for the step map in shared memory");
   cudaError_t e = cudaFuncSetAttribute(march_all_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(march_all_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

@@ -1,6 +1,7 @@
 // Definitions shared by the forward march (march.cu) and its adjoint (march_bwd.cu).
 #pragma once
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace rnerf {
 
@@ -49,6 +50,79 @@ struct So3Args {
   float window[10];      // cosine-easing window of annealed_pos_enc (rnerf/model_utils.py:236-245) per octave
 };
 
+
+// ---- packed fp32 pairs (SASS: FFMA2) -------------------------------------------------------------------------------------
+// A three-register FFMA issues every other cycle per scheduler on this part; the packed form does two IEEE fmas per
+// issue, so the so3 GEMM loops keep their accumulators as column pairs.  Per-lane results equal fmaf's bit for bit.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// ---- TMA-fed weight ring -------------------------------------------------------------------------------------------
+// The so3 weight matrices are streamed L2 -> shared memory in chunks of <= SO3_CH rows by the TMA engine
+// (cp.async.bulk, one elected thread, completion on one mbarrier per slot); the FMA loops read them with conflict-free
+// LDS.  The chunk sequence of an evaluation is fixed and periodic, so the ring simply keeps running: chunk number g
+// (counted over the whole kernel) lives in slot g % n_slots and is chunk g % period of the stream.  While chunk g is
+// consumed, chunks g+1 .. g+n_slots-1 are in flight -- across evaluation boundaries too, so the next evaluation finds
+// its first chunks already resident.  Slot reuse is ordered by the block barrier every chunk starts with.
+constexpr int SO3_CH = 16;                                   // rows per chunk
+constexpr int SO3_SLOT_FLOATS = SO3_CH * SO3_W;              // 8 KB slots
+constexpr int SO3_MAX_SLOTS = 16;
+
+struct So3Ring {
+  float* slots;          // [n_slots][SO3_SLOT_FLOATS]
+  uint32_t slots_s;      // the same, as a shared-window address
+  uint32_t bars_s;       // n_slots mbarriers (8 bytes each)
+  int n_slots;
+  uint32_t pos;          // chunks consumed so far (uniform over the CTA)
+  bool primed;           // chunks pos .. pos + n_slots - 2 have been issued
+};
+
+// thread 0 initialises the barriers; the caller must __syncthreads() before first use
+__device__ __forceinline__ void ring_init(So3Ring& r, float* slots, void* bars, int n_slots, int tid) {
+  r.slots = slots; r.slots_s = smem_u32(slots); r.bars_s = smem_u32(bars); r.n_slots = n_slots; r.pos = 0; r.primed = false;
+  if (tid == 0) {
+    for (int i = 0; i < n_slots; ++i) mbar_init(r.bars_s + 8 * i, 1);
+    fence_barrier_init();
+  }
+}
+// thread 0 only: start the copy of global chunk number g; `stream(g, src, bytes)` names its source
+template <class Stream>
+__device__ __forceinline__ void ring_issue(const So3Ring& r, uint32_t g, const Stream& stream) {
+  const float* src; uint32_t bytes;
+  stream(g, src, bytes);
+  const uint32_t slot = g % (uint32_t)r.n_slots, bar = r.bars_s + 8 * slot;
+  mbar_arrive_expect_tx(bar, bytes);
+  tma_bulk_g2s(r.slots_s + slot * (SO3_SLOT_FLOATS * 4), src, bytes, bar);
+}
+// every thread, at the start of an evaluation
+template <class Stream>
+__device__ __forceinline__ void ring_prime(So3Ring& r, int tid, const Stream& stream) {
+  if (!r.primed) {
+    if (tid == 0)
+      for (int i = 0; i < r.n_slots - 1; ++i) ring_issue(r, r.pos + i, stream);
+    r.primed = true;
+  }
+}
+// every thread, once per chunk: waits for chunk r.pos, frees the slot of chunk r.pos - 1 (block barrier), refills it, and
+// returns the chunk's data.  The caller consumes the chunk and then does ++r.pos.
+template <class Stream>
+__device__ __forceinline__ const float* ring_acquire(So3Ring& r, int tid, const Stream& stream) {
+  const uint32_t g = r.pos, slot = g % (uint32_t)r.n_slots;
+  mbar_wait(r.bars_s + 8 * slot, (g / (uint32_t)r.n_slots) & 1u);
+  __syncthreads();                 // everyone is done with chunk g-1 (and sees the activations written before this point)
+  if (tid == 0) ring_issue(r, g + r.n_slots - 1, stream);
+  return r.slots + slot * SO3_SLOT_FLOATS;
+}
+// every thread, before the kernel exits: the copies issued ahead must have landed
+__device__ __forceinline__ void ring_drain(So3Ring& r) {
+  if (r.primed)
+    for (int i = 0; i < r.n_slots - 1; ++i) {
+      const uint32_t g = r.pos + i;
+      mbar_wait(r.bars_s + 8 * (g % (uint32_t)r.n_slots), (g / (uint32_t)r.n_slots) & 1u);
+    }
+}
 
 // verified reciprocal of a grid pitch for div_by_const, or 0 (march.cu)
 float recip_for(float d, cudaStream_t st);

@@ -11,6 +11,7 @@ ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", ty
 ap.add_argument("--batch", type=int, default=4096, help="global batch (rays per step over all GPUs)")
 ap.add_argument("--grid", type=int, default=512)
 ap.add_argument("--eager", action="store_true", help="no CUDA-graph capture of the step")
+ap.add_argument("--stage", default="radiance", help='"radiance" (configs[2]) or "all" (so3_mlp trained through the scan adjoint)')
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -25,7 +26,7 @@ n = ops.grid_blur(synthetic.rescale_ior(data, "ship_skydome"), ndim, 9, 3.0)
 del data
 args = utils.Flags(config="ship_skydome-bkgd_no-partial-reflect_cycles", num_path_samples=12, white_bkgd=False,
                    use_online_sparsity=False, bg_weight=0.025, bg_smooth_weight=1.0, bg_patch_size=128, randomized=True,
-                   max_steps=200000, lr_delay_steps=2500, lr_delay_mult=0.01)
+                   max_steps=200000, lr_delay_steps=2500, lr_delay_mult=0.01, stage=a.stage)
 model, variables = models.construct_nerf(0, None, args, ndim, nmin, nmax, n)
 state = train.TrainState.create(variables, args)
 B = a.batch // world
@@ -68,7 +69,7 @@ if world > 1:
 if rank == 0:
     print(json.dumps({"metric": "training rays/sec (fwd+bwd+allreduce+Adam)", "value": a.batch * a.steps / (ms * 1e-3),
                       "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-                      "scaling": "strong", "global_batch": a.batch, "cuda_graph": not a.eager, "gpu_launches": int(_lib.launch_count() + state.replayed_kernel_launches() - l0),
+                      "scaling": "strong", "global_batch": a.batch, "stage": a.stage, "cuda_graph": not a.eager, "gpu_launches": int(_lib.launch_count() + state.replayed_kernel_launches() - l0),
                       "loss": float(stats["loss"]), "cpu_issue_ms_per_step": cpu_issue_ms, "config": "ship_skydome training step, S=768, G=%d, 64+192 samples, "
                       "bg_weight 0.025, bg_smooth 1.0 on a 128x128 env patch" % G}))
 if world > 1:
