@@ -109,6 +109,24 @@ def bkgd_color(model, variables: Dict, viewdirs: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- "all"-stage march (a4-a7, trainable so3_mlp)
+SO3_SORT_MAX_RAYS = 16384
+
+
+def _activity_order(model, origins, viewdirs):
+    """Permutation that groups rays by the march steps at which they need so3_mlp (first and last step with |grad n| > 1e-3,
+    found by a radiance-stage march: the entry step is not affected by the rotation).  A CTA of the so3 kernels
+    evaluates the MLP at the union of its rays' active steps, so a batch of random pixels costs every CTA nearly the whole
+    active range; sorted, CTAs of rays that miss the object do none and the others only their own short range."""
+    path = ops.march(model.table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
+                     model.num_march_steps, bricks=model.bricks, compact=False, t_col=False)
+    act = path.rec[..., 8:11].norm(dim=-1) > 1e-3
+    S = act.shape[1]
+    k = torch.arange(S, device=act.device)
+    first = torch.where(act, k, S).amin(dim=1)
+    last = torch.where(act, k, -1).amax(dim=1)
+    return torch.argsort(first * (S + 1) + last + 1)
+
+
 class _MarchAll(torch.autograd.Function):
     """PathSampler + coarse selection with so3_mlp in the loop.  Differentiable outputs: pos_c, dir_c (the only way a
     loss reaches the scan: ray_dist is stop_gradient, rnerf/eikonal_utils.py:120, and so are the fine samples,
@@ -116,19 +134,33 @@ class _MarchAll(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, sink, w, window, origins, viewdirs, jitter, compact, *params):
+        import os
+        perm = None
+        if 256 < origins.shape[0] <= SO3_SORT_MAX_RAYS and os.environ.get("RNERF_SO3_SORT", "1") != "0":
+            perm = _activity_order(model, origins, viewdirs)
+            origins, viewdirs = origins[perm].contiguous(), viewdirs[perm].contiguous()
         path = ops.march(model.table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
                          model.num_march_steps, bricks=model.bricks, compact=compact, so3=(w, window))
         pos_c, dir_c, t_c, _ = ops.select(path, jitter)
         ctx.model, ctx.sink, ctx.window = model, sink, window
-        ctx.save_for_backward(w, path.rec, jitter)
-        ctx.mark_non_differentiable(t_c, path.rec, path.t)
-        return pos_c, dir_c, t_c, path.rec, path.t
+        rec, t_col = path.rec, path.t
+        if perm is not None:                  # hand everything back in the caller's ray order; the sweep keeps the sorted copy
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(perm.numel(), device=perm.device)
+            pos_c, dir_c, t_c, rec, t_col = pos_c[inv], dir_c[inv], t_c[inv], rec[inv], t_col[inv]
+        ctx.save_for_backward(w, path.rec, jitter, perm if perm is not None else jitter.new_empty(0))
+        ctx.mark_non_differentiable(t_c, rec, t_col)
+        return pos_c, dir_c, t_c, rec, t_col
 
     @staticmethod
     def backward(ctx, d_pos_c, d_dir_c, _dt, _drec, _dtcol):
-        w, rec, jitter = ctx.saved_tensors
+        w, rec, jitter, perm = ctx.saved_tensors
         m = ctx.model
-        z = lambda g: torch.zeros(rec.shape[0], jitter.numel(), 3, device=rec.device) if g is None else g
+
+        def z(g):
+            g = torch.zeros(rec.shape[0], jitter.numel(), 3, device=rec.device) if g is None else g
+            return g[perm] if perm.numel() else g
+
         g, _, _ = ops.march_all_bwd(m.table, m.ndim, m.nmin, m.nmax, rec, m.near, m.far, jitter, z(d_pos_c), z(d_dir_c),
                                     (w, ctx.window), bricks=m.bricks, g_so3=ctx.sink)
         if ctx.sink is not None:

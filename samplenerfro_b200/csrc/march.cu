@@ -292,14 +292,17 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
                                                               float near, float step, int n_steps,
                                                               float4* __restrict__ path, float* __restrict__ t_col,
                                                               const float* __restrict__ bricks, int dbg, const So3Args so3,
-                                                              int so3_slots) {
+                                                              int so3_slots, int rays_per_cta) {
   extern __shared__ __align__(16) float so3_scratch[];     // SO3 only: so3_smem_bytes(so3_slots)
   constexpr int F4_PER_FLUSH = STEPS_PER_FLUSH * RECF4;   // float4 per ray per flush: 8 (compact) / 12 (full)
   constexpr int PITCH = F4_PER_FLUSH + 1;                  // +1 float4 pad: conflict-free column writes
   __shared__ float4 stage[MARCH_THREADS / 32][32 * PITCH];
   __shared__ float tstage[MARCH_THREADS / 32][T_FLUSH * 32];        // ray_dist of the last <= 16 steps, [step][lane]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t warp_ray0 = (blockIdx.x * (int64_t)MARCH_THREADS) + warp * 32;
+  // SO3, small launches: a CTA may carry fewer than 128 rays (rays_per_cta = 32 or 64) so that a training batch spreads
+  // over all SMs and a CTA evaluates the MLP only at the steps its own few rays need; the warps without rays still take
+  // part in every evaluation (warp_ray0 = n_rays: not live, nothing staged or flushed)
+  const int64_t warp_ray0 = (SO3 && warp * 32 >= rays_per_cta) ? n_rays : (blockIdx.x * (int64_t)(SO3 ? rays_per_cta : MARCH_THREADS)) + warp * 32;
   if (!SO3 && warp_ray0 >= n_rays) return;      // SO3: every warp stays for the block barriers of so3_eval
   So3Ring ring;
   if (SO3) {
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
   float px = add(ox, mul(near, vx)), py = add(oy, mul(near, vy)), pz = add(oz, mul(near, vz));
   float t = near;
   float4* my_stage = &stage[warp][lane * PITCH];
-  const int rays_here = (int)min((int64_t)32, n_rays - warp_ray0);
+  const int rays_here = (int)max((int64_t)0, min((int64_t)32, n_rays - warp_ray0));
   const int ray_stride4 = n_steps * RECF4;                            // float4 units between consecutive rays
   const bool t_vec = t_col != nullptr && (n_steps & 3) == 0 && (reinterpret_cast<uintptr_t>(t_col) & 15u) == 0;
   float* ts = tstage[warp];
@@ -462,6 +465,14 @@ static bool fast_div_enabled() {
   return !(e != nullptr && strcmp(e, "ieee") == 0);
 }
 
+// rays per CTA of the so3 kernels (forward and reverse sweep agree): 128, or fewer when that still leaves SMs idle
+int rnerf::so3_rays_per_cta(int64_t n_rays, int n_sm) {
+  int rpc = n_rays <= (int64_t)32 * n_sm ? 32 : (n_rays <= (int64_t)64 * n_sm ? 64 : MARCH_THREADS);
+  const char* e = getenv("RNERF_SO3_RPC");      // development aid
+  if (e != nullptr && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128)) rpc = atoi(e);
+  return rpc;
+}
+
 bool rnerf::make_march_geom(const int ndim[3], const double nmin[3], const double nmax[3], cudaStream_t st, MarchGeom& mg) {
   mg.g = make_geom(ndim, nmin, nmax);
   mg.nby = (ndim[1] + BRICK - 1) >> BRICK_LOG2;
@@ -493,7 +504,8 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
   const float step = (float)((far - near) / (n_steps - 1));
   const char* dbg_env = getenv("RNERF_MARCH_DEBUG");   // development aid: 1 = no record stores, 2 = no t stores, 4 = plain stores
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
-  const unsigned blocks = (unsigned)((n_rays + MARCH_THREADS - 1) / MARCH_THREADS);
+  unsigned blocks = (unsigned)((n_rays + MARCH_THREADS - 1) / MARCH_THREADS);
+  int rpc = MARCH_THREADS;
   So3Args so3;
   memset(&so3, 0, sizeof(so3));
   size_t dyn = 0;
@@ -504,6 +516,8 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    rpc = so3_rays_per_cta(n_rays, n_sm);
+    blocks = (unsigned)((n_rays + rpc - 1) / rpc);
     // Small launches (a training batch) leave at most one CTA per SM: a deep ring (12 chunks = 96 KB in flight) hides
     // the L2 latency alone.  Full frames keep two CTAs per SM (110 KB each) with a 4-slot ring and hide it with the
     // other CTA.  RNERF_SO3_SLOTS overrides (development aid).
@@ -524,7 +538,7 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
   }
 #define RNERF_MARCH_LAUNCH(R, F, A)                                                                                       \
   march_kernel<R, F, A><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
-                                                            step, n_steps, (float4*)path, t_col, bricks, dbg, so3, slots)
+                                                            step, n_steps, (float4*)path, t_col, bricks, dbg, so3, slots, rpc)
   if (so3_w == nullptr) {
     if (rec_floats == 8) { if (fast) RNERF_MARCH_LAUNCH(2, true, false); else RNERF_MARCH_LAUNCH(2, false, false); }
     else                 { if (fast) RNERF_MARCH_LAUNCH(3, true, false); else RNERF_MARCH_LAUNCH(3, false, false); }

@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) march_all_bwd_kernel(
     const float4* __restrict__ table, const MarchGeom mg, const float* __restrict__ bricks, const float4* __restrict__ path,
     int recf4, int64_t n_rays, float near, float step, int n_steps, const int32_t* __restrict__ jitter, int n_coarse,
     const float* __restrict__ d_pos_c, const float* __restrict__ d_dir_c, const So3BwdArgs so3, float* __restrict__ d_origins,
-    float* __restrict__ d_viewdirs) {
+    float* __restrict__ d_viewdirs, int rays_per_cta) {
   extern __shared__ __align__(16) float sm[];
   int* cnt = reinterpret_cast<int*>(sm + BW_ACT_FLOATS);
   float* ring_mem = sm + BW_ACT_FLOATS + 4 + 2 * BW_RING_SLOTS;          // after cnt (16 B) and the mbarriers (8 B each)
@@ -485,8 +485,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) march_all_bwd_kernel(
   for (int i = 0; i < n_coarse; ++i) k_last = max(k_last, min(max(__ldg(jitter + i), 0), n_steps - 1));
   for (int i = tid; i < n_coarse; i += MARCH_THREADS) kmap[min(max(__ldg(jitter + i), 0), n_steps - 1)] = (int16_t)i;
   __syncthreads();
-  const int64_t ray = blockIdx.x * (int64_t)MARCH_THREADS + tid;
-  const bool live = ray < n_rays;
+  const int64_t ray = blockIdx.x * (int64_t)rays_per_cta + tid;      // threads beyond rays_per_cta only help with the MLP
+  const bool live = tid < rays_per_cta && ray < n_rays;
   const int64_t rr = live ? ray : (n_rays - 1);
   const float4* rec = path + rr * (int64_t)n_steps * recf4;
   float lp[3] = {0.f, 0.f, 0.f}, lv[3] = {0.f, 0.f, 0.f};
@@ -576,15 +576,19 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   cudaError_t e = cudaFuncSetAttribute(march_all_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(march_all_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) { set_error("rnerf_march_all_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-  const unsigned blocks = (unsigned)((n_rays + MARCH_THREADS - 1) / MARCH_THREADS);
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int rpc = so3_rays_per_cta(n_rays, n_sm);
+  const unsigned blocks = (unsigned)((n_rays + rpc - 1) / rpc);
   if (fast)
     march_all_bwd_kernel<true><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
                                                                    n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
-                                                                   d_dir_c, a, d_origins, d_viewdirs);
+                                                                   d_dir_c, a, d_origins, d_viewdirs, rpc);
   else
     march_all_bwd_kernel<false><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
                                                                     n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
-                                                                    d_dir_c, a, d_origins, d_viewdirs);
+                                                                    d_dir_c, a, d_origins, d_viewdirs, rpc);
   count_launch();
   return check_launch("rnerf_march_all_bwd");
 }
