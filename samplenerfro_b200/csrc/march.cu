@@ -108,16 +108,21 @@ __device__ __forceinline__ float4 march_lookup(const float4* __restrict__ table,
 // so3_mlp = model_utils.MLP(net_width=128, net_depth=4, skip_layer=2, 3 outputs): 60 -> 128 -> 128 -> 128 (+60) -> 128 -> 3.
 //
 // The `where` makes the MLP irrelevant wherever |grad n| <= 1e-3 (everywhere but the blurred object boundary): a CTA
-// only evaluates it at steps where one of its 128 rays needs it, and only for those rays.  They are compacted (ballot +
+// only evaluates it at steps where one of its rays needs it, and only for those rays.  They are compacted (ballot +
 // per-warp counts) into columns of CTA-wide activation buffers [feature][ray] in shared memory, at most 64 per pass (two
-// groups of 32; more active rays -- rare -- take another pass), and processed by ALL four warps: thread t owns neurons
-// 2j, 2j+1 (j = t mod 64) for one half (t / 64) of every group's rays, i.e. 32 accumulators per group; the layer input is
-// read with broadcast LDS.128, the weights with LDS.64.  The 64-column buffers keep the CTA at 110 KB of shared memory
-// and ~170 registers, so two CTAs share an SM: one can march or evaluate while the other waits on a barrier or a load.
+// groups of 32; more active rays -- rare -- take another pass).  The so3 variant of the kernel runs SO3_THREADS = 256
+// threads: the first 128 carry the rays, all eight warps work on an evaluation (with only the four ray warps the chain
+// ran at 26 % issue utilisation, one warp per scheduler: profiles/r1w).  Thread t owns neurons 2j, 2j+1 (j = t mod 64)
+// for columns 8h .. 8h+7 (h = t / 64) of every group, i.e. 8 packed accumulators per group; the layer input is read with
+// broadcast LDS.128, the weights with LDS.64; the encoding and the 3-wide output layer are spread over the CTA too.
+// 113 KB of shared memory and <= 128 registers keep two CTAs per SM.
 // fp32 on the CUDA cores (the result steers the ray, so no reduced-precision operands).
+constexpr int SO3_THREADS = 256;
 constexpr int SO3_COLS = 64;                                 // active rays per pass
 constexpr int SO3_RP = SO3_COLS + 4;                         // ray pitch of the activation buffers (16-byte aligned rows)
-constexpr int SO3_ACT_FLOATS = (SO3_IN + SO3_W) * SO3_RP;    // X[60][68] + H[128][68]
+constexpr int SO3_OFF_P = (SO3_IN + SO3_W) * SO3_RP;         // X[60][68] + H[128][68], then P[3][68] positions, RAW[3][68] outputs
+constexpr int SO3_OFF_RAW = SO3_OFF_P + 3 * SO3_RP;
+constexpr int SO3_ACT_FLOATS = SO3_OFF_RAW + 3 * SO3_RP;
 
 // The four hidden-layer kernels are contiguous in the weight image: one [504][128] fp32 matrix (60 + 128 + 128 + 188
 // rows).  It is streamed through the TMA-fed shared-memory ring of march_common.cuh in chunks of <= 16 rows that never
@@ -126,8 +131,9 @@ constexpr int SO3_ACT_FLOATS = (SO3_IN + SO3_W) * SO3_RP;    // X[60][68] + H[12
 // L2 -> SM once per CTA evaluation, n_slots - 1 chunks ahead of the FMA loop (also across evaluations: the stream is
 // periodic), and are read with conflict-free LDS.
 constexpr int SO3_NCHUNK = 4 + 8 + 8 + 8 + 4;                // 32
-// dynamic shared memory: activations | per-warp active-ray counts (16 B) | mbarriers (128 B) | ring slots
-constexpr int SO3_OFF_CNT = SO3_ACT_FLOATS * 4, SO3_OFF_BARS = SO3_OFF_CNT + 16, SO3_OFF_RING = SO3_OFF_BARS + 8 * SO3_MAX_SLOTS;
+// dynamic shared memory: activations | per-warp active-ray counts (32 B) | mbarriers (128 B) | ring slots
+constexpr int SO3_OFF_CNT = SO3_ACT_FLOATS * 4, SO3_OFF_BARS = SO3_OFF_CNT + 4 * (SO3_THREADS / 32), SO3_OFF_RING = SO3_OFF_BARS + 8 * SO3_MAX_SLOTS;
+static_assert(SO3_OFF_RING % 16 == 0, "ring slots must be 16-byte aligned");
 static size_t so3_smem_bytes(int n_slots) { return (size_t)SO3_OFF_RING + (size_t)n_slots * SO3_SLOT_FLOATS * 4; }
 
 struct So3Chunk { int row0, rows, in_k0, in_is_x, last_of_layer; };
@@ -166,7 +172,7 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
   const int tid = warp * 32 + lane;
   const So3FwdStream stream{a.w};
   ring_prime(ring, tid, stream);
-  // ---- compaction: active ray -> column idx of the activation buffers
+  // ---- compaction: active ray -> column idx of the activation buffers (only the first MARCH_THREADS threads carry rays)
   const unsigned bal = __ballot_sync(0xffffffffu, act);
   if (lane == 0) cnt[warp] = __popc(bal);
   __syncthreads();
@@ -179,34 +185,31 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
   }
   const int idx = base + __popc(bal & ((1u << lane) - 1u));
   const float* bias = a.w + SO3_OFF_B;
-  const int j = tid & 63, h = tid >> 6;        // neurons 2j, 2j+1; columns 16h .. 16h+15 of every group
+  float* P = dyn_smem + SO3_OFF_P;
+  float* RAW = dyn_smem + SO3_OFF_RAW;
+  const int j = tid & 63, h = tid >> 6;        // neurons 2j, 2j+1; columns 8h .. 8h+7 of every group
   r0 = r1 = r2 = 0.f;
 #pragma unroll 1
   for (int col0 = 0; col0 < n_act; col0 += SO3_COLS) {
-    const int n_groups = (min(SO3_COLS, n_act - col0) + 31) >> 5;   // 1 or 2 groups of 32 columns (unused columns hold garbage)
+    const int n_here = min(SO3_COLS, n_act - col0);
+    const int n_groups = (n_here + 31) >> 5;   // 1 or 2 groups of 32 columns (unused columns hold garbage)
     const bool mine = act && idx >= col0 && idx < col0 + SO3_COLS;
     const int col = idx - col0;
-    if (col0 > 0) __syncthreads();             // another pass: everyone is done with X and Hs of the previous one
-    if (mine) {
-      const float xs[3] = {px, py, pz};
-      const float half_pi = 1.57079632679489661923f;
-      float sc = 1.f;
-#pragma unroll
-      for (int k = 0; k < 10; ++k) {           // feature index k*6 + c (sin), k*6 + 3 + c (sin(x + pi/2)), times window[k]
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float xb = mul(xs[c], sc);
-          X[(k * 6 + c) * SO3_RP + col] = mul(sinf(xb), a.window[k]);
-          X[(k * 6 + 3 + c) * SO3_RP + col] = mul(sinf(add(xb, half_pi)), a.window[k]);
-        }
-        sc *= 2.f;
-      }
+    if (col0 > 0) __syncthreads();             // another pass: everyone is done with the buffers of the previous one
+    if (mine) { P[col] = px; P[SO3_RP + col] = py; P[2 * SO3_RP + col] = pz; }
+    __syncthreads();
+    // ---- encoding, all threads: feature k*6 + c = sin(2^k p_c) w_k, k*6 + 3 + c = sin(2^k p_c + pi/2) w_k
+    for (int e = tid; e < SO3_IN * n_here; e += SO3_THREADS) {
+      const int f = e / n_here, cc = e - f * n_here;
+      const int k = f / 6, q = f - 6 * k, c = q >= 3 ? q - 3 : q;
+      const float xb = mul(P[c * SO3_RP + cc], (float)(1 << k));
+      X[f * SO3_RP + cc] = mul(sinf(q >= 3 ? add(xb, 1.57079632679489661923f) : xb), a.window[k]);
     }
-    f32x2 acc[2][2][8];                        // [group][neuron][column pair]
+    f32x2 acc[2][2][4];                        // [group][neuron][column pair]
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
-      for (int r = 0; r < 8; ++r) { acc[g][0][r] = 0ull; acc[g][1][r] = 0ull; }
+      for (int r = 0; r < 4; ++r) { acc[g][0][r] = 0ull; acc[g][1][r] = 0ull; }
     int layer = 0;
 #pragma unroll 1
     for (int c = 0; c < SO3_NCHUNK; ++c) {
@@ -214,7 +217,7 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
       // last layer) visible
       const float* wbuf = ring_acquire(ring, tid, stream) + 2 * j;
       const So3Chunk k = so3_chunk(c);
-      const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_RP + 16 * h;
+      const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_RP + 8 * h;
 #pragma unroll 4
       for (int r = 0; r < k.rows; ++r) {
         const float2 w = *reinterpret_cast<const float2*>(wbuf + r * SO3_W);
@@ -224,8 +227,8 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
           if (g < n_groups) {
             const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(in + r * SO3_RP + 32 * g);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const ulonglong2 x = xr[q];      // columns 4q, 4q+1 | 4q+2, 4q+3
+            for (int q = 0; q < 2; ++q) {
+              const ulonglong2 x = xr[q];      // columns 4q, 4q+1 | 4q+2, 4q+3 of this thread's eight
               acc[g][0][2 * q] = fma2(w0, x.x, acc[g][0][2 * q]); acc[g][0][2 * q + 1] = fma2(w0, x.y, acc[g][0][2 * q + 1]);
               acc[g][1][2 * q] = fma2(w1, x.x, acc[g][1][2 * q]); acc[g][1][2 * q + 1] = fma2(w1, x.y, acc[g][1][2 * q + 1]);
             }
@@ -239,10 +242,10 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < n_groups) {
-            float4* o0 = reinterpret_cast<float4*>(Hs + (2 * j) * SO3_RP + 32 * g + 16 * h);
-            float4* o1 = reinterpret_cast<float4*>(Hs + (2 * j + 1) * SO3_RP + 32 * g + 16 * h);
+            float4* o0 = reinterpret_cast<float4*>(Hs + (2 * j) * SO3_RP + 32 * g + 8 * h);
+            float4* o1 = reinterpret_cast<float4*>(Hs + (2 * j + 1) * SO3_RP + 32 * g + 8 * h);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 2; ++q) {
               float a0, a1, a2, a3;
               unpack2(acc[g][0][2 * q], a0, a1); unpack2(acc[g][0][2 * q + 1], a2, a3);
               o0[q] = make_float4(fmaxf(a0 + b0, 0.f), fmaxf(a1 + b0, 0.f), fmaxf(a2 + b0, 0.f), fmaxf(a3 + b0, 0.f));
@@ -251,22 +254,24 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
             }
           }
 #pragma unroll
-          for (int r = 0; r < 8; ++r) { acc[g][0][r] = 0ull; acc[g][1][r] = 0ull; }
+          for (int r = 0; r < 4; ++r) { acc[g][0][r] = 0ull; acc[g][1][r] = 0ull; }
         }
         ++layer;
       }
     }
     __syncthreads();                           // Dense_3 output visible
-    if (mine) {
+    {                                          // Dense_4: raw[m][column], one thread per output
       const float* W4 = a.w + SO3_OFF_W4;
-      const float* b4 = bias + 4 * SO3_W;
-      r0 = __ldg(b4); r1 = __ldg(b4 + 1); r2 = __ldg(b4 + 2);
-#pragma unroll 4
-      for (int k = 0; k < SO3_W; ++k) {        // Dense_4: this thread's own ray
-        const float hv = Hs[k * SO3_RP + col];
-        r0 = fmaf(hv, __ldg(W4 + 3 * k), r0); r1 = fmaf(hv, __ldg(W4 + 3 * k + 1), r1); r2 = fmaf(hv, __ldg(W4 + 3 * k + 2), r2);
+      for (int e = tid; e < 3 * n_here; e += SO3_THREADS) {
+        const int m = e / n_here, cc = e - m * n_here;
+        float r = __ldg(bias + 4 * SO3_W + m);
+#pragma unroll 8
+        for (int k = 0; k < SO3_W; ++k) r = fmaf(Hs[k * SO3_RP + cc], __ldg(W4 + 3 * k + m), r);
+        RAW[m * SO3_RP + cc] = r;
       }
     }
+    __syncthreads();
+    if (mine) { r0 = RAW[col]; r1 = RAW[SO3_RP + col]; r2 = RAW[2 * SO3_RP + col]; }
   }
 }
 
@@ -286,7 +291,7 @@ __device__ __forceinline__ void so3_rotate(float r0, float r1, float r2, float& 
 }
 
 template <int RECF4, bool FAST, bool SO3>
-__global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const float4* __restrict__ table, const MarchGeom mg,
+__global__ void __launch_bounds__(SO3 ? SO3_THREADS : MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const float4* __restrict__ table, const MarchGeom mg,
                                                               const float* __restrict__ origins,
                                                               const float* __restrict__ viewdirs, int64_t n_rays,
                                                               float near, float step, int n_steps,
@@ -302,7 +307,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
   // SO3, small launches: a CTA may carry fewer than 128 rays (rays_per_cta = 32 or 64) so that a training batch spreads
   // over all SMs and a CTA evaluates the MLP only at the steps its own few rays need; the warps without rays still take
   // part in every evaluation (warp_ray0 = n_rays: not live, nothing staged or flushed)
-  const int64_t warp_ray0 = (SO3 && warp * 32 >= rays_per_cta) ? n_rays : (blockIdx.x * (int64_t)(SO3 ? rays_per_cta : MARCH_THREADS)) + warp * 32;
+  const bool carrier = !SO3 || warp * 32 < rays_per_cta;        // warp-uniform; the other warps only join the evaluations
+  const int64_t warp_ray0 = !carrier ? n_rays : (blockIdx.x * (int64_t)(SO3 ? rays_per_cta : MARCH_THREADS)) + warp * 32;
   if (!SO3 && warp_ray0 >= n_rays) return;      // SO3: every warp stays for the block barriers of so3_eval
   So3Ring ring;
   if (SO3) {
@@ -317,11 +323,12 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
   float vx = viewdirs[3 * rr], vy = viewdirs[3 * rr + 1], vz = viewdirs[3 * rr + 2];
   float px = add(ox, mul(near, vx)), py = add(oy, mul(near, vy)), pz = add(oz, mul(near, vz));
   float t = near;
-  float4* my_stage = &stage[warp][lane * PITCH];
+  const int sw = carrier ? warp : 0;            // (non-carrier warps never touch the staging buffers)
+  float4* my_stage = &stage[sw][lane * PITCH];
   const int rays_here = (int)max((int64_t)0, min((int64_t)32, n_rays - warp_ray0));
   const int ray_stride4 = n_steps * RECF4;                            // float4 units between consecutive rays
   const bool t_vec = t_col != nullptr && (n_steps & 3) == 0 && (reinterpret_cast<uintptr_t>(t_col) & 15u) == 0;
-  float* ts = tstage[warp];
+  float* ts = tstage[sw];
   const bool want_t = t_col != nullptr && !(dbg & 2);
 
   // cooperative flush mapping, fixed per thread: element e = it*32 + lane -> (ray e / F4, float4 e % F4)
@@ -336,19 +343,22 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
     s_off[m] = r * PITCH + j;
     g_off[m] = r * ray_stride4 + j;
   }
-  const float4* s_rd = stage[warp];
+  const float4* s_rd = stage[sw];
   float4* g_wr = path + warp_ray0 * (int64_t)ray_stride4;             // advanced by F4_PER_FLUSH per flush
   const int round_stride4 = RAYS_PER_ROUND * ray_stride4;
 
   // one eikonal step: emit the record of the current state, then advance it
   auto one_step = [&](int kk, int trow) {
-    const float4 c = march_lookup<FAST>(table, mg, bricks, px, py, pz);  // (n, gx, gy, gz) at the pre-update position
-    // the direction is stored un-normalised; readers apply safe_l2_normalize (path_dir()) to the few records they
-    // use, which keeps 3 IEEE divides + 1 sqrt per step out of the march loop
-    my_stage[kk * RECF4 + 0] = make_float4(px, py, pz, t);
-    my_stage[kk * RECF4 + 1] = make_float4(vx, vy, vz, c.x);
-    if (RECF4 == 3) my_stage[kk * RECF4 + 2] = make_float4(c.y, c.z, c.w, 0.f);
-    ts[(trow + kk) * 32 + lane] = t;
+    float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (carrier) {
+      c = march_lookup<FAST>(table, mg, bricks, px, py, pz);                // (n, gx, gy, gz) at the pre-update position
+      // the direction is stored un-normalised; readers apply safe_l2_normalize (path_dir()) to the few records they
+      // use, which keeps 3 IEEE divides + 1 sqrt per step out of the march loop
+      my_stage[kk * RECF4 + 0] = make_float4(px, py, pz, t);
+      my_stage[kk * RECF4 + 1] = make_float4(vx, vy, vz, c.x);
+      if (RECF4 == 3) my_stage[kk * RECF4 + 2] = make_float4(c.y, c.z, c.w, 0.f);
+      ts[(trow + kk) * 32 + lane] = t;
+    }
     float gx = c.y, gy = c.z, gz = c.w;
     if (SO3) {
       const bool act = live && sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;     // jnp.linalg.norm(idx_grad) > 1e-3
@@ -358,11 +368,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
         if (act) so3_rotate(r0, r1, r2, gx, gy, gz);
       }
     }
-    const float s = divf(step, c.x);
-    const float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
-    vx = add(vx, mul(step, gx)); vy = add(vy, mul(step, gy)); vz = add(vz, mul(step, gz));
-    t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
-    px = nx; py = ny; pz = nz;
+    if (carrier) {
+      const float s = divf(step, c.x);
+      const float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
+      vx = add(vx, mul(step, gx)); vy = add(vy, mul(step, gy)); vz = add(vz, mul(step, gz));
+      t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
+      px = nx; py = ny; pz = nz;
+    }
   };
 
   for (int k0 = 0; k0 < n_steps; k0 += STEPS_PER_FLUSH) {
@@ -376,6 +388,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, SO3 ? 2 : 8) march_kernel(const
       for (int kk = 0; kk < STEPS_PER_FLUSH; ++kk)
         if (kk < nk) one_step(kk, trow);
     }
+    if (!carrier) continue;                      // nothing staged, nothing to flush
     __syncwarp();
     if (want_t && (trow + nk == T_FLUSH || k0 + nk >= n_steps)) {
       // dense t column: lanes 4r..4r+3 write the 16 staged steps of ray r as four float4 (64 B, sector-complete)
@@ -537,7 +550,7 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
     }
   }
 #define RNERF_MARCH_LAUNCH(R, F, A)                                                                                       \
-  march_kernel<R, F, A><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
+  march_kernel<R, F, A><<<blocks, (A) ? SO3_THREADS : MARCH_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
                                                             step, n_steps, (float4*)path, t_col, bricks, dbg, so3, slots, rpc)
   if (so3_w == nullptr) {
     if (rec_floats == 8) { if (fast) RNERF_MARCH_LAUNCH(2, true, false); else RNERF_MARCH_LAUNCH(2, false, false); }

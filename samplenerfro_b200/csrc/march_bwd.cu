@@ -35,7 +35,9 @@ constexpr int BW_OFF_H = BW_OFF_X + SO3_IN * BW_RP;             // H  [4][128][R
 constexpr int BW_OFF_D = BW_OFF_H + 4 * SO3_W * BW_RP;          // D  [128][RP]  dZ of the layer being processed
 constexpr int BW_OFF_DX = BW_OFF_D + SO3_W * BW_RP;             // DX [60][RP]   gradient wrt the encoding
 constexpr int BW_OFF_R = BW_OFF_DX + SO3_IN * BW_RP;            // R  [4][RP]    d raw (3 rows used)
-constexpr int BW_ACT_FLOATS = BW_OFF_R + 4 * BW_RP;
+constexpr int BW_OFF_P = BW_OFF_R + 4 * BW_RP;              // P  [4][RP]    column positions, then d p through the encoding
+constexpr int BW_OFF_RAW = BW_OFF_P + 4 * BW_RP;            // RAW [4][RP]   so3_mlp output
+constexpr int BW_ACT_FLOATS = BW_OFF_RAW + 4 * BW_RP;
 constexpr int SO3T_OFF_0 = 0, SO3T_OFF_1 = SO3_W * SO3_IN, SO3T_OFF_2 = SO3T_OFF_1 + SO3_W * SO3_W,
               SO3T_OFF_3A = SO3T_OFF_2 + SO3_W * SO3_W, SO3T_OFF_3B = SO3T_OFF_3A + SO3_W * SO3_W,
               SO3T_FLOATS = SO3T_OFF_3B + SO3_W * SO3_IN;
@@ -179,71 +181,68 @@ struct So3BwdStream {
   }
 };
 
-// acc[n][c] += sum_{r < K} W[r][2j + n] * In[r][16h + c]: W ([K][wp], K <= 128) arrives as the next ceil(K/16) chunks of the
+// Thread layout of the cooperative chain: BW_THREADS = 512 (16 warps: four per scheduler, so LDS / barrier latencies of one
+// warp hide under the FFMA2s of the others -- with 4 warps the chain ran at 13 % issue utilisation, profiles/r1w).  Thread t
+// owns neurons 2j, 2j+1 (j = t mod 64) for the BW_CPT = 4 columns 4h .. 4h+3 (h = t / 64) in the forward and input-gradient
+// GEMMs; in the weight-gradient loops it owns the same neurons for ALL 32 columns on the rows r = h (mod 8), so every
+// gW element is reduced by exactly one red per evaluation.
+constexpr int BW_THREADS = 512;
+constexpr int BW_H = BW_THREADS / 64;          // 8 column groups / row residues
+constexpr int BW_CPT = BW_COLS / BW_H;         // 4 columns per thread
+
+// acc[n][c] += sum_{r < K} W[r][2j + n] * In[r][4h + c]: W ([K][wp], K <= 128) arrives as the next ceil(K/16) chunks of the
 // ring.  Every thread of the CTA runs the chunk loop (block barrier per chunk); `work` = this thread owns output rows.
-__device__ __forceinline__ void gemm_ring(float (&acc)[2][16], So3Ring& ring, int tid, const So3BwdStream& stream, int K, int wp,
+__device__ __forceinline__ void gemm_ring(float (&acc)[2][BW_CPT], So3Ring& ring, int tid, const So3BwdStream& stream, int K, int wp,
                                           const float* __restrict__ In, int j, int h, bool work) {
-  const float* in = In + 16 * h;
-  f32x2 a2[2][8];                                // column pairs (SASS: FFMA2)
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { a2[0][q] = pack2(acc[0][2 * q], acc[0][2 * q + 1]); a2[1][q] = pack2(acc[1][2 * q], acc[1][2 * q + 1]); }
+  const float* in = In + BW_CPT * h;
+  f32x2 a00 = pack2(acc[0][0], acc[0][1]), a01 = pack2(acc[0][2], acc[0][3]);
+  f32x2 a10 = pack2(acc[1][0], acc[1][1]), a11 = pack2(acc[1][2], acc[1][3]);
 #pragma unroll 1
   for (int k0 = 0; k0 < K; k0 += SO3_CH) {
     const float* wq = ring_acquire(ring, tid, stream) + 2 * j;
     const int rows = min(SO3_CH, K - k0);
     if (work) {
-#pragma unroll 4
+#pragma unroll 8
       for (int r = 0; r < rows; ++r) {
         const float2 w = *reinterpret_cast<const float2*>(wq + r * wp);
         const f32x2 w0 = pack2(w.x, w.x), w1 = pack2(w.y, w.y);
-        const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(in + (k0 + r) * BW_RP);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const ulonglong2 x = xr[q];
-          a2[0][2 * q] = fma2(w0, x.x, a2[0][2 * q]); a2[0][2 * q + 1] = fma2(w0, x.y, a2[0][2 * q + 1]);
-          a2[1][2 * q] = fma2(w1, x.x, a2[1][2 * q]); a2[1][2 * q + 1] = fma2(w1, x.y, a2[1][2 * q + 1]);
-        }
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(in + (k0 + r) * BW_RP);
+        a00 = fma2(w0, x.x, a00); a01 = fma2(w0, x.y, a01);
+        a10 = fma2(w1, x.x, a10); a11 = fma2(w1, x.y, a11);
       }
     }
     ++ring.pos;
   }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { unpack2(a2[0][q], acc[0][2 * q], acc[0][2 * q + 1]); unpack2(a2[1][q], acc[1][2 * q], acc[1][2 * q + 1]); }
+  unpack2(a00, acc[0][0], acc[0][1]); unpack2(a01, acc[0][2], acc[0][3]);
+  unpack2(a10, acc[1][0], acc[1][1]); unpack2(a11, acc[1][2], acc[1][3]);
 }
 
-__device__ __forceinline__ void zero_acc(float (&acc)[2][16]) {
+__device__ __forceinline__ void zero_acc(float (&acc)[2][BW_CPT]) {
 #pragma unroll
-  for (int c = 0; c < 16; ++c) { acc[0][c] = 0.f; acc[1][c] = 0.f; }
+  for (int c = 0; c < BW_CPT; ++c) { acc[0][c] = 0.f; acc[1][c] = 0.f; }
 }
 
-// rows 2j, 2j+1 of a [.][RP] buffer, columns 16h .. 16h+15
-__device__ __forceinline__ void store_rows(const float (&acc)[2][16], float* buf, int j, int h) {
+// rows 2j, 2j+1 of a [.][RP] buffer, columns 4h .. 4h+3
+__device__ __forceinline__ void store_rows(const float (&acc)[2][BW_CPT], float* buf, int j, int h) {
 #pragma unroll
-  for (int n = 0; n < 2; ++n) {
-    float4* o = reinterpret_cast<float4*>(buf + (2 * j + n) * BW_RP + 16 * h);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[n][4 * q], acc[n][4 * q + 1], acc[n][4 * q + 2], acc[n][4 * q + 3]);
-  }
+  for (int n = 0; n < 2; ++n)
+    *reinterpret_cast<float4*>(buf + (2 * j + n) * BW_RP + BW_CPT * h) = make_float4(acc[n][0], acc[n][1], acc[n][2], acc[n][3]);
 }
 
-__device__ __forceinline__ void relu_bias_store(float (&acc)[2][16], const float* __restrict__ bias, float* buf, int j, int h) {
+__device__ __forceinline__ void relu_bias_store(float (&acc)[2][BW_CPT], const float* __restrict__ bias, float* buf, int j, int h) {
   const float b0 = __ldg(bias + 2 * j), b1 = __ldg(bias + 2 * j + 1);
 #pragma unroll
-  for (int c = 0; c < 16; ++c) { acc[0][c] = fmaxf(acc[0][c] + b0, 0.f); acc[1][c] = fmaxf(acc[1][c] + b1, 0.f); }
+  for (int c = 0; c < BW_CPT; ++c) { acc[0][c] = fmaxf(acc[0][c] + b0, 0.f); acc[1][c] = fmaxf(acc[1][c] + b1, 0.f); }
   store_rows(acc, buf, j, h);
 }
 
 // dZ = dH where the saved activation is positive
-__device__ __forceinline__ void relu_mask(float (&acc)[2][16], const float* __restrict__ Hl, int j, int h) {
+__device__ __forceinline__ void relu_mask(float (&acc)[2][BW_CPT], const float* __restrict__ Hl, int j, int h) {
 #pragma unroll
   for (int n = 0; n < 2; ++n) {
-    const float4* hr = reinterpret_cast<const float4*>(Hl + (2 * j + n) * BW_RP + 16 * h);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 x = hr[q];
-      acc[n][4 * q] = x.x > 0.f ? acc[n][4 * q] : 0.f;         acc[n][4 * q + 1] = x.y > 0.f ? acc[n][4 * q + 1] : 0.f;
-      acc[n][4 * q + 2] = x.z > 0.f ? acc[n][4 * q + 2] : 0.f; acc[n][4 * q + 3] = x.w > 0.f ? acc[n][4 * q + 3] : 0.f;
-    }
+    const float4 x = *reinterpret_cast<const float4*>(Hl + (2 * j + n) * BW_RP + BW_CPT * h);
+    acc[n][0] = x.x > 0.f ? acc[n][0] : 0.f; acc[n][1] = x.y > 0.f ? acc[n][1] : 0.f;
+    acc[n][2] = x.z > 0.f ? acc[n][2] : 0.f; acc[n][3] = x.w > 0.f ? acc[n][3] : 0.f;
   }
 }
 
@@ -251,28 +250,38 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
-// gb[2j + n] += sum_c dz[n][c];  gW[r][2j + n] += sum_c A[r][16h + c] dz[n][c]  for r < rows   (gW row pitch 128)
-__device__ __forceinline__ void bias_grad(const float (&dz)[2][16], float* gb, int j) {
-  float s0 = 0.f, s1 = 0.f;
+// dZ rows 2j, 2j+1 over all 32 columns, as column pairs, read back from D (published by store_rows + a block barrier)
+struct DzRows { f32x2 d[2][BW_COLS / 2]; };
+__device__ __forceinline__ void load_dz_rows(DzRows& z, const float* __restrict__ D, int j) {
 #pragma unroll
-  for (int c = 0; c < 16; ++c) { s0 += dz[0][c]; s1 += dz[1][c]; }
-  red_add2(gb + 2 * j, s0, s1);
+  for (int n = 0; n < 2; ++n) {
+    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(D + (2 * j + n) * BW_RP);
+#pragma unroll
+    for (int q = 0; q < BW_COLS / 4; ++q) { const ulonglong2 v = row[q]; z.d[n][2 * q] = v.x; z.d[n][2 * q + 1] = v.y; }
+  }
 }
-__device__ __forceinline__ void wgrad_rows(const float (&dz)[2][16], const float* __restrict__ A, int rows, float* gW, int j, int h) {
-  const float* in = A + 16 * h;
-  float* g = gW + 2 * j;
-  f32x2 d2[2][8];
+// gb[2j + n] += sum_c dz[n][c]   (threads with h == 0)
+__device__ __forceinline__ void bias_grad(const DzRows& z, float* gb, int j) {
+  f32x2 s0 = 0ull, s1 = 0ull;
+  const f32x2 one = pack2(1.f, 1.f);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { d2[0][q] = pack2(dz[0][2 * q], dz[0][2 * q + 1]); d2[1][q] = pack2(dz[1][2 * q], dz[1][2 * q + 1]); }
+  for (int q = 0; q < BW_COLS / 2; ++q) { s0 = fma2(z.d[0][q], one, s0); s1 = fma2(z.d[1][q], one, s1); }
+  float a, b, c, d;
+  unpack2(s0, a, b); unpack2(s1, c, d);
+  red_add2(gb + 2 * j, a + b, c + d);
+}
+// gW[r][2j + n] += sum_c A[r][c] dz[n][c]  for the rows r = h, h + 8, ... < rows   (gW row pitch 128)
+__device__ __forceinline__ void wgrad_rows(const DzRows& z, const float* __restrict__ A, int rows, float* gW, int j, int h) {
+  float* g = gW + 2 * j;
 #pragma unroll 2
-  for (int r = 0; r < rows; ++r) {
-    const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(in + r * BW_RP);
+  for (int r = h; r < rows; r += BW_H) {
+    const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(A + r * BW_RP);
     f32x2 s0 = 0ull, s1 = 0ull;                  // (even columns, odd columns) partial sums
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < BW_COLS / 4; ++q) {
       const ulonglong2 x = xr[q];
-      s0 = fma2(x.x, d2[0][2 * q], s0); s0 = fma2(x.y, d2[0][2 * q + 1], s0);
-      s1 = fma2(x.x, d2[1][2 * q], s1); s1 = fma2(x.y, d2[1][2 * q + 1], s1);
+      s0 = fma2(x.x, z.d[0][2 * q], s0); s0 = fma2(x.y, z.d[0][2 * q + 1], s0);
+      s1 = fma2(x.x, z.d[1][2 * q], s1); s1 = fma2(x.y, z.d[1][2 * q + 1], s1);
     }
     float a, b, c, d;
     unpack2(s0, a, b); unpack2(s1, c, d);
@@ -289,7 +298,9 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
   float* H = sm + BW_OFF_H;
   float* D = sm + BW_OFF_D;
   float* DX = sm + BW_OFF_DX;
-  float* R = sm + BW_OFF_R;
+  float* R = sm + BW_OFF_R;                      // d raw  [3][RP]
+  float* P = sm + BW_OFF_P;                      // positions of the columns [3][RP]; later their gradient through the encoding
+  float* RAW = sm + BW_OFF_RAW;                  // so3_mlp output [3][RP]
   const int tid = warp * 32 + lane;
   const int j = tid & 63, h = tid >> 6;
   const float* bias = a.w + SO3_OFF_B;
@@ -302,41 +313,37 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
   __syncthreads();
   int base = 0, n_act = 0;
 #pragma unroll
-  for (int w = 0; w < MARCH_THREADS / 32; ++w) {
+  for (int w = 0; w < MARCH_THREADS / 32; ++w) { // only the first MARCH_THREADS threads carry rays
     const int c = cnt[w];
     if (w < warp) base += c;
     n_act += c;
   }
   const int idx = base + __popc(bal & ((1u << lane) - 1u));
   constexpr int HL = SO3_W * BW_RP;              // floats per saved layer
+  const float half_pi = 1.57079632679489661923f;
 #pragma unroll 1
   for (int col0 = 0; col0 < n_act; col0 += BW_COLS) {
     const int n_here = min(BW_COLS, n_act - col0);
     const bool mine = act && idx >= col0 && idx < col0 + BW_COLS;
     const int col = idx - col0;
     if (col0 > 0) __syncthreads();               // another pass: everyone is done with the buffers of the previous one
-    // unused columns are zeroed: their dZ stays exactly 0 through the chain, and 0 * (finite activation) adds nothing
-    if (tid < BW_COLS && tid >= n_here) {
-      for (int f = 0; f < SO3_IN; ++f) X[f * BW_RP + tid] = 0.f;
-      R[tid] = 0.f; R[BW_RP + tid] = 0.f; R[2 * BW_RP + tid] = 0.f;
-    }
-    if (mine) {
-      const float half_pi = 1.57079632679489661923f;
-      float sc = 1.f;
-#pragma unroll
-      for (int k = 0; k < 10; ++k) {             // feature k*6 + c = sin(2^k p_c) w_k, k*6 + 3 + c = sin(2^k p_c + pi/2) w_k
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float xb = mul(p[c], sc);
-          X[(k * 6 + c) * BW_RP + col] = mul(sinf(xb), a.window[k]);
-          X[(k * 6 + 3 + c) * BW_RP + col] = mul(sinf(add(xb, half_pi)), a.window[k]);
-        }
-        sc *= 2.f;
-      }
-    }
+    if (mine) { P[col] = p[0]; P[BW_RP + col] = p[1]; P[2 * BW_RP + col] = p[2]; }
     __syncthreads();
+    // ---- encoding, all threads: feature k*6 + c = sin(2^k p_c) w_k, k*6 + 3 + c = sin(2^k p_c + pi/2) w_k.  Unused columns
+    // are zeroed: their dZ stays exactly 0 through the chain, and 0 * (finite activation) adds nothing
+    for (int e = tid; e < SO3_IN * BW_COLS; e += BW_THREADS) {
+      const int f = e >> 5, cc = e & 31;
+      float v = 0.f;
+      if (cc < n_here) {
+        const int k = f / 6, q = f - 6 * k, c = q >= 3 ? q - 3 : q;
+        const float xb = mul(P[c * BW_RP + cc], (float)(1 << k));
+        v = mul(sinf(q >= 3 ? add(xb, half_pi) : xb), a.window[k]);
+      }
+      X[f * BW_RP + cc] = v;
+    }
+    // (the first chunk barrier of the GEMM publishes X)
     // ---- forward, keeping every hidden activation
-    float acc[2][16];
+    float acc[2][BW_CPT];
     zero_acc(acc);
     gemm_ring(acc, ring, tid, stream, SO3_IN, SO3_W, X, j, h, true);
     relu_bias_store(acc, bias, H, j, h);
@@ -353,54 +360,63 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     __syncthreads();
     const float* H4 = H + 3 * HL;
     const float* W4 = a.w + SO3_OFF_W4;
-    // ---- Dense_4 + rotation, forward and reverse, by the ray's own thread
+    // ---- Dense_4: raw[m][col], one thread per output
+    if (tid < 3 * BW_COLS) {
+      const int m = tid >> 5, cc = tid & 31;
+      float r = __ldg(bias + 4 * SO3_W + m);
+#pragma unroll 8
+      for (int k = 0; k < SO3_W; ++k) r = fmaf(H4[k * BW_RP + cc], __ldg(W4 + 3 * k + m), r);
+      RAW[m * BW_RP + cc] = r;
+    }
+    __syncthreads();
+    // ---- rotation, forward and reverse, by the ray's own thread (it holds g and dG); unused columns get d raw = 0
     if (mine) {
-      const float* b4 = bias + 4 * SO3_W;
-      float r[3] = {__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2)};
-#pragma unroll 4
-      for (int k = 0; k < SO3_W; ++k) {
-        const float hv = H4[k * BW_RP + col];
-        r[0] = fmaf(hv, __ldg(W4 + 3 * k), r[0]); r[1] = fmaf(hv, __ldg(W4 + 3 * k + 1), r[1]); r[2] = fmaf(hv, __ldg(W4 + 3 * k + 2), r[2]);
-      }
+      const float r[3] = {RAW[col], RAW[BW_RP + col], RAW[2 * BW_RP + col]};
       float dr[3];
       rodrigues_bwd(r, g, dG, dr, dg);
       R[col] = dr[0]; R[BW_RP + col] = dr[1]; R[2 * BW_RP + col] = dr[2];
     }
+    if (tid < BW_COLS && tid >= n_here) { R[tid] = 0.f; R[BW_RP + tid] = 0.f; R[2 * BW_RP + tid] = 0.f; }
     __syncthreads();
     // ---- Dense_4 backward: dH4 = W4 d raw, masked; gW4 += H4 (x) d raw; gb4 += sum d raw
     {
-      float gw4[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
       float w4[2][3];
 #pragma unroll
       for (int n = 0; n < 2; ++n)
 #pragma unroll
         for (int m = 0; m < 3; ++m) w4[n][m] = __ldg(W4 + (2 * j + n) * 3 + m);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float r0 = R[16 * h + c], r1 = R[BW_RP + 16 * h + c], r2 = R[2 * BW_RP + 16 * h + c];
+      for (int c = 0; c < BW_CPT; ++c) {
+        const float r0 = R[BW_CPT * h + c], r1 = R[BW_RP + BW_CPT * h + c], r2 = R[2 * BW_RP + BW_CPT * h + c];
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
-          const float hv = H4[(2 * j + n) * BW_RP + 16 * h + c];
+          const float hv = H4[(2 * j + n) * BW_RP + BW_CPT * h + c];
           acc[n][c] = hv > 0.f ? (w4[n][0] * r0 + w4[n][1] * r1 + w4[n][2] * r2) : 0.f;
-          gw4[n][0] = fmaf(hv, r0, gw4[n][0]); gw4[n][1] = fmaf(hv, r1, gw4[n][1]); gw4[n][2] = fmaf(hv, r2, gw4[n][2]);
         }
       }
-      float* g4 = a.gw + SO3_OFF_W4 + (2 * j) * 3;           // rows 2j, 2j+1 are 6 consecutive floats, 8-byte aligned
-      red_add2(g4, gw4[0][0], gw4[0][1]); red_add2(g4 + 2, gw4[0][2], gw4[1][0]); red_add2(g4 + 4, gw4[1][1], gw4[1][2]);
-      if (tid < 3) {
+      if (tid < 3 * SO3_W) {                     // gW4[k][m] += sum_c H4[k][c] d raw[m][c], one thread per element
+        const int k = tid / 3, m = tid - 3 * k;
         float s = 0.f;
-        for (int c = 0; c < BW_COLS; ++c) s += R[tid * BW_RP + c];
-        atomicAdd(gbias + 4 * SO3_W + tid, s);
+#pragma unroll 8
+        for (int c = 0; c < BW_COLS; ++c) s = fmaf(H4[k * BW_RP + c], R[m * BW_RP + c], s);
+        atomicAdd(a.gw + SO3_OFF_W4 + tid, s);
+      } else if (tid < 3 * SO3_W + 3) {
+        const int m = tid - 3 * SO3_W;
+        float s = 0.f;
+        for (int c = 0; c < BW_COLS; ++c) s += R[m * BW_RP + c];
+        atomicAdd(gbias + 4 * SO3_W + m, s);
       }
     }
+    DzRows z;
     // ---- Dense_3 (inputs [H3, X]): acc = dZ4
-    bias_grad(acc, gbias + 3 * SO3_W, j);
-    wgrad_rows(acc, H + 2 * HL, SO3_W, a.gw + SO3_OFF_W3, j, h);
-    wgrad_rows(acc, X, SO3_IN, a.gw + SO3_OFF_W3 + SO3_W * SO3_W, j, h);
     store_rows(acc, D, j, h);
     __syncthreads();
+    load_dz_rows(z, D, j);
+    if (h == 0) bias_grad(z, gbias + 3 * SO3_W, j);
+    wgrad_rows(z, H + 2 * HL, SO3_W, a.gw + SO3_OFF_W3, j, h);
+    wgrad_rows(z, X, SO3_IN, a.gw + SO3_OFF_W3 + SO3_W * SO3_W, j, h);
     {                                                        // gradient wrt the skip-concatenated encoding
-      float ax[2][16];
+      float ax[2][BW_CPT];
       zero_acc(ax);
       gemm_ring(ax, ring, tid, stream, SO3_W, SO3_IN, D, j, h, j < SO3_IN / 2);
       if (j < SO3_IN / 2) store_rows(ax, DX, j, h);
@@ -410,93 +426,102 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     relu_mask(acc, H + 2 * HL, j, h);                        // dZ3
     __syncthreads();                                         // D has been read by everyone
     // ---- Dense_2 (input H2)
-    bias_grad(acc, gbias + 2 * SO3_W, j);
-    wgrad_rows(acc, H + HL, SO3_W, a.gw + SO3_OFF_W2, j, h);
     store_rows(acc, D, j, h);
     __syncthreads();
+    load_dz_rows(z, D, j);
+    if (h == 0) bias_grad(z, gbias + 2 * SO3_W, j);
+    wgrad_rows(z, H + HL, SO3_W, a.gw + SO3_OFF_W2, j, h);
     zero_acc(acc);
     gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, D, j, h, true);
     relu_mask(acc, H + HL, j, h);                            // dZ2
     __syncthreads();
     // ---- Dense_1 (input H1)
-    bias_grad(acc, gbias + SO3_W, j);
-    wgrad_rows(acc, H, SO3_W, a.gw + SO3_OFF_W1, j, h);
     store_rows(acc, D, j, h);
     __syncthreads();
+    load_dz_rows(z, D, j);
+    if (h == 0) bias_grad(z, gbias + SO3_W, j);
+    wgrad_rows(z, H, SO3_W, a.gw + SO3_OFF_W1, j, h);
     zero_acc(acc);
     gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, D, j, h, true);
     relu_mask(acc, H, j, h);                                 // dZ1
     __syncthreads();
     // ---- Dense_0 (input X)
-    bias_grad(acc, gbias, j);
-    wgrad_rows(acc, X, SO3_IN, a.gw, j, h);
     store_rows(acc, D, j, h);
     __syncthreads();
+    load_dz_rows(z, D, j);
+    if (h == 0) bias_grad(z, gbias, j);
+    wgrad_rows(z, X, SO3_IN, a.gw, j, h);
     {
-      float ax[2][16];
+      float ax[2][BW_CPT];
       zero_acc(ax);
       if (j < SO3_IN / 2) {
 #pragma unroll
         for (int n = 0; n < 2; ++n) {                        // continue from the skip part (own rows / columns)
-          const float4* o = reinterpret_cast<const float4*>(DX + (2 * j + n) * BW_RP + 16 * h);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { const float4 x = o[q]; ax[n][4 * q] = x.x; ax[n][4 * q + 1] = x.y; ax[n][4 * q + 2] = x.z; ax[n][4 * q + 3] = x.w; }
+          const float4 x = *reinterpret_cast<const float4*>(DX + (2 * j + n) * BW_RP + BW_CPT * h);
+          ax[n][0] = x.x; ax[n][1] = x.y; ax[n][2] = x.z; ax[n][3] = x.w;
         }
       }
       gemm_ring(ax, ring, tid, stream, SO3_W, SO3_IN, D, j, h, j < SO3_IN / 2);
       if (j < SO3_IN / 2) store_rows(ax, DX, j, h);
     }
     __syncthreads();
-    // ---- encoding backward: d/dp_c of sin(2^k p_c [+ pi/2]) w_k
-    if (mine) {
-      const float half_pi = 1.57079632679489661923f;
-      float sc = 1.f;
-      dp[0] = dp[1] = dp[2] = 0.f;
+    // ---- encoding backward, one thread per (component, column): d/dp_c of sin(2^k p_c [+ pi/2]) w_k
+    float gpc = 0.f;
+    if (tid < 3 * BW_COLS) {
+      const int c = tid >> 5, cc = tid & 31;
+      if (cc < n_here) {
+        const float x = P[c * BW_RP + cc];
+        float sc = 1.f;
 #pragma unroll
-      for (int k = 0; k < 10; ++k) {
-        const float ws = a.window[k] * sc;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float xb = mul(p[c], sc);
-          dp[c] += ws * (cosf(xb) * DX[(k * 6 + c) * BW_RP + col] + cosf(add(xb, half_pi)) * DX[(k * 6 + 3 + c) * BW_RP + col]);
+        for (int k = 0; k < 10; ++k) {
+          const float xb = mul(x, sc);
+          gpc += a.window[k] * sc * (cosf(xb) * DX[(k * 6 + c) * BW_RP + cc] + cosf(add(xb, half_pi)) * DX[(k * 6 + 3 + c) * BW_RP + cc]);
+          sc *= 2.f;
         }
-        sc *= 2.f;
       }
     }
+    __syncthreads();                             // every thread has read P
+    if (tid < 3 * BW_COLS) P[(tid >> 5) * BW_RP + (tid & 31)] = gpc;
+    __syncthreads();
+    if (mine) { dp[0] = P[col]; dp[1] = P[BW_RP + col]; dp[2] = P[2 * BW_RP + col]; }
   }
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(MARCH_THREADS, 1) march_all_bwd_kernel(
+__global__ void __launch_bounds__(BW_THREADS, 1) march_all_bwd_kernel(
     const float4* __restrict__ table, const MarchGeom mg, const float* __restrict__ bricks, const float4* __restrict__ path,
     int recf4, int64_t n_rays, float near, float step, int n_steps, const int32_t* __restrict__ jitter, int n_coarse,
     const float* __restrict__ d_pos_c, const float* __restrict__ d_dir_c, const So3BwdArgs so3, float* __restrict__ d_origins,
     float* __restrict__ d_viewdirs, int rays_per_cta) {
   extern __shared__ __align__(16) float sm[];
   int* cnt = reinterpret_cast<int*>(sm + BW_ACT_FLOATS);
-  float* ring_mem = sm + BW_ACT_FLOATS + 4 + 2 * BW_RING_SLOTS;          // after cnt (16 B) and the mbarriers (8 B each)
+  float* ring_mem = sm + BW_ACT_FLOATS + 16 + 2 * BW_RING_SLOTS;         // after cnt (64 B) and the mbarriers (8 B each)
   int16_t* kmap = reinterpret_cast<int16_t*>(ring_mem + BW_RING_SLOTS * SO3_SLOT_FLOATS);   // march step -> coarse sample, or -1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   So3Ring ring;
-  ring_init(ring, ring_mem, cnt + 4, BW_RING_SLOTS, tid);
-  for (int i = tid; i < n_steps; i += MARCH_THREADS) kmap[i] = -1;
+  ring_init(ring, ring_mem, cnt + 16, BW_RING_SLOTS, tid);
+  for (int i = tid; i < n_steps; i += BW_THREADS) kmap[i] = -1;
   __syncthreads();
   int k_last = 0;
   for (int i = 0; i < n_coarse; ++i) k_last = max(k_last, min(max(__ldg(jitter + i), 0), n_steps - 1));
-  for (int i = tid; i < n_coarse; i += MARCH_THREADS) kmap[min(max(__ldg(jitter + i), 0), n_steps - 1)] = (int16_t)i;
+  for (int i = tid; i < n_coarse; i += BW_THREADS) kmap[min(max(__ldg(jitter + i), 0), n_steps - 1)] = (int16_t)i;
   __syncthreads();
   const int64_t ray = blockIdx.x * (int64_t)rays_per_cta + tid;      // threads beyond rays_per_cta only help with the MLP
   const bool live = tid < rays_per_cta && ray < n_rays;
   const int64_t rr = live ? ray : (n_rays - 1);
   const float4* rec = path + rr * (int64_t)n_steps * recf4;
   float lp[3] = {0.f, 0.f, 0.f}, lv[3] = {0.f, 0.f, 0.f};
+  const bool carrier = tid < rays_per_cta;       // warp-uniform: the other warps only take part in the MLP evaluations
 #pragma unroll 1
   for (int k = k_last; k >= 0; --k) {
-    const float4 r0 = __ldg(rec + k * recf4), r1 = __ldg(rec + k * recf4 + 1);
-    const float p[3] = {r0.x, r0.y, r0.z}, v[3] = {r1.x, r1.y, r1.z};
+    float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+    if (carrier) {
+      const float4 r0 = __ldg(rec + k * recf4), r1 = __ldg(rec + k * recf4 + 1);
+      p[0] = r0.x; p[1] = r0.y; p[2] = r0.z; v[0] = r1.x; v[1] = r1.y; v[2] = r1.z;
+    }
     if (k < k_last) {                            // transition k -> k+1, reverse
-      float4 c, jx, jy, jz;
-      lookup_with_jacobian<FAST>(table, mg, bricks, p[0], p[1], p[2], c, jx, jy, jz);
+      float4 c = make_float4(1.f, 0.f, 0.f, 0.f), jx = make_float4(0.f, 0.f, 0.f, 0.f), jy = jx, jz = jx;
+      if (carrier) lookup_with_jacobian<FAST>(table, mg, bricks, p[0], p[1], p[2], c, jx, jy, jz);
       const float g[3] = {c.y, c.z, c.w};
       const float hn = step / c.x;
       const float dn = -(hn / c.x) * (v[0] * lp[0] + v[1] * lp[1] + v[2] * lp[2]);
@@ -570,7 +595,7 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   So3BwdArgs a;
   a.w = so3_w; a.wt = so3_wt; a.gw = g_so3;
   for (int k = 0; k < 10; ++k) a.window[k] = (float)so3_window[k];
-  const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 16 + 8 * BW_RING_SLOTS + (size_t)BW_RING_SLOTS * SO3_SLOT_FLOATS * 4 +
+  const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 64 + 8 * BW_RING_SLOTS + (size_t)BW_RING_SLOTS * SO3_SLOT_FLOATS * 4 +
                      (((size_t)n_steps * 2 + 15) & ~(size_t)15);
   RNERF_REQUIRE(dyn <= 227 * 1024, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps too large for the step map in shared memory");
   cudaError_t e = cudaFuncSetAttribute(march_all_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -582,11 +607,11 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   const int rpc = so3_rays_per_cta(n_rays, n_sm);
   const unsigned blocks = (unsigned)((n_rays + rpc - 1) / rpc);
   if (fast)
-    march_all_bwd_kernel<true><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
+    march_all_bwd_kernel<true><<<blocks, BW_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
                                                                    n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
                                                                    d_dir_c, a, d_origins, d_viewdirs, rpc);
   else
-    march_all_bwd_kernel<false><<<blocks, MARCH_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
+    march_all_bwd_kernel<false><<<blocks, BW_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
                                                                     n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
                                                                     d_dir_c, a, d_origins, d_viewdirs, rpc);
   count_launch();
