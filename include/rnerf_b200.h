@@ -203,6 +203,11 @@ int rnerf_sq_err(const float* a, const float* b, int64_t n, float* out_accum, vo
  *   written by rnerf_march_all_fwd for the same inputs; jitter[Nc]: strictly increasing march-step indices;
  *   d_pos_c/d_dir_c: [B][Nc][3] loss gradients; so3_wt: rnerf_so3_transpose(so3_w).  g_so3 (layout of so3_w) is
  *   ACCUMULATED into; d_origins/d_viewdirs [B][3] (gradients wrt the ray, not used by train.py) may be NULL. */
+/* VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267) on free-standing points: pred[N][3] = rodrigues(so3_mlp(
+ * annealed_pos_enc(pts)), cond) -- the evaluation behind PathSampler.compute_normal_loss_and_smooth
+ * (rnerf/eikonal_utils.py:84-98). */
+int rnerf_so3_predict(const float* so3_w, const double so3_window_host[10], const float* pts, const float* cond, int64_t n,
+                      float* pred, void* stream);
 size_t rnerf_mlp_input_grad_packed_floats(void);
 int rnerf_mlp_input_grad_pack(const float* dense0_kernel, const float* dense5_kernel, const float* dense10_kernel,
                               float* wt, void* stream);

@@ -339,6 +339,23 @@ def rodrigues_grad(raw: torch.Tensor, grad: torch.Tensor) -> torch.Tensor:
     return a * (torch.cos(theta) * v + torch.sin(theta) * cross + (1 - torch.cos(theta)) * ev * e)
 
 
+def so3_predict(so3_params, pts, cond, annealed_alpha=1.0):
+    """VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267), use_residual / use_direct_output branch."""
+    raw = small_mlp(so3_params, annealed_pos_enc(pts[:, None], 0, 10, annealed_alpha * 10))[:, 0]
+    return rodrigues_grad(raw, cond)
+
+
+def normal_loss_and_smooth(so3_params, ray_pos, idx_grad, annealed_alpha, noise, ndelta):
+    """PathSampler.compute_normal_loss_and_smooth (rnerf/eikonal_utils.py:84-98) with the np.random.normal draw passed in
+    (`noise`, already scaled by normal_radius_scale).  Returns (0.0, smoothness)."""
+    dt = ray_pos.dtype
+    pred = so3_predict(so3_params, ray_pos, idx_grad, annealed_alpha)
+    shifted = ray_pos + (as_t(noise, torch.float64) * torch.tensor(ndelta, dtype=torch.float64)).to(dt)
+    pred_rand = so3_predict(so3_params, shifted, idx_grad, annealed_alpha)
+    factor = safe_l2_norm(idx_grad)
+    return 0.0, ((pred - pred_rand) / factor).abs().sum(-1, keepdim=True).mean()
+
+
 # ----------------------------------------------------------------------------------------------
 # a5/a6. eikonal march  (rnerf/eikonal_utils.py:30-49, 101-124)
 # ----------------------------------------------------------------------------------------------

@@ -64,6 +64,7 @@ SIGNATURES = {
     "rnerf_mlp_input_grad_packed_floats": (C.c_size_t, []),
     "rnerf_mlp_input_grad_pack": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_mlp_input_grad": (C.c_int, [C.c_void_p, c_i64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_so3_predict": (C.c_int, [c_f32p, C.POINTER(C.c_double), c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_so3_transposed_floats": (C.c_size_t, []),
     "rnerf_so3_transpose": (C.c_int, [c_f32p, c_f32p, C.c_void_p]),
     "rnerf_march_all_bwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,

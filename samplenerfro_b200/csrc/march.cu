@@ -437,6 +437,30 @@ __global__ void __launch_bounds__(SO3 ? SO3_THREADS : MARCH_THREADS, SO3 ? 2 : 8
   if (SO3) ring_drain(ring);                     // weight chunks fetched ahead for an evaluation that never came
 }
 
+// VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267) on free-standing points: pred = rodrigues(so3_mlp(annealed_pos_enc(x)),
+// condition), no |grad n| threshold.  What PathSampler.compute_normal_loss_and_smooth (rnerf/eikonal_utils.py:84-98) evaluates.
+__global__ void __launch_bounds__(SO3_THREADS, 2) so3_predict_kernel(const float* __restrict__ pts, const float* __restrict__ cond,
+                                                                     int64_t n, const So3Args so3, int so3_slots,
+                                                                     float* __restrict__ pred) {
+  extern __shared__ __align__(16) float so3_scratch[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  So3Ring ring;
+  char* base = reinterpret_cast<char*>(so3_scratch);
+  ring_init(ring, reinterpret_cast<float*>(base + SO3_OFF_RING), base + SO3_OFF_BARS, so3_slots, threadIdx.x);
+  __syncthreads();
+  const int64_t i = blockIdx.x * (int64_t)MARCH_THREADS + threadIdx.x;
+  const bool act = threadIdx.x < MARCH_THREADS && i < n;
+  const float px = act ? pts[3 * i] : 0.f, py = act ? pts[3 * i + 1] : 0.f, pz = act ? pts[3 * i + 2] : 0.f;
+  float r0, r1, r2;
+  so3_eval(so3, so3_scratch, ring, warp, lane, act, px, py, pz, r0, r1, r2);
+  if (act) {
+    float gx = cond[3 * i], gy = cond[3 * i + 1], gz = cond[3 * i + 2];
+    so3_rotate(r0, r1, r2, gx, gy, gz);
+    pred[3 * i] = gx; pred[3 * i + 1] = gy; pred[3 * i + 2] = gz;
+  }
+  ring_drain(ring);
+}
+
 // ray_dir of every record, normalised: the array PathSampler returns (rnerf/eikonal_utils.py:113)
 __global__ void __launch_bounds__(256) path_dirs_kernel(const float4* __restrict__ path, int recf4, int64_t n_rec,
                                                         float* __restrict__ out) {
@@ -609,4 +633,23 @@ extern "C" int rnerf_path_dirs(const float* path, int rec_floats, int64_t n_rays
   path_dirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)path, rec_floats / 4, n, ray_dir);
   count_launch();
   return check_launch("rnerf_path_dirs");
+}
+
+extern "C" int rnerf_so3_predict(const float* so3_w, const double so3_window[10], const float* pts, const float* cond, int64_t n,
+                                 float* pred, void* stream) {
+  RNERF_REQUIRE(n >= 0, RNERF_E_SHAPE, "rnerf_so3_predict: n < 0");
+  if (n == 0) return 0;
+  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(so3_window); RNERF_REQUIRE_PTR(pts); RNERF_REQUIRE_PTR(cond); RNERF_REQUIRE_PTR(pred);
+  RNERF_REQUIRE(aligned16(so3_w), RNERF_E_ALIGN, "rnerf_so3_predict: so3_w must be 16-byte aligned");
+  So3Args so3;
+  so3.w = so3_w;
+  for (int k = 0; k < 10; ++k) so3.window[k] = (float)so3_window[k];
+  const int slots = 4;
+  const size_t dyn = so3_smem_bytes(slots);
+  cudaError_t e = cudaFuncSetAttribute(so3_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) { set_error("rnerf_so3_predict: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  so3_predict_kernel<<<(unsigned)((n + MARCH_THREADS - 1) / MARCH_THREADS), SO3_THREADS, dyn, (cudaStream_t)stream>>>(pts, cond, n, so3,
+                                                                                                                   slots, pred);
+  count_launch();
+  return check_launch("rnerf_so3_predict");
 }

@@ -76,7 +76,7 @@ class NerfModel:
                  min_deg_point=0, max_deg_point=10, deg_view=4, lindisp=False, rgb_activation="sigmoid",
                  sigma_activation="softplus", legacy_posenc_order=False, rgb_padding=0.001, sigma_bias=-1.0,
                  num_path_samples=8, sh_direnc_deg=-1, use_mask_bbox=False, bd_cut_dist=None, cfg_name=None,
-                 use_random_choice=True, device=None):
+                 use_random_choice=True, normal_radius_scale=0.1, device=None):
         self.device = torch.device(device if device is not None else "cuda")
         self.ndim, self.nmin, self.nmax = [int(v) for v in ndim], [float(v) for v in nmin], [float(v) for v in nmax]
         self.stage = stage
@@ -88,6 +88,7 @@ class NerfModel:
         self.num_path_samples = int(num_path_samples)
         self.use_mask_bbox, self.bd_cut_dist, self.cfg_name = bool(use_mask_bbox), bd_cut_dist, cfg_name or ""
         self.use_random_choice = bool(use_random_choice)
+        self.normal_radius_scale = float(normal_radius_scale)     # PathSampler.normal_radius_scale (0.1 in every .gin)
         self.deg_view, self.min_deg_point, self.max_deg_point = deg_view, min_deg_point, max_deg_point
         # The sm_100a kernels are specialised for the one architecture every shipped config uses
         # (flag defaults rnerf/utils.py:138-181); anything else is rejected loudly rather than approximated.
@@ -202,6 +203,25 @@ class NerfModel:
         from . import autograd as ag
         return ag.bkgd_color(self, variables, viewdirs.reshape(-1, 3).contiguous())
 
+    def wrapper_compute_normal_loss_and_smooth(self, variables: Dict, ray_pos, idx_grad, annealed_alpha: float = 1.0, noise=None):
+        """PathSampler.compute_normal_loss_and_smooth (rnerf/eikonal_utils.py:84-98, rnerf/models.py:139-140) ->
+        (0.0, smoothness): mean over points of sum |pred(x) - pred(x + N(0, normal_radius_scale) * ndelta)| / |grad n|_safe.
+        A statistic only: train.py:156 hard-codes annealing_rate = 0, which multiplies it in the loss and in the stats,
+        so it is evaluated without autograd.  `noise` [N,3] replaces np.random.normal for reproducible parity tests."""
+        pts = torch.as_tensor(ray_pos).to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        cond = torch.as_tensor(idx_grad).to(self.device, torch.float32).reshape(-1, 3).contiguous()
+        if noise is None:
+            noise = np.random.normal(scale=self.normal_radius_scale, size=tuple(pts.shape))
+        nd = torch.tensor([(self.nmax[i] - self.nmin[i]) / (self.ndim[i] - 1.0) for i in range(3)], dtype=torch.float64)
+        jit = (torch.as_tensor(np.asarray(noise), dtype=torch.float64).reshape(-1, 3) * nd).to(self.device, torch.float32)
+        with torch.no_grad():
+            so3 = (self._so3_packed(variables), self.so3_window(annealed_alpha))
+            pred = ops.so3_predict(so3[0], so3[1], pts, cond)
+            pred_rand = ops.so3_predict(so3[0], so3[1], pts + jit, cond)
+            factor = torch.sqrt(torch.clamp((cond * cond).sum(-1, keepdim=True), min=1e-6))
+            smooth = ((pred - pred_rand) / factor).abs().sum(-1, keepdim=True).mean()
+        return 0.0, smooth
+
     def _bd_bbox(self):
         """Scene-name-selected bbox of the bd_cut_dist passes (rnerf/models.py:485-497)."""
         if "pen" in self.cfg_name:
@@ -300,7 +320,10 @@ def construct_nerf(key, example_batch, args, ndim, nmin, nmax, grid):
     """Construct a Neural Radiance Field (rnerf/models.py:538-618).  Returns (model, init_variables)."""
     if getattr(args, "sh_deg", -1) >= 0:
         assert not args.use_viewdirs, "You can only use up to one of: SH or use_viewdirs."
-    gin_model = getattr(args, "gin_bindings", {}).get("NerfModel", {}) if hasattr(args, "gin_bindings") else {}
+    gin_model = dict(getattr(args, "gin_bindings", {}).get("NerfModel", {})) if hasattr(args, "gin_bindings") else {}
+    gin_path = getattr(args, "gin_bindings", {}).get("PathSampler", {}) if hasattr(args, "gin_bindings") else {}
+    if "normal_radius_scale" in gin_path:
+        gin_model["normal_radius_scale"] = gin_path["normal_radius_scale"]
     model = NerfModel(
         min_deg_point=args.min_deg_point, max_deg_point=args.max_deg_point, deg_view=args.deg_view,
         num_coarse_samples=args.num_coarse_samples, num_fine_samples=args.num_fine_samples,

@@ -192,6 +192,17 @@ def so3_unpack_views(g: torch.Tensor):
     return out
 
 
+def so3_predict(w: torch.Tensor, window: Sequence[float], pts: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
+    """VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267): rodrigues(so3_mlp(annealed_pos_enc(pts)), cond) -> [N,3]."""
+    pts = _chk(pts.reshape(-1, 3).contiguous(), "pts"); cond = _chk(cond.reshape(-1, 3).contiguous(), "cond")
+    assert pts.shape == cond.shape and len(window) == 10
+    pred = torch.empty_like(pts)
+    win = (C.c_double * 10)(*[float(v) for v in window])
+    check(_lib.load().rnerf_so3_predict(_p(_chk(w, "so3 weights")), win, _p(pts), _p(cond), pts.shape[0], _p(pred), _stream()),
+          "rnerf_so3_predict")
+    return pred
+
+
 def so3_transpose(w: torch.Tensor) -> torch.Tensor:
     """T_l[out][in] images of the four hidden so3 kernels (the adjoint's input-gradient GEMMs stream them row by row)."""
     lib = _lib.load()

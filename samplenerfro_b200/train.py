@@ -1,9 +1,10 @@
-"""Host-side mirror of train.py's optimisation step for the radiance stage (train.py:58-183).
+"""Host-side mirror of train.py's optimisation step for the radiance and "all" stages (train.py:58-183, 290-310).
 
 `train_step(model, rng, state, batch) -> (new_state, stats, rng)` keeps the reference's signature.  The loss is
 train.py:75-162 with annealing_rate hard-coded to 0 (train.py:156); gradients are averaged across ranks
 (`jax.lax.pmean(grads, "batch")`, train.py:166) with torch.distributed all-reduces bucketed per MLP, then Adam
-(optax.adam defaults) with `learning_rate_decay` is applied identically on every rank.
+(optax.adam defaults) with `learning_rate_decay` is applied identically on every rank.  In the "all" stage so3_mlp is a
+fourth trainable bucket: its gradient comes from the reverse sweep of the eikonal scan (`autograd._MarchAll`).
 """
 from __future__ import annotations
 
@@ -240,6 +241,13 @@ def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, ar
                                            + 0.5 * ((env[:, 1:] - env[:, :-1]) ** 2).reshape(-1))
     else:
         loss_bg_smooth = torch.zeros((), device=rgb.device)
+    loss_nrm = torch.zeros((), device=rgb.device)
+    annealing_rate = 0.0                      # train.py:156 (the annealed expression is commented out): loss_nrm and loss_sp are multiplied by it
+    if (str(getattr(args, "stage", "radiance")).startswith("all") and batch.get("pts") is not None
+            and (args.normal_loss_weight + args.normal_smooth_weight) > 0):
+        # train.py:120-124: evaluated like the reference does, although annealing_rate = 0 removes it from loss and stats
+        nl, ns = model.apply(variables, batch["pts"], batch["grads"], annealed_alpha, method=model.wrapper_compute_normal_loss_and_smooth)
+        loss_nrm = annealing_rate * (args.normal_loss_weight * nl + args.normal_smooth_weight * ns)
     if arena is not None:
         with torch.no_grad():
             weight_l2 = arena.weight_l2()
@@ -252,7 +260,7 @@ def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, ar
              "psnr_c": utils.compute_psnr(loss_c.detach()), "weight_l2": weight_l2.detach(),
              "loss_bg": (args.bg_weight * loss_bg).detach() if torch.is_tensor(loss_bg) else loss_bg,
              "loss_bg_smooth": loss_bg_smooth.detach() if torch.is_tensor(loss_bg_smooth) else loss_bg_smooth,
-             "loss_sp": torch.zeros((), device=rgb.device), "loss_nrm": torch.zeros((), device=rgb.device),
+             "loss_sp": torch.zeros((), device=rgb.device), "loss_nrm": loss_nrm,
              "annealing_rate": annealed_alpha}
     return total, stats
 

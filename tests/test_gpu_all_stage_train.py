@@ -241,3 +241,27 @@ def test_all_stage_train_step_updates_so3(cuda_lib):
     assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0], losses
     after = so3["Dense_0"]["kernel"].detach()
     assert torch.isfinite(after).all() and (after - before).abs().max().item() > 0
+
+
+def test_normal_smoothness_statistic(cuda_lib):
+    """compute_normal_loss_and_smooth (rnerf/eikonal_utils.py:84-98): so3 prediction on free-standing points (ragged count,
+    several CTAs) and the smoothness statistic, vs the oracle with the same noise draw."""
+    from samplenerfro_b200 import models, ops, utils
+    n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
+    args = utils.Flags(config="example", stage="all", num_path_samples=12, white_bkgd=False, use_online_sparsity=False)
+    model, variables = models.construct_nerf(3, None, args, ndim, nmin, nmax, n)
+    so3 = _so3_params(12)
+    variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"] = H.to_cuda_params(so3)
+    gen = torch.Generator().manual_seed(3)
+    N = 333
+    pts = (torch.rand(N, 3, generator=gen) * 2 - 1) * 1.2
+    grads = torch.randn(N, 3, generator=gen) * 2.0
+    grads[:7] = 0.0                                         # |grad n| below the safe-norm floor
+    noise = torch.randn(N, 3, generator=gen) * 0.1
+    pred = ops.so3_predict(model._so3_packed(variables), model.so3_window(0.7), pts.cuda(), grads.cuda())
+    opred = O.so3_predict(so3, pts, grads, 0.7)
+    assert (pred.cpu() - opred).abs().max().item() < 1e-5 * max(opred.abs().max().item(), 1.0)
+    zero, smooth = model.apply(variables, pts, grads, 0.7, noise=noise, method=model.wrapper_compute_normal_loss_and_smooth)
+    nd = [(nmax[i] - nmin[i]) / (ndim[i] - 1.0) for i in range(3)]
+    _, osmooth = O.normal_loss_and_smooth(so3, pts, grads, 0.7, noise, nd)
+    assert zero == 0.0 and abs(float(smooth) - float(osmooth)) < 1e-4 * abs(float(osmooth)), (float(smooth), float(osmooth))
