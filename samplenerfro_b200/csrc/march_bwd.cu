@@ -153,30 +153,32 @@ __device__ __forceinline__ void rodrigues_bwd(const float r[3], const float g[3]
 }
 
 // ---- building blocks of the cooperative MLP chain -----------------------------------------------------------------------
-// Weight stream of one evaluation through the TMA ring (march_common.cuh), 72 chunks of <= 16 rows:
-//   0..31   the forward image, segments S0 (Dense_0 x X), S1, S2, S3a (Dense_3[:128] x H3), S3b (Dense_3[128:] x X)
-//   32..39  T3b [128][60]   40..47 T3a [128][128]   48..55 T2   56..63 T1   64..71 T0 [128][60]     (order of use)
-constexpr int BW_NCHUNK = 72;
-constexpr int BW_RING_SLOTS = 12;
+// Weight stream of one evaluation through the TMA ring (march_common.cuh), 18 chunks of <= 64 rows (32 KB slots: the CTA
+// has the SM to itself, and every chunk costs a block barrier, so the chunks are as large as three slots allow):
+//   0..7    the forward image, segments S0 (Dense_0 x X; 1 chunk), S1, S2, S3a (Dense_3[:128] x H3; 2 chunks each),
+//           S3b (Dense_3[128:] x X; 1 chunk)
+//   8..17   T3b [128][60], T3a [128][128], T2, T1, T0 [128][60]  (order of use; 2 chunks each)
+constexpr int BW_CH = 64;
+constexpr int BW_SLOT_FLOATS = BW_CH * SO3_W;
+constexpr int BW_NCHUNK = 18;
+constexpr int BW_RING_SLOTS = 3;
 struct So3BwdStream {
   const float* w;
   const float* wt;
   __device__ __forceinline__ void operator()(uint32_t g, const float*& src, uint32_t& bytes) const {
     const int c = (int)(g % (uint32_t)BW_NCHUNK);
-    if (c < 32) {
-      int seg, i;
-      if (c < 4) { seg = 0; i = c; } else if (c < 12) { seg = 1; i = c - 4; } else if (c < 20) { seg = 2; i = c - 12; }
-      else if (c < 28) { seg = 3; i = c - 20; } else { seg = 4; i = c - 28; }
-      const int seg_row0 = seg == 0 ? 0 : (seg == 1 ? 60 : (seg == 2 ? 188 : (seg == 3 ? 316 : 444)));
-      const int seg_rows = (seg == 0 || seg == 4) ? 60 : 128;
-      src = w + (size_t)(seg_row0 + i * SO3_CH) * SO3_W;
-      bytes = (uint32_t)min(SO3_CH, seg_rows - i * SO3_CH) * SO3_W * 4;
+    if (c < 8) {
+      // chunk -> (first row, rows) of the [504][128] forward matrix: segments start at rows 0, 60, 188, 316, 444
+      const int row0 = c == 0 ? 0 : (c == 7 ? 444 : 60 + (c - 1) * BW_CH);
+      const int rows = (c == 0 || c == 7) ? SO3_IN : BW_CH;
+      src = w + (size_t)row0 * SO3_W;
+      bytes = (uint32_t)rows * SO3_W * 4;
     } else {
-      const int b = (c - 32) >> 3, i = (c - 32) & 7;         // block in order of use, 8 chunks of 16 rows each
+      const int b = (c - 8) >> 1, i = (c - 8) & 1;           // block in order of use, 2 chunks of 64 rows each
       const int off = b == 0 ? SO3T_OFF_3B : (b == 1 ? SO3T_OFF_3A : (b == 2 ? SO3T_OFF_2 : (b == 3 ? SO3T_OFF_1 : SO3T_OFF_0)));
       const int wp = (b == 0 || b == 4) ? SO3_IN : SO3_W;
-      src = wt + off + (size_t)i * SO3_CH * wp;
-      bytes = (uint32_t)SO3_CH * wp * 4;
+      src = wt + off + (size_t)i * BW_CH * wp;
+      bytes = (uint32_t)BW_CH * wp * 4;
     }
   }
 };
@@ -190,7 +192,7 @@ constexpr int BW_THREADS = 512;
 constexpr int BW_H = BW_THREADS / 64;          // 8 column groups / row residues
 constexpr int BW_CPT = BW_COLS / BW_H;         // 4 columns per thread
 
-// acc[n][c] += sum_{r < K} W[r][2j + n] * In[r][4h + c]: W ([K][wp], K <= 128) arrives as the next ceil(K/16) chunks of the
+// acc[n][c] += sum_{r < K} W[r][2j + n] * In[r][4h + c]: W ([K][wp], K <= 128) arrives as the next ceil(K/64) chunks of the
 // ring.  Every thread of the CTA runs the chunk loop (block barrier per chunk); `work` = this thread owns output rows.
 __device__ __forceinline__ void gemm_ring(float (&acc)[2][BW_CPT], So3Ring& ring, int tid, const So3BwdStream& stream, int K, int wp,
                                           const float* __restrict__ In, int j, int h, bool work) {
@@ -198,9 +200,9 @@ __device__ __forceinline__ void gemm_ring(float (&acc)[2][BW_CPT], So3Ring& ring
   f32x2 a00 = pack2(acc[0][0], acc[0][1]), a01 = pack2(acc[0][2], acc[0][3]);
   f32x2 a10 = pack2(acc[1][0], acc[1][1]), a11 = pack2(acc[1][2], acc[1][3]);
 #pragma unroll 1
-  for (int k0 = 0; k0 < K; k0 += SO3_CH) {
+  for (int k0 = 0; k0 < K; k0 += BW_CH) {
     const float* wq = ring_acquire(ring, tid, stream) + 2 * j;
-    const int rows = min(SO3_CH, K - k0);
+    const int rows = min(BW_CH, K - k0);
     if (work) {
 #pragma unroll 8
       for (int r = 0; r < rows; ++r) {
@@ -495,11 +497,12 @@ __global__ void __launch_bounds__(BW_THREADS, 1) march_all_bwd_kernel(
     float* __restrict__ d_viewdirs, int rays_per_cta) {
   extern __shared__ __align__(16) float sm[];
   int* cnt = reinterpret_cast<int*>(sm + BW_ACT_FLOATS);
-  float* ring_mem = sm + BW_ACT_FLOATS + 16 + 2 * BW_RING_SLOTS;         // after cnt (64 B) and the mbarriers (8 B each)
-  int16_t* kmap = reinterpret_cast<int16_t*>(ring_mem + BW_RING_SLOTS * SO3_SLOT_FLOATS);   // march step -> coarse sample, or -1
+  float* ring_mem = sm + BW_ACT_FLOATS + 16 + 2 * SO3_MAX_SLOTS;         // after cnt (64 B) and room for 16 mbarriers (128 B)
+  static_assert((BW_ACT_FLOATS + 16 + 2 * SO3_MAX_SLOTS) % 4 == 0, "ring slots must be 16-byte aligned");
+  int16_t* kmap = reinterpret_cast<int16_t*>(ring_mem + BW_RING_SLOTS * BW_SLOT_FLOATS);   // march step -> coarse sample, or -1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   So3Ring ring;
-  ring_init(ring, ring_mem, cnt + 16, BW_RING_SLOTS, tid);
+  ring_init(ring, ring_mem, cnt + 16, BW_RING_SLOTS, tid, BW_SLOT_FLOATS);
   for (int i = tid; i < n_steps; i += BW_THREADS) kmap[i] = -1;
   __syncthreads();
   int k_last = 0;
@@ -595,7 +598,7 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   So3BwdArgs a;
   a.w = so3_w; a.wt = so3_wt; a.gw = g_so3;
   for (int k = 0; k < 10; ++k) a.window[k] = (float)so3_window[k];
-  const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 64 + 8 * BW_RING_SLOTS + (size_t)BW_RING_SLOTS * SO3_SLOT_FLOATS * 4 +
+  const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 64 + 8 * SO3_MAX_SLOTS + (size_t)BW_RING_SLOTS * BW_SLOT_FLOATS * 4 +
                      (((size_t)n_steps * 2 + 15) & ~(size_t)15);
   RNERF_REQUIRE(dyn <= 227 * 1024, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps too large for the step map in shared memory");
   cudaError_t e = cudaFuncSetAttribute(march_all_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

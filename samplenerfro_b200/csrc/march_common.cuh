@@ -66,7 +66,7 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 // (counted over the whole kernel) lives in slot g % n_slots and is chunk g % period of the stream.  While chunk g is
 // consumed, chunks g+1 .. g+n_slots-1 are in flight -- across evaluation boundaries too, so the next evaluation finds
 // its first chunks already resident.  Slot reuse is ordered by the block barrier every chunk starts with.
-constexpr int SO3_CH = 16;                                   // rows per chunk
+constexpr int SO3_CH = 16;                                   // rows per chunk (forward march; the reverse sweep uses 64)
 constexpr int SO3_SLOT_FLOATS = SO3_CH * SO3_W;              // 8 KB slots
 constexpr int SO3_MAX_SLOTS = 16;
 
@@ -75,13 +75,16 @@ struct So3Ring {
   uint32_t slots_s;      // the same, as a shared-window address
   uint32_t bars_s;       // n_slots mbarriers (8 bytes each)
   int n_slots;
+  int slot_floats;       // capacity of one slot
   uint32_t pos;          // chunks consumed so far (uniform over the CTA)
   bool primed;           // chunks pos .. pos + n_slots - 2 have been issued
 };
 
 // thread 0 initialises the barriers; the caller must __syncthreads() before first use
-__device__ __forceinline__ void ring_init(So3Ring& r, float* slots, void* bars, int n_slots, int tid) {
-  r.slots = slots; r.slots_s = smem_u32(slots); r.bars_s = smem_u32(bars); r.n_slots = n_slots; r.pos = 0; r.primed = false;
+__device__ __forceinline__ void ring_init(So3Ring& r, float* slots, void* bars, int n_slots, int tid,
+                                          int slot_floats = SO3_SLOT_FLOATS) {
+  r.slots = slots; r.slots_s = smem_u32(slots); r.bars_s = smem_u32(bars); r.n_slots = n_slots; r.slot_floats = slot_floats;
+  r.pos = 0; r.primed = false;
   if (tid == 0) {
     for (int i = 0; i < n_slots; ++i) mbar_init(r.bars_s + 8 * i, 1);
     fence_barrier_init();
@@ -94,7 +97,7 @@ __device__ __forceinline__ void ring_issue(const So3Ring& r, uint32_t g, const S
   stream(g, src, bytes);
   const uint32_t slot = g % (uint32_t)r.n_slots, bar = r.bars_s + 8 * slot;
   mbar_arrive_expect_tx(bar, bytes);
-  tma_bulk_g2s(r.slots_s + slot * (SO3_SLOT_FLOATS * 4), src, bytes, bar);
+  tma_bulk_g2s(r.slots_s + slot * (uint32_t)(r.slot_floats * 4), src, bytes, bar);
 }
 // every thread, at the start of an evaluation
 template <class Stream>
@@ -113,7 +116,7 @@ __device__ __forceinline__ const float* ring_acquire(So3Ring& r, int tid, const 
   mbar_wait(r.bars_s + 8 * slot, (g / (uint32_t)r.n_slots) & 1u);
   __syncthreads();                 // everyone is done with chunk g-1 (and sees the activations written before this point)
   if (tid == 0) ring_issue(r, g + r.n_slots - 1, stream);
-  return r.slots + slot * SO3_SLOT_FLOATS;
+  return r.slots + slot * r.slot_floats;
 }
 // every thread, before the kernel exits: the copies issued ahead must have landed
 __device__ __forceinline__ void ring_drain(So3Ring& r) {

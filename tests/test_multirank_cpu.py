@@ -94,3 +94,50 @@ def test_two_rank_arena_allreduce():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]
+
+
+def _arena_all_stage_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from samplenerfro_b200 import models, train, utils
+    gen = torch.Generator().manual_seed(0)
+    so3 = models.init_small_mlp_params(gen, "cpu", in_dim=60, out_std=1e-5)
+    want_image = torch.cat([so3[f"Dense_{i}"]["kernel"].reshape(-1) for i in range(5)] +
+                           [so3[f"Dense_{i}"]["bias"].reshape(-1) for i in range(5)]).clone()
+    V = {"params": {"coarse_mlp": models.init_nerf_mlp_params(gen, "cpu"), "fine_mlp": models.init_nerf_mlp_params(gen, "cpu"),
+                    "bkgd_mlp": models.init_small_mlp_params(gen, "cpu"),
+                    "path_sampler": {"scan": {"idx_model": {"so3_mlp": so3}}}}}
+    state = train.TrainState.create(V, utils.Flags(stage="all"))
+    arena = state.arena
+    names = train.ALL_STAGE_BUCKETS
+    ok = arena.buckets == names and len(arena.bucket_grads()) == 4
+    # the so3 bucket is the march kernels' weight image (5 kernels, then 5 biases), dense, and its gradient view is the sink
+    ok = ok and bool(torch.equal(arena.theta_flat["so3_mlp"], want_image))
+    ok = ok and arena.sinks["so3_mlp"].numel() == want_image.numel() == 64896 + 4 * 128 + 3
+    leaf = V["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]["Dense_3"]["kernel"]
+    ok = ok and leaf.requires_grad and leaf.grad.data_ptr() == arena.sinks["so3_mlp"][7680 + 2 * 16384:].data_ptr()
+    # a kernel that accumulates into the sink (the reverse sweep does) is seen by the leaves and by the all-reduce
+    arena.sinks["so3_mlp"].add_(float(rank + 1))
+    loss = sum(p.sum() for n in train.GRAD_BUCKETS for p in train.tree_leaves(V["params"][n])) * (rank + 1)
+    loss.backward()
+    arena.allreduce_mean(world)
+    leaves = [p for n in names for p in train.tree_leaves(V["params"][n])]
+    ok = ok and all(bool(torch.allclose(p.grad, torch.full((1,), 1.5))) for p in leaves)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_arena_allreduce_all_stage():
+    """"all" stage (train.py:302-310): so3_mlp is a fourth bucket laid out as the march kernels' weight image; gradients a
+    kernel accumulates into its sink are averaged over ranks like the others."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_arena_all_stage_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True]
