@@ -217,6 +217,70 @@ def render_view(render_fn: Callable, camtoworld, height: int, width: int, rng, f
     return render_image(render_fn, rays, rng, normalize_disp, chunk=chunk)
 
 
+def band_rows(height: int, rank: int, world_size: int):
+    """Image rows [r0, r1) of `rank` when a frame is cut into `world_size` bands of ceil(H / N) rows (the last bands may be
+    short or empty) -> (r0, r1, rows_per_band)."""
+    per = -(-height // world_size)
+    r0 = min(rank * per, height)
+    return r0, min(r0 + per, height), per
+
+
+def _gather_bands(local: List[torch.Tensor], height: int, width: int, per: int, world_size: int, group=None):
+    """all_gather of per-rank row bands ([rows*W, C] each, C = 3 + 1 + 1) into [H*W, C] on every rank; bands are padded to
+    `per` rows by edge replication so that all ranks contribute equally sized tiles (like rnerf/utils.py:357-361 pads)."""
+    import torch.distributed as dist
+    tile = torch.cat(local, dim=-1)              # [rows*W, 5]
+    want = per * width
+    if tile.shape[0] < want:
+        fill = tile[-1:] if tile.shape[0] else tile.new_zeros(1, tile.shape[1])
+        tile = torch.cat([tile, fill.expand(want - tile.shape[0], -1)], dim=0)
+    tiles = [torch.empty_like(tile) for _ in range(world_size)]
+    dist.all_gather(tiles, tile.contiguous(), group=group)
+    return torch.cat(tiles, dim=0)[:height * width]
+
+
+def render_image_sharded(render_fn: Callable, rays: Rays, rng, normalize_disp: bool, chunk: int = 8192, rank: int = 0,
+                         world_size: int = 1, group=None):
+    """render_image with the frame's rows partitioned over `world_size` processes (one per GPU): every rank renders its
+    band -- rays are independent, so there is no data-path collective -- and the bands are all-gathered, which is the
+    role of `jax.lax.all_gather(..., "batch")` in eval.py:96.  Returns the full (rgb, distance, acc) on every rank."""
+    height, width = rays[0].shape[:2]
+    r0, r1, per = band_rows(height, rank, world_size)
+    if r1 > r0:
+        band = namedtuple_map(lambda r: r[r0:r1], rays)
+        rgb, dist_, acc = render_image(render_fn, band, rng, False, chunk=chunk)
+        local = [rgb.reshape(-1, 3), dist_.reshape(-1, 1), acc.reshape(-1, 1)]
+    else:
+        ref = rays[0]
+        local = [torch.zeros(0, c, device=ref.device, dtype=torch.float32) for c in (3, 1, 1)]
+    full = _gather_bands(local, height, width, per, world_size, group) if world_size > 1 else torch.cat(local, dim=-1)
+    rgb, distance, acc = full[:, 0:3], full[:, 3:4], full[:, 4:5]
+    if normalize_disp:
+        distance = (distance - distance.min()) / (distance.max() - distance.min())
+    return rgb.reshape(height, width, 3), distance.reshape(height, width, 1), acc.reshape(height, width, 1)
+
+
+def render_view_sharded(render_fn: Callable, camtoworld, height: int, width: int, rng, focal: Optional[float] = None,
+                        cam_mat=None, use_pixel_centers: bool = True, normalize_disp: bool = False, chunk: int = 8192,
+                        rank: int = 0, world_size: int = 1, group=None, device="cuda"):
+    """render_view over `world_size` GPUs: each rank generates ONLY its band's rays on its device (rnerf_generate_rays
+    takes a row range), renders them and the bands are all-gathered (config D of BASELINE.json: one frame, 8 x B200)."""
+    from . import ops
+    r0, r1, per = band_rows(height, rank, world_size)
+    if r1 > r0:
+        o, d, v, r = ops.generate_rays(camtoworld, height, width, focal=focal, cam_mat=cam_mat,
+                                       use_pixel_centers=use_pixel_centers, row0=r0, n_rows=r1 - r0, device=device)
+        rgb, dist_, acc = render_image(render_fn, Rays(o, d, v, r), rng, False, chunk=chunk)
+        local = [rgb.reshape(-1, 3), dist_.reshape(-1, 1), acc.reshape(-1, 1)]
+    else:
+        local = [torch.zeros(0, c, device=device, dtype=torch.float32) for c in (3, 1, 1)]
+    full = _gather_bands(local, height, width, per, world_size, group) if world_size > 1 else torch.cat(local, dim=-1)
+    rgb, distance, acc = full[:, 0:3], full[:, 3:4], full[:, 4:5]
+    if normalize_disp:
+        distance = (distance - distance.min()) / (distance.max() - distance.min())
+    return rgb.reshape(height, width, 3), distance.reshape(height, width, 1), acc.reshape(height, width, 1)
+
+
 def image_psnr(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """compute_psnr(mean((pred - target)^2)) with the reduction on the device (eval.py's per-image metric)."""
     from . import ops

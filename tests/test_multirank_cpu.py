@@ -141,3 +141,45 @@ def test_two_rank_arena_allreduce_all_stage():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]
+
+
+def _fake_render_fn(key_0, key_1, rays):
+    """Stands in for model.apply on CPU: any per-ray function will do (rays are independent)."""
+    rgb = torch.sin(rays.origins * 3.0 + rays.viewdirs)
+    dist_ = (rays.origins * rays.viewdirs).sum(-1)
+    acc = rays.viewdirs.abs().sum(-1)
+    return [(rgb, dist_, acc, acc[:, None], rgb)], torch.zeros(())
+
+
+def _sharded_render_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from samplenerfro_b200 import utils
+    gen = torch.Generator().manual_seed(0)
+    ok = True
+    for (H, W) in ((5, 7), (1, 4), (8, 3)):                       # H not divisible by N; fewer rows than ranks; even split
+        rays = utils.Rays(torch.randn(H, W, 3, generator=gen), torch.randn(H, W, 3, generator=gen),
+                          torch.randn(H, W, 3, generator=gen), torch.rand(H, W, 1, generator=gen))
+        want = utils.render_image(_fake_render_fn, rays, 0, True, chunk=6)
+        got = utils.render_image_sharded(_fake_render_fn, rays, 0, True, chunk=6, rank=rank, world_size=world)
+        ok = ok and all(bool(torch.equal(a, b)) for a, b in zip(want, got))
+        r0, r1, per = utils.band_rows(H, rank, world)
+        ok = ok and 0 <= r0 <= r1 <= H and per * world >= H
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_render_gathers_the_frame():
+    """Render partitioning (SURVEY 8(e)): row bands per rank, no data-path collective, bands all-gathered like eval.py:96;
+    the assembled frame equals the single-process render_image bit for bit, ragged splits included."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_render_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True]
