@@ -202,7 +202,11 @@ int rnerf_sq_err(const float* a, const float* b, int64_t n, float* out_accum, vo
  * rnerf_march_all_bwd: reverse sweep of the scan (rnerf/eikonal_utils.py:30-49,75-82).  path/rec_floats: the records
  *   written by rnerf_march_all_fwd for the same inputs; jitter[Nc]: strictly increasing march-step indices;
  *   d_pos_c/d_dir_c: [B][Nc][3] loss gradients; so3_wt: rnerf_so3_transpose(so3_w).  g_so3 (layout of so3_w) is
- *   ACCUMULATED into; d_origins/d_viewdirs [B][3] (gradients wrt the ray, not used by train.py) may be NULL. */
+ *   ACCUMULATED into; d_origins/d_viewdirs [B][3] (gradients wrt the ray, not used by train.py) may be NULL.
+ *   Extension without a reference counterpart (the reference keeps the grid constant; BASELINE.json's north_star asks for
+ *   "learned IoR-grid" gradients): d_table [G^3][4] or NULL is ACCUMULATED with the gradient wrt the (n, grad n) table, and
+ *   rnerf_grid_table_bwd takes it on to the n-grid (adjoint of rnerf_grid_table).  so3_w may be NULL (radiance stage: the
+ *   sweep then only yields the ray / table gradients; so3_wt, so3_window_host, g_so3 are ignored). */
 /* VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267) on free-standing points: pred[N][3] = rodrigues(so3_mlp(
  * annealed_pos_enc(pts)), cond) -- the evaluation behind PathSampler.compute_normal_loss_and_smooth
  * (rnerf/eikonal_utils.py:84-98). */
@@ -221,7 +225,9 @@ int rnerf_march_all_bwd(const float* table, const float* bricks, const int ndim_
                         const double nmax_host[3], const float* path, int rec_floats, int64_t n_rays, double near,
                         double far, int n_steps, const int32_t* jitter, int n_coarse, const float* d_pos_c,
                         const float* d_dir_c, const float* so3_w, const float* so3_wt, const double so3_window_host[10],
-                        float* g_so3, float* d_origins, float* d_viewdirs, void* stream);
+                        float* g_so3, float* d_origins, float* d_viewdirs, float* d_table, void* stream);
+int rnerf_grid_table_bwd(const float* d_table, const int ndim_host[3], const double nmin_host[3], const double nmax_host[3],
+                         float* d_n, void* stream);
 
 /* ---- a15: rnerf/models.py:498-503 bd_cut_dist mask: reverse-cumsum(inside bbox) > 0 ---- */
 int rnerf_bbox_tail_mask(const float* pos, int64_t n_rays, int n_samples, const double lo_host[3],

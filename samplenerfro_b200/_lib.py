@@ -69,7 +69,9 @@ SIGNATURES = {
     "rnerf_so3_transpose": (C.c_int, [c_f32p, c_f32p, C.c_void_p]),
     "rnerf_march_all_bwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                       C.c_int, c_i64, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, c_f32p, c_f32p,
-                                      c_f32p, c_f32p, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, C.c_void_p]),
+                                      c_f32p, c_f32p, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_grid_table_bwd": (C.c_int, [c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
+                                       C.c_void_p]),
     "rnerf_composite_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,
                                       C.c_double, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_composite_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,

@@ -112,13 +112,32 @@ def bkgd_color(model, variables: Dict, viewdirs: torch.Tensor) -> torch.Tensor:
 SO3_SORT_MAX_RAYS = 16384
 
 
-def _activity_order(model, origins, viewdirs):
+class _GridTable(torch.autograd.Function):
+    """(n, grad n) table of a LEARNED IoR grid (extension, no reference counterpart): forward = VoxMLP.setup's table
+    (rnerf_grid_table), backward = its adjoint (rnerf_grid_table_bwd)."""
+
+    @staticmethod
+    def forward(ctx, model, grid_n):
+        ctx.model = model
+        return ops.grid_table(grid_n, model.ndim, model.nmin, model.nmax)
+
+    @staticmethod
+    def backward(ctx, d_table):
+        m = ctx.model
+        return None, ops.grid_table_bwd(d_table.contiguous(), m.ndim, m.nmin, m.nmax)
+
+
+def grid_table(model, grid_n: torch.Tensor) -> torch.Tensor:
+    return _GridTable.apply(model, grid_n)
+
+
+def _activity_order(model, table, bricks, origins, viewdirs):
     """Permutation that groups rays by the march steps at which they need so3_mlp (first and last step with |grad n| > 1e-3,
     found by a radiance-stage march: the entry step is not affected by the rotation).  A CTA of the so3 kernels
     evaluates the MLP at the union of its rays' active steps, so a batch of random pixels costs every CTA nearly the whole
     active range; sorted, CTAs of rays that miss the object do none and the others only their own short range."""
-    path = ops.march(model.table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
-                     model.num_march_steps, bricks=model.bricks, compact=False, t_col=False)
+    path = ops.march(table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
+                     model.num_march_steps, bricks=bricks, compact=False, t_col=False)
     act = path.rec[..., 8:11].norm(dim=-1) > 1e-3
     S = act.shape[1]
     k = torch.arange(S, device=act.device)
@@ -130,17 +149,19 @@ def _activity_order(model, origins, viewdirs):
 class _MarchAll(torch.autograd.Function):
     """PathSampler + coarse selection with so3_mlp in the loop.  Differentiable outputs: pos_c, dir_c (the only way a
     loss reaches the scan: ray_dist is stop_gradient, rnerf/eikonal_utils.py:120, and so are the fine samples,
-    rnerf/model_utils.py:406-411).  Backward = the reverse sweep kernel (rnerf_march_all_bwd)."""
+    rnerf/model_utils.py:406-411).  Backward = the reverse sweep kernel (rnerf_march_all_bwd): gradients of so3_mlp and,
+    when `table` requires grad (learned IoR grid, extension), of the table.  `w` is None in the radiance stage."""
 
     @staticmethod
-    def forward(ctx, model, sink, w, window, origins, viewdirs, jitter, compact, *params):
+    def forward(ctx, model, sink, w, window, origins, viewdirs, jitter, compact, table, bricks, *params):
         import os
         perm = None
-        if 256 < origins.shape[0] <= SO3_SORT_MAX_RAYS and os.environ.get("RNERF_SO3_SORT", "1") != "0":
-            perm = _activity_order(model, origins, viewdirs)
+        so3 = (w, window) if w is not None else None
+        if so3 is not None and 256 < origins.shape[0] <= SO3_SORT_MAX_RAYS and os.environ.get("RNERF_SO3_SORT", "1") != "0":
+            perm = _activity_order(model, table, bricks, origins, viewdirs)
             origins, viewdirs = origins[perm].contiguous(), viewdirs[perm].contiguous()
-        path = ops.march(model.table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
-                         model.num_march_steps, bricks=model.bricks, compact=compact, so3=(w, window))
+        path = ops.march(table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
+                         model.num_march_steps, bricks=bricks, compact=compact, so3=so3)
         pos_c, dir_c, t_c, _ = ops.select(path, jitter)
         ctx.model, ctx.sink, ctx.window = model, sink, window
         rec, t_col = path.rec, path.t
@@ -148,32 +169,43 @@ class _MarchAll(torch.autograd.Function):
             inv = torch.empty_like(perm)
             inv[perm] = torch.arange(perm.numel(), device=perm.device)
             pos_c, dir_c, t_c, rec, t_col = pos_c[inv], dir_c[inv], t_c[inv], rec[inv], t_col[inv]
-        ctx.save_for_backward(w, path.rec, jitter, perm if perm is not None else jitter.new_empty(0))
+        none = jitter.new_empty(0)
+        ctx.save_for_backward(w if w is not None else none, path.rec, jitter, perm if perm is not None else none, table,
+                              bricks if bricks is not None else none)
         ctx.mark_non_differentiable(t_c, rec, t_col)
         return pos_c, dir_c, t_c, rec, t_col
 
     @staticmethod
     def backward(ctx, d_pos_c, d_dir_c, _dt, _drec, _dtcol):
-        w, rec, jitter, perm = ctx.saved_tensors
+        w, rec, jitter, perm, table, bricks = ctx.saved_tensors
         m = ctx.model
 
         def z(g):
             g = torch.zeros(rec.shape[0], jitter.numel(), 3, device=rec.device) if g is None else g
             return g[perm] if perm.numel() else g
 
-        g, _, _ = ops.march_all_bwd(m.table, m.ndim, m.nmin, m.nmax, rec, m.near, m.far, jitter, z(d_pos_c), z(d_dir_c),
-                                    (w, ctx.window), bricks=m.bricks, g_so3=ctx.sink)
-        if ctx.sink is not None:
-            return (None,) * 18
-        return (None,) * 8 + tuple(ops.so3_unpack_views(g))
+        d_table = torch.zeros_like(table) if ctx.needs_input_grad[8] else None
+        so3 = (w, ctx.window) if w.numel() else None
+        g, _, _ = ops.march_all_bwd(table, m.ndim, m.nmin, m.nmax, rec, m.near, m.far, jitter, z(d_pos_c), z(d_dir_c), so3,
+                                    bricks=bricks if bricks.numel() else None, g_so3=ctx.sink if so3 is not None else None,
+                                    d_table=d_table)
+        n_par = len(ctx.needs_input_grad) - 10
+        if ctx.sink is not None or so3 is None:
+            return (None,) * 8 + (d_table, None) + (None,) * n_par
+        return (None,) * 8 + (d_table, None) + tuple(ops.so3_unpack_views(g))
 
 
-def march_all(model, variables: Dict, origins, viewdirs, jitter, annealed_alpha: float, compact: bool):
-    """-> (BentPath, pos_c, dir_c, t_c) with autograd edges from pos_c / dir_c to so3_mlp."""
-    p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
-    w = model._so3_packed(variables)
-    pos_c, dir_c, t_c, rec, t_col = _MarchAll.apply(model, _sink(model, "so3_mlp"), w, model.so3_window(annealed_alpha),
-                                                    origins, viewdirs, jitter, compact, *_mlp_param_list(p, 5))
+def march_all(model, variables: Dict, origins, viewdirs, jitter, annealed_alpha: float, compact: bool, table=None, bricks=None):
+    """-> (BentPath, pos_c, dir_c, t_c) with autograd edges from pos_c / dir_c to so3_mlp ("all" stage) and to `table` when
+    it requires grad."""
+    table = model.table if table is None else table
+    bricks = model.bricks if bricks is None and table is model.table else bricks
+    if model.stage.startswith("all"):
+        p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+        w, window, plist, sink = model._so3_packed(variables), model.so3_window(annealed_alpha), _mlp_param_list(p, 5), _sink(model, "so3_mlp")
+    else:
+        w, window, plist, sink = None, None, [], None
+    pos_c, dir_c, t_c, rec, t_col = _MarchAll.apply(model, sink, w, window, origins, viewdirs, jitter, compact, table, bricks, *plist)
     return ops.BentPath(rec, t_col), pos_c, dir_c, t_c
 
 

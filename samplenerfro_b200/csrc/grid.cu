@@ -51,6 +51,36 @@ __global__ void __launch_bounds__(256) table_kernel(const float* __restrict__ n,
   }
 }
 
+// Adjoint of table_kernel (extension, no reference counterpart: a learned IoR grid): d_n[i] = d_table[i].n + the transposed
+// central differences, edge clamping included (n[0] and n[G-1] each enter their own boundary difference twice).
+__global__ void __launch_bounds__(256) table_bwd_kernel(const float4* __restrict__ dt, float* __restrict__ dn, GridGeom g) {
+  const int64_t total = (int64_t)g.gx * g.gy * g.gz;
+  const int64_t sx = (int64_t)g.gy * g.gz, sy = g.gz;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i % g.gz), y = (int)((i / g.gz) % g.gy), x = (int)(i / ((int64_t)g.gz * g.gy));
+    float acc = __ldg(dt + i).x;
+    float s = 0.f;
+    if (x >= 1) s += __ldg(dt + i - sx).y;
+    if (x == g.gx - 1) s += __ldg(dt + i).y;
+    if (x <= g.gx - 2) s -= __ldg(dt + i + sx).y;
+    if (x == 0) s -= __ldg(dt + i).y;
+    acc += s / g.two_ndelta[0];
+    s = 0.f;
+    if (y >= 1) s += __ldg(dt + i - sy).z;
+    if (y == g.gy - 1) s += __ldg(dt + i).z;
+    if (y <= g.gy - 2) s -= __ldg(dt + i + sy).z;
+    if (y == 0) s -= __ldg(dt + i).z;
+    acc += s / g.two_ndelta[1];
+    s = 0.f;
+    if (z >= 1) s += __ldg(dt + i - 1).w;
+    if (z == g.gz - 1) s += __ldg(dt + i).w;
+    if (z <= g.gz - 2) s -= __ldg(dt + i + 1).w;
+    if (z == 0) s -= __ldg(dt + i).w;
+    acc += s / g.two_ndelta[2];
+    dn[i] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(256) lookup_kernel(const float4* __restrict__ table, GridGeom g,
                                                      const float* __restrict__ pts, int64_t n_pts,
                                                      float4* __restrict__ out) {
@@ -128,6 +158,18 @@ extern "C" int rnerf_grid_table(const float* n, const int ndim[3], const double 
   table_kernel<<<grid_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(n, (float4*)table, g);
   count_launch();
   return check_launch("rnerf_grid_table");
+}
+
+extern "C" int rnerf_grid_table_bwd(const float* d_table, const int ndim[3], const double nmin[3], const double nmax[3],
+                                    float* d_n, void* stream) {
+  RNERF_REQUIRE_PTR(d_table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax); RNERF_REQUIRE_PTR(d_n);
+  RNERF_REQUIRE(ndim[0] > 1 && ndim[1] > 1 && ndim[2] > 1, RNERF_E_SHAPE, "rnerf_grid_table_bwd: every grid side must be >= 2");
+  RNERF_REQUIRE(aligned16(d_table), RNERF_E_ALIGN, "rnerf_grid_table_bwd: d_table must be 16-byte aligned");
+  GridGeom g = make_geom(ndim, nmin, nmax);
+  const int64_t total = (int64_t)ndim[0] * ndim[1] * ndim[2];
+  table_bwd_kernel<<<grid_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_table, d_n, g);
+  count_launch();
+  return check_launch("rnerf_grid_table_bwd");
 }
 
 extern "C" int rnerf_grid_lookup(const float* table, const int ndim[3], const double nmin[3], const double nmax[3],

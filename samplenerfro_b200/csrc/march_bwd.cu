@@ -111,6 +111,34 @@ __device__ __forceinline__ void lookup_with_jacobian(const float4* __restrict__ 
 #undef RNERF_JAC
 }
 
+// Gradient wrt the (n, grad n) table itself (extension: the reference keeps the grid constant): the adjoint
+// (dn, dg) of a lookup is spread over its eight corners with the trilinear weights, one red.global.add.v4.f32 per corner.
+template <bool FAST>
+__device__ __forceinline__ void scatter_table_grad(float4* __restrict__ d_table, const MarchGeom& mg, float px, float py, float pz,
+                                                   float dn, const float dg[3]) {
+  float x, y, z;
+  grid_coords<FAST>(mg, px, py, pz, x, y, z);
+  const float xf = floorf(x), yf = floorf(y), zf = floorf(z);
+  const float xd = x - xf, yd = y - yf, zd = z - zf;
+  const float mx = (float)(mg.g.gx - 1), my = (float)(mg.g.gy - 1), mz = (float)(mg.g.gz - 1);
+  const int xi[2] = {(int)fminf(fmaxf(xf, 0.f), mx), (int)fminf(fmaxf(xf + 1.f, 0.f), mx)};
+  const int yi[2] = {(int)fminf(fmaxf(yf, 0.f), my), (int)fminf(fmaxf(yf + 1.f, 0.f), my)};
+  const int zi[2] = {(int)fminf(fmaxf(zf, 0.f), mz), (int)fminf(fmaxf(zf + 1.f, 0.f), mz)};
+  const float wx[2] = {1.f - xd, xd}, wy[2] = {1.f - yd, yd}, wz[2] = {1.f - zd, zd};
+  const int sx = mg.g.gy * mg.g.gz, sy = mg.g.gz;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float w = wx[a] * wy[b] * wz[c];
+        float4* dst = d_table + (sx * xi[a] + sy * yi[b] + zi[c]);
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(w * dn), "f"(w * dg[0]), "f"(w * dg[1]),
+                     "f"(w * dg[2]) : "memory");
+      }
+}
+
 // ---- Rodrigues rotation (rnerf/ior_utils.py:300-306), reverse mode ------------------------------------------------------
 // pred = a (cos(th) v + sin(th) e x v + (1 - cos(th)) (e.v) e), th = |r|_safe, e = r/th, a = |g|_safe, v = g/a.
 // Given d pred, returns d r and d g.
@@ -494,7 +522,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) march_all_bwd_kernel(
     const float4* __restrict__ table, const MarchGeom mg, const float* __restrict__ bricks, const float4* __restrict__ path,
     int recf4, int64_t n_rays, float near, float step, int n_steps, const int32_t* __restrict__ jitter, int n_coarse,
     const float* __restrict__ d_pos_c, const float* __restrict__ d_dir_c, const So3BwdArgs so3, float* __restrict__ d_origins,
-    float* __restrict__ d_viewdirs, int rays_per_cta) {
+    float* __restrict__ d_viewdirs, int rays_per_cta, float4* __restrict__ d_table) {
   extern __shared__ __align__(16) float sm[];
   int* cnt = reinterpret_cast<int*>(sm + BW_ACT_FLOATS);
   float* ring_mem = sm + BW_ACT_FLOATS + 16 + 2 * SO3_MAX_SLOTS;         // after cnt (64 B) and room for 16 mbarriers (128 B)
@@ -530,8 +558,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) march_all_bwd_kernel(
       const float dn = -(hn / c.x) * (v[0] * lp[0] + v[1] * lp[1] + v[2] * lp[2]);
       const float dG[3] = {step * lv[0], step * lv[1], step * lv[2]};
       float dg[3] = {dG[0], dG[1], dG[2]}, dpm[3] = {0.f, 0.f, 0.f};
-      const bool act = live && sqrtf(sumsq3(g[0], g[1], g[2])) > 1e-3f;     // the forward's test, on the same bits
+      // the forward's test, on the same bits (so3.w == NULL: radiance stage, the sweep only yields ray / table gradients)
+      const bool act = so3.w != nullptr && live && sqrtf(sumsq3(g[0], g[1], g[2])) > 1e-3f;
       if (__syncthreads_or(act)) so3_fwd_bwd(so3, sm, cnt, ring, warp, lane, act, p, g, dG, dg, dpm);
+      if (d_table != nullptr && live) scatter_table_grad<FAST>(d_table, mg, p[0], p[1], p[2], dn, dg);
 #pragma unroll
       for (int i = 0; i < 3; ++i) lv[i] = fmaf(hn, lp[i], lv[i]);
       lp[0] += jx.x * dn + jx.y * dg[0] + jx.z * dg[1] + jx.w * dg[2] + dpm[0];
@@ -579,7 +609,7 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
                                    double far, int n_steps, const int32_t* jitter, int n_coarse, const float* d_pos_c,
                                    const float* d_dir_c, const float* so3_w, const float* so3_wt,
                                    const double so3_window[10], float* g_so3, float* d_origins, float* d_viewdirs,
-                                   void* stream) {
+                                   float* d_table, void* stream) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_rays < 0");
   RNERF_REQUIRE(n_steps >= 2 && n_steps <= 32767, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps must be in [2, 32767]");
@@ -587,9 +617,9 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   RNERF_REQUIRE(rec_floats == 8 || rec_floats == 12, RNERF_E_SHAPE, "rnerf_march_all_bwd: rec_floats must be 8 or 12");
   if (n_rays == 0) return 0;
   RNERF_REQUIRE_PTR(path); RNERF_REQUIRE_PTR(jitter); RNERF_REQUIRE_PTR(d_pos_c); RNERF_REQUIRE_PTR(d_dir_c);
-  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(so3_wt); RNERF_REQUIRE_PTR(so3_window); RNERF_REQUIRE_PTR(g_so3);
-  RNERF_REQUIRE(aligned16(table) && aligned16(path) && aligned16(so3_w) && aligned16(so3_wt) && aligned16(g_so3), RNERF_E_ALIGN,
-                "rnerf_march_all_bwd: table/path/so3 images must be 16-byte aligned");
+  if (so3_w != nullptr) { RNERF_REQUIRE_PTR(so3_wt); RNERF_REQUIRE_PTR(so3_window); RNERF_REQUIRE_PTR(g_so3); }
+  RNERF_REQUIRE(aligned16(table) && aligned16(path) && aligned16(so3_w) && aligned16(so3_wt) && aligned16(g_so3) && aligned16(d_table),
+                RNERF_E_ALIGN, "rnerf_march_all_bwd: table/path/so3 images/d_table must be 16-byte aligned");
   RNERF_REQUIRE(grid_fits_int32(ndim), RNERF_E_SHAPE, "rnerf_march_all_bwd: grids with >= 2^31 voxels are not supported");
   cudaStream_t st = (cudaStream_t)stream;
   MarchGeom mg;
@@ -597,7 +627,7 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   const float step = (float)((far - near) / (n_steps - 1));
   So3BwdArgs a;
   a.w = so3_w; a.wt = so3_wt; a.gw = g_so3;
-  for (int k = 0; k < 10; ++k) a.window[k] = (float)so3_window[k];
+  for (int k = 0; k < 10; ++k) a.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
   const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 64 + 8 * SO3_MAX_SLOTS + (size_t)BW_RING_SLOTS * BW_SLOT_FLOATS * 4 +
                      (((size_t)n_steps * 2 + 15) & ~(size_t)15);
   RNERF_REQUIRE(dyn <= 227 * 1024, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps too large for the step map in shared memory");
@@ -612,11 +642,11 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   if (fast)
     march_all_bwd_kernel<true><<<blocks, BW_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
                                                                    n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
-                                                                   d_dir_c, a, d_origins, d_viewdirs, rpc);
+                                                                   d_dir_c, a, d_origins, d_viewdirs, rpc, (float4*)d_table);
   else
     march_all_bwd_kernel<false><<<blocks, BW_THREADS, dyn, st>>>((const float4*)table, mg, bricks, (const float4*)path, rec_floats / 4,
                                                                     n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
-                                                                    d_dir_c, a, d_origins, d_viewdirs, rpc);
+                                                                    d_dir_c, a, d_origins, d_viewdirs, rpc, (float4*)d_table);
   count_launch();
   return check_launch("rnerf_march_all_bwd");
 }

@@ -118,6 +118,8 @@ class NerfModel:
         self.table = ops.grid_table(g, self.ndim, self.nmin, self.nmax)
         self.bricks = ops.grid_bricks(self.table, self.ndim)   # access-skipping aid for the march (bit-identical results)
         self.num_march_steps = self.num_coarse_samples * self.num_path_samples  # rnerf/models.py:121
+        self.grid_n: Optional[torch.Tensor] = None   # extension: a learned IoR grid (enable_grid_learning)
+        self._grid_version = None
         self._pack_cache: Dict[str, Any] = {}
         self._grad_sink = None       # set by train.train_step: backward kernels accumulate into a ParamArena
         self._theta_flat = None
@@ -133,6 +135,22 @@ class NerfModel:
             "bkgd_mlp": init_small_mlp_params(gen, device),
             "path_sampler": {"scan": {"idx_model": {"so3_mlp": init_small_mlp_params(gen, device, in_dim=60, out_std=1e-5)}}},
         }}
+
+    def enable_grid_learning(self) -> torch.Tensor:
+        """Extension without a reference counterpart (the reference keeps the grid constant; BASELINE.json's
+        north_star asks for learned IoR-grid gradients): makes the n-grid a trainable leaf `model.grid_n` [G^3].  With it,
+        `apply` rebuilds the (n, grad n) table from `grid_n` whenever it changed and `loss.backward()` leaves
+        d loss / d grid in `grid_n.grad` (reverse sweep of the scan -> table adjoint); all-reduce it like any gradient."""
+        self.grid_n = self.table.view(-1, 4)[:, 0].clone().requires_grad_(True)
+        self._grid_version = self.grid_n._version
+        return self.grid_n
+
+    def _refresh_table(self) -> None:
+        if self.grid_n is not None and self.grid_n._version != self._grid_version:
+            with torch.no_grad():
+                self.table = ops.grid_table(self.grid_n.detach(), self.ndim, self.nmin, self.nmax)
+                self.bricks = ops.grid_bricks(self.table, self.ndim)
+            self._grid_version = self.grid_n._version
 
     def _packed(self, variables: Dict, name: str) -> torch.Tensor:
         """Device image of one MLP's weights; repacked only when a parameter tensor changed."""
@@ -249,7 +267,17 @@ class NerfModel:
         need_grad = debug or self.use_online_sparsity
         jit = self.draw_jitter(k0) if jitter is None else torch.as_tensor(jitter).to(self.device, torch.int32).contiguous()
         so3_p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"] if self.stage.startswith("all") else None
-        if so3_p is not None and ag._needs_grad(so3_p):
+        self._refresh_table()
+        learn_grid = self.grid_n is not None and self.grid_n.requires_grad and torch.is_grad_enabled()
+        if learn_grid:
+            # extension: the table as a differentiable function of the learned grid (same values as self.table)
+            path, pos_c, dir_c, t_c = ag.march_all(self, variables, origins, viewdirs, jit, annealed_alpha, not need_grad,
+                                                   table=ag.grid_table(self, self.grid_n), bricks=self.bricks)
+            grad_c = None
+            if self.use_online_sparsity:
+                with torch.no_grad():
+                    grad_c = ops.select(path, jit, want_grad=True)[3]
+        elif so3_p is not None and ag._needs_grad(so3_p):
             # "all" stage, training: so3_mlp rotates grad n inside every step (a4) and is reached by the loss through the
             # coarse samples; the reverse sweep of the scan is its own kernel
             path, pos_c, dir_c, t_c = ag.march_all(self, variables, origins, viewdirs, jit, annealed_alpha, not need_grad)

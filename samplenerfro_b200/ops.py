@@ -212,17 +212,33 @@ def so3_transpose(w: torch.Tensor) -> torch.Tensor:
 
 
 def march_all_bwd(table, ndim, nmin, nmax, path, near: float, far: float, jitter: torch.Tensor, d_pos_c: torch.Tensor,
-                  d_dir_c: torch.Tensor, so3: Tuple[torch.Tensor, Sequence[float]], bricks: Optional[torch.Tensor] = None,
-                  g_so3: Optional[torch.Tensor] = None, want_ray_grads: bool = False):
+                  d_dir_c: torch.Tensor, so3: Optional[Tuple[torch.Tensor, Sequence[float]]], bricks: Optional[torch.Tensor] = None,
+                  g_so3: Optional[torch.Tensor] = None, want_ray_grads: bool = False, d_table: Optional[torch.Tensor] = None):
     """Reverse sweep of the "all"-stage scan (rnerf/eikonal_utils.py:30-49,75-82 under jax.value_and_grad, train.py:164):
     from the loss gradients of the coarse samples, d_pos_c / d_dir_c [B,Nc,3] at march steps `jitter` (strictly
     increasing), to the gradient of so3_mlp.  Returns (g_so3 [so3 image layout, accumulated into when given],
-    d_origins, d_viewdirs [B,3] or None)."""
+    d_origins, d_viewdirs [B,3] or None).
+    Extension (no reference counterpart): `d_table` [G^3,4], when given, is ACCUMULATED with the gradient wrt the (n, grad n)
+    table (take it on to the n-grid with grid_table_bwd); `so3=None` sweeps a radiance-stage path (g_so3 is then None)."""
     rec = _rec(path); jitter = _chk(jitter, "jitter", torch.int32)
     B, S, W = rec.shape
     Nc = jitter.numel()
-    w, window = so3
-    _chk(w, "so3 weights"); _chk(table, "table")
+    w, window = so3 if so3 is not None else (None, None)
+    _chk(table, "table")
+    if d_table is not None:
+        _chk(d_table, "d_table")
+        assert d_table.numel() == table.numel()
+    if w is None:
+        d_pos_c = _chk(d_pos_c.contiguous(), "d_pos_c"); d_dir_c = _chk(d_dir_c.contiguous(), "d_dir_c")
+        assert d_pos_c.shape == (B, Nc, 3) and d_dir_c.shape == (B, Nc, 3)
+        d_o = torch.empty(B, 3, device=rec.device) if want_ray_grads else None
+        d_d = torch.empty(B, 3, device=rec.device) if want_ray_grads else None
+        nd, lo, hi = _geom(ndim, nmin, nmax)
+        check(_lib.load().rnerf_march_all_bwd(_p(table), _p(bricks), nd, lo, hi, _p(rec), W, B, float(near), float(far), S,
+                                              _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), None, None, None, None, _p(d_o),
+                                              _p(d_d), _p(d_table), _stream()), "rnerf_march_all_bwd")
+        return None, d_o, d_d
+    _chk(w, "so3 weights")
     d_pos_c = _chk(d_pos_c.contiguous(), "d_pos_c"); d_dir_c = _chk(d_dir_c.contiguous(), "d_dir_c")
     assert d_pos_c.shape == (B, Nc, 3) and d_dir_c.shape == (B, Nc, 3) and len(window) == 10
     if bricks is not None:
@@ -236,8 +252,17 @@ def march_all_bwd(table, ndim, nmin, nmax, path, near: float, far: float, jitter
     win = (C.c_double * 10)(*[float(v) for v in window])
     check(_lib.load().rnerf_march_all_bwd(_p(table), _p(bricks), nd, lo, hi, _p(rec), W, B, float(near), float(far), S,
                                           _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), _p(w), _p(wt), win, _p(g), _p(d_o),
-                                          _p(d_d), _stream()), "rnerf_march_all_bwd")
+                                          _p(d_d), _p(d_table), _stream()), "rnerf_march_all_bwd")
     return g, d_o, d_d
+
+
+def grid_table_bwd(d_table: torch.Tensor, ndim, nmin, nmax) -> torch.Tensor:
+    """Adjoint of grid_table (extension: gradients of a learned IoR grid): d_table [G^3,4] -> d_n [G^3]."""
+    _chk(d_table, "d_table")
+    d_n = torch.empty(d_table.numel() // 4, device=d_table.device, dtype=torch.float32)
+    nd, lo, hi = _geom(ndim, nmin, nmax)
+    check(_lib.load().rnerf_grid_table_bwd(_p(d_table), nd, lo, hi, _p(d_n), _stream()), "rnerf_grid_table_bwd")
+    return d_n
 
 
 # ---------------------------------------------------------------- encoding-fused radiance MLP (a8, a9)
