@@ -119,7 +119,9 @@ class _GridTable(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, grid_n):
         ctx.model = model
-        return ops.grid_table(grid_n, model.ndim, model.nmin, model.nmax)
+        # rebuilt in place in the model's own 16 B/voxel buffer (2 GiB at 512^3): no per-step allocation, graph-capturable
+        ops.grid_table(grid_n, model.ndim, model.nmin, model.nmax, out=model.table)
+        return model.table.view_as(model.table)
 
     @staticmethod
     def backward(ctx, d_table):

@@ -49,10 +49,11 @@ def grid_blur(n: torch.Tensor, ndim: Sequence[int], ws: int, sigma: float) -> to
     return out.reshape(-1, 1)
 
 
-def grid_table(n: torch.Tensor, ndim, nmin, nmax) -> torch.Tensor:
+def grid_table(n: torch.Tensor, ndim, nmin, nmax, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """VoxMLP.setup (rnerf/ior_utils.py:161): [G^3,4] = (n, grad n)."""
     n = _chk(n.reshape(-1), "n")
-    table = torch.empty(n.numel(), 4, device=n.device, dtype=torch.float32)
+    table = torch.empty(n.numel(), 4, device=n.device, dtype=torch.float32) if out is None else _chk(out, "out")
+    assert table.numel() == 4 * n.numel()
     nd, lo, hi = _geom(ndim, nmin, nmax)
     check(_lib.load().rnerf_grid_table(_p(n), nd, lo, hi, _p(table), _stream()), "rnerf_grid_table")
     return table
@@ -69,12 +70,14 @@ def grid_lookup(table: torch.Tensor, ndim, nmin, nmax, pts: torch.Tensor) -> tor
 
 
 # ---------------------------------------------------------------- march (a5, a6) / select (a7)
-def grid_bricks(table: torch.Tensor, ndim) -> torch.Tensor:
+def grid_bricks(table: torch.Tensor, ndim, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Brick map of a (n, grad n) table: per 8^3-voxel brick the common n, or NaN if the brick is not homogeneous."""
     _chk(table, "table")
     lib = _lib.load()
     nd = Int3(*[int(v) for v in ndim])
-    bricks = torch.empty(int(lib.rnerf_grid_brick_count(nd)), device=table.device, dtype=torch.float32)
+    n_bricks = int(lib.rnerf_grid_brick_count(nd))
+    bricks = torch.empty(n_bricks, device=table.device, dtype=torch.float32) if out is None else _chk(out, "out")
+    assert bricks.numel() == n_bricks
     check(lib.rnerf_grid_bricks(_p(table), nd, _p(bricks), _stream()), "rnerf_grid_bricks")
     return bricks
 

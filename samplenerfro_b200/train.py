@@ -193,6 +193,39 @@ class ArenaAdam:
         self.count += 1
 
 
+class GridAdam:
+    """Extension (no reference counterpart): optax.adam on a learned IoR grid, `model.grid_n` [G^3], with the MLPs' learning
+    rate schedule, no weight decay and no clipping; the same fused kernel as ArenaAdam, its own moments and scalars."""
+
+    def __init__(self, model, arena_opt: "ArenaAdam"):
+        from . import ops
+        self.model, self.ref = model, arena_opt
+        g = model.grid_n
+        g.grad = torch.zeros_like(g)
+        self.mu, self.nu = torch.zeros_like(g), torch.zeros_like(g)
+        self.hyper = torch.zeros(ops.HYPER_FLOATS, device=g.device, dtype=torch.float32)
+        self.ring = _PinnedRing((ops.HYPER_FLOATS,), torch.float32, g.device)
+
+    def stage_hyper(self, lr: float) -> None:
+        t = self.ref.count + 1
+        self.ring.push(torch.tensor([lr, self.ref.b1, self.ref.b2, self.ref.eps, 1.0 - self.ref.b1 ** t, 1.0 - self.ref.b2 ** t,
+                                     1.0, 0.0, 0.0, 0.0], dtype=torch.float32), self.hyper)
+
+    def zero_grad(self) -> None:
+        self.model.grid_n.grad.zero_()
+
+    def allreduce_mean(self, world_size: int, group=None) -> None:
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.model.grid_n.grad, op=dist.ReduceOp.SUM, group=group)
+            self.model.grid_n.grad.mul_(1.0 / world_size)
+
+    def apply(self) -> None:
+        from . import ops
+        g = self.model.grid_n
+        ops.adam_step(g.detach(), g.grad, self.mu, self.nu, self.hyper, None)
+
+
 @dataclasses.dataclass
 class TrainState:
     """flax.training.train_state.TrainState stand-in: step, params (the variables tree), optimiser state."""
@@ -201,19 +234,22 @@ class TrainState:
     opt: Any = None
     arena: Optional[ParamArena] = None
     graphs: Dict = dataclasses.field(default_factory=dict)
+    grid_opt: Optional[GridAdam] = None
 
     def replayed_kernel_launches(self) -> int:
         """Kernels of this library launched through graph replays so far (the eager ones are in _lib.launch_count())."""
         return sum(g.kernels_per_replay * g.replays for g in self.graphs.values() if isinstance(g, _GraphedStep))
 
     @staticmethod
-    def create(variables: Dict, args) -> "TrainState":
+    def create(variables: Dict, args, model=None) -> "TrainState":
         """Re-homes the variables into a ParamArena (the tree keeps its names; leaves become views) and attaches the
         fused Adam.  Radiance stage: path_sampler gets optax.set_to_zero (T7) -> it sits in the frozen tail; "all" stage
         (train.py:302-310): so3_mlp is a fourth trainable bucket, laid out as the march kernels' weight image."""
         stage = str(getattr(args, "stage", "radiance"))
         arena = ParamArena(variables, ALL_STAGE_BUCKETS if stage.startswith("all") else GRAD_BUCKETS)
-        return TrainState(step=0, params=variables, opt=ArenaAdam(arena, args), arena=arena)
+        opt = ArenaAdam(arena, args)
+        grid_opt = GridAdam(model, opt) if model is not None and getattr(model, "grid_n", None) is not None else None
+        return TrainState(step=0, params=variables, opt=opt, arena=arena, grid_opt=grid_opt)
 
 
 def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, arena: Optional[ParamArena] = None):
@@ -293,6 +329,8 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
     gradient + stats all-reduce, fused Adam.  No host synchronisation: capturable in a CUDA graph."""
     arena = state.arena
     arena.zero_grad()
+    if state.grid_opt is not None:
+        state.grid_opt.zero_grad()
     model._grad_sink, model._theta_flat = arena.sinks, arena.theta_flat
     try:
         total, stats = loss_fn(model, state.params, batch, args, key_0, key_1, jitter=jitter, u=u, arena=arena)
@@ -300,6 +338,8 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
     finally:
         model._grad_sink = None
     arena.allreduce_mean(world_size, group)
+    if state.grid_opt is not None:
+        state.grid_opt.allreduce_mean(world_size, group)
     if world_size > 1:
         import torch.distributed as dist
         keys = [k for k, v in stats.items() if torch.is_tensor(v)]
@@ -308,6 +348,8 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
         for k, v in zip(keys, packed / world_size):
             stats[k] = v
     state.opt.apply()
+    if state.grid_opt is not None:
+        state.grid_opt.apply()
     return stats
 
 
@@ -379,6 +421,8 @@ def train_step(model, rng, state: TrainState, batch: Dict, args=None, world_size
     if use_graph is None:
         use_graph = on_cuda and jitter is None and u is None
     state.opt.stage_hyper(lr)
+    if state.grid_opt is not None:
+        state.grid_opt.stage_hyper(lr)
     stats = None
     if use_graph:
         key = _graph_key(batch, args, world_size)

@@ -12,6 +12,8 @@ ap.add_argument("--batch", type=int, default=4096, help="global batch (rays per 
 ap.add_argument("--grid", type=int, default=512)
 ap.add_argument("--eager", action="store_true", help="no CUDA-graph capture of the step")
 ap.add_argument("--stage", default="radiance", help='"radiance" (configs[2]) or "all" (so3_mlp trained through the scan adjoint)')
+ap.add_argument("--learn-grid", action="store_true", help="extension: the IoR grid is a trainable parameter too (gradient by the "
+                "reverse sweep, all-reduced and updated by a fused Adam)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -28,7 +30,9 @@ args = utils.Flags(config="ship_skydome-bkgd_no-partial-reflect_cycles", num_pat
                    use_online_sparsity=False, bg_weight=0.025, bg_smooth_weight=1.0, bg_patch_size=128, randomized=True,
                    max_steps=200000, lr_delay_steps=2500, lr_delay_mult=0.01, stage=a.stage)
 model, variables = models.construct_nerf(0, None, args, ndim, nmin, nmax, n)
-state = train.TrainState.create(variables, args)
+if a.learn_grid:
+    model.enable_grid_learning()
+state = train.TrainState.create(variables, args, model=model)
 B = a.batch // world
 rays_hw = synthetic.blender_rays(synthetic.camera_pose(0.7, 1.0, 4.03), 800, 800)
 flat = utils.namedtuple_map(lambda r: r.reshape(-1, r.shape[-1]), rays_hw)
@@ -69,7 +73,7 @@ if world > 1:
 if rank == 0:
     print(json.dumps({"metric": "training rays/sec (fwd+bwd+allreduce+Adam)", "value": a.batch * a.steps / (ms * 1e-3),
                       "unit": "rays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-                      "scaling": "strong", "global_batch": a.batch, "stage": a.stage, "cuda_graph": not a.eager, "gpu_launches": int(_lib.launch_count() + state.replayed_kernel_launches() - l0),
+                      "scaling": "strong", "global_batch": a.batch, "stage": a.stage, "learn_grid": a.learn_grid, "cuda_graph": not a.eager, "gpu_launches": int(_lib.launch_count() + state.replayed_kernel_launches() - l0),
                       "loss": float(stats["loss"]), "cpu_issue_ms_per_step": cpu_issue_ms, "config": "ship_skydome training step, S=768, G=%d, 64+192 samples, "
                       "bg_weight 0.025, bg_smooth 1.0 on a 128x128 env patch" % G}))
 if world > 1:

@@ -348,3 +348,36 @@ def test_learned_grid_training_gradient(cuda_lib):
         before = model.table.clone()
         model.apply(variables, 1, 2, batch["rays"], False, jitter=jitter, u=O.deterministic_u(128))
     assert (model.table.view(-1, 4)[:, 0] - before.view(-1, 4)[:, 0] - 0.01).abs().max().item() < 1e-6
+
+
+def test_learned_grid_train_step(cuda_lib):
+    """train_step with a learned grid (extension): eager steps, then CUDA-graph replays; the grid moves only where rays
+    passed, the table / brick map follow it, the loss stays finite and falls."""
+    from samplenerfro_b200 import models, ops, train, utils
+    n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
+    args = utils.Flags(config="example", num_path_samples=12, white_bkgd=False, use_online_sparsity=False, bg_weight=0.025,
+                       bg_smooth_weight=0.0, randomized=True, max_steps=200000, lr_delay_steps=0)
+    model, variables = models.construct_nerf(3, None, args, ndim, nmin, nmax, n)
+    grid_n = model.enable_grid_learning()
+    state = train.TrainState.create(variables, args, model=model)
+    assert state.grid_opt is not None
+    B = 128
+    o, d = H.random_rays(B, seed=7, target_extent=0.6)
+    gen = torch.Generator().manual_seed(2)
+    batch = {"rays": utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(B, 1).cuda()), "pixels": torch.rand(B, 3, generator=gen).cuda() * 0 + 0.2,
+             "env_rays": None, "annealed_alpha": 0.5}
+    before = grid_n.detach().clone()
+    losses, rng = [], 0
+    state.step = 1
+    for _ in range(8):
+        state, stats, rng = train.train_step(model, rng, state, batch, args)
+        losses.append(float(stats["loss"]))
+    assert any(isinstance(g, train._GraphedStep) for g in state.graphs.values())
+    assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0], losses
+    moved = (grid_n.detach() - before).abs()
+    assert torch.isfinite(grid_n).all() and moved.max().item() > 0
+    assert (moved == 0).float().mean().item() > 0.05          # voxels no ray came near keep their value exactly
+    with torch.no_grad():                                     # eval after training: table and bricks rebuilt from the grid
+        model.apply(variables, 1, 2, batch["rays"], False)
+    assert torch.equal(model.table.view(-1, 4)[:, 0], grid_n.detach())
+    assert torch.equal(model.bricks.isnan(), ops.grid_bricks(ops.grid_table(grid_n.detach(), ndim, nmin, nmax), ndim).isnan())
