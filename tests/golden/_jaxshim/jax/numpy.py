@@ -32,6 +32,11 @@ class _AtIdx:
         return out
 
 
+# jax.config.update("jax_enable_x64", True) stand-in: with X64 set, 64-bit types are kept (used only by the finite-difference
+# goldens of make_reference_goldens.py, where the reference's own scan is evaluated in float64)
+X64 = False
+
+
 class ndarray(_np.ndarray):
     @property
     def at(self):
@@ -44,7 +49,9 @@ class ndarray(_np.ndarray):
                         for a in arrs)
         conv = []
         for a in arrs:
-            if isinstance(a, _np.ndarray):
+            if X64:
+                pass
+            elif isinstance(a, _np.ndarray):
                 if a.dtype == _np.float64:
                     a = a.astype(_np.float32)
                 elif a.dtype == _np.int64:
@@ -58,7 +65,9 @@ class ndarray(_np.ndarray):
 
     def astype(self, dtype, *a, **k):
         dt = _np.dtype(dtype)
-        if dt == _np.int64:
+        if X64:
+            pass
+        elif dt == _np.int64:
             dt = _np.dtype(_np.int32)
         elif dt == _np.float64:
             dt = _np.dtype(_np.float32)
@@ -84,11 +93,15 @@ def _down(x):
     if isinstance(x, list):
         return [_down(v) for v in x]
     if isinstance(x, _np.ndarray):
+        if X64:
+            return x.view(ndarray)
         if x.dtype == _np.float64:
             x = x.astype(_np.float32)
         elif x.dtype == _np.int64:
             x = x.astype(_np.int32)
         return x.view(ndarray)
+    if X64:
+        return x
     if isinstance(x, _np.float64):
         return _np.float32(x)
     if isinstance(x, _np.int64):

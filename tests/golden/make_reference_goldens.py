@@ -182,6 +182,44 @@ def run_functions():
     out.update(all_grid=f32(grid), all_o=o, all_d=d, all_pos=f32(pos), all_dir=f32(dirs), all_dist=f32(dist), all_grad=f32(idg))
     for k, val in flatten(so3).items():
         out["all_so3:" + k] = f32(val)
+    # Directional derivatives of a linear functional of the coarse samples, L = sum(ray_pos[:, jit] * gp + ray_dir[:, jit] * gd),
+    # with respect to so3_mlp, by central differences THROUGH THE REFERENCE'S OWN SCAN (the shim has no autodiff): pins the
+    # gradients of the "all"-stage training path (oracle autograd, CUDA reverse sweep) to the reference's code.  The scan is
+    # piecewise smooth in the parameters (ReLU, trilinear cells), so the differences are taken in float64 (the shim's
+    # jax_enable_x64 stand-in) with a small step; inputs and weights are the float32 values above.
+    jit = np.array([0, 9, 17, 30, 41, 55, 70, 95])
+    gp, gd = f32(rs.normal(size=(12, 8, 3))), f32(rs.normal(size=(12, 8, 3)))
+    base = {k: {kk: np.asarray(f32(vv), np.float64) for kk, vv in lay.items()} for k, lay in so3.items()}
+    jnp.X64 = True
+    try:
+        ps64 = eikonal_utils.PathSampler(near=2.0, far=6.0, stage="all", num_samples=S, step_size=4.0 / (S - 1), ndim=ndim,
+                                         nmin=nmin, nmax=nmax, grid=jnp.array(np.asarray(f32(grid), np.float64)))
+        o64, d64 = jnp.array(np.asarray(o, np.float64)), jnp.array(np.asarray(d, np.float64))
+
+        def functional(params):
+            v64 = {"params": {"scan": {"idx_model": {"so3_mlp": {k: {kk: jnp.array(vv) for kk, vv in lay.items()}
+                                                                    for k, lay in params.items()}}}}}
+            p_, d_, _, _, _ = ps64.apply(v64, o64, d64, 0.7)
+            assert np.asarray(p_).dtype == np.float64
+            return float((np.asarray(p_)[:, jit] * gp).sum() + (np.asarray(d_)[:, jit] * gd).sum())
+
+        out.update(fd_jitter=jit, fd_gp=gp, fd_gd=gd)
+        for i in range(3):
+            delta = {k: {kk: np.asarray(f32(rs.normal(size=vv.shape) * max(float(np.sqrt((vv ** 2).mean())), 0.05)), np.float64)
+                         for kk, vv in lay.items()} for k, lay in base.items()}
+            vals = []
+            for eps in (2e-6, 1e-6):
+                plus = functional({k: {kk: base[k][kk] + eps * delta[k][kk] for kk in lay} for k, lay in base.items()})
+                minus = functional({k: {kk: base[k][kk] - eps * delta[k][kk] for kk in lay} for k, lay in base.items()})
+                vals.append((plus - minus) / (2 * eps))
+            print(f"  fd direction {i}: dL = {vals[0]:.8f} (eps 2e-6), {vals[1]:.8f} (eps 1e-6)")
+            assert abs(vals[0] - vals[1]) < 5e-3 * abs(vals[1]), "finite differences not converged"
+            out[f"fd_dL_{i}"] = np.float64(vals[1])
+            for k, lay in delta.items():
+                for kk, vv in lay.items():
+                    out[f"fd_delta_{i}:{k}/{kk}"] = f32(vv)
+    finally:
+        jnp.X64 = False
     # math helpers (rnerf/math_utils.py:6-20)
     z = f32(rs.normal(size=(20, 3))); z[0] = 0
     out["mh_x"] = z

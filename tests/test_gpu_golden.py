@@ -109,3 +109,32 @@ def test_all_stage_march_vs_reference_golden(cuda_lib):
     # the rotation really acted on these rays (the radiance-stage path differs)
     plain = ops.path_views(ops.march(table, ndim, nmin, nmax, C("all_o"), C("all_d"), 2.0, 6.0, 96))[0]
     assert (plain - pos).abs().max().item() > 1e-3
+
+
+def test_all_stage_gradient_vs_reference_finite_differences(cuda_lib):
+    """The CUDA reverse sweep of the scan against the reference itself: its so3_mlp gradient, projected on three random
+    parameter directions, vs central differences through the reference's own scan (float64, under the shim; committed as
+    fd_* in ref_functions.npz).  Tolerance 2 % (piecewise-smooth scan, see tests/test_oracle_vs_reference.py)."""
+    from samplenerfro_b200 import models, ops
+    fn = np.load(os.path.join(G, "ref_functions.npz"))
+    C = lambda k: torch.from_numpy(fn[k]).cuda().contiguous()
+    ndim, nmin, nmax = [16] * 3, [-1.5] * 3, [1.5] * 3
+    table = ops.grid_table(C("all_grid"), ndim, nmin, nmax)
+    so3 = {}
+    for k in fn.files:
+        if k.startswith("all_so3:"):
+            layer, leaf = k[len("all_so3:"):].split("/")
+            so3.setdefault(layer, {})[leaf] = C(k)
+    model = models.NerfModel(ndim=ndim, nmin=nmin, nmax=nmax, grid=fn["all_grid"], stage="all", num_path_samples=12)
+    w, window = ops.so3_pack(so3), model.so3_window(0.7)
+    path = ops.march(table, ndim, nmin, nmax, C("all_o"), C("all_d"), 2.0, 6.0, 96, compact=True, so3=(w, window))
+    jit = torch.from_numpy(fn["fd_jitter"].astype(np.int32)).cuda()
+    g, _, _ = ops.march_all_bwd(table, ndim, nmin, nmax, path, 2.0, 6.0, jit, C("fd_gp"), C("fd_gd"), (w, window))
+    views = ops.so3_unpack_views(g)
+    for i in range(3):
+        dL = 0.0
+        for li in range(5):
+            dL += float((views[2 * li].double().cpu() * torch.from_numpy(fn[f"fd_delta_{i}:Dense_{li}/kernel"]).double()).sum())
+            dL += float((views[2 * li + 1].double().cpu() * torch.from_numpy(fn[f"fd_delta_{i}:Dense_{li}/bias"]).double()).sum())
+        want = float(fn[f"fd_dL_{i}"])
+        assert abs(dL - want) < 0.02 * abs(want), (i, dL, want)

@@ -83,6 +83,29 @@ def test_all_stage_march(fn):
     assert np.abs(fn["all_dir"][:, -1] - fn["all_d"]).max() > 1e-2
 
 
+def test_all_stage_gradient_vs_reference_finite_differences(fn):
+    """Gradients of the "all"-stage scan wrt so3_mlp: the oracle's autograd, projected on three random parameter
+    directions, against central differences taken THROUGH THE REFERENCE'S OWN SCAN (float64 run of rnerf/eikonal_utils.py +
+    rnerf/ior_utils.py under the shim).  Pins the derivative the CUDA reverse sweep is tested against.  Tolerance 2 %: the
+    scan is only piecewise smooth in the parameters (ReLU, trilinear cells), which the differences feel at the 1e-3 level."""
+    ndim, nmin, nmax = [16] * 3, [-1.5] * 3, [1.5] * 3
+    table = O.build_table(T(fn["all_grid"]), ndim, nmin, nmax)
+    so3 = {}
+    for k in fn.files:
+        if k.startswith("all_so3:"):
+            layer, leaf = k[len("all_so3:"):].split("/")
+            so3.setdefault(layer, {})[leaf] = T(fn[k]).clone().requires_grad_(True)
+    pos, dirs, _, _, _ = O.march(table, ndim, nmin, nmax, T(fn["all_o"]), T(fn["all_d"]), 2.0, 6.0, 96, stage="all",
+                                 so3_params=so3, annealed_alpha=0.7)
+    jit = torch.as_tensor(fn["fd_jitter"]).long()
+    ((pos[:, jit] * T(fn["fd_gp"])).sum() + (dirs[:, jit] * T(fn["fd_gd"])).sum()).backward()
+    for i in range(3):
+        dL = sum(float((so3[layer][leaf].grad.double() * torch.as_tensor(fn[f"fd_delta_{i}:{layer}/{leaf}"]).double()).sum())
+                 for layer in so3 for leaf in so3[layer])
+        want = float(fn[f"fd_dL_{i}"])
+        assert abs(dL - want) < 0.02 * abs(want), (i, dL, want)
+
+
 def _load_model(name):
     d = np.load(os.path.join(G, f"ref_model_{name}.npz"))
     prm = np.load(os.path.join(G, "ref_params.npz"))
