@@ -11,7 +11,10 @@ numpy-backed jax/flax shim that reproduces JAX's 32-bit type semantics, Flax par
 (tests/golden/make_reference_goldens.py -> tests/golden/ref_*.npz).  tests/test_oracle_vs_reference.py checks the
 oracle against those fixtures (bent path bit-exact, full NerfModel.__call__ within fp32 summation-order
 tolerance, incl. the bd_cut_dist passes and the "all"-stage so3 rotation); tests/test_oracle_kat.py adds analytic
-known-answer tests.  What the shim cannot pin is XLA's own code generation (FMA contraction, reduction order).
+known-answer tests.  The DERIVATIVE of the "all"-stage scan (what torch autograd of this file is used for as the
+reference of the CUDA reverse sweep) is pinned too: central differences through the reference's own scan, run in
+float64 under the shim, are committed as fd_* goldens and reproduced by this oracle's autograd within 2 %.
+What the shim cannot pin is XLA's own code generation (FMA contraction, reduction order).
 
 Conventions
   * all arrays are torch CPU tensors; `dt` is torch.float32 (default) or torch.float64.
