@@ -542,43 +542,78 @@ __global__ void __launch_bounds__(BW_THREADS, 1) march_all_bwd_kernel(
   const int64_t rr = live ? ray : (n_rays - 1);
   const float4* rec = path + rr * (int64_t)n_steps * recf4;
   float lp[3] = {0.f, 0.f, 0.f}, lv[3] = {0.f, 0.f, 0.f};
-  const bool carrier = tid < rays_per_cta;       // warp-uniform: the other warps only take part in the MLP evaluations
+  // Rays of a CTA are NOT kept in lockstep: a ray sweeps its own steps until one needs so3_mlp, then waits; the CTA
+  // evaluates the MLP for all waiting rays together -- whatever their step, the MLP does not care -- so the number of
+  // evaluations a CTA runs in series tends to the largest active-step count of one of its rays instead of the size of the
+  // union of their active steps (353 vs 165 on a sorted batch of 4096 random pixels, scripts/all_stage_batch_probe.py).
+  // A ray that needs nothing runs at most SWEEP_QUANTUM steps ahead per round, so waiting rays are served promptly.
+  constexpr int SWEEP_QUANTUM = 16;
+  int k = k_last;
+  bool done = !live;
+  // loss gradients of coarse sample jc = record k (v = direction state of that record)
+  auto inject = [&](int kk, const float (&v)[3]) {
+    const int jc = kmap[kk];
+    if (jc < 0) return;
+    const float* gp = d_pos_c + (ray * n_coarse + jc) * 3;
+    const float* gd = d_dir_c + (ray * n_coarse + jc) * 3;
+    const float s = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const float im = 1.f / sqrtf(fmaxf(s, 1e-6f));
+    const float d0 = v[0] * im, d1 = v[1] * im, d2 = v[2] * im;           // safe_l2_normalize (rnerf/math_utils.py:6-12)
+    const float g0 = __ldg(gd), g1 = __ldg(gd + 1), g2 = __ldg(gd + 2);
+    const float proj = s > 1e-6f ? (d0 * g0 + d1 * g1 + d2 * g2) : 0.f;
+    lv[0] += (g0 - d0 * proj) * im; lv[1] += (g1 - d1 * proj) * im; lv[2] += (g2 - d2 * proj) * im;
+    lp[0] += __ldg(gp); lp[1] += __ldg(gp + 1); lp[2] += __ldg(gp + 2);
+  };
+  // second half of the transition k -> k+1, reverse, once dg (adjoint of grad n) and dpm (through the encoding) are known
+  auto finish = [&](const float (&p)[3], float hn, float dn, const float (&dg)[3], const float (&dpm)[3], const float4& jx,
+                    const float4& jy, const float4& jz) {
+    if (d_table != nullptr) scatter_table_grad<FAST>(d_table, mg, p[0], p[1], p[2], dn, dg);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) lv[i] = fmaf(hn, lp[i], lv[i]);
+    lp[0] += jx.x * dn + jx.y * dg[0] + jx.z * dg[1] + jx.w * dg[2] + dpm[0];
+    lp[1] += jy.x * dn + jy.y * dg[0] + jy.z * dg[1] + jy.w * dg[2] + dpm[1];
+    lp[2] += jz.x * dn + jz.y * dg[0] + jz.z * dg[1] + jz.w * dg[2] + dpm[2];
+  };
 #pragma unroll 1
-  for (int k = k_last; k >= 0; --k) {
-    float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
-    if (carrier) {
+  while (true) {
+    // state of a ray waiting for the MLP (valid when `need`)
+    float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f}, g[3] = {0.f, 0.f, 0.f}, dG[3] = {0.f, 0.f, 0.f};
+    float4 jx = make_float4(0.f, 0.f, 0.f, 0.f), jy = jx, jz = jx;
+    float hn = 0.f, dn = 0.f;
+    bool need = false;
+#pragma unroll 1
+    for (int it = 0; it < SWEEP_QUANTUM && !done && !need; ++it) {
       const float4 r0 = __ldg(rec + k * recf4), r1 = __ldg(rec + k * recf4 + 1);
       p[0] = r0.x; p[1] = r0.y; p[2] = r0.z; v[0] = r1.x; v[1] = r1.y; v[2] = r1.z;
+      if (k < k_last) {                          // transition k -> k+1, reverse
+        float4 c;
+        lookup_with_jacobian<FAST>(table, mg, bricks, p[0], p[1], p[2], c, jx, jy, jz);
+        g[0] = c.y; g[1] = c.z; g[2] = c.w;
+        hn = step / c.x;
+        dn = -(hn / c.x) * (v[0] * lp[0] + v[1] * lp[1] + v[2] * lp[2]);
+        dG[0] = step * lv[0]; dG[1] = step * lv[1]; dG[2] = step * lv[2];
+        // the forward's test, on the same bits (so3.w == NULL: radiance stage, the sweep only yields ray / table gradients)
+        need = so3.w != nullptr && sqrtf(sumsq3(g[0], g[1], g[2])) > 1e-3f;
+        if (!need) {
+          const float zero[3] = {0.f, 0.f, 0.f};
+          finish(p, hn, dn, dG, zero, jx, jy, jz);
+        }
+      }
+      if (!need) {
+        inject(k, v);
+        done = --k < 0;
+      }
     }
-    if (k < k_last) {                            // transition k -> k+1, reverse
-      float4 c = make_float4(1.f, 0.f, 0.f, 0.f), jx = make_float4(0.f, 0.f, 0.f, 0.f), jy = jx, jz = jx;
-      if (carrier) lookup_with_jacobian<FAST>(table, mg, bricks, p[0], p[1], p[2], c, jx, jy, jz);
-      const float g[3] = {c.y, c.z, c.w};
-      const float hn = step / c.x;
-      const float dn = -(hn / c.x) * (v[0] * lp[0] + v[1] * lp[1] + v[2] * lp[2]);
-      const float dG[3] = {step * lv[0], step * lv[1], step * lv[2]};
-      float dg[3] = {dG[0], dG[1], dG[2]}, dpm[3] = {0.f, 0.f, 0.f};
-      // the forward's test, on the same bits (so3.w == NULL: radiance stage, the sweep only yields ray / table gradients)
-      const bool act = so3.w != nullptr && live && sqrtf(sumsq3(g[0], g[1], g[2])) > 1e-3f;
-      if (__syncthreads_or(act)) so3_fwd_bwd(so3, sm, cnt, ring, warp, lane, act, p, g, dG, dg, dpm);
-      if (d_table != nullptr && live) scatter_table_grad<FAST>(d_table, mg, p[0], p[1], p[2], dn, dg);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) lv[i] = fmaf(hn, lp[i], lv[i]);
-      lp[0] += jx.x * dn + jx.y * dg[0] + jx.z * dg[1] + jx.w * dg[2] + dpm[0];
-      lp[1] += jy.x * dn + jy.y * dg[0] + jy.z * dg[1] + jy.w * dg[2] + dpm[1];
-      lp[2] += jz.x * dn + jz.y * dg[0] + jz.z * dg[1] + jz.w * dg[2] + dpm[2];
-    }
-    const int jc = kmap[k];
-    if (jc >= 0 && live) {                       // loss gradients of coarse sample jc = record k
-      const float* gp = d_pos_c + (ray * n_coarse + jc) * 3;
-      const float* gd = d_dir_c + (ray * n_coarse + jc) * 3;
-      const float s = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-      const float im = 1.f / sqrtf(fmaxf(s, 1e-6f));
-      const float d0 = v[0] * im, d1 = v[1] * im, d2 = v[2] * im;           // safe_l2_normalize (rnerf/math_utils.py:6-12)
-      const float g0 = __ldg(gd), g1 = __ldg(gd + 1), g2 = __ldg(gd + 2);
-      const float proj = s > 1e-6f ? (d0 * g0 + d1 * g1 + d2 * g2) : 0.f;
-      lv[0] += (g0 - d0 * proj) * im; lv[1] += (g1 - d1 * proj) * im; lv[2] += (g2 - d2 * proj) * im;
-      lp[0] += __ldg(gp); lp[1] += __ldg(gp + 1); lp[2] += __ldg(gp + 2);
+    if (__syncthreads_or(need)) {
+      float dg[3] = {0.f, 0.f, 0.f}, dpm[3] = {0.f, 0.f, 0.f};
+      so3_fwd_bwd(so3, sm, cnt, ring, warp, lane, need, p, g, dG, dg, dpm);
+      if (need) {
+        finish(p, hn, dn, dg, dpm, jx, jy, jz);
+        inject(k, v);
+        done = --k < 0;
+      }
+    } else if (!__syncthreads_or(!done)) {
+      break;
     }
   }
   ring_drain(ring);                              // weight chunks fetched ahead for an evaluation that never came
