@@ -437,6 +437,76 @@ __global__ void __launch_bounds__(SO3 ? SO3_THREADS : MARCH_THREADS, SO3 ? 2 : 8
   if (SO3) ring_drain(ring);                     // weight chunks fetched ahead for an evaluation that never came
 }
 
+// "all"-stage march for SMALL launches (a training batch): the rays of a CTA are not kept in lockstep.  A ray marches on
+// its own until a step needs so3_mlp, then waits; the CTA evaluates the MLP for all waiting rays together, whatever their
+// step, so the number of evaluations a CTA runs in series tends to the largest active-step count of one of its rays
+// instead of the union of their active steps (random pixels have little in common even after sorting,
+// scripts/all_stage_batch_probe.py).  Records are stored straight to global memory (32 or 48 B per ray and step, sector
+// complete); the coalesced staging of march_kernel needs lockstep and pays off only for full frames.  Per ray the
+// arithmetic is that of march_kernel, so the records are bit-identical.
+template <int RECF4, bool FAST>
+__global__ void __launch_bounds__(SO3_THREADS, 2) march_all_ragged_kernel(const float4* __restrict__ table, const MarchGeom mg,
+                                                                          const float* __restrict__ origins,
+                                                                          const float* __restrict__ viewdirs, int64_t n_rays,
+                                                                          float near, float step, int n_steps,
+                                                                          float4* __restrict__ path, float* __restrict__ t_col,
+                                                                          const float* __restrict__ bricks, const So3Args so3,
+                                                                          int so3_slots, int rays_per_cta) {
+  extern __shared__ __align__(16) float so3_scratch[];
+  constexpr int QUANTUM = 16;                    // steps a ray that needs nothing may run ahead per round
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  So3Ring ring;
+  char* base = reinterpret_cast<char*>(so3_scratch);
+  ring_init(ring, reinterpret_cast<float*>(base + SO3_OFF_RING), base + SO3_OFF_BARS, so3_slots, threadIdx.x);
+  __syncthreads();
+  const int64_t ray = blockIdx.x * (int64_t)rays_per_cta + threadIdx.x;
+  const bool live = (int)threadIdx.x < rays_per_cta && ray < n_rays;
+  const int64_t rr = live ? ray : (n_rays - 1);
+  float vx = viewdirs[3 * rr], vy = viewdirs[3 * rr + 1], vz = viewdirs[3 * rr + 2];
+  float px = add(origins[3 * rr], mul(near, vx)), py = add(origins[3 * rr + 1], mul(near, vy)), pz = add(origins[3 * rr + 2], mul(near, vz));
+  float t = near;
+  float4* rec = path + rr * (int64_t)n_steps * RECF4;
+  float* tc = t_col != nullptr ? t_col + rr * (int64_t)n_steps : nullptr;
+  int k = 0;
+  bool done = !live;
+  float n_here = 1.f;
+  auto advance = [&](float gx, float gy, float gz) {
+    const float s = divf(step, n_here);
+    const float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
+    vx = add(vx, mul(step, gx)); vy = add(vy, mul(step, gy)); vz = add(vz, mul(step, gz));
+    t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
+    px = nx; py = ny; pz = nz;
+    done = ++k >= n_steps;
+  };
+#pragma unroll 1
+  while (true) {
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    bool need = false;
+#pragma unroll 1
+    for (int it = 0; it < QUANTUM && !done && !need; ++it) {
+      const float4 c = march_lookup<FAST>(table, mg, bricks, px, py, pz);
+      __stcs(rec + k * RECF4, make_float4(px, py, pz, t));
+      __stcs(rec + k * RECF4 + 1, make_float4(vx, vy, vz, c.x));
+      if (RECF4 == 3) __stcs(rec + k * RECF4 + 2, make_float4(c.y, c.z, c.w, 0.f));
+      if (tc != nullptr) tc[k] = t;
+      n_here = c.x; gx = c.y; gy = c.z; gz = c.w;
+      need = sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;          // jnp.linalg.norm(idx_grad) > 1e-3
+      if (!need) advance(gx, gy, gz);
+    }
+    if (__syncthreads_or(need)) {
+      float r0, r1, r2;
+      so3_eval(so3, so3_scratch, ring, warp, lane, need, px, py, pz, r0, r1, r2);
+      if (need) {
+        so3_rotate(r0, r1, r2, gx, gy, gz);
+        advance(gx, gy, gz);
+      }
+    } else if (!__syncthreads_or(!done)) {
+      break;
+    }
+  }
+  ring_drain(ring);
+}
+
 // VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267) on free-standing points: pred = rodrigues(so3_mlp(annealed_pos_enc(x)),
 // condition), no |grad n| threshold.  What PathSampler.compute_normal_loss_and_smooth (rnerf/eikonal_utils.py:84-98) evaluates.
 __global__ void __launch_bounds__(SO3_THREADS, 2) so3_predict_kernel(const float* __restrict__ pts, const float* __restrict__ cond,
@@ -576,7 +646,19 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
 #define RNERF_MARCH_LAUNCH(R, F, A)                                                                                       \
   march_kernel<R, F, A><<<blocks, (A) ? SO3_THREADS : MARCH_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
                                                             step, n_steps, (float4*)path, t_col, bricks, dbg, so3, slots, rpc)
-  if (so3_w == nullptr) {
+  if (so3_w != nullptr && rpc < MARCH_THREADS) {          // a small launch: rays not in lockstep (see march_all_ragged_kernel)
+    cudaError_t e = cudaSuccess;
+#define RNERF_RAGGED_LAUNCH(R, F)                                                                                           \
+    e = cudaFuncSetAttribute(march_all_ragged_kernel<R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);             \
+    if (e == cudaSuccess)                                                                                                      \
+      march_all_ragged_kernel<R, F><<<blocks, SO3_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays,       \
+                                                                      (float)near, step, n_steps, (float4*)path, t_col, bricks, \
+                                                                      so3, slots, rpc)
+    if (rec_floats == 8) { if (fast) { RNERF_RAGGED_LAUNCH(2, true); } else { RNERF_RAGGED_LAUNCH(2, false); } }
+    else                 { if (fast) { RNERF_RAGGED_LAUNCH(3, true); } else { RNERF_RAGGED_LAUNCH(3, false); } }
+#undef RNERF_RAGGED_LAUNCH
+    if (e != cudaSuccess) { set_error("rnerf_march_all_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  } else if (so3_w == nullptr) {
     if (rec_floats == 8) { if (fast) RNERF_MARCH_LAUNCH(2, true, false); else RNERF_MARCH_LAUNCH(2, false, false); }
     else                 { if (fast) RNERF_MARCH_LAUNCH(3, true, false); else RNERF_MARCH_LAUNCH(3, false, false); }
   } else {

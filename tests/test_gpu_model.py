@@ -184,3 +184,26 @@ def test_all_stage_march_many_active_rays_per_cta(cuda_lib):
     assert (pos.cpu() - opos).abs().max().item() < 1e-4 * scale, (pos.cpu() - opos).abs().max().item()
     assert (dirs.cpu() - odir).abs().max().item() < 1e-4
     assert (dist.cpu() - odist).abs().max().item() < 1e-4 * odist.abs().max().item()
+
+
+def test_all_stage_ragged_march_is_bit_identical_to_lockstep(cuda_lib, monkeypatch):
+    """Small launches of the "all"-stage march let every ray run at its own step and batch the so3 evaluations of rays at
+    different steps (march_all_ragged_kernel); per ray the arithmetic is unchanged, so records and the t column equal the
+    lockstep kernel's bit for bit (compact and full records, ragged ray count)."""
+    from samplenerfro_b200 import models, ops
+    n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
+    gen = torch.Generator().manual_seed(8)
+    model, variables = models.construct_nerf(5, None, _flags(stage="all"), ndim, nmin, nmax, n)
+    so3 = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+    so3["Dense_4"]["kernel"].copy_((torch.randn(128, 3, generator=gen) * 0.05).cuda())
+    so3["Dense_4"]["bias"].copy_((torch.randn(3, generator=gen) * 0.2).cuda())
+    o, d = H.random_rays(333, seed=4, target_extent=0.8)
+    w = (ops.so3_pack(so3), model.so3_window(0.8))
+    for compact in (True, False):
+        monkeypatch.setenv("RNERF_SO3_RPC", "128")                       # lockstep kernel
+        a = ops.march(model.table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768, bricks=model.bricks, compact=compact, so3=w)
+        monkeypatch.delenv("RNERF_SO3_RPC")                               # 333 rays -> 32 rays per CTA, ragged kernel
+        b = ops.march(model.table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768, bricks=model.bricks, compact=compact, so3=w)
+        assert torch.equal(a.rec, b.rec) and torch.equal(a.t, b.t)
+    act = (ops.path_views(b)[4].norm(dim=-1) > 1e-3)
+    assert act.any(dim=1).sum().item() > 50                               # the MLP was needed on many rays
