@@ -39,6 +39,26 @@ def test_abi_argument_validation_without_gpu():
                             C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), None, None)
     assert rc == -2
     assert lib.rnerf_encmlp_fwd(None, None, None, 0, None, None) == 0      # empty input is a no-op
+    # entries of the "all"-stage training path
+    P = C.c_void_p(16)
+    win = (C.c_double * 10)(*([1.0] * 10))
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 1, P, 2, P, P, P, P, win, P, None, None, None, None)
+    assert rc == -2 and b"n_steps" in lib.rnerf_last_error()
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 10, 4, 2.0, 6.0, 96, P, 8, P, P, P, P, win, P, None, None, None, None)
+    assert rc == -2 and b"rec_floats" in lib.rnerf_last_error()
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, P, None, win, P, None, None, None, None)
+    assert rc == -1 and b"so3_wt" in lib.rnerf_last_error()            # so3_w given without its transposed image
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, C.c_void_p(20), P, win, P, None, None, None, None)
+    assert rc == -3                                                       # misaligned weight image
+    assert lib.rnerf_march_all_bwd(P, None, nd, lo, hi, None, 8, 0, 2.0, 6.0, 96, None, 8, None, None, None, None, None, None,
+                                   None, None, None, None) == 0           # no rays: a no-op
+    assert lib.rnerf_mlp_input_grad(None, 0, None, None, None, None, None, None) == 0
+    assert lib.rnerf_mlp_input_grad(None, 5, None, None, None, None, None, None) == -1
+    assert lib.rnerf_so3_predict(None, win, P, P, 3, P, None) == -1
+    assert lib.rnerf_grid_table_bwd(P, _lib.Int3(1, 4, 4), lo, hi, P, None) == -2
+    assert lib.rnerf_bkgd_mlp_bwd_dirs(P, P, 4, 3, P, P, None, None) == -1
+    assert lib.rnerf_so3_transposed_floats() == 2 * 128 * 60 + 3 * 128 * 128
+    assert lib.rnerf_mlp_input_grad_packed_floats() == 640 * 64
     assert lib.rnerf_march_fwd(C.c_void_p(16), None, nd, lo, hi, None, None, 0, 2.0, 6.0, 768, 12, None, None, None) == 0
 
 
