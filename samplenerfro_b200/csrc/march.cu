@@ -205,12 +205,58 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
       const float xb = mul(P[c * SO3_RP + cc], (float)(1 << k));
       X[f * SO3_RP + cc] = mul(sinf(q >= 3 ? add(xb, 1.57079632679489661923f) : xb), a.window[k]);
     }
+    int layer = 0;
+    if (n_act <= 8) {
+      // Few columns (the usual case once rays are out of lockstep, and at the rim of an object): splitting the 128 / 188
+      // input rows of a layer over the four thread groups instead of the columns makes the dependent FMA chain of a layer
+      // four times shorter.  Thread (j, h) sums rows r = h (mod 4) for neurons 2j, 2j+1 and all 8 columns; the four
+      // partial sums meet in columns 8 + 8h .. of the output rows of Hs (free in an 8-column pass), then thread t adds
+      // them for neuron t / 2, columns 4 (t mod 2) .. +3.
+      f32x2 pa[2][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { pa[0][q] = 0ull; pa[1][q] = 0ull; }
+#pragma unroll 1
+      for (int c = 0; c < SO3_NCHUNK; ++c) {
+        const float* wbuf = ring_acquire(ring, tid, stream) + 2 * j;
+        const So3Chunk k = so3_chunk(c);
+        const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_RP;
+#pragma unroll 4
+        for (int r = h; r < k.rows; r += SO3_THREADS / 64) {
+          const float2 w = *reinterpret_cast<const float2*>(wbuf + r * SO3_W);
+          const f32x2 w0 = pack2(w.x, w.x), w1 = pack2(w.y, w.y);
+          const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(in + r * SO3_RP);
+          const ulonglong2 x0 = xr[0], x1 = xr[1];
+          pa[0][0] = fma2(w0, x0.x, pa[0][0]); pa[0][1] = fma2(w0, x0.y, pa[0][1]); pa[0][2] = fma2(w0, x1.x, pa[0][2]); pa[0][3] = fma2(w0, x1.y, pa[0][3]);
+          pa[1][0] = fma2(w1, x0.x, pa[1][0]); pa[1][1] = fma2(w1, x0.y, pa[1][1]); pa[1][2] = fma2(w1, x1.x, pa[1][2]); pa[1][3] = fma2(w1, x1.y, pa[1][3]);
+        }
+        ++ring.pos;
+        if (k.last_of_layer) {
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            ulonglong2* o = reinterpret_cast<ulonglong2*>(Hs + (2 * j + n) * SO3_RP + 8 + 8 * h);
+            o[0] = make_ulonglong2(pa[n][0], pa[n][1]); o[1] = make_ulonglong2(pa[n][2], pa[n][3]);
+          }
+          __syncthreads();                     // all partial sums are there, nobody reads the layer input any more
+          const int nrn = tid >> 1, c4 = 4 * (tid & 1);
+          const float b = __ldg(bias + layer * SO3_W + nrn);
+          float4 sum = make_float4(b, b, b, b);
+#pragma unroll
+          for (int hh = 0; hh < SO3_THREADS / 64; ++hh) {
+            const float4 v = *reinterpret_cast<const float4*>(Hs + nrn * SO3_RP + 8 + 8 * hh + c4);
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+          }
+          *reinterpret_cast<float4*>(Hs + nrn * SO3_RP + c4) = make_float4(fmaxf(sum.x, 0.f), fmaxf(sum.y, 0.f), fmaxf(sum.z, 0.f), fmaxf(sum.w, 0.f));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { pa[0][q] = 0ull; pa[1][q] = 0ull; }
+          ++layer;
+        }
+      }
+    } else {
     f32x2 acc[2][2][4];                        // [group][neuron][column pair]
 #pragma unroll
     for (int g = 0; g < 2; ++g)
 #pragma unroll
       for (int r = 0; r < 4; ++r) { acc[g][0][r] = 0ull; acc[g][1][r] = 0ull; }
-    int layer = 0;
 #pragma unroll 1
     for (int c = 0; c < SO3_NCHUNK; ++c) {
       // chunk c has landed; the barrier inside also makes the activations written before this point (X, or Hs of the
@@ -258,6 +304,7 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
         }
         ++layer;
       }
+    }
     }
     __syncthreads();                           // Dense_3 output visible
     {                                          // Dense_4: raw[m][column], one thread per output

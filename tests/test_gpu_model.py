@@ -186,10 +186,11 @@ def test_all_stage_march_many_active_rays_per_cta(cuda_lib):
     assert (dist.cpu() - odist).abs().max().item() < 1e-4 * odist.abs().max().item()
 
 
-def test_all_stage_ragged_march_is_bit_identical_to_lockstep(cuda_lib, monkeypatch):
+def test_all_stage_ragged_march_matches_lockstep(cuda_lib, monkeypatch):
     """Small launches of the "all"-stage march let every ray run at its own step and batch the so3 evaluations of rays at
-    different steps (march_all_ragged_kernel); per ray the arithmetic is unchanged, so records and the t column equal the
-    lockstep kernel's bit for bit (compact and full records, ragged ray count)."""
+    different steps (march_all_ragged_kernel).  Per ray the march arithmetic is unchanged; only the fp32 summation order
+    inside so3_mlp depends on how many rays share an evaluation (row-split path for <= 8 columns), so records and the t
+    column agree with the lockstep kernel to rounding (compact and full records, ragged ray count)."""
     from samplenerfro_b200 import models, ops
     n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
     gen = torch.Generator().manual_seed(8)
@@ -204,6 +205,11 @@ def test_all_stage_ragged_march_is_bit_identical_to_lockstep(cuda_lib, monkeypat
         a = ops.march(model.table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768, bricks=model.bricks, compact=compact, so3=w)
         monkeypatch.delenv("RNERF_SO3_RPC")                               # 333 rays -> 32 rays per CTA, ragged kernel
         b = ops.march(model.table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, 768, bricks=model.bricks, compact=compact, so3=w)
-        assert torch.equal(a.rec, b.rec) and torch.equal(a.t, b.t)
+        assert (a.rec - b.rec).abs().max().item() < 1e-5 * a.rec.abs().max().item() and (a.t - b.t).abs().max().item() < 1e-4
+        homog = ops.path_views(a)[3][..., 0] == ops.path_views(a)[3][:, :1, 0]        # n still the ambient value
+        first_bent = (~homog).float().argmax(dim=1)                                   # before the boundary: bit-identical
+        k = torch.arange(768, device="cuda")[None]
+        before = (k < first_bent[:, None]) | homog.all(dim=1, keepdim=True)
+        assert torch.equal(a.rec[before], b.rec[before])
     act = (ops.path_views(b)[4].norm(dim=-1) > 1e-3)
     assert act.any(dim=1).sum().item() > 50                               # the MLP was needed on many rays
