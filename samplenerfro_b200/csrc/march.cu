@@ -130,33 +130,42 @@ constexpr int SO3_ACT_FLOATS = SO3_OFF_RAW + 3 * SO3_RP;
 // S2 = Dense_2 x H, S3a = Dense_3[:128] x H, S3b = Dense_3[128:] x X (the skip concat [h, inputs]).  The weights cross
 // L2 -> SM once per CTA evaluation, n_slots - 1 chunks ahead of the FMA loop (also across evaluations: the stream is
 // periodic), and are read with conflict-free LDS.
-constexpr int SO3_NCHUNK = 4 + 8 + 8 + 8 + 4;                // 32
+// Rows per chunk CH: 16 (8 KB slots; full frames: two CTAs per SM share the shared memory) or 64 (32 KB slots; small
+// launches own the SM, and every chunk costs a block barrier, so fewer and larger chunks are faster).
+template <int CH> struct So3Chunking {
+  static constexpr int C_X = (SO3_IN + CH - 1) / CH, C_H = (SO3_W + CH - 1) / CH;     // chunks of a 60-row / 128-row segment
+  static constexpr int NCHUNK = 2 * C_X + 3 * C_H;                                      // 32 (CH = 16) or 8 (CH = 64)
+  static constexpr int SLOT_FLOATS = CH * SO3_W;
+};
 // dynamic shared memory: activations | per-warp active-ray counts (32 B) | mbarriers (128 B) | ring slots
 constexpr int SO3_OFF_CNT = SO3_ACT_FLOATS * 4, SO3_OFF_BARS = SO3_OFF_CNT + 4 * (SO3_THREADS / 32), SO3_OFF_RING = SO3_OFF_BARS + 8 * SO3_MAX_SLOTS;
 static_assert(SO3_OFF_RING % 16 == 0, "ring slots must be 16-byte aligned");
-static size_t so3_smem_bytes(int n_slots) { return (size_t)SO3_OFF_RING + (size_t)n_slots * SO3_SLOT_FLOATS * 4; }
+static size_t so3_smem_bytes(int n_slots, int ch = SO3_CH) { return (size_t)SO3_OFF_RING + (size_t)n_slots * ch * SO3_W * 4; }
 
 struct So3Chunk { int row0, rows, in_k0, in_is_x, last_of_layer; };
+template <int CH>
 __device__ __forceinline__ So3Chunk so3_chunk(int c) {
-  // segment starts (chunks): S0 0..3, S1 4..11, S2 12..19, S3a 20..27, S3b 28..31; weight-row starts 0, 60, 188, 316, 444
+  // segments S0 (60 rows), S1, S2, S3a (128 rows each), S3b (60 rows); weight-row starts 0, 60, 188, 316, 444
+  constexpr int CX = So3Chunking<CH>::C_X, CHH = So3Chunking<CH>::C_H;
   So3Chunk k;
   int seg, j;
-  if (c < 4) { seg = 0; j = c; } else if (c < 12) { seg = 1; j = c - 4; } else if (c < 20) { seg = 2; j = c - 12; }
-  else if (c < 28) { seg = 3; j = c - 20; } else { seg = 4; j = c - 28; }
+  if (c < CX) { seg = 0; j = c; } else if (c < CX + CHH) { seg = 1; j = c - CX; } else if (c < CX + 2 * CHH) { seg = 2; j = c - CX - CHH; }
+  else if (c < CX + 3 * CHH) { seg = 3; j = c - CX - 2 * CHH; } else { seg = 4; j = c - CX - 3 * CHH; }
   const int seg_row0 = seg == 0 ? 0 : (seg == 1 ? 60 : (seg == 2 ? 188 : (seg == 3 ? 316 : 444)));
   const int seg_rows = (seg == 0 || seg == 4) ? 60 : 128;
-  k.in_k0 = j * SO3_CH;
+  k.in_k0 = j * CH;
   k.row0 = seg_row0 + k.in_k0;
-  k.rows = min(SO3_CH, seg_rows - k.in_k0);
+  k.rows = min(CH, seg_rows - k.in_k0);
   k.in_is_x = (seg == 0 || seg == 4);
   k.last_of_layer = (seg != 3) && (k.in_k0 + k.rows == seg_rows);     // S3a continues into S3b
   return k;
 }
 
+template <int CH>
 struct So3FwdStream {
   const float* w;
   __device__ __forceinline__ void operator()(uint32_t g, const float*& src, uint32_t& bytes) const {
-    const So3Chunk k = so3_chunk((int)(g % (uint32_t)SO3_NCHUNK));
+    const So3Chunk k = so3_chunk<CH>((int)(g % (uint32_t)So3Chunking<CH>::NCHUNK));
     src = w + (size_t)k.row0 * SO3_W;
     bytes = (uint32_t)k.rows * SO3_W * 4;
   }
@@ -164,13 +173,15 @@ struct So3FwdStream {
 
 // raw = so3_mlp(annealed_pos_enc(p)) for the CTA's active rays.  EVERY thread of the CTA must call this (block barriers
 // inside); only threads with `act` get a result.
+template <int CH = SO3_CH>
 __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3Ring& ring, int warp, int lane, bool act, float px,
                                          float py, float pz, float& r0, float& r1, float& r2) {
   float* X = dyn_smem;                         // [60][68]
   float* Hs = dyn_smem + SO3_IN * SO3_RP;      // [128][68]
   int* cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(dyn_smem) + SO3_OFF_CNT);
   const int tid = warp * 32 + lane;
-  const So3FwdStream stream{a.w};
+  const So3FwdStream<CH> stream{a.w};
+  constexpr int SO3_NCHUNK = So3Chunking<CH>::NCHUNK;
   ring_prime(ring, tid, stream);
   // ---- compaction: active ray -> column idx of the activation buffers (only the first MARCH_THREADS threads carry rays)
   const unsigned bal = __ballot_sync(0xffffffffu, act);
@@ -218,7 +229,7 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
 #pragma unroll 1
       for (int c = 0; c < SO3_NCHUNK; ++c) {
         const float* wbuf = ring_acquire(ring, tid, stream) + 2 * j;
-        const So3Chunk k = so3_chunk(c);
+        const So3Chunk k = so3_chunk<CH>(c);
         const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_RP;
 #pragma unroll 4
         for (int r = h; r < k.rows; r += SO3_THREADS / 64) {
@@ -262,7 +273,7 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
       // chunk c has landed; the barrier inside also makes the activations written before this point (X, or Hs of the
       // last layer) visible
       const float* wbuf = ring_acquire(ring, tid, stream) + 2 * j;
-      const So3Chunk k = so3_chunk(c);
+      const So3Chunk k = so3_chunk<CH>(c);
       const float* in = (k.in_is_x ? X : Hs) + k.in_k0 * SO3_RP + 8 * h;
 #pragma unroll 4
       for (int r = 0; r < k.rows; ++r) {
@@ -491,8 +502,9 @@ __global__ void __launch_bounds__(SO3 ? SO3_THREADS : MARCH_THREADS, SO3 ? 2 : 8
 // scripts/all_stage_batch_probe.py).  Records are stored straight to global memory (32 or 48 B per ray and step, sector
 // complete); the coalesced staging of march_kernel needs lockstep and pays off only for full frames.  Per ray the
 // arithmetic is that of march_kernel, so the records are bit-identical.
+constexpr int RAGGED_CH = 64, RAGGED_SLOTS = 3;         // 8 chunks per evaluation through three 32 KB slots
 template <int RECF4, bool FAST>
-__global__ void __launch_bounds__(SO3_THREADS, 2) march_all_ragged_kernel(const float4* __restrict__ table, const MarchGeom mg,
+__global__ void __launch_bounds__(SO3_THREADS, 1) march_all_ragged_kernel(const float4* __restrict__ table, const MarchGeom mg,
                                                                           const float* __restrict__ origins,
                                                                           const float* __restrict__ viewdirs, int64_t n_rays,
                                                                           float near, float step, int n_steps,
@@ -504,7 +516,8 @@ __global__ void __launch_bounds__(SO3_THREADS, 2) march_all_ragged_kernel(const 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   So3Ring ring;
   char* base = reinterpret_cast<char*>(so3_scratch);
-  ring_init(ring, reinterpret_cast<float*>(base + SO3_OFF_RING), base + SO3_OFF_BARS, so3_slots, threadIdx.x);
+  ring_init(ring, reinterpret_cast<float*>(base + SO3_OFF_RING), base + SO3_OFF_BARS, so3_slots, threadIdx.x,
+            So3Chunking<RAGGED_CH>::SLOT_FLOATS);
   __syncthreads();
   const int64_t ray = blockIdx.x * (int64_t)rays_per_cta + threadIdx.x;
   const bool live = (int)threadIdx.x < rays_per_cta && ray < n_rays;
@@ -542,7 +555,7 @@ __global__ void __launch_bounds__(SO3_THREADS, 2) march_all_ragged_kernel(const 
     }
     if (__syncthreads_or(need)) {
       float r0, r1, r2;
-      so3_eval(so3, so3_scratch, ring, warp, lane, need, px, py, pz, r0, r1, r2);
+      so3_eval<RAGGED_CH>(so3, so3_scratch, ring, warp, lane, need, px, py, pz, r0, r1, r2);
       if (need) {
         so3_rotate(r0, r1, r2, gx, gy, gz);
         advance(gx, gy, gz);
@@ -695,6 +708,8 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
                                                             step, n_steps, (float4*)path, t_col, bricks, dbg, so3, slots, rpc)
   if (so3_w != nullptr && rpc < MARCH_THREADS) {          // a small launch: rays not in lockstep (see march_all_ragged_kernel)
     cudaError_t e = cudaSuccess;
+    slots = RAGGED_SLOTS;
+    dyn = so3_smem_bytes(slots, RAGGED_CH);
 #define RNERF_RAGGED_LAUNCH(R, F)                                                                                           \
     e = cudaFuncSetAttribute(march_all_ragged_kernel<R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);             \
     if (e == cudaSuccess)                                                                                                      \
