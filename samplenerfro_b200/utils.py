@@ -281,6 +281,37 @@ def render_view_sharded(render_fn: Callable, camtoworld, height: int, width: int
     return rgb.reshape(height, width, 3), distance.reshape(height, width, 1), acc.reshape(height, width, 1)
 
 
+class GridPoints:
+    """datasets.Grid (rnerf/datasets.py:245-328), the producer of batch["pts"] / batch["grads"] for
+    compute_normal_loss_and_smooth, on the device: candidate voxels are those with |grad n| > 1e-3 (:264); a batch picks
+    `extra_batch_size` of them at random, places the point at idx / ndim * (nmax - nmin) + nmin (the reference divides by
+    ndim, not ndim - 1, :272-273) plus uniform(-1, 1) * ndelta (:274) and interpolates grad n there (:275; the same
+    central-difference gradient and trilinear interpolation as the model's table, so the table's lookup kernel is used)."""
+
+    def __init__(self, model, extra_batch_size: int = 1024):
+        self.model, self.batch_size = model, int(extra_batch_size)
+        g = model.table.view(model.ndim[0], model.ndim[1], model.ndim[2], 4)[..., 1:4]
+        self.candidate_indices = torch.nonzero(g.norm(dim=-1) > 1e-3)          # [K, 3] (x, y, z) voxel indices
+        if self.candidate_indices.shape[0] == 0:
+            raise ValueError("the grid has no voxel with |grad n| > 1e-3")
+
+    def next_train(self, generator: Optional[torch.Generator] = None, indices=None, noise=None) -> Dict[str, torch.Tensor]:
+        """-> {"pts": [B,1,3], "grads": [B,1,3]}.  `indices` (into candidate_indices) / `noise` ([B,3] in [-1,1)) replace
+        the random draws for reproducible parity tests."""
+        from . import ops
+        m, dev = self.model, self.model.table.device
+        if indices is None:
+            indices = torch.randint(0, self.candidate_indices.shape[0], (self.batch_size,), generator=generator, device=dev)
+        idx = self.candidate_indices[torch.as_tensor(indices, device=dev).long()].double()
+        nd, lo, hi = (torch.tensor(v, dtype=torch.float64, device=dev) for v in (m.ndim, m.nmin, m.nmax))
+        if noise is None:
+            noise = torch.rand(idx.shape[0], 3, generator=generator, device=dev, dtype=torch.float64) * 2 - 1
+        ndelta = (hi - lo) / (nd - 1.0)
+        pts = (idx / nd * (hi - lo) + lo + torch.as_tensor(noise, device=dev).double() * ndelta).float().contiguous()
+        grads = ops.grid_lookup(m.table, m.ndim, m.nmin, m.nmax, pts)[:, 1:4].contiguous()
+        return {"pts": pts[:, None], "grads": grads[:, None]}
+
+
 def image_psnr(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """compute_psnr(mean((pred - target)^2)) with the reduction on the device (eval.py's per-image metric)."""
     from . import ops

@@ -381,3 +381,38 @@ def test_learned_grid_train_step(cuda_lib):
         model.apply(variables, 1, 2, batch["rays"], False)
     assert torch.equal(model.table.view(-1, 4)[:, 0], grid_n.detach())
     assert torch.equal(model.bricks.isnan(), ops.grid_bricks(ops.grid_table(grid_n.detach(), ndim, nmin, nmax), ndim).isnan())
+
+
+def test_grid_points_dataset(cuda_lib):
+    """utils.GridPoints = datasets.Grid (rnerf/datasets.py:245-328) on the device: candidate voxels, the idx / ndim point
+    placement, the interpolated gradient, against a numpy restatement of the reference lines with the same draws; and its
+    batch feeds the smoothness statistic through the training loss without changing it (annealing_rate = 0)."""
+    from samplenerfro_b200 import models, train, utils
+    n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
+    args = utils.Flags(config="example", stage="all", num_path_samples=12, white_bkgd=False, use_online_sparsity=False,
+                       normal_smooth_weight=1.0, bg_smooth_weight=0.0)
+    model, variables = models.construct_nerf(3, None, args, ndim, nmin, nmax, n)
+    gp = utils.GridPoints(model, extra_batch_size=200)
+    table = O.build_table(n, ndim, nmin, nmax)
+    gnorm = table[:, 1:].norm(dim=-1).reshape(*ndim)
+    cand = np.stack(np.where(gnorm.numpy() > 1e-3), axis=-1)                                  # :264
+    assert np.array_equal(gp.candidate_indices.cpu().numpy(), cand)
+    rs = np.random.RandomState(0)
+    pick = rs.choice(cand.shape[0], 200)
+    noise = rs.uniform(-1.0, 1.0, size=(200, 3))
+    batch = gp.next_train(indices=torch.from_numpy(pick), noise=torch.from_numpy(noise))
+    nd = np.array([(nmax[i] - nmin[i]) / (ndim[i] - 1.0) for i in range(3)])
+    pts = cand[pick] / np.array(ndim)[None] * (np.array(nmax) - np.array(nmin))[None] + np.array(nmin)[None] + noise * nd[None]   # :272-274
+    want = O.linear3(table, ndim, nmin, nmax, torch.from_numpy(pts).float())[:, 1:]            # :275
+    assert batch["pts"].shape == (200, 1, 3) and np.abs(batch["pts"][:, 0].cpu().numpy() - pts).max() < 1e-6
+    assert (batch["grads"][:, 0].cpu() - want).abs().max().item() <= 1e-6 * want.abs().max().item()
+    # through the loss: evaluated, but multiplied by annealing_rate = 0 (train.py:156)
+    B = 32
+    o, d = H.random_rays(B, seed=7, target_extent=0.6)
+    tb = {"rays": utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(B, 1).cuda()), "pixels": torch.rand(B, 3).cuda(),
+          "env_rays": None, "annealed_alpha": 0.5, **gp.next_train()}
+    with torch.no_grad():
+        total, stats = train.loss_fn(model, variables, tb, args, 1, 2)
+        tb2 = {k: v for k, v in tb.items() if k not in ("pts", "grads")}
+        total2, _ = train.loss_fn(model, variables, tb2, args, 1, 2)
+    assert float(stats["loss_nrm"]) == 0.0 and abs(float(total) - float(total2)) < 1e-6
