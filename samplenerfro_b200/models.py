@@ -105,8 +105,6 @@ class NerfModel:
         if (str(net_activation), str(rgb_activation), str(sigma_activation)) != ("relu", "sigmoid", "softplus"):
             unsupported.append("activations other than relu/sigmoid/softplus")
         if (num_rgb_channels, num_sigma_channels) != (3, 1): unsupported.append("num_rgb_channels/num_sigma_channels != 3/1")
-        if stage.startswith("ior"):
-            unsupported.append(f"stage={stage!r} (the IoR-fitting stage is not built; SURVEY section 8(f) rank 1)")
         if self.num_fine_samples <= 0: unsupported.append("num_fine_samples <= 0")
         if unsupported:
             raise NotImplementedError("rnerf_b200 kernels do not cover: " + "; ".join(unsupported))
@@ -155,7 +153,7 @@ class NerfModel:
         """Device image of one MLP's weights; repacked only when a parameter tensor changed."""
         p = variables["params"][name]
         flat = getattr(self, "_theta_flat", None)
-        if name == "bkgd_mlp" and flat is not None and p["Dense_0"]["kernel"].data_ptr() == flat[name].data_ptr():
+        if name == "bkgd_mlp" and flat is not None and name in flat and p["Dense_0"]["kernel"].data_ptr() == flat[name].data_ptr():
             return flat[name]      # the arena bucket IS the background kernels' weight image (train.ParamArena)
         sig = tuple((id(d["kernel"]), d["kernel"]._version, id(d["bias"]), d["bias"]._version) for d in p.values())
         hit = self._pack_cache.get(name)

@@ -18,6 +18,7 @@ from . import utils
 
 GRAD_BUCKETS = ("fine_mlp", "coarse_mlp", "bkgd_mlp")   # reverse order of backward completion
 ALL_STAGE_BUCKETS = GRAD_BUCKETS + ("path_sampler",)    # train.py:302-310: the "all" stage also trains so3_mlp
+IOR_STAGE_BUCKETS = ("path_sampler",)                   # train.py:295-301: the "ior" stage freezes the three radiance MLPs
 
 
 def tree_leaves(tree) -> List[torch.Tensor]:
@@ -246,16 +247,40 @@ class TrainState:
         fused Adam.  Radiance stage: path_sampler gets optax.set_to_zero (T7) -> it sits in the frozen tail; "all" stage
         (train.py:302-310): so3_mlp is a fourth trainable bucket, laid out as the march kernels' weight image."""
         stage = str(getattr(args, "stage", "radiance"))
-        arena = ParamArena(variables, ALL_STAGE_BUCKETS if stage.startswith("all") else GRAD_BUCKETS)
+        arena = ParamArena(variables, ALL_STAGE_BUCKETS if stage.startswith("all") else
+                           (IOR_STAGE_BUCKETS if stage.startswith("ior") else GRAD_BUCKETS))
         opt = ArenaAdam(arena, args)
         grid_opt = GridAdam(model, opt) if model is not None and getattr(model, "grid_n", None) is not None else None
         return TrainState(step=0, params=variables, opt=opt, arena=arena, grid_opt=grid_opt)
+
+
+def _ior_stage_loss(model, variables, batch, args, annealed_alpha, arena):
+    """train.py:131-143, the "ior" stage as the reference has it: no rendering; loss_nrm = normal_loss, which
+    compute_normal_loss_and_smooth returns as the constant 0.0 (rnerf/eikonal_utils.py:98), and every other term is 0 -- so
+    the only thing that reaches the parameters is the weight-decay term.  The smoothness statistic is still evaluated when the
+    batch carries the Grid points, like the reference does."""
+    dev = model.device
+    zero = torch.zeros((), device=dev)
+    if batch.get("pts") is not None:
+        model.apply(variables, batch["pts"], batch["grads"], annealed_alpha, method=model.wrapper_compute_normal_loss_and_smooth)
+    if arena is not None:
+        with torch.no_grad():
+            weight_l2 = arena.weight_l2()
+    else:
+        leaves = tree_leaves(variables)
+        weight_l2 = sum((z ** 2).sum() for z in leaves) / sum(z.numel() for z in leaves)
+    total = args.weight_decay_mult * weight_l2
+    stats = {"loss": zero, "psnr": zero, "loss_c": zero, "psnr_c": zero, "weight_l2": weight_l2.detach(), "loss_bg": zero,
+             "loss_bg_smooth": zero, "loss_sp": zero, "loss_nrm": zero, "annealing_rate": annealed_alpha}
+    return total, stats
 
 
 def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, arena: Optional[ParamArena] = None):
     """train.py:75-162, radiance stage.  Returns (total, stats).  With `arena`, the weight_l2 term is a statistic only:
     its closed-form gradient is applied by the optimiser kernel (ArenaAdam)."""
     annealed_alpha = float(batch["annealed_alpha"])
+    if str(getattr(args, "stage", "radiance")).startswith("ior"):
+        return _ior_stage_loss(model, variables, batch, args, annealed_alpha, arena)
     rays = batch["rays"]
     ret, loss_sp = model.apply(variables, key_0, key_1, rays, args.randomized, annealed_alpha, jitter=jitter, u=u)
     rgb, _d, _a, trans, trans_rgb_bkgd = ret[-1]
@@ -334,7 +359,8 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
     model._grad_sink, model._theta_flat = arena.sinks, arena.theta_flat
     try:
         total, stats = loss_fn(model, state.params, batch, args, key_0, key_1, jitter=jitter, u=u, arena=arena)
-        total.backward()
+        if total.requires_grad:       # ("ior" stage with the arena: only the closed-form weight-decay gradient exists)
+            total.backward()
     finally:
         model._grad_sink = None
     arena.allreduce_mean(world_size, group)
@@ -418,8 +444,8 @@ def train_step(model, rng, state: TrainState, batch: Dict, args=None, world_size
     lr = utils.learning_rate_decay(state.step, args.lr_init, args.lr_final, args.max_steps, args.lr_delay_steps,
                                    args.lr_delay_mult)
     on_cuda = state.arena.theta.is_cuda
-    if use_graph is None:
-        use_graph = on_cuda and jitter is None and u is None
+    if use_graph is None:     # (the "ior" stage has no rays and a handful of kernels: nothing to capture)
+        use_graph = on_cuda and jitter is None and u is None and not str(getattr(args, "stage", "")).startswith("ior")
     state.opt.stage_hyper(lr)
     if state.grid_opt is not None:
         state.grid_opt.stage_hyper(lr)

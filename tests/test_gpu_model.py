@@ -114,7 +114,7 @@ def test_unsupported_configs_fail_loudly(cuda_lib, example_scene):
     with pytest.raises(NotImplementedError):
         models.construct_nerf(0, None, _flags(net_width=128), ndim, nmin, nmax, n)
     with pytest.raises(NotImplementedError):
-        models.construct_nerf(0, None, _flags(stage="ior"), ndim, nmin, nmax, n)
+        models.construct_nerf(0, None, _flags(legacy_posenc_order=True), ndim, nmin, nmax, n)
 
 
 def test_cpu_tensors_are_rejected(cuda_lib):
@@ -213,3 +213,31 @@ def test_all_stage_ragged_march_matches_lockstep(cuda_lib, monkeypatch):
         assert torch.equal(a.rec[before], b.rec[before])
     act = (ops.path_views(b)[4].norm(dim=-1) > 1e-3)
     assert act.any(dim=1).sum().item() > 50                               # the MLP was needed on many rays
+
+
+def test_ior_stage_is_the_reference_s_degenerate_stage(cuda_lib, example_scene):
+    """stage="ior" (train.py:131-143): no rendering, loss_nrm = normal_loss = the constant 0.0 of
+    rnerf/eikonal_utils.py:98 -- only weight decay reaches the parameters, and only path_sampler is trainable
+    (train.py:295-301).  Rendering in this stage marches without the so3 rotation (rnerf/eikonal_utils.py:34 tests "all")."""
+    from samplenerfro_b200 import models, train, utils
+    n, ndim, nmin, nmax = example_scene
+    args = _flags(stage="ior")
+    args.weight_decay_mult, args.lr_delay_steps, args.normal_loss_weight = 0.1, 0, 1.0
+    model, variables = models.construct_nerf(0, None, args, ndim, nmin, nmax, n)
+    state = train.TrainState.create(variables, args)
+    assert state.arena.buckets == ("path_sampler",)
+    so3 = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]["Dense_0"]["kernel"]
+    coarse = variables["params"]["coarse_mlp"]["Dense_0"]["kernel"]
+    assert so3.requires_grad and not coarse.requires_grad
+    s0, c0 = so3.detach().clone(), coarse.detach().clone()
+    batch = {"annealed_alpha": 0.5, **utils.GridPoints(model, 64).next_train()}
+    state.step = 1
+    state, stats, _ = train.train_step(model, 0, state, batch, args)
+    assert float(stats["loss"]) == 0.0 and float(stats["loss_nrm"]) == 0.0
+    assert torch.equal(coarse, c0)
+    moved = so3.detach() - s0
+    assert moved.abs().max().item() > 0 and (torch.sign(moved) == -torch.sign(s0))[s0 != 0].all()     # pure decay
+    o, d = H.random_rays(16, seed=1)
+    with torch.no_grad():
+        ret, _ = model.apply(variables, 1, 2, utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(16, 1).cuda()), False)
+    assert torch.isfinite(ret[1][0]).all()
