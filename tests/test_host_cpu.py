@@ -151,3 +151,18 @@ def test_mesh_pkl_loader(tmp_path):
         pickle.dump(d, f)
     _, _, nmin, nmax = utils.load_mesh_pkl(str(tmp_path / "mesh.pkl"))
     assert nmin == [0, 0, 0] and nmax == [1, 1, 1]
+
+
+def test_band_rows_partition_every_frame():
+    """utils.band_rows: the bands of all ranks tile [0, H) in order, for any H and world size (incl. more ranks than rows)."""
+    from samplenerfro_b200 import utils
+    for H in (1, 2, 5, 7, 756, 800):
+        for N in (1, 2, 3, 4, 8):
+            edge, per0 = 0, None
+            for r in range(N):
+                r0, r1, per = utils.band_rows(H, r, N)
+                assert r0 == min(edge, H) and r0 <= r1 <= H and r1 - r0 <= per
+                per0 = per if per0 is None else per0
+                assert per == per0
+                edge = r1
+            assert edge == H

@@ -156,3 +156,53 @@ def test_loss_gradient_flows_only_to_radiance_params():
     assert P["bkgd_mlp"]["Dense_0"]["kernel"].grad.abs().sum() > 0
     g = P["path_sampler"]["scan"]["idx_model"]["so3_mlp"]["Dense_0"]["kernel"].grad
     assert g is None or g.abs().max() == 0      # only the (zero-weighted) weight_l2 term touches it
+
+
+def test_rodrigues_is_a_rotation_and_identity_at_zero_angle():
+    """rnerf/ior_utils.py:300-306: pred = |g|_safe * R(raw) g/|g|_safe -- the norm is preserved, raw -> 0 leaves g unchanged
+    (theta is clamped to 1e-3, e = raw/theta -> 0: cos(1e-3) g), and a quarter turn about z maps x to y."""
+    gen = torch.Generator().manual_seed(0)
+    g = torch.randn(50, 3, generator=gen) * 3
+    raw = torch.randn(50, 3, generator=gen)
+    pred = O.rodrigues_grad(raw, g)
+    assert torch.allclose(pred.norm(dim=-1), g.norm(dim=-1), rtol=1e-5)
+    same = O.rodrigues_grad(torch.zeros(50, 3), g)
+    assert torch.allclose(same, g * math.cos(1e-3), rtol=1e-6, atol=1e-7)
+    q = O.rodrigues_grad(torch.tensor([[0.0, 0.0, math.pi / 2]]), torch.tensor([[2.0, 0.0, 0.0]]))
+    assert torch.allclose(q, torch.tensor([[0.0, 2.0, 0.0]]), atol=1e-6)
+
+
+def test_all_stage_loss_reaches_so3_mlp_only_through_the_coarse_samples():
+    """'all' stage: so3_mlp receives gradient from the training loss, and the fine samples carry none of it -- they are
+    stop_gradient (rnerf/model_utils.py:406-411), like ray_dist (rnerf/eikonal_utils.py:120) -- which is what the CUDA
+    reverse sweep relies on (it is fed d ray_pos_c / d ray_dir_c only)."""
+    G = 12
+    ndim, nmin, nmax = [G] * 3, [-1.5] * 3, [1.5] * 3
+    lin = torch.linspace(-1.5, 1.5, G)
+    X, Y, Z = torch.meshgrid(lin, lin, lin, indexing="ij")
+    n = (1.0 + 0.5 * torch.sigmoid((0.8 - (X ** 2 + Y ** 2 + Z ** 2).sqrt()) * 6)).reshape(-1, 1)
+    table = O.build_table(n, ndim, nmin, nmax)
+    cfg = O.ModelCfg(ndim=ndim, nmin=nmin, nmax=nmax, num_coarse_samples=8, num_fine_samples=8, num_path_samples=4, stage="all")
+    gen = torch.Generator().manual_seed(1)
+    V = O.init_variables(0)
+    so3 = V["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+    so3["Dense_4"]["kernel"] = torch.randn(128, 3, generator=gen) * 0.05
+    for p in O.tree_leaves(V):
+        p.requires_grad_(True)
+    o = torch.tensor([[0.1 * i, 0.0, 4.0] for i in range(6)]); d = torch.tensor([[0.0, 0.03 * i, -1.0] for i in range(6)])
+    d = d / d.norm(dim=-1, keepdim=True)
+    rays, px = O.Rays(o, d, d, torch.ones(6, 1)), torch.rand(6, 3, generator=gen)
+    jitter, u = O.default_jitter(cfg), O.deterministic_u(8)
+    loss, _ = O.train_loss(V, table, cfg, rays, px, None, jitter, u, 0.7, bg_smooth_weight=0.0)
+    loss.backward()
+    g = V["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]["Dense_0"]["kernel"].grad
+    assert g is not None and g.abs().max() > 0
+    # the resampled (fine) positions / directions are cut from the graph although the path they come from is not
+    ray_pos, ray_dir, ray_dist, _, idx_grad = O.march(table, ndim, nmin, nmax, o, d, cfg.near, cfg.far, 32, stage="all",
+                                                      so3_params=V["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"],
+                                                      annealed_alpha=0.7)
+    jl = jitter.long()
+    t_mid = 0.5 * (ray_dist[:, jl][..., 1:] + ray_dist[:, jl][..., :-1])
+    w = torch.rand(6, 6, generator=gen)
+    _, pos_f, dir_f, _ = O.sample_pdf(t_mid, w, ray_pos, ray_dir, ray_dist.detach(), idx_grad, u, jl)
+    assert not pos_f.requires_grad and not dir_f.requires_grad
