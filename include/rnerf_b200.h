@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 5
+#define RNERF_ABI_VERSION 6
 #define RNERF_PATH_STRIDE 12         /* full records */
 #define RNERF_PATH_STRIDE_COMPACT 8
 
@@ -81,12 +81,17 @@ int rnerf_march_fwd(const float* table, const float* bricks /* from rnerf_grid_b
  * alpha*10), Rodrigues rotation of grad n) inside rnerf/eikonal_utils.py:30-49 (grad = where(|grad n| > 1e-3, pred,
  * grad n)).  so3_w: the 5 Dense kernels of so3_mlp ([in,out] row-major: 60x128, 128x128, 128x128, 188x128, 128x3) then
  * the 5 biases, fp32, rnerf_so3_weight_floats() values.  so3_window_host[10]: cosine-easing window per octave
- * (rnerf/model_utils.py:222-245 at alpha * 10).  Outputs as rnerf_march_fwd (idx_grad is the un-rotated grad n). */
+ * (rnerf/model_utils.py:222-245 at alpha * 10).  so3_window_dev: the same 10 values as fp32 in DEVICE memory, or NULL;
+ * when given it wins and is read at run time, so a captured CUDA graph of the training step follows the annealing
+ * schedule (train.py:350-351) instead of replaying its capture-time window (so3_window_host may then be NULL).  The same
+ * pair of arguments appears in rnerf_so3_predict and rnerf_march_all_bwd.
+ * Outputs as rnerf_march_fwd (idx_grad is the un-rotated grad n). */
 size_t rnerf_so3_weight_floats(void);
 int rnerf_march_all_fwd(const float* table, const float* bricks, const int ndim_host[3], const double nmin_host[3],
                         const double nmax_host[3], const float* origins, const float* viewdirs, int64_t n_rays,
                         double near, double far, int n_steps, int rec_floats, const float* so3_w,
-                        const double so3_window_host[10], float* path, float* t_col, void* stream);
+                        const double so3_window_host[10], const float* so3_window_dev, float* path, float* t_col,
+                        void* stream);
 
 /* ray_dir[B][S][3] = safe_l2_normalize(v) of every record: the `ray_dir` array of PathSampler.__call__
  * (rnerf/eikonal_utils.py:113), for callers that want the whole bent path (extract_mesh.py:178). */
@@ -210,8 +215,8 @@ int rnerf_sq_err(const float* a, const float* b, int64_t n, float* out_accum, vo
 /* VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267) on free-standing points: pred[N][3] = rodrigues(so3_mlp(
  * annealed_pos_enc(pts)), cond) -- the evaluation behind PathSampler.compute_normal_loss_and_smooth
  * (rnerf/eikonal_utils.py:84-98). */
-int rnerf_so3_predict(const float* so3_w, const double so3_window_host[10], const float* pts, const float* cond, int64_t n,
-                      float* pred, void* stream);
+int rnerf_so3_predict(const float* so3_w, const double so3_window_host[10], const float* so3_window_dev, const float* pts,
+                      const float* cond, int64_t n, float* pred, void* stream);
 size_t rnerf_mlp_input_grad_packed_floats(void);
 int rnerf_mlp_input_grad_pack(const float* dense0_kernel, const float* dense5_kernel, const float* dense10_kernel,
                               float* wt, void* stream);
@@ -225,7 +230,7 @@ int rnerf_march_all_bwd(const float* table, const float* bricks, const int ndim_
                         const double nmax_host[3], const float* path, int rec_floats, int64_t n_rays, double near,
                         double far, int n_steps, const int32_t* jitter, int n_coarse, const float* d_pos_c,
                         const float* d_dir_c, const float* so3_w, const float* so3_wt, const double so3_window_host[10],
-                        float* g_so3, float* d_origins, float* d_viewdirs, float* d_table, void* stream);
+                        const float* so3_window_dev, float* g_so3, float* d_origins, float* d_viewdirs, float* d_table, void* stream);
 int rnerf_grid_table_bwd(const float* d_table, const int ndim_host[3], const double nmin_host[3], const double nmax_host[3],
                          float* d_n, void* stream);
 

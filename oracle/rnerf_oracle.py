@@ -716,13 +716,85 @@ def generate_rays(camtoworld: np.ndarray, h: int, w: int, focal: float, use_pixe
 
 
 # ----------------------------------------------------------------------------------------------
-# a18. mip helpers for curved rays -- DEAD on the live path (T8); restated behind this flag only
-# (rnerf/mip.py:26-57,116-175)
+# a18. mip helpers for curved rays -- DEAD on the live path (T8: both call sites in rnerf/models.py:249-254,386-391 are
+# commented out); restated here so that the row exists behind a flag.  Pinned by tests/golden/ref_functions.npz (mip_*),
+# produced by executing rnerf/mip.py under the shim.  (rnerf/mip.py:26-57,60-113,116-175; rnerf/math_utils.py:27-38)
 # ----------------------------------------------------------------------------------------------
+def _safe_trig(x, fn, t=100 * math.pi):
+    """math_utils.safe_trig_helper (rnerf/math_utils.py:27-28): fn(where(|x| < t, x, x % t)); jnp's % is the floor-mod."""
+    tt = _c(t, x.dtype)
+    return fn(torch.where(torch.abs(x) < tt, x, torch.remainder(x, tt)))
+
+
+def safe_sin(x):
+    return _safe_trig(x, torch.sin)
+
+
+def safe_cos(x):
+    return _safe_trig(x, torch.cos)
+
+
 def expected_sin(x, x_var):
-    y = torch.exp(-0.5 * x_var) * torch.sin(x)
-    y_var = torch.clamp(0.5 * (1 - torch.exp(-2 * x_var) * torch.cos(2 * x)) - y ** 2, min=0)
+    """mip.expected_sin (rnerf/mip.py:26-32): mean and variance of sin(z), z ~ N(x, x_var)."""
+    y = torch.exp(-0.5 * x_var) * safe_sin(x)
+    y_var = torch.clamp(0.5 * (1 - torch.exp(-2 * x_var) * safe_cos(2 * x)) - y ** 2, min=0)
     return y, y_var
+
+
+def lift_gaussian(d, t_mean, t_var, r_var, diag, near):
+    """mip.lift_gaussian (rnerf/mip.py:35-57) for CURVED rays: `d` is per-sample [B,N,3]; the mean is the running sum of
+    d * dt with dt_0 = t_mean_0 - near (the refraction-ray-cone construction), not origin + d * t."""
+    t = torch.cat([t_mean[:, 0:1] - near, t_mean[:, 1:] - t_mean[:, :-1]], dim=-1)[..., None]
+    mean = torch.cumsum(d * t, dim=1)
+    d_mag_sq = torch.clamp((d ** 2).sum(-1, keepdim=True), min=1e-10)
+    if diag:
+        d_outer_diag = d ** 2
+        null_outer_diag = 1 - d_outer_diag / d_mag_sq
+        return mean, t_var[..., None] * d_outer_diag + r_var[..., None] * null_outer_diag
+    d_outer = d[..., :, None] * d[..., None, :]
+    eye = torch.eye(d.shape[-1], dtype=d.dtype)
+    null_outer = eye - d[..., :, None] * (d / d_mag_sq)[..., None, :]
+    # (rnerf/mip.py:50-56 is written for upstream mip-NeRF's one direction per RAY -- `d[..., :, None] * d` and the
+    # `[..., None, :, :]` indices do not broadcast for this fork's per-sample [B,N,3] directions -- so the full-covariance
+    # branch is restated with the per-sample meaning and is UNPINNED; diag=True, cast_rays' default, is the pinned branch)
+    return mean, t_var[..., None, None] * d_outer + r_var[..., None, None] * null_outer
+
+
+def conical_frustum_to_gaussian(d, t0, t1, base_radius, diag, near, stable=True):
+    """mip.conical_frustum_to_gaussian (rnerf/mip.py:60-94)."""
+    if stable:
+        mu = (t0 + t1) / 2
+        hw = (t1 - t0) / 2
+        t_mean = mu + (2 * mu * hw ** 2) / (3 * mu ** 2 + hw ** 2)
+        t_var = (hw ** 2) / 3 - (4 / 15) * ((hw ** 4 * (12 * mu ** 2 - hw ** 2)) / (3 * mu ** 2 + hw ** 2) ** 2)
+        r_var = base_radius ** 2 * ((mu ** 2) / 4 + (5 / 12) * hw ** 2 - 4 / 15 * (hw ** 4) / (3 * mu ** 2 + hw ** 2))
+    else:
+        t_mean = (3 * (t1 ** 4 - t0 ** 4)) / (4 * (t1 ** 3 - t0 ** 3))
+        r_var = base_radius ** 2 * (3 / 20 * (t1 ** 5 - t0 ** 5) / (t1 ** 3 - t0 ** 3))
+        t_mosq = 3 / 5 * (t1 ** 5 - t0 ** 5) / (t1 ** 3 - t0 ** 3)
+        t_var = t_mosq - t_mean ** 2
+    return lift_gaussian(d, t_mean, t_var, r_var, diag, near)
+
+
+def cylinder_to_gaussian(d, t0, t1, radius, diag, near):
+    """mip.cylinder_to_gaussian (rnerf/mip.py:97-113)."""
+    t_mean = (t0 + t1) / 2
+    r_var = radius ** 2 / 4
+    t_var = (t1 - t0) ** 2 / 12
+    return lift_gaussian(d, t_mean, t_var, r_var, diag, near)
+
+
+def cast_rays(t_vals, origins, directions, radii, ray_shape, near, diag=True):
+    """mip.cast_rays (rnerf/mip.py:116-140): t_vals [B,N+1] fence posts, origins = bent sample positions [B,N,3] (only
+    origins[:, 0] is used), directions = per-sample bent directions [B,N,3], radii [B,1] -> (means [B,N,3], covs)."""
+    t0, t1 = t_vals[..., :-1], t_vals[..., 1:]
+    if ray_shape == "cone":
+        means, covs = conical_frustum_to_gaussian(directions, t0, t1, radii, diag, near)
+    elif ray_shape == "cylinder":
+        means, covs = cylinder_to_gaussian(directions, t0, t1, radii, diag, near)
+    else:
+        raise AssertionError(ray_shape)
+    return means + origins[:, 0:1], covs
 
 
 def integrated_pos_enc(mean, var_diag, min_deg, max_deg):

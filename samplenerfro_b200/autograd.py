@@ -197,14 +197,14 @@ class _MarchAll(torch.autograd.Function):
         return (None,) * 8 + (d_table, None) + tuple(ops.so3_unpack_views(g))
 
 
-def march_all(model, variables: Dict, origins, viewdirs, jitter, annealed_alpha: float, compact: bool, table=None, bricks=None):
+def march_all(model, variables: Dict, origins, viewdirs, jitter, window, compact: bool, table=None, bricks=None):
     """-> (BentPath, pos_c, dir_c, t_c) with autograd edges from pos_c / dir_c to so3_mlp ("all" stage) and to `table` when
-    it requires grad."""
+    it requires grad.  `window`: model.so3_window(annealed_alpha) as 10 floats, or a CUDA tensor [10] read at run time."""
     table = model.table if table is None else table
     bricks = model.bricks if bricks is None and table is model.table else bricks
     if model.stage.startswith("all"):
         p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
-        w, window, plist, sink = model._so3_packed(variables), model.so3_window(annealed_alpha), _mlp_param_list(p, 5), _sink(model, "so3_mlp")
+        w, plist, sink = model._so3_packed(variables), _mlp_param_list(p, 5), _sink(model, "so3_mlp")
     else:
         w, window, plist, sink = None, None, [], None
     pos_c, dir_c, t_c, rec, t_col = _MarchAll.apply(model, sink, w, window, origins, viewdirs, jitter, compact, table, bricks, *plist)
@@ -214,17 +214,21 @@ def march_all(model, variables: Dict, origins, viewdirs, jitter, annealed_alpha:
 # ----------------------------------------------------------------------------- compositing (a11 + a12)
 class _Composite(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias):
-        o = ops.composite_fwd(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias, want_weights=True)
+    def forward(ctx, raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias, want_alpha=False):
+        o = ops.composite_fwd(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias, want_weights=True,
+                              want_alpha=want_alpha)
         ctx.cfg = (white_bkgd, rgb_padding, sigma_bias, bkgd_raw is not None, mask is not None)
         ctx.save_for_backward(raw, t, dirs, bkgd_raw if bkgd_raw is not None else raw.new_empty(0),
                               mask if mask is not None else raw.new_empty(0))
-        outs = (o["comp_rgb"], o["distance"], o["acc"], o["weights"], o["trans"], o["trans_rgb_bkgd"])
-        ctx.mark_non_differentiable(o["distance"], o["acc"], o["weights"])
+        # alpha feeds only the online-sparsity term, which train.py:156-159 multiplies by annealing_rate = 0:
+        # its gradient contribution is exactly zero, so it is handed out as a non-differentiable output
+        alpha = o["alpha"] if want_alpha else raw.new_empty(0)
+        outs = (o["comp_rgb"], o["distance"], o["acc"], o["weights"], o["trans"], o["trans_rgb_bkgd"], alpha)
+        ctx.mark_non_differentiable(o["distance"], o["acc"], o["weights"], alpha)
         return outs
 
     @staticmethod
-    def backward(ctx, d_rgb, _d_dist, _d_acc, _d_w, d_trans, d_trb):
+    def backward(ctx, d_rgb, _d_dist, _d_acc, _d_w, d_trans, d_trb, _d_alpha=None):
         raw, t, dirs, bk, mask = ctx.saved_tensors
         white_bkgd, rgb_padding, sigma_bias, has_bk, has_mask = ctx.cfg
         d_raw, d_bk = ops.composite_bwd(raw, t, dirs, bk if has_bk else None, mask if has_mask else None,
@@ -232,16 +236,17 @@ class _Composite(torch.autograd.Function):
                                         None if d_trans is None else d_trans.contiguous().view(-1),
                                         None if d_trb is None else d_trb.contiguous(),
                                         white_bkgd, rgb_padding, sigma_bias)
-        return d_raw, None, None, (d_bk if has_bk else None), None, None, None, None
+        return d_raw, None, None, (d_bk if has_bk else None), None, None, None, None, None
 
 
 def composite(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias, want_weights=True, want_alpha=False):
     """activations + volumetric_rendering -> dict.  Differentiable wrt raw / bkgd_raw through comp_rgb, trans and
     trans_rgb_bkgd (the outputs train.py's loss reads); distance / acc / weights are not differentiated."""
     if torch.is_grad_enabled() and (raw.requires_grad or (bkgd_raw is not None and bkgd_raw.requires_grad)):
-        rgb, dist, acc, w, trans, trb = _Composite.apply(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias)
-        return {"comp_rgb": rgb, "distance": dist, "acc": acc, "weights": w, "alpha": None, "trans": trans,
-                "trans_rgb_bkgd": trb}
+        rgb, dist, acc, w, trans, trb, alpha = _Composite.apply(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding,
+                                                                sigma_bias, bool(want_alpha))
+        return {"comp_rgb": rgb, "distance": dist, "acc": acc, "weights": w, "alpha": alpha if want_alpha else None,
+                "trans": trans, "trans_rgb_bkgd": trb}
     with torch.no_grad():
         return ops.composite_fwd(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias,
                                  want_weights=want_weights, want_alpha=want_alpha)

@@ -214,7 +214,7 @@ __device__ __forceinline__ void so3_eval(const So3Args& a, float* dyn_smem, So3R
       const int f = e / n_here, cc = e - f * n_here;
       const int k = f / 6, q = f - 6 * k, c = q >= 3 ? q - 3 : q;
       const float xb = mul(P[c * SO3_RP + cc], (float)(1 << k));
-      X[f * SO3_RP + cc] = mul(sinf(q >= 3 ? add(xb, 1.57079632679489661923f) : xb), a.window[k]);
+      X[f * SO3_RP + cc] = mul(sinf(q >= 3 ? add(xb, 1.57079632679489661923f) : xb), so3_window_at(a, k));
     }
     int layer = 0;
     if (n_act <= 8) {
@@ -655,7 +655,7 @@ bool rnerf::make_march_geom(const int ndim[3], const double nmin[3], const doubl
 static int march_impl(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
                       const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
                       double near, double far, int n_steps, int rec_floats, const float* so3_w,
-                      const double* so3_window, float* path, float* t_col, void* stream) {
+                      const double* so3_window, const float* so3_window_dev, float* path, float* t_col, void* stream) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_fwd: n_rays < 0");
   RNERF_REQUIRE(n_steps >= 2, RNERF_E_SHAPE, "rnerf_march_fwd: n_steps must be >= 2 (step = (far-near)/(S-1))");
@@ -679,7 +679,8 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
   int slots = 0;
   if (so3_w != nullptr) {
     so3.w = so3_w;
-    for (int k = 0; k < 10; ++k) so3.window[k] = (float)so3_window[k];
+    for (int k = 0; k < 10; ++k) so3.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
+    so3.window_dev = so3_window_dev;
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -737,7 +738,7 @@ extern "C" int rnerf_march_fwd(const float* table, const float* bricks, const in
                                double near, double far, int n_steps, int rec_floats, float* path, float* t_col,
                                void* stream) {
   return march_impl(table, bricks, ndim, nmin, nmax, origins, viewdirs, n_rays, near, far, n_steps, rec_floats, nullptr,
-                    nullptr, path, t_col, stream);
+                    nullptr, nullptr, path, t_col, stream);
 }
 
 extern "C" size_t rnerf_so3_weight_floats(void) { return SO3_FLOATS; }
@@ -745,10 +746,12 @@ extern "C" size_t rnerf_so3_weight_floats(void) { return SO3_FLOATS; }
 extern "C" int rnerf_march_all_fwd(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
                                    const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
                                    double near, double far, int n_steps, int rec_floats, const float* so3_w,
-                                   const double so3_window[10], float* path, float* t_col, void* stream) {
-  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(so3_window);
+                                   const double so3_window[10], const float* so3_window_dev, float* path, float* t_col,
+                                   void* stream) {
+  RNERF_REQUIRE_PTR(so3_w);
+  RNERF_REQUIRE(so3_window != nullptr || so3_window_dev != nullptr, RNERF_E_NULL, "rnerf_march_all_fwd: no so3 window given");
   return march_impl(table, bricks, ndim, nmin, nmax, origins, viewdirs, n_rays, near, far, n_steps, rec_floats, so3_w,
-                    so3_window, path, t_col, stream);
+                    so3_window, so3_window_dev, path, t_col, stream);
 }
 
 extern "C" int rnerf_select(const float* path, int rec_floats, int64_t n_rays, int n_steps, const int32_t* jitter,
@@ -779,15 +782,17 @@ extern "C" int rnerf_path_dirs(const float* path, int rec_floats, int64_t n_rays
   return check_launch("rnerf_path_dirs");
 }
 
-extern "C" int rnerf_so3_predict(const float* so3_w, const double so3_window[10], const float* pts, const float* cond, int64_t n,
-                                 float* pred, void* stream) {
+extern "C" int rnerf_so3_predict(const float* so3_w, const double so3_window[10], const float* so3_window_dev, const float* pts,
+                                 const float* cond, int64_t n, float* pred, void* stream) {
   RNERF_REQUIRE(n >= 0, RNERF_E_SHAPE, "rnerf_so3_predict: n < 0");
   if (n == 0) return 0;
-  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(so3_window); RNERF_REQUIRE_PTR(pts); RNERF_REQUIRE_PTR(cond); RNERF_REQUIRE_PTR(pred);
+  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(pts); RNERF_REQUIRE_PTR(cond); RNERF_REQUIRE_PTR(pred);
+  RNERF_REQUIRE(so3_window != nullptr || so3_window_dev != nullptr, RNERF_E_NULL, "rnerf_so3_predict: no so3 window given");
   RNERF_REQUIRE(aligned16(so3_w), RNERF_E_ALIGN, "rnerf_so3_predict: so3_w must be 16-byte aligned");
   So3Args so3;
   so3.w = so3_w;
-  for (int k = 0; k < 10; ++k) so3.window[k] = (float)so3_window[k];
+  for (int k = 0; k < 10; ++k) so3.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
+  so3.window_dev = so3_window_dev;
   const int slots = 4;
   const size_t dyn = so3_smem_bytes(slots);
   cudaError_t e = cudaFuncSetAttribute(so3_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

@@ -47,6 +47,7 @@ struct So3BwdArgs {
   const float* wt;       // transposed image: T0 [128][60], T1, T2, T3a [128][128], T3b [128][60]  (T_l[out][in] = W_l[in][out])
   float* gw;             // gradient image, same layout as w, accumulated into
   float window[10];
+  const float* window_dev;   // device copy of the window or NULL (So3Args::window_dev)
 };
 
 __global__ void __launch_bounds__(256) so3_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt) {
@@ -367,7 +368,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
       if (cc < n_here) {
         const int k = f / 6, q = f - 6 * k, c = q >= 3 ? q - 3 : q;
         const float xb = mul(P[c * BW_RP + cc], (float)(1 << k));
-        v = mul(sinf(q >= 3 ? add(xb, half_pi) : xb), a.window[k]);
+        v = mul(sinf(q >= 3 ? add(xb, half_pi) : xb), so3_window_at(a, k));
       }
       X[f * BW_RP + cc] = v;
     }
@@ -505,7 +506,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
 #pragma unroll
         for (int k = 0; k < 10; ++k) {
           const float xb = mul(x, sc);
-          gpc += a.window[k] * sc * (cosf(xb) * DX[(k * 6 + c) * BW_RP + cc] + cosf(add(xb, half_pi)) * DX[(k * 6 + 3 + c) * BW_RP + cc]);
+          gpc += so3_window_at(a, k) * sc * (cosf(xb) * DX[(k * 6 + c) * BW_RP + cc] + cosf(add(xb, half_pi)) * DX[(k * 6 + 3 + c) * BW_RP + cc]);
           sc *= 2.f;
         }
       }
@@ -643,7 +644,8 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
                                    const double nmax[3], const float* path, int rec_floats, int64_t n_rays, double near,
                                    double far, int n_steps, const int32_t* jitter, int n_coarse, const float* d_pos_c,
                                    const float* d_dir_c, const float* so3_w, const float* so3_wt,
-                                   const double so3_window[10], float* g_so3, float* d_origins, float* d_viewdirs,
+                                   const double so3_window[10], const float* so3_window_dev, float* g_so3, float* d_origins,
+                                   float* d_viewdirs,
                                    float* d_table, void* stream) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_rays < 0");
@@ -652,7 +654,10 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   RNERF_REQUIRE(rec_floats == 8 || rec_floats == 12, RNERF_E_SHAPE, "rnerf_march_all_bwd: rec_floats must be 8 or 12");
   if (n_rays == 0) return 0;
   RNERF_REQUIRE_PTR(path); RNERF_REQUIRE_PTR(jitter); RNERF_REQUIRE_PTR(d_pos_c); RNERF_REQUIRE_PTR(d_dir_c);
-  if (so3_w != nullptr) { RNERF_REQUIRE_PTR(so3_wt); RNERF_REQUIRE_PTR(so3_window); RNERF_REQUIRE_PTR(g_so3); }
+  if (so3_w != nullptr) {
+    RNERF_REQUIRE_PTR(so3_wt); RNERF_REQUIRE_PTR(g_so3);
+    RNERF_REQUIRE(so3_window != nullptr || so3_window_dev != nullptr, RNERF_E_NULL, "rnerf_march_all_bwd: no so3 window given");
+  }
   RNERF_REQUIRE(aligned16(table) && aligned16(path) && aligned16(so3_w) && aligned16(so3_wt) && aligned16(g_so3) && aligned16(d_table),
                 RNERF_E_ALIGN, "rnerf_march_all_bwd: table/path/so3 images/d_table must be 16-byte aligned");
   RNERF_REQUIRE(grid_fits_int32(ndim), RNERF_E_SHAPE, "rnerf_march_all_bwd: grids with >= 2^31 voxels are not supported");
@@ -663,6 +668,7 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   So3BwdArgs a;
   a.w = so3_w; a.wt = so3_wt; a.gw = g_so3;
   for (int k = 0; k < 10; ++k) a.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
+  a.window_dev = so3_w != nullptr ? so3_window_dev : nullptr;
   const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 64 + 8 * SO3_MAX_SLOTS + (size_t)BW_RING_SLOTS * BW_SLOT_FLOATS * 4 +
                      (((size_t)n_steps * 2 + 15) & ~(size_t)15);
   RNERF_REQUIRE(dyn <= 227 * 1024, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps too large for the step map in shared memory");

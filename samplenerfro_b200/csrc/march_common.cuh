@@ -48,7 +48,13 @@ constexpr int SO3_OFF_W1 = SO3_IN * SO3_W, SO3_OFF_W2 = SO3_OFF_W1 + SO3_W * SO3
 struct So3Args {
   const float* w;        // kernels W0..W4 ([in][out] row-major) then biases b0..b4, fp32, SO3_FLOATS
   float window[10];      // cosine-easing window of annealed_pos_enc (rnerf/model_utils.py:236-245) per octave
+  const float* window_dev;   // the same 10 values in device memory, or NULL: read at run time, so a captured CUDA graph follows
+                             // a changing annealed_alpha (train.py:350-351) instead of freezing the capture-time window
 };
+template <typename A>
+__device__ __forceinline__ float so3_window_at(const A& a, int k) {
+  return a.window_dev != nullptr ? __ldg(a.window_dev + k) : a.window[k];
+}
 
 
 // ---- packed fp32 pairs (SASS: FFMA2) -------------------------------------------------------------------------------------

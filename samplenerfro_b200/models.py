@@ -218,7 +218,8 @@ class NerfModel:
         from . import autograd as ag
         return ag.bkgd_color(self, variables, viewdirs.reshape(-1, 3).contiguous())
 
-    def wrapper_compute_normal_loss_and_smooth(self, variables: Dict, ray_pos, idx_grad, annealed_alpha: float = 1.0, noise=None):
+    def wrapper_compute_normal_loss_and_smooth(self, variables: Dict, ray_pos, idx_grad, annealed_alpha: float = 1.0, noise=None,
+                                               so3_window=None):
         """PathSampler.compute_normal_loss_and_smooth (rnerf/eikonal_utils.py:84-98, rnerf/models.py:139-140) ->
         (0.0, smoothness): mean over points of sum |pred(x) - pred(x + N(0, normal_radius_scale) * ndelta)| / |grad n|_safe.
         A statistic only: train.py:156 hard-codes annealing_rate = 0, which multiplies it in the loss and in the stats,
@@ -230,7 +231,7 @@ class NerfModel:
         nd = torch.tensor([(self.nmax[i] - self.nmin[i]) / (self.ndim[i] - 1.0) for i in range(3)], dtype=torch.float64)
         jit = (torch.as_tensor(np.asarray(noise), dtype=torch.float64).reshape(-1, 3) * nd).to(self.device, torch.float32)
         with torch.no_grad():
-            so3 = (self._so3_packed(variables), self.so3_window(annealed_alpha))
+            so3 = (self._so3_packed(variables), so3_window if so3_window is not None else self.so3_window(annealed_alpha))
             pred = ops.so3_predict(so3[0], so3[1], pts, cond)
             pred_rand = ops.so3_predict(so3[0], so3[1], pts + jit, cond)
             factor = torch.sqrt(torch.clamp((cond * cond).sum(-1, keepdim=True), min=1e-6))
@@ -250,8 +251,14 @@ class NerfModel:
         return lo, hi
 
     def __call__(self, variables: Dict, rng_0, rng_1, rays: Rays, randomized: bool, annealed_alpha: float = 1.0, *,
-                 jitter: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None, debug: bool = False):
+                 jitter: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None, debug: bool = False,
+                 so3_window: Optional[torch.Tensor] = None):
+        """`so3_window`: optional CUDA tensor [10] holding so3_window(annealed_alpha); the "all"-stage kernels then read the
+        window from device memory at run time (a captured CUDA graph of the training step refreshes it before every replay,
+        train._GraphedStep) instead of taking it by value."""
         from . import autograd as ag
+        window = so3_window if so3_window is not None else (
+            self.so3_window(annealed_alpha) if self.stage.startswith("all") else None)
         Nc, Nf, S = self.num_coarse_samples, self.num_fine_samples, self.num_march_steps
         origins = rays.origins.to(self.device, torch.float32).contiguous()
         viewdirs = rays.viewdirs.to(self.device, torch.float32).contiguous()   # T1: the unit viewdirs, not directions
@@ -269,28 +276,28 @@ class NerfModel:
             # extension: the table as a differentiable function of the learned grid, rebuilt in place with its brick map
             table = ag.grid_table(self, self.grid_n)
             ops.grid_bricks(self.table, self.ndim, out=self.bricks)
-            path, pos_c, dir_c, t_c = ag.march_all(self, variables, origins, viewdirs, jit, annealed_alpha, not need_grad,
+            path, pos_c, dir_c, t_c = ag.march_all(self, variables, origins, viewdirs, jit, window, not need_grad,
                                                    table=table, bricks=self.bricks)
             grad_c = None
-            if self.use_online_sparsity:
+            if need_grad:
                 with torch.no_grad():
                     grad_c = ops.select(path, jit, want_grad=True)[3]
         elif so3_p is not None and ag._needs_grad(so3_p):
             self._refresh_table()
             # "all" stage, training: so3_mlp rotates grad n inside every step (a4) and is reached by the loss through the
             # coarse samples; the reverse sweep of the scan is its own kernel
-            path, pos_c, dir_c, t_c = ag.march_all(self, variables, origins, viewdirs, jit, annealed_alpha, not need_grad)
+            path, pos_c, dir_c, t_c = ag.march_all(self, variables, origins, viewdirs, jit, window, not need_grad)
             grad_c = None
-            if self.use_online_sparsity:
+            if need_grad:
                 with torch.no_grad():
                     grad_c = ops.select(path, jit, want_grad=True)[3]
         else:
             self._refresh_table()
             with torch.no_grad():
-                so3 = (self._so3_packed(variables), self.so3_window(annealed_alpha)) if so3_p is not None else None
+                so3 = (self._so3_packed(variables), window) if so3_p is not None else None
                 path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S,
                                  bricks=self.bricks, compact=not need_grad, so3=so3)
-                pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=self.use_online_sparsity)
+                pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=need_grad)
         with torch.no_grad():
             mask_c = self._bbox_mask(pos_c) if self.use_mask_bbox else None
         # --- coarse pass
@@ -307,7 +314,7 @@ class NerfModel:
         with torch.no_grad():
             uu = self.draw_u(k1, B, randomized) if u is None else torch.as_tensor(u).to(self.device, torch.float32).contiguous()
             t_f, pos_f, dir_f, grad_f = ops.resample(path, t_c.detach(), out_c["weights"].detach(), uu, Nf,
-                                                     want_grad=self.use_online_sparsity and self.use_fine_sparsity)
+                                                     want_grad=debug or (self.use_online_sparsity and self.use_fine_sparsity))
             mask_f = self._bbox_mask(pos_f) if self.use_mask_bbox else None
         # --- fine pass
         raw_f = ag.radiance_mlp(self, variables, "fine_mlp", pos_f, dir_f)        # [B,Nc+Nf,4]
@@ -333,7 +340,8 @@ class NerfModel:
             rp, rd, rt, idn, idg = ops.path_views(path)
             dbg = {"path": path.rec, "ray_pos": rp, "ray_dir": rd, "ray_dist": rt, "idx_data": idn, "idx_grad": idg,
                    "ray_pos_c": pos_c, "jitter": jit, "u": uu, "t_c": t_c, "weights_c": out_c["weights"],
-                   "raw_c": raw_c, "raw_f": raw_f, "t_f": t_f, "pos_f": pos_f, "dir_f": dir_f, "raw_bkgd": raw_bkgd}
+                   "raw_c": raw_c, "raw_f": raw_f, "t_f": t_f, "pos_f": pos_f, "dir_f": dir_f, "raw_bkgd": raw_bkgd,
+                   "dir_c": dir_c, "idx_grad_c": grad_c, "idx_grad_f": grad_f}
             return ret, loss_sp, dbg
         return ret, loss_sp
 

@@ -107,6 +107,18 @@ def so3_pack(p: Dict) -> torch.Tensor:
     return w
 
 
+def _window_args(window):
+    """so3 window as the (host double[10] or None, device fp32[10] or None) pair of the C ABI: a CUDA tensor is passed by
+    pointer (read at run time -- what a captured graph needs), anything else by value."""
+    if isinstance(window, torch.Tensor) and window.is_cuda:
+        _chk(window, "so3 window")
+        assert window.numel() == 10
+        return None, _p(window)
+    vals = [float(v) for v in window]
+    assert len(vals) == 10
+    return (C.c_double * 10)(*vals), None
+
+
 def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n_steps: int,
           out: Optional[BentPath] = None, bricks: Optional[torch.Tensor] = None, compact: bool = False,
           t_col: bool = True, so3: Optional[Tuple[torch.Tensor, Sequence[float]]] = None) -> BentPath:
@@ -133,10 +145,9 @@ def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n
     if so3 is not None:
         w, window = so3
         _chk(w, "so3 weights")
-        assert len(window) == 10
-        win = (C.c_double * 10)(*[float(v) for v in window])
+        win, win_dev = _window_args(window)
         check(_lib.load().rnerf_march_all_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
-                                              float(far), int(n_steps), W, _p(w), win, _p(out.rec), _p(out.t), _stream()),
+                                              float(far), int(n_steps), W, _p(w), win, win_dev, _p(out.rec), _p(out.t), _stream()),
               "rnerf_march_all_fwd")
         return out
     check(_lib.load().rnerf_march_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
@@ -198,10 +209,10 @@ def so3_unpack_views(g: torch.Tensor):
 def so3_predict(w: torch.Tensor, window: Sequence[float], pts: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
     """VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267): rodrigues(so3_mlp(annealed_pos_enc(pts)), cond) -> [N,3]."""
     pts = _chk(pts.reshape(-1, 3).contiguous(), "pts"); cond = _chk(cond.reshape(-1, 3).contiguous(), "cond")
-    assert pts.shape == cond.shape and len(window) == 10
+    assert pts.shape == cond.shape
     pred = torch.empty_like(pts)
-    win = (C.c_double * 10)(*[float(v) for v in window])
-    check(_lib.load().rnerf_so3_predict(_p(_chk(w, "so3 weights")), win, _p(pts), _p(cond), pts.shape[0], _p(pred), _stream()),
+    win, win_dev = _window_args(window)
+    check(_lib.load().rnerf_so3_predict(_p(_chk(w, "so3 weights")), win, win_dev, _p(pts), _p(cond), pts.shape[0], _p(pred), _stream()),
           "rnerf_so3_predict")
     return pred
 
@@ -238,12 +249,12 @@ def march_all_bwd(table, ndim, nmin, nmax, path, near: float, far: float, jitter
         d_d = torch.empty(B, 3, device=rec.device) if want_ray_grads else None
         nd, lo, hi = _geom(ndim, nmin, nmax)
         check(_lib.load().rnerf_march_all_bwd(_p(table), _p(bricks), nd, lo, hi, _p(rec), W, B, float(near), float(far), S,
-                                              _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), None, None, None, None, _p(d_o),
+                                              _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), None, None, None, None, None, _p(d_o),
                                               _p(d_d), _p(d_table), _stream()), "rnerf_march_all_bwd")
         return None, d_o, d_d
     _chk(w, "so3 weights")
     d_pos_c = _chk(d_pos_c.contiguous(), "d_pos_c"); d_dir_c = _chk(d_dir_c.contiguous(), "d_dir_c")
-    assert d_pos_c.shape == (B, Nc, 3) and d_dir_c.shape == (B, Nc, 3) and len(window) == 10
+    assert d_pos_c.shape == (B, Nc, 3) and d_dir_c.shape == (B, Nc, 3)
     if bricks is not None:
         _chk(bricks, "bricks")
     g = torch.zeros_like(w) if g_so3 is None else _chk(g_so3, "g_so3")
@@ -252,9 +263,9 @@ def march_all_bwd(table, ndim, nmin, nmax, path, near: float, far: float, jitter
     d_o = torch.empty(B, 3, device=rec.device) if want_ray_grads else None
     d_d = torch.empty(B, 3, device=rec.device) if want_ray_grads else None
     nd, lo, hi = _geom(ndim, nmin, nmax)
-    win = (C.c_double * 10)(*[float(v) for v in window])
+    win, win_dev = _window_args(window)
     check(_lib.load().rnerf_march_all_bwd(_p(table), _p(bricks), nd, lo, hi, _p(rec), W, B, float(near), float(far), S,
-                                          _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), _p(w), _p(wt), win, _p(g), _p(d_o),
+                                          _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), _p(w), _p(wt), win, win_dev, _p(g), _p(d_o),
                                           _p(d_d), _p(d_table), _stream()), "rnerf_march_all_bwd")
     return g, d_o, d_d
 

@@ -282,7 +282,8 @@ def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, ar
     if str(getattr(args, "stage", "radiance")).startswith("ior"):
         return _ior_stage_loss(model, variables, batch, args, annealed_alpha, arena)
     rays = batch["rays"]
-    ret, loss_sp = model.apply(variables, key_0, key_1, rays, args.randomized, annealed_alpha, jitter=jitter, u=u)
+    ret, loss_sp = model.apply(variables, key_0, key_1, rays, args.randomized, annealed_alpha, jitter=jitter, u=u,
+                               so3_window=batch.get("so3_window"))
     rgb, _d, _a, trans, trans_rgb_bkgd = ret[-1]
     px = batch["pixels"][..., :3]
     loss = ((rgb - px) ** 2).mean()
@@ -307,7 +308,8 @@ def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, ar
     if (str(getattr(args, "stage", "radiance")).startswith("all") and batch.get("pts") is not None
             and (args.normal_loss_weight + args.normal_smooth_weight) > 0):
         # train.py:120-124: evaluated like the reference does, although annealing_rate = 0 removes it from loss and stats
-        nl, ns = model.apply(variables, batch["pts"], batch["grads"], annealed_alpha, method=model.wrapper_compute_normal_loss_and_smooth)
+        nl, ns = model.apply(variables, batch["pts"], batch["grads"], annealed_alpha, method=model.wrapper_compute_normal_loss_and_smooth,
+                             so3_window=batch.get("so3_window"))
         loss_nrm = annealing_rate * (args.normal_loss_weight * nl + args.normal_smooth_weight * ns)
     if arena is not None:
         with torch.no_grad():
@@ -399,6 +401,13 @@ class _GraphedStep:
                   else model.draw_u(None, B, False))
         self.static_batch = {"rays": self.rays, "pixels": self.pixels, "env_rays": self.env,
                              "annealed_alpha": float(batch["annealed_alpha"])}
+        # "all" stage: the so3 positional-encoding window follows annealed_alpha (train.py:350-351), which changes every
+        # step -- the captured kernels read it from this device buffer, refreshed before each replay (not baked in by value)
+        self.window = None
+        if str(getattr(args, "stage", "radiance")).startswith("all"):
+            self.window = torch.zeros(10, device=dev, dtype=torch.float32)
+            self.window_ring = _PinnedRing((10,), torch.float32, dev)
+            self.static_batch["so3_window"] = self.window
         self.load(model, batch, 0, 0, args)
         from . import _lib
         self.graph = torch.cuda.CUDAGraph()
@@ -418,6 +427,8 @@ class _GraphedStep:
             for dst, src in zip(self.env, batch["env_rays"]):
                 dst.copy_(src, non_blocking=True)
         self.jitter_ring.push(model.draw_jitter(key_0, host=True), self.jitter)
+        if self.window is not None:
+            self.window_ring.push(torch.tensor(model.so3_window(float(batch["annealed_alpha"])), dtype=torch.float32), self.window)
         if args.randomized:
             self.u.copy_(model.draw_u(key_1, self.u.shape[0], True))
 

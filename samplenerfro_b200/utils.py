@@ -130,6 +130,13 @@ def render_image(render_fn: Callable, rays: Rays, rng, normalize_disp: bool, chu
     render_fn(key_0, key_1, chunk_rays) -> (ret, loss_sp) with ret[-1] = (rgb, distance, acc, trans, trans_rgb_bkgd).
     Chunks are padded by edge replication to a multiple of `world_size` like the reference pads to the
     device count (rnerf/utils.py:357-361).  Returns (rgb[H,W,3], distance[H,W,1], acc[H,W,1]).
+
+    debug=True is the reference's commented "NOTE(debug): visualize coarse and fine samples" variant
+    (rnerf/utils.py:371-389 with rnerf/models.py:362-365,533-534; consumer extract_mesh.py:178): render_fn must then
+    return model.apply(..., debug=True)'s 3-tuple, and the result is the 8-tuple
+    (rgb, distance, acc, ray_pos[H,W,Nt,3], ray_dir[H,W,Nt,3], idx_grad[H,W,Nt,3], trans[H,W,1], ray_pos_c[H,W,Nc,3]):
+    the bent FINE sample positions / directions / grad n (what the fine tuple's ray_pos_c, ray_dir_c, idx_grad_c hold after
+    sample_pdf, rnerf/models.py:371) and the coarse sample positions.
     """
     height, width = rays[0].shape[:2]
     num_rays = height * width
@@ -143,12 +150,25 @@ def render_image(render_fn: Callable, rays: Rays, rng, normalize_disp: bool, chu
         padding = world_size - rem if rem != 0 else 0
         if padding:
             chunk_rays = namedtuple_map(lambda r: torch.cat([r, r[-1:].expand(padding, -1)], dim=0), chunk_rays)
-        chunk_results = render_fn(key_0, key_1, chunk_rays)[0][-1]
+        out = render_fn(key_0, key_1, chunk_rays)
+        chunk_results = list(out[0][-1])
+        if debug:
+            if len(out) < 3 or not isinstance(out[2], dict):
+                raise ValueError("render_image(debug=True) needs a render_fn that calls model.apply(..., debug=True)")
+            dbg = out[2]
+            chunk_results += [dbg["pos_f"], dbg["dir_f"], dbg["idx_grad_f"], dbg["ray_pos_c"]]
         results.append([x[:-padding] if padding else x for x in chunk_results])
-    rgb, distance, acc, trans, trans_rgb_bkgd = [torch.cat(r, dim=0) for r in zip(*results)]
+    cat = [torch.cat(r, dim=0) for r in zip(*results)]
+    rgb, distance, acc, trans, trans_rgb_bkgd = cat[:5]
     if normalize_disp:
         distance = (distance - distance.min()) / (distance.max() - distance.min())
-    return (rgb.reshape(height, width, -1), distance.reshape(height, width, -1), acc.reshape(height, width, -1))
+    ret = (rgb.reshape(height, width, -1), distance.reshape(height, width, -1), acc.reshape(height, width, -1))
+    if debug:
+        ray_pos, ray_dir, idx_grad, ray_pos_c = cat[5:9]
+        ret += (ray_pos.reshape(height, width, -1, 3), ray_dir.reshape(height, width, -1, 3),
+                idx_grad.reshape(height, width, -1, 3), trans.reshape(height, width, 1),
+                ray_pos_c.reshape(height, width, -1, 3))
+    return ret
 
 
 def _split_key(rng):

@@ -67,7 +67,7 @@ def args_for(config, **kw):
 
 
 def run_model(name, config, G, extent, radius, center, ws, sigma, B, seed, near, far, P, ri_scale, bd_cut_dist=None,
-              randomized=False, shift=(0, 0, 0), bias_scale=0.1):
+              randomized=False, shift=(0, 0, 0), bias_scale=0.1, keep_path=16):
     ndim, nmin, nmax = [G] * 3, [-extent] * 3, [extent] * 3
     data = sphere_grid(G, extent, radius, center)
     grid = ior_utils.conv3d_normal((data - 1.0) * ri_scale / 0.33 + 1.0, ndim, ws, sigma)       # train.py:223
@@ -111,7 +111,15 @@ def run_model(name, config, G, extent, radius, center, ws, sigma, B, seed, near,
     ps = eikonal_utils.PathSampler(near=near, far=far, stage="radiance", num_samples=64 * P,
                                    step_size=(far - near) / (64 * P - 1), ndim=ndim, nmin=nmin, nmax=nmax, grid=grid)
     pos, dirs, dist, idn, idg = ps.apply({"params": variables["params"]["path_sampler"]}, rays.origins, rays.viewdirs, 1.0)
-    out.update(path_pos=f32(pos), path_dir=f32(dirs), path_dist=f32(dist), path_n=f32(idn), path_grad=f32(idg))
+    # the whole path of the first `keep_path` rays, and a SHA-256 digest of every array over ALL rays (the oracle and the
+    # CUDA march are bit-exact against the reference's scan, so digests can be compared; 1024 rays x 768 steps x 11 floats
+    # would be 35 MB per scene)
+    import hashlib
+    kp = keep_path
+    out.update(path_pos=f32(pos)[:kp], path_dir=f32(dirs)[:kp], path_dist=f32(dist)[:kp], path_n=f32(idn)[:kp], path_grad=f32(idg)[:kp])
+    for nm, arr in (("pos", pos), ("dir", dirs), ("dist", dist), ("n", idn), ("grad", idg)):
+        out[f"path_{nm}_sha256"] = hashlib.sha256(np.ascontiguousarray(f32(arr)).tobytes()).hexdigest()
+        out[f"path_{nm}_sum64"] = np.float64(np.asarray(arr, dtype=np.float64).sum())
     params = {k: f32(v) for k, v in flatten(variables["params"]).items()}
     ppath = os.path.join(HERE, "ref_params.npz")
     if os.path.exists(ppath):
@@ -120,7 +128,7 @@ def run_model(name, config, G, extent, radius, center, ws, sigma, B, seed, near,
     else:
         np.savez_compressed(ppath, **params)
     np.savez_compressed(os.path.join(HERE, f"ref_model_{name}.npz"), **out)
-    print(name, "rgb fine mean", out["ret1_rgb"].mean(), "bend", np.abs(out["path_dir"][:, -1] - d).max())
+    print(name, "rgb fine mean", out["ret1_rgb"].mean(), "bend", np.abs(f32(dirs)[:, -1] - d).max())
 
 
 def run_functions():
@@ -225,8 +233,110 @@ def run_functions():
     out["mh_x"] = z
     out["mh_normalize"] = f32(math_utils.safe_l2_normalize(jnp.array(z)))
     out["mh_log"] = f32(math_utils.safe_log(jnp.array(np.abs(z))))
+    # mip helpers for curved rays (rnerf/mip.py:26-57,60-113,116-175; dead on the live path): the call the
+    # commented lines rnerf/models.py:249-254 would make -- t_vals = [ray_dist_c, last + 1e-3], bent positions and per-sample
+    # directions, cone and cylinder, diag=True -- then integrated_pos_enc(samples, 0, 10)
+    from rnerf import mip
+    B, N = 7, 24
+    tv = f32(2 + np.sort(rs.uniform(size=(B, N)) * 4, axis=-1))
+    tv = np.concatenate([tv, tv[:, -1:] + f32(1e-3)], -1)
+    mo = f32(rs.normal(size=(B, N, 3))); md = f32(rs.normal(size=(B, N, 3))); md /= np.linalg.norm(md, axis=-1, keepdims=True)
+    md = f32(md * rs.uniform(0.9, 1.1, size=(B, N, 1)))
+    mr = f32(rs.uniform(5e-4, 3e-3, size=(B, 1)))
+    out.update(mip_t_vals=tv, mip_origins=mo, mip_dirs=md, mip_radii=mr, mip_near=np.float32(2.0))
+    for shape in ("cone", "cylinder"):
+        mean, cov = mip.cast_rays(jnp.array(tv), jnp.array(mo), jnp.array(md), jnp.array(mr), shape, 2.0)
+        out[f"mip_{shape}_mean"], out[f"mip_{shape}_cov"] = f32(mean), f32(cov)
+        out[f"mip_{shape}_ipe"] = f32(mip.integrated_pos_enc((mean, cov), 0, 10))
+    ex = f32(rs.uniform(-400, 400, size=(50,))); ev = f32(rs.uniform(0, 4, size=(50,)) ** 2)
+    ey, eyv = mip.expected_sin(jnp.array(ex), jnp.array(ev))
+    out.update(mip_es_x=ex, mip_es_var=ev, mip_es_y=f32(ey), mip_es_yvar=f32(eyv))
     np.savez_compressed(os.path.join(HERE, "ref_functions.npz"), **out)
     print("functions ok")
+
+
+def run_train_loss():
+    """The forward of train.py's loss (train.py:75-162), by executing the UNMODIFIED source text of `train_step`
+    (train.py:58-183) -- cut out of the file with `ast`, because importing train.py would run absl flag parsing and pull
+    in optax / tensorboard -- in a namespace that supplies FLAGS and the shim.  The shim has no autodiff: jax.value_and_grad
+    evaluates the function and returns zero gradients, so what is pinned is the VALUE of the loss and every entry of
+    `stats` (the gradients are pinned by finite differences elsewhere).  -> ref_train_loss.npz"""
+    import ast
+    src = open("/root/reference/train.py").read()
+    node = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "train_step"][0]
+    fn_src = "\n".join(src.splitlines()[node.lineno - 1:node.end_lineno])
+    captured = {}
+
+    def value_and_grad(f, has_aux=False):
+        def run(params):
+            val, aux = f(params)
+            captured["total"] = val
+            return (val, aux), jax.tree_util.tree_map(lambda z: np.zeros_like(np.asarray(z)), params)
+        return run
+
+    def tree_reduce(f, tree, initializer=0):
+        acc = initializer
+        stack = [tree]
+        while stack:
+            t = stack.pop(0)
+            if isinstance(t, dict):
+                stack = list(t.values()) + stack
+            else:
+                acc = f(acc, t)
+        return acc
+
+    jax.value_and_grad = value_and_grad
+    jax.tree_util.tree_reduce = staticmethod(tree_reduce)
+    jax.lax.pmean = lambda x, axis_name=None: x
+    G, extent, B, P = 20, 1.5, 64, 12
+    ndim, nmin, nmax = [G] * 3, [-extent] * 3, [extent] * 3
+    grid = ior_utils.conv3d_normal((sphere_grid(G, extent, 0.8) - 1.0) * 0.5 / 0.33 + 1.0, ndim, 3, 1.0)
+    o, d = rays_towards_box(B, 21)
+    rs = np.random.RandomState(77)
+    rays = utils.Rays(origins=jnp.array(o), directions=jnp.array(d), viewdirs=jnp.array(d), radii=jnp.array(np.ones((B, 1))))
+    env = f32(rs.normal(size=(8, 8, 3))); env /= np.linalg.norm(env, axis=-1, keepdims=True)
+    env_rays = utils.Rays(origins=jnp.array(env), directions=jnp.array(env), viewdirs=jnp.array(env), radii=jnp.array(env[..., :1]))
+    pixels = f32(rs.uniform(size=(B, 3)))
+    out = {"grid": f32(grid), "ndim": np.array(ndim), "nmin": np.array(nmin), "nmax": np.array(nmax), "origins": o,
+           "viewdirs": d, "pixels": pixels, "env_viewdirs": f32(env), "num_path_samples": P}
+    for case, (alpha, bgw, smw, wd) in {"a": (0.5, 0.025, 1.0, 0.0), "b": (0.0, 0.025, 1.0, 0.0), "c": (0.7, 1.0, 0.5, 0.1)}.items():
+        args = args_for("example", randomized=True, num_path_samples=P)
+        flags = types.SimpleNamespace(stage="radiance", randomized=True, bg_weight=bgw, beta_weight=0.0, use_online_sparsity=False,
+                                      sparsity_weight=0.0, normal_loss_weight=0.0, normal_smooth_weight=0.0,
+                                      bg_smooth_weight=smw, weight_decay_mult=wd, grad_max_val=0.0, grad_max_norm=0.0)
+        import flax.linen as _nn
+        _nn._CTX["key"] = 0
+        model, variables = models.construct_nerf(jax.random.PRNGKey(3), {"rays": utils.namedtuple_map(lambda x: x[None], rays)},
+                                                 args, ndim=ndim, nmin=nmin, nmax=nmax, grid=grid)
+        brs = np.random.RandomState(1234)
+        for mlp in ("coarse_mlp", "fine_mlp", "bkgd_mlp"):
+            for dn in variables["params"][mlp].values():
+                dn["bias"] = jnp.array(brs.uniform(-0.1, 0.1, size=dn["bias"].shape))
+        params = {k: f32(v) for k, v in flatten(variables["params"]).items()}
+        old = np.load(os.path.join(HERE, "ref_params.npz"))
+        assert all(np.array_equal(old[k], params[k]) for k in params), "parameter draw differs from ref_params.npz"
+        # random-init sigma composites to trans ~ 0.3 everywhere, which would leave mask_bg = trans > 0.5 empty: lower the fine
+        # sigma head's bias (recorded) so that the background term sees a mix of rays
+        sig_bias = {"a": -2.2, "b": -2.2, "c": -1.6}[case]
+        variables["params"]["fine_mlp"]["Dense_8"]["bias"] = jnp.array(f32([sig_bias]))
+        out[f"{case}_fine_sigma_bias"] = np.float32(sig_bias)
+        state = types.SimpleNamespace(params=variables, apply_gradients=lambda grads: "new_state")
+        batch = {"rays": rays, "pixels": jnp.array(pixels), "env_rays": env_rays, "annealed_alpha": jnp.array(f32([alpha]))}
+        ns = {"FLAGS": flags, "jax": jax, "jnp": jnp, "random": jax.random, "utils": utils, "math_utils": math_utils}
+        exec(compile(fn_src, "/root/reference/train.py", "exec"), ns)
+        jax.random.DRAWS.clear()
+        new_state, stats, _ = ns["train_step"](model, jax.random.PRNGKey(5), state, batch)
+        assert new_state == "new_state"
+        draws = list(jax.random.DRAWS)
+        out[f"{case}_jitter"] = np.arange(0, 64 * P, P) + np.asarray([v for k, v in draws if k == "randint"][0])
+        out[f"{case}_u_noise"] = f32([v for k, v in draws if k == "uniform"][0])
+        out[f"{case}_cfg"] = np.array([alpha, bgw, smw, wd], dtype=np.float64)
+        out[f"{case}_total"] = f32(captured["total"])
+        for k in ("loss", "psnr", "loss_c", "psnr_c", "weight_l2", "loss_sp", "loss_nrm", "annealing_rate", "loss_bg",
+                  "loss_bg_c", "loss_bg_smooth"):
+            out[f"{case}_{k}"] = f32(getattr(stats, k))
+        print("train loss", case, "total", float(out[f"{case}_total"]), "rays with trans > 0.5:", int(captured.get("n_bg", -1)), {k: float(out[f"{case}_{k}"]) for k in ("loss", "loss_c", "loss_bg", "loss_bg_smooth", "weight_l2")})
+    np.savez_compressed(os.path.join(HERE, "ref_train_loss.npz"), **out)
 
 
 if __name__ == "__main__":
@@ -234,11 +344,12 @@ if __name__ == "__main__":
         os.remove(os.path.join(HERE, "ref_params.npz"))
     run_functions()
     # config A shape (example.gin/yaml): near/far 2/6, P=12, blur 3/1, IoR scale 0.5
-    run_model("example", "example", G=20, extent=1.5, radius=0.8, center=(0, 0, 0), ws=3, sigma=1.0, B=24, seed=3,
-              near=2.0, far=6.0, P=12, ri_scale=0.5)
+    run_model("example", "example", G=20, extent=1.5, radius=0.8, center=(0, 0, 0), ws=3, sigma=1.0, B=1024, seed=3,
+              near=2.0, far=6.0, P=12, ri_scale=0.5, keep_path=24)
     # training-mode sampling (randomized=True): stratified u
-    run_model("example_rand", "example", G=20, extent=1.5, radius=0.8, center=(0, 0, 0), ws=3, sigma=1.0, B=16, seed=4,
+    run_model("example_rand", "example", G=20, extent=1.5, radius=0.8, center=(0, 0, 0), ws=3, sigma=1.0, B=1024, seed=4,
               near=2.0, far=6.0, P=12, ri_scale=0.5, randomized=True)
     # config D shape (ball.gin/yaml): near/far 0.2/12, P=24, blur 5/3, bd_cut_dist passes with the hard-coded ball box
-    run_model("ball", "ball", G=16, extent=2.0, radius=1.0, center=(0, 1.036, 0), ws=5, sigma=3.0, B=16, seed=5,
+    run_model("ball", "ball", G=16, extent=2.0, radius=1.0, center=(0, 1.036, 0), ws=5, sigma=3.0, B=1024, seed=5,
               near=0.2, far=12.0, P=24, ri_scale=0.5, bd_cut_dist=6.0, shift=(0, 1.0, 0))
+    run_train_loss()

@@ -416,3 +416,51 @@ def test_grid_points_dataset(cuda_lib):
         tb2 = {k: v for k, v in tb.items() if k not in ("pts", "grads")}
         total2, _ = train.loss_fn(model, variables, tb2, args, 1, 2)
     assert float(stats["loss_nrm"]) == 0.0 and abs(float(total) - float(total2)) < 1e-6
+
+
+def test_graph_replay_follows_annealed_alpha(cuda_lib):
+    """The annealing schedule changes annealed_alpha every step after anneal_delay_steps (train.py:350-351), and with it
+    the so3 positional-encoding window.  A replayed CUDA graph must use THIS step's window (the kernels read it from a
+    device buffer refreshed before each replay), not the capture-time one: replay at alpha_2 == eager at alpha_2, and
+    != what the capture-time window alpha_1 gives."""
+    from samplenerfro_b200 import train, utils
+    model, variables, args, _, o, d, env, pixels, gen = _setup_all(B=128)
+    args.lr_delay_steps = 0
+    B = o.shape[0]
+    state = train.TrainState.create(variables, args)
+
+    def batch_at(alpha):
+        return {"rays": utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(B, 1).cuda()), "pixels": pixels.cuda(),
+                "env_rays": utils.Rays(env.cuda(), env.cuda(), env.cuda(), env.cuda()[..., :1]), "annealed_alpha": alpha}
+
+    a1, a2 = 0.25, 0.85
+    assert model.so3_window(a1) != model.so3_window(a2)
+    rng = 0
+    state.step = 10
+    for _ in range(3):                                  # 2 eager steps, then capture + first replay, all at alpha_1
+        state, stats, rng = train.train_step(model, rng, state, batch_at(a1), args)
+    assert any(isinstance(v, train._GraphedStep) for v in state.graphs.values())
+    n_graphs = len(state.graphs)
+    snap = (state.arena.theta.clone(), state.opt.mu.clone(), state.opt.nu.clone(), state.opt.count, state.step, rng)
+
+    def restore():
+        state.arena.theta.copy_(snap[0]); state.opt.mu.copy_(snap[1]); state.opt.nu.copy_(snap[2])
+        state.opt.count, state.step = snap[3], snap[4]
+        model._pack_cache.clear()
+
+    lo, hi = state.arena.bucket_range["path_sampler"]
+    state, st_replay, _ = train.train_step(model, snap[5], state, batch_at(a2), args)       # replay at alpha_2
+    assert len(state.graphs) == n_graphs, "a new alpha must not re-capture"
+    g_replay = state.arena.grad[lo:hi].clone()
+    restore()
+    state, st_eager, _ = train.train_step(model, snap[5], state, batch_at(a2), args, use_graph=False)
+    g_eager = state.arena.grad[lo:hi].clone()
+    restore()
+    state, st_old, _ = train.train_step(model, snap[5], state, batch_at(a1), args, use_graph=False)
+    g_old = state.arena.grad[lo:hi].clone()
+    rel = ((g_replay - g_eager).norm() / g_eager.norm()).item()
+    rel_old = ((g_replay - g_old).norm() / g_old.norm()).item()
+    print(f"so3 gradient: replay(alpha2) vs eager(alpha2) {rel:.2e}; vs eager(alpha1) {rel_old:.2e}")
+    assert rel < 1e-3, rel
+    assert rel_old > 10 * max(rel, 1e-6), (rel, rel_old)
+    assert abs(float(st_replay["loss"]) - float(st_eager["loss"])) <= 1e-5 * max(1.0, abs(float(st_eager["loss"])))

@@ -87,6 +87,42 @@ def test_render_image_chunks_and_padding(cuda_lib, example_scene):
     assert H.psnr(rgb_c, rgb_a) > 60.0 and (acc_c - acc_a).abs().max() < 2e-3
 
 
+def test_render_image_debug_variant(cuda_lib, example_scene):
+    """The reference's commented debug variant (rnerf/utils.py:371-389, consumer extract_mesh.py:178): render_image returns
+    the 8-tuple (rgb, distance, acc, ray_pos, ray_dir, idx_grad, trans, ray_pos_c) with the bent FINE samples and the coarse
+    sample positions -- the "per-ray sample positions out" of the render-level API -- checked against the oracle."""
+    from samplenerfro_b200 import models, utils
+    n, ndim, nmin, nmax = example_scene
+    model, variables = models.construct_nerf(3, None, _flags(), ndim, nmin, nmax, n)
+    Hh, Ww = 12, 10
+    rays = H.camera_rays(Hh, Ww, seed=5)
+    jitter = model.draw_jitter(utils._split_key(0)[0])
+    fn = lambda k0, k1, r: model.apply(variables, k0, k1, r, False, debug=True)
+    out = utils.render_image(fn, utils.namedtuple_map(lambda r: r.cuda(), rays), 0, False, chunk=50, debug=True)
+    assert len(out) == 8
+    rgb, dist, acc, ray_pos, ray_dir, idx_grad, trans, ray_pos_c = [x.cpu() for x in out]
+    assert ray_pos.shape == (Hh, Ww, 192, 3) and ray_dir.shape == (Hh, Ww, 192, 3) and idx_grad.shape == (Hh, Ww, 192, 3)
+    assert trans.shape == (Hh, Ww, 1) and ray_pos_c.shape == (Hh, Ww, 64, 3) and rgb.shape == (Hh, Ww, 3)
+    plain = utils.render_image(lambda k0, k1, r: model.apply(variables, k0, k1, r, False),
+                               utils.namedtuple_map(lambda r: r.cuda(), rays), 0, False, chunk=50)
+    assert len(plain) == 3 and H.psnr(plain[0], rgb) > 60.0
+    flat = utils.namedtuple_map(lambda r: r.reshape(-1, r.shape[-1]), rays)
+    cfg = O.ModelCfg(ndim=ndim, nmin=nmin, nmax=nmax, cfg_name="example")
+    oret, _, odbg = O.nerf_model_apply(_oracle_vars(variables), O.build_table(n, ndim, nmin, nmax), cfg, O.Rays(*flat),
+                                       jitter.cpu().long(), O.deterministic_u(128), debug=True)
+    assert torch.equal(ray_pos_c.reshape(-1, 64, 3), odbg["ray_pos_c"])                    # coarse samples: bit-exact
+    # fine samples sit where the bf16 coarse pass put its weights: same tolerance as the resampling tests
+    assert (ray_pos.reshape(-1, 192, 3) - odbg["pos_f"]).abs().max() < 5e-3
+    close = (ray_pos.reshape(-1, 192, 3) - odbg["pos_f"]).abs().amax(-1) < 1e-4
+    assert close.float().mean() > 0.9
+    assert ((idx_grad.reshape(-1, 192, 3) - odbg["grad_f"]).abs().amax(-1)[close] < 1e-5).all()
+    assert ((ray_dir.reshape(-1, 192, 3) - odbg["dir_f"]).abs().amax(-1)[close] < 1e-5).all()
+    assert (trans.reshape(-1) - oret[1][3].reshape(-1)).abs().max() < 5e-3
+    with pytest.raises(ValueError):
+        utils.render_image(lambda k0, k1, r: model.apply(variables, k0, k1, r, False),
+                           utils.namedtuple_map(lambda r: r.cuda(), rays), 0, False, chunk=50, debug=True)
+
+
 def test_bd_cut_dist_passes(cuda_lib):
     """ball.gin shape (S=1536, near/far 0.2/12, bd_cut_dist) against the oracle's extra composites (a15)."""
     from samplenerfro_b200 import models, utils

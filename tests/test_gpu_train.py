@@ -236,3 +236,40 @@ def test_graph_replayed_step_equals_eager_step(cuda_lib):
     n_graphs = len(state.graphs)
     state, stats, _ = train.train_step(model, 7, state, batch, args)
     assert len(state.graphs) == n_graphs and state.step == snap[4] + 2 and state.opt.count == snap[3] + 2
+
+
+def test_training_with_online_sparsity_flag(cuda_lib):
+    """use_online_sparsity=True is the reference's flag default (rnerf/utils.py define_flags): the coarse composite must
+    hand out alpha under autograd too (rnerf/models.py:351-357), loss_sp is finite, and the step trains.  Its weight in the
+    loss is annealing_rate = 0 (train.py:156), so gradients equal the use_online_sparsity=False ones."""
+    from samplenerfro_b200 import models, train, utils
+    model0, variables0, args0, (n, ndim, nmin, nmax), o, d, env, pixels, gen = _setup(B=64)
+    args = utils.Flags(config="example", num_path_samples=12, white_bkgd=False, use_online_sparsity=True, use_fine_sparsity=True,
+                       bg_weight=0.025, bg_smooth_weight=1.0, bg_patch_size=8, randomized=True, max_steps=200000)
+    model, variables = models.construct_nerf(3, None, args, ndim, nmin, nmax, n)
+    for name in ("coarse_mlp", "fine_mlp", "bkgd_mlp"):
+        for k, dd in variables["params"][name].items():
+            dd["bias"].copy_(variables0["params"][name][k]["bias"])
+    B = o.shape[0]
+    batch = {"rays": utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(B, 1).cuda()), "pixels": pixels.cuda(),
+             "env_rays": utils.Rays(env.cuda(), env.cuda(), env.cuda(), env.cuda()[..., :1]), "annealed_alpha": 0.5}
+    jitter = model.draw_jitter(5)
+    u = O.stratified_u(torch.rand(B, 128, generator=gen) * (1 / 128 - float(np.finfo(np.float32).eps))).cuda()
+    grads = []
+    for m, v, a in ((model, variables, args), (model0, variables0, args0)):
+        for leaf in train.tree_leaves(v["params"]):
+            leaf.requires_grad_(True)
+        rays = batch["rays"]
+        ret, loss_sp = m.apply(v, 1, 2, rays, True, 0.5, jitter=jitter, u=u)
+        assert torch.isfinite(loss_sp).all()
+        total, _ = train.loss_fn(m, v, batch, a, 1, 2, jitter=jitter, u=u)
+        total.backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for name in train.GRAD_BUCKETS for p in train.tree_leaves(v["params"][name])]))
+    assert float(loss_sp) == 0.0 and model.use_online_sparsity        # (model0: flag off -> exactly zero)
+    rel = ((grads[0] - grads[1]).norm() / grads[1].norm()).item()
+    assert rel < 1e-3, rel
+    state = train.TrainState.create(variables, args)
+    rng = 0
+    for _ in range(4):                      # eager, eager, capture + replay, replay
+        state, stats, rng = train.train_step(model, rng, state, batch, args)
+    assert np.isfinite(float(stats["loss"]))

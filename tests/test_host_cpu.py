@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rnerf_abi_version() == 5
+    assert lib.rnerf_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define RNERF_ABI_VERSION (\d+)", header).group(1))
     assert lib.rnerf_encmlp_packed_bytes() > 1_000_000 and lib.rnerf_bkgd_weight_floats() == 56448 + 515
 
 
@@ -42,19 +42,19 @@ def test_abi_argument_validation_without_gpu():
     # entries of the "all"-stage training path
     P = C.c_void_p(16)
     win = (C.c_double * 10)(*([1.0] * 10))
-    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 1, P, 2, P, P, P, P, win, P, None, None, None, None)
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 1, P, 2, P, P, P, P, win, None, P, None, None, None, None)
     assert rc == -2 and b"n_steps" in lib.rnerf_last_error()
-    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 10, 4, 2.0, 6.0, 96, P, 8, P, P, P, P, win, P, None, None, None, None)
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 10, 4, 2.0, 6.0, 96, P, 8, P, P, P, P, win, None, P, None, None, None, None)
     assert rc == -2 and b"rec_floats" in lib.rnerf_last_error()
-    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, P, None, win, P, None, None, None, None)
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, P, None, win, None, P, None, None, None, None)
     assert rc == -1 and b"so3_wt" in lib.rnerf_last_error()            # so3_w given without its transposed image
-    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, C.c_void_p(20), P, win, P, None, None, None, None)
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, C.c_void_p(20), P, win, None, P, None, None, None, None)
     assert rc == -3                                                       # misaligned weight image
     assert lib.rnerf_march_all_bwd(P, None, nd, lo, hi, None, 8, 0, 2.0, 6.0, 96, None, 8, None, None, None, None, None, None,
-                                   None, None, None, None) == 0           # no rays: a no-op
+                                   None, None, None, None, None) == 0           # no rays: a no-op
     assert lib.rnerf_mlp_input_grad(None, 0, None, None, None, None, None, None) == 0
     assert lib.rnerf_mlp_input_grad(None, 5, None, None, None, None, None, None) == -1
-    assert lib.rnerf_so3_predict(None, win, P, P, 3, P, None) == -1
+    assert lib.rnerf_so3_predict(None, win, None, P, P, 3, P, None) == -1
     assert lib.rnerf_grid_table_bwd(P, _lib.Int3(1, 4, 4), lo, hi, P, None) == -2
     assert lib.rnerf_bkgd_mlp_bwd_dirs(P, P, 4, 3, P, P, None, None) == -1
     assert lib.rnerf_so3_transposed_floats() == 2 * 128 * 60 + 3 * 128 * 128

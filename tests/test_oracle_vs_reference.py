@@ -130,11 +130,18 @@ def test_full_model_apply(name):
                      num_path_samples=int(d["num_path_samples"]), bd_cut_dist=None if bd < 0 else bd, cfg_name=str(d["config"]))
     o, v = T(d["origins"]), T(d["viewdirs"])
     S = 64 * cfg.num_path_samples
-    # 1. the bent path: bit-exact against the reference's scan
+    # 1. the bent path: bit-exact against the reference's scan -- the stored rays element by element, ALL 1024 rays through
+    # the SHA-256 digests of the reference's arrays
+    import hashlib
+    assert o.shape[0] >= 1024
     pos, dirs, dist, n, g = O.march(table, ndim, nmin, nmax, o, v, cfg.near, cfg.far, S)
+    kp = d["path_pos"].shape[0]
     for nm, a, b in (("ray_pos", pos, d["path_pos"]), ("ray_dir", dirs, d["path_dir"]), ("ray_dist", dist, d["path_dist"]),
                      ("idx_data", n, d["path_n"]), ("idx_grad", g, d["path_grad"])):
-        assert np.array_equal(a.numpy(), b), f"{name}: {nm} differs, max {np.abs(a.numpy() - b).max():.3e}"
+        assert np.array_equal(a.numpy()[:kp], b), f"{name}: {nm} differs, max {np.abs(a.numpy()[:kp] - b).max():.3e}"
+    for key, a in (("pos", pos), ("dir", dirs), ("dist", dist), ("n", n), ("grad", g)):
+        got = hashlib.sha256(np.ascontiguousarray(a.numpy(), dtype=np.float32).tobytes()).hexdigest()
+        assert got == str(d[f"path_{key}_sha256"]), f"{name}: path_{key} digest over all {o.shape[0]} rays differs"
     # 2. full forward with the recorded stochastic draws
     u = O.stratified_u(T(d["u_noise"])) if "u_noise" in d.files else O.deterministic_u(128)
     ret, loss_sp = O.nerf_model_apply(variables, table, cfg, O.Rays(o, v, v, torch.ones(o.shape[0], 1)),
@@ -145,3 +152,62 @@ def test_full_model_apply(name):
             tol = 2e-4 if nm == "distance" else 3e-5        # fp32 matmul summation order (MKL vs numpy) through 12 layers
             close(val, ref, tol, f"{name}: ret[{lvl}].{nm}")
     assert float(loss_sp) == float(d["loss_sp"]) == 0.0
+
+
+def test_mip_helpers_for_curved_rays(fn):
+    """Row a18 (dead code on the live path): the oracle's cast_rays / lift_gaussian / conical_frustum /
+    cylinder / integrated_pos_enc / expected_sin against rnerf/mip.py executed under the shim, on the inputs the commented
+    call sites rnerf/models.py:249-254 would pass (bent positions, per-sample directions, t fence posts)."""
+    tv, mo, md, mr = [T(fn[k]) for k in ("mip_t_vals", "mip_origins", "mip_dirs", "mip_radii")]
+    near = float(fn["mip_near"])
+    for shape in ("cone", "cylinder"):
+        mean, cov = O.cast_rays(tv, mo, md, mr, shape, near)
+        close(mean, fn[f"mip_{shape}_mean"], 2e-6, f"{shape} mean")
+        assert np.abs(cov.numpy() - fn[f"mip_{shape}_cov"]).max() <= 1e-6 * np.abs(fn[f"mip_{shape}_cov"]).max() + 1e-12
+        # IPE through the REFERENCE's (mean, cov): octave 9 multiplies the argument error by 512 -> 1e-4 on sin()
+        close(O.integrated_pos_enc(T(fn[f"mip_{shape}_mean"]), T(fn[f"mip_{shape}_cov"]), 0, 10), fn[f"mip_{shape}_ipe"],
+              1e-4, f"{shape} ipe")
+        assert fn[f"mip_{shape}_ipe"].shape == (7, 24, 60)
+    # the mean follows the BENT ray: cumulative sum of d * dt from origins[:, 0], not origin + d * t
+    mean, _ = O.cast_rays(tv, mo, md, mr, "cone", near)
+    straight = mo[:, 0:1] + md[:, 0:1] * (0.5 * (tv[:, :-1] + tv[:, 1:]) - near)[..., None]
+    assert (mean - straight)[:, 5:].abs().max() > 0.1
+    y, yv = O.expected_sin(T(fn["mip_es_x"]), T(fn["mip_es_var"]))
+    close(y, fn["mip_es_y"], 2e-5, "expected_sin mean (|x| up to 400 > 100 pi: the safe_sin wrap is exercised)")
+    close(yv, fn["mip_es_yvar"], 2e-5, "expected_sin var")
+    # full-covariance branch (unpinned: the reference's non-diag lift_gaussian is shape-inconsistent for per-sample
+    # directions): its diagonal must equal the diag=True result
+    m2, c2 = O.cast_rays(tv, mo, md, mr, "cone", near, diag=False)
+    _, c1 = O.cast_rays(tv, mo, md, mr, "cone", near, diag=True)
+    assert torch.allclose(torch.diagonal(c2, dim1=-2, dim2=-1), c1, rtol=1e-5, atol=1e-12) and torch.equal(m2, mean)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_train_loss_vs_reference_train_step(case):
+    """oracle.train_loss against the forward of the reference's own `train_step` (train.py:58-183, its unmodified source
+    executed under the shim; tests/golden/ref_train_loss.npz): total and every stats entry, for (a) the shipped synthetic
+    weights bg_weight 0.025 / bg_smooth 1.0, (b) annealed_alpha = 0 (both background terms gated off, train.py:92,130) and
+    (c) other weights + weight decay."""
+    d = np.load(os.path.join(G, "ref_train_loss.npz"))
+    _, variables = _load_model("example")
+    variables["params"]["fine_mlp"]["Dense_8"]["bias"] = torch.tensor([float(d[f"{case}_fine_sigma_bias"])])
+    ndim, nmin, nmax = d["ndim"].tolist(), d["nmin"].tolist(), d["nmax"].tolist()
+    table = O.build_table(T(d["grid"]), ndim, nmin, nmax)
+    cfg = O.ModelCfg(ndim=ndim, nmin=nmin, nmax=nmax, num_path_samples=int(d["num_path_samples"]), cfg_name="example")
+    o, v = T(d["origins"]), T(d["viewdirs"])
+    alpha, bgw, smw, wd = [float(x) for x in d[f"{case}_cfg"]]
+    total, stats = O.train_loss(variables, table, cfg, O.Rays(o, v, v, torch.ones(o.shape[0], 1)), T(d["pixels"]),
+                                T(d["env_viewdirs"]), torch.from_numpy(d[f"{case}_jitter"]).long(),
+                                O.stratified_u(T(d[f"{case}_u_noise"])), alpha, bg_weight=bgw, bg_smooth_weight=smw,
+                                weight_decay_mult=wd)
+    rel = lambda a, b: abs(float(a) - float(b)) / max(abs(float(b)), 1e-6)
+    assert rel(total, d[f"{case}_total"]) < 1e-4, (float(total), float(d[f"{case}_total"]))
+    for k in ("loss", "psnr", "loss_c", "psnr_c", "weight_l2", "loss_bg", "loss_bg_smooth"):
+        assert rel(stats[k], d[f"{case}_{k}"]) < 1e-4 or abs(float(stats[k]) - float(d[f"{case}_{k}"])) < 1e-7, (k, float(stats[k]), float(d[f"{case}_{k}"]))
+    # train.py:156: annealing_rate = 0 -> these are exactly zero in the reference's stats
+    assert float(d[f"{case}_loss_sp"]) == 0.0 and float(d[f"{case}_loss_nrm"]) == 0.0 and float(d[f"{case}_loss_bg_c"]) == 0.0
+    assert float(d[f"{case}_annealing_rate"]) == np.float32(alpha)
+    if alpha > 0:
+        assert float(d[f"{case}_loss_bg"]) > 0 and float(d[f"{case}_loss_bg_smooth"]) > 0
+    else:
+        assert float(d[f"{case}_loss_bg"]) == 0.0 and float(d[f"{case}_loss_bg_smooth"]) == 0.0
