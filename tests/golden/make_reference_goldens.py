@@ -9,6 +9,7 @@ against these files.  The shim reproduces jax/flax *semantics* (32-bit types, Fl
 .at[].set, lax.fori_loop, the positional-argument quirk of jnp.nan_to_num); random draws are recorded and stored so
 the oracle receives the same jitter / u / noise.
 """
+import dataclasses
 import os
 import sys
 import types
@@ -255,6 +256,86 @@ def run_functions():
     print("functions ok")
 
 
+def run_config_a():
+    """BASELINE.json configs[0] at its stated size: configs/example.{gin,yaml} (read with this repo's
+    own gin-subset / YAML loaders, so the fixture also pins them), the single camera of example_data/transforms_train.json
+    rendered at 100x100 with use_pixel_centers, G = 128, extent 1.5, IoR scale 0.5, blur 3/1; grid = a radius-0.5 sphere
+    voxelised with 4^3 supersampling like voxelize_mesh.py:72-106 (the real mesh.pkl is a missing blob).
+    All 10 000 rays go through the reference's NerfModel.__call__.  -> ref_model_config_a.npz + config_a.json"""
+    import json
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from samplenerfro_b200 import utils as U
+    cfg, gin = U.load_config(["/root/reference/configs/example.gin"])
+    flags = U.Flags(config="/root/reference/configs/example")
+    U.update_flags(flags)
+    meta = json.load(open("/root/reference/example_data/transforms_train.json"))
+    c2w = np.array(meta["frames"][0]["transform_matrix"], dtype=np.float32)
+    Hh = Ww = 100
+    focal = .5 * Ww / np.tan(.5 * float(meta["camera_angle_x"]))                                   # rnerf/datasets.py:355-356
+    pc = 0.5 if flags.use_pixel_centers else 0.0
+    x, y = np.meshgrid(np.arange(Ww, dtype=np.float32) + pc, np.arange(Hh, dtype=np.float32) + pc, indexing="xy")
+    cam = np.stack([(x - Ww * 0.5) / focal, -(y - Hh * 0.5) / focal, -np.ones_like(x)], axis=-1)  # rnerf/datasets.py:218-230
+    dirs = (cam[..., None, :] * c2w[None, None, :3, :3]).sum(axis=-1)
+    orig = np.broadcast_to(c2w[None, None, :3, -1], dirs.shape)
+    view = dirs / np.linalg.norm(dirs, axis=-1, keepdims=True)
+    o, dr, v = f32(orig.reshape(-1, 3)), f32(dirs.reshape(-1, 3)), f32(view.reshape(-1, 3))
+    G, extent, ss = 128, 1.5, 4
+    lin = np.linspace(-extent, extent, G)
+    dl = lin[1] - lin[0]
+    offs = (np.arange(ss) + 0.5) / ss - 0.5
+    occ = np.zeros((G, G, G))
+    X, Y, Z = np.meshgrid(lin, lin, lin, indexing="ij")
+    for a_ in offs:
+        for b_ in offs:
+            for c_ in offs:
+                occ += ((X + a_ * dl) ** 2 + (Y + b_ * dl) ** 2 + (Z + c_ * dl) ** 2) < 0.5 ** 2
+    data = (1.0 + 0.33 * occ / ss ** 3).reshape(-1, 1)
+    ndim, nmin, nmax = [G] * 3, [-extent] * 3, [extent] * 3
+    grid = ior_utils.conv3d_normal((data - 1.0) * 0.5 / 0.33 + 1.0, ndim, cfg.kernel_size, cfg.kernel_sigma)
+    rays = utils.Rays(origins=jnp.array(o), directions=jnp.array(dr), viewdirs=jnp.array(v), radii=jnp.array(np.ones((Hh * Ww, 1))))
+    args = args_for("example", near=flags.near, far=flags.far, num_path_samples=flags.num_path_samples, randomized=False,
+                    num_coarse_samples=flags.num_coarse_samples, num_fine_samples=flags.num_fine_samples, white_bkgd=flags.white_bkgd)
+    import flax.linen as _nn
+    _nn._CTX["key"] = 0
+    model, variables = models.construct_nerf(jax.random.PRNGKey(0), {"rays": utils.namedtuple_map(lambda t: t[None, :8], rays)},
+                                             args, ndim=ndim, nmin=nmin, nmax=nmax, grid=grid)
+    assert model.use_mask_bbox is False
+    rs = np.random.RandomState(1234)
+    for mlp in ("coarse_mlp", "fine_mlp", "bkgd_mlp"):
+        for dn in variables["params"][mlp].values():
+            dn["bias"] = jnp.array(rs.uniform(-0.1, 0.1, size=dn["bias"].shape))
+    params = {k: f32(val) for k, val in flatten(variables["params"]).items()}
+    old = np.load(os.path.join(HERE, "ref_params.npz"))
+    assert all(np.array_equal(old[k], params[k]) for k in params)
+    jax.random.DRAWS.clear()
+    ret, loss_sp = model.apply(variables, jax.random.PRNGKey(11), jax.random.PRNGKey(12), rays, False)   # eval.py:97
+    P = flags.num_path_samples
+    out = {"grid": f32(grid), "jitter": np.arange(0, 64 * P, P) + np.asarray([val for k, val in jax.random.DRAWS if k == "randint"][0]),
+           "loss_sp": f32(loss_sp)}
+    for lvl, tup in enumerate(ret):
+        for nm, val in zip(("rgb", "distance", "acc", "trans", "trans_rgb_bkgd"), tup):
+            out[f"ret{lvl}_{nm}"] = f32(val)
+    ps = eikonal_utils.PathSampler(near=flags.near, far=flags.far, stage="radiance", num_samples=64 * P,
+                                   step_size=(flags.far - flags.near) / (64 * P - 1), ndim=ndim, nmin=nmin, nmax=nmax, grid=grid)
+    pos, pdirs, dist, idn, idg = ps.apply({"params": variables["params"]["path_sampler"]}, rays.origins, rays.viewdirs, 1.0)
+    import hashlib
+    for nm, arr in (("pos", pos), ("dir", pdirs), ("dist", dist), ("n", idn), ("grad", idg)):
+        out[f"path_{nm}_sha256"] = hashlib.sha256(np.ascontiguousarray(f32(arr)).tobytes()).hexdigest()
+    out["path_pos_last"], out["path_dir_last"] = f32(pos)[:, -1], f32(pdirs)[:, -1]
+    np.savez_compressed(os.path.join(HERE, "ref_model_config_a.npz"), **out)
+    fx = {"source": "configs/example.gin + configs/example.yaml + example_data/transforms_train.json of the reference, parsed by "
+                    "samplenerfro_b200.utils.load_config / update_flags (tests/golden/make_reference_goldens.py:run_config_a)",
+          "flags": {k: val for k, val in flags.__dict__.items() if k != "config"}, "gin": gin,
+          "config": dataclasses.asdict(cfg), "camera_angle_x": float(meta["camera_angle_x"]),
+          "camtoworld": np.asarray(meta["frames"][0]["transform_matrix"], dtype=np.float64).tolist(), "height": Hh, "width": Ww,
+          "grid": {"G": G, "extent": extent, "sphere_radius": 0.5, "supersampling": ss, "ior_scale": 0.5}}
+    with open(os.path.join(HERE, "config_a.json"), "w") as f:
+        json.dump(fx, f, indent=1, sort_keys=True)
+    bend = np.abs(f32(pdirs)[:, -1] - v).max()
+    print("config A: 10000 rays, rgb fine mean", out["ret1_rgb"].mean(), "rays bent:", int((np.abs(f32(pdirs)[:, -1] - v).max(-1) > 1e-3).sum()),
+          "max bend", bend)
+
+
 def run_train_loss():
     """The forward of train.py's loss (train.py:75-162), by executing the UNMODIFIED source text of `train_step`
     (train.py:58-183) -- cut out of the file with `ast`, because importing train.py would run absl flag parsing and pull
@@ -353,3 +434,4 @@ if __name__ == "__main__":
     run_model("ball", "ball", G=16, extent=2.0, radius=1.0, center=(0, 1.036, 0), ws=5, sigma=3.0, B=1024, seed=5,
               near=0.2, far=12.0, P=24, ri_scale=0.5, bd_cut_dist=6.0, shift=(0, 1.0, 0))
     run_train_loss()
+    run_config_a()

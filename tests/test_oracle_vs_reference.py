@@ -211,3 +211,56 @@ def test_train_loss_vs_reference_train_step(case):
         assert float(d[f"{case}_loss_bg"]) > 0 and float(d[f"{case}_loss_bg_smooth"]) > 0
     else:
         assert float(d[f"{case}_loss_bg"]) == 0.0 and float(d[f"{case}_loss_bg_smooth"]) == 0.0
+
+
+def _config_a():
+    import json
+    fx = json.load(open(os.path.join(G, "config_a.json")))
+    d = np.load(os.path.join(G, "ref_model_config_a.npz"))
+    g = fx["grid"]
+    ndim, nmin, nmax = [g["G"]] * 3, [-g["extent"]] * 3, [g["extent"]] * 3
+    focal = 0.5 * fx["width"] / np.tan(0.5 * fx["camera_angle_x"])
+    rays = O.generate_rays(np.asarray(fx["camtoworld"]), fx["height"], fx["width"], focal, fx["flags"]["use_pixel_centers"])
+    flat = O.Rays(*[r.reshape(-1, r.shape[-1]) for r in rays])
+    return fx, d, ndim, nmin, nmax, flat
+
+
+def test_config_a_full_size_vs_reference():
+    """BASELINE.json configs[0] at its stated size: configs/example.{gin,yaml}, the transforms_train.json camera at
+    100x100, G = 128 -- all 10 000 rays of the oracle against the reference's own NerfModel.__call__ (run under the shim)."""
+    import hashlib
+    fx, d, ndim, nmin, nmax, flat = _config_a()
+    fl = fx["flags"]
+    assert (fl["num_coarse_samples"], fl["num_fine_samples"], fl["num_path_samples"], fl["near"], fl["far"]) == (64, 128, 12, 2.0, 6.0)
+    assert fx["config"]["kernel_size"] == 3 and fx["gin"]["NerfModel"]["use_mask_bbox"] is False
+    _, variables = _load_model("example")
+    table = O.build_table(T(d["grid"]), ndim, nmin, nmax)
+    cfg = O.ModelCfg(ndim=ndim, nmin=nmin, nmax=nmax, near=fl["near"], far=fl["far"], num_path_samples=fl["num_path_samples"],
+                     cfg_name="example")
+    S = 64 * cfg.num_path_samples
+    assert flat.origins.shape[0] == 10000
+    with torch.no_grad():
+        ret, _, dbg = O.nerf_model_apply(variables, table, cfg, flat, torch.from_numpy(d["jitter"]).long(), O.deterministic_u(128),
+                                         debug=True)
+    for key, nm in (("pos", "ray_pos"), ("dir", "ray_dir"), ("dist", "ray_dist"), ("n", "idx_data"), ("grad", "idx_grad")):
+        got = hashlib.sha256(np.ascontiguousarray(dbg[nm].numpy(), dtype=np.float32).tobytes()).hexdigest()
+        assert got == str(d[f"path_{key}_sha256"]), f"config A: path_{key} digest over all 10000 rays differs"
+    for lvl in (0, 1):
+        for nm, val in zip(("rgb", "distance", "acc", "trans", "trans_rgb_bkgd"), ret[lvl]):
+            close(val, d[f"ret{lvl}_{nm}"], 3e-4 if nm == "distance" else 5e-5, f"config A: ret[{lvl}].{nm}")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present")
+def test_config_a_fixture_matches_the_reference_files():
+    """config_a.json is what THIS repo's loaders read from the reference's unchanged example.gin / example.yaml /
+    transforms_train.json (the GPU box has no /root/reference, so the GPU test reads the fixture)."""
+    import json
+    from samplenerfro_b200 import utils
+    fx = json.load(open(os.path.join(G, "config_a.json")))
+    cfg, gin = utils.load_config(["/root/reference/configs/example.gin"])
+    flags = utils.Flags(config="/root/reference/configs/example")
+    utils.update_flags(flags)
+    assert {k: v for k, v in flags.__dict__.items() if k != "config"} == fx["flags"]
+    assert gin == fx["gin"] and cfg.kernel_size == fx["config"]["kernel_size"] and cfg.kernel_sigma == fx["config"]["kernel_sigma"]
+    meta = json.load(open("/root/reference/example_data/transforms_train.json"))
+    assert meta["camera_angle_x"] == fx["camera_angle_x"] and meta["frames"][0]["transform_matrix"] == fx["camtoworld"]
