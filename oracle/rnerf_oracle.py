@@ -222,10 +222,27 @@ def _bf16r(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(x.dtype)
 
 
-def dense(p, x, emulate_bf16=False):
+class _RoundGradBf16(torch.autograd.Function):
+    """Identity whose BACKWARD rounds the incoming gradient to bf16: the CUDA dgrad chain stores every layer's dZ as bf16
+    (csrc/mlp_bwd.cu), and both the next dgrad GEMM and the weight / bias gradients read that rounded dZ."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16r(g)
+
+
+def dense(p, x, emulate_bf16=False, round_dy=False):
+    """y = x @ K + b.  emulate_bf16: operands rounded to bf16, fp32 accumulate (what the tcgen05 kernels compute; autograd
+    then yields dX = dY bf16(K)^T and dK = bf16(x)^T dY).  round_dy (emulate_bf16 == "full", MMA layers only): dY is rounded
+    to bf16 before it is used, like the kernels' stored dZ -- a bf16-emulating BACKWARD for tight gradient tolerances."""
     k, b = p["kernel"], p["bias"]
     if emulate_bf16:
-        return _bf16r(x) @ _bf16r(k) + b
+        y = _bf16r(x) @ _bf16r(k) + b
+        return _RoundGradBf16.apply(y) if round_dy else y
     return x @ k + b
 
 
@@ -237,19 +254,20 @@ def nerf_mlp(params: Dict, x: torch.Tensor, condition: Optional[torch.Tensor], n
     inputs = x
     layers = []
     li = 0
+    rd = emulate_bf16 == "full"       # the two skinny heads (Dense_8, Dense_11) take the fp32 d_raw: no rounding there
     for i in range(net_depth):
-        x = torch.relu(dense(params[f"Dense_{li}"], x, emulate_bf16)); li += 1
+        x = torch.relu(dense(params[f"Dense_{li}"], x, emulate_bf16, rd)); li += 1
         layers.append(x)
         if i % skip_layer == 0 and i > 0:
             x = torch.cat([x, inputs], dim=-1)
     raw_sigma = dense(params[f"Dense_{li}"], x, emulate_bf16).reshape(-1, num_samples, 1); li += 1
     if condition is not None:
-        bottleneck = dense(params[f"Dense_{li}"], x, emulate_bf16); li += 1
+        bottleneck = dense(params[f"Dense_{li}"], x, emulate_bf16, rd); li += 1
         layers.append(bottleneck)
         condition = condition.reshape(-1, condition.shape[-1])
         x = torch.cat([bottleneck, condition], dim=-1)
         for i in range(net_depth_condition):
-            x = torch.relu(dense(params[f"Dense_{li}"], x, emulate_bf16)); li += 1
+            x = torch.relu(dense(params[f"Dense_{li}"], x, emulate_bf16, rd)); li += 1
             layers.append(x)
     raw_rgb = dense(params[f"Dense_{li}"], x, emulate_bf16).reshape(-1, num_samples, 3)
     if return_layers:

@@ -1,6 +1,13 @@
 """Flax-compatible checkpoints: `checkpoint_<step>` files holding the msgpack
 serialisation `flax.serialization.to_bytes` produces, with the reference's tree names, so that weights trained by the
-reference render through this path and vice versa (train.py:322,424-427; eval.py:124-152).
+reference render through this path (train.py:322,424-427; eval.py:124-152).
+
+Interoperability is in the PARAMETER direction: files written by the reference are read here (parameters + step), and
+files written here can be read by the reference wherever it restores with target=None and picks sub-trees
+(`checkpoints.restore_checkpoint(dir, None)["params"]["params"][...]`, eval.py:124-152, train.py:286-310).  The
+reference's `restore_checkpoint(stage_dir, state)` (train.py:322) runs `from_state_dict` against its
+optax.multi_transform state and would reject the "arena_adam" optimiser state stored here: resuming THIS library's
+training run inside the reference's train.py is not supported (and vice versa the reference's optimiser state is skipped).
 
 Wire format (flax/serialization.py): a msgpack map; every ndarray is ExtType(1, packb((shape, dtype.name, bytes)));
 numpy scalars are ExtType(3, same tuple).  The reference's state dict is
@@ -136,6 +143,14 @@ def restore_checkpoint(ckpt_dir_or_file: str, target=None, prefix: str = PREFIX)
     target.step = int(loaded["step"])
     adam = loaded.get("opt_state", {}).get("arena_adam") if isinstance(loaded.get("opt_state"), dict) else None
     if adam is not None and getattr(target, "opt", None) is not None:
+        n_file, n_here = int(np.asarray(adam["mu"]).size), int(target.opt.mu.numel())
+        if n_file != n_here:
+            # the moments cover the TRAINABLE buckets of the stage that wrote the file (radiance: 3 MLPs; "all": + so3_mlp);
+            # restoring into another stage keeps the parameters and starts the optimiser fresh, like the reference does when
+            # it loads radiance weights into the "all" stage by sub-tree (train.py:286-330 / eval.py:124-152)
+            import warnings
+            warnings.warn(f"checkpoint Adam moments cover {n_file} values, this stage trains {n_here}: optimiser state not restored")
+            return target
         with torch.no_grad():
             target.opt.mu.copy_(torch.from_numpy(adam["mu"]).to(target.opt.mu.device))
             target.opt.nu.copy_(torch.from_numpy(adam["nu"]).to(target.opt.nu.device))

@@ -172,6 +172,7 @@ class ArenaAdam:
         self.count = 0                               # optax's own step counter (bias correction)
         self.wd_coef = 2.0 * float(args.weight_decay_mult) / arena.numel
         self.grad_max_val, self.grad_max_norm = float(args.grad_max_val), float(args.grad_max_norm)
+        self._zero_frozen = None
 
     def stage_hyper(self, lr: float) -> None:
         """Host -> device copy of this step's scalars (outside any captured graph)."""
@@ -186,6 +187,13 @@ class ArenaAdam:
         if self.grad_max_norm > 0:
             self.norm_sq.zero_()
             norm = ops.grad_sumsq(self.arena.grad, self.arena.theta, self.hyper, self.norm_sq)
+            # train.py:176-180 takes the norm over the WHOLE grads tree, before optax.set_to_zero() discards the frozen
+            # subtrees: those leaves still carry the (value-clipped) weight-decay gradient 2 wd / numel * theta
+            n_frozen = self.arena.theta.numel() - self.arena.n_train
+            if self.wd_coef != 0.0 and n_frozen > 0:
+                if self._zero_frozen is None:
+                    self._zero_frozen = torch.zeros(n_frozen, device=self.arena.theta.device, dtype=torch.float32)
+                ops.grad_sumsq(self._zero_frozen, self.arena.theta[self.arena.n_train:], self.hyper, self.norm_sq)
         ops.adam_step(self.arena.theta, self.arena.grad, self.mu, self.nu, self.hyper, norm)
 
     def step(self, lr: float) -> None:

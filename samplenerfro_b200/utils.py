@@ -198,7 +198,11 @@ def learning_rate_decay(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr
 
 
 def shard_range(n: int, rank: int, world_size: int):
-    """Contiguous ray range of `rank` (reference: shard() reshapes to [n_dev, B/n_dev, ...], rnerf/utils.py:531-534)."""
+    """Contiguous ray range of `rank` (reference: shard() reshapes to [n_dev, B/n_dev, ...], rnerf/utils.py:531-534).
+    Like the reference (train.py:196: "Batch size must be divisible by the number of devices") a remainder is an error,
+    not silently dropped rays."""
+    if n % world_size != 0:
+        raise ValueError(f"batch size {n} must be divisible by the number of devices {world_size}")
     per = n // world_size
     return rank * per, (rank + 1) * per
 

@@ -7,9 +7,29 @@ def stop_gradient(x):
 
 
 def fori_loop(lo, hi, body, val):
-    for i in range(int(lo), int(hi)):
-        val = body(i, val)
+    """The carry is copied once on entry and is then exclusively owned by the loop, so `.at[].set` inside the body may
+    update it in place (same values as JAX's functional update; without this a 10 000-ray sample_pdf loop copies its
+    [B,192,9] carry 30 000 times)."""
+    import jax as _jax
+    val = _jax.tree_map(lambda a: _np.array(a, copy=True).view(jnp.ndarray) if isinstance(a, _np.ndarray) else a, val)
+    jnp._LOOP_OWNED.append({id(a) for a in ([val] if isinstance(val, _np.ndarray) else list(_leaves(val))) if isinstance(a, _np.ndarray)})
+    try:
+        for i in range(int(lo), int(hi)):
+            val = body(i, val)
+    finally:
+        jnp._LOOP_OWNED.pop()
     return val
+
+
+def _leaves(tree):
+    if isinstance(tree, dict):
+        for v in tree.values():
+            yield from _leaves(v)
+    elif isinstance(tree, (list, tuple)):
+        for v in tree:
+            yield from _leaves(v)
+    else:
+        yield tree
 
 
 class Precision:

@@ -17,11 +17,17 @@ class _At:
         return _AtIdx(self.arr, idx)
 
 
+_LOOP_OWNED = []      # stack of id-sets of arrays owned by the running lax.fori_loop (see lax.fori_loop)
+
+
 class _AtIdx:
     def __init__(self, arr, idx):
         self.arr, self.idx = arr, idx
 
     def set(self, v):
+        if _LOOP_OWNED and id(self.arr) in _LOOP_OWNED[-1]:      # carry of a lax.fori_loop: exclusively owned, update in place
+            self.arr[self.idx] = v
+            return self.arr
         out = _np.array(self.arr, copy=True).view(ndarray)
         out[self.idx] = v
         return out

@@ -271,7 +271,9 @@ def run_config_a():
     meta = json.load(open("/root/reference/example_data/transforms_train.json"))
     c2w = np.array(meta["frames"][0]["transform_matrix"], dtype=np.float32)
     Hh = Ww = 100
-    focal = .5 * Ww / np.tan(.5 * float(meta["camera_angle_x"]))                                   # rnerf/datasets.py:355-356
+    # rnerf/datasets.py:355-356.  A Python float on purpose: the reference's pinned NumPy 1.x keeps `float32 array /
+    # np.float64 scalar` in float32 (value-based casting), NumPy 2 would promote the whole ray computation to float64
+    focal = float(.5 * Ww / np.tan(.5 * float(meta["camera_angle_x"])))
     pc = 0.5 if flags.use_pixel_centers else 0.0
     x, y = np.meshgrid(np.arange(Ww, dtype=np.float32) + pc, np.arange(Hh, dtype=np.float32) + pc, indexing="xy")
     cam = np.stack([(x - Ww * 0.5) / focal, -(y - Hh * 0.5) / focal, -np.ones_like(x)], axis=-1)  # rnerf/datasets.py:218-230

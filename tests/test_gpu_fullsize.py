@@ -84,3 +84,64 @@ def test_full_size_march_sortedness_and_oracle_on_a_subset(ship):
     assert torch.equal(path.rec[pick][..., 3].cpu(), odist)
     assert torch.equal(ops.path_dirs(path.rec[pick].contiguous()).cpu(), odir)
     assert torch.equal(path.rec[pick][..., 7].cpu(), on[..., 0])
+
+
+def test_config_d_ball_full_size_properties(cuda_lib):
+    """BASELINE.json configs[3] at FULL size: ball.gin / ball.yaml shape -- 1008x756 OpenCV camera (762 048 rays), S = 1536
+    (P = 24), near/far 0.2/12, G = 256 extent 2, blur 5/3, bd_cut_dist = 6 with the hard-coded ball box
+    (rnerf/models.py:489-491) -- through size-independent properties, plus the oracle on a subset of rays that cross the ball.
+    Also the row-band decomposition used to shard this frame over 8 GPUs: 8 bands rendered one after the other on this GPU
+    (each from rays generated for its band only) reproduce the frame bit for bit."""
+    from samplenerfro_b200 import models, ops, synthetic, utils
+    G = 256
+    ndim, nmin, nmax = [G] * 3, [-2.0] * 3, [2.0] * 3
+    data = synthetic.ellipsoid_occupancy(G, 2.0, (1.0, 1.0, 1.0), center=(0.0, 1.036, 0.0), ss=4)
+    n = ops.grid_blur(synthetic.rescale_ior(data, "ball"), ndim, 5, 3.0)
+    flags = utils.Flags(config="ball", num_path_samples=24, white_bkgd=False, use_online_sparsity=False, near=0.2, far=12.0)
+    flags.gin_bindings = {"NerfModel": {"use_mask_bbox": False, "bd_cut_dist": 6.0}}
+    model, variables = models.construct_nerf(0, None, flags, ndim, nmin, nmax, n)
+    Hh, Ww, S = 756, 1008, 1536
+    assert model.num_march_steps == S
+    c2w = np.eye(4); c2w[:3, 3] = [0.0, 1.036, -5.0]              # OpenCV camera 5 units in front of the ball (+z forward)
+    K = np.array([[1100.0, 0, Ww / 2], [0, 1100.0, Hh / 2], [0, 0, 1]])
+    rays = utils.generate_rays(c2w, Hh, Ww, cam_mat=K)
+    flat = utils.namedtuple_map(lambda r: r.reshape(-1, r.shape[-1]).contiguous(), rays)
+    B = flat.origins.shape[0]
+    assert B == 762048
+    jitter = model.draw_jitter(3)
+    fn = lambda k0, k1, r: model.apply(variables, k0, k1, r, False, jitter=jitter)
+    with torch.no_grad():
+        chunk = 190512                                                             # a quarter of the frame per call
+        rgb, dist, acc = utils.render_image(fn, rays, 0, False, chunk=chunk)
+        assert rgb.shape == (Hh, Ww, 3) and torch.isfinite(rgb).all() and torch.isfinite(dist).all()
+        assert rgb.min().item() >= -0.0011 and rgb.max().item() <= 1.0011
+        assert (acc >= -1e-6).all() and (acc <= 1 + 1e-5).all()
+        # one quarter again with the full tuple: telescoping sum, bd_cut_dist outputs in range
+        q = utils.namedtuple_map(lambda x: x[chunk:2 * chunk], flat)
+        ret, _ = model.apply(variables, 1, 2, q, False, jitter=jitter)
+        r1, d1, a1, tr1, trb1 = ret[1]
+        r0, d0, a0, tr0, trb0 = ret[0]
+        assert (a0 + tr0[:, 0] - 1).abs().max().item() < 2e-5                    # coarse level: plain composite
+        assert (tr1 >= -1e-6).all() and (tr1 <= 1 + 1e-6).all()                   # masked transmittance (rnerf/models.py:504-513)
+        assert (trb1 >= -0.0011 - 1e-6).all() and (trb1 <= 1.0011 + 1e-6).all()   # trans * (colour behind the box)
+        assert (tr1[:, 0] >= 1 - a1 - 2e-5).all()       # masking samples out can only raise the transmittance above 1 - acc
+        assert torch.equal(rgb.reshape(-1, 3)[chunk:2 * chunk], r1)
+        # 8 row bands, each from its own device-generated rays = the frame (what render_view_sharded does on 8 GPUs)
+        bands = []
+        for rk in range(8):
+            b0, b1, per = utils.band_rows(Hh, rk, 8)
+            o, d, v, rr = ops.generate_rays(c2w, Hh, Ww, cam_mat=K, row0=b0, n_rows=b1 - b0)
+            bands.append(utils.render_image(fn, utils.Rays(o, d, v, rr), 0, False, chunk=chunk)[0])
+        assert torch.equal(torch.cat(bands, dim=0), rgb)
+        # the march at S = 1536: sortedness, start value, oracle rows on rays that cross the ball
+        sub = utils.namedtuple_map(lambda x: x[::37].contiguous(), flat)
+        path = ops.march(model.table, ndim, nmin, nmax, sub.origins, sub.viewdirs, 0.2, 12.0, S, bricks=model.bricks, compact=True)
+        t = path.t
+        assert (t[:, 1:] > t[:, :-1]).all() and (t[:, 0] == np.float32(0.2)).all()
+        bent = ((path.rec[:, -1, 4:7] - sub.viewdirs).norm(dim=-1) > 1e-2).nonzero()[:, 0]
+        assert bent.numel() > 500
+        pick = bent[torch.linspace(0, bent.numel() - 1, 12).long()]
+        opos, odir, odist, on, og = O.march(model.table.cpu(), ndim, nmin, nmax, sub.origins[pick].cpu(), sub.viewdirs[pick].cpu(),
+                                            0.2, 12.0, S)
+        assert torch.equal(path.rec[pick][..., 0:3].cpu(), opos) and torch.equal(path.rec[pick][..., 3].cpu(), odist)
+        assert torch.equal(ops.path_dirs(path.rec[pick].contiguous()).cpu(), odir)

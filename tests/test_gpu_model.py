@@ -111,13 +111,17 @@ def test_render_image_debug_variant(cuda_lib, example_scene):
     oret, _, odbg = O.nerf_model_apply(_oracle_vars(variables), O.build_table(n, ndim, nmin, nmax), cfg, O.Rays(*flat),
                                        jitter.cpu().long(), O.deterministic_u(128), debug=True)
     assert torch.equal(ray_pos_c.reshape(-1, 64, 3), odbg["ray_pos_c"])                    # coarse samples: bit-exact
-    # fine samples sit where the bf16 coarse pass put its weights: same tolerance as the resampling tests
-    assert (ray_pos.reshape(-1, 192, 3) - odbg["pos_f"]).abs().max() < 5e-3
-    close = (ray_pos.reshape(-1, 192, 3) - odbg["pos_f"]).abs().amax(-1) < 1e-4
-    assert close.float().mean() > 0.9
-    assert ((idx_grad.reshape(-1, 192, 3) - odbg["grad_f"]).abs().amax(-1)[close] < 1e-5).all()
-    assert ((ray_dir.reshape(-1, 192, 3) - odbg["dir_f"]).abs().amax(-1)[close] < 1e-5).all()
-    assert (trans.reshape(-1) - oret[1][3].reshape(-1)).abs().max() < 5e-3
+    # the fine samples sit where the coarse pass put its weights (bf16 MLP here, fp32 in the oracle), so they are compared
+    # through the oracle's sample_pdf fed with THIS path's coarse weights: same tolerance as the resampling tests
+    _, _, dbg = model.apply(variables, *utils._split_key(0), utils.namedtuple_map(lambda r: r.cuda(), flat), False, debug=True)
+    t_c, w_c = dbg["t_c"].cpu(), dbg["weights_c"].cpu()
+    t_f, pos_f, dir_f, grad_f = O.sample_pdf(0.5 * (t_c[:, 1:] + t_c[:, :-1]), w_c[:, 1:-1], odbg["ray_pos"], odbg["ray_dir"],
+                                             odbg["ray_dist"], odbg["idx_grad"], O.deterministic_u(128), jitter.cpu().long())
+    assert (ray_pos.reshape(-1, 192, 3) - pos_f).abs().max() < 1e-4
+    assert (ray_dir.reshape(-1, 192, 3) - dir_f).abs().max() < 1e-4
+    assert (idx_grad.reshape(-1, 192, 3) - grad_f).abs().max() < 1e-4
+    assert idx_grad.abs().max() > 0.1, "no fine sample near the refractive boundary"
+    assert (trans.reshape(-1) - oret[1][3].reshape(-1)).abs().max() < 1e-2
     with pytest.raises(ValueError):
         utils.render_image(lambda k0, k1, r: model.apply(variables, k0, k1, r, False),
                            utils.namedtuple_map(lambda r: r.cuda(), rays), 0, False, chunk=50, debug=True)

@@ -68,6 +68,25 @@ def test_loss_and_gradients_match_oracle(cuda_lib):
     assert sorted(t[4] for t in table)[len(table) // 2] < 0.03
     so3 = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]["Dense_0"]["kernel"]
     assert so3.grad is None            # radiance stage: the sampler receives no gradient (T7)
+    # Against the bf16-EMULATING oracle backward (operands and every stored dZ rounded to bf16 like the kernels do, fp32
+    # accumulate): what is left is summation order, the encodings' double-angle recurrence and the SFU activations.
+    # Stated tolerance: every parameter gradient within 5 % in l2 with cosine >= 0.998.
+    V2 = cv(variables)
+    etotal, _ = O.train_loss(V2, O.build_table(n, ndim, nmin, nmax), cfg, O.Rays(o, d, d, torch.ones(B, 1)), pixels, env,
+                             jitter.cpu().long(), u, 0.5, bg_weight=0.025, bg_smooth_weight=1.0, emulate_bf16="full")
+    etotal.backward()
+    assert abs(total.item() - etotal.item()) < 5e-4 * abs(etotal.item()), (total.item(), etotal.item())
+    table2 = []
+    for mlp, nl in (("fine_mlp", 12), ("coarse_mlp", 12), ("bkgd_mlp", 5)):
+        for i in range(nl):
+            for leaf in ("kernel", "bias"):
+                g = variables["params"][mlp][f"Dense_{i}"][leaf].grad.cpu().double().reshape(-1)
+                og = V2["params"][mlp][f"Dense_{i}"][leaf].grad.double().reshape(-1)
+                table2.append((mlp, i, leaf, round((g @ og / (g.norm() * og.norm() + 1e-30)).item(), 5),
+                               round(((g - og).norm() / (og.norm() + 1e-30)).item(), 4)))
+    print("vs bf16-emulating backward:\n" + "\n".join(map(str, table2)))
+    assert min(t[3] for t in table2) > 0.998, min(table2, key=lambda t: t[3])
+    assert max(t[4] for t in table2) < 0.05, max(table2, key=lambda t: t[4])
 
 
 def test_train_step_reduces_loss(cuda_lib):

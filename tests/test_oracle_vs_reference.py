@@ -219,7 +219,9 @@ def _config_a():
     d = np.load(os.path.join(G, "ref_model_config_a.npz"))
     g = fx["grid"]
     ndim, nmin, nmax = [g["G"]] * 3, [-g["extent"]] * 3, [g["extent"]] * 3
-    focal = 0.5 * fx["width"] / np.tan(0.5 * fx["camera_angle_x"])
+    # a Python float: the rays are computed in float32 like the reference's pinned NumPy 1.x does (value-based casting),
+    # not promoted to float64 by NumPy 2's strong np.float64 scalar
+    focal = float(0.5 * fx["width"] / np.tan(0.5 * fx["camera_angle_x"]))
     rays = O.generate_rays(np.asarray(fx["camtoworld"]), fx["height"], fx["width"], focal, fx["flags"]["use_pixel_centers"])
     flat = O.Rays(*[r.reshape(-1, r.shape[-1]) for r in rays])
     return fx, d, ndim, nmin, nmax, flat
