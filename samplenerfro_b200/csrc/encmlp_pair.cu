@@ -14,8 +14,9 @@
 //     and vice versa: the tensor pipe never waits for an epilogue as long as it takes < ~2000 cycles.
 //
 // Cross-CTA protocol (leader = cluster rank 0 issues every MMA):
-//   full[s]   (local)   this CTA's half of weight slot s has landed (TMA complete_tx)
-//   pfull[s]  (leader)  the peer's half has landed: relayed by the peer's idle warp 1 with a remote arrive
+//   full[s]   (local)   this CTA's half of weight slot s has landed (TMA complete_tx); on the LEADER the barrier takes a
+//                       second arrival, the peer's "my half has landed" relayed by the peer's idle warp 1 (remote arrive),
+//                       so the MMA issuer waits once per chunk for both halves
 //   empty[s]  (both)    multicast tcgen05.commit after the slot's last consumer
 //   acc[j]    (both)    multicast tcgen05.commit after tile pair j's K-loop
 //   aready[j] (leader)  16 arrivals: the 8 epilogue warps of tile j in both CTAs (the peer's arrive remotely)
@@ -95,11 +96,30 @@ __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uin
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with the two shared-memory descriptors given as (low word, shared high word): the K-loop advances a descriptor
+// by adding 2 (32 bytes >> 4) to its low word -- one uniform add per operand instead of rebuilding the 64-bit descriptor
+// from the address (shift, mask, or: ~12 dependent uniform-datapath instructions per MMA, which made the single issuing
+// thread, at ~145 cycles per MMA, slower than the tensor pipe's 128).
+__device__ __forceinline__ void umma2_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on the mbarrier at this offset in BOTH CTAs once all previously issued MMAs have completed
 __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"((uint16_t)3)
                : "memory");
+}
+
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tile_bar_sync(int tile) { asm volatile("bar.sync %0, 256;" ::"r"(tile + 1) : "memory"); }
@@ -201,7 +221,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SL::TMEM_SLOT);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PAIR_NSLOT; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_pfull(s), 1); mbar_init(bar_empty(s), 1); }
+    // full[s] of the LEADER completes on two arrivals: its own producer's arrive.expect_tx (+ the bytes) and the peer's
+    // relayed "my half has landed" -- one wait per chunk on the MMA issuer's critical path instead of two (~150 cycles each)
+    for (int s = 0; s < PAIR_NSLOT; ++s) { mbar_init(bar_full(s), leader ? 2 : 1); mbar_init(bar_pfull(s), 1); mbar_init(bar_empty(s), 1); }
     for (int j = 0; j < 2; ++j) { mbar_init(bar_acc(j), 1); mbar_init(bar_aready(j), 16); }
     fence_barrier_init();
   }
@@ -237,7 +259,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // one elected lane of the (converged) warp: elect.sync lets ptxas emit the uniform-datapath MMA issue without the
+    // per-instruction ELECT / BRA.U.ANY retry loop it wraps around UTCHMMA in code it must assume divergent
+    if (elect_one_sync()) {
       if (!leader) {
         // ===================== peer: relay "my half of slot s has landed" to the leader =====================
         uint32_t c = 0;
@@ -245,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
           for (int i = 0; i < PAIR_NCHUNK; ++i, ++c) {
             const int s = c % PAIR_NSLOT;
             mbar_wait(bar_full(s), (c / PAIR_NSLOT) & 1);
-            mbar_arrive_remote(mapa_shared(bar_pfull(s), 0));
+            mbar_arrive_remote(mapa_shared(bar_full(s), 0));
           }
         }
       } else {
@@ -280,9 +304,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
                 if (first_consumer) {
                   const bool pw = prof && l == 3 && j == 0;     // layer 3, P0: stamps for each of the 4 chunks
                   if (pw) args.prof[240 + i * 4 + 0] = clock64();
-                  if (!(args.dbg & 4)) mbar_wait(bar_full(s), ph);
+                  if (!(args.dbg & 4)) mbar_wait_cluster(bar_full(s), ph);     // both halves of the slot (see the barrier init)
                   if (pw) args.prof[240 + i * 4 + 1] = clock64();
-                  if (!(args.dbg & 2)) mbar_wait_cluster(bar_pfull(s), ph);
                   if (pw) args.prof[240 + i * 4 + 2] = clock64();
                   tc_fence_after();
                 }
@@ -290,11 +313,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
                                                      : (sbase + SL::E_OFF + j * ABLK_BYTES);
                 const uint32_t b_addr = sbase + SL::W_OFF + s * PAIR_HALF_BYTES;
                 const uint32_t d_addr = tmem_base + (uint32_t)(j * 256);
+                const uint64_t a_desc = make_sw128_desc(a_addr), b_desc = make_sw128_desc(b_addr);
+                const uint32_t a_lo = (uint32_t)a_desc, b_lo = (uint32_t)b_desc, desc_hi = (uint32_t)(a_desc >> 32);
 #pragma unroll
-                for (int ks = 0; ks < KB / 16; ++ks) {
-                  umma2_bf16(d_addr, make_sw128_desc(a_addr + ks * 32), make_sw128_desc(b_addr + ks * 32), idesc,
-                             (started || ks > 0) ? 1u : 0u);
-                }
+                for (int ks = 0; ks < KB / 16; ++ks)      // +32 bytes of K per step = +2 in the descriptor's address field
+                  umma2_bf16_lohi(d_addr, a_lo + 2u * ks, b_lo + 2u * ks, desc_hi, idesc, (started || ks > 0) ? 1u : 0u);
                 started = true;
                 if (last_consumer) umma2_commit_mc(bar_empty(s));   // both CTAs may refill their half of the slot
               }
