@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0, ar_phase = 0;
       for (int g = 0; g < my_groups; ++g) {
@@ -252,11 +252,11 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
                 const uint32_t a_addr = ((kbi < akb) ? (sbase + SL::A_OFF + (t * 4 + kbi) * ABLK_BYTES)
                                                      : (sbase + SL::E_OFF + t * ABLK_BYTES)) + sub * (KCH * 2);
                 const uint32_t d_addr = tmem_base + (uint32_t)(t * 256);
+                const uint64_t ad = make_sw128_desc(a_addr), bd = make_sw64_desc(b_addr);
 #pragma unroll
-                for (int ks = 0; ks < KCH / 16; ++ks) {
-                  umma_bf16(d_addr, make_sw128_desc(a_addr + ks * 32), make_sw64_desc(b_addr + ks * 32), idesc,
-                            (kbi > 0 || sub > 0 || ks > 0) ? 1u : 0u);
-                }
+                for (int ks = 0; ks < KCH / 16; ++ks)     // +32 bytes of K per step = +2 in the descriptors' address fields
+                  umma_bf16_lohi(d_addr, (uint32_t)ad + 2u * ks, (uint32_t)(ad >> 32), (uint32_t)bd + 2u * ks, (uint32_t)(bd >> 32),
+                                 idesc, (kbi > 0 || sub > 0 || ks > 0) ? 1u : 0u);
               }
               umma_commit(bar_empty(stage));  // frees the weight slot once these MMAs have read it
               if (++stage == NSTAGE) { stage = 0; phase ^= 1; }

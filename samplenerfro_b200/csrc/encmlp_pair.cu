@@ -116,12 +116,6 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
                : "memory");
 }
 
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
 __device__ __forceinline__ void tile_bar_sync(int tile) { asm volatile("bar.sync %0, 256;" ::"r"(tile + 1) : "memory"); }
 
 // Epilogue of one layer for one row and one 128-column half (64 columns for the condition layer).

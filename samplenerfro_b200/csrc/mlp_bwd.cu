@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // MMA issuer
+    if (elect_one_sync()) {   // MMA issuer
       constexpr uint32_t idesc = make_idesc(TILE_M, 256);
       int stage = 0; uint32_t phase = 0, ar_phase = 0;
       for (int g = 0; g < my_groups; ++g)
@@ -151,10 +151,11 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
 #pragma unroll
               for (int t = 0; t < NT; ++t) {
                 const uint32_t a_addr = sbase + SL::A_OFF + (t * 4 + kbi) * ABLK_BYTES + sub * (KCH * 2);
+                const uint64_t ad = make_sw128_desc(a_addr), bd = make_sw64_desc(b_addr);
 #pragma unroll
-                for (int ks = 0; ks < KCH / 16; ++ks)
-                  umma_bf16(tmem_base + (uint32_t)(t * 256), make_sw128_desc(a_addr + ks * 32), make_sw64_desc(b_addr + ks * 32),
-                            idesc, (kbi > 0 || sub > 0 || ks > 0) ? 1u : 0u);
+                for (int ks = 0; ks < KCH / 16; ++ks)     // +32 bytes of K per step = +2 in the descriptors' address fields
+                  umma_bf16_lohi(tmem_base + (uint32_t)(t * 256), (uint32_t)ad + 2u * ks, (uint32_t)(ad >> 32), (uint32_t)bd + 2u * ks,
+                                 (uint32_t)(bd >> 32), idesc, (kbi > 0 || sub > 0 || ks > 0) ? 1u : 0u);
               }
               umma_commit(bar_empty(stage));
               if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
   const int xatoms = a.kx / 64, zatoms = a.n / 64;  // MN-atoms per K-group
 
   if (warp == 0) {
-    if (lane == 0 && n_steps > 0) {
+    if (n_steps > 0 && elect_one_sync()) {
       const uint32_t idesc = make_idesc_mn(m_rows, a.n);
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < n_steps; ++it) {
@@ -400,13 +401,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
         tc_fence_after();
         const uint32_t xs = sbase + SL::ST_OFF + stage * WG_STAGE_BYTES;
         const uint32_t zs = xs + WG_ROWS * 256 * 2;
+        // descriptors of the stage's first atoms; every MMA adds its byte offset >> 4 to the low words (umma_bf16_lohi)
+        const uint64_t ad0 = make_mn_sw128_desc(xs, 1024, xatoms * 1024), bd0 = make_mn_sw128_desc(zs, 1024, zatoms * 1024);
         for (int mb = 0; mb < n_mblk; ++mb)
 #pragma unroll
           for (int ks = 0; ks < WG_ROWS / 16; ++ks) {
             // K-step = 16 rows = 2 k-groups; A: MN-atoms 2*mb, 2*mb+1 of the X tile; B: all n/64 atoms of the dZ tile
-            const uint64_t ad = make_mn_sw128_desc(xs + (2 * ks) * xatoms * 1024 + mb * 2 * 1024, 1024, xatoms * 1024);
-            const uint64_t bd = make_mn_sw128_desc(zs + (2 * ks) * zatoms * 1024, 1024, zatoms * 1024);
-            umma_bf16(tmem_base + (uint32_t)(mb * 256), ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            const uint32_t a_off = (uint32_t)(((2 * ks) * xatoms * 1024 + mb * 2 * 1024) >> 4);
+            const uint32_t b_off = (uint32_t)(((2 * ks) * zatoms * 1024) >> 4);
+            umma_bf16_lohi(tmem_base + (uint32_t)(mb * 256), (uint32_t)ad0 + a_off, (uint32_t)(ad0 >> 32), (uint32_t)bd0 + b_off,
+                           (uint32_t)(bd0 >> 32), idesc, (it > 0 || ks > 0) ? 1u : 0u);
           }
         umma_commit(bar_empty(stage));
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }

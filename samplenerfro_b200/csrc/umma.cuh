@@ -143,6 +143,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same with each shared-memory descriptor given as (low word, high word).  The K loop of every kernel here advances a
+// descriptor by adding (byte offset >> 4) to its LOW word (the 14-bit start-address field; it cannot carry for addresses
+// inside the 227 KB window): one uniform add per operand and MMA instead of rebuilding the 64-bit descriptor from the
+// address (shift, mask, or -- a ~12-deep dependent chain on the uniform datapath that held the single issuing thread to
+// one MMA per ~145 cycles, slower than the tensor pipe executes them).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One lane of a CONVERGED warp.  Unlike `if (lane == 0)`, elect.sync tells ptxas the branch holds exactly one thread, so
+// the uniform-datapath instructions inside (UTCHMMA, UTCBAR, UBLKCP) are emitted plainly instead of each being wrapped in
+// an ELECT / BRA.U.ANY retry loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
