@@ -187,8 +187,12 @@ def train_arm(a, model, rank, world, local, dev, barrier, peaks):
     gen = torch.Generator().manual_seed(1234 + rank)
     idx = torch.randint(0, 640000, (B,), generator=gen)
     rays = utils.namedtuple_map(lambda r: r[idx].to(dev).contiguous(), flat)
+    # the env patch is part of the batch dict the reference shards over its devices (datasets.py:98-100 -> utils.shard:
+    # [128,128,.] -> [n_dev, 128/n_dev, 128, .]), so each rank evaluates 128/N rows of it (and train.py:128-129 reshapes its
+    # shard to [ps, ps, -1] with ps = 128/N, which loss_fn reproduces)
     env = synthetic.blender_rays(synthetic.camera_pose(1.3, 0.8, 4.03), 128, 128, camera_angle_x=0.2)
-    env = utils.namedtuple_map(lambda r: r.to(dev).contiguous(), env)
+    e0, e1 = utils.shard_range(128, rank, world)
+    env = utils.namedtuple_map(lambda r: r[e0:e1].to(dev).contiguous(), env)
     batch = {"rays": rays, "pixels": torch.rand(B, 3, generator=gen).to(dev), "env_rays": env, "annealed_alpha": 0.5}
     out = {}
     for label, ws in (("with_allreduce", world),) + ((("compute_only", 1),) if world > 1 else ()):

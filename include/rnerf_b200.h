@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 6
+#define RNERF_ABI_VERSION 7
 #define RNERF_PATH_STRIDE 12         /* full records */
 #define RNERF_PATH_STRIDE_COMPACT 8
 
@@ -85,13 +85,16 @@ int rnerf_march_fwd(const float* table, const float* bricks /* from rnerf_grid_b
  * when given it wins and is read at run time, so a captured CUDA graph of the training step follows the annealing
  * schedule (train.py:350-351) instead of replaying its capture-time window (so3_window_host may then be NULL).  The same
  * pair of arguments appears in rnerf_so3_predict and rnerf_march_all_bwd.
+ * so3_tc_packed: rnerf_so3_tc_pack(so3_w) or NULL.  When given, launches large enough to keep the rays of a CTA in lockstep
+ * (full frames) with compact records evaluate so3_mlp on the tensor pipe (tcgen05.mma kind::tf32, 3xTF32 split: fp32-grade
+ * products, positions within the same 1e-4 of the reference); otherwise the fp32 CUDA-core chain runs.
  * Outputs as rnerf_march_fwd (idx_grad is the un-rotated grad n). */
 size_t rnerf_so3_weight_floats(void);
 int rnerf_march_all_fwd(const float* table, const float* bricks, const int ndim_host[3], const double nmin_host[3],
                         const double nmax_host[3], const float* origins, const float* viewdirs, int64_t n_rays,
                         double near, double far, int n_steps, int rec_floats, const float* so3_w,
-                        const double so3_window_host[10], const float* so3_window_dev, float* path, float* t_col,
-                        void* stream);
+                        const double so3_window_host[10], const float* so3_window_dev, const void* so3_tc_packed,
+                        float* path, float* t_col, void* stream);
 
 /* ray_dir[B][S][3] = safe_l2_normalize(v) of every record: the `ray_dir` array of PathSampler.__call__
  * (rnerf/eikonal_utils.py:113), for callers that want the whole bent path (extract_mesh.py:178). */
@@ -217,6 +220,13 @@ int rnerf_sq_err(const float* a, const float* b, int64_t n, float* out_accum, vo
  * (rnerf/eikonal_utils.py:84-98). */
 int rnerf_so3_predict(const float* so3_w, const double so3_window_host[10], const float* so3_window_dev, const float* pts,
                       const float* cond, int64_t n, float* pred, void* stream);
+/* so3_mlp on the tensor pipe (tcgen05.mma kind::tf32, 3xTF32 split for fp32-grade products): rnerf_so3_tc_pack turns the fp32
+ * image so3_w into the pre-swizzled hi/lo weight chunks the evaluator streams (rnerf_so3_tc_packed_bytes() bytes; repack
+ * whenever so3_w changes); rnerf_so3_predict_tc = rnerf_so3_predict through that evaluator (same arguments + the packed image). */
+size_t rnerf_so3_tc_packed_bytes(void);
+int rnerf_so3_tc_pack(const float* so3_w, void* so3_tc_packed, void* stream);
+int rnerf_so3_predict_tc(const void* so3_tc_packed, const float* so3_w, const double so3_window_host[10],
+                         const float* so3_window_dev, const float* pts, const float* cond, int64_t n, float* pred, void* stream);
 size_t rnerf_mlp_input_grad_packed_floats(void);
 int rnerf_mlp_input_grad_pack(const float* dense0_kernel, const float* dense5_kernel, const float* dense10_kernel,
                               float* wt, void* stream);

@@ -19,6 +19,7 @@
 #include <mutex>
 #include "common.cuh"
 #include "march_common.cuh"
+#include "so3_tc.cuh"
 
 namespace rnerf {
 
@@ -591,6 +592,412 @@ __global__ void __launch_bounds__(SO3_THREADS, 2) so3_predict_kernel(const float
   ring_drain(ring);
 }
 
+// The same on the tensor pipe (so3_tc.cuh): persistent CTAs, 64 points per pass.  Warp 0: weight producer (TMA ring), warp 1:
+// MMA issuer, warps 2-5: encoding / epilogue / head (thread = TMEM lane = neuron).  Stand-alone form of the evaluator the
+// "all"-stage march uses; also what pins its arithmetic against the CUDA-core chain (tests/test_gpu_kernels.py).
+constexpr int TCP_THREADS = 192, TCP_SLOTS = 6;
+struct TcPredictSmem {
+  static constexpr uint32_t P_OFF = TcSmem::RING + TCP_SLOTS * TC_A_BYTES;      // positions [3][64], then raw [3][64]
+  static constexpr uint32_t BAR_OFF = P_OFF + 6 * TC_N * 4;                      // full[6], empty[6], acc, act
+  static constexpr uint32_t TMEM_SLOT = BAR_OFF + (2 * TCP_SLOTS + 2) * 8;
+  static constexpr uint32_t BYTES = TMEM_SLOT + 16;
+};
+__global__ void __launch_bounds__(TCP_THREADS, 1) so3_predict_tc_kernel(const uint8_t* __restrict__ packed, const So3Args so3,
+                                                                        const float* __restrict__ pts, const float* __restrict__ cond,
+                                                                        int64_t n, float* __restrict__ pred) {
+  using SL = TcPredictSmem;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  const uint32_t sbase = smem_u32(tc_smem);
+  if ((sbase & 1023u) != 0) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full0 = sbase + SL::BAR_OFF, bar_empty0 = bar_full0 + 8 * TCP_SLOTS;
+  const uint32_t bar_acc = bar_empty0 + 8 * TCP_SLOTS, bar_act = bar_acc + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(tc_smem + SL::TMEM_SLOT);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TCP_SLOTS; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_empty0 + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_act, 4);                       // the four worker warps
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(sbase + SL::TMEM_SLOT, TC_N); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t n_tiles = (n + TC_N - 1) / TC_N;
+  const int64_t my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {                      // weight producer: the 32 chunks of an evaluation, over and over
+      uint32_t c = 0;
+      for (int64_t t = 0; t < my_tiles; ++t)
+        for (int i = 0; i < TC_NCHUNK; ++i, ++c) {
+          const uint32_t s = c % TCP_SLOTS;
+          mbar_wait(bar_empty0 + 8 * s, ((c / TCP_SLOTS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(bar_full0 + 8 * s, TC_A_BYTES);
+          tma_bulk_g2s(sbase + TcSmem::RING + s * TC_A_BYTES, packed + (size_t)i * TC_A_BYTES, TC_A_BYTES, bar_full0 + 8 * s);
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {                      // MMA issuer
+      uint32_t c = 0, act_phase = 0;
+      for (int64_t t = 0; t < my_tiles; ++t)
+        for (int l = 0; l < 4; ++l) {
+          mbar_wait(bar_act, act_phase); act_phase ^= 1u;
+          tc_fence_after();
+          tc_issue_layer(l, sbase, tmem_base, bar_full0, bar_empty0, TCP_SLOTS, c, bar_acc, so3.dbg);
+        }
+    }
+  } else {
+    const int q = warp & 3, wt = threadIdx.x - 64, m = q * 32 + lane;
+    float* P = reinterpret_cast<float*>(tc_smem + SL::P_OFF);
+    float* RAW = P + 3 * TC_N;
+    const float* bias = so3.w + SO3_OFF_B;
+    const float* W4 = so3.w + SO3_OFF_W4;
+    const float* hs = reinterpret_cast<const float*>(tc_smem + TcSmem::HS);
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_phase = 0;
+    auto workers_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    auto publish = [&] {                         // generic-proxy writes -> visible to the MMA, accumulators drained
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_act);
+    };
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int64_t p0 = (blockIdx.x + t * gridDim.x) * TC_N;
+      const int n_here = (int)min((int64_t)TC_N, n - p0);
+      workers_sync();                            // the previous pass's head has finished with P / RAW / HS
+      if (wt < TC_N) {
+        const int64_t i = p0 + min(wt, n_here - 1);
+        P[wt] = pts[3 * i]; P[TC_N + wt] = pts[3 * i + 1]; P[2 * TC_N + wt] = pts[3 * i + 2];
+      }
+      workers_sync();
+      if (!(so3.dbg & 4)) tc_write_encoding(so3, tc_smem, P, TC_N, wt, 128);
+      publish();
+      for (int l = 0; l < 4; ++l) {
+        mbar_wait(bar_acc, acc_phase); acc_phase ^= 1u;
+        tc_fence_after();
+        if (!(so3.dbg & 2)) tc_epilogue(l, tc_smem, tmem_lane, q, lane, __ldg(bias + l * SO3_W + m));
+        if (l < 3) publish();
+      }
+      tc_fence_before();
+      workers_sync();                            // Dense_3 output complete in HS
+      if (!(so3.dbg & 8))
+      for (int e = wt; e < 3 * TC_N; e += 128) {     // Dense_4: raw[j][column]
+        const int j = e / TC_N, cc = e - j * TC_N;
+        float r = __ldg(bias + 4 * SO3_W + j);
+#pragma unroll 8
+        for (int k = 0; k < SO3_W; ++k) r = fmaf(hs[k * TcSmem::HS_PITCH + cc], __ldg(W4 + 3 * k + j), r);
+        RAW[j * TC_N + cc] = r;
+      }
+      workers_sync();
+      if (wt < n_here) {
+        const int64_t i = p0 + wt;
+        float gx = cond[3 * i], gy = cond[3 * i + 1], gz = cond[3 * i + 2];
+        so3_rotate(RAW[wt], RAW[TC_N + wt], RAW[2 * TC_N + wt], gx, gy, gz);
+        pred[3 * i] = gx; pred[3 * i + 1] = gy; pred[3 * i + 2] = gz;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TC_N);
+}
+
+// ---- "all"-stage march with so3_mlp on the tensor pipe ------------------------------------------------------------------
+// Lockstep march of 256 rays per CTA (one CTA per SM: the evaluator's operands take ~160 KB of shared memory), compact
+// records.  Warps 0-7 carry the rays AND are the evaluator's workers (encoding, epilogues, head); warp 8 streams the weight
+// chunks (TMA ring, keeps running across evaluations), warp 9 issues the MMAs.  Per ray the march arithmetic is that of
+// march_kernel; the evaluation differs from the CUDA-core chain only by the 3xTF32 products (fp32-grade, so3_tc.cuh).
+constexpr int MTC_CW = 8;                            // carrier = worker warps
+constexpr int MTC_RAYS = MTC_CW * 32;
+constexpr int MTC_THREADS = MTC_RAYS + 64;
+constexpr int MTC_SLOTS = 4;
+constexpr int MTC_PITCH = STEPS_PER_FLUSH * 2 + 1;   // float4 per ray in the staging buffer (compact records + 1 pad)
+struct MtcSmem {
+  static constexpr uint32_t STAGE = TcSmem::RING + MTC_SLOTS * TC_A_BYTES;                  // [8 warps][32 * MTC_PITCH] float4
+  static constexpr uint32_t TSTAGE = STAGE + MTC_CW * 32 * MTC_PITCH * 16;                   // [8 warps][T_FLUSH * 32] float
+  static constexpr uint32_t P_OFF = TSTAGE + MTC_CW * T_FLUSH * 32 * 4;                      // P[3][64], RAW[3][64]
+  static constexpr uint32_t CNT = P_OFF + 6 * TC_N * 4;                                      // counts[8] | exit flag | chunks consumed
+  static constexpr uint32_t BAR_OFF = CNT + 64;                                               // full[4], empty[4], acc, act
+  static constexpr uint32_t TMEM_SLOT = BAR_OFF + (2 * MTC_SLOTS + 2) * 8;
+  static constexpr uint32_t BYTES = TMEM_SLOT + 16;
+};
+static_assert(MtcSmem::BYTES <= 232448, "march_tc_kernel exceeds the shared-memory budget");
+
+__device__ __forceinline__ void mtc_workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ bool mtc_workers_or(bool p) {
+  uint32_t r;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbarrier.cta.red.or.pred q, 1, 256, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+               : "=r"(r) : "r"((uint32_t)p) : "memory");
+  return r != 0;
+}
+
+struct MtcEval {
+  uint8_t* smem;
+  uint32_t tmem_base, bar_acc, bar_act, acc_phase, passes;
+};
+
+// raw = so3_mlp(annealed_pos_enc(p)) for the CTA's active rays on the tensor pipe.  All 256 worker threads call this.
+__device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int warp, int lane, bool act, float px, float py, float pz,
+                                            float& r0, float& r1, float& r2) {
+  uint8_t* smem = ev.smem;
+  int* cnt = reinterpret_cast<int*>(smem + MtcSmem::CNT);
+  float* P = reinterpret_cast<float*>(smem + MtcSmem::P_OFF);
+  float* RAW = P + 3 * TC_N;
+  const float* hs = reinterpret_cast<const float*>(smem + TcSmem::HS);
+  const int tid = warp * 32 + lane;
+  const unsigned bal = __ballot_sync(0xffffffffu, act);
+  if (lane == 0) cnt[warp] = __popc(bal);
+  mtc_workers_sync();
+  int base = 0, n_act = 0;
+#pragma unroll
+  for (int w = 0; w < MTC_CW; ++w) {
+    const int c = cnt[w];
+    if (w < warp) base += c;
+    n_act += c;
+  }
+  const int idx = base + __popc(bal & ((1u << lane) - 1u));
+  const float* bias = a.w + SO3_OFF_B;
+  const float* W4 = a.w + SO3_OFF_W4;
+  const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+  const uint32_t tmem_lane = ev.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+  auto publish = [&] {                           // generic-proxy writes -> visible to the MMA; accumulators drained
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ev.bar_act);
+  };
+  r0 = r1 = r2 = 0.f;
+#pragma unroll 1
+  for (int col0 = 0; col0 < n_act; col0 += TC_N) {
+    const int n_here = min(TC_N, n_act - col0);
+    const bool mine = act && idx >= col0 && idx < col0 + TC_N;
+    const int col = idx - col0;
+    mtc_workers_sync();                          // counts read; the previous pass's RAW / HS are no longer needed
+    if (mine) { P[col] = px; P[TC_N + col] = py; P[2 * TC_N + col] = pz; }
+    mtc_workers_sync();
+    // ---- encoding: warp w takes columns w, w + 8, ...; lane = feature (two per lane: f and f + 32) -> 128-byte row writes
+    for (int c = warp; c < n_here; c += MTC_CW) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int f = lane + 32 * hh;
+        float val = 0.f;
+        if (f < SO3_IN) {
+          const int k = f / 6, qq = f - 6 * k, ax = qq >= 3 ? qq - 3 : qq;
+          const float xb = mul(P[ax * TC_N + c], (float)(1 << k));
+          val = mul(sinf(qq >= 3 ? add(xb, 1.57079632679489661923f) : xb), so3_window_at(a, k));
+        }
+        const float vh = tf32_rn(val);
+        const uint32_t off = (uint32_t)hh * TC_B_BYTES + tc_sw128_off(c, lane);
+        *reinterpret_cast<float*>(smem + TcSmem::X_HI + off) = vh;
+        *reinterpret_cast<float*>(smem + TcSmem::X_LO + off) = val - vh;
+      }
+    }
+    publish();
+    const bool has_cols = half * 32 < n_here;    // (warp-uniform) this warp's 32 columns hold at least one active ray
+#pragma unroll 1
+    for (int l = 0; l < 4; ++l) {
+      mbar_wait(ev.bar_acc, ev.acc_phase); ev.acc_phase ^= 1u;
+      tc_fence_after();
+      if (has_cols) {
+        const float b = __ldg(bias + l * SO3_W + m);
+        uint32_t v[32];
+        tmem_ld32(tmem_lane, v);
+        tmem_ld_wait();
+        if (l < 3) {
+          uint8_t* hi = smem + TcSmem::H_HI + q * TC_B_BYTES;
+          uint8_t* lo = smem + TcSmem::H_LO + q * TC_B_BYTES;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float h = fmaxf(__uint_as_float(v[j]) + b, 0.f);
+            const float hh = tf32_rn(h);
+            const uint32_t off = tc_sw128_off(half * 32 + j, lane);
+            *reinterpret_cast<float*>(hi + off) = hh;
+            *reinterpret_cast<float*>(lo + off) = h - hh;
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(smem + TcSmem::HS) + m * TcSmem::HS_PITCH + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(fmaxf(__uint_as_float(v[j]) + b, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b, 0.f),
+                                                            fmaxf(__uint_as_float(v[j + 2]) + b, 0.f), fmaxf(__uint_as_float(v[j + 3]) + b, 0.f));
+        }
+      }
+      if (l < 3) publish();
+    }
+    tc_fence_before();
+    mtc_workers_sync();                          // Dense_3 output complete in HS
+    // ---- Dense_4 (128 -> 3): four threads per output, 32 inputs each, combined with two shuffles
+    for (int it = tid; it < ((12 * n_here + 255) & ~255); it += MTC_RAYS) {
+      const int e = it >> 2, kq = it & 3;
+      float part = 0.f;
+      const bool live = e < 3 * n_here;
+      const int j = live ? e / n_here : 0, cc = live ? e - j * n_here : 0;
+      if (live) {
+#pragma unroll 8
+        for (int k = kq * 32; k < kq * 32 + 32; ++k) part = fmaf(hs[k * TcSmem::HS_PITCH + cc], __ldg(W4 + 3 * k + j), part);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      if (live && kq == 0) RAW[j * TC_N + cc] = part + __ldg(bias + 4 * SO3_W + j);
+    }
+    mtc_workers_sync();
+    if (mine) { r0 = RAW[col]; r1 = RAW[TC_N + col]; r2 = RAW[2 * TC_N + col]; }
+    ++ev.passes;
+  }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(MTC_THREADS, 1) march_tc_kernel(const float4* __restrict__ table, const MarchGeom mg,
+                                                                  const float* __restrict__ origins, const float* __restrict__ viewdirs,
+                                                                  int64_t n_rays, float near, float step, int n_steps,
+                                                                  float4* __restrict__ path, float* __restrict__ t_col,
+                                                                  const float* __restrict__ bricks, const So3Args so3,
+                                                                  const uint8_t* __restrict__ packed) {
+  using SL = MtcSmem;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  const uint32_t sbase = smem_u32(tc_smem);
+  if ((sbase & 1023u) != 0) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full0 = sbase + SL::BAR_OFF, bar_empty0 = bar_full0 + 8 * MTC_SLOTS;
+  const uint32_t bar_acc = bar_empty0 + 8 * MTC_SLOTS, bar_act = bar_acc + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(tc_smem + SL::TMEM_SLOT);
+  volatile int* flags = reinterpret_cast<volatile int*>(tc_smem + SL::CNT) + 8;      // [0] exit, [1] chunks consumed
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MTC_SLOTS; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_empty0 + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_act, MTC_CW);
+    flags[0] = 0; flags[1] = 0;
+    fence_barrier_init();
+  }
+  if (warp == MTC_CW + 1) { tmem_alloc(sbase + SL::TMEM_SLOT, TC_N); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == MTC_CW) {
+    if (elect_one_sync()) {                      // weight producer: chunk c % 32 of the periodic stream into slot c % 4
+      uint32_t c = 0;
+      bool stop = false;
+      while (!stop) {
+        const uint32_t s = c % MTC_SLOTS, par = ((c / MTC_SLOTS) & 1u) ^ 1u;
+        while (!mbar_try_wait(bar_empty0 + 8 * s, par))
+          if (flags[0]) { stop = true; break; }
+        if (stop) break;
+        mbar_arrive_expect_tx(bar_full0 + 8 * s, TC_A_BYTES);
+        tma_bulk_g2s(sbase + TcSmem::RING + s * TC_A_BYTES, packed + (size_t)(c % TC_NCHUNK) * TC_A_BYTES, TC_A_BYTES, bar_full0 + 8 * s);
+        ++c;
+      }
+      // chunks fetched ahead for an evaluation that never came must have landed before the CTA may exit
+      for (uint32_t g = (uint32_t)flags[1]; g < c; ++g) mbar_wait(bar_full0 + 8 * (g % MTC_SLOTS), (g / MTC_SLOTS) & 1u);
+    }
+  } else if (warp == MTC_CW + 1) {
+    if (elect_one_sync()) {                      // MMA issuer: one layer per "activations ready"
+      uint32_t c = 0, act_phase = 0, layer = 0;
+      bool stop = false;
+      while (!stop) {
+        while (!mbar_try_wait(bar_act, act_phase))
+          if (flags[0]) { stop = true; break; }
+        if (stop) break;
+        act_phase ^= 1u;
+        tc_fence_after();
+        tc_issue_layer((int)layer, sbase, tmem_base, bar_full0, bar_empty0, MTC_SLOTS, c, bar_acc);
+        layer = (layer + 1) & 3u;
+      }
+    }
+  } else {
+    // ===================== the rays: 8 warps x 32 consecutive rays, in lockstep =====================
+    MtcEval ev;
+    ev.smem = tc_smem; ev.tmem_base = tmem_base; ev.bar_acc = bar_acc; ev.bar_act = bar_act; ev.acc_phase = 0; ev.passes = 0;
+    const int64_t warp_ray0 = blockIdx.x * (int64_t)MTC_RAYS + warp * 32;
+    const int64_t ray = warp_ray0 + lane;
+    const bool live = ray < n_rays;
+    const int64_t rr = live ? ray : (n_rays - 1);
+    float ox = origins[3 * rr], oy = origins[3 * rr + 1], oz = origins[3 * rr + 2];
+    float vx = viewdirs[3 * rr], vy = viewdirs[3 * rr + 1], vz = viewdirs[3 * rr + 2];
+    float px = add(ox, mul(near, vx)), py = add(oy, mul(near, vy)), pz = add(oz, mul(near, vz));
+    float t = near;
+    float4* stage_w = reinterpret_cast<float4*>(tc_smem + SL::STAGE) + warp * 32 * MTC_PITCH;
+    float4* my_stage = stage_w + lane * MTC_PITCH;
+    float* ts = reinterpret_cast<float*>(tc_smem + SL::TSTAGE) + warp * T_FLUSH * 32;
+    const int rays_here = (int)max((int64_t)0, min((int64_t)32, n_rays - warp_ray0));
+    const int ray_stride4 = n_steps * 2;
+    const bool t_vec = t_col != nullptr && (n_steps & 3) == 0 && (reinterpret_cast<uintptr_t>(t_col) & 15u) == 0;
+    constexpr int F4 = STEPS_PER_FLUSH * 2;      // float4 per ray per flush
+    const int fr = lane >> 3, fu = lane & 7;     // flush mapping: 4 rays x 8 units per iteration
+    float4* g_wr = path + warp_ray0 * (int64_t)ray_stride4;
+
+    for (int k0 = 0; k0 < n_steps; k0 += STEPS_PER_FLUSH) {
+      const int nk = min(STEPS_PER_FLUSH, n_steps - k0);
+      const int trow = k0 & (T_FLUSH - 1);
+      for (int kk = 0; kk < nk; ++kk) {
+        const float4 c = march_lookup<FAST>(table, mg, bricks, px, py, pz);
+        my_stage[kk * 2 + 0] = make_float4(px, py, pz, t);
+        my_stage[kk * 2 + 1] = make_float4(vx, vy, vz, c.x);
+        ts[(trow + kk) * 32 + lane] = t;
+        float gx = c.y, gy = c.z, gz = c.w;
+        const bool act = live && sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;     // jnp.linalg.norm(idx_grad) > 1e-3
+        if (mtc_workers_or(act)) {
+          float r0, r1, r2;
+          so3_eval_tc(so3, ev, warp, lane, act, px, py, pz, r0, r1, r2);
+          if (act) so3_rotate(r0, r1, r2, gx, gy, gz);
+        }
+        const float s = divf(step, c.x);
+        const float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
+        vx = add(vx, mul(step, gx)); vy = add(vy, mul(step, gy)); vz = add(vz, mul(step, gz));
+        t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
+        px = nx; py = ny; pz = nz;
+      }
+      __syncwarp();
+      if (t_col != nullptr && (trow + nk == T_FLUSH || k0 + nk >= n_steps)) {
+        const int filled = trow + nk, kbase = k0 - trow;
+        float* tb = t_col + warp_ray0 * (int64_t)n_steps + kbase;
+        if (filled == T_FLUSH && t_vec) {
+#pragma unroll
+          for (int it = 0; it < T_FLUSH / 4; ++it) {
+            const int e = it * 32 + lane, r = e >> 2, qd = e & 3;
+            if (r < rays_here)
+              __stcs(reinterpret_cast<float4*>(tb + r * n_steps + 4 * qd),
+                     make_float4(ts[(4 * qd) * 32 + r], ts[(4 * qd + 1) * 32 + r], ts[(4 * qd + 2) * 32 + r], ts[(4 * qd + 3) * 32 + r]));
+          }
+        } else {
+          for (int e = lane; e < rays_here * filled; e += 32) {
+            const int r = e / filled, j = e - r * filled;
+            tb[r * n_steps + j] = ts[j * 32 + r];
+          }
+        }
+      }
+      if (nk == STEPS_PER_FLUSH && rays_here == 32) {
+#pragma unroll
+        for (int round = 0; round < 8; ++round) {
+          const int r = round * 4 + fr;
+          __stcs(g_wr + r * ray_stride4 + fu, stage_w[r * MTC_PITCH + fu]);
+        }
+      } else {
+        const int n4 = nk * 2, total4 = rays_here * n4;
+        for (int e = lane; e < total4; e += 32) {
+          const int r = e / n4, j = e - r * n4;
+          __stcs(g_wr + r * ray_stride4 + j, stage_w[r * MTC_PITCH + j]);
+        }
+      }
+      g_wr += F4;
+      __syncwarp();
+    }
+    mtc_workers_sync();
+    if (threadIdx.x == 0) {
+      flags[1] = (int)(ev.passes * TC_NCHUNK);
+      __threadfence_block();
+      flags[0] = 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MTC_CW + 1) tmem_dealloc(tmem_base, TC_N);
+}
+
 // ray_dir of every record, normalised: the array PathSampler returns (rnerf/eikonal_utils.py:113)
 __global__ void __launch_bounds__(256) path_dirs_kernel(const float4* __restrict__ path, int recf4, int64_t n_rec,
                                                         float* __restrict__ out) {
@@ -655,7 +1062,8 @@ bool rnerf::make_march_geom(const int ndim[3], const double nmin[3], const doubl
 static int march_impl(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
                       const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
                       double near, double far, int n_steps, int rec_floats, const float* so3_w,
-                      const double* so3_window, const float* so3_window_dev, float* path, float* t_col, void* stream) {
+                      const double* so3_window, const float* so3_window_dev, const void* so3_tc_packed, float* path, float* t_col,
+                      void* stream) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_fwd: n_rays < 0");
   RNERF_REQUIRE(n_steps >= 2, RNERF_E_SHAPE, "rnerf_march_fwd: n_steps must be >= 2 (step = (far-near)/(S-1))");
@@ -704,6 +1112,24 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
       attr_set[dev] = dyn;
     }
   }
+  // Full frames with compact records: so3_mlp on the tensor pipe (march_tc_kernel), when the caller supplies the packed
+  // hi/lo weight image.  RNERF_SO3_TC=0 keeps the CUDA-core chain (development aid for A/B runs).
+  if (so3_w != nullptr && so3_tc_packed != nullptr && rec_floats == 8 && rpc == MARCH_THREADS &&
+      !(getenv("RNERF_SO3_TC") != nullptr && atoi(getenv("RNERF_SO3_TC")) == 0)) {
+    RNERF_REQUIRE(aligned16(so3_tc_packed), RNERF_E_ALIGN, "rnerf_march_all_fwd: so3_tc_packed must be 16-byte aligned");
+    cudaError_t e = cudaFuncSetAttribute(march_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MtcSmem::BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(march_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MtcSmem::BYTES);
+    if (e != cudaSuccess) { set_error("rnerf_march_all_fwd: cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e)); return (int)e; }
+    const unsigned tb = (unsigned)((n_rays + MTC_RAYS - 1) / MTC_RAYS);
+    if (fast)
+      march_tc_kernel<true><<<tb, MTC_THREADS, MtcSmem::BYTES, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, step,
+                                                                    n_steps, (float4*)path, t_col, bricks, so3, (const uint8_t*)so3_tc_packed);
+    else
+      march_tc_kernel<false><<<tb, MTC_THREADS, MtcSmem::BYTES, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, step,
+                                                                     n_steps, (float4*)path, t_col, bricks, so3, (const uint8_t*)so3_tc_packed);
+    count_launch();
+    return check_launch("rnerf_march_all_fwd(tc)");
+  }
 #define RNERF_MARCH_LAUNCH(R, F, A)                                                                                       \
   march_kernel<R, F, A><<<blocks, (A) ? SO3_THREADS : MARCH_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
                                                             step, n_steps, (float4*)path, t_col, bricks, dbg, so3, slots, rpc)
@@ -738,7 +1164,7 @@ extern "C" int rnerf_march_fwd(const float* table, const float* bricks, const in
                                double near, double far, int n_steps, int rec_floats, float* path, float* t_col,
                                void* stream) {
   return march_impl(table, bricks, ndim, nmin, nmax, origins, viewdirs, n_rays, near, far, n_steps, rec_floats, nullptr,
-                    nullptr, nullptr, path, t_col, stream);
+                    nullptr, nullptr, nullptr, path, t_col, stream);
 }
 
 extern "C" size_t rnerf_so3_weight_floats(void) { return SO3_FLOATS; }
@@ -746,12 +1172,12 @@ extern "C" size_t rnerf_so3_weight_floats(void) { return SO3_FLOATS; }
 extern "C" int rnerf_march_all_fwd(const float* table, const float* bricks, const int ndim[3], const double nmin[3],
                                    const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
                                    double near, double far, int n_steps, int rec_floats, const float* so3_w,
-                                   const double so3_window[10], const float* so3_window_dev, float* path, float* t_col,
-                                   void* stream) {
+                                   const double so3_window[10], const float* so3_window_dev, const void* so3_tc_packed,
+                                   float* path, float* t_col, void* stream) {
   RNERF_REQUIRE_PTR(so3_w);
   RNERF_REQUIRE(so3_window != nullptr || so3_window_dev != nullptr, RNERF_E_NULL, "rnerf_march_all_fwd: no so3 window given");
   return march_impl(table, bricks, ndim, nmin, nmax, origins, viewdirs, n_rays, near, far, n_steps, rec_floats, so3_w,
-                    so3_window, so3_window_dev, path, t_col, stream);
+                    so3_window, so3_window_dev, so3_tc_packed, path, t_col, stream);
 }
 
 extern "C" int rnerf_select(const float* path, int rec_floats, int64_t n_rays, int n_steps, const int32_t* jitter,
@@ -782,6 +1208,42 @@ extern "C" int rnerf_path_dirs(const float* path, int rec_floats, int64_t n_rays
   return check_launch("rnerf_path_dirs");
 }
 
+extern "C" size_t rnerf_so3_tc_packed_bytes(void) { return TC_PACKED_BYTES; }
+
+extern "C" int rnerf_so3_tc_pack(const float* so3_w, void* packed, void* stream) {
+  RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(packed);
+  RNERF_REQUIRE(aligned16(packed), RNERF_E_ALIGN, "rnerf_so3_tc_pack: packed must be 16-byte aligned");
+  so3_tc_pack_kernel<<<(TC_NKB * SO3_W * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(so3_w, (uint8_t*)packed);
+  count_launch();
+  return check_launch("rnerf_so3_tc_pack");
+}
+
+extern "C" int rnerf_so3_predict_tc(const void* so3_tc_packed, const float* so3_w, const double so3_window[10],
+                                    const float* so3_window_dev, const float* pts, const float* cond, int64_t n, float* pred,
+                                    void* stream) {
+  RNERF_REQUIRE(n >= 0, RNERF_E_SHAPE, "rnerf_so3_predict_tc: n < 0");
+  if (n == 0) return 0;
+  RNERF_REQUIRE_PTR(so3_tc_packed); RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(pts); RNERF_REQUIRE_PTR(cond); RNERF_REQUIRE_PTR(pred);
+  RNERF_REQUIRE(so3_window != nullptr || so3_window_dev != nullptr, RNERF_E_NULL, "rnerf_so3_predict_tc: no so3 window given");
+  RNERF_REQUIRE(aligned16(so3_tc_packed) && aligned16(so3_w), RNERF_E_ALIGN, "rnerf_so3_predict_tc: weight images must be 16-byte aligned");
+  So3Args so3;
+  memset(&so3, 0, sizeof(so3));
+  so3.w = so3_w;
+  for (int k = 0; k < 10; ++k) so3.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
+  so3.window_dev = so3_window_dev;
+  { const char* d = getenv("RNERF_SO3_TC_DEBUG"); so3.dbg = d ? atoi(d) : 0; }
+  cudaError_t e = cudaFuncSetAttribute(so3_predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPredictSmem::BYTES);
+  if (e != cudaSuccess) { set_error("rnerf_so3_predict_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (n + TC_N - 1) / TC_N;
+  so3_predict_tc_kernel<<<(unsigned)(tiles < n_sm ? tiles : n_sm), TCP_THREADS, TcPredictSmem::BYTES, (cudaStream_t)stream>>>(
+      (const uint8_t*)so3_tc_packed, so3, pts, cond, n, pred);
+  count_launch();
+  return check_launch("rnerf_so3_predict_tc");
+}
+
 extern "C" int rnerf_so3_predict(const float* so3_w, const double so3_window[10], const float* so3_window_dev, const float* pts,
                                  const float* cond, int64_t n, float* pred, void* stream) {
   RNERF_REQUIRE(n >= 0, RNERF_E_SHAPE, "rnerf_so3_predict: n < 0");
@@ -790,6 +1252,7 @@ extern "C" int rnerf_so3_predict(const float* so3_w, const double so3_window[10]
   RNERF_REQUIRE(so3_window != nullptr || so3_window_dev != nullptr, RNERF_E_NULL, "rnerf_so3_predict: no so3 window given");
   RNERF_REQUIRE(aligned16(so3_w), RNERF_E_ALIGN, "rnerf_so3_predict: so3_w must be 16-byte aligned");
   So3Args so3;
+  memset(&so3, 0, sizeof(so3));
   so3.w = so3_w;
   for (int k = 0; k < 10; ++k) so3.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
   so3.window_dev = so3_window_dev;

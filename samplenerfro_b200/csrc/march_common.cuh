@@ -50,6 +50,7 @@ struct So3Args {
   float window[10];      // cosine-easing window of annealed_pos_enc (rnerf/model_utils.py:236-245) per octave
   const float* window_dev;   // the same 10 values in device memory, or NULL: read at run time, so a captured CUDA graph follows
                              // a changing annealed_alpha (train.py:350-351) instead of freezing the capture-time window
+  int dbg;                   // development aid (RNERF_SO3_TC_DEBUG; timing experiments only, results are wrong when set)
 };
 template <typename A>
 __device__ __forceinline__ float so3_window_at(const A& a, int k) {

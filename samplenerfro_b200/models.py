@@ -184,6 +184,19 @@ class NerfModel:
             self._pack_cache["so3_mlp"] = hit
         return hit[1]
 
+    def _so3_tc_packed(self, variables: Dict) -> torch.Tensor:
+        """hi / lo TF32 weight chunks of so3_mlp for the tensor-pipe evaluator of full-frame "all"-stage marches
+        (ops.so3_tc_pack), rebuilt only when a parameter changed."""
+        w = self._so3_packed(variables)
+        p = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+        sig = (w.data_ptr(),) + tuple((d["kernel"]._version, d["bias"]._version) for d in p.values())
+        hit = self._pack_cache.get("so3_tc")
+        if hit is None or hit[0] != sig:
+            with torch.no_grad():
+                hit = (sig, ops.so3_tc_pack(w, out=hit[1] if hit else None))
+            self._pack_cache["so3_tc"] = hit
+        return hit[1]
+
     # ------------------------------------------------------------------ stochastic inputs
     def draw_jitter(self, key, host: bool = False) -> torch.Tensor:
         """rnerf/models.py:240-242: arange(0, S, P) + randint(key, [Nc], 0, P) (also at eval, T9)."""
@@ -296,7 +309,8 @@ class NerfModel:
             with torch.no_grad():
                 so3 = (self._so3_packed(variables), window) if so3_p is not None else None
                 path = ops.march(self.table, self.ndim, self.nmin, self.nmax, origins, viewdirs, self.near, self.far, S,
-                                 bricks=self.bricks, compact=not need_grad, so3=so3)
+                                 bricks=self.bricks, compact=not need_grad, so3=so3,
+                                 so3_tc=self._so3_tc_packed(variables) if so3 is not None and not need_grad else None)
                 pos_c, dir_c, t_c, grad_c = ops.select(path, jit, want_grad=need_grad)
         with torch.no_grad():
             mask_c = self._bbox_mask(pos_c) if self.use_mask_bbox else None

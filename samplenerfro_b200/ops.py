@@ -121,12 +121,14 @@ def _window_args(window):
 
 def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n_steps: int,
           out: Optional[BentPath] = None, bricks: Optional[torch.Tensor] = None, compact: bool = False,
-          t_col: bool = True, so3: Optional[Tuple[torch.Tensor, Sequence[float]]] = None) -> BentPath:
+          t_col: bool = True, so3: Optional[Tuple[torch.Tensor, Sequence[float]]] = None,
+          so3_tc: Optional[torch.Tensor] = None) -> BentPath:
     """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124).  Returns the BentPath.
     `bricks` (from grid_bricks) lets the kernel skip the gathers in homogeneous space; results are bit-identical.
     `compact` drops idx_grad from the records (8 instead of 12 floats per step).
     `so3` = (so3_pack(...) weights, 10 window values): the "all" stage, where every step rotates grad n by the so3_mlp
-    prediction wherever |grad n| > 1e-3 (rnerf/eikonal_utils.py:34-35); None = radiance stage."""
+    prediction wherever |grad n| > 1e-3 (rnerf/eikonal_utils.py:34-35); None = radiance stage.
+    `so3_tc` = so3_tc_pack(weights): lets full-frame launches with compact records run so3_mlp on the tensor pipe."""
     _chk(table, "table"); origins = _chk(origins, "origins"); viewdirs = _chk(viewdirs, "viewdirs")
     if bricks is not None:
         _chk(bricks, "bricks")
@@ -147,7 +149,8 @@ def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n
         _chk(w, "so3 weights")
         win, win_dev = _window_args(window)
         check(_lib.load().rnerf_march_all_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
-                                              float(far), int(n_steps), W, _p(w), win, win_dev, _p(out.rec), _p(out.t), _stream()),
+                                              float(far), int(n_steps), W, _p(w), win, win_dev, _p(so3_tc), _p(out.rec), _p(out.t),
+                                              _stream()),
               "rnerf_march_all_fwd")
         return out
     check(_lib.load().rnerf_march_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
@@ -214,6 +217,26 @@ def so3_predict(w: torch.Tensor, window: Sequence[float], pts: torch.Tensor, con
     win, win_dev = _window_args(window)
     check(_lib.load().rnerf_so3_predict(_p(_chk(w, "so3 weights")), win, win_dev, _p(pts), _p(cond), pts.shape[0], _p(pred), _stream()),
           "rnerf_so3_predict")
+    return pred
+
+
+def so3_tc_pack(w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """hi / lo TF32 halves of the so3 kernels as the pre-swizzled chunks the tensor-pipe evaluator streams (so3_tc.cuh)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(lib.rnerf_so3_tc_packed_bytes(), device=w.device, dtype=torch.uint8)
+    check(lib.rnerf_so3_tc_pack(_p(_chk(w, "so3 weights")), _p(out), _stream()), "rnerf_so3_tc_pack")
+    return out
+
+
+def so3_predict_tc(packed: torch.Tensor, w: torch.Tensor, window, pts: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
+    """so3_predict through the tensor-pipe evaluator (tcgen05 kind::tf32, 3xTF32 split)."""
+    pts = _chk(pts.reshape(-1, 3).contiguous(), "pts"); cond = _chk(cond.reshape(-1, 3).contiguous(), "cond")
+    assert pts.shape == cond.shape
+    pred = torch.empty_like(pts)
+    win, win_dev = _window_args(window)
+    check(_lib.load().rnerf_so3_predict_tc(_p(_chk(packed, "so3 tc image", torch.uint8)), _p(_chk(w, "so3 weights")), win, win_dev,
+                                           _p(pts), _p(cond), pts.shape[0], _p(pred), _stream()), "rnerf_so3_predict_tc")
     return pred
 
 

@@ -34,6 +34,9 @@ def timeit(fn, n=5):
 path = ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True)
 t_rad = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, out=path))
 t_all = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, out=path, so3=so3))
+tc = model._so3_tc_packed(variables)
+t_tc = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, out=path, so3=so3, so3_tc=tc))
+print(f"all-stage march on the tensor pipe (march_tc_kernel): {t_tc:.3f} ms  (CUDA-core chain {t_all:.3f} ms, radiance {t_rad:.3f} ms)")
 del path
 n_ray = n_warp = n_cta = 0.0
 for i in range(0, a.rays // 128 * 128, 65536):

@@ -40,7 +40,8 @@ gen = torch.Generator().manual_seed(rank)
 idx = torch.randint(0, 640000, (B,), generator=gen)
 rays = utils.namedtuple_map(lambda r: r[idx].to(dev).contiguous(), flat)
 env = synthetic.blender_rays(synthetic.camera_pose(1.3, 0.8, 4.03), 128, 128, camera_angle_x=0.2)
-env = utils.namedtuple_map(lambda r: r.to(dev).contiguous(), env)
+_e0, _e1 = utils.shard_range(128, rank, world)       # the reference shards the whole batch dict, env patch included (utils.shard)
+env = utils.namedtuple_map(lambda r: r[_e0:_e1].to(dev).contiguous(), env)
 batch = {"rays": rays, "pixels": torch.rand(B, 3, generator=gen).to(dev), "env_rays": env, "annealed_alpha": 0.5}
 
 

@@ -281,3 +281,81 @@ def test_ior_stage_is_the_reference_s_degenerate_stage(cuda_lib, example_scene):
     with torch.no_grad():
         ret, _ = model.apply(variables, 1, 2, utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(16, 1).cuda()), False)
     assert torch.isfinite(ret[1][0]).all()
+
+
+def test_so3_tensor_pipe_evaluator_matches_cuda_core_and_oracle(cuda_lib):
+    """so3_mlp on tcgen05 kind::tf32 with the 3xTF32 split (csrc/so3_tc.cuh) against the fp32 CUDA-core chain and the oracle:
+    VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267) on free-standing points.  Stated tolerance 2e-6 relative to the
+    largest output (fp32-grade: the dropped lo*lo products are 2^-22 relative), ragged tile sizes included."""
+    from samplenerfro_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    so3 = O.init_small_mlp(gen, in_dim=60, out_std=0.05)
+    for d in so3.values():
+        d["bias"] = (torch.rand(d["bias"].shape, generator=gen) * 2 - 1) * 0.05
+    w = ops.so3_pack(H.to_cuda_params(so3))
+    packed = ops.so3_tc_pack(w)
+    assert packed.numel() == 32 * 16384
+    for N, alpha in ((1, 1.0), (63, 0.35), (65, 0.72), (5000, 0.5)):
+        pts = (torch.rand(N, 3, generator=gen) * 2 - 1) * 1.5
+        cond = torch.randn(N, 3, generator=gen)
+        window = [float(v) for v in O.cosine_easing_window(0, 9, 10, alpha * 10)]
+        a = ops.so3_predict(w, window, pts.cuda(), cond.cuda()).cpu()
+        b = ops.so3_predict_tc(packed, w, window, pts.cuda(), cond.cuda()).cpu()
+        ref = O.so3_predict(so3, pts, cond, alpha)
+        scale = ref.abs().max().item()
+        assert torch.isfinite(b).all()
+        assert (a - b).abs().max().item() < 2e-6 * scale, (N, (a - b).abs().max().item(), scale)
+        assert (b - ref).abs().max().item() < 1e-5 * scale, (N, (b - ref).abs().max().item(), scale)
+    # a device-resident window (what a captured training graph passes) gives the same numbers
+    wd = torch.tensor(window, device="cuda", dtype=torch.float32)
+    assert torch.equal(ops.so3_predict_tc(packed, w, wd, pts.cuda(), cond.cuda()).cpu(), b)
+
+
+def test_all_stage_full_frame_march_on_the_tensor_pipe(cuda_lib, monkeypatch):
+    """Launches large enough for lockstep CTAs (a frame) with compact records run so3_mlp on the tensor pipe
+    (march_tc_kernel, 256 rays per CTA).  Against the CUDA-core kernel on every ray (same inputs, RNERF_SO3_TC=0) and
+    against the oracle's scan on rays that cross the object: bent positions within the stated 1e-4 relative.  The batch
+    starts with a bundle of nearly parallel rays (> 64 active rays in one CTA-step: the multi-pass path) and has a ragged
+    tail (not a multiple of 256)."""
+    from samplenerfro_b200 import models, ops
+    n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
+    gen = torch.Generator().manual_seed(5)
+    ob = torch.tensor([0.3, -3.9, 0.5]) + torch.randn(300, 3, generator=gen) * 0.01
+    db = -ob + torch.randn(300, 3, generator=gen) * 0.02
+    cam = H.camera_rays(112, 112, seed=4)
+    o = torch.cat([ob, cam.origins.reshape(-1, 3)])[:12701].contiguous()
+    d = torch.cat([db, cam.viewdirs.reshape(-1, 3)])[:12701]
+    d = (d / d.norm(dim=-1, keepdim=True)).contiguous()
+    model, variables = models.construct_nerf(5, None, _flags(stage="all"), ndim, nmin, nmax, n)
+    so3 = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+    so3["Dense_4"]["kernel"].copy_((torch.randn(128, 3, generator=gen) * 0.05).cuda())
+    so3["Dense_4"]["bias"].copy_((torch.randn(3, generator=gen) * 0.2).cuda())
+    S = 768
+    w = ops.so3_pack(so3)
+    win = model.so3_window(0.8)
+    args = (model.table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, S)
+    tc = ops.march(*args, bricks=model.bricks, compact=True, so3=(w, win), so3_tc=ops.so3_tc_pack(w))
+    monkeypatch.setenv("RNERF_SO3_TC", "0")
+    cc = ops.march(*args, bricks=model.bricks, compact=True, so3=(w, win), so3_tc=ops.so3_tc_pack(w))
+    monkeypatch.delenv("RNERF_SO3_TC")
+    full = ops.march(*args, bricks=model.bricks, compact=False, so3=(w, win))        # full records: CUDA-core chain, has grad n
+    scale = cc.rec[..., 0:3].abs().max().item()
+    assert torch.isfinite(tc.rec).all()
+    err = (tc.rec[..., 0:3] - cc.rec[..., 0:3]).abs().max().item()
+    assert err < 2e-5 * scale, err                                   # tensor pipe vs CUDA cores: summation order + 2^-21 products
+    assert (tc.t - cc.t).abs().max().item() < 2e-5 * cc.t.abs().max().item()
+    assert torch.equal(tc.rec[..., 3], tc.t)
+    act = full.rec[..., 8:11].norm(dim=-1) > 1e-3
+    assert act[:256].sum(dim=0).max().item() > 64                    # the first CTA needs more than one 64-column pass
+    bent = act.any(dim=1).nonzero()[:, 0]
+    assert bent.numel() > 2000
+    pick = torch.cat([torch.arange(0, 300, 10), bent[torch.linspace(300, bent.numel() - 1, 34).long()].cpu()])
+    cpu = {k: {kk: vv.detach().cpu() for kk, vv in v.items()} for k, v in so3.items()}
+    opos, odir, odist, _, _ = O.march(O.build_table(n, ndim, nmin, nmax), ndim, nmin, nmax, o[pick], d[pick], 2.0, 6.0, S, stage="all",
+                                      so3_params=cpu, annealed_alpha=0.8)
+    assert (tc.rec[pick.cuda()][..., 0:3].cpu() - opos).abs().max().item() < 1e-4 * opos.abs().max().item()
+    assert (ops.path_dirs(tc.rec[pick.cuda()].contiguous()).cpu() - odir).abs().max().item() < 1e-4
+    assert (tc.t[pick.cuda()].cpu() - odist).abs().max().item() < 1e-4 * odist.abs().max().item()
+    # the rotation is visible: the radiance-stage path differs
+    plain = ops.march(*args, bricks=model.bricks, compact=True)
+    assert (plain.rec[..., 0:3] - tc.rec[..., 0:3]).abs().max().item() > 1e-3
