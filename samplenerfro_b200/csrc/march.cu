@@ -713,13 +713,20 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) so3_predict_tc_kernel(const ui
 constexpr int MTC_CW = 8;                            // carrier = worker warps
 constexpr int MTC_RAYS = MTC_CW * 32;
 constexpr int MTC_THREADS = MTC_RAYS + 64;
-constexpr int MTC_SLOTS = 4;
-constexpr int MTC_PITCH = STEPS_PER_FLUSH * 2 + 1;   // float4 per ray in the staging buffer (compact records + 1 pad)
+// Shared memory goes to the evaluator first: a 6-slot weight ring (three k-blocks: two of look-ahead, which is what hides the
+// ~1 us L2 -> SM latency of a chunk behind the ~0.4 us of MMAs per k-block; with four slots the chain ran at one TMA latency
+// per k-block).  The record staging is therefore half as deep as march_kernel's: flushes of 2 steps (64 contiguous bytes per
+// ray, still sector-complete) and a t column flushed every 8 steps (32 bytes per ray).
+constexpr int MTC_SLOTS = 6;
+constexpr int MTC_SPF = 2;                           // steps per record flush
+constexpr int MTC_TF = 8;                            // steps per t-column flush
+constexpr int MTC_PITCH = MTC_SPF * 2 + 1;           // float4 per ray in the staging buffer (compact records + 1 pad)
 struct MtcSmem {
   static constexpr uint32_t STAGE = TcSmem::RING + MTC_SLOTS * TC_A_BYTES;                  // [8 warps][32 * MTC_PITCH] float4
   static constexpr uint32_t TSTAGE = STAGE + MTC_CW * 32 * MTC_PITCH * 16;                   // [8 warps][T_FLUSH * 32] float
-  static constexpr uint32_t P_OFF = TSTAGE + MTC_CW * T_FLUSH * 32 * 4;                      // P[3][64], RAW[3][64]
-  static constexpr uint32_t CNT = P_OFF + 6 * TC_N * 4;                                      // counts[8] | exit flag | chunks consumed
+  static constexpr uint32_t P_OFF = TSTAGE + MTC_CW * MTC_TF * 32 * 4;                       // P[3][64], RAW[3][64]
+  static constexpr uint32_t W4_OFF = P_OFF + 6 * TC_N * 4;                                   // Dense_4 kernel [128][3] + bias[3] (+pad)
+  static constexpr uint32_t CNT = W4_OFF + (3 * SO3_W + 4) * 4;                              // counts[8] | exit flag | chunks consumed
   static constexpr uint32_t BAR_OFF = CNT + 64;                                               // full[4], empty[4], acc, act
   static constexpr uint32_t TMEM_SLOT = BAR_OFF + (2 * MTC_SLOTS + 2) * 8;
   static constexpr uint32_t BYTES = TMEM_SLOT + 16;
@@ -760,7 +767,7 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
   }
   const int idx = base + __popc(bal & ((1u << lane) - 1u));
   const float* bias = a.w + SO3_OFF_B;
-  const float* W4 = a.w + SO3_OFF_W4;
+  const float* W4 = reinterpret_cast<const float*>(smem + MtcSmem::W4_OFF);     // staged once per CTA: [128][3], then bias[3]
   const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
   const uint32_t tmem_lane = ev.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
   auto publish = [&] {                           // generic-proxy writes -> visible to the MMA; accumulators drained
@@ -779,20 +786,43 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
     if (mine) { P[col] = px; P[TC_N + col] = py; P[2 * TC_N + col] = pz; }
     mtc_workers_sync();
     // ---- encoding: warp w takes columns w, w + 8, ...; lane = feature (two per lane: f and f + 32) -> 128-byte row writes
-    for (int c = warp; c < n_here; c += MTC_CW) {
+    if (!(a.dbg & 4)) {
+      // per lane: features f = lane and lane + 32 (octave, sin | cos, axis are fixed per lane); two columns per iteration
+      // give four independent sinf chains
+      int kf[2], axf[2]; float ph[2], wf[2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        const int f = lane + 32 * hh;
-        float val = 0.f;
-        if (f < SO3_IN) {
-          const int k = f / 6, qq = f - 6 * k, ax = qq >= 3 ? qq - 3 : qq;
-          const float xb = mul(P[ax * TC_N + c], (float)(1 << k));
-          val = mul(sinf(qq >= 3 ? add(xb, 1.57079632679489661923f) : xb), so3_window_at(a, k));
+        const int f = lane + 32 * hh, k = f / 6, qq = f - 6 * k;
+        kf[hh] = k; axf[hh] = qq >= 3 ? qq - 3 : qq; ph[hh] = qq >= 3 ? 1.57079632679489661923f : 0.f;
+        wf[hh] = f < SO3_IN ? so3_window_at(a, k) : 0.f;
+      }
+      for (int c0 = warp; c0 < n_here; c0 += 2 * MTC_CW) {
+        float val[2][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = min(c0 + u * MTC_CW, TC_N - 1);            // (a column past n_here is garbage either way)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int f = lane + 32 * hh;
+            float v = 0.f;
+            if (f < SO3_IN) {
+              const float xb = mul(P[axf[hh] * TC_N + c], (float)(1 << kf[hh]));
+              v = mul(sinf(ph[hh] != 0.f ? add(xb, ph[hh]) : xb), wf[hh]);
+            }
+            val[u][hh] = v;
+          }
         }
-        const float vh = tf32_rn(val);
-        const uint32_t off = (uint32_t)hh * TC_B_BYTES + tc_sw128_off(c, lane);
-        *reinterpret_cast<float*>(smem + TcSmem::X_HI + off) = vh;
-        *reinterpret_cast<float*>(smem + TcSmem::X_LO + off) = val - vh;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = min(c0 + u * MTC_CW, TC_N - 1);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float vh = tf32_rn(val[u][hh]);
+            const uint32_t off = (uint32_t)hh * TC_B_BYTES + tc_sw128_off(c, lane);
+            *reinterpret_cast<float*>(smem + TcSmem::X_HI + off) = vh;
+            *reinterpret_cast<float*>(smem + TcSmem::X_LO + off) = val[u][hh] - vh;
+          }
+        }
       }
     }
     publish();
@@ -801,7 +831,7 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
     for (int l = 0; l < 4; ++l) {
       mbar_wait(ev.bar_acc, ev.acc_phase); ev.acc_phase ^= 1u;
       tc_fence_after();
-      if (has_cols) {
+      if (has_cols && !(a.dbg & 2)) {
         const float b = __ldg(bias + l * SO3_W + m);
         uint32_t v[32];
         tmem_ld32(tmem_lane, v);
@@ -830,6 +860,7 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
     tc_fence_before();
     mtc_workers_sync();                          // Dense_3 output complete in HS
     // ---- Dense_4 (128 -> 3): four threads per output, 32 inputs each, combined with two shuffles
+    if (!(a.dbg & 8))
     for (int it = tid; it < ((12 * n_here + 255) & ~255); it += MTC_RAYS) {
       const int e = it >> 2, kq = it & 3;
       float part = 0.f;
@@ -837,11 +868,11 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
       const int j = live ? e / n_here : 0, cc = live ? e - j * n_here : 0;
       if (live) {
 #pragma unroll 8
-        for (int k = kq * 32; k < kq * 32 + 32; ++k) part = fmaf(hs[k * TcSmem::HS_PITCH + cc], __ldg(W4 + 3 * k + j), part);
+        for (int k = kq * 32; k < kq * 32 + 32; ++k) part = fmaf(hs[k * TcSmem::HS_PITCH + cc], W4[3 * k + j], part);
       }
       part += __shfl_xor_sync(0xffffffffu, part, 1);
       part += __shfl_xor_sync(0xffffffffu, part, 2);
-      if (live && kq == 0) RAW[j * TC_N + cc] = part + __ldg(bias + 4 * SO3_W + j);
+      if (live && kq == 0) RAW[j * TC_N + cc] = part + W4[3 * SO3_W + j];
     }
     mtc_workers_sync();
     if (mine) { r0 = RAW[col]; r1 = RAW[TC_N + col]; r2 = RAW[2 * TC_N + col]; }
@@ -904,12 +935,18 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) march_tc_kernel(const float4* 
         if (stop) break;
         act_phase ^= 1u;
         tc_fence_after();
-        tc_issue_layer((int)layer, sbase, tmem_base, bar_full0, bar_empty0, MTC_SLOTS, c, bar_acc);
+        tc_issue_layer((int)layer, sbase, tmem_base, bar_full0, bar_empty0, MTC_SLOTS, c, bar_acc, so3.dbg);
         layer = (layer + 1) & 3u;
       }
     }
   } else {
     // ===================== the rays: 8 warps x 32 consecutive rays, in lockstep =====================
+    {                                            // Dense_4 kernel + bias into shared memory (the head reads them per evaluation)
+      float* w4s = reinterpret_cast<float*>(tc_smem + SL::W4_OFF);
+      for (int i = threadIdx.x; i < 3 * SO3_W + 3; i += MTC_RAYS)
+        w4s[i] = i < 3 * SO3_W ? __ldg(so3.w + SO3_OFF_W4 + i) : __ldg(so3.w + SO3_OFF_B + 4 * SO3_W + (i - 3 * SO3_W));
+      mtc_workers_sync();
+    }
     MtcEval ev;
     ev.smem = tc_smem; ev.tmem_base = tmem_base; ev.bar_acc = bar_acc; ev.bar_act = bar_act; ev.acc_phase = 0; ev.passes = 0;
     const int64_t warp_ray0 = blockIdx.x * (int64_t)MTC_RAYS + warp * 32;
@@ -922,17 +959,17 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) march_tc_kernel(const float4* 
     float t = near;
     float4* stage_w = reinterpret_cast<float4*>(tc_smem + SL::STAGE) + warp * 32 * MTC_PITCH;
     float4* my_stage = stage_w + lane * MTC_PITCH;
-    float* ts = reinterpret_cast<float*>(tc_smem + SL::TSTAGE) + warp * T_FLUSH * 32;
+    float* ts = reinterpret_cast<float*>(tc_smem + SL::TSTAGE) + warp * MTC_TF * 32;
     const int rays_here = (int)max((int64_t)0, min((int64_t)32, n_rays - warp_ray0));
     const int ray_stride4 = n_steps * 2;
     const bool t_vec = t_col != nullptr && (n_steps & 3) == 0 && (reinterpret_cast<uintptr_t>(t_col) & 15u) == 0;
-    constexpr int F4 = STEPS_PER_FLUSH * 2;      // float4 per ray per flush
-    const int fr = lane >> 3, fu = lane & 7;     // flush mapping: 4 rays x 8 units per iteration
+    constexpr int F4 = MTC_SPF * 2;              // float4 per ray per flush (64 bytes)
+    const int fr = lane >> 2, fu = lane & 3;     // flush mapping: 8 rays x 4 units per iteration
     float4* g_wr = path + warp_ray0 * (int64_t)ray_stride4;
 
-    for (int k0 = 0; k0 < n_steps; k0 += STEPS_PER_FLUSH) {
-      const int nk = min(STEPS_PER_FLUSH, n_steps - k0);
-      const int trow = k0 & (T_FLUSH - 1);
+    for (int k0 = 0; k0 < n_steps; k0 += MTC_SPF) {
+      const int nk = min(MTC_SPF, n_steps - k0);
+      const int trow = k0 & (MTC_TF - 1);
       for (int kk = 0; kk < nk; ++kk) {
         const float4 c = march_lookup<FAST>(table, mg, bricks, px, py, pz);
         my_stage[kk * 2 + 0] = make_float4(px, py, pz, t);
@@ -940,7 +977,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) march_tc_kernel(const float4* 
         ts[(trow + kk) * 32 + lane] = t;
         float gx = c.y, gy = c.z, gz = c.w;
         const bool act = live && sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;     // jnp.linalg.norm(idx_grad) > 1e-3
-        if (mtc_workers_or(act)) {
+        if (mtc_workers_or(act) && !(so3.dbg & 16)) {
           float r0, r1, r2;
           so3_eval_tc(so3, ev, warp, lane, act, px, py, pz, r0, r1, r2);
           if (act) so3_rotate(r0, r1, r2, gx, gy, gz);
@@ -952,13 +989,13 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) march_tc_kernel(const float4* 
         px = nx; py = ny; pz = nz;
       }
       __syncwarp();
-      if (t_col != nullptr && (trow + nk == T_FLUSH || k0 + nk >= n_steps)) {
+      if (t_col != nullptr && (trow + nk == MTC_TF || k0 + nk >= n_steps)) {
         const int filled = trow + nk, kbase = k0 - trow;
         float* tb = t_col + warp_ray0 * (int64_t)n_steps + kbase;
-        if (filled == T_FLUSH && t_vec) {
+        if (filled == MTC_TF && t_vec) {
 #pragma unroll
-          for (int it = 0; it < T_FLUSH / 4; ++it) {
-            const int e = it * 32 + lane, r = e >> 2, qd = e & 3;
+          for (int it = 0; it < MTC_TF / 4; ++it) {      // lanes 2r, 2r + 1 write the 8 staged steps of ray r (32 B, one sector)
+            const int e = it * 32 + lane, r = e >> 1, qd = e & 1;
             if (r < rays_here)
               __stcs(reinterpret_cast<float4*>(tb + r * n_steps + 4 * qd),
                      make_float4(ts[(4 * qd) * 32 + r], ts[(4 * qd + 1) * 32 + r], ts[(4 * qd + 2) * 32 + r], ts[(4 * qd + 3) * 32 + r]));
@@ -970,10 +1007,10 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) march_tc_kernel(const float4* 
           }
         }
       }
-      if (nk == STEPS_PER_FLUSH && rays_here == 32) {
+      if (nk == MTC_SPF && rays_here == 32) {
 #pragma unroll
-        for (int round = 0; round < 8; ++round) {
-          const int r = round * 4 + fr;
+        for (int round = 0; round < 4; ++round) {
+          const int r = round * 8 + fr;
           __stcs(g_wr + r * ray_stride4 + fu, stage_w[r * MTC_PITCH + fu]);
         }
       } else {
@@ -1089,6 +1126,7 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
     so3.w = so3_w;
     for (int k = 0; k < 10; ++k) so3.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
     so3.window_dev = so3_window_dev;
+    { const char* d = getenv("RNERF_SO3_TC_DEBUG"); so3.dbg = d ? atoi(d) : 0; }
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);

@@ -37,6 +37,11 @@ t_all = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 
 tc = model._so3_tc_packed(variables)
 t_tc = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, out=path, so3=so3, so3_tc=tc))
 print(f"all-stage march on the tensor pipe (march_tc_kernel): {t_tc:.3f} ms  (CUDA-core chain {t_all:.3f} ms, radiance {t_rad:.3f} ms)")
+for dbg in os.environ.get("PROBE_DBG", "").split():
+    os.environ["RNERF_SO3_TC_DEBUG"] = dbg
+    tt = timeit(lambda: ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, out=path, so3=so3, so3_tc=tc))
+    print(f"  RNERF_SO3_TC_DEBUG={dbg} (1 no MMA, 2 no epilogue, 4 no encoding, 8 no head, 16 no evaluation): {tt:.3f} ms")
+os.environ["RNERF_SO3_TC_DEBUG"] = "0"
 del path
 n_ray = n_warp = n_cta = 0.0
 for i in range(0, a.rays // 128 * 128, 65536):
@@ -46,8 +51,11 @@ for i in range(0, a.rays // 128 * 128, 65536):
     n_ray += act.sum().item()
     n_warp += act.reshape(-1, 32, 768).amax(dim=1).sum().item()
     n_cta += act.reshape(-1, 128, 768).amax(dim=1).sum().item()
+    n_cta256 = globals().get("n_cta256", 0.0) + act.reshape(-1, 256, 768).amax(dim=1).sum().item()
+    n_over64 = globals().get("n_over64", 0.0) + (act.reshape(-1, 256, 768).sum(dim=1) > 64).float().sum().item()
     del full, act
 tot = a.rays * 768
+print(f"256-ray CTAs: {n_cta256:.0f} CTA-steps need an evaluation, {n_over64:.0f} of them more than 64 columns")
 print(f"rays {a.rays}: radiance march {t_rad:.3f} ms, all-stage march {t_all:.3f} ms; |grad n| > 1e-3 at {100 * n_ray / tot:.2f} % of "
       f"ray-steps, {100 * n_warp * 32 / tot:.2f} % of warp-steps, {100 * n_cta * 128 / tot:.2f} % of CTA-steps = {n_cta:.0f} CTA "
       f"evaluations -> {(t_all - t_rad) * 1e3 * 148 / max(n_cta, 1):.1f} us per evaluation per SM; "
