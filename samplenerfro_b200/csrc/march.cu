@@ -673,12 +673,22 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) so3_predict_tc_kernel(const ui
         P[wt] = pts[3 * i]; P[TC_N + wt] = pts[3 * i + 1]; P[2 * TC_N + wt] = pts[3 * i + 2];
       }
       workers_sync();
-      if (!(so3.dbg & 4)) tc_write_encoding(so3, tc_smem, P, TC_N, wt, 128);
+      if (!(so3.dbg & 4)) {
+        const TcEncLane enc = tc_enc_lane(so3, lane);
+        for (int c = warp - 2; c < TC_N; c += 4)                 // one warp per column, lane = feature (and feature + 32)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+            tc_enc_store(tc_smem, c, hh, lane, tc_enc_value(enc, hh, lane, P[c], P[TC_N + c], P[2 * TC_N + c]));
+      }
       publish();
       for (int l = 0; l < 4; ++l) {
         mbar_wait(bar_acc, acc_phase); acc_phase ^= 1u;
         tc_fence_after();
-        if (!(so3.dbg & 2)) tc_epilogue(l, tc_smem, tmem_lane, q, lane, __ldg(bias + l * SO3_W + m));
+        if (!(so3.dbg & 2)) {
+          const float b = __ldg(bias + l * SO3_W + m);
+          tc_epilogue32(l, tc_smem, tmem_lane, m, 0, b);
+          tc_epilogue32(l, tc_smem, tmem_lane + 32, m, 32, b);
+        }
         if (l < 3) publish();
       }
       tc_fence_before();
@@ -725,7 +735,8 @@ struct MtcSmem {
   static constexpr uint32_t STAGE = TcSmem::RING + MTC_SLOTS * TC_A_BYTES;                  // [8 warps][32 * MTC_PITCH] float4
   static constexpr uint32_t TSTAGE = STAGE + MTC_CW * 32 * MTC_PITCH * 16;                   // [8 warps][T_FLUSH * 32] float
   static constexpr uint32_t P_OFF = TSTAGE + MTC_CW * MTC_TF * 32 * 4;                       // P[3][64], RAW[3][64]
-  static constexpr uint32_t W4_OFF = P_OFF + 6 * TC_N * 4;                                   // Dense_4 kernel [128][3] + bias[3] (+pad)
+  static constexpr uint32_t PART_OFF = P_OFF + 3 * TC_N * 4;                                 // head partial sums [4][3][64] (over RAW, + 2.25 KB)
+  static constexpr uint32_t W4_OFF = PART_OFF + 12 * TC_N * 4;                               // Dense_4 kernel [128][3] + bias[3] (+pad)
   static constexpr uint32_t CNT = W4_OFF + (3 * SO3_W + 4) * 4;                              // counts[8] | exit flag | chunks consumed
   static constexpr uint32_t BAR_OFF = CNT + 64;                                               // full[4], empty[4], acc, act
   static constexpr uint32_t TMEM_SLOT = BAR_OFF + (2 * MTC_SLOTS + 2) * 8;
@@ -752,7 +763,6 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
   uint8_t* smem = ev.smem;
   int* cnt = reinterpret_cast<int*>(smem + MtcSmem::CNT);
   float* P = reinterpret_cast<float*>(smem + MtcSmem::P_OFF);
-  float* RAW = P + 3 * TC_N;
   const float* hs = reinterpret_cast<const float*>(smem + TcSmem::HS);
   const int tid = warp * 32 + lane;
   const unsigned bal = __ballot_sync(0xffffffffu, act);
@@ -787,42 +797,20 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
     mtc_workers_sync();
     // ---- encoding: warp w takes columns w, w + 8, ...; lane = feature (two per lane: f and f + 32) -> 128-byte row writes
     if (!(a.dbg & 4)) {
-      // per lane: features f = lane and lane + 32 (octave, sin | cos, axis are fixed per lane); two columns per iteration
-      // give four independent sinf chains
-      int kf[2], axf[2]; float ph[2], wf[2];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int f = lane + 32 * hh, k = f / 6, qq = f - 6 * k;
-        kf[hh] = k; axf[hh] = qq >= 3 ? qq - 3 : qq; ph[hh] = qq >= 3 ? 1.57079632679489661923f : 0.f;
-        wf[hh] = f < SO3_IN ? so3_window_at(a, k) : 0.f;
-      }
+      // one warp per column, lane = feature f (and f + 32); two columns per iteration give four independent sinf chains
+      const TcEncLane enc = tc_enc_lane(a, lane);
       for (int c0 = warp; c0 < n_here; c0 += 2 * MTC_CW) {
         float val[2][2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int c = min(c0 + u * MTC_CW, TC_N - 1);            // (a column past n_here is garbage either way)
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int f = lane + 32 * hh;
-            float v = 0.f;
-            if (f < SO3_IN) {
-              const float xb = mul(P[axf[hh] * TC_N + c], (float)(1 << kf[hh]));
-              v = mul(sinf(ph[hh] != 0.f ? add(xb, ph[hh]) : xb), wf[hh]);
-            }
-            val[u][hh] = v;
-          }
+          for (int hh = 0; hh < 2; ++hh) val[u][hh] = tc_enc_value(enc, hh, lane, P[c], P[TC_N + c], P[2 * TC_N + c]);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = min(c0 + u * MTC_CW, TC_N - 1);
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const float vh = tf32_rn(val[u][hh]);
-            const uint32_t off = (uint32_t)hh * TC_B_BYTES + tc_sw128_off(c, lane);
-            *reinterpret_cast<float*>(smem + TcSmem::X_HI + off) = vh;
-            *reinterpret_cast<float*>(smem + TcSmem::X_LO + off) = val[u][hh] - vh;
-          }
-        }
+          for (int hh = 0; hh < 2; ++hh) tc_enc_store(smem, min(c0 + u * MTC_CW, TC_N - 1), hh, lane, val[u][hh]);
       }
     }
     publish();
@@ -831,51 +819,34 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
     for (int l = 0; l < 4; ++l) {
       mbar_wait(ev.bar_acc, ev.acc_phase); ev.acc_phase ^= 1u;
       tc_fence_after();
-      if (has_cols && !(a.dbg & 2)) {
-        const float b = __ldg(bias + l * SO3_W + m);
-        uint32_t v[32];
-        tmem_ld32(tmem_lane, v);
-        tmem_ld_wait();
-        if (l < 3) {
-          uint8_t* hi = smem + TcSmem::H_HI + q * TC_B_BYTES;
-          uint8_t* lo = smem + TcSmem::H_LO + q * TC_B_BYTES;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float h = fmaxf(__uint_as_float(v[j]) + b, 0.f);
-            const float hh = tf32_rn(h);
-            const uint32_t off = tc_sw128_off(half * 32 + j, lane);
-            *reinterpret_cast<float*>(hi + off) = hh;
-            *reinterpret_cast<float*>(lo + off) = h - hh;
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(smem + TcSmem::HS) + m * TcSmem::HS_PITCH + half * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(fmaxf(__uint_as_float(v[j]) + b, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b, 0.f),
-                                                            fmaxf(__uint_as_float(v[j + 2]) + b, 0.f), fmaxf(__uint_as_float(v[j + 3]) + b, 0.f));
-        }
-      }
+      if (has_cols && !(a.dbg & 2)) tc_epilogue32(l, smem, tmem_lane, m, half * 32, __ldg(bias + l * SO3_W + m));
       if (l < 3) publish();
     }
     tc_fence_before();
     mtc_workers_sync();                          // Dense_3 output complete in HS
-    // ---- Dense_4 (128 -> 3): four threads per output, 32 inputs each, combined with two shuffles
-    if (!(a.dbg & 8))
-    for (int it = tid; it < ((12 * n_here + 255) & ~255); it += MTC_RAYS) {
-      const int e = it >> 2, kq = it & 3;
-      float part = 0.f;
-      const bool live = e < 3 * n_here;
-      const int j = live ? e / n_here : 0, cc = live ? e - j * n_here : 0;
-      if (live) {
+    // ---- Dense_4 (128 -> 3): thread (column cc = tid mod 64, k-quarter kq = tid / 64) sums 32 inputs for the three outputs
+    // (a warp reads 32 consecutive columns of a row: conflict-free; the weights are broadcasts), partial sums meet in PART
+    float* PART = reinterpret_cast<float*>(smem + MtcSmem::PART_OFF);         // [4 quarters][3][64]
+    if (!(a.dbg & 8)) {
+      const int cc = tid & 63, kq = tid >> 6;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+      if (cc < n_here) {
 #pragma unroll 8
-        for (int k = kq * 32; k < kq * 32 + 32; ++k) part = fmaf(hs[k * TcSmem::HS_PITCH + cc], W4[3 * k + j], part);
+        for (int k = kq * 32; k < kq * 32 + 32; ++k) {
+          const float h = hs[k * TcSmem::HS_PITCH + cc];
+          s0 = fmaf(h, W4[3 * k], s0); s1 = fmaf(h, W4[3 * k + 1], s1); s2 = fmaf(h, W4[3 * k + 2], s2);
+        }
       }
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      if (live && kq == 0) RAW[j * TC_N + cc] = part + W4[3 * SO3_W + j];
+      PART[(kq * 3 + 0) * TC_N + cc] = s0; PART[(kq * 3 + 1) * TC_N + cc] = s1; PART[(kq * 3 + 2) * TC_N + cc] = s2;
     }
     mtc_workers_sync();
-    if (mine) { r0 = RAW[col]; r1 = RAW[TC_N + col]; r2 = RAW[2 * TC_N + col]; }
+    if (mine) {
+      float r[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        r[j] = ((PART[j * TC_N + col] + PART[(3 + j) * TC_N + col]) + (PART[(6 + j) * TC_N + col] + PART[(9 + j) * TC_N + col])) + W4[3 * SO3_W + j];
+      r0 = r[0]; r1 = r[1]; r2 = r[2];
+    }
     ++ev.passes;
   }
 }
@@ -1251,7 +1222,7 @@ extern "C" size_t rnerf_so3_tc_packed_bytes(void) { return TC_PACKED_BYTES; }
 extern "C" int rnerf_so3_tc_pack(const float* so3_w, void* packed, void* stream) {
   RNERF_REQUIRE_PTR(so3_w); RNERF_REQUIRE_PTR(packed);
   RNERF_REQUIRE(aligned16(packed), RNERF_E_ALIGN, "rnerf_so3_tc_pack: packed must be 16-byte aligned");
-  so3_tc_pack_kernel<<<(TC_NKB * SO3_W * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(so3_w, (uint8_t*)packed);
+  so3_tc_pack_kernel<<<(TC_NKB * SO3_W * TC_KBLK + 255) / 256, 256, 0, (cudaStream_t)stream>>>(so3_w, (uint8_t*)packed);
   count_launch();
   return check_launch("rnerf_so3_tc_pack");
 }

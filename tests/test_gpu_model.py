@@ -284,9 +284,9 @@ def test_ior_stage_is_the_reference_s_degenerate_stage(cuda_lib, example_scene):
 
 
 def test_so3_tensor_pipe_evaluator_matches_cuda_core_and_oracle(cuda_lib):
-    """so3_mlp on tcgen05 kind::tf32 with the 3xTF32 split (csrc/so3_tc.cuh) against the fp32 CUDA-core chain and the oracle:
+    """so3_mlp on tcgen05 kind::f16 with fp16 hi/lo split operands (csrc/so3_tc.cuh) against the fp32 CUDA-core chain and the oracle:
     VoxMLP.wrapper_grad_mlp (rnerf/ior_utils.py:225-267) on free-standing points.  Stated tolerance 2e-6 relative to the
-    largest output (fp32-grade: the dropped lo*lo products are 2^-22 relative), ragged tile sizes included."""
+    largest output (fp32-grade: 22-bit operands, the dropped lo*lo products are 2^-22 relative), ragged tile sizes included."""
     from samplenerfro_b200 import ops
     gen = torch.Generator().manual_seed(0)
     so3 = O.init_small_mlp(gen, in_dim=60, out_std=0.05)
@@ -294,7 +294,7 @@ def test_so3_tensor_pipe_evaluator_matches_cuda_core_and_oracle(cuda_lib):
         d["bias"] = (torch.rand(d["bias"].shape, generator=gen) * 2 - 1) * 0.05
     w = ops.so3_pack(H.to_cuda_params(so3))
     packed = ops.so3_tc_pack(w)
-    assert packed.numel() == 32 * 16384
+    assert packed.numel() == 16 * 16384          # 8 k-blocks of 64 x (hi, lo) x [128 neurons x 64 k] fp16
     for N, alpha in ((1, 1.0), (63, 0.35), (65, 0.72), (5000, 0.5)):
         pts = (torch.rand(N, 3, generator=gen) * 2 - 1) * 1.5
         cond = torch.randn(N, 3, generator=gen)
