@@ -595,9 +595,9 @@ __global__ void __launch_bounds__(SO3_THREADS, 2) so3_predict_kernel(const float
 // The same on the tensor pipe (so3_tc.cuh): persistent CTAs, 64 points per pass.  Warp 0: weight producer (TMA ring), warp 1:
 // MMA issuer, warps 2-5: encoding / epilogue / head (thread = TMEM lane = neuron).  Stand-alone form of the evaluator the
 // "all"-stage march uses; also what pins its arithmetic against the CUDA-core chain (tests/test_gpu_kernels.py).
-constexpr int TCP_THREADS = 192, TCP_SLOTS = 6;
+constexpr int TCP_THREADS = 192, TCP_SLOTS = 3;
 struct TcPredictSmem {
-  static constexpr uint32_t P_OFF = TcSmem::RING + TCP_SLOTS * TC_A_BYTES;      // positions [3][64], then raw [3][64]
+  static constexpr uint32_t P_OFF = TcSmem::RING + TCP_SLOTS * TC_CHUNK_BYTES;  // positions [3][64], then raw [3][64]
   static constexpr uint32_t BAR_OFF = P_OFF + 6 * TC_N * 4;                      // full[6], empty[6], acc, act
   static constexpr uint32_t TMEM_SLOT = BAR_OFF + (2 * TCP_SLOTS + 2) * 8;
   static constexpr uint32_t BYTES = TMEM_SLOT + 16;
@@ -634,8 +634,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) so3_predict_tc_kernel(const ui
         for (int i = 0; i < TC_NCHUNK; ++i, ++c) {
           const uint32_t s = c % TCP_SLOTS;
           mbar_wait(bar_empty0 + 8 * s, ((c / TCP_SLOTS) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(bar_full0 + 8 * s, TC_A_BYTES);
-          tma_bulk_g2s(sbase + TcSmem::RING + s * TC_A_BYTES, packed + (size_t)i * TC_A_BYTES, TC_A_BYTES, bar_full0 + 8 * s);
+          mbar_arrive_expect_tx(bar_full0 + 8 * s, TC_CHUNK_BYTES);
+          tma_bulk_g2s(sbase + TcSmem::RING + s * TC_CHUNK_BYTES, packed + (size_t)i * TC_CHUNK_BYTES, TC_CHUNK_BYTES, bar_full0 + 8 * s);
         }
     }
   } else if (warp == 1) {
@@ -723,16 +723,16 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) so3_predict_tc_kernel(const ui
 constexpr int MTC_CW = 8;                            // carrier = worker warps
 constexpr int MTC_RAYS = MTC_CW * 32;
 constexpr int MTC_THREADS = MTC_RAYS + 64;
-// Shared memory goes to the evaluator first: a 6-slot weight ring (three k-blocks: two of look-ahead, which is what hides the
-// ~1 us L2 -> SM latency of a chunk behind the ~0.4 us of MMAs per k-block; with four slots the chain ran at one TMA latency
-// per k-block).  The record staging is therefore half as deep as march_kernel's: flushes of 2 steps (64 contiguous bytes per
-// ray, still sector-complete) and a t column flushed every 8 steps (32 bytes per ray).
-constexpr int MTC_SLOTS = 6;
+// Shared memory goes to the evaluator first: a 3-slot ring of 32 KB weight chunks (one k-block, hi and lo halves, per chunk:
+// the k-block in use plus two of look-ahead, which is what hides the ~1 us L2 -> SM latency of a chunk behind the MMAs of a
+// k-block).  The record staging is therefore half as deep as march_kernel's: flushes of 2 steps (64 contiguous bytes per ray,
+// still sector-complete) and a t column flushed every 8 steps (32 bytes per ray).
+constexpr int MTC_SLOTS = 3;                         // 32 KB each: the k-block in use + two of look-ahead
 constexpr int MTC_SPF = 2;                           // steps per record flush
 constexpr int MTC_TF = 8;                            // steps per t-column flush
 constexpr int MTC_PITCH = MTC_SPF * 2 + 1;           // float4 per ray in the staging buffer (compact records + 1 pad)
 struct MtcSmem {
-  static constexpr uint32_t STAGE = TcSmem::RING + MTC_SLOTS * TC_A_BYTES;                  // [8 warps][32 * MTC_PITCH] float4
+  static constexpr uint32_t STAGE = TcSmem::RING + MTC_SLOTS * TC_CHUNK_BYTES;              // [8 warps][32 * MTC_PITCH] float4
   static constexpr uint32_t TSTAGE = STAGE + MTC_CW * 32 * MTC_PITCH * 16;                   // [8 warps][T_FLUSH * 32] float
   static constexpr uint32_t P_OFF = TSTAGE + MTC_CW * MTC_TF * 32 * 4;                       // P[3][64], RAW[3][64]
   static constexpr uint32_t PART_OFF = P_OFF + 3 * TC_N * 4;                                 // head partial sums [4][3][64] (over RAW, + 2.25 KB)
@@ -889,8 +889,9 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) march_tc_kernel(const float4* 
         while (!mbar_try_wait(bar_empty0 + 8 * s, par))
           if (flags[0]) { stop = true; break; }
         if (stop) break;
-        mbar_arrive_expect_tx(bar_full0 + 8 * s, TC_A_BYTES);
-        tma_bulk_g2s(sbase + TcSmem::RING + s * TC_A_BYTES, packed + (size_t)(c % TC_NCHUNK) * TC_A_BYTES, TC_A_BYTES, bar_full0 + 8 * s);
+        mbar_arrive_expect_tx(bar_full0 + 8 * s, TC_CHUNK_BYTES);
+        tma_bulk_g2s(sbase + TcSmem::RING + s * TC_CHUNK_BYTES, packed + (size_t)(c % TC_NCHUNK) * TC_CHUNK_BYTES, TC_CHUNK_BYTES,
+                     bar_full0 + 8 * s);
         ++c;
       }
       // chunks fetched ahead for an evaluation that never came must have landed before the CTA may exit

@@ -30,8 +30,9 @@ constexpr int TC_KBLK = 64;                       // k per k-block: one 128-byte
 constexpr int TC_A_BYTES = SO3_W * 128;           // one weight chunk: [128 neurons][64 k] x 2 B = 16 KB (hi or lo)
 constexpr int TC_B_BYTES = TC_N * 128;            // one activation k-block, hi or lo: [64 columns][64 k] x 2 B = 8 KB
 constexpr int TC_NKB = 1 + 2 + 2 + 3;             // k-blocks of the four hidden layers (K = 64, 128, 128, 128 + 64)
-constexpr int TC_NCHUNK = 2 * TC_NKB;             // (k-block, hi | lo) chunks of 16 KB, in the order the MMA issuer consumes them
-constexpr size_t TC_PACKED_BYTES = (size_t)TC_NCHUNK * TC_A_BYTES;      // 256 KB
+constexpr int TC_NCHUNK = TC_NKB;                 // one 32 KB chunk per k-block (hi half, then lo half), in consumption order
+constexpr int TC_CHUNK_BYTES = 2 * TC_A_BYTES;    // -> one TMA copy and one full / empty barrier pair per k-block
+constexpr size_t TC_PACKED_BYTES = (size_t)TC_NCHUNK * TC_CHUNK_BYTES;  // 256 KB
 __host__ __device__ constexpr int tc_layer_kb(int l) { return l == 0 ? 1 : (l == 3 ? 3 : 2); }
 __host__ __device__ constexpr int tc_layer_kb0(int l) { return l == 0 ? 0 : (l == 1 ? 1 : (l == 2 ? 3 : 5)); }
 
@@ -88,7 +89,7 @@ struct TcSmem {
   static constexpr uint32_t H_LO = H_HI + 2 * TC_B_BYTES;               //                      hidden activations, lo
   static constexpr uint32_t HS = H_LO + 2 * TC_B_BYTES;                 // [128][68] fp32: the last hidden layer, for the 3-wide head
   static constexpr int HS_PITCH = TC_N + 4;
-  static constexpr uint32_t RING = (HS + SO3_W * HS_PITCH * 4 + 1023u) & ~1023u;      // [n_slots][16 KB] weight chunks
+  static constexpr uint32_t RING = (HS + SO3_W * HS_PITCH * 4 + 1023u) & ~1023u;      // [n_slots][32 KB] weight chunks (hi | lo)
 };
 
 // One MMA pass of layer `l`: everything the issuing thread does between "activations ready" and "accumulators committed".
@@ -99,17 +100,15 @@ __device__ __forceinline__ void tc_issue_layer(int l, uint32_t sbase, uint32_t t
   const int nkb = tc_layer_kb(l);
   bool started = false;
   for (int kb = 0; kb < nkb; ++kb) {
-    const uint32_t s_hi = c % (uint32_t)n_slots, s_lo = (c + 1) % (uint32_t)n_slots;
-    const uint32_t ph_hi = (c / (uint32_t)n_slots) & 1u, ph_lo = ((c + 1) / (uint32_t)n_slots) & 1u;
-    mbar_wait(bar_full0 + 8 * s_hi, ph_hi);
-    mbar_wait(bar_full0 + 8 * s_lo, ph_lo);
+    const uint32_t s = c % (uint32_t)n_slots;
+    mbar_wait(bar_full0 + 8 * s, (c / (uint32_t)n_slots) & 1u);
     tc_fence_after();
     const bool from_x = (l == 0) || (l == 3 && kb >= 2);
     const int bkb = (l == 3 && kb >= 2) ? kb - 2 : kb;
     const uint32_t b_hi_addr = sbase + (from_x ? TcSmem::X_HI : TcSmem::H_HI) + bkb * TC_B_BYTES;
     const uint32_t b_lo_addr = sbase + (from_x ? TcSmem::X_LO : TcSmem::H_LO) + bkb * TC_B_BYTES;
-    const uint64_t a_hi_d = make_sw128_desc(sbase + TcSmem::RING + s_hi * TC_A_BYTES);
-    const uint64_t a_lo_d = make_sw128_desc(sbase + TcSmem::RING + s_lo * TC_A_BYTES);
+    const uint64_t a_hi_d = make_sw128_desc(sbase + TcSmem::RING + s * TC_CHUNK_BYTES);
+    const uint64_t a_lo_d = make_sw128_desc(sbase + TcSmem::RING + s * TC_CHUNK_BYTES + TC_A_BYTES);
     const uint64_t b_hi_d = make_sw128_desc(b_hi_addr), b_lo_d = make_sw128_desc(b_lo_addr);
     const uint32_t dh = (uint32_t)(a_hi_d >> 32);
     if (!(dbg & 1))
@@ -120,9 +119,8 @@ __device__ __forceinline__ void tc_issue_layer(int l, uint32_t sbase, uint32_t t
       umma_f16_lohi(tmem_d, (uint32_t)a_hi_d + 2u * ks, (uint32_t)b_hi_d + 2u * ks, dh, idesc, 1u);
     }
     started = true;
-    umma_commit(bar_empty0 + 8 * s_hi);
-    umma_commit(bar_empty0 + 8 * s_lo);
-    c += 2;
+    umma_commit(bar_empty0 + 8 * s);
+    c += 1;
   }
   umma_commit(bar_acc);
 }
