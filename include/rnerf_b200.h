@@ -134,6 +134,12 @@ int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed, const uint
                     int64_t n_samples, uint16_t* dz_out, void* stream);
 int rnerf_mlp_wgrad(const uint16_t* x, int ldx, int x_cols, int kx_valid, const uint16_t* dz, int n, int64_t n_samples,
                     float* gw, float* gb, void* stream);
+/* rnerf_mlp_wgrad_batched: up to 16 rnerf_mlp_wgrad jobs over the same n_samples rows in ONE launch (per-job arguments as
+ * arrays of length n_jobs; gb[j] may be NULL): all the layers of one MLP's backward.  The SMs are divided between the jobs in
+ * proportion to the bytes each streams. */
+int rnerf_mlp_wgrad_batched(int n_jobs, const uint16_t* const* x, const int* ldx, const int* x_cols, const int* kx_valid,
+                            const uint16_t* const* dz, const int* n, int64_t n_samples, float* const* gw, float* const* gb,
+                            void* stream);
 int rnerf_mlp_head_grad(const uint16_t* layer_out, const float* d_raw, int64_t n_samples, float* out_rgb_head,
                         float* out_sigma_head, void* stream);
 

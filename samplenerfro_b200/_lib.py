@@ -51,6 +51,9 @@ SIGNATURES = {
     "rnerf_mlp_dgrad_pack": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "rnerf_mlp_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_i64, C.c_void_p, C.c_void_p]),
     "rnerf_mlp_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, c_i64, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_mlp_wgrad_batched": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int), c_i64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.c_void_p]),
     "rnerf_mlp_head_grad": (C.c_int, [C.c_void_p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_generate_rays": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                       C.c_double, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),

@@ -365,8 +365,23 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 
 // Tile layout in a stage: [operand (X, dZ)][k-group kb = 0..7][MN-atom mm = 0..3][8 rows x 128 B], i.e. for a row r
 // (= GEMM K index) and column c: atom (kb = r/8, mm = c/64), row-in-atom kk = r%8, 16-byte unit (c%64)/8 ^ kk.
-__global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArgs a) {
+// A launch carries up to WG_MAX_JOBS independent weight-gradient GEMMs (all the layers of one MLP's backward): CTA b works
+// on job j with cta0[j] <= b < cta0[j + 1].  One launch per MLP instead of one per layer: no launch gaps or per-launch tails
+// between the layers, and for small batches (a 512-ray shard of an 8-GPU step) one wave of CTAs instead of 13 launches that
+// each pay the fixed costs (TMEM allocation, the 256 KB accumulator flush) on every SM.
+constexpr int WG_MAX_JOBS = 16;
+struct WgradBatch {
+  WgradArgs job[WG_MAX_JOBS];
+  int cta0[WG_MAX_JOBS + 1];
+  int n_jobs;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_constant__ WgradBatch batch) {
   using SL = WgradSmem;
+  int jb = 0;
+  while (jb + 1 < batch.n_jobs && (int)blockIdx.x >= batch.cta0[jb + 1]) ++jb;
+  const WgradArgs& a = batch.job[jb];
+  const int cta = (int)blockIdx.x - batch.cta0[jb];
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   if ((sbase & 1023u) != 0) __trap();
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const WgradArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int64_t row0 = (int64_t)blockIdx.x * a.rows_per_cta;
+  const int64_t row0 = (int64_t)cta * a.rows_per_cta;
   const int64_t row1 = min(row0 + a.rows_per_cta, a.n_samples);
   const int n_steps = row1 > row0 ? (int)((row1 - row0 + WG_ROWS - 1) / WG_ROWS) : 0;
   const int xatoms = a.kx / 64, zatoms = a.n / 64;  // MN-atoms per K-group
@@ -626,14 +641,76 @@ extern "C" int rnerf_mlp_wgrad(const uint16_t* x, int ldx, int x_cols, int kx_va
   }
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  WgradArgs a;
+  WgradBatch b;
+  memset(&b, 0, sizeof(b));
+  WgradArgs& a = b.job[0];
   a.X = (const __nv_bfloat16*)x; a.dZ = (const __nv_bfloat16*)dz; a.ldx = ldx; a.kx = kx; a.x_cols = x_cols; a.kx_valid = kx_valid; a.n = n;
   a.n_samples = n_samples; a.gW = gw; a.gb = gb;
   int64_t per = (n_samples + n_sm - 1) / n_sm;
   per = (per + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
   a.rows_per_cta = (int)per;
   const unsigned grid = (unsigned)((n_samples + per - 1) / per);
-  mlp_wgrad_kernel<<<grid, WG_THREADS, WgradSmem::BYTES, (cudaStream_t)stream>>>(a);
+  b.n_jobs = 1; b.cta0[0] = 0; b.cta0[1] = (int)grid;
+  mlp_wgrad_kernel<<<grid, WG_THREADS, WgradSmem::BYTES, (cudaStream_t)stream>>>(b);
   count_launch();
   return check_launch("rnerf_mlp_wgrad");
+}
+
+// All weight-gradient GEMMs of one MLP's backward in ONE launch (same per-job arguments as rnerf_mlp_wgrad, as arrays).
+// The SMs are divided between the jobs in proportion to the bytes each job streams (rows x (x_cols + n)), one CTA per SM.
+extern "C" int rnerf_mlp_wgrad_batched(int n_jobs, const uint16_t* const* x, const int* ldx, const int* x_cols, const int* kx_valid,
+                                       const uint16_t* const* dz, const int* n, int64_t n_samples, float* const* gw,
+                                       float* const* gb, void* stream) {
+  if (n_samples <= 0 || n_jobs <= 0) return 0;
+  RNERF_REQUIRE(n_jobs <= WG_MAX_JOBS, RNERF_E_SHAPE, "rnerf_mlp_wgrad_batched: at most %d jobs per launch (got %d)", WG_MAX_JOBS, n_jobs);
+  RNERF_REQUIRE_PTR(x); RNERF_REQUIRE_PTR(ldx); RNERF_REQUIRE_PTR(x_cols); RNERF_REQUIRE_PTR(kx_valid); RNERF_REQUIRE_PTR(dz);
+  RNERF_REQUIRE_PTR(n); RNERF_REQUIRE_PTR(gw); RNERF_REQUIRE_PTR(gb);
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradSmem::BYTES);
+  if (e != cudaSuccess) { set_error("rnerf_mlp_wgrad_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  WgradBatch b;
+  memset(&b, 0, sizeof(b));
+  double total = 0.0;
+  for (int j = 0; j < n_jobs; ++j) {
+    RNERF_REQUIRE(x[j] != nullptr && dz[j] != nullptr && gw[j] != nullptr, RNERF_E_NULL, "rnerf_mlp_wgrad_batched: job %d has a null pointer", j);
+    RNERF_REQUIRE(x_cols[j] >= 8 && x_cols[j] <= 256 && (x_cols[j] % 8) == 0 && x_cols[j] <= ldx[j] && (ldx[j] % 8) == 0 && kx_valid[j] >= 1 &&
+                  kx_valid[j] <= x_cols[j], RNERF_E_SHAPE, "rnerf_mlp_wgrad_batched: job %d: bad x_cols / ldx / kx_valid", j);
+    RNERF_REQUIRE(n[j] == 128 || n[j] == 256, RNERF_E_SHAPE, "rnerf_mlp_wgrad_batched: job %d: n must be 128 or 256", j);
+    RNERF_REQUIRE(aligned16(x[j]) && aligned16(dz[j]), RNERF_E_ALIGN, "rnerf_mlp_wgrad_batched: job %d: x/dz must be 16-byte aligned", j);
+    total += (double)(x_cols[j] + n[j]);
+  }
+  // CTAs per job.  Large batches (>= 32 pipeline stages per CTA even when a job is cut over every SM): every job gets all the
+  // SMs, jobs in sequence -- the schedule of 13 separate launches without their gaps and tails (measured: a single wave with
+  // ~60 000 rows per CTA is slower, the per-stage floor of the short-row jobs unbalances it).  Small batches (a 512-ray shard
+  // of an 8-GPU step): one wave, the SMs divided in proportion to the bytes each job streams, so the fixed costs (TMEM
+  // allocation, the 256 KB accumulator flush) are paid once per SM instead of 13 times.
+  int ctas[WG_MAX_JOBS], sum = 0;
+  const int64_t max_ctas = (n_samples + WG_ROWS - 1) / WG_ROWS;
+  const bool big = n_samples >= (int64_t)n_sm * WG_ROWS * 32;
+  for (int j = 0; j < n_jobs; ++j) {
+    int c = big ? n_sm : (int)((double)n_sm * (x_cols[j] + n[j]) / total);
+    if (c < 1) c = 1;
+    if (c > max_ctas) c = (int)max_ctas;
+    ctas[j] = c; sum += c;
+  }
+  for (int j = 0; !big && sum < n_sm && j < n_jobs; ++j)  // hand the rounding remainder to the largest jobs first
+    if (n[j] == 256 && x_cols[j] == 256 && ctas[j] < max_ctas) { ++ctas[j]; ++sum; }
+  int c0 = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    WgradArgs& a = b.job[j];
+    a.X = (const __nv_bfloat16*)x[j]; a.dZ = (const __nv_bfloat16*)dz[j]; a.ldx = ldx[j]; a.kx = x_cols[j] <= 128 ? 128 : 256;
+    a.x_cols = x_cols[j]; a.kx_valid = kx_valid[j]; a.n = n[j]; a.n_samples = n_samples; a.gW = gw[j]; a.gb = gb[j];
+    int64_t per = (n_samples + ctas[j] - 1) / ctas[j];
+    per = (per + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+    a.rows_per_cta = (int)per;
+    b.cta0[j] = c0;
+    c0 += (int)((n_samples + per - 1) / per);
+  }
+  b.cta0[n_jobs] = c0;
+  b.n_jobs = n_jobs;
+  mlp_wgrad_kernel<<<(unsigned)c0, WG_THREADS, WgradSmem::BYTES, (cudaStream_t)stream>>>(b);
+  count_launch();
+  return check_launch("rnerf_mlp_wgrad_batched");
 }

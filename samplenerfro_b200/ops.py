@@ -483,6 +483,21 @@ def mlp_wgrad(x: torch.Tensor, x_cols: int, kx_valid: int, dz: torch.Tensor, n: 
           "rnerf_mlp_wgrad")
 
 
+def mlp_wgrad_batched(jobs, M: int) -> None:
+    """All weight-gradient GEMMs of one MLP's backward in one launch.  jobs: list of (x, x_cols, kx_valid, dz, n, gw, gb) with
+    the meaning of mlp_wgrad's arguments (x / dz may be column-offset views of [M, ld] bf16 tensors)."""
+    nj = len(jobs)
+    xs, ldx, xc, kv, dzs, ns, gws, gbs = [], [], [], [], [], [], [], []
+    for x, x_cols, kx_valid, dz, n, gw, gb in jobs:
+        assert x.dtype == torch.bfloat16 and dz.dtype == torch.bfloat16 and x.is_contiguous() and dz.is_contiguous()
+        assert gw.dtype == torch.float32 and gw.is_contiguous() and gw.shape == (kx_valid, n) and x.shape[0] == M and dz.shape == (M, 256)
+        xs.append(x.data_ptr()); ldx.append(x.shape[1]); xc.append(int(x_cols)); kv.append(int(kx_valid))
+        dzs.append(dz.data_ptr()); ns.append(int(n)); gws.append(gw.data_ptr()); gbs.append(0 if gb is None else gb.data_ptr())
+    vp, ip = C.c_void_p * nj, C.c_int * nj
+    check(_lib.load().rnerf_mlp_wgrad_batched(nj, vp(*xs), ip(*ldx), ip(*xc), ip(*kv), vp(*dzs), ip(*ns), int(M), vp(*gws), vp(*gbs),
+                                              _stream()), "rnerf_mlp_wgrad_batched")
+
+
 def mlp_input_grad_pack(k0: torch.Tensor, k5: torch.Tensor, k10: torch.Tensor) -> torch.Tensor:
     """Transposed [640][64] fp32 image of the weight rows the encodings multiply (Dense_0, Dense_5[256:], Dense_10[256:])."""
     lib = _lib.load()
@@ -523,14 +538,12 @@ def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None, input_gra
         gB = [torch.zeros_like(b) for b in params[1::2]]
         gK[11], gB[11] = head_rgb[:384].view(128, 3), head_rgb[384:387]
         gK[8], gB[8] = head_sig[:256].view(256, 1), head_sig[256:257]
-    mlp_wgrad(enc[0], 64, 63, dz[0], 256, gK[0], gB[0])
-    for l in (1, 2, 3, 4, 6, 7):
-        mlp_wgrad(layers[l - 1], 256, 256, dz[l], 256, gK[l], gB[l])
-    mlp_wgrad(layers[4], 256, 256, dz[5], 256, gK[5][:256], gB[5])
-    mlp_wgrad(enc[0], 64, 63, dz[5], 256, gK[5][256:], None)
-    mlp_wgrad(layers[7], 256, 256, dz[8], 256, gK[9], gB[9])
-    mlp_wgrad(layers[8], 256, 256, dz[9], 128, gK[10][:256], gB[10])
-    mlp_wgrad(enc[1], 32, 27, dz[9], 128, gK[10][256:], None)
+    jobs = [(enc[0], 64, 63, dz[0], 256, gK[0], gB[0])]
+    jobs += [(layers[l - 1], 256, 256, dz[l], 256, gK[l], gB[l]) for l in (1, 2, 3, 4, 6, 7)]
+    jobs += [(layers[4], 256, 256, dz[5], 256, gK[5][:256], gB[5]), (enc[0], 64, 63, dz[5], 256, gK[5][256:], None),
+             (layers[7], 256, 256, dz[8], 256, gK[9], gB[9]), (layers[8], 256, 256, dz[9], 128, gK[10][:256], gB[10]),
+             (enc[1], 32, 27, dz[9], 128, gK[10][256:], None)]
+    mlp_wgrad_batched(jobs, M)          # 13 GEMMs, one launch
     if contiguous_pairs:      # (kernel, bias) of Dense_11 / Dense_8 are adjacent in the arena: accumulate in place
         check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(gK[11]), _p(gK[8]), _stream()), "rnerf_mlp_head_grad")
     else:

@@ -24,7 +24,8 @@ else:
     idx = torch.arange(r0, r0 + a.rays)
 o = flat.origins[idx].to(dev).contiguous(); d = flat.viewdirs[idx].to(dev).contiguous()
 so3 = (model._so3_packed(variables), model.so3_window(1.0))
-path = ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, so3=so3)
+path = ops.march(model.table, ndim, nmin, nmax, o, d, 2.0, 6.0, 768, bricks=model.bricks, compact=True, so3=so3,
+                 so3_tc=None if a.random else model._so3_tc_packed(variables))      # band of rows: the tensor-pipe kernel
 jitter = torch.arange(0, 768, 12, dtype=torch.int32, device=dev)
 gen = torch.Generator(device=dev).manual_seed(1)
 gp = torch.randn(a.rays, 64, 3, device=dev, generator=gen); gd = torch.randn(a.rays, 64, 3, device=dev, generator=gen)
