@@ -42,7 +42,8 @@ FLOP_PER_SAMPLE = 2 * 593408          # un-padded MACs of NerfMLP
 MLP_DRAM_BYTES_PER_SAMPLE = (102.945536e6 + 37.994752e6) / 4194304
 # dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass launch from `ncu --set full` at the bench's own launch size
 # (samples per launch -> bytes); filled from profiles/<tag>_render_ncu_summary.txt
-MLP_DRAM_BYTES = {}
+MLP_DRAM_BYTES = {122880000: 4915326000,     # profiles/r4a_render_ncu_summary.txt: fine launch of the 640 000-ray frame (40.0 B/sample)
+                  40960000: 1617748000}      # the coarse launch (39.5 B/sample); algorithmic: 24 B in + 16 B out per sample
 NC, NF, P = 64, 128, 12
 S = NC * P
 NEAR, FAR = 2.0, 6.0
