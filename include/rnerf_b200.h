@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 7
+#define RNERF_ABI_VERSION 8
 #define RNERF_PATH_STRIDE 12         /* full records */
 #define RNERF_PATH_STRIDE_COMPACT 8
 
@@ -120,17 +120,20 @@ int rnerf_encmlp_fwd_debug(const void* packed, const float* pos, const float* di
 
 /* ---- a17 (train.py:164-165 differentiates the MLPs): training forward + backward of pos_enc + NerfMLP ----
  * rnerf_encmlp_fwd_train additionally saves layer_out[10][M][256] (bf16 post-activation outputs of Dense_0..7,
- * Dense_9, Dense_10) and enc_out[2][M][64] (bf16 pos_enc / dir_enc rows, zero padded).
+ * Dense_9, Dense_10), enc_out[2][M][64] (bf16 pos_enc / dir_enc rows, zero padded) and relu_masks[10][M][8] (uint32: one bit
+ * per activation, set where it is positive -- all the dgrad chain needs of the activations; 32 B instead of 512 B per
+ * sample and layer; bit layout: csrc/umma.cuh relu_mask_push).
  * rnerf_mlp_dgrad: fused tcgen05 chain producing dz_out[10][M][256] (bf16 gradient wrt every layer's pre-activation)
- *   from d_raw[M][4]; dgrad_packed comes from rnerf_mlp_dgrad_pack (transposed weight image, rebuilt when weights change).
+ *   from d_raw[M][4] and relu_masks; dgrad_packed comes from rnerf_mlp_dgrad_pack (transposed weight image, rebuilt when
+ *   weights change).
  * rnerf_mlp_wgrad: gw[kx_valid][n] += x[:, :x_cols]^T dz (fp32, accumulating), gb[n] += column sums of dz (or NULL).
  * rnerf_mlp_head_grad: out_rgb_head[387] += (gW11[128][3], gb11[3]), out_sigma_head[257] += (gW8[256], gb8) from d_raw
  *   and the saved activations (each pair laid out like the Flax (kernel, bias) of Dense_11 / Dense_8). */
 int rnerf_encmlp_fwd_train(const void* packed, const float* pos, const float* dir, int64_t n_samples, float* raw_out,
-                           uint16_t* layer_out, uint16_t* enc_out, void* stream);
+                           uint16_t* layer_out, uint16_t* enc_out, uint32_t* relu_masks, void* stream);
 size_t rnerf_mlp_dgrad_packed_bytes(void);
 int rnerf_mlp_dgrad_pack(const float* const* kernels_host, void* dgrad_packed, void* stream);
-int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed, const uint16_t* layer_out, const float* d_raw,
+int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed, const uint32_t* relu_masks, const float* d_raw,
                     int64_t n_samples, uint16_t* dz_out, void* stream);
 int rnerf_mlp_wgrad(const uint16_t* x, int ldx, int x_cols, int kx_valid, const uint16_t* dz, int n, int64_t n_samples,
                     float* gw, float* gb, void* stream);

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RNERF_LIB") or os.path.join(_HERE, "librnerf_b200.so")
 
 _lib: Optional[C.CDLL] = None
-ABI_VERSION = 7      # include/rnerf_b200.h RNERF_ABI_VERSION
+ABI_VERSION = 8      # include/rnerf_b200.h RNERF_ABI_VERSION
 
 c_f32p = C.c_void_p
 c_i64 = C.c_int64
@@ -46,7 +46,7 @@ SIGNATURES = {
     "rnerf_encmlp_fwd": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_encmlp_fwd_debug": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p, C.c_void_p]),
     "rnerf_encmlp_fwd_profile": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p, C.c_void_p]),
-    "rnerf_encmlp_fwd_train": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rnerf_encmlp_fwd_train": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rnerf_mlp_dgrad_packed_bytes": (C.c_size_t, []),
     "rnerf_mlp_dgrad_pack": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "rnerf_mlp_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_i64, C.c_void_p, C.c_void_p]),

@@ -32,16 +32,16 @@ def _sink(model, name):
 class _RadianceMLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sink, packed, pos, dirs, *params):
-        raw, (layers, enc) = ops.encmlp_fwd_train(packed, pos, dirs)
+        raw, (layers, enc, masks) = ops.encmlp_fwd_train(packed, pos, dirs)
         ctx.sink = sink
-        ctx.save_for_backward(packed, pos, dirs, layers, enc, *params)
+        ctx.save_for_backward(packed, pos, dirs, layers, enc, masks, *params)
         return raw.view(pos.shape[0], pos.shape[1], 4)
 
     @staticmethod
     def backward(ctx, d_raw):
-        packed, pos, dirs, layers, enc, *params = ctx.saved_tensors
+        packed, pos, dirs, layers, enc, masks, *params = ctx.saved_tensors
         want_in = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]      # "all" stage: the samples depend on so3_mlp
-        grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc), d_raw.contiguous().view(-1, 4), params,
+        grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.contiguous().view(-1, 4), params,
                                grad_out=ctx.sink, input_grads=want_in)
         d_pos, d_dirs = grads.pop() if want_in else (None, None)
         if ctx.sink is not None:        # already accumulated into the arena's .grad views

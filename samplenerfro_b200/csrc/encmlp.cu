@@ -110,8 +110,9 @@ struct SmemLayout {
 template <int KIND, bool DUMP>
 __device__ __forceinline__ void epilogue_row(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ vslot,
                                              uint8_t* __restrict__ a_row, uint32_t r7s, EpiOut& o,
-                                             __nv_bfloat16* __restrict__ dump_row) {
+                                             __nv_bfloat16* __restrict__ dump_row, uint32_t* __restrict__ mask_row = nullptr) {
   constexpr int NCG = (KIND == 3) ? 4 : 8;
+  uint32_t m2[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};      // ReLU bit-mask words of columns 0..127 / 128..255 (umma.cuh)
 #pragma unroll 1
   for (int cg2 = 0; cg2 < NCG; cg2 += 2) {   // 2 x 32 accumulator columns per iteration, both TMEM loads in flight
     uint32_t v[2][32];
@@ -132,6 +133,7 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, const float* __rest
         if (KIND == 2) { pk[2 * j4] = pack_bf16(f0, f1);      pk[2 * j4 + 1] = pack_bf16(f2, f3); }
         else           { pk[2 * j4] = pack_bf16_relu(f0, f1); pk[2 * j4 + 1] = pack_bf16_relu(f2, f3); }
       }
+      if (DUMP && KIND != 2) { if (cg2 < 4) relu_mask_push(m2[0], pk); else relu_mask_push(m2[1], pk); }
       if (KIND == 1) {  // sigma head (Dense_8) on the bf16-rounded trunk output; weights in vslot[0..255]
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -170,6 +172,10 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, const float* __rest
         }
       }
     }
+  }
+  if (DUMP && KIND != 2 && mask_row != nullptr) {
+    reinterpret_cast<uint4*>(mask_row)[0] = make_uint4(m2[0][0], m2[0][1], m2[0][2], m2[0][3]);
+    reinterpret_cast<uint4*>(mask_row)[1] = make_uint4(m2[1][0], m2[1][1], m2[1][2], m2[1][3]);
   }
 }
 
@@ -331,10 +337,11 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) encmlp_kernel(const EncMlpAr
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
           __nv_bfloat16* dump_row = nullptr;
           if (DEBUG) dump_row = (args.layer_out && live && l == 9) ? args.layer_out + ((size_t)l * args.n_samples + srow) * 256 : nullptr;
-          if (l == 7)      epilogue_row<1, false>(taddr, bias, vslot, a_row, r7s, eo, nullptr);
+          uint32_t* mrow = (DEBUG && args.mask_out && live) ? args.mask_out + ((size_t)l * args.n_samples + srow) * 8 : nullptr;
+          if (l == 7)      epilogue_row<1, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, nullptr, mrow);
           else if (l == 8) epilogue_row<2, false>(taddr, bias, vslot, a_row, r7s, eo, nullptr);
-          else if (l == 9) epilogue_row<3, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row);   // no smem copy: direct stores
-          else             epilogue_row<0, false>(taddr, bias, vslot, a_row, r7s, eo, nullptr);
+          else if (l == 9) epilogue_row<3, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, dump_row, mrow);   // no smem copy: direct stores
+          else             epilogue_row<0, DEBUG>(taddr, bias, vslot, a_row, r7s, eo, nullptr, mrow);
         }
         if (l == 8) {
           // condition input for Dense_10: pos_enc(dir, 0, 4) replaces the position encoding (last used by layer 5)
@@ -433,7 +440,8 @@ static bool use_pair_kernel() {
 }
 
 static int encmlp_fwd_impl(const void* packed, const float* pos, const float* dir, int64_t n_samples, float* raw_out,
-                           uint16_t* layer_out, void* stream, long long* prof = nullptr, uint16_t* enc_out = nullptr) {
+                           uint16_t* layer_out, void* stream, long long* prof = nullptr, uint16_t* enc_out = nullptr,
+                           uint32_t* mask_out = nullptr) {
   RNERF_REQUIRE(n_samples >= 0, RNERF_E_SHAPE, "rnerf_encmlp_fwd: n_samples < 0");
   if (n_samples == 0) return 0;
   RNERF_REQUIRE_PTR(packed); RNERF_REQUIRE_PTR(pos); RNERF_REQUIRE_PTR(dir); RNERF_REQUIRE_PTR(raw_out);
@@ -441,7 +449,7 @@ static int encmlp_fwd_impl(const void* packed, const float* pos, const float* di
   RNERF_REQUIRE(layer_out == nullptr || aligned16(layer_out), RNERF_E_ALIGN, "rnerf_encmlp_fwd: layer_out must be 16-byte aligned");
   EncMlpArgs a;
   a.packed = (const uint8_t*)packed; a.pos = pos; a.dir = dir; a.n_samples = n_samples;
-  a.raw_out = (float4*)raw_out; a.layer_out = (__nv_bfloat16*)layer_out; a.enc_out = (__nv_bfloat16*)enc_out; a.prof = prof; a.n_groups = 0;
+  a.raw_out = (float4*)raw_out; a.layer_out = (__nv_bfloat16*)layer_out; a.enc_out = (__nv_bfloat16*)enc_out; a.mask_out = mask_out; a.prof = prof; a.n_groups = 0;
   { const char* d = getenv("RNERF_PAIR_DEBUG"); a.dbg = d ? atoi(d) : 0; }
   if (prof != nullptr && layer_out == nullptr && n_samples >= 74 * 512 && getenv("RNERF_PROFILE_PAIR") != nullptr)
     return launch_encmlp_pair(a, (cudaStream_t)stream);
@@ -473,8 +481,8 @@ extern "C" int rnerf_encmlp_fwd_profile(const void* packed, const float* pos, co
 // training forward: saves every layer's post-activation output (bf16 [10][M][256]) and the two encodings
 // (bf16 [2][M][64]) for rnerf_mlp_dgrad / rnerf_mlp_wgrad
 extern "C" int rnerf_encmlp_fwd_train(const void* packed, const float* pos, const float* dir, int64_t n_samples,
-                                      float* raw_out, uint16_t* layer_out, uint16_t* enc_out, void* stream) {
-  RNERF_REQUIRE_PTR(layer_out); RNERF_REQUIRE_PTR(enc_out);
-  RNERF_REQUIRE(aligned16(enc_out), RNERF_E_ALIGN, "rnerf_encmlp_fwd_train: enc_out must be 16-byte aligned");
-  return encmlp_fwd_impl(packed, pos, dir, n_samples, raw_out, layer_out, stream, nullptr, enc_out);
+                                      float* raw_out, uint16_t* layer_out, uint16_t* enc_out, uint32_t* relu_masks, void* stream) {
+  RNERF_REQUIRE_PTR(layer_out); RNERF_REQUIRE_PTR(enc_out); RNERF_REQUIRE_PTR(relu_masks);
+  RNERF_REQUIRE(aligned16(enc_out) && aligned16(relu_masks), RNERF_E_ALIGN, "rnerf_encmlp_fwd_train: enc_out / relu_masks must be 16-byte aligned");
+  return encmlp_fwd_impl(packed, pos, dir, n_samples, raw_out, layer_out, stream, nullptr, enc_out, relu_masks);
 }

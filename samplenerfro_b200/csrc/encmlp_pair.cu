@@ -123,8 +123,10 @@ __device__ __forceinline__ void tile_bar_sync(int tile) { asm volatile("bar.sync
 template <int KIND, bool DUMP = false>
 __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ hw,
                                               uint8_t* __restrict__ a_row, uint32_t r7s, int col0, EpiOut& o,
-                                              __nv_bfloat16* __restrict__ dump_row = nullptr /* KIND 3 in training mode */) {
+                                              __nv_bfloat16* __restrict__ dump_row = nullptr /* KIND 3 in training mode */,
+                                              uint32_t* __restrict__ mask_row = nullptr /* training: this row's 4 mask words */) {
   constexpr int NCG = (KIND == 3) ? 2 : 4;
+  uint32_t m2[4] = {0u, 0u, 0u, 0u};
 #ifdef RNERF_PAIR_PIPELINED_LD
   // two TMEM loads in flight: group cg+1 is fetched while group cg is converted and stored
   uint32_t vv[2][32];
@@ -154,6 +156,7 @@ __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __res
       if (KIND == 2) { pk[2 * j4] = pack_bf16(f0, f1);      pk[2 * j4 + 1] = pack_bf16(f2, f3); }
       else           { pk[2 * j4] = pack_bf16_relu(f0, f1); pk[2 * j4 + 1] = pack_bf16_relu(f2, f3); }
     }
+    if (DUMP && KIND != 2) relu_mask_push(m2, pk);
     if (KIND == 1) {  // sigma head (Dense_8): hw = w_sigma[256]
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
@@ -190,6 +193,11 @@ __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __res
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<uint4*>(blk + (((u0 + c) << 4) ^ r7s)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
     }
+  }
+  if (DUMP && KIND != 2 && mask_row != nullptr) {
+    // KIND 3: this warpgroup holds 64 of the layer's 128 columns (two groups): columns 0..63 go to bits 15..8, 64..127 to 7..0
+    const int sh = (KIND == 3 && col0 == 0) ? 8 : 0;
+    *reinterpret_cast<uint4*>(mask_row) = make_uint4(m2[0] << sh, m2[1] << sh, m2[2] << sh, m2[3] << sh);
   }
 }
 
@@ -400,7 +408,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
           for (int i = ttid; i < 384; i += 256) a_scratch[i] = __ldg(wrgb_g + i);
           tile_bar_sync(t);
           pair_epilogue<3, TRAIN>(taddr_row + half * 64, bias_s, a_scratch, a_row, r7s, half * 64, eo,
-                                  (TRAIN && live) ? args.layer_out + ((size_t)9 * args.n_samples + srow) * 256 : nullptr);
+                                  (TRAIN && live) ? args.layer_out + ((size_t)9 * args.n_samples + srow) * 256 : nullptr,
+                                  (TRAIN && live && args.mask_out) ? args.mask_out + ((size_t)9 * args.n_samples + srow) * 8 + half * 4 : nullptr);
           // combine the two column halves: half 1 parks its partial sums, half 0 adds and writes the row
           float4* part = reinterpret_cast<float4*>(a_scratch + 1024);
           if (half == 1) part[row] = make_float4(eo.r, eo.g, eo.b, eo.sigma);
@@ -413,9 +422,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
           tc_fence_before();   // accumulators drained; signalled with the next group's encoding (or never)
         } else {
           const uint32_t ta = taddr_row + half * 128;
-          if (l == 7)      pair_epilogue<1>(ta, bias_s, e_scratch, a_row, r7s, half * 128, eo);
+          uint32_t* mrow = (TRAIN && live && args.mask_out) ? args.mask_out + ((size_t)l * args.n_samples + srow) * 8 + half * 4 : nullptr;
+          if (l == 7)      pair_epilogue<1, TRAIN>(ta, bias_s, e_scratch, a_row, r7s, half * 128, eo, nullptr, mrow);
           else if (l == 8) pair_epilogue<2>(ta, bias_s, nullptr, a_row, r7s, half * 128, eo);
-          else             pair_epilogue<0>(ta, bias_s, nullptr, a_row, r7s, half * 128, eo);
+          else             pair_epilogue<0, TRAIN>(ta, bias_s, nullptr, a_row, r7s, half * 128, eo, nullptr, mrow);
           if (l == 8 && half == 0) {
             // condition input for Dense_10: pos_enc(dir, 0, 4) replaces the position encoding
             const float d0 = __ldg(args.dir + 3 * lrow), d1 = __ldg(args.dir + 3 * lrow + 1), d2 = __ldg(args.dir + 3 * lrow + 2);

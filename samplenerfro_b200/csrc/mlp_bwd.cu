@@ -57,40 +57,12 @@ struct DgradSmem {
 struct DgradArgs {
   const uint8_t* packed;        // dgrad weight image (dgrad_pack_kernel)
   const float* head_w;          // w_sigma[256] then w_rgb[3][128], bf16-rounded fp32 (forward image tail)
-  const __nv_bfloat16* H;       // [10][M][256] saved activations
+  const uint32_t* masks;        // [10][M][8] ReLU bit-masks written by the training forward (relu_mask_push, umma.cuh)
   const float4* d_raw;          // [M] (d rgb_raw[3], d sigma_raw)
   __nv_bfloat16* dZ;            // [10][M][256] out
   int64_t n_samples;
   int n_groups;
 };
-
-// ReLU masks of 32 consecutive saved activation rows (H > 0  <=>  bf16 bits != 0 after ReLU), loaded warp-cooperatively:
-// lane i reads the 16-byte unit i of a row, so one load instruction covers one full 512-byte row (4 lines) instead of
-// 32 different rows.  The bits are exchanged with ballots: mask[p] bit i of the row's owner (lane r <-> row wrow0 + r)
-// says whether column 8 i + p is active.
-__device__ __forceinline__ void load_row_masks(const __nv_bfloat16* __restrict__ Hl, int64_t wrow0, int64_t n_samples,
-                                               int lane, uint32_t (&mask)[8]) {
-  constexpr int NB = 16;          // rows in flight: the loads are HBM-latency bound and must finish under one MMA phase
-#pragma unroll 1
-  for (int r0 = 0; r0 < 32; r0 += NB) {
-    uint4 v[NB];
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const int64_t row = min(wrow0 + r0 + k, n_samples - 1);
-      v[k] = __ldg(reinterpret_cast<const uint4*>(Hl + (size_t)row * 256) + lane);
-    }
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const uint32_t u[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const bool on = (p & 1) ? ((u[p >> 1] >> 16) != 0u) : ((u[p >> 1] & 0xFFFFu) != 0u);
-        const uint32_t bal = __ballot_sync(0xffffffffu, on);
-        if (lane == r0 + k) mask[p] = bal;
-      }
-    }
-  }
-}
 
 template <int NT, int NSTAGE>
 __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const DgradArgs args,
@@ -193,8 +165,12 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
       const float4 draw = live ? __ldg(args.d_raw + lrow) : make_float4(0.f, 0.f, 0.f, 0.f);
       // ---- prologue: rgb head (Dense_11) backward + ReLU of the condition layer -> dZ[9] (128 columns)
       {
-        uint32_t m9[8];
-        load_row_masks(args.H + 9 * layer_stride, wrow0, args.n_samples, lane, m9);    // columns >= 128 are ignored
+        uint32_t m9[4];                           // condition layer: 128 columns, the two writers' words OR-ed
+        {
+          const uint4* mp = reinterpret_cast<const uint4*>(args.masks + ((size_t)9 * args.n_samples + lrow) * 8);
+          const uint4 a4 = __ldg(mp), b4 = __ldg(mp + 1);
+          m9[0] = a4.x | b4.x; m9[1] = a4.y | b4.y; m9[2] = a4.z | b4.z; m9[3] = a4.w | b4.w;
+        }
         tile_free();
 #pragma unroll 1
         for (int c8 = 0; c8 < 16; ++c8) {         // 8 columns per 16-byte unit
@@ -204,8 +180,9 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
             const int j0 = c8 * 8 + i * 2;
             float g0 = draw.x * w_rgb[j0] + draw.y * w_rgb[128 + j0] + draw.z * w_rgb[256 + j0];
             float g1 = draw.x * w_rgb[j0 + 1] + draw.y * w_rgb[128 + j0 + 1] + draw.z * w_rgb[256 + j0 + 1];
-            if (!((m9[2 * i] >> c8) & 1u)) g0 = 0.f;
-            if (!((m9[2 * i + 1] >> c8) & 1u)) g1 = 0.f;
+            // columns 8 c8 + 2 i, + 1: pair index (c8 & 3) * 4 + i of group c8 >> 2, i.e. word i, step c8 (relu_mask_push)
+            if (!((m9[i] >> (15 - c8)) & 1u)) g0 = 0.f;
+            if (!((m9[i] >> (31 - c8)) & 1u)) g1 = 0.f;
             pk[i] = pack_bf16(g0, g1);
           }
           *reinterpret_cast<uint4*>(a_row + (c8 >> 3) * ABLK_BYTES + ((uint32_t)((c8 & 7) << 4) ^ r7s)) =
@@ -218,8 +195,13 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
       if (lane == 0) { mbar_arrive(bar_aready); store_tile(wrow0, 9, 2); }
       for (int d = 0; d < DG_GEMMS; ++d) {
         const int lo = 8 - d;                       // MMA layer whose dZ this GEMM produces
-        uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (d >= 1) load_row_masks(args.H + (size_t)lo * layer_stride, wrow0, args.n_samples, lane, mask);   // hidden under the MMAs
+        uint32_t mask[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};       // this row's ReLU bits of layer lo: columns 0..127 | 128..255
+        if (d >= 1) {                                            // 32 bytes per row, hidden under the MMAs
+          const uint4* mp = reinterpret_cast<const uint4*>(args.masks + ((size_t)lo * args.n_samples + lrow) * 8);
+          const uint4 a4 = __ldg(mp), b4 = __ldg(mp + 1);
+          mask[0][0] = a4.x; mask[0][1] = a4.y; mask[0][2] = a4.z; mask[0][3] = a4.w;
+          mask[1][0] = b4.x; mask[1][1] = b4.y; mask[1][2] = b4.z; mask[1][3] = b4.w;
+        }
         mbar_wait(bar_acc, acc_phase); acc_phase ^= 1;
         tc_fence_after();
         tile_free();
@@ -228,9 +210,9 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + cg * 32), v);
           tmem_ld_wait();
-          uint32_t mk[8];                           // bit (j >> 2) of mk[p]: column cg*32 + 8*(j >> 2) + p
+          uint32_t mk[4];                           // this group's four steps of the half's words, aligned to bit 3 / bit 19
 #pragma unroll
-          for (int p = 0; p < 8; ++p) mk[p] = mask[p] >> (cg * 4);
+          for (int p = 0; p < 4; ++p) mk[p] = ((cg & 4) ? mask[1][p] : mask[0][p]) >> (12 - (cg & 3) * 4);
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -239,9 +221,9 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
               f0 = fmaf(draw.w, w_sigma[cg * 32 + 2 * j], f0);
               f1 = fmaf(draw.w, w_sigma[cg * 32 + 2 * j + 1], f1);
             }
-            if (d >= 1) {
-              if (!((mk[(2 * j) & 7] >> (j >> 2)) & 1u)) f0 = 0.f;
-              if (!((mk[(2 * j + 1) & 7] >> (j >> 2)) & 1u)) f1 = 0.f;
+            if (d >= 1) {                          // columns 32 cg + 2 j, + 1: word j & 3, step 4 (cg & 3) + (j >> 2)
+              if (!((mk[j & 3] >> (3 - (j >> 2))) & 1u)) f0 = 0.f;
+              if (!((mk[j & 3] >> (19 - (j >> 2))) & 1u)) f1 = 0.f;
             }
             pk[j] = pack_bf16(f0, f1);
           }
@@ -575,12 +557,12 @@ extern "C" int rnerf_mlp_dgrad_pack(const float* const* kernels, void* packed, v
   return check_launch("rnerf_mlp_dgrad_pack");
 }
 
-extern "C" int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed, const uint16_t* saved_h, const float* d_raw,
+extern "C" int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed, const uint32_t* relu_masks, const float* d_raw,
                                int64_t n_samples, uint16_t* dz_out, void* stream) {
   RNERF_REQUIRE(n_samples >= 0, RNERF_E_SHAPE, "rnerf_mlp_dgrad: n_samples < 0");
   if (n_samples == 0) return 0;
-  RNERF_REQUIRE_PTR(dgrad_packed); RNERF_REQUIRE_PTR(fwd_packed); RNERF_REQUIRE_PTR(saved_h); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(dz_out);
-  RNERF_REQUIRE(aligned16(dgrad_packed) && aligned16(saved_h) && aligned16(d_raw) && aligned16(dz_out), RNERF_E_ALIGN,
+  RNERF_REQUIRE_PTR(dgrad_packed); RNERF_REQUIRE_PTR(fwd_packed); RNERF_REQUIRE_PTR(relu_masks); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(dz_out);
+  RNERF_REQUIRE(aligned16(dgrad_packed) && aligned16(relu_masks) && aligned16(d_raw) && aligned16(dz_out), RNERF_E_ALIGN,
                 "rnerf_mlp_dgrad: buffers must be 16-byte aligned");
   constexpr int NT = 2, NSTAGE = 4;
   using SL = DgradSmem<NT, NSTAGE>;
@@ -598,7 +580,7 @@ extern "C" int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed,
   DgradArgs a;
   a.packed = (const uint8_t*)dgrad_packed;
   a.head_w = reinterpret_cast<const float*>((const uint8_t*)fwd_packed + PK_WSIGMA);
-  a.H = (const __nv_bfloat16*)saved_h; a.d_raw = (const float4*)d_raw; a.dZ = (__nv_bfloat16*)dz_out;
+  a.masks = relu_masks; a.d_raw = (const float4*)d_raw; a.dZ = (__nv_bfloat16*)dz_out;
   a.n_samples = n_samples;
   a.n_groups = (int)((n_samples + TILE_M * NT - 1) / (TILE_M * NT));
   const int grid = a.n_groups < n_sm ? a.n_groups : n_sm;

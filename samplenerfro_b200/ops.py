@@ -451,17 +451,19 @@ def encmlp_fwd_profile(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tens
 
 # ---------------------------------------------------------------- training-mode MLP: forward with saved activations, backward
 def encmlp_fwd_train(packed: torch.Tensor, pos: torch.Tensor, dirs: torch.Tensor):
-    """Forward that keeps what the backward kernels need: every layer's post-activation output (bf16 [10,M,256])
-    and the two encodings (bf16 [2,M,64]).  Returns (raw [M,4], (layers, enc))."""
+    """Forward that keeps what the backward kernels need: every layer's post-activation output (bf16 [10,M,256]; the weight
+    gradients' X operand), the two encodings (bf16 [2,M,64]) and the ReLU bit-masks (int32 [10,M,8]; all the dgrad chain needs
+    of the activations).  Returns (raw [M,4], (layers, enc, masks))."""
     _chk(packed, "packed", torch.uint8)
     pos = _chk(pos, "pos").reshape(-1, 3); dirs = _chk(dirs, "dirs").reshape(-1, 3)
     M = pos.shape[0]
     raw = torch.empty(M, 4, device=pos.device, dtype=torch.float32)
     layers = torch.empty(10, M, 256, device=pos.device, dtype=torch.bfloat16)
     enc = torch.empty(2, M, 64, device=pos.device, dtype=torch.bfloat16)
-    check(_lib.load().rnerf_encmlp_fwd_train(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(layers), _p(enc), _stream()),
+    masks = torch.empty(10, M, 8, device=pos.device, dtype=torch.int32)
+    check(_lib.load().rnerf_encmlp_fwd_train(_p(packed), _p(pos), _p(dirs), M, _p(raw), _p(layers), _p(enc), _p(masks), _stream()),
           "rnerf_encmlp_fwd_train")
-    return raw, (layers, enc)
+    return raw, (layers, enc, masks)
 
 
 def mlp_dgrad_pack(kernels) -> torch.Tensor:
@@ -514,7 +516,7 @@ def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None, input_gra
     flat parameter arena, where every (kernel, bias) pair is contiguous; fresh zero buffers otherwise.
     `input_grads`: also return (d_pos, d_dirs), the gradients wrt the sample positions / directions ("all" stage), as
     the last element of the returned list."""
-    layers, enc = saved
+    layers, enc, masks = saved
     M = layers.shape[1]
     lib = _lib.load()
     K = [p for p in params[0::2]]
@@ -522,7 +524,8 @@ def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None, input_gra
     d_raw = _chk(d_raw.contiguous(), "d_raw")
     dgp = mlp_dgrad_pack(K)
     dz = torch.empty(10, M, 256, device=dev, dtype=torch.bfloat16)
-    check(lib.rnerf_mlp_dgrad(_p(dgp), _p(packed), _p(layers), _p(d_raw), M, _p(dz), _stream()), "rnerf_mlp_dgrad")
+    check(lib.rnerf_mlp_dgrad(_p(dgp), _p(packed), _p(_chk(masks, "relu masks", torch.int32)), _p(d_raw), M, _p(dz), _stream()),
+          "rnerf_mlp_dgrad")
     if grad_out is not None:
         gK, gB = list(grad_out[0::2]), list(grad_out[1::2])
         for g in gK + gB:

@@ -154,11 +154,11 @@ def test_mlp_backward_kernels(cuda_lib, M):
     dirs = torch.randn(M, 3, generator=gen).cuda(); dirs = dirs / dirs.norm(dim=-1, keepdim=True)
     d_raw = torch.randn(M, 4, generator=gen).cuda() * 0.1
     packed = ops.encmlp_pack(p)
-    raw, (layers, enc) = ops.encmlp_fwd_train(packed, pos, dirs)
+    raw, (layers, enc, masks) = ops.encmlp_fwd_train(packed, pos, dirs)
     params = []
     for i in range(12):
         params += [p[f"Dense_{i}"]["kernel"], p[f"Dense_{i}"]["bias"]]
-    grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc), d_raw, params)
+    grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw, params)
     torch.cuda.synchronize()
     gK, gB, dzs = _ref_mlp_bwd(p, pos, dirs, layers, d_raw)
     # saved encodings
