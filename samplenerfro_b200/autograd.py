@@ -162,8 +162,11 @@ class _MarchAll(torch.autograd.Function):
         if so3 is not None and 256 < origins.shape[0] <= SO3_SORT_MAX_RAYS and os.environ.get("RNERF_SO3_SORT", "1") != "0":
             perm = _activity_order(model, table, bricks, origins, viewdirs)
             origins, viewdirs = origins[perm].contiguous(), viewdirs[perm].contiguous()
+        # the forward evaluates so3_mlp on the tensor pipe (fp16 hi/lo split operands, fp32-grade); the hi/lo weight image is
+        # rebuilt from this step's weights (one small kernel)
+        so3_tc = ops.so3_tc_pack(w) if so3 is not None else None
         path = ops.march(table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
-                         model.num_march_steps, bricks=bricks, compact=compact, so3=so3)
+                         model.num_march_steps, bricks=bricks, compact=compact, so3=so3, so3_tc=so3_tc)
         pos_c, dir_c, t_c, _ = ops.select(path, jitter)
         ctx.model, ctx.sink, ctx.window = model, sink, window
         rec, t_col = path.rec, path.t

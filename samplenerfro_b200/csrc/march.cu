@@ -1007,6 +1007,136 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) march_tc_kernel(const float4* 
   if (warp == MTC_CW + 1) tmem_dealloc(tmem_base, TC_N);
 }
 
+// The ragged "all"-stage march (march_all_ragged_kernel) with the tensor-pipe evaluator: small launches (a training batch),
+// 32 or 64 rays per CTA so that every SM is busy, rays not in lockstep.  Threads 0 .. rays_per_cta-1 carry a ray each, all
+// eight worker warps take part in an evaluation, warps 8 / 9 stream the weights / issue the MMAs as in march_tc_kernel.
+template <int RECF4, bool FAST>
+__global__ void __launch_bounds__(MTC_THREADS, 1) march_ragged_tc_kernel(const float4* __restrict__ table, const MarchGeom mg,
+                                                                         const float* __restrict__ origins,
+                                                                         const float* __restrict__ viewdirs, int64_t n_rays,
+                                                                         float near, float step, int n_steps,
+                                                                         float4* __restrict__ path, float* __restrict__ t_col,
+                                                                         const float* __restrict__ bricks, const So3Args so3,
+                                                                         const uint8_t* __restrict__ packed, int rays_per_cta) {
+  using SL = MtcSmem;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  const uint32_t sbase = smem_u32(tc_smem);
+  if ((sbase & 1023u) != 0) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full0 = sbase + SL::BAR_OFF, bar_empty0 = bar_full0 + 8 * MTC_SLOTS;
+  const uint32_t bar_acc = bar_empty0 + 8 * MTC_SLOTS, bar_act = bar_acc + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(tc_smem + SL::TMEM_SLOT);
+  volatile int* flags = reinterpret_cast<volatile int*>(tc_smem + SL::CNT) + 8;      // [0] exit, [1] chunks consumed
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MTC_SLOTS; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_empty0 + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_act, MTC_CW);
+    flags[0] = 0; flags[1] = 0;
+    fence_barrier_init();
+  }
+  if (warp == MTC_CW + 1) { tmem_alloc(sbase + SL::TMEM_SLOT, TC_N); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == MTC_CW) {
+    if (elect_one_sync()) {                      // weight producer (see march_tc_kernel)
+      uint32_t c = 0;
+      bool stop = false;
+      while (!stop) {
+        const uint32_t s = c % MTC_SLOTS, par = ((c / MTC_SLOTS) & 1u) ^ 1u;
+        while (!mbar_try_wait(bar_empty0 + 8 * s, par))
+          if (flags[0]) { stop = true; break; }
+        if (stop) break;
+        mbar_arrive_expect_tx(bar_full0 + 8 * s, TC_CHUNK_BYTES);
+        tma_bulk_g2s(sbase + TcSmem::RING + s * TC_CHUNK_BYTES, packed + (size_t)(c % TC_NCHUNK) * TC_CHUNK_BYTES, TC_CHUNK_BYTES,
+                     bar_full0 + 8 * s);
+        ++c;
+      }
+      for (uint32_t g = (uint32_t)flags[1]; g < c; ++g) mbar_wait(bar_full0 + 8 * (g % MTC_SLOTS), (g / MTC_SLOTS) & 1u);
+    }
+  } else if (warp == MTC_CW + 1) {
+    if (elect_one_sync()) {                      // MMA issuer
+      uint32_t c = 0, act_phase = 0, layer = 0;
+      bool stop = false;
+      while (!stop) {
+        while (!mbar_try_wait(bar_act, act_phase))
+          if (flags[0]) { stop = true; break; }
+        if (stop) break;
+        act_phase ^= 1u;
+        tc_fence_after();
+        tc_issue_layer((int)layer, sbase, tmem_base, bar_full0, bar_empty0, MTC_SLOTS, c, bar_acc, so3.dbg);
+        layer = (layer + 1) & 3u;
+      }
+    }
+  } else {
+    {
+      float* w4s = reinterpret_cast<float*>(tc_smem + SL::W4_OFF);
+      for (int i = threadIdx.x; i < 3 * SO3_W + 3; i += MTC_RAYS)
+        w4s[i] = i < 3 * SO3_W ? __ldg(so3.w + SO3_OFF_W4 + i) : __ldg(so3.w + SO3_OFF_B + 4 * SO3_W + (i - 3 * SO3_W));
+      mtc_workers_sync();
+    }
+    MtcEval ev;
+    ev.smem = tc_smem; ev.tmem_base = tmem_base; ev.bar_acc = bar_acc; ev.bar_act = bar_act; ev.acc_phase = 0; ev.passes = 0;
+    constexpr int QUANTUM = 16;                  // steps a ray that needs nothing may run ahead per round
+    const int64_t ray = blockIdx.x * (int64_t)rays_per_cta + threadIdx.x;
+    const bool live = (int)threadIdx.x < rays_per_cta && ray < n_rays;
+    const int64_t rr = live ? ray : (n_rays - 1);
+    float vx = viewdirs[3 * rr], vy = viewdirs[3 * rr + 1], vz = viewdirs[3 * rr + 2];
+    float px = add(origins[3 * rr], mul(near, vx)), py = add(origins[3 * rr + 1], mul(near, vy)), pz = add(origins[3 * rr + 2], mul(near, vz));
+    float t = near;
+    float4* rec = path + rr * (int64_t)n_steps * RECF4;
+    float* tc = t_col != nullptr ? t_col + rr * (int64_t)n_steps : nullptr;
+    int k = 0;
+    bool done = !live;
+    float n_here = 1.f;
+    auto advance = [&](float gx, float gy, float gz) {
+      const float s = divf(step, n_here);
+      const float nx = add(px, mul(s, vx)), ny = add(py, mul(s, vy)), nz = add(pz, mul(s, vz));
+      vx = add(vx, mul(step, gx)); vy = add(vy, mul(step, gy)); vz = add(vz, mul(step, gz));
+      t = add(t, sqrtf(sumsq3(sub(px, nx), sub(py, ny), sub(pz, nz))));
+      px = nx; py = ny; pz = nz;
+      done = ++k >= n_steps;
+    };
+#pragma unroll 1
+    while (true) {
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      bool need = false;
+#pragma unroll 1
+      for (int it = 0; it < QUANTUM && !done && !need; ++it) {
+        const float4 c = march_lookup<FAST>(table, mg, bricks, px, py, pz);
+        __stcs(rec + k * RECF4, make_float4(px, py, pz, t));
+        __stcs(rec + k * RECF4 + 1, make_float4(vx, vy, vz, c.x));
+        if (RECF4 == 3) __stcs(rec + k * RECF4 + 2, make_float4(c.y, c.z, c.w, 0.f));
+        if (tc != nullptr) tc[k] = t;
+        n_here = c.x; gx = c.y; gy = c.z; gz = c.w;
+        need = sqrtf(sumsq3(gx, gy, gz)) > 1e-3f;          // jnp.linalg.norm(idx_grad) > 1e-3
+        if (!need) advance(gx, gy, gz);
+      }
+      if (mtc_workers_or(need)) {
+        float r0, r1, r2;
+        so3_eval_tc(so3, ev, warp, lane, need, px, py, pz, r0, r1, r2);
+        if (need) {
+          so3_rotate(r0, r1, r2, gx, gy, gz);
+          advance(gx, gy, gz);
+        }
+      } else if (!mtc_workers_or(!done)) {
+        break;
+      }
+    }
+    mtc_workers_sync();
+    if (threadIdx.x == 0) {
+      flags[1] = (int)(ev.passes * TC_NCHUNK);
+      __threadfence_block();
+      flags[0] = 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MTC_CW + 1) tmem_dealloc(tmem_base, TC_N);
+}
+
 // ray_dir of every record, normalised: the array PathSampler returns (rnerf/eikonal_utils.py:113)
 __global__ void __launch_bounds__(256) path_dirs_kernel(const float4* __restrict__ path, int recf4, int64_t n_rec,
                                                         float* __restrict__ out) {
@@ -1143,6 +1273,24 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
 #define RNERF_MARCH_LAUNCH(R, F, A)                                                                                       \
   march_kernel<R, F, A><<<blocks, (A) ? SO3_THREADS : MARCH_THREADS, dyn, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, (float)near, \
                                                             step, n_steps, (float4*)path, t_col, bricks, dbg, so3, slots, rpc)
+  if (so3_w != nullptr && rpc < MARCH_THREADS && so3_tc_packed != nullptr &&
+      !(getenv("RNERF_SO3_TC") != nullptr && atoi(getenv("RNERF_SO3_TC")) == 0)) {
+    // a small launch with the packed hi/lo image: the ragged march with the tensor-pipe evaluator
+    RNERF_REQUIRE(aligned16(so3_tc_packed), RNERF_E_ALIGN, "rnerf_march_all_fwd: so3_tc_packed must be 16-byte aligned");
+    cudaError_t e = cudaSuccess;
+#define RNERF_RAGGED_TC_LAUNCH(R, F)                                                                                         \
+    e = cudaFuncSetAttribute(march_ragged_tc_kernel<R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MtcSmem::BYTES);   \
+    if (e == cudaSuccess)                                                                                                      \
+      march_ragged_tc_kernel<R, F><<<blocks, MTC_THREADS, MtcSmem::BYTES, st>>>((const float4*)table, mg, origins, viewdirs, n_rays, \
+                                                                                (float)near, step, n_steps, (float4*)path, t_col,  \
+                                                                                bricks, so3, (const uint8_t*)so3_tc_packed, rpc)
+    if (rec_floats == 8) { if (fast) { RNERF_RAGGED_TC_LAUNCH(2, true); } else { RNERF_RAGGED_TC_LAUNCH(2, false); } }
+    else                 { if (fast) { RNERF_RAGGED_TC_LAUNCH(3, true); } else { RNERF_RAGGED_TC_LAUNCH(3, false); } }
+#undef RNERF_RAGGED_TC_LAUNCH
+    if (e != cudaSuccess) { set_error("rnerf_march_all_fwd: cudaFuncSetAttribute(ragged tc): %s", cudaGetErrorString(e)); return (int)e; }
+    count_launch();
+    return check_launch("rnerf_march_all_fwd(ragged tc)");
+  }
   if (so3_w != nullptr && rpc < MARCH_THREADS) {          // a small launch: rays not in lockstep (see march_all_ragged_kernel)
     cudaError_t e = cudaSuccess;
     slots = RAGGED_SLOTS;

@@ -359,3 +359,37 @@ def test_all_stage_full_frame_march_on_the_tensor_pipe(cuda_lib, monkeypatch):
     # the rotation is visible: the radiance-stage path differs
     plain = ops.march(*args, bricks=model.bricks, compact=True)
     assert (plain.rec[..., 0:3] - tc.rec[..., 0:3]).abs().max().item() > 1e-3
+
+
+def test_all_stage_ragged_march_on_the_tensor_pipe(cuda_lib, monkeypatch):
+    """Small launches (a training batch: rays out of lockstep, 32 rays per CTA) with the packed hi/lo image run so3_mlp on the
+    tensor pipe too (march_ragged_tc_kernel).  Against the CUDA-core ragged kernel on the same inputs, compact and full
+    records, and against the oracle's scan: same tolerances as the full-frame kernel."""
+    from samplenerfro_b200 import models, ops
+    n, ndim, nmin, nmax = H.sphere_grid(G=24, radius=0.7, ws=3, sigma=1.0)
+    gen = torch.Generator().manual_seed(9)
+    o, d = H.random_rays(777, seed=13, target_extent=0.6)
+    model, variables = models.construct_nerf(5, None, _flags(stage="all"), ndim, nmin, nmax, n)
+    so3 = variables["params"]["path_sampler"]["scan"]["idx_model"]["so3_mlp"]
+    so3["Dense_4"]["kernel"].copy_((torch.randn(128, 3, generator=gen) * 0.05).cuda())
+    so3["Dense_4"]["bias"].copy_((torch.randn(3, generator=gen) * 0.2).cuda())
+    S = 768
+    w = ops.so3_pack(so3)
+    win = model.so3_window(0.8)
+    args = (model.table, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, S)
+    for compact in (True, False):
+        tc = ops.march(*args, bricks=model.bricks, compact=compact, so3=(w, win), so3_tc=ops.so3_tc_pack(w))
+        cc = ops.march(*args, bricks=model.bricks, compact=compact, so3=(w, win))
+        scale = cc.rec[..., 0:3].abs().max().item()
+        assert torch.isfinite(tc.rec).all()
+        assert (tc.rec[..., 0:3] - cc.rec[..., 0:3]).abs().max().item() < 2e-5 * scale
+        assert (tc.t - cc.t).abs().max().item() < 2e-5 * cc.t.abs().max().item()
+        if not compact:
+            assert torch.equal(tc.rec[..., 8:11], cc.rec[..., 8:11]) or (tc.rec[..., 8:11] - cc.rec[..., 8:11]).abs().max().item() < 1e-3
+    cpu = {k: {kk: vv.detach().cpu() for kk, vv in v.items()} for k, v in so3.items()}
+    opos, odir, odist, _, _ = O.march(O.build_table(n, ndim, nmin, nmax), ndim, nmin, nmax, o[:96], d[:96], 2.0, 6.0, S, stage="all",
+                                      so3_params=cpu, annealed_alpha=0.8)
+    assert (tc.rec[:96, :, 0:3].cpu() - opos).abs().max().item() < 1e-4 * opos.abs().max().item()
+    assert (ops.path_dirs(tc.rec[:96].contiguous()).cpu() - odir).abs().max().item() < 1e-4
+    plain = ops.march(*args, bricks=model.bricks, compact=True)
+    assert (plain.rec[..., 0:3] - tc.rec[..., 0:3]).abs().max().item() > 1e-3
