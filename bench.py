@@ -342,10 +342,8 @@ def main():
         else:
             rgb, dist_, acc = utils.render_image_sharded(apply_host, host_hw, 0, False, chunk=chunk, rank=rank,
                                                          world_size=world)
-        if rank == 0:
-            out_host[..., 0:3].copy_(rgb, non_blocking=True)
-            out_host[..., 3:4].copy_(dist_, non_blocking=True)
-            out_host[..., 4:5].copy_(acc, non_blocking=True)
+        if rank == 0:      # one contiguous [H,W,5] device tensor -> ONE device-to-host copy into pinned memory
+            out_host.copy_(torch.cat([rgb, dist_, acc], dim=-1), non_blocking=True)
         torch.cuda.synchronize()
         return out_host
 

@@ -258,9 +258,13 @@ def _gather_bands(local: List[torch.Tensor], height: int, width: int, per: int, 
     if tile.shape[0] < want:
         fill = tile[-1:] if tile.shape[0] else tile.new_zeros(1, tile.shape[1])
         tile = torch.cat([tile, fill.expand(want - tile.shape[0], -1)], dim=0)
-    tiles = [torch.empty_like(tile) for _ in range(world_size)]
-    dist.all_gather(tiles, tile.contiguous(), group=group)
-    return torch.cat(tiles, dim=0)[:height * width]
+    tile = tile.contiguous()
+    full = torch.empty((world_size * want, tile.shape[1]), device=tile.device, dtype=tile.dtype)
+    if tile.is_cuda:       # NCCL writes every band straight into its slot of the frame (no list of tiles + concatenation)
+        dist.all_gather_into_tensor(full, tile, group=group)
+    else:                  # gloo (CPU tests)
+        dist.all_gather(list(full.split(want, dim=0)), tile, group=group)
+    return full[:height * width]
 
 
 def render_image_sharded(render_fn: Callable, rays: Rays, rng, normalize_disp: bool, chunk: int = 8192, rank: int = 0,
