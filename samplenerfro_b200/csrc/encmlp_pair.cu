@@ -21,7 +21,7 @@
 //   acc[j]    (both)    multicast tcgen05.commit after tile pair j's K-loop
 //   aready[j] (leader)  16 arrivals: the 8 epilogue warps of tile j in both CTAs (the peer's arrive remotely)
 #include <stdlib.h>
-#include "umma.cuh"
+#include "pair.cuh"
 
 namespace rnerf {
 
@@ -41,82 +41,6 @@ struct PairSmem {
 static_assert(PairSmem::BYTES <= 232448, "pair kernel exceeds the shared-memory budget");
 
 __constant__ PairChunk c_pair_stream[PAIR_NCHUNK] = {RNERF_PAIR_STREAM};
-
-// ---- cluster / cta_group::2 PTX ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  // default semantics (release at CTA scope) like cutlass::arch::ClusterBarrier::arrive(cta_id): an explicit
-  // .release.cluster compiles to MEMBAR.ALL.GPU (~1 us) in front of every arrive
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster_local(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-// wait on a barrier that also receives arrivals from the peer CTA (default semantics, as cutlass's ClusterBarrier::wait;
-// an explicit .acquire.cluster adds an L1 invalidate after every wait)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0, ok = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T   (SASS: UTCHMMA.2CTA)
-__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// The same with the two shared-memory descriptors given as (low word, shared high word): the K-loop advances a descriptor
-// by adding 2 (32 bytes >> 4) to its low word -- one uniform add per operand instead of rebuilding the 64-bit descriptor
-// from the address (shift, mask, or: ~12 dependent uniform-datapath instructions per MMA, which made the single issuing
-// thread, at ~145 cycles per MMA, slower than the tensor pipe's 128).
-__device__ __forceinline__ void umma2_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier at this offset in BOTH CTAs once all previously issued MMAs have completed
-__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
-
-__device__ __forceinline__ void tile_bar_sync(int tile) { asm volatile("bar.sync %0, 256;" ::"r"(tile + 1) : "memory"); }
 
 // Epilogue of one layer for one row and one 128-column half (64 columns for the condition layer).
 //   KIND 0: ReLU, write A   1: + sigma partial   2: no activation, write A   3: ReLU, rgb partial only

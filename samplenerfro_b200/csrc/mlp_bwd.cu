@@ -13,25 +13,35 @@
 //
 // Layer numbering: "MMA layer" l = 0..9 as in the forward (Dense_0..7, Dense_9 bottleneck, Dense_10 condition);
 // H[l] = saved post-activation output of MMA layer l ([M][256] bf16), dZ[l] = gradient wrt its pre-activation.
-#include "umma.cuh"
+#include <stdlib.h>
+#include "mlp_bwd.cuh"
 
 namespace rnerf {
 
 // ------------------------------------------------------------------------------------------------
 // dgrad chain
 // ------------------------------------------------------------------------------------------------
-constexpr int DG_GEMMS = 9;                       // d = 0: Dense_10[:256]^T (K = 128), d = 1: Dense_9^T, d >= 2: Dense_(9-d)^T
-__host__ __device__ constexpr int dg_dense(int d) { return d == 0 ? 10 : (d == 1 ? 9 : 9 - d); }
-__host__ __device__ constexpr int dg_k(int d) { return d == 0 ? 128 : 256; }           // GEMM K = width of the layer's output
-__host__ __device__ constexpr int dg_chunks(int d) { return dg_k(d) / KCH; }           // [256 x 32] SWIZZLE_64B chunks
-constexpr int DG_NCHUNK = 4 + 8 * 8;              // 68
-constexpr size_t DG_PACKED_BYTES = (size_t)DG_NCHUNK * SLOT_BYTES;
-
 struct DgradPackArgs { const float* kern[12]; };
 
 // chunk c of GEMM d: rows r = input feature kin (0..255), 32 columns = output features n0..n0+31 of the layer:
 // B[kin][n] = W[kin][n], i.e. plain row slices of the Flax [in,out] kernel (only its first 256 rows matter).
 __global__ void __launch_bounds__(256) dgrad_pack_kernel(DgradPackArgs a, uint8_t* __restrict__ packed) {
+  if (blockIdx.x >= DG_NCHUNK) {
+    // pair image: chunk pc = k-block kb of GEMM d, N-half h holds rows kin = 128 h + r
+    int kb = (int)blockIdx.x - DG_NCHUNK, d = 0;
+    while (kb >= dg_k(d) / KB) { kb -= dg_k(d) / KB; ++d; }
+    const int out_dim = dg_k(d);
+    const float* W = a.kern[dg_dense(d)];
+    for (int h = 0; h < 2; ++h) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed + DG_PAIR_OFF + (size_t)(blockIdx.x - DG_NCHUNK) * PAIR_CHUNK_STRIDE +
+                                                            h * PAIR_HALF_BYTES);
+      for (int e = threadIdx.x; e < 128 * KB; e += blockDim.x) {
+        const int r = e / KB, k = e % KB;
+        dst[sw128_offset(r, k) / 2] = __float2bfloat16_rn(W[(size_t)(h * 128 + r) * out_dim + kb * KB + k]);
+      }
+    }
+    return;
+  }
   int c = blockIdx.x, d = 0;
   while (c >= dg_chunks(d)) { c -= dg_chunks(d); ++d; }
   const int out_dim = dg_k(d);
@@ -52,16 +62,6 @@ struct DgradSmem {
   static constexpr uint32_t N_BARS = 2 * NSTAGE + 2;
   static constexpr uint32_t TMEM_SLOT = BAR_OFF + N_BARS * 8;
   static constexpr uint32_t BYTES = TMEM_SLOT + 16;
-};
-
-struct DgradArgs {
-  const uint8_t* packed;        // dgrad weight image (dgrad_pack_kernel)
-  const float* head_w;          // w_sigma[256] then w_rgb[3][128], bf16-rounded fp32 (forward image tail)
-  const uint32_t* masks;        // [10][M][8] ReLU bit-masks written by the training forward (relu_mask_push, umma.cuh)
-  const float4* d_raw;          // [M] (d rgb_raw[3], d sigma_raw)
-  __nv_bfloat16* dZ;            // [10][M][256] out
-  int64_t n_samples;
-  int n_groups;
 };
 
 template <int NT, int NSTAGE>
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
 
 using namespace rnerf;
 
-extern "C" size_t rnerf_mlp_dgrad_packed_bytes(void) { return DG_PACKED_BYTES; }
+extern "C" size_t rnerf_mlp_dgrad_packed_bytes(void) { return DG_TOTAL_BYTES; }
 
 extern "C" int rnerf_mlp_dgrad_pack(const float* const* kernels, void* packed, void* stream) {
   RNERF_REQUIRE_PTR(kernels); RNERF_REQUIRE_PTR(packed);
@@ -552,7 +552,7 @@ extern "C" int rnerf_mlp_dgrad_pack(const float* const* kernels, void* packed, v
     if (!kernels[i]) { set_error("rnerf_mlp_dgrad_pack: null kernel %d", i); return RNERF_E_NULL; }
     a.kern[i] = kernels[i];
   }
-  dgrad_pack_kernel<<<DG_NCHUNK, 256, 0, (cudaStream_t)stream>>>(a, (uint8_t*)packed);
+  dgrad_pack_kernel<<<DG_NCHUNK + DGP_NCHUNK, 256, 0, (cudaStream_t)stream>>>(a, (uint8_t*)packed);
   count_launch();
   return check_launch("rnerf_mlp_dgrad_pack");
 }
@@ -587,6 +587,9 @@ extern "C" int rnerf_mlp_dgrad(const void* dgrad_packed, const void* fwd_packed,
   CUtensorMap tm;
   int rc = make_rows_tmap(&tm, dz_out, n_samples, N_MMA_LAYERS);
   if (rc) return rc;
+  // large batches: CTA-pair chain (epilogue of one tile pair under the MMAs of the other); RNERF_DGRAD_KERNEL=single disables
+  const char* kenv = getenv("RNERF_DGRAD_KERNEL");
+  if (!(kenv && kenv[0] == 's') && n_samples >= 74 * 512) return launch_mlp_dgrad_pair(a, tm, (cudaStream_t)stream);
   kfn<<<grid, 64 + 128 * NT, SL::BYTES, (cudaStream_t)stream>>>(a, tm);
   count_launch();
   return check_launch("rnerf_mlp_dgrad");

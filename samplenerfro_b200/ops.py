@@ -475,6 +475,17 @@ def mlp_dgrad_pack(kernels) -> torch.Tensor:
     return out
 
 
+def mlp_dgrad(dgrad_packed: torch.Tensor, packed: torch.Tensor, masks: torch.Tensor, d_raw: torch.Tensor) -> torch.Tensor:
+    """The dgrad chain: dZ [10, M, 256] bf16 (gradient wrt every MMA layer's pre-activation; layer 9 uses 128 columns) from
+    d_raw [M, 4] and the forward's ReLU bit-masks.  Batches of >= 37 888 samples run the CTA-pair kernel
+    (csrc/mlp_dgrad_pair.cu; RNERF_DGRAD_KERNEL=single forces the one-CTA kernel -- same results bit for bit)."""
+    M = d_raw.shape[0]
+    dz = torch.empty(10, M, 256, device=d_raw.device, dtype=torch.bfloat16)
+    check(_lib.load().rnerf_mlp_dgrad(_p(dgrad_packed), _p(packed), _p(_chk(masks, "relu masks", torch.int32)),
+                                      _p(_chk(d_raw.contiguous(), "d_raw")), M, _p(dz), _stream()), "rnerf_mlp_dgrad")
+    return dz
+
+
 def mlp_wgrad(x: torch.Tensor, x_cols: int, kx_valid: int, dz: torch.Tensor, n: int, gw: torch.Tensor,
               gb: Optional[torch.Tensor]) -> None:
     """gw[kx_valid, n] += x[:, :x_cols]^T dz[:, :n];  gb[n] += colsum(dz[:, :n]).  x: bf16 [M, ldx], dz: bf16 [M, 256]."""
@@ -522,10 +533,7 @@ def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None, input_gra
     K = [p for p in params[0::2]]
     dev = layers.device
     d_raw = _chk(d_raw.contiguous(), "d_raw")
-    dgp = mlp_dgrad_pack(K)
-    dz = torch.empty(10, M, 256, device=dev, dtype=torch.bfloat16)
-    check(lib.rnerf_mlp_dgrad(_p(dgp), _p(packed), _p(_chk(masks, "relu masks", torch.int32)), _p(d_raw), M, _p(dz), _stream()),
-          "rnerf_mlp_dgrad")
+    dz = mlp_dgrad(mlp_dgrad_pack(K), packed, masks, d_raw)
     if grad_out is not None:
         gK, gB = list(grad_out[0::2]), list(grad_out[1::2])
         for g in gK + gB:

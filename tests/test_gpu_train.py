@@ -172,6 +172,28 @@ def test_mlp_backward_kernels(cuda_lib, M):
             assert rel < 2e-2, (i, name, rel)
 
 
+@pytest.mark.parametrize("M", [74 * 512, 100001])
+def test_dgrad_pair_kernel_equals_single_cta_kernel(cuda_lib, M, monkeypatch):
+    """The CTA-pair dgrad chain (large batches) and the one-CTA chain produce the same dZ bit for bit (ragged tail included)."""
+    from samplenerfro_b200 import models, ops
+    gen = torch.Generator().manual_seed(M)
+    p = models.init_nerf_mlp_params(gen, "cuda")
+    pos = ((torch.rand(M, 3, generator=gen) * 2 - 1) * 2).cuda()
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3, generator=gen), dim=-1).cuda()
+    d_raw = torch.randn(M, 4, generator=gen).cuda() * 0.1
+    packed = ops.encmlp_pack(p)
+    _, (layers, enc, masks) = ops.encmlp_fwd_train(packed, pos, dirs)
+    dgp = ops.mlp_dgrad_pack([p[f"Dense_{i}"]["kernel"] for i in range(12)])
+    monkeypatch.delenv("RNERF_DGRAD_KERNEL", raising=False)
+    dz_pair = ops.mlp_dgrad(dgp, packed, masks, d_raw)
+    monkeypatch.setenv("RNERF_DGRAD_KERNEL", "single")
+    dz_one = ops.mlp_dgrad(dgp, packed, masks, d_raw)
+    torch.cuda.synchronize()
+    assert dz_one[:9].abs().sum().item() > 0
+    assert torch.equal(dz_pair[:9].view(torch.int16), dz_one[:9].view(torch.int16))
+    assert torch.equal(dz_pair[9, :, :128].view(torch.int16), dz_one[9, :, :128].view(torch.int16))
+
+
 def test_train_step_uses_no_library_gemm_for_the_radiance_mlps(cuda_lib):
     """The MLP backward must run this repo's kernels: the launch counter advances by the dgrad/wgrad/head launches."""
     from samplenerfro_b200 import _lib, models, ops
