@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RNERF_LIB") or os.path.join(_HERE, "librnerf_b200.so")
 
 _lib: Optional[C.CDLL] = None
-ABI_VERSION = 8      # include/rnerf_b200.h RNERF_ABI_VERSION
+ABI_VERSION = 9      # include/rnerf_b200.h RNERF_ABI_VERSION
 
 c_f32p = C.c_void_p
 c_i64 = C.c_int64
@@ -57,6 +57,11 @@ SIGNATURES = {
     "rnerf_mlp_head_grad": (C.c_int, [C.c_void_p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_generate_rays": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                       C.c_double, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_radiance_loss_ws_floats": (C.c_size_t, []),
+    "rnerf_radiance_loss_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, C.c_int, C.c_double, C.c_double,
+                                          C.c_double, c_f32p, c_f32p, C.c_void_p]),
+    "rnerf_radiance_loss_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, C.c_int, C.c_double, C.c_double,
+                                          C.c_double, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_sq_err": (C.c_int, [c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_sumsq": (C.c_int, [c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_grad_sumsq": (C.c_int, [c_f32p, c_f32p, c_i64, c_f32p, c_f32p, C.c_void_p]),

@@ -253,3 +253,39 @@ def composite(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias,
     with torch.no_grad():
         return ops.composite_fwd(raw, t, dirs, bkgd_raw, mask, white_bkgd, rgb_padding, sigma_bias,
                                  want_weights=want_weights, want_alpha=want_alpha)
+
+
+# ----------------------------------------------------------------------------- radiance-stage loss (train.py:75-162)
+class _RadianceLoss(torch.autograd.Function):
+    """loss + loss_c + bg_weight loss_bg + bg_smooth_weight loss_bg_smooth and its gradient as two kernels (csrc/loss.cu)
+    instead of ~70 elementwise / reduction launches on 48 KB operands."""
+
+    @staticmethod
+    def forward(ctx, rgb, rgb_c, trb, trans, env, px, bg_weight, bg_smooth_weight, gate):
+        rgb, rgb_c, px = rgb.contiguous(), rgb_c.contiguous(), px.contiguous()
+        trb = None if trb is None else trb.contiguous()
+        trans = None if trb is None else trans.contiguous()
+        env = None if env is None else env.contiguous()
+        out = ops.radiance_loss_fwd(rgb, rgb_c, trb, trans, px, env, bg_weight, bg_smooth_weight, gate)
+        ctx.cfg = (bg_weight, bg_smooth_weight, gate, trb is not None, env is not None)
+        e = rgb.new_empty(0)
+        ctx.save_for_backward(rgb, rgb_c, trb if trb is not None else e, trans if trans is not None else e,
+                              env if env is not None else e, px, out)
+        total, stats = out[0], out[1:]
+        ctx.mark_non_differentiable(stats)
+        return total, stats
+
+    @staticmethod
+    def backward(ctx, g_total, _g_stats):
+        rgb, rgb_c, trb, trans, env, px, out = ctx.saved_tensors
+        bg_weight, bg_smooth_weight, gate, has_bg, has_env = ctx.cfg
+        d_rgb, d_rgb_c, d_trb, d_env = ops.radiance_loss_bwd(rgb, rgb_c, trb if has_bg else None, trans if has_bg else None, px,
+                                                             env if has_env else None, bg_weight, bg_smooth_weight, gate, out,
+                                                             g_total.to(torch.float32))
+        return d_rgb, d_rgb_c, d_trb, None, d_env, None, None, None, None
+
+
+def radiance_loss(rgb, rgb_c, trb, trans, env, px, bg_weight: float, bg_smooth_weight: float, gate: float):
+    """Returns (total, stats) with stats = (loss, loss_c, loss_bg, loss_bg_smooth, psnr, psnr_c, sum(mask)) detached;
+    trb / trans = None drops the background term, env = None the smoothness term."""
+    return _RadianceLoss.apply(rgb, rgb_c, trb, trans, env, px, float(bg_weight), float(bg_smooth_weight), float(gate))

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librnerf_b200.so")
-SOURCES = ["api.cu", "grid.cu", "march.cu", "composite.cu", "resample.cu", "bkgd_mlp.cu", "encmlp.cu", "encmlp_pair.cu", "mlp_bwd.cu", "mlp_dgrad_pair.cu", "optim.cu", "rays.cu", "march_bwd.cu", "input_grad.cu"]
+SOURCES = ["api.cu", "grid.cu", "march.cu", "composite.cu", "resample.cu", "bkgd_mlp.cu", "encmlp.cu", "encmlp_pair.cu", "mlp_bwd.cu", "mlp_dgrad_pair.cu", "optim.cu", "loss.cu", "rays.cu", "march_bwd.cu", "input_grad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 NVCC_FLAGS += os.environ.get("RNERF_NVCC_EXTRA", "").split()   # development aid: -D switches for A/B builds

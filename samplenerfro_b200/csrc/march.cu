@@ -367,7 +367,13 @@ __global__ void __launch_bounds__(SO3 ? SO3_THREADS : MARCH_THREADS, SO3 ? 2 : 8
   // over all SMs and a CTA evaluates the MLP only at the steps its own few rays need; the warps without rays still take
   // part in every evaluation (warp_ray0 = n_rays: not live, nothing staged or flushed)
   const bool carrier = !SO3 || warp * 32 < rays_per_cta;        // warp-uniform; the other warps only join the evaluations
-  const int64_t warp_ray0 = !carrier ? n_rays : (blockIdx.x * (int64_t)(SO3 ? rays_per_cta : MARCH_THREADS)) + warp * 32;
+  // Radiance stage, small launches: a warp may carry fewer than 32 rays (rpw = rays_per_cta / 4 = 1 .. 32).  A warp steps in
+  // lockstep, so it waits for the table gathers at every step where ANY of its rays is inside a non-homogeneous brick; a
+  // training batch of random pixels has little in common (the union of 32 rays' active steps is ~2.5x one ray's) and too
+  // few warps to hide the latency (4096 rays = 128 warps on 148 SMs).  Fewer rays per warp -> more warps, each waiting only
+  // for its own rays; the surplus lanes shadow the warp's first ray (same addresses: no extra traffic, no extra divergence).
+  const int rpw = SO3 ? 32 : rays_per_cta / (MARCH_THREADS / 32);
+  const int64_t warp_ray0 = !carrier ? n_rays : (blockIdx.x * (int64_t)rays_per_cta) + warp * rpw;
   if (!SO3 && warp_ray0 >= n_rays) return;      // SO3: every warp stays for the block barriers of so3_eval
   So3Ring ring;
   if (SO3) {
@@ -376,15 +382,15 @@ __global__ void __launch_bounds__(SO3 ? SO3_THREADS : MARCH_THREADS, SO3 ? 2 : 8
     __syncthreads();
   }
   const int64_t ray = warp_ray0 + lane;
-  const bool live = ray < n_rays;
-  const int64_t rr = live ? ray : (n_rays - 1);
+  const bool live = lane < rpw && ray < n_rays;
+  const int64_t rr = live ? ray : (SO3 ? n_rays - 1 : warp_ray0);
   float ox = origins[3 * rr], oy = origins[3 * rr + 1], oz = origins[3 * rr + 2];
   float vx = viewdirs[3 * rr], vy = viewdirs[3 * rr + 1], vz = viewdirs[3 * rr + 2];
   float px = add(ox, mul(near, vx)), py = add(oy, mul(near, vy)), pz = add(oz, mul(near, vz));
   float t = near;
   const int sw = carrier ? warp : 0;            // (non-carrier warps never touch the staging buffers)
   float4* my_stage = &stage[sw][lane * PITCH];
-  const int rays_here = (int)max((int64_t)0, min((int64_t)32, n_rays - warp_ray0));
+  const int rays_here = (int)max((int64_t)0, min((int64_t)rpw, n_rays - warp_ray0));
   const int ray_stride4 = n_steps * RECF4;                            // float4 units between consecutive rays
   const bool t_vec = t_col != nullptr && (n_steps & 3) == 0 && (reinterpret_cast<uintptr_t>(t_col) & 15u) == 0;
   float* ts = tstage[sw];
@@ -1220,6 +1226,22 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   unsigned blocks = (unsigned)((n_rays + MARCH_THREADS - 1) / MARCH_THREADS);
   int rpc = MARCH_THREADS;
+  if (so3_w == nullptr) {
+    // radiance stage: rays per warp (see march_kernel) halved while the launch still has <= 7 warps per SM (measured on random
+    // pixels of the ship frame, scripts/march_rpw_probe.py: 512 rays 0.51 -> 0.35 ms at 1, 4096 rays 0.53 -> 0.46 at 4, 16 384
+    // unchanged at 16; with more warps the shadow lanes cost more issue slots than the shorter waits save); full frames keep 32
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int rpw = 32;
+    while (rpw > 1 && (n_rays + rpw / 2 - 1) / (rpw / 2) <= (int64_t)n_sm * 7) rpw >>= 1;
+    if (const char* e = getenv("RNERF_MARCH_RPW")) {     // development aid: 1, 2, 4, 8, 16 or 32
+      const int v = atoi(e);
+      if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) rpw = v;
+    }
+    rpc = rpw * (MARCH_THREADS / 32);
+    blocks = (unsigned)((n_rays + rpc - 1) / rpc);
+  }
   So3Args so3;
   memset(&so3, 0, sizeof(so3));
   size_t dyn = 0;

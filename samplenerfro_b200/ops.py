@@ -675,3 +675,37 @@ def image_mse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(1, device=a.device, dtype=torch.float32)
     check(_lib.load().rnerf_sq_err(_p(a), _p(b), a.numel(), _p(out), _stream()), "rnerf_sq_err")
     return out[0] / a.numel()
+
+
+def radiance_loss_fwd(rgb, rgb_c, trb, trans, px, env, bg_weight: float, bg_smooth_weight: float, gate: float) -> torch.Tensor:
+    """The radiance-stage loss terms of train.py:75-162 in one launch.  rgb / rgb_c / px: [B, 3]; trb (trans_rgb_bkgd [B, 3])
+    and trans [B, 1] or None; env [P, P, 3] or None.  Returns out [8] = (total, loss, loss_c, loss_bg, loss_bg_smooth, psnr,
+    psnr_c, sum(mask)), layout in include/rnerf_b200.h."""
+    lib = _lib.load()
+    B = rgb.shape[0]
+    ws = torch.zeros(lib.rnerf_radiance_loss_ws_floats(), device=rgb.device, dtype=torch.float32)
+    out = torch.empty(8, device=rgb.device, dtype=torch.float32)
+    for t in (rgb, rgb_c, px):
+        assert _chk(t, "loss input").shape == (B, 3)
+    check(lib.rnerf_radiance_loss_fwd(_p(rgb), _p(rgb_c), _p(None if trb is None else _chk(trb, "trans_rgb_bkgd")),
+                                      _p(None if trb is None else _chk(trans, "trans")), _p(px), B,
+                                      _p(None if env is None else _chk(env, "env")), 0 if env is None else int(env.shape[0]),
+                                      float(bg_weight), float(bg_smooth_weight), float(gate), _p(ws), _p(out), _stream()),
+          "rnerf_radiance_loss_fwd")
+    return out
+
+
+def radiance_loss_bwd(rgb, rgb_c, trb, trans, px, env, bg_weight: float, bg_smooth_weight: float, gate: float, out: torch.Tensor,
+                      g_total: torch.Tensor):
+    """Gradients of radiance_loss_fwd's total times the device scalar g_total: (d_rgb, d_rgb_c, d_trb | None, d_env | None)."""
+    lib = _lib.load()
+    B = rgb.shape[0]
+    d_rgb, d_rgb_c = torch.empty_like(rgb), torch.empty_like(rgb_c)
+    d_trb = None if trb is None else torch.empty_like(trb)
+    d_env = None if env is None else torch.empty_like(env)
+    g = _chk(g_total.reshape(1).contiguous(), "g_total")
+    check(lib.rnerf_radiance_loss_bwd(_p(rgb), _p(rgb_c), _p(trb), _p(trans), _p(px), B, _p(env),
+                                      0 if env is None else int(env.shape[0]), float(bg_weight), float(bg_smooth_weight),
+                                      float(gate), _p(out), _p(g), _p(d_rgb), _p(d_rgb_c), _p(d_trb), _p(d_env), _stream()),
+          "rnerf_radiance_loss_bwd")
+    return d_rgb, d_rgb_c, d_trb, d_env

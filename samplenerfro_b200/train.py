@@ -294,23 +294,21 @@ def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, ar
                                so3_window=batch.get("so3_window"))
     rgb, _d, _a, trans, trans_rgb_bkgd = ret[-1]
     px = batch["pixels"][..., :3]
-    loss = ((rgb - px) ** 2).mean()
     gate = 1.0 if annealed_alpha > 0 else 0.0
-    if args.bg_weight > 0:
-        mask_bg = (trans > 0.5).float()
-        loss_bg = gate * (mask_bg * torch.abs(trans_rgb_bkgd - px)).sum() / (mask_bg.sum() + 1)
-    else:
-        loss_bg = torch.zeros((), device=rgb.device)
     rgb_c = ret[0][0]
-    loss_c = ((rgb_c - px) ** 2).mean()
+    env = None
     if args.bg_smooth_weight > 0:
         vd = batch["env_rays"].viewdirs
         ps = vd.shape[0]
         env = model.apply(variables, vd.reshape(-1, 3), method=model.forward_envmap).reshape(ps, ps, -1)
-        loss_bg_smooth = gate * torch.mean(0.5 * ((env[1:, :] - env[:-1, :]) ** 2).reshape(-1)
-                                           + 0.5 * ((env[:, 1:] - env[:, :-1]) ** 2).reshape(-1))
-    else:
-        loss_bg_smooth = torch.zeros((), device=rgb.device)
+    # train.py:86-118: the image losses, the background term and the env-map smoothness term, fused with their gradient
+    # (csrc/loss.cu): loss = mse(rgb), loss_c = mse(rgb_c), loss_bg = gate sum(mask |trb - px|) / (sum(mask) + 1) with
+    # mask = trans > 0.5, loss_bg_smooth = gate mean(0.5 dv^2 + 0.5 dh^2) over the env patch
+    from . import autograd as ag
+    has_bg = args.bg_weight > 0
+    image_total, ls = ag.radiance_loss(rgb, rgb_c, trans_rgb_bkgd if has_bg else None, trans if has_bg else None, env, px,
+                                       args.bg_weight, args.bg_smooth_weight, gate)
+    loss, loss_c, loss_bg, loss_bg_smooth, psnr, psnr_c = ls[0], ls[1], ls[2], ls[3], ls[4], ls[5]
     loss_nrm = torch.zeros((), device=rgb.device)
     annealing_rate = 0.0                      # train.py:156 (the annealed expression is commented out): loss_nrm and loss_sp are multiplied by it
     if (str(getattr(args, "stage", "radiance")).startswith("all") and batch.get("pts") is not None
@@ -325,12 +323,9 @@ def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, ar
     else:
         leaves = tree_leaves(variables)
         weight_l2 = sum((z ** 2).sum() for z in leaves) / sum(z.numel() for z in leaves)
-    total = (loss + loss_c + args.bg_weight * loss_bg + args.bg_smooth_weight * loss_bg_smooth
-             + args.weight_decay_mult * weight_l2)
-    stats = {"loss": loss.detach(), "psnr": utils.compute_psnr(loss.detach()), "loss_c": loss_c.detach(),
-             "psnr_c": utils.compute_psnr(loss_c.detach()), "weight_l2": weight_l2.detach(),
-             "loss_bg": (args.bg_weight * loss_bg).detach() if torch.is_tensor(loss_bg) else loss_bg,
-             "loss_bg_smooth": loss_bg_smooth.detach() if torch.is_tensor(loss_bg_smooth) else loss_bg_smooth,
+    total = image_total + args.weight_decay_mult * weight_l2
+    stats = {"loss": loss, "psnr": psnr, "loss_c": loss_c, "psnr_c": psnr_c, "weight_l2": weight_l2.detach(),
+             "loss_bg": args.bg_weight * loss_bg, "loss_bg_smooth": loss_bg_smooth,
              "loss_sp": torch.zeros((), device=rgb.device), "loss_nrm": loss_nrm,
              "annealing_rate": annealed_alpha}
     return total, stats

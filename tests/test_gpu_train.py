@@ -1,5 +1,6 @@
 """Training step (config C shape, small): loss and gradients of the CUDA path vs the oracle's autograd."""
 import numpy as np
+import math
 import pytest
 import torch
 
@@ -319,3 +320,38 @@ def test_training_with_online_sparsity_flag(cuda_lib):
     for _ in range(4):                      # eager, eager, capture + replay, replay
         state, stats, rng = train.train_step(model, rng, state, batch, args)
     assert np.isfinite(float(stats["loss"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,ps,bgw,smw,gate", [(4096, 128, 0.025, 1.0, 1.0), (300, 5, 0.1, 0.5, 1.0), (1000, 16, 0.0, 0.0, 1.0),
+                                              (512, 8, 0.025, 1.0, 0.0)])
+def test_fused_radiance_loss_matches_tensor_expressions(cuda_lib, B, ps, bgw, smw, gate):
+    """csrc/loss.cu against train.py:86-118 written with torch ops: values to 1e-6 relative, gradients to 1e-6 of their scale,
+    including the upstream gradient scale and the inputs without gradient (trans, pixels)."""
+    from samplenerfro_b200 import autograd as ag
+    gen = torch.Generator().manual_seed(B)
+    mk = lambda *sh: torch.rand(*sh, generator=gen).cuda()
+    rgb, rgb_c, trb, env, px = mk(B, 3), mk(B, 3), mk(B, 3), mk(ps, ps, 3), mk(B, 3)
+    trans = mk(B, 1)
+    px[::7] = trb[::7]                        # exact zeros of |trb - px|: sign(0) = 0 like torch.abs
+    leaves = [t.clone().requires_grad_(True) for t in (rgb, rgb_c, trb, env)]
+    r, rc, tb, ev = leaves
+    loss = ((r - px) ** 2).mean(); loss_c = ((rc - px) ** 2).mean()
+    mask = (trans > 0.5).float()
+    loss_bg = gate * (mask * torch.abs(tb - px)).sum() / (mask.sum() + 1)
+    loss_sm = gate * torch.mean(0.5 * ((ev[1:, :] - ev[:-1, :]) ** 2).reshape(-1) + 0.5 * ((ev[:, 1:] - ev[:, :-1]) ** 2).reshape(-1))
+    ref = loss + loss_c + bgw * loss_bg + smw * loss_sm
+    (3.0 * ref).backward()
+    leaves2 = [t.clone().requires_grad_(True) for t in (rgb, rgb_c, trb, env)]
+    r2, rc2, tb2, ev2 = leaves2
+    total, st = ag.radiance_loss(r2, rc2, tb2 if bgw > 0 else None, trans if bgw > 0 else None, ev2 if smw > 0 else None, px, bgw, smw, gate)
+    (3.0 * total).backward()
+    close = lambda a, b: abs(float(a.detach() if torch.is_tensor(a) else a) - float(b)) <= 1e-6 * max(1.0, abs(float(b)))
+    assert close(total, ref) and close(st[0], loss) and close(st[1], loss_c)
+    assert close(st[2], loss_bg if bgw > 0 else 0.0) and close(st[3], loss_sm if smw > 0 else 0.0)
+    assert close(st[4], -10.0 * torch.log(loss) / math.log(10.0)) and close(st[5], -10.0 * torch.log(loss_c) / math.log(10.0))
+    for a, b, on in zip(leaves2, leaves, (True, True, bgw > 0, smw > 0)):
+        if not on:
+            assert a.grad is None
+            continue
+        assert (a.grad - b.grad).abs().max().item() <= 1e-6 * max(b.grad.abs().max().item(), 1e-12) + 1e-12
