@@ -259,44 +259,71 @@ __global__ void __launch_bounds__(64 + 128 * NT, 1) mlp_dgrad_kernel(const Dgrad
 __global__ void __launch_bounds__(256) mlp_head_grad_kernel(const __nv_bfloat16* __restrict__ H, const float4* __restrict__ d_raw,
                                                             int64_t n_samples, int rows_per_block,
                                                             float* __restrict__ out, float* __restrict__ out_sig) {
-  // 256 threads = 2 row streams x 128 column pairs: thread (s, p) reads columns 2p, 2p+1 of H7 (and of H9 when p < 64)
-  // as one 4-byte load per row, rows s, s+2, ... of the block's slab, four rows in flight.
+  // 256 threads = 4 row streams x 64 column quads: thread (s, c) reads columns 4c .. 4c+3 of H7 (and of H9 when c < 32) with
+  // one 8-byte load per row -- a warp covers 256 contiguous bytes of a row -- rows s, s+4, ... of a slab, four rows in flight.
+  // The grid is persistent (slabs are taken round-robin): the 644 atomics per block are paid ~600 times per launch, not once
+  // per 512 rows, and there is no partial last wave.  (The first version, 4-byte loads and one slab per block, ran at 1.8 TB/s
+  // with 40 % of the issue slots busy and 2.08 waves: profiles/r5d_train_backward_ncu_summary.txt.)
   const size_t layer_stride = (size_t)n_samples * 256;
-  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t m1 = min(m0 + rows_per_block, n_samples);
-  const int p = threadIdx.x & 127, s = threadIdx.x >> 7;
-  const uint32_t* H7 = reinterpret_cast<const uint32_t*>(H + 7 * layer_stride) + p;     // + m * 128 per row
-  const uint32_t* H9 = reinterpret_cast<const uint32_t*>(H + 9 * layer_stride) + p;
-  float sg0 = 0.f, sg1 = 0.f, r0 = 0.f, r1 = 0.f, g0 = 0.f, g1 = 0.f, b0 = 0.f, b1 = 0.f;
-  float s_r = 0.f, s_g = 0.f, s_b = 0.f, s_s = 0.f;
+  const int c = threadIdx.x & 63, s = threadIdx.x >> 6;
+  const uint2* H7 = reinterpret_cast<const uint2*>(H + 7 * layer_stride) + c;     // + m * 64 per row
+  const uint2* H9 = reinterpret_cast<const uint2*>(H + 9 * layer_stride) + c;
+  float sg[4] = {0.f, 0.f, 0.f, 0.f};
+  float rgb[4][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  float sb[4] = {0.f, 0.f, 0.f, 0.f};          // bias gradients (c == 0 only)
   constexpr int U = 4;
-  for (int64_t m = m0 + s; m < m1; m += 2 * U) {
-    uint32_t h7[U], h9[U];
-    float4 d[U];
+  for (int64_t m0 = (int64_t)blockIdx.x * rows_per_block; m0 < n_samples; m0 += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t m1 = min(m0 + rows_per_block, n_samples);
+    for (int64_t m = m0 + s; m < m1; m += 4 * U) {
+      uint2 h7[U], h9[U];
+      float4 d[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t mm = m + 2 * u;
-      const bool ok = mm < m1;
-      const int64_t mc = ok ? mm : m;
-      h7[u] = __ldg(H7 + (size_t)mc * 128);
-      h9[u] = p < 64 ? __ldg(H9 + (size_t)mc * 128) : 0u;
-      d[u] = ok ? __ldg(d_raw + mc) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+      for (int u = 0; u < U; ++u) {
+        const int64_t mm = m + 4 * u;
+        const bool ok = mm < m1;
+        const int64_t mc = ok ? mm : m;
+        h7[u] = __ldg(H7 + (size_t)mc * 64);
+        h9[u] = c < 32 ? __ldg(H9 + (size_t)mc * 64) : make_uint2(0u, 0u);
+        d[u] = ok ? __ldg(d_raw + mc) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      sg0 = fmaf(bf16_lo(h7[u]), d[u].w, sg0); sg1 = fmaf(bf16_hi(h7[u]), d[u].w, sg1);
-      const float a = bf16_lo(h9[u]), c = bf16_hi(h9[u]);
-      r0 = fmaf(a, d[u].x, r0); g0 = fmaf(a, d[u].y, g0); b0 = fmaf(a, d[u].z, b0);
-      r1 = fmaf(c, d[u].x, r1); g1 = fmaf(c, d[u].y, g1); b1 = fmaf(c, d[u].z, b1);
-      if (p == 0) { s_r += d[u].x; s_g += d[u].y; s_b += d[u].z; s_s += d[u].w; }
+      for (int u = 0; u < U; ++u) {
+        sg[0] = fmaf(bf16_lo(h7[u].x), d[u].w, sg[0]); sg[1] = fmaf(bf16_hi(h7[u].x), d[u].w, sg[1]);
+        sg[2] = fmaf(bf16_lo(h7[u].y), d[u].w, sg[2]); sg[3] = fmaf(bf16_hi(h7[u].y), d[u].w, sg[3]);
+        const float a[4] = {bf16_lo(h9[u].x), bf16_hi(h9[u].x), bf16_lo(h9[u].y), bf16_hi(h9[u].y)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          rgb[k][0] = fmaf(a[k], d[u].x, rgb[k][0]); rgb[k][1] = fmaf(a[k], d[u].y, rgb[k][1]); rgb[k][2] = fmaf(a[k], d[u].z, rgb[k][2]);
+        }
+        if (c == 0) { sb[0] += d[u].x; sb[1] += d[u].y; sb[2] += d[u].z; sb[3] += d[u].w; }
+      }
     }
   }
-  atomicAdd(out_sig + 2 * p, sg0); atomicAdd(out_sig + 2 * p + 1, sg1);
-  if (p < 64) {
-    atomicAdd(out + (2 * p) * 3, r0); atomicAdd(out + (2 * p) * 3 + 1, g0); atomicAdd(out + (2 * p) * 3 + 2, b0);
-    atomicAdd(out + (2 * p + 1) * 3, r1); atomicAdd(out + (2 * p + 1) * 3 + 1, g1); atomicAdd(out + (2 * p + 1) * 3 + 2, b1);
+  // fold the four row streams in shared memory, then one atomic per output element and block
+  __shared__ float red[3][64][16 + 4];
+  if (s > 0) {
+    float* r = red[s - 1][c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r[k] = sg[k]; r[4 + 3 * k] = rgb[k][0]; r[5 + 3 * k] = rgb[k][1]; r[6 + 3 * k] = rgb[k][2]; r[16 + k] = sb[k]; }
   }
-  if (p == 0) { atomicAdd(out + 384, s_r); atomicAdd(out + 385, s_g); atomicAdd(out + 386, s_b); atomicAdd(out_sig + 256, s_s); }
+  __syncthreads();
+  if (s == 0) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      const float* r = red[w][c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { sg[k] += r[k]; rgb[k][0] += r[4 + 3 * k]; rgb[k][1] += r[5 + 3 * k]; rgb[k][2] += r[6 + 3 * k]; sb[k] += r[16 + k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(out_sig + 4 * c + k, sg[k]);
+    if (c < 32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(out + (4 * c + k) * 3, rgb[k][0]); atomicAdd(out + (4 * c + k) * 3 + 1, rgb[k][1]); atomicAdd(out + (4 * c + k) * 3 + 2, rgb[k][2]);
+      }
+    }
+    if (c == 0) { atomicAdd(out + 384, sb[0]); atomicAdd(out + 385, sb[1]); atomicAdd(out + 386, sb[2]); atomicAdd(out_sig + 256, sb[3]); }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -599,8 +626,12 @@ extern "C" int rnerf_mlp_head_grad(const uint16_t* saved_h, const float* d_raw, 
                                    float* out_sigma_head, void* stream) {
   if (n_samples <= 0) return 0;
   RNERF_REQUIRE_PTR(saved_h); RNERF_REQUIRE_PTR(d_raw); RNERF_REQUIRE_PTR(out_rgb_head); RNERF_REQUIRE_PTR(out_sigma_head);
-  const int rows_per_block = 512;
-  const unsigned grid = (unsigned)((n_samples + rows_per_block - 1) / rows_per_block);
+  const int rows_per_block = 256;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  int64_t slabs = (n_samples + rows_per_block - 1) / rows_per_block;
+  const unsigned grid = (unsigned)(slabs < (int64_t)n_sm * 4 ? slabs : (int64_t)n_sm * 4);
   mlp_head_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)saved_h, (const float4*)d_raw, n_samples,
                                                                 rows_per_block, out_rgb_head, out_sigma_head);
   count_launch();
