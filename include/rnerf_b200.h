@@ -202,17 +202,19 @@ int rnerf_adam_step(float* theta, const float* grad, float* mu, float* nu, int64
 /* ---- the radiance-stage loss of /root/reference/train.py:75-162 and its gradient, two launches instead of ~70 tensor ops:
  *   total = mean((rgb - px)^2) + mean((rgb_c - px)^2)
  *         + bg_weight * gate * sum(mask |trans_rgb_bkgd - px|) / (sum(mask) + 1)         mask = trans > 0.5   (train.py:89-95)
- *         + bg_smooth_weight * gate * mean(0.5 dv^2 + 0.5 dh^2)   over the [patch][patch][3] env map's differences (:110-118)
+ *         + bg_smooth_weight * gate * mean(0.5 dv^2 + 0.5 dh^2)   over the differences of the env map [patch][patch][env_channels]
+ *           along its first two axes (:126-129; 3 channels for a whole patch -- a device's [P/N][P][3] shard is reshaped to
+ *           (P/N, P/N, 3N) by the reference, quirk kept)
  * gate = (annealed_alpha > 0).  trans_rgb_bkgd / trans may be NULL (no background term), env may be NULL (no smoothness
  * term).  ws: rnerf_radiance_loss_ws_floats() floats, ZERO before the first call (the kernel leaves it zeroed).
  * out[8]: total, loss, loss_c, loss_bg (gated, unweighted), loss_bg_smooth (gated), psnr, psnr_c, sum(mask).
  * _bwd: gradients of `total` times the device scalar g_total[0]; d_trans_rgb_bkgd / d_env NULL exactly when their input is. */
 size_t rnerf_radiance_loss_ws_floats(void);
 int rnerf_radiance_loss_fwd(const float* rgb, const float* rgb_c, const float* trans_rgb_bkgd, const float* trans,
-                            const float* pixels, int64_t n_rays, const float* env, int patch, double bg_weight,
+                            const float* pixels, int64_t n_rays, const float* env, int patch, int env_channels, double bg_weight,
                             double bg_smooth_weight, double gate, float* ws, float* out, void* stream);
 int rnerf_radiance_loss_bwd(const float* rgb, const float* rgb_c, const float* trans_rgb_bkgd, const float* trans,
-                            const float* pixels, int64_t n_rays, const float* env, int patch, double bg_weight,
+                            const float* pixels, int64_t n_rays, const float* env, int patch, int env_channels, double bg_weight,
                             double bg_smooth_weight, double gate, const float* out, const float* g_total, float* d_rgb,
                             float* d_rgb_c, float* d_trans_rgb_bkgd, float* d_env, void* stream);
 

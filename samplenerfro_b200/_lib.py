@@ -58,9 +58,9 @@ SIGNATURES = {
     "rnerf_generate_rays": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                       C.c_double, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_radiance_loss_ws_floats": (C.c_size_t, []),
-    "rnerf_radiance_loss_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, C.c_int, C.c_double, C.c_double,
+    "rnerf_radiance_loss_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, C.c_int, C.c_int, C.c_double, C.c_double,
                                           C.c_double, c_f32p, c_f32p, C.c_void_p]),
-    "rnerf_radiance_loss_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, C.c_int, C.c_double, C.c_double,
+    "rnerf_radiance_loss_bwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, c_f32p, C.c_int, C.c_int, C.c_double, C.c_double,
                                           C.c_double, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_sq_err": (C.c_int, [c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p]),
     "rnerf_sumsq": (C.c_int, [c_f32p, c_i64, c_f32p, C.c_void_p]),

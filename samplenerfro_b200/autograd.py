@@ -31,22 +31,36 @@ def _sink(model, name):
 
 class _RadianceMLP(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, sink, packed, pos, dirs, *params):
+    def forward(ctx, sink, fork, packed, pos, dirs, *params):
         raw, (layers, enc, masks) = ops.encmlp_fwd_train(packed, pos, dirs)
         ctx.sink = sink
+        ctx.fork = fork
         ctx.save_for_backward(packed, pos, dirs, layers, enc, masks, *params)
         return raw.view(pos.shape[0], pos.shape[1], 4)
 
     @staticmethod
     def backward(ctx, d_raw):
         packed, pos, dirs, layers, enc, masks, *params = ctx.saved_tensors
-        want_in = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]      # "all" stage: the samples depend on so3_mlp
+        want_in = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]      # "all" stage: the samples depend on so3_mlp
+        if ctx.fork is not None and ctx.sink is not None and not want_in:
+            # Radiance stage inside a training step (train._step_body): this backward is a leaf -- it only accumulates into
+            # the arena's gradient views -- so it is forked onto a side stream and joined before the gradient all-reduce.
+            # The other MLP's backward, the composite and background backward kernels then run beside it: per-rank
+            # batches of a multi-GPU step (512 rays) leave every one of these launches well under a wave.
+            side, keep = ctx.fork
+            cur = torch.cuda.current_stream()
+            d_raw = d_raw.contiguous()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.view(-1, 4), params, grad_out=ctx.sink)
+            keep.append((side, d_raw, packed, pos, dirs, layers, enc, masks))   # alive until the join (no cross-stream reuse)
+            return (None, None, None, None, None) + (None,) * len(params)
         grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.contiguous().view(-1, 4), params,
                                grad_out=ctx.sink, input_grads=want_in)
         d_pos, d_dirs = grads.pop() if want_in else (None, None)
         if ctx.sink is not None:        # already accumulated into the arena's .grad views
-            return (None, None, d_pos, d_dirs) + (None,) * len(params)
-        return (None, None, d_pos, d_dirs, *grads)
+            return (None, None, None, d_pos, d_dirs) + (None,) * len(params)
+        return (None, None, None, d_pos, d_dirs, *grads)
 
 
 def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
@@ -54,7 +68,9 @@ def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: tor
     p = variables["params"][name]
     packed = model._packed(variables, name)
     if _needs_grad(p):
-        return _RadianceMLP.apply(_sink(model, name), packed, pos, dirs, *_mlp_param_list(p, 12))
+        forks = getattr(model, "_bwd_fork", None)
+        return _RadianceMLP.apply(_sink(model, name), None if forks is None else forks.get(name), packed, pos, dirs,
+                                  *_mlp_param_list(p, 12))
     with torch.no_grad():
         return ops.encmlp_fwd(packed, pos, dirs).view(pos.shape[0], pos.shape[1], 4)
 

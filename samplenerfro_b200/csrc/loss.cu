@@ -22,9 +22,9 @@ struct RadianceLossArgs {
   const float* trb;      // [B][3] trans * rgb_bkgd of the fine pass, or null (bg_weight = 0)
   const float* trans;    // [B]    fine-pass transmittance (with trb)
   const float* px;       // [B][3] target pixels
-  const float* env;      // [P][P][3] environment patch, or null (bg_smooth_weight = 0)
+  const float* env;      // [P][P][C] environment patch, or null (bg_smooth_weight = 0)
   int64_t n_rays;
-  int patch;
+  int patch, env_c;      // C = 3 for a whole patch; the reference reshapes a device's [P/N][P][3] shard to (P/N, P/N, -1) (train.py:127-128)
   float bg_weight, bg_smooth_weight, gate;
 };
 
@@ -60,13 +60,13 @@ __global__ void __launch_bounds__(RL_THREADS) radiance_loss_fwd_kernel(const Rad
     }
   }
   if (a.env != nullptr) {
-    const int P = a.patch;
-    const int64_t n_el = (int64_t)P * P * 3;
+    const int P = a.patch, C = a.env_c;
+    const int64_t n_el = (int64_t)P * P * C;
     for (int64_t e = tid; e < n_el; e += nthr) {
-      const int i = (int)(e / (3 * P)), j = (int)((e / 3) % P);
+      const int i = (int)(e / ((int64_t)C * P)), j = (int)((e / C) % P);
       const float v = a.env[e];
-      if (i + 1 < P) { const float d = a.env[e + 3 * P] - v; s[4] += d * d; }
-      if (j + 1 < P) { const float d = a.env[e + 3] - v; s[5] += d * d; }
+      if (i + 1 < P) { const float d = a.env[e + (int64_t)C * P] - v; s[4] += d * d; }
+      if (j + 1 < P) { const float d = a.env[e + C] - v; s[5] += d * d; }
     }
   }
 #pragma unroll
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(RL_THREADS) radiance_loss_fwd_kernel(const Rad
     const float loss = t[0] * inv_n, loss_c = t[1] * inv_n;
     const float loss_bg = a.trb != nullptr ? a.gate * t[2] / (t[3] + 1.f) : 0.f;
     float loss_sm = 0.f;
-    if (a.env != nullptr) loss_sm = a.gate * 0.5f * (t[4] + t[5]) / (float)((int64_t)(a.patch - 1) * a.patch * 3);
+    if (a.env != nullptr) loss_sm = a.gate * 0.5f * (t[4] + t[5]) / (float)((int64_t)(a.patch - 1) * a.patch * a.env_c);
     out[0] = loss + loss_c + a.bg_weight * loss_bg + a.bg_smooth_weight * loss_sm;
     out[1] = loss; out[2] = loss_c; out[3] = loss_bg; out[4] = loss_sm;
     out[5] = -10.f * logf(loss) / 2.302585092994046f;      // utils.compute_psnr
@@ -121,17 +121,17 @@ __global__ void __launch_bounds__(RL_THREADS) radiance_loss_bwd_kernel(const Rad
     }
   }
   if (d_env != nullptr) {
-    const int P = a.patch;
-    const int64_t n_el = (int64_t)P * P * 3;
-    const float k = up * a.bg_smooth_weight * a.gate / (float)((int64_t)(P - 1) * P * 3);   // d/dx of 0.5 d^2 = d
+    const int P = a.patch, C = a.env_c;
+    const int64_t n_el = (int64_t)P * P * C, row = (int64_t)C * P;
+    const float k = up * a.bg_smooth_weight * a.gate / (float)((int64_t)(P - 1) * P * C);   // d/dx of 0.5 d^2 = d
     for (int64_t e = tid; e < n_el; e += nthr) {
-      const int i = (int)(e / (3 * P)), j = (int)((e / 3) % P);
+      const int i = (int)(e / row), j = (int)((e / C) % P);
       const float v = a.env[e];
       float acc = 0.f;
-      if (i > 0) acc += v - a.env[e - 3 * P];
-      if (i + 1 < P) acc -= a.env[e + 3 * P] - v;
-      if (j > 0) acc += v - a.env[e - 3];
-      if (j + 1 < P) acc -= a.env[e + 3] - v;
+      if (i > 0) acc += v - a.env[e - row];
+      if (i + 1 < P) acc -= a.env[e + row] - v;
+      if (j > 0) acc += v - a.env[e - C];
+      if (j + 1 < P) acc -= a.env[e + C] - v;
       d_env[e] = k * acc;
     }
   }
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(RL_THREADS) radiance_loss_bwd_kernel(const Rad
 
 static int loss_grid(const RadianceLossArgs& a) {
   int64_t work = a.n_rays;
-  if (a.env != nullptr) work = work > (int64_t)a.patch * a.patch * 3 ? work : (int64_t)a.patch * a.patch * 3;
+  if (a.env != nullptr) work = work > (int64_t)a.patch * a.patch * a.env_c ? work : (int64_t)a.patch * a.patch * a.env_c;
   int64_t b = (work + RL_THREADS - 1) / RL_THREADS;
   return (int)(b < 1 ? 1 : (b > RL_MAX_BLOCKS ? RL_MAX_BLOCKS : b));
 }
@@ -149,12 +149,12 @@ static int loss_grid(const RadianceLossArgs& a) {
 using namespace rnerf;
 
 static int fill_args(RadianceLossArgs& a, const float* rgb, const float* rgb_c, const float* trb, const float* trans, const float* px,
-                     int64_t n_rays, const float* env, int patch, double bg_weight, double bg_smooth_weight, double gate) {
+                     int64_t n_rays, const float* env, int patch, int env_c, double bg_weight, double bg_smooth_weight, double gate) {
   RNERF_REQUIRE(n_rays > 0, RNERF_E_SHAPE, "rnerf_radiance_loss: n_rays must be positive");
   RNERF_REQUIRE_PTR(rgb); RNERF_REQUIRE_PTR(rgb_c); RNERF_REQUIRE_PTR(px);
   RNERF_REQUIRE(trb == nullptr || trans != nullptr, RNERF_E_NULL, "rnerf_radiance_loss: trans_rgb_bkgd given without trans");
-  RNERF_REQUIRE(env == nullptr || patch >= 2, RNERF_E_SHAPE, "rnerf_radiance_loss: the env patch must be at least 2 x 2");
-  a.rgb = rgb; a.rgb_c = rgb_c; a.trb = trb; a.trans = trans; a.px = px; a.env = env; a.n_rays = n_rays; a.patch = patch;
+  RNERF_REQUIRE(env == nullptr || (patch >= 2 && env_c >= 1), RNERF_E_SHAPE, "rnerf_radiance_loss: the env patch must be at least 2 x 2 x 1");
+  a.rgb = rgb; a.rgb_c = rgb_c; a.trb = trb; a.trans = trans; a.px = px; a.env = env; a.n_rays = n_rays; a.patch = patch; a.env_c = env_c;
   a.bg_weight = (float)bg_weight; a.bg_smooth_weight = (float)bg_smooth_weight; a.gate = (float)gate;
   return 0;
 }
@@ -162,10 +162,10 @@ static int fill_args(RadianceLossArgs& a, const float* rgb, const float* rgb_c, 
 extern "C" size_t rnerf_radiance_loss_ws_floats(void) { return 1 + (size_t)RL_MAX_BLOCKS * RL_NSUM; }
 
 extern "C" int rnerf_radiance_loss_fwd(const float* rgb, const float* rgb_c, const float* trans_rgb_bkgd, const float* trans,
-                                       const float* pixels, int64_t n_rays, const float* env, int patch, double bg_weight,
+                                       const float* pixels, int64_t n_rays, const float* env, int patch, int env_channels, double bg_weight,
                                        double bg_smooth_weight, double gate, float* ws, float* out, void* stream) {
   RadianceLossArgs a;
-  int rc = fill_args(a, rgb, rgb_c, trans_rgb_bkgd, trans, pixels, n_rays, env, patch, bg_weight, bg_smooth_weight, gate);
+  int rc = fill_args(a, rgb, rgb_c, trans_rgb_bkgd, trans, pixels, n_rays, env, patch, env_channels, bg_weight, bg_smooth_weight, gate);
   if (rc) return rc;
   RNERF_REQUIRE_PTR(ws); RNERF_REQUIRE_PTR(out);
   radiance_loss_fwd_kernel<<<loss_grid(a), RL_THREADS, 0, (cudaStream_t)stream>>>(a, ws, out);
@@ -174,11 +174,11 @@ extern "C" int rnerf_radiance_loss_fwd(const float* rgb, const float* rgb_c, con
 }
 
 extern "C" int rnerf_radiance_loss_bwd(const float* rgb, const float* rgb_c, const float* trans_rgb_bkgd, const float* trans,
-                                       const float* pixels, int64_t n_rays, const float* env, int patch, double bg_weight,
+                                       const float* pixels, int64_t n_rays, const float* env, int patch, int env_channels, double bg_weight,
                                        double bg_smooth_weight, double gate, const float* out, const float* g_total, float* d_rgb,
                                        float* d_rgb_c, float* d_trans_rgb_bkgd, float* d_env, void* stream) {
   RadianceLossArgs a;
-  int rc = fill_args(a, rgb, rgb_c, trans_rgb_bkgd, trans, pixels, n_rays, env, patch, bg_weight, bg_smooth_weight, gate);
+  int rc = fill_args(a, rgb, rgb_c, trans_rgb_bkgd, trans, pixels, n_rays, env, patch, env_channels, bg_weight, bg_smooth_weight, gate);
   if (rc) return rc;
   RNERF_REQUIRE_PTR(out); RNERF_REQUIRE_PTR(g_total); RNERF_REQUIRE_PTR(d_rgb); RNERF_REQUIRE_PTR(d_rgb_c);
   RNERF_REQUIRE((trans_rgb_bkgd == nullptr) == (d_trans_rgb_bkgd == nullptr) && (env == nullptr) == (d_env == nullptr), RNERF_E_NULL,

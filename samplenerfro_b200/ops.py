@@ -677,9 +677,18 @@ def image_mse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out[0] / a.numel()
 
 
+def _env_dims(env):
+    """(patch, channels) of an env map [P, P, C] (C = 3 for a whole patch; a [P/N, P, 3] shard reshaped like the reference
+    does, train.py:127-128, has C = 3 N)."""
+    if env is None:
+        return 0, 0
+    assert env.dim() == 3 and env.shape[0] == env.shape[1], f"env map must be [P, P, C], got {tuple(env.shape)}"
+    return int(env.shape[0]), int(env.shape[2])
+
+
 def radiance_loss_fwd(rgb, rgb_c, trb, trans, px, env, bg_weight: float, bg_smooth_weight: float, gate: float) -> torch.Tensor:
     """The radiance-stage loss terms of train.py:75-162 in one launch.  rgb / rgb_c / px: [B, 3]; trb (trans_rgb_bkgd [B, 3])
-    and trans [B, 1] or None; env [P, P, 3] or None.  Returns out [8] = (total, loss, loss_c, loss_bg, loss_bg_smooth, psnr,
+    and trans [B, 1] or None; env [P, P, C] or None.  Returns out [8] = (total, loss, loss_c, loss_bg, loss_bg_smooth, psnr,
     psnr_c, sum(mask)), layout in include/rnerf_b200.h."""
     lib = _lib.load()
     B = rgb.shape[0]
@@ -689,7 +698,7 @@ def radiance_loss_fwd(rgb, rgb_c, trb, trans, px, env, bg_weight: float, bg_smoo
         assert _chk(t, "loss input").shape == (B, 3)
     check(lib.rnerf_radiance_loss_fwd(_p(rgb), _p(rgb_c), _p(None if trb is None else _chk(trb, "trans_rgb_bkgd")),
                                       _p(None if trb is None else _chk(trans, "trans")), _p(px), B,
-                                      _p(None if env is None else _chk(env, "env")), 0 if env is None else int(env.shape[0]),
+                                      _p(None if env is None else _chk(env, "env")), *_env_dims(env),
                                       float(bg_weight), float(bg_smooth_weight), float(gate), _p(ws), _p(out), _stream()),
           "rnerf_radiance_loss_fwd")
     return out
@@ -705,7 +714,7 @@ def radiance_loss_bwd(rgb, rgb_c, trb, trans, px, env, bg_weight: float, bg_smoo
     d_env = None if env is None else torch.empty_like(env)
     g = _chk(g_total.reshape(1).contiguous(), "g_total")
     check(lib.rnerf_radiance_loss_bwd(_p(rgb), _p(rgb_c), _p(trb), _p(trans), _p(px), B, _p(env),
-                                      0 if env is None else int(env.shape[0]), float(bg_weight), float(bg_smooth_weight),
+                                      *_env_dims(env), float(bg_weight), float(bg_smooth_weight),
                                       float(gate), _p(out), _p(g), _p(d_rgb), _p(d_rgb_c), _p(d_trb), _p(d_env), _stream()),
           "rnerf_radiance_loss_bwd")
     return d_rgb, d_rgb_c, d_trb, d_env

@@ -9,6 +9,7 @@ fourth trainable bucket: its gradient comes from the reverse sweep of the eikona
 from __future__ import annotations
 
 import dataclasses
+import os
 import math
 from typing import Any, Dict, List, Optional
 
@@ -29,6 +30,10 @@ def tree_leaves(tree) -> List[torch.Tensor]:
     else:
         out.append(tree)
     return out
+
+
+# development aid: RNERF_FORK_BACKWARD=0 keeps the whole backward on one stream (A/B runs)
+_FORK_BACKWARD = os.environ.get("RNERF_FORK_BACKWARD", "1") != "0"
 
 
 class ParamArena:
@@ -290,17 +295,32 @@ def loss_fn(model, variables, batch, args, key_0, key_1, jitter=None, u=None, ar
     if str(getattr(args, "stage", "radiance")).startswith("ior"):
         return _ior_stage_loss(model, variables, batch, args, annealed_alpha, arena)
     rays = batch["rays"]
+    env, env_stream = None, getattr(model, "_env_stream", None)
+    if args.bg_smooth_weight > 0:
+        vd = batch["env_rays"].viewdirs
+        ps = vd.shape[0]
+        if vd.shape[0] * vd.shape[1] > 4096:
+            # a whole 128 x 128 patch fills the GPU on its own: beside the march and the MLP backwards it only delays their
+            # persistent CTAs (measured 6.35 -> 6.59 ms at 4096 rays); the 16-row shard of an 8-GPU step gains 0.11 of 1.73 ms
+            env_stream = None
+        if env_stream is not None:
+            # inside a training step: the env patch depends on nothing the rays produce, so its forward runs on a side stream
+            # under the (latency-bound) march -- and autograd runs its backward on that stream too, beside the MLP backwards
+            model._env_forked = True          # train._step_body joins the stream after backward
+            env_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(env_stream):
+                env = model.apply(variables, vd.reshape(-1, 3), method=model.forward_envmap).reshape(ps, ps, -1)
     ret, loss_sp = model.apply(variables, key_0, key_1, rays, args.randomized, annealed_alpha, jitter=jitter, u=u,
                                so3_window=batch.get("so3_window"))
     rgb, _d, _a, trans, trans_rgb_bkgd = ret[-1]
     px = batch["pixels"][..., :3]
     gate = 1.0 if annealed_alpha > 0 else 0.0
     rgb_c = ret[0][0]
-    env = None
     if args.bg_smooth_weight > 0:
-        vd = batch["env_rays"].viewdirs
-        ps = vd.shape[0]
-        env = model.apply(variables, vd.reshape(-1, 3), method=model.forward_envmap).reshape(ps, ps, -1)
+        if env_stream is not None:
+            torch.cuda.current_stream().wait_stream(env_stream)
+        else:
+            env = model.apply(variables, vd.reshape(-1, 3), method=model.forward_envmap).reshape(ps, ps, -1)
     # train.py:86-118: the image losses, the background term and the env-map smoothness term, fused with their gradient
     # (csrc/loss.cu): loss = mse(rgb), loss_c = mse(rgb_c), loss_bg = gate sum(mask |trb - px|) / (sum(mask) + 1) with
     # mask = trans > 0.5, loss_bg_smooth = gate mean(0.5 dv^2 + 0.5 dh^2) over the env patch
@@ -362,12 +382,35 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
     if state.grid_opt is not None:
         state.grid_opt.zero_grad()
     model._grad_sink, model._theta_flat = arena.sinks, arena.theta_flat
+    keep: list = []
+    if arena.theta.is_cuda and _FORK_BACKWARD:
+        # the radiance MLPs' backwards (leaves: they only accumulate into arena.grad) run on side streams next to everything
+        # autograd executes after them; joined below, before the gradients are reduced (autograd._RadianceMLP.backward)
+        if getattr(state, "_bwd_streams", None) is None:
+            state._bwd_streams = [torch.cuda.Stream(device=arena.theta.device) for _ in range(2)]
+        names = os.environ.get("RNERF_FORK_BACKWARD_MLPS", "fine_mlp,coarse_mlp").split(",")
+        model._bwd_fork = {n: (st, keep) for n, st in zip(names, state._bwd_streams)}
+        if os.environ.get("RNERF_FORK_ENV", "1") != "0":
+            if getattr(state, "_env_stream", None) is None:
+                state._env_stream = torch.cuda.Stream(device=arena.theta.device)
+            model._env_stream = state._env_stream
     try:
         total, stats = loss_fn(model, state.params, batch, args, key_0, key_1, jitter=jitter, u=u, arena=arena)
         if total.requires_grad:       # ("ior" stage with the arena: only the closed-form weight-decay gradient exists)
             total.backward()
     finally:
         model._grad_sink = None
+        model._bwd_fork = None
+        model._env_stream = None
+        if keep:
+            for st in {id(k[0]): k[0] for k in keep}.values():      # only the streams a backward was actually forked onto
+                torch.cuda.current_stream().wait_stream(st)
+            keep.clear()
+        if getattr(model, "_env_forked", False):
+            # the env patch's backward accumulates into arena.grad on its own stream and hands autograd no leaf gradient,
+            # so the engine has nothing to synchronise on: join explicitly before the gradients are read
+            torch.cuda.current_stream().wait_stream(state._env_stream)
+            model._env_forked = False
     arena.allreduce_mean(world_size, group)
     if state.grid_opt is not None:
         state.grid_opt.allreduce_mean(world_size, group)

@@ -14,6 +14,8 @@ ap.add_argument("--eager", action="store_true", help="no CUDA-graph capture of t
 ap.add_argument("--stage", default="radiance", help='"radiance" (configs[2]) or "all" (so3_mlp trained through the scan adjoint)')
 ap.add_argument("--learn-grid", action="store_true", help="extension: the IoR grid is a trainable parameter too (gradient by the "
                 "reverse sweep, all-reduced and updated by a fused Adam)")
+ap.add_argument("--emulate-world", type=int, default=0, help="development aid: one process with the per-rank shapes of a "
+                "W-GPU step (batch / W rays, 128 / W env rows) and no communicator -- the per-rank latency floor of the step")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -33,14 +35,15 @@ model, variables = models.construct_nerf(0, None, args, ndim, nmin, nmax, n)
 if a.learn_grid:
     model.enable_grid_learning()
 state = train.TrainState.create(variables, args, model=model)
-B = a.batch // world
+shape_world = a.emulate_world if a.emulate_world > 0 else world
+B = a.batch // shape_world
 rays_hw = synthetic.blender_rays(synthetic.camera_pose(0.7, 1.0, 4.03), 800, 800)
 flat = utils.namedtuple_map(lambda r: r.reshape(-1, r.shape[-1]), rays_hw)
 gen = torch.Generator().manual_seed(rank)
 idx = torch.randint(0, 640000, (B,), generator=gen)
 rays = utils.namedtuple_map(lambda r: r[idx].to(dev).contiguous(), flat)
 env = synthetic.blender_rays(synthetic.camera_pose(1.3, 0.8, 4.03), 128, 128, camera_angle_x=0.2)
-_e0, _e1 = utils.shard_range(128, rank, world)       # the reference shards the whole batch dict, env patch included (utils.shard)
+_e0, _e1 = utils.shard_range(128, rank, shape_world)       # the reference shards the whole batch dict, env patch included (utils.shard)
 env = utils.namedtuple_map(lambda r: r[_e0:_e1].to(dev).contiguous(), env)
 batch = {"rays": rays, "pixels": torch.rand(B, 3, generator=gen).to(dev), "env_rays": env, "annealed_alpha": 0.5}
 

@@ -323,15 +323,16 @@ def test_training_with_online_sparsity_flag(cuda_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,ps,bgw,smw,gate", [(4096, 128, 0.025, 1.0, 1.0), (300, 5, 0.1, 0.5, 1.0), (1000, 16, 0.0, 0.0, 1.0),
-                                              (512, 8, 0.025, 1.0, 0.0)])
-def test_fused_radiance_loss_matches_tensor_expressions(cuda_lib, B, ps, bgw, smw, gate):
+@pytest.mark.parametrize("B,ps,C,bgw,smw,gate", [(4096, 128, 3, 0.025, 1.0, 1.0), (300, 5, 3, 0.1, 0.5, 1.0), (1000, 16, 3, 0.0, 0.0, 1.0),
+                                                (512, 8, 3, 0.025, 1.0, 0.0),
+                                                (512, 16, 24, 0.025, 1.0, 1.0)])    # a [16, 128, 3] shard of an 8-device step, reshaped
+def test_fused_radiance_loss_matches_tensor_expressions(cuda_lib, B, ps, C, bgw, smw, gate):
     """csrc/loss.cu against train.py:86-118 written with torch ops: values to 1e-6 relative, gradients to 1e-6 of their scale,
     including the upstream gradient scale and the inputs without gradient (trans, pixels)."""
     from samplenerfro_b200 import autograd as ag
     gen = torch.Generator().manual_seed(B)
     mk = lambda *sh: torch.rand(*sh, generator=gen).cuda()
-    rgb, rgb_c, trb, env, px = mk(B, 3), mk(B, 3), mk(B, 3), mk(ps, ps, 3), mk(B, 3)
+    rgb, rgb_c, trb, env, px = mk(B, 3), mk(B, 3), mk(B, 3), mk(ps, ps, C), mk(B, 3)
     trans = mk(B, 1)
     px[::7] = trb[::7]                        # exact zeros of |trb - px|: sign(0) = 0 like torch.abs
     leaves = [t.clone().requires_grad_(True) for t in (rgb, rgb_c, trb, env)]
