@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 9
+#define RNERF_ABI_VERSION 10
 #define RNERF_PATH_STRIDE 12         /* full records */
 #define RNERF_PATH_STRIDE_COMPACT 8
 
@@ -85,16 +85,21 @@ int rnerf_march_fwd(const float* table, const float* bricks /* from rnerf_grid_b
  * when given it wins and is read at run time, so a captured CUDA graph of the training step follows the annealing
  * schedule (train.py:350-351) instead of replaying its capture-time window (so3_window_host may then be NULL).  The same
  * pair of arguments appears in rnerf_so3_predict and rnerf_march_all_bwd.
- * so3_tc_packed: rnerf_so3_tc_pack(so3_w) or NULL.  When given, launches large enough to keep the rays of a CTA in lockstep
- * (full frames) with compact records evaluate so3_mlp on the tensor pipe (tcgen05.mma kind::tf32, 3xTF32 split: fp32-grade
+ * so3_tc_packed: rnerf_so3_tc_pack(so3_w) or NULL.  When given, full frames with compact records and all small launches
+ * (training batches) evaluate so3_mlp on the tensor pipe (tcgen05.mma kind::f16 on fp16 hi/lo split operands: fp32-grade
  * products, positions within the same 1e-4 of the reference); otherwise the fp32 CUDA-core chain runs.
+ * so3_saved: NULL, or (training) a buffer of rnerf_so3_saved_floats(n_rays, n_steps) floats in which the forward leaves the four
+ * hidden activations of every so3_mlp evaluation, [(ray * n_steps + step)][4][128]; only the slots of evaluated (ray, step)
+ * pairs are written.  rnerf_march_all_bwd given the same buffer reads them back instead of recomputing the forward.
+ * rnerf_so3_saved_floats returns 0 when the launch would not run the kernel that writes it (pass NULL then).
  * Outputs as rnerf_march_fwd (idx_grad is the un-rotated grad n). */
 size_t rnerf_so3_weight_floats(void);
+size_t rnerf_so3_saved_floats(int64_t n_rays, int n_steps);
 int rnerf_march_all_fwd(const float* table, const float* bricks, const int ndim_host[3], const double nmin_host[3],
                         const double nmax_host[3], const float* origins, const float* viewdirs, int64_t n_rays,
                         double near, double far, int n_steps, int rec_floats, const float* so3_w,
                         const double so3_window_host[10], const float* so3_window_dev, const void* so3_tc_packed,
-                        float* path, float* t_col, void* stream);
+                        float* so3_saved, float* path, float* t_col, void* stream);
 
 /* ray_dir[B][S][3] = safe_l2_normalize(v) of every record: the `ray_dir` array of PathSampler.__call__
  * (rnerf/eikonal_utils.py:113), for callers that want the whole bent path (extract_mesh.py:178). */
@@ -268,7 +273,8 @@ int rnerf_march_all_bwd(const float* table, const float* bricks, const int ndim_
                         const double nmax_host[3], const float* path, int rec_floats, int64_t n_rays, double near,
                         double far, int n_steps, const int32_t* jitter, int n_coarse, const float* d_pos_c,
                         const float* d_dir_c, const float* so3_w, const float* so3_wt, const double so3_window_host[10],
-                        const float* so3_window_dev, float* g_so3, float* d_origins, float* d_viewdirs, float* d_table, void* stream);
+                        const float* so3_window_dev, const float* so3_saved /* or NULL */, float* g_so3, float* d_origins,
+                        float* d_viewdirs, float* d_table, void* stream);
 int rnerf_grid_table_bwd(const float* d_table, const int ndim_host[3], const double nmin_host[3], const double nmax_host[3],
                          float* d_n, void* stream);
 

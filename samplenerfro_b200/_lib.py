@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RNERF_LIB") or os.path.join(_HERE, "librnerf_b200.so")
 
 _lib: Optional[C.CDLL] = None
-ABI_VERSION = 9      # include/rnerf_b200.h RNERF_ABI_VERSION
+ABI_VERSION = 10      # include/rnerf_b200.h RNERF_ABI_VERSION
 
 c_f32p = C.c_void_p
 c_i64 = C.c_int64
@@ -36,9 +36,10 @@ SIGNATURES = {
     "rnerf_march_fwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                   c_f32p, c_i64, C.c_double, C.c_double, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_so3_weight_floats": (C.c_size_t, []),
+    "rnerf_so3_saved_floats": (C.c_size_t, [c_i64, C.c_int]),
     "rnerf_march_all_fwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                       c_f32p, c_i64, C.c_double, C.c_double, C.c_int, C.c_int, c_f32p, C.POINTER(C.c_double),
-                                      c_f32p, C.c_void_p, c_f32p, c_f32p, C.c_void_p]),
+                                      c_f32p, C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_path_dirs": (C.c_int, [c_f32p, C.c_int, c_i64, C.c_int, c_f32p, C.c_void_p]),
     "rnerf_select": (C.c_int, [c_f32p, C.c_int, c_i64, C.c_int, C.c_void_p, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_encmlp_packed_bytes": (C.c_size_t, []),
@@ -81,7 +82,7 @@ SIGNATURES = {
     "rnerf_so3_transpose": (C.c_int, [c_f32p, c_f32p, C.c_void_p]),
     "rnerf_march_all_bwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                       C.c_int, c_i64, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, c_f32p, c_f32p,
-                                      c_f32p, c_f32p, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+                                      c_f32p, c_f32p, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "rnerf_grid_table_bwd": (C.c_int, [c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,
                                        C.c_void_p]),
     "rnerf_composite_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64, C.c_int, C.c_int, C.c_double,

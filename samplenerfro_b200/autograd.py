@@ -181,8 +181,12 @@ class _MarchAll(torch.autograd.Function):
         # the forward evaluates so3_mlp on the tensor pipe (fp16 hi/lo split operands, fp32-grade); the hi/lo weight image is
         # rebuilt from this step's weights (one small kernel)
         so3_tc = ops.so3_tc_pack(w) if so3 is not None else None
+        # ... and leaves the hidden activations of every evaluation for the reverse sweep (2 KB per evaluated (ray, step))
+        saved = None
+        if so3 is not None and os.environ.get("RNERF_SO3_SAVE", "1") != "0":
+            saved = ops.so3_saved_buffer(origins.shape[0], model.num_march_steps, origins.device)
         path = ops.march(table, model.ndim, model.nmin, model.nmax, origins, viewdirs, model.near, model.far,
-                         model.num_march_steps, bricks=bricks, compact=compact, so3=so3, so3_tc=so3_tc)
+                         model.num_march_steps, bricks=bricks, compact=compact, so3=so3, so3_tc=so3_tc, so3_saved=saved)
         pos_c, dir_c, t_c, _ = ops.select(path, jitter)
         ctx.model, ctx.sink, ctx.window = model, sink, window
         rec, t_col = path.rec, path.t
@@ -192,13 +196,13 @@ class _MarchAll(torch.autograd.Function):
             pos_c, dir_c, t_c, rec, t_col = pos_c[inv], dir_c[inv], t_c[inv], rec[inv], t_col[inv]
         none = jitter.new_empty(0)
         ctx.save_for_backward(w if w is not None else none, path.rec, jitter, perm if perm is not None else none, table,
-                              bricks if bricks is not None else none)
+                              bricks if bricks is not None else none, saved if saved is not None else none)
         ctx.mark_non_differentiable(t_c, rec, t_col)
         return pos_c, dir_c, t_c, rec, t_col
 
     @staticmethod
     def backward(ctx, d_pos_c, d_dir_c, _dt, _drec, _dtcol):
-        w, rec, jitter, perm, table, bricks = ctx.saved_tensors
+        w, rec, jitter, perm, table, bricks, saved = ctx.saved_tensors
         m = ctx.model
 
         def z(g):
@@ -209,7 +213,7 @@ class _MarchAll(torch.autograd.Function):
         so3 = (w, ctx.window) if w.numel() else None
         g, _, _ = ops.march_all_bwd(table, m.ndim, m.nmin, m.nmax, rec, m.near, m.far, jitter, z(d_pos_c), z(d_dir_c), so3,
                                     bricks=bricks if bricks.numel() else None, g_so3=ctx.sink if so3 is not None else None,
-                                    d_table=d_table)
+                                    d_table=d_table, so3_saved=saved if saved.numel() else None)
         n_par = len(ctx.needs_input_grad) - 10
         if ctx.sink is not None or so3 is None:
             return (None,) * 8 + (d_table, None) + (None,) * n_par

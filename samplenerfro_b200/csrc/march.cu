@@ -744,7 +744,8 @@ struct MtcSmem {
   static constexpr uint32_t PART_OFF = P_OFF + 3 * TC_N * 4;                                 // head partial sums [4][3][64] (over RAW, + 2.25 KB)
   static constexpr uint32_t W4_OFF = PART_OFF + 12 * TC_N * 4;                               // Dense_4 kernel [128][3] + bias[3] (+pad)
   static constexpr uint32_t CNT = W4_OFF + (3 * SO3_W + 4) * 4;                              // counts[8] | exit flag | chunks consumed
-  static constexpr uint32_t BAR_OFF = CNT + 64;                                               // full[4], empty[4], acc, act
+  static constexpr uint32_t SLOT_OFF = CNT + 64;                                              // int[64]: (ray, step) slot of each column (training)
+  static constexpr uint32_t BAR_OFF = SLOT_OFF + TC_N * 4;                                    // full[4], empty[4], acc, act
   static constexpr uint32_t TMEM_SLOT = BAR_OFF + (2 * MTC_SLOTS + 2) * 8;
   static constexpr uint32_t BYTES = TMEM_SLOT + 16;
 };
@@ -765,9 +766,10 @@ struct MtcEval {
 
 // raw = so3_mlp(annealed_pos_enc(p)) for the CTA's active rays on the tensor pipe.  All 256 worker threads call this.
 __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int warp, int lane, bool act, float px, float py, float pz,
-                                            float& r0, float& r1, float& r2) {
+                                            float& r0, float& r1, float& r2, int slot = 0 /* ray * n_steps + step, with a.saved */) {
   uint8_t* smem = ev.smem;
   int* cnt = reinterpret_cast<int*>(smem + MtcSmem::CNT);
+  int* slots = reinterpret_cast<int*>(smem + MtcSmem::SLOT_OFF);
   float* P = reinterpret_cast<float*>(smem + MtcSmem::P_OFF);
   const float* hs = reinterpret_cast<const float*>(smem + TcSmem::HS);
   const int tid = warp * 32 + lane;
@@ -799,7 +801,7 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
     const bool mine = act && idx >= col0 && idx < col0 + TC_N;
     const int col = idx - col0;
     mtc_workers_sync();                          // counts read; the previous pass's RAW / HS are no longer needed
-    if (mine) { P[col] = px; P[TC_N + col] = py; P[2 * TC_N + col] = pz; }
+    if (mine) { P[col] = px; P[TC_N + col] = py; P[2 * TC_N + col] = pz; slots[col] = slot; }
     mtc_workers_sync();
     // ---- encoding: warp w takes columns w, w + 8, ...; lane = feature (two per lane: f and f + 32) -> 128-byte row writes
     if (!(a.dbg & 4)) {
@@ -825,7 +827,7 @@ __device__ __forceinline__ void so3_eval_tc(const So3Args& a, MtcEval& ev, int w
     for (int l = 0; l < 4; ++l) {
       mbar_wait(ev.bar_acc, ev.acc_phase); ev.acc_phase ^= 1u;
       tc_fence_after();
-      if (has_cols && !(a.dbg & 2)) tc_epilogue32(l, smem, tmem_lane, m, half * 32, __ldg(bias + l * SO3_W + m));
+      if (has_cols && !(a.dbg & 2)) tc_epilogue32(l, smem, tmem_lane, m, half * 32, __ldg(bias + l * SO3_W + m), a.saved, slots, n_here);
       if (l < 3) publish();
     }
     tc_fence_before();
@@ -1122,7 +1124,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) march_ragged_tc_kernel(const f
       }
       if (mtc_workers_or(need)) {
         float r0, r1, r2;
-        so3_eval_tc(so3, ev, warp, lane, need, px, py, pz, r0, r1, r2);
+        so3_eval_tc(so3, ev, warp, lane, need, px, py, pz, r0, r1, r2, (int)(rr * n_steps + k));
         if (need) {
           so3_rotate(r0, r1, r2, gx, gy, gz);
           advance(gx, gy, gz);
@@ -1208,7 +1210,7 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
                       const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
                       double near, double far, int n_steps, int rec_floats, const float* so3_w,
                       const double* so3_window, const float* so3_window_dev, const void* so3_tc_packed, float* path, float* t_col,
-                      void* stream) {
+                      void* stream, float* so3_saved = nullptr) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_fwd: n_rays < 0");
   RNERF_REQUIRE(n_steps >= 2, RNERF_E_SHAPE, "rnerf_march_fwd: n_steps must be >= 2 (step = (far-near)/(S-1))");
@@ -1279,6 +1281,7 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
   if (so3_w != nullptr && so3_tc_packed != nullptr && rec_floats == 8 && rpc == MARCH_THREADS &&
       !(getenv("RNERF_SO3_TC") != nullptr && atoi(getenv("RNERF_SO3_TC")) == 0)) {
     RNERF_REQUIRE(aligned16(so3_tc_packed), RNERF_E_ALIGN, "rnerf_march_all_fwd: so3_tc_packed must be 16-byte aligned");
+    RNERF_REQUIRE(so3_saved == nullptr, RNERF_E_SHAPE, "rnerf_march_all_fwd: so3_saved given for a full-frame launch (see rnerf_so3_saved_floats)");
     cudaError_t e = cudaFuncSetAttribute(march_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MtcSmem::BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(march_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MtcSmem::BYTES);
     if (e != cudaSuccess) { set_error("rnerf_march_all_fwd: cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e)); return (int)e; }
@@ -1299,6 +1302,10 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
       !(getenv("RNERF_SO3_TC") != nullptr && atoi(getenv("RNERF_SO3_TC")) == 0)) {
     // a small launch with the packed hi/lo image: the ragged march with the tensor-pipe evaluator
     RNERF_REQUIRE(aligned16(so3_tc_packed), RNERF_E_ALIGN, "rnerf_march_all_fwd: so3_tc_packed must be 16-byte aligned");
+    RNERF_REQUIRE(so3_saved == nullptr || (double)n_rays * n_steps < 2147483648.0, RNERF_E_SHAPE,
+                  "rnerf_march_all_fwd: so3_saved needs n_rays * n_steps < 2^31");
+    so3.saved = so3_saved;
+    so3_saved = nullptr;        // consumed
     cudaError_t e = cudaSuccess;
 #define RNERF_RAGGED_TC_LAUNCH(R, F)                                                                                         \
     e = cudaFuncSetAttribute(march_ragged_tc_kernel<R, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MtcSmem::BYTES);   \
@@ -1313,6 +1320,9 @@ static int march_impl(const float* table, const float* bricks, const int ndim[3]
     count_launch();
     return check_launch("rnerf_march_all_fwd(ragged tc)");
   }
+  RNERF_REQUIRE(so3_saved == nullptr, RNERF_E_SHAPE,
+                "rnerf_march_all_fwd: so3_saved is only written by the ragged tensor-pipe march (small launch + so3_tc_packed); "
+                "rnerf_so3_saved_floats() says whether a launch qualifies");
   if (so3_w != nullptr && rpc < MARCH_THREADS) {          // a small launch: rays not in lockstep (see march_all_ragged_kernel)
     cudaError_t e = cudaSuccess;
     slots = RAGGED_SLOTS;
@@ -1353,11 +1363,23 @@ extern "C" int rnerf_march_all_fwd(const float* table, const float* bricks, cons
                                    const double nmax[3], const float* origins, const float* viewdirs, int64_t n_rays,
                                    double near, double far, int n_steps, int rec_floats, const float* so3_w,
                                    const double so3_window[10], const float* so3_window_dev, const void* so3_tc_packed,
-                                   float* path, float* t_col, void* stream) {
+                                   float* so3_saved, float* path, float* t_col, void* stream) {
   RNERF_REQUIRE_PTR(so3_w);
   RNERF_REQUIRE(so3_window != nullptr || so3_window_dev != nullptr, RNERF_E_NULL, "rnerf_march_all_fwd: no so3 window given");
   return march_impl(table, bricks, ndim, nmin, nmax, origins, viewdirs, n_rays, near, far, n_steps, rec_floats, so3_w,
-                    so3_window, so3_window_dev, so3_tc_packed, path, t_col, stream);
+                    so3_window, so3_window_dev, so3_tc_packed, path, t_col, stream, so3_saved);
+}
+
+// Floats of the `so3_saved` buffer a training forward of n_rays x n_steps may hand to rnerf_march_all_fwd, or 0 when that
+// launch would not run the ragged tensor-pipe march (the only kernel that writes it).
+extern "C" size_t rnerf_so3_saved_floats(int64_t n_rays, int n_steps) {
+  if (n_rays <= 0 || n_steps <= 0 || (double)n_rays * n_steps >= 2147483648.0) return 0;
+  if (getenv("RNERF_SO3_TC") != nullptr && atoi(getenv("RNERF_SO3_TC")) == 0) return 0;
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if (so3_rays_per_cta(n_rays, n_sm) >= MARCH_THREADS) return 0;
+  return (size_t)n_rays * n_steps * SO3_SAVED_FLOATS;
 }
 
 extern "C" int rnerf_select(const float* path, int rec_floats, int64_t n_rays, int n_steps, const int32_t* jitter,

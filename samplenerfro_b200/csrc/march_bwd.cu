@@ -48,6 +48,7 @@ struct So3BwdArgs {
   float* gw;             // gradient image, same layout as w, accumulated into
   float window[10];
   const float* window_dev;   // device copy of the window or NULL (So3Args::window_dev)
+  const float* saved;        // hidden activations left by the training forward (So3Args::saved), or NULL: recompute them
 };
 
 __global__ void __launch_bounds__(256) so3_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt) {
@@ -194,8 +195,9 @@ constexpr int BW_RING_SLOTS = 3;
 struct So3BwdStream {
   const float* w;
   const float* wt;
+  bool saved;            // the forward's activations are read back: only the transposed chunks 8..17 are streamed
   __device__ __forceinline__ void operator()(uint32_t g, const float*& src, uint32_t& bytes) const {
-    const int c = (int)(g % (uint32_t)BW_NCHUNK);
+    const int c = saved ? 8 + (int)(g % (uint32_t)(BW_NCHUNK - 8)) : (int)(g % (uint32_t)BW_NCHUNK);
     if (c < 8) {
       // chunk -> (first row, rows) of the [504][128] forward matrix: segments start at rows 0, 60, 188, 316, 444
       const int row0 = c == 0 ? 0 : (c == 7 ? 444 : 60 + (c - 1) * BW_CH);
@@ -324,7 +326,8 @@ __device__ __forceinline__ void wgrad_rows(const DzRows& z, const float* __restr
 // In (threads with `act`): position p, lookup gradient g, adjoint dG of the rotated gradient.
 // Out (threads with `act`): dg (adjoint of g), dp (adjoint of p through the encoding).  Parameter gradients -> a.gw.
 __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int* cnt, So3Ring& ring, int warp, int lane, bool act,
-                                            const float p[3], const float g[3], const float dG[3], float dg[3], float dp[3]) {
+                                            const float p[3], const float g[3], const float dG[3], float dg[3], float dp[3],
+                                            int slot /* ray * n_steps + step: the evaluation's record in a.saved */) {
   float* X = sm + BW_OFF_X;
   float* H = sm + BW_OFF_H;
   float* D = sm + BW_OFF_D;
@@ -336,7 +339,8 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
   const int j = tid & 63, h = tid >> 6;
   const float* bias = a.w + SO3_OFF_B;
   float* gbias = a.gw + SO3_OFF_B;
-  const So3BwdStream stream{a.w, a.wt};
+  const So3BwdStream stream{a.w, a.wt, a.saved != nullptr};
+  int* SLOT = reinterpret_cast<int*>(R + 3 * BW_RP);     // (row 3 of R is unused)
   ring_prime(ring, tid, stream);
   __syncthreads();                               // the previous evaluation has finished with cnt and the buffers
   const unsigned bal = __ballot_sync(0xffffffffu, act);
@@ -358,7 +362,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     const bool mine = act && idx >= col0 && idx < col0 + BW_COLS;
     const int col = idx - col0;
     if (col0 > 0) __syncthreads();               // another pass: everyone is done with the buffers of the previous one
-    if (mine) { P[col] = p[0]; P[BW_RP + col] = p[1]; P[2 * BW_RP + col] = p[2]; }
+    if (mine) { P[col] = p[0]; P[BW_RP + col] = p[1]; P[2 * BW_RP + col] = p[2]; SLOT[col] = slot; }
     __syncthreads();
     // ---- encoding, all threads: feature k*6 + c = sin(2^k p_c) w_k, k*6 + 3 + c = sin(2^k p_c + pi/2) w_k.  Unused columns
     // are zeroed: their dZ stays exactly 0 through the chain, and 0 * (finite activation) adds nothing
@@ -372,9 +376,32 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
       }
       X[f * BW_RP + cc] = v;
     }
+    float acc[2][BW_CPT];
+    if (a.saved != nullptr) {
+      // ---- the forward march left every hidden activation of this evaluation in global memory (2 KB per column): read them
+      // back instead of recomputing four layers (8 of the 18 weight chunks and their barrier rounds).  Consecutive threads
+      // read consecutive neurons of one column; unused columns are zero (their dZ stays 0 through the chain)
+      // thread tid owns row n = tid (= layer * 128 + neuron) of H: its value for every live column, eight loads in flight,
+      // then the whole 32-column row with conflict-free 16-byte stores
+      static_assert(BW_THREADS == 4 * SO3_W && BW_COLS == 32, "one thread per saved activation row");
+      float hv[BW_COLS];
+#pragma unroll
+      for (int c8 = 0; c8 < BW_COLS; c8 += 8) {
+        if (c8 < n_here) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            hv[c8 + u] = c8 + u < n_here ? __ldg(a.saved + (size_t)SLOT[c8 + u] * (4 * SO3_W) + tid) : 0.f;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) hv[c8 + u] = 0.f;
+        }
+      }
+      float4* hrow = reinterpret_cast<float4*>(H + tid * BW_RP);
+#pragma unroll
+      for (int q = 0; q < BW_COLS / 4; ++q) hrow[q] = make_float4(hv[4 * q], hv[4 * q + 1], hv[4 * q + 2], hv[4 * q + 3]);
+    } else {
     // (the first chunk barrier of the GEMM publishes X)
     // ---- forward, keeping every hidden activation
-    float acc[2][BW_CPT];
     zero_acc(acc);
     gemm_ring(acc, ring, tid, stream, SO3_IN, SO3_W, X, j, h, true);
     relu_bias_store(acc, bias, H, j, h);
@@ -388,6 +415,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, H + 2 * HL, j, h, true);  // skip concat [h, inputs]
     gemm_ring(acc, ring, tid, stream, SO3_IN, SO3_W, X, j, h, true);
     relu_bias_store(acc, bias + 3 * SO3_W, H + 3 * HL, j, h);
+    }
     __syncthreads();
     const float* H4 = H + 3 * HL;
     const float* W4 = a.w + SO3_OFF_W4;
@@ -607,7 +635,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) march_all_bwd_kernel(
     }
     if (__syncthreads_or(need)) {
       float dg[3] = {0.f, 0.f, 0.f}, dpm[3] = {0.f, 0.f, 0.f};
-      so3_fwd_bwd(so3, sm, cnt, ring, warp, lane, need, p, g, dG, dg, dpm);
+      so3_fwd_bwd(so3, sm, cnt, ring, warp, lane, need, p, g, dG, dg, dpm, (int)(rr * n_steps + k));
       if (need) {
         finish(p, hn, dn, dg, dpm, jx, jy, jz);
         inject(k, v);
@@ -644,8 +672,8 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
                                    const double nmax[3], const float* path, int rec_floats, int64_t n_rays, double near,
                                    double far, int n_steps, const int32_t* jitter, int n_coarse, const float* d_pos_c,
                                    const float* d_dir_c, const float* so3_w, const float* so3_wt,
-                                   const double so3_window[10], const float* so3_window_dev, float* g_so3, float* d_origins,
-                                   float* d_viewdirs,
+                                   const double so3_window[10], const float* so3_window_dev, const float* so3_saved, float* g_so3,
+                                   float* d_origins, float* d_viewdirs,
                                    float* d_table, void* stream) {
   RNERF_REQUIRE_PTR(table); RNERF_REQUIRE_PTR(ndim); RNERF_REQUIRE_PTR(nmin); RNERF_REQUIRE_PTR(nmax);
   RNERF_REQUIRE(n_rays >= 0, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_rays < 0");
@@ -669,6 +697,9 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   a.w = so3_w; a.wt = so3_wt; a.gw = g_so3;
   for (int k = 0; k < 10; ++k) a.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
   a.window_dev = so3_w != nullptr ? so3_window_dev : nullptr;
+  a.saved = so3_w != nullptr ? so3_saved : nullptr;
+  RNERF_REQUIRE(a.saved == nullptr || (double)n_rays * n_steps < 2147483648.0, RNERF_E_SHAPE,
+                "rnerf_march_all_bwd: so3_saved needs n_rays * n_steps < 2^31");
   const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 64 + 8 * SO3_MAX_SLOTS + (size_t)BW_RING_SLOTS * BW_SLOT_FLOATS * 4 +
                      (((size_t)n_steps * 2 + 15) & ~(size_t)15);
   RNERF_REQUIRE(dyn <= 227 * 1024, RNERF_E_SHAPE, "rnerf_march_all_bwd: n_steps too large for the step map in shared memory");

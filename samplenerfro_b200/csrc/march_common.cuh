@@ -51,7 +51,10 @@ struct So3Args {
   const float* window_dev;   // the same 10 values in device memory, or NULL: read at run time, so a captured CUDA graph follows
                              // a changing annealed_alpha (train.py:350-351) instead of freezing the capture-time window
   int dbg;                   // development aid (RNERF_SO3_TC_DEBUG; timing experiments only, results are wrong when set)
+  float* saved;              // training forward (ragged tensor-pipe march): the four hidden activations of every evaluation are
+                             // left here for the reverse sweep, [(ray * n_steps + step)][4][128] fp32, or NULL
 };
+constexpr int SO3_SAVED_FLOATS = 4 * SO3_W;    // per (ray, step) slot
 template <typename A>
 __device__ __forceinline__ float so3_window_at(const A& a, int k) {
   return a.window_dev != nullptr ? __ldg(a.window_dev + k) : a.window[k];

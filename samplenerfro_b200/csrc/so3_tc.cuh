@@ -128,10 +128,19 @@ __device__ __forceinline__ void tc_issue_layer(int l, uint32_t sbase, uint32_t t
 // Epilogue of a hidden layer for one neuron m (thread = TMEM lane) and 32 of the 64 columns (first column c0): bias + ReLU,
 // then either the next layer's B operand (hi / lo halves: element (row c, k = m)) or, for the last hidden layer, the plain
 // fp32 head input HS[m][c].  `tmem_addr` addresses this thread's lane and column c0.
-__device__ __forceinline__ void tc_epilogue32(int l, uint8_t* smem, uint32_t tmem_addr, int m, int c0, float bias) {
+__device__ __forceinline__ void tc_epilogue32(int l, uint8_t* smem, uint32_t tmem_addr, int m, int c0, float bias,
+                                              float* __restrict__ saved = nullptr, const int* __restrict__ slots = nullptr, int n_here = 0) {
   uint32_t v[32];
   tmem_ld32(tmem_addr, v);
   tmem_ld_wait();
+  if (saved != nullptr) {
+    // training: the post-ReLU activation of neuron m for every live column goes to that column's (ray, step) slot -- a warp
+    // writes 128 contiguous bytes per column -- so that the reverse sweep need not recompute the forward
+    float* dst = saved + l * 128 + m;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)            // (fully unrolled: v[] stays in registers)
+      if (c0 + j < n_here) dst[(size_t)slots[c0 + j] * (4 * 128)] = fmaxf(__uint_as_float(v[j]) + bias, 0.f);
+  }
   if (l < 3) {
     uint8_t* hi = smem + TcSmem::H_HI + (m >> 6) * TC_B_BYTES;
     uint8_t* lo = smem + TcSmem::H_LO + (m >> 6) * TC_B_BYTES;

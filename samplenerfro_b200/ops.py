@@ -93,6 +93,16 @@ class BentPath(NamedTuple):
         return self.rec.shape[-1] == PATH_STRIDE_COMPACT
 
 
+def so3_saved_buffer(n_rays: int, n_steps: int, device, max_bytes: int = 24 << 30) -> Optional[torch.Tensor]:
+    """Uninitialised buffer for the hidden activations of the so3_mlp evaluations of a training forward (2 KB per (ray, step)
+    slot; only evaluated slots are ever written or read), or None when the launch would not run the kernel that writes it
+    (a full-frame launch, RNERF_SO3_TC=0) or the buffer would exceed `max_bytes`."""
+    n = int(_lib.load().rnerf_so3_saved_floats(int(n_rays), int(n_steps)))
+    if n == 0 or 4 * n > max_bytes:
+        return None
+    return torch.empty(n, device=device, dtype=torch.float32)
+
+
 def so3_pack(p: Dict) -> torch.Tensor:
     """so3_mlp parameters (model_utils.MLP 60 -> 128 x4 (+60 after layer 2) -> 3, rnerf/ior_utils.py:147-152) as the flat
     fp32 image rnerf_march_all_fwd reads: the 5 kernels, then the 5 biases."""
@@ -122,8 +132,10 @@ def _window_args(window):
 def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n_steps: int,
           out: Optional[BentPath] = None, bricks: Optional[torch.Tensor] = None, compact: bool = False,
           t_col: bool = True, so3: Optional[Tuple[torch.Tensor, Sequence[float]]] = None,
-          so3_tc: Optional[torch.Tensor] = None) -> BentPath:
+          so3_tc: Optional[torch.Tensor] = None, so3_saved: Optional[torch.Tensor] = None) -> BentPath:
     """PathSampler.__call__ (rnerf/eikonal_utils.py:101-124).  Returns the BentPath.
+    `so3_saved` = so3_saved_buffer(B, n_steps) (training): the forward leaves the hidden activations of every so3_mlp
+    evaluation there and march_all_bwd reads them back instead of recomputing them.
     `bricks` (from grid_bricks) lets the kernel skip the gathers in homogeneous space; results are bit-identical.
     `compact` drops idx_grad from the records (8 instead of 12 floats per step).
     `so3` = (so3_pack(...) weights, 10 window values): the "all" stage, where every step rotates grad n by the so3_mlp
@@ -149,7 +161,8 @@ def march(table, ndim, nmin, nmax, origins, viewdirs, near: float, far: float, n
         _chk(w, "so3 weights")
         win, win_dev = _window_args(window)
         check(_lib.load().rnerf_march_all_fwd(_p(table), _p(bricks), nd, lo, hi, _p(origins), _p(viewdirs), B, float(near),
-                                              float(far), int(n_steps), W, _p(w), win, win_dev, _p(so3_tc), _p(out.rec), _p(out.t),
+                                              float(far), int(n_steps), W, _p(w), win, win_dev, _p(so3_tc),
+                                              _p(None if so3_saved is None else _chk(so3_saved, "so3_saved")), _p(out.rec), _p(out.t),
                                               _stream()),
               "rnerf_march_all_fwd")
         return out
@@ -250,7 +263,8 @@ def so3_transpose(w: torch.Tensor) -> torch.Tensor:
 
 def march_all_bwd(table, ndim, nmin, nmax, path, near: float, far: float, jitter: torch.Tensor, d_pos_c: torch.Tensor,
                   d_dir_c: torch.Tensor, so3: Optional[Tuple[torch.Tensor, Sequence[float]]], bricks: Optional[torch.Tensor] = None,
-                  g_so3: Optional[torch.Tensor] = None, want_ray_grads: bool = False, d_table: Optional[torch.Tensor] = None):
+                  g_so3: Optional[torch.Tensor] = None, want_ray_grads: bool = False, d_table: Optional[torch.Tensor] = None,
+                  so3_saved: Optional[torch.Tensor] = None):
     """Reverse sweep of the "all"-stage scan (rnerf/eikonal_utils.py:30-49,75-82 under jax.value_and_grad, train.py:164):
     from the loss gradients of the coarse samples, d_pos_c / d_dir_c [B,Nc,3] at march steps `jitter` (strictly
     increasing), to the gradient of so3_mlp.  Returns (g_so3 [so3 image layout, accumulated into when given],
@@ -272,7 +286,7 @@ def march_all_bwd(table, ndim, nmin, nmax, path, near: float, far: float, jitter
         d_d = torch.empty(B, 3, device=rec.device) if want_ray_grads else None
         nd, lo, hi = _geom(ndim, nmin, nmax)
         check(_lib.load().rnerf_march_all_bwd(_p(table), _p(bricks), nd, lo, hi, _p(rec), W, B, float(near), float(far), S,
-                                              _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), None, None, None, None, None, _p(d_o),
+                                              _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), None, None, None, None, None, None, _p(d_o),
                                               _p(d_d), _p(d_table), _stream()), "rnerf_march_all_bwd")
         return None, d_o, d_d
     _chk(w, "so3 weights")
@@ -288,7 +302,8 @@ def march_all_bwd(table, ndim, nmin, nmax, path, near: float, far: float, jitter
     nd, lo, hi = _geom(ndim, nmin, nmax)
     win, win_dev = _window_args(window)
     check(_lib.load().rnerf_march_all_bwd(_p(table), _p(bricks), nd, lo, hi, _p(rec), W, B, float(near), float(far), S,
-                                          _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), _p(w), _p(wt), win, win_dev, _p(g), _p(d_o),
+                                          _p(jitter), Nc, _p(d_pos_c), _p(d_dir_c), _p(w), _p(wt), win, win_dev,
+                                          _p(None if so3_saved is None else _chk(so3_saved, "so3_saved")), _p(g), _p(d_o),
                                           _p(d_d), _p(d_table), _stream()), "rnerf_march_all_bwd")
     return g, d_o, d_d
 

@@ -81,6 +81,27 @@ def test_march_adjoint_matches_oracle_autograd(cuda_lib, bundle):
         # agreement of the forward.  Stated tolerance: 1e-4 in l2 per leaf (measured 3e-7 .. 5e-6 on B200).
         assert min(r[1] for r in rows) > 0.999999, min(rows, key=lambda r: r[1])
         assert max(r[2] for r in rows) < 1e-4, max(rows, key=lambda r: r[2])
+    # training path: the forward on the tensor pipe leaves its hidden activations, the sweep reads them back instead of
+    # recomputing them -- same tolerance against the oracle, and against the recomputing sweep on the same path
+    saved = ops.so3_saved_buffer(B, S, "cuda")
+    assert saved is not None and saved.numel() == B * S * 512
+    saved.fill_(float("nan"))                 # an unwritten slot that is read would poison the gradients
+    path_tc = ops.march(tab, ndim, nmin, nmax, o.cuda(), d.cuda(), 2.0, 6.0, S, bricks=bricks, compact=True, so3=(w, window),
+                        so3_tc=ops.so3_tc_pack(w), so3_saved=saved)
+    g_s, do_s, dd_s = ops.march_all_bwd(tab, ndim, nmin, nmax, path_tc, 2.0, 6.0, jitter.cuda(), gp.cuda(), gd.cuda(), (w, window),
+                                        bricks=bricks, want_ray_grads=True, so3_saved=saved)
+    g_r, do_r, dd_r = ops.march_all_bwd(tab, ndim, nmin, nmax, path_tc, 2.0, 6.0, jitter.cuda(), gp.cuda(), gd.cuda(), (w, window),
+                                        bricks=bricks, want_ray_grads=True)
+    assert torch.isfinite(g_s).all() and torch.isfinite(do_s).all() and torch.isfinite(dd_s).all()
+    for got, ref in ((g_s, g_r), (do_s, do_r), (dd_s, dd_r)):
+        assert _cmp(got, ref.cpu())[1] < 2e-5, _cmp(got, ref.cpu())
+    rows = []
+    for i, (gk, gb) in enumerate(zip(ops.so3_unpack_views(g_s)[0::2], ops.so3_unpack_views(g_s)[1::2])):
+        rows.append((f"Dense_{i}.kernel",) + _cmp(gk, P[f"Dense_{i}"]["kernel"].grad))
+        rows.append((f"Dense_{i}.bias",) + _cmp(gb, P[f"Dense_{i}"]["bias"].grad))
+    rows.append(("origins",) + _cmp(do_s, oo.grad))
+    rows.append(("viewdirs",) + _cmp(dd_s, od.grad))
+    assert min(r[1] for r in rows) > 0.999999 and max(r[2] for r in rows) < 1e-4, rows
     # accumulation into a caller-provided gradient image
     g2 = g.clone()
     ops.march_all_bwd(tab, ndim, nmin, nmax, path, 2.0, 6.0, jitter.cuda(), gp.cuda(), gd.cuda(), (w, window), bricks=bricks, g_so3=g2)

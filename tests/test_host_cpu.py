@@ -42,16 +42,16 @@ def test_abi_argument_validation_without_gpu():
     # entries of the "all"-stage training path
     P = C.c_void_p(16)
     win = (C.c_double * 10)(*([1.0] * 10))
-    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 1, P, 2, P, P, P, P, win, None, P, None, None, None, None)
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 1, P, 2, P, P, P, P, win, None, None, P, None, None, None, None)
     assert rc == -2 and b"n_steps" in lib.rnerf_last_error()
-    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 10, 4, 2.0, 6.0, 96, P, 8, P, P, P, P, win, None, P, None, None, None, None)
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 10, 4, 2.0, 6.0, 96, P, 8, P, P, P, P, win, None, None, P, None, None, None, None)
     assert rc == -2 and b"rec_floats" in lib.rnerf_last_error()
-    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, P, None, win, None, P, None, None, None, None)
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, P, None, win, None, None, P, None, None, None, None)
     assert rc == -1 and b"so3_wt" in lib.rnerf_last_error()            # so3_w given without its transposed image
-    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, C.c_void_p(20), P, win, None, P, None, None, None, None)
+    rc = lib.rnerf_march_all_bwd(P, None, nd, lo, hi, P, 8, 4, 2.0, 6.0, 96, P, 8, P, P, C.c_void_p(20), P, win, None, None, P, None, None, None, None)
     assert rc == -3                                                       # misaligned weight image
     assert lib.rnerf_march_all_bwd(P, None, nd, lo, hi, None, 8, 0, 2.0, 6.0, 96, None, 8, None, None, None, None, None, None,
-                                   None, None, None, None, None) == 0           # no rays: a no-op
+                                   None, None, None, None, None, None) == 0           # no rays: a no-op
     assert lib.rnerf_mlp_input_grad(None, 0, None, None, None, None, None, None) == 0
     assert lib.rnerf_mlp_input_grad(None, 5, None, None, None, None, None, None) == -1
     assert lib.rnerf_so3_predict(None, win, None, P, P, 3, P, None) == -1
