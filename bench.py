@@ -235,8 +235,9 @@ def train_arm(a, model, rank, world, local, dev, barrier, peaks):
         res["compute_only_ms"] = cms
         res["exposed_comm_ms"] = ms - cms
         res["limiter"] = ("exposed all-reduce" if ms - cms > 0.5 * cms else
-                          "per-rank constant work (128x128 env patch through bkgd_mlp, latency-bound 768-step march, "
-                          "launch floor of the captured graph) -- the MLP GEMMs are the only part that shrinks with B/N")
+                          "per-rank latency that does not shrink with B/N: one-wave weight-gradient launches (TMEM allocation, "
+                          "pipeline fill, 256 KB accumulator flush), the serial 768-step march, single-block chains of the "
+                          "background MLP, ~60 launches of a few microseconds -- DESIGN.md section 6")
     return res
 
 

@@ -47,12 +47,14 @@ class _RadianceMLP(torch.autograd.Function):
             # the arena's gradient views -- so it is forked onto a side stream and joined before the gradient all-reduce.
             # The other MLP's backward, the composite and background backward kernels then run beside it: per-rank
             # batches of a multi-GPU step (512 rays) leave every one of these launches well under a wave.
-            side, keep = ctx.fork
+            side, keep, after = ctx.fork
             cur = torch.cuda.current_stream()
             d_raw = d_raw.contiguous()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.view(-1, 4), params, grad_out=ctx.sink)
+                if after is not None:          # multi-GPU: this bucket's all-reduce starts now, under the rest of the backward
+                    after()
             keep.append((side, d_raw, packed, pos, dirs, layers, enc, masks))   # alive until the join (no cross-stream reuse)
             return (None, None, None, None, None) + (None,) * len(params)
         grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.contiguous().view(-1, 4), params,

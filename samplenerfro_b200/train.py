@@ -116,12 +116,20 @@ class ParamArena:
     def bucket_grads(self) -> List[torch.Tensor]:
         return [self.grad[self.bucket_range[n][0]:self.bucket_range[n][1]] for n in self.buckets]
 
-    def allreduce_mean(self, world_size: int, group=None) -> None:
-        """jax.lax.pmean(grads, "batch") (train.py:166): one in-place all-reduce per bucket view, then one scale."""
+    def allreduce_bucket(self, name: str, group=None):
+        """Start the in-place all-reduce(sum) of one bucket's gradient view on the CURRENT stream; returns the work handle."""
+        import torch.distributed as dist
+        lo, hi = self.bucket_range[name]
+        return dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def allreduce_mean(self, world_size: int, group=None, started=()) -> None:
+        """jax.lax.pmean(grads, "batch") (train.py:166): one in-place all-reduce per bucket view, then one scale.
+        `started`: (bucket name, work) pairs whose all-reduce was already issued (train._step_body starts a radiance MLP's
+        bucket on the side stream of its backward, so the transfer runs under the rest of the backward)."""
         if world_size <= 1:
             return
-        import torch.distributed as dist
-        works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in self.bucket_grads()]
+        done = {n for n, _ in started}
+        works = [w for _, w in started] + [self.allreduce_bucket(n, group) for n in self.buckets if n not in done]
         for w in works:
             w.wait()
         self.grad.mul_(1.0 / world_size)
@@ -383,13 +391,19 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
         state.grid_opt.zero_grad()
     model._grad_sink, model._theta_flat = arena.sinks, arena.theta_flat
     keep: list = []
+    started: list = []          # (bucket, work) of all-reduces issued on the side streams
     if arena.theta.is_cuda and _FORK_BACKWARD:
         # the radiance MLPs' backwards (leaves: they only accumulate into arena.grad) run on side streams next to everything
         # autograd executes after them; joined below, before the gradients are reduced (autograd._RadianceMLP.backward)
         if getattr(state, "_bwd_streams", None) is None:
             state._bwd_streams = [torch.cuda.Stream(device=arena.theta.device) for _ in range(2)]
         names = os.environ.get("RNERF_FORK_BACKWARD_MLPS", "fine_mlp,coarse_mlp").split(",")
-        model._bwd_fork = {n: (st, keep) for n, st in zip(names, state._bwd_streams)}
+        early = world_size > 1 and os.environ.get("RNERF_EARLY_ALLREDUCE", "1") != "0"
+
+        def after(name):        # runs on the bucket's side stream right after its backward kernels were issued
+            return (lambda: started.append((name, arena.allreduce_bucket(name, group)))) if early else None
+
+        model._bwd_fork = {n: (st, keep, after(n)) for n, st in zip(names, state._bwd_streams) if n in arena.buckets}
         if os.environ.get("RNERF_FORK_ENV", "1") != "0":
             if getattr(state, "_env_stream", None) is None:
                 state._env_stream = torch.cuda.Stream(device=arena.theta.device)
@@ -411,7 +425,7 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
             # so the engine has nothing to synchronise on: join explicitly before the gradients are read
             torch.cuda.current_stream().wait_stream(state._env_stream)
             model._env_forked = False
-    arena.allreduce_mean(world_size, group)
+    arena.allreduce_mean(world_size, group, started=started)
     if state.grid_opt is not None:
         state.grid_opt.allreduce_mean(world_size, group)
     if world_size > 1:
