@@ -95,6 +95,38 @@ def test_loss_and_gradients_match_oracle(cuda_lib):
     assert min(t[3] for t in first) > 0.995 and max(t[4] for t in first) < 0.10, first
 
 
+def test_sharded_env_patch_follows_the_reference_reshape(cuda_lib):
+    """A device of an N-device step gets a [P/N, P, 3] shard of the env patch (utils.shard) and train.py:127-128 reshapes the
+    colours to (P/N, P/N, -1): the fused loss must reproduce that, value and gradient (oracle: the same expression)."""
+    from samplenerfro_b200 import train, utils
+    model, variables, args, (n, ndim, nmin, nmax), o, d, env, pixels, gen = _setup(B=64)
+    env = env[:4].contiguous()                                   # rows 0..3 of the 8 x 8 patch: the shard of rank 0 of 2
+    B = o.shape[0]
+    train.TrainState.create(variables, args)                     # leaves become arena views that require grad
+    jitter = model.draw_jitter(5)
+    u = O.stratified_u(torch.rand(B, 128, generator=gen) * (1 / 128 - float(np.finfo(np.float32).eps)))
+    batch = {"rays": utils.Rays(o.cuda(), d.cuda(), d.cuda(), torch.ones(B, 1).cuda()), "pixels": pixels.cuda(),
+             "env_rays": utils.Rays(env.cuda(), env.cuda(), env.cuda(), env.cuda()[..., :1]), "annealed_alpha": 0.5}
+    total, stats = train.loss_fn(model, variables, batch, args, 1, 2, jitter=jitter, u=u.cuda())
+    total.backward()
+
+    def cv(t):
+        return {k: cv(v) for k, v in t.items()} if isinstance(t, dict) else t.detach().cpu().clone().requires_grad_(True)
+
+    V = cv(variables)
+    cfg = O.ModelCfg(ndim=ndim, nmin=nmin, nmax=nmax, cfg_name="example")
+    ototal, ostats = O.train_loss(V, O.build_table(n, ndim, nmin, nmax), cfg, O.Rays(o, d, d, torch.ones(B, 1)), pixels, env,
+                                  jitter.cpu().long(), u, 0.5, bg_weight=0.025, bg_smooth_weight=1.0)
+    ototal.backward()
+    assert float(ostats["loss_bg_smooth"].detach()) > 1e-6
+    assert abs(float(stats["loss_bg_smooth"]) - float(ostats["loss_bg_smooth"].detach())) < 1e-4 * float(ostats["loss_bg_smooth"].detach())
+    assert abs(total.item() - ototal.item()) < 2e-3 * abs(ototal.item())
+    for i in range(5):                 # bkgd_mlp is fp32 end to end: its gradient (rays + env patch) to 1e-3
+        g = variables["params"]["bkgd_mlp"][f"Dense_{i}"]["kernel"].grad.cpu().double().reshape(-1)
+        og = V["params"]["bkgd_mlp"][f"Dense_{i}"]["kernel"].grad.double().reshape(-1)
+        assert ((g - og).norm() / (og.norm() + 1e-30)).item() < 2e-2, i
+
+
 def test_train_step_reduces_loss(cuda_lib):
     from samplenerfro_b200 import train, utils
     model, variables, args, _, o, d, env, pixels, gen = _setup(B=128, bias=0.0)
