@@ -47,16 +47,49 @@ class _RadianceMLP(torch.autograd.Function):
             # the arena's gradient views -- so it is forked onto a side stream and joined before the gradient all-reduce.
             # The other MLP's backward, the composite and background backward kernels then run beside it: per-rank
             # batches of a multi-GPU step (512 rays) leave every one of these launches well under a wave.
-            side, keep, after = ctx.fork
-            cur = torch.cuda.current_stream()
+            side, keep, after, defer = ctx.fork
             d_raw = d_raw.contiguous()
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.view(-1, 4), params, grad_out=ctx.sink)
-                if after is not None:          # multi-GPU: this bucket's all-reduce starts now, under the rest of the backward
-                    after()
+
+            def launch(ev=None):
+                # ev: an event on the autograd stream after which everything this backward reads exists (deferred launch),
+                # or None: order the side stream after the current one right here
+                if ev is None:
+                    side.wait_stream(torch.cuda.current_stream())
+                else:
+                    side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.view(-1, 4), params, grad_out=ctx.sink)
+                    if after is not None:      # multi-GPU: this bucket's all-reduce starts now, under the rest of the backward
+                        after()
+
             keep.append((side, d_raw, packed, pos, dirs, layers, enc, masks))   # alive until the join (no cross-stream reuse)
+            if defer is not None:
+                defer.append(launch)           # "all" stage: launched right behind the reverse sweep (_MarchAll.backward)
+            else:
+                launch()
             return (None, None, None, None, None) + (None,) * len(params)
+        if ctx.fork is not None and ctx.sink is not None and want_in and ctx.fork[3] is not None:
+            # "all" stage, coarse MLP: the sweep waits for d pos / d dirs, so the dgrad chain and the input gradients run now;
+            # the weight gradients are leaves and go behind the sweep like the fine MLP's whole backward
+            side, keep, after, defer = ctx.fork
+            d_raw = d_raw.contiguous()
+            grads, weight_part = ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.view(-1, 4), params,
+                                                grad_out=ctx.sink, input_grads=True, split=True)
+            d_pos, d_dirs = grads.pop()
+
+            def launch_weights(ev=None):
+                if ev is None:
+                    side.wait_stream(torch.cuda.current_stream())
+                else:
+                    side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    weight_part()
+                    if after is not None:
+                        after()
+
+            keep.append((side, d_raw, packed, pos, dirs, layers, enc, masks, weight_part))
+            defer.append(launch_weights)
+            return (None, None, None, d_pos, d_dirs) + (None,) * len(params)
         grads = ops.encmlp_bwd(packed, pos, dirs, (layers, enc, masks), d_raw.contiguous().view(-1, 4), params,
                                grad_out=ctx.sink, input_grads=want_in)
         d_pos, d_dirs = grads.pop() if want_in else (None, None)
@@ -213,9 +246,21 @@ class _MarchAll(torch.autograd.Function):
 
         d_table = torch.zeros_like(table) if ctx.needs_input_grad[8] else None
         so3 = (w, ctx.window) if w.numel() else None
+        # training step: MLP backward work that nothing downstream waits for was deferred to here -- it is launched right
+        # BEHIND the sweep (whose CTAs are latency-bound chains that free their SMs at very different times) on its side
+        # streams, ordered after an event recorded BEFORE the sweep, so the two run side by side
+        deferred = getattr(m, "_bwd_defer", None)
+        ev = None
+        if deferred:
+            ev = torch.cuda.Event()
+            ev.record()
         g, _, _ = ops.march_all_bwd(table, m.ndim, m.nmin, m.nmax, rec, m.near, m.far, jitter, z(d_pos_c), z(d_dir_c), so3,
                                     bricks=bricks if bricks.numel() else None, g_so3=ctx.sink if so3 is not None else None,
                                     d_table=d_table, so3_saved=saved if saved.numel() else None)
+        if deferred:
+            for launch in deferred:
+                launch(ev)
+            deferred.clear()
         n_par = len(ctx.needs_input_grad) - 10
         if ctx.sink is not None or so3 is None:
             return (None,) * 8 + (d_table, None) + (None,) * n_par

@@ -535,13 +535,16 @@ def mlp_input_grad_pack(k0: torch.Tensor, k5: torch.Tensor, k10: torch.Tensor) -
     return wt
 
 
-def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None, input_grads: bool = False):
+def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None, input_grads: bool = False, split: bool = False):
     """Backward of pos_enc + NerfMLP wrt the 12 Dense layers: fused tcgen05 dgrad chain (dZ of every layer), then one
     MN-major tcgen05 wgrad per layer (+ the two skinny heads on CUDA cores).  Returns [gK0, gb0, ..., gK11, gb11].
     `grad_out`: optional list of 24 fp32 tensors (same order) the kernels ACCUMULATE into -- the gradient views of a
     flat parameter arena, where every (kernel, bias) pair is contiguous; fresh zero buffers otherwise.
     `input_grads`: also return (d_pos, d_dirs), the gradients wrt the sample positions / directions ("all" stage), as
-    the last element of the returned list."""
+    the last element of the returned list.
+    `split` (with `grad_out`): only the dgrad chain (and the input gradients) run now; returns (list as above, weight_part)
+    where weight_part() launches the weight-gradient and head kernels on whatever stream is current when it is called (the
+    caller orders that stream after this call and keeps it from outliving the step: train._step_body)."""
     layers, enc, masks = saved
     M = layers.shape[1]
     lib = _lib.load()
@@ -555,39 +558,49 @@ def encmlp_bwd(packed, pos, dirs, saved, d_raw, params, grad_out=None, input_gra
             _chk(g, "grad_out")
         contiguous_pairs = all(gB[i].data_ptr() == gK[i].data_ptr() + 4 * gK[i].numel() for i in (8, 11))
     else:
+        assert not split, "split needs grad_out (the weight part has nowhere to return its gradients)"
         contiguous_pairs = False
-    if not contiguous_pairs:
-        heads = torch.zeros(644, device=dev, dtype=torch.float32)
-        head_rgb, head_sig = heads[:387], heads[387:]
-    if grad_out is None:
-        gK = [torch.zeros_like(k) for k in K]
-        gB = [torch.zeros_like(b) for b in params[1::2]]
-        gK[11], gB[11] = head_rgb[:384].view(128, 3), head_rgb[384:387]
-        gK[8], gB[8] = head_sig[:256].view(256, 1), head_sig[256:257]
-    jobs = [(enc[0], 64, 63, dz[0], 256, gK[0], gB[0])]
-    jobs += [(layers[l - 1], 256, 256, dz[l], 256, gK[l], gB[l]) for l in (1, 2, 3, 4, 6, 7)]
-    jobs += [(layers[4], 256, 256, dz[5], 256, gK[5][:256], gB[5]), (enc[0], 64, 63, dz[5], 256, gK[5][256:], None),
-             (layers[7], 256, 256, dz[8], 256, gK[9], gB[9]), (layers[8], 256, 256, dz[9], 128, gK[10][:256], gB[10]),
-             (enc[1], 32, 27, dz[9], 128, gK[10][256:], None)]
-    mlp_wgrad_batched(jobs, M)          # 13 GEMMs, one launch
-    if contiguous_pairs:      # (kernel, bias) of Dense_11 / Dense_8 are adjacent in the arena: accumulate in place
-        check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(gK[11]), _p(gK[8]), _stream()), "rnerf_mlp_head_grad")
-    else:
-        check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(head_rgb), _p(head_sig), _stream()), "rnerf_mlp_head_grad")
-        if grad_out is not None:
-            gK[11].add_(head_rgb[:384].view(128, 3)); gB[11].add_(head_rgb[384:387])
-            gK[8].add_(head_sig[:256].view(256, 1)); gB[8].add_(head_sig[256:257])
-    out = []
-    for i in range(12):
-        out += [gK[i], gB[i]]
+    inputs = None
     if input_grads:
         wt = mlp_input_grad_pack(K[0], K[5], K[10])
         pos2, dirs2 = _chk(pos.reshape(-1, 3), "pos"), _chk(dirs.reshape(-1, 3), "dirs")
         d_pos, d_dirs = torch.empty_like(pos2), torch.empty_like(dirs2)
         check(lib.rnerf_mlp_input_grad(_p(dz), M, _p(wt), _p(pos2), _p(dirs2), _p(d_pos), _p(d_dirs), _stream()),
               "rnerf_mlp_input_grad")
-        out.append((d_pos.view(pos.shape), d_dirs.view(dirs.shape)))
-    return out
+        inputs = (d_pos.view(pos.shape), d_dirs.view(dirs.shape))
+
+    def weight_part():
+        nonlocal gK, gB
+        if not contiguous_pairs:
+            heads = torch.zeros(644, device=dev, dtype=torch.float32)
+            head_rgb, head_sig = heads[:387], heads[387:]
+        if grad_out is None:
+            gK = [torch.zeros_like(k) for k in K]
+            gB = [torch.zeros_like(b) for b in params[1::2]]
+            gK[11], gB[11] = head_rgb[:384].view(128, 3), head_rgb[384:387]
+            gK[8], gB[8] = head_sig[:256].view(256, 1), head_sig[256:257]
+        jobs = [(enc[0], 64, 63, dz[0], 256, gK[0], gB[0])]
+        jobs += [(layers[l - 1], 256, 256, dz[l], 256, gK[l], gB[l]) for l in (1, 2, 3, 4, 6, 7)]
+        jobs += [(layers[4], 256, 256, dz[5], 256, gK[5][:256], gB[5]), (enc[0], 64, 63, dz[5], 256, gK[5][256:], None),
+                 (layers[7], 256, 256, dz[8], 256, gK[9], gB[9]), (layers[8], 256, 256, dz[9], 128, gK[10][:256], gB[10]),
+                 (enc[1], 32, 27, dz[9], 128, gK[10][256:], None)]
+        mlp_wgrad_batched(jobs, M)          # 13 GEMMs, one launch
+        if contiguous_pairs:      # (kernel, bias) of Dense_11 / Dense_8 are adjacent in the arena: accumulate in place
+            check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(gK[11]), _p(gK[8]), _stream()), "rnerf_mlp_head_grad")
+        else:
+            check(lib.rnerf_mlp_head_grad(_p(layers), _p(d_raw), M, _p(head_rgb), _p(head_sig), _stream()), "rnerf_mlp_head_grad")
+            if grad_out is not None:
+                gK[11].add_(head_rgb[:384].view(128, 3)); gB[11].add_(head_rgb[384:387])
+                gK[8].add_(head_sig[:256].view(256, 1)); gB[8].add_(head_sig[256:257])
+
+    if not split:
+        weight_part()
+    out = []
+    for i in range(12):
+        out += [gK[i], gB[i]]
+    if inputs is not None:
+        out.append(inputs)
+    return (out, weight_part) if split else out
 
 
 def bkgd_mlp_bwd(w, dirs, n_rays, stride, offset, d_raw, params, gw_out=None, want_d_dirs: bool = False):

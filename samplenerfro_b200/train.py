@@ -403,7 +403,12 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
         def after(name):        # runs on the bucket's side stream right after its backward kernels were issued
             return (lambda: started.append((name, arena.allreduce_bucket(name, group)))) if early else None
 
-        model._bwd_fork = {n: (st, keep, after(n)) for n, st in zip(names, state._bwd_streams) if n in arena.buckets}
+        # "all" stage: the reverse sweep of the scan is a 14 ms chain of latency-bound CTAs; MLP backward work that nothing
+        # waits for is deferred and launched behind it (autograd._MarchAll.backward), instead of ahead of it
+        defer = [] if (str(getattr(args, "stage", "")).startswith("all") and "path_sampler" in arena.buckets
+                       and os.environ.get("RNERF_DEFER_UNDER_SWEEP", "1") != "0") else None
+        model._bwd_defer = defer
+        model._bwd_fork = {n: (st, keep, after(n), defer) for n, st in zip(names, state._bwd_streams) if n in arena.buckets}
         if os.environ.get("RNERF_FORK_ENV", "1") != "0":
             if getattr(state, "_env_stream", None) is None:
                 state._env_stream = torch.cuda.Stream(device=arena.theta.device)
@@ -416,6 +421,12 @@ def _step_body(model, state: TrainState, batch: Dict, args, key_0, key_1, world_
         model._grad_sink = None
         model._bwd_fork = None
         model._env_stream = None
+        leftover = getattr(model, "_bwd_defer", None)
+        model._bwd_defer = None
+        if leftover:                    # no sweep ran (nothing reached the sampler): launch what was deferred now
+            for launch in leftover:
+                launch(None)
+            leftover.clear()
         if keep:
             for st in {id(k[0]): k[0] for k in keep}.values():      # only the streams a backward was actually forked onto
                 torch.cuda.current_stream().wait_stream(st)
