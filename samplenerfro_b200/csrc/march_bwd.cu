@@ -24,6 +24,8 @@
 //     input grad    acc[in][col]     = sum_out Wt[out][in]      dZ[out][col]      (Wt: transposed image, rnerf_so3_transpose)
 //     weight grad   gW[in][neuron]  += sum_col A[in][col] dZ[neuron][col]          (red.global.add.v2.f32 per row)
 // fp32 on the CUDA cores, like the forward (the gradient steers the ray).
+#include <stdio.h>
+#include <stdlib.h>
 #include "march_common.cuh"
 
 namespace rnerf {
@@ -49,6 +51,8 @@ struct So3BwdArgs {
   float window[10];
   const float* window_dev;   // device copy of the window or NULL (So3Args::window_dev)
   const float* saved;        // hidden activations left by the training forward (So3Args::saved), or NULL: recompute them
+  long long* prof;           // development aid (RNERF_SWEEP_PROF): clock64 stamps [CTA][32] of one evaluation per CTA, or NULL
+  int prof_eval;             // which evaluation of a CTA is stamped
 };
 
 __global__ void __launch_bounds__(256) so3_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt) {
@@ -327,7 +331,15 @@ __device__ __forceinline__ void wgrad_rows(const DzRows& z, const float* __restr
 // Out (threads with `act`): dg (adjoint of g), dp (adjoint of p through the encoding).  Parameter gradients -> a.gw.
 __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int* cnt, So3Ring& ring, int warp, int lane, bool act,
                                             const float p[3], const float g[3], const float dG[3], float dg[3], float dp[3],
-                                            int slot /* ray * n_steps + step: the evaluation's record in a.saved */) {
+                                            int slot /* ray * n_steps + step: the evaluation's record in a.saved */,
+                                            int eval_idx = 0) {
+  int stamp_i = 0;
+  auto STAMP = [&]() {       // development aid: phase boundaries of evaluation a.prof_eval (scripts/sweep_phases.py)
+    if (a.prof != nullptr && eval_idx == a.prof_eval && warp == 0 && lane == 0 && stamp_i < 29)
+      a.prof[blockIdx.x * 32 + 1 + stamp_i] = clock64();
+    ++stamp_i;
+  };
+  STAMP();   // 0: entry
   float* X = sm + BW_OFF_X;
   float* H = sm + BW_OFF_H;
   float* D = sm + BW_OFF_D;
@@ -354,6 +366,8 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     n_act += c;
   }
   const int idx = base + __popc(bal & ((1u << lane) - 1u));
+  STAMP();   // 1: counted
+  if (a.prof != nullptr && eval_idx == a.prof_eval && warp == 0 && lane == 0) a.prof[blockIdx.x * 32] = n_act;
   constexpr int HL = SO3_W * BW_RP;              // floats per saved layer
   const float half_pi = 1.57079632679489661923f;
 #pragma unroll 1
@@ -417,17 +431,22 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     relu_bias_store(acc, bias + 3 * SO3_W, H + 3 * HL, j, h);
     }
     __syncthreads();
+    STAMP();   // 2: X + H ready
     const float* H4 = H + 3 * HL;
     const float* W4 = a.w + SO3_OFF_W4;
-    // ---- Dense_4: raw[m][col], one thread per output
-    if (tid < 3 * BW_COLS) {
-      const int m = tid >> 5, cc = tid & 31;
-      float r = __ldg(bias + 4 * SO3_W + m);
+    // ---- Dense_4: raw[m][col]: four threads per output, each a quarter of the 128-long sum (one thread per output was a
+    // 128-deep dependent FMA chain: 3.3 us of every 54 us evaluation, scripts/sweep_phases.py)
+    if (tid < 4 * 3 * BW_COLS) {
+      const int o = tid >> 2, kq = tid & 3, m = o >> 5, cc = o & 31;
+      float r = 0.f;
 #pragma unroll 8
-      for (int k = 0; k < SO3_W; ++k) r = fmaf(H4[k * BW_RP + cc], __ldg(W4 + 3 * k + m), r);
-      RAW[m * BW_RP + cc] = r;
+      for (int k = kq; k < SO3_W; k += 4) r = fmaf(H4[k * BW_RP + cc], __ldg(W4 + 3 * k + m), r);
+      r += __shfl_xor_sync(0xffffffffu, r, 1);
+      r += __shfl_xor_sync(0xffffffffu, r, 2);
+      if (kq == 0) RAW[m * BW_RP + cc] = r + __ldg(bias + 4 * SO3_W + m);
     }
     __syncthreads();
+    STAMP();   // 3: raw
     // ---- rotation, forward and reverse, by the ray's own thread (it holds g and dG); unused columns get d raw = 0
     if (mine) {
       const float r[3] = {RAW[col], RAW[BW_RP + col], RAW[2 * BW_RP + col]};
@@ -437,6 +456,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     }
     if (tid < BW_COLS && tid >= n_here) { R[tid] = 0.f; R[BW_RP + tid] = 0.f; R[2 * BW_RP + tid] = 0.f; }
     __syncthreads();
+    STAMP();   // 4: rotation reverse
     // ---- Dense_4 backward: dH4 = W4 d raw, masked; gW4 += H4 (x) d raw; gb4 += sum d raw
     {
       float w4[2][3];
@@ -470,10 +490,12 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     // ---- Dense_3 (inputs [H3, X]): acc = dZ4
     store_rows(acc, D, j, h);
     __syncthreads();
+    STAMP();   // 5: Dense_4 backward, dZ4 published
     load_dz_rows(z, D, j);
     if (h == 0) bias_grad(z, gbias + 3 * SO3_W, j);
     wgrad_rows(z, H + 2 * HL, SO3_W, a.gw + SO3_OFF_W3, j, h);
     wgrad_rows(z, X, SO3_IN, a.gw + SO3_OFF_W3 + SO3_W * SO3_W, j, h);
+    STAMP();   // 6: weight gradients of Dense_3 (this thread)
     {                                                        // gradient wrt the skip-concatenated encoding
       float ax[2][BW_CPT];
       zero_acc(ax);
@@ -484,6 +506,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, D, j, h, true);
     relu_mask(acc, H + 2 * HL, j, h);                        // dZ3
     __syncthreads();                                         // D has been read by everyone
+    STAMP();   // 7: Dense_3 input gradients (4 chunks)
     // ---- Dense_2 (input H2)
     store_rows(acc, D, j, h);
     __syncthreads();
@@ -494,6 +517,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, D, j, h, true);
     relu_mask(acc, H + HL, j, h);                            // dZ2
     __syncthreads();
+    STAMP();   // 8: Dense_2
     // ---- Dense_1 (input H1)
     store_rows(acc, D, j, h);
     __syncthreads();
@@ -504,6 +528,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     gemm_ring(acc, ring, tid, stream, SO3_W, SO3_W, D, j, h, true);
     relu_mask(acc, H, j, h);                                 // dZ1
     __syncthreads();
+    STAMP();   // 9: Dense_1
     // ---- Dense_0 (input X)
     store_rows(acc, D, j, h);
     __syncthreads();
@@ -524,6 +549,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
       if (j < SO3_IN / 2) store_rows(ax, DX, j, h);
     }
     __syncthreads();
+    STAMP();   // 10: Dense_0
     // ---- encoding backward, one thread per (component, column): d/dp_c of sin(2^k p_c [+ pi/2]) w_k
     float gpc = 0.f;
     if (tid < 3 * BW_COLS) {
@@ -543,6 +569,7 @@ __device__ __forceinline__ void so3_fwd_bwd(const So3BwdArgs& a, float* sm, int*
     if (tid < 3 * BW_COLS) P[(tid >> 5) * BW_RP + (tid & 31)] = gpc;
     __syncthreads();
     if (mine) { dp[0] = P[col]; dp[1] = P[BW_RP + col]; dp[2] = P[2 * BW_RP + col]; }
+    STAMP();   // 11: encoding backward, done
   }
 }
 
@@ -579,6 +606,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) march_all_bwd_kernel(
   constexpr int SWEEP_QUANTUM = 16;
   int k = k_last;
   bool done = !live;
+  int n_eval = 0;
   // loss gradients of coarse sample jc = record k (v = direction state of that record)
   auto inject = [&](int kk, const float (&v)[3]) {
     const int jc = kmap[kk];
@@ -635,7 +663,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) march_all_bwd_kernel(
     }
     if (__syncthreads_or(need)) {
       float dg[3] = {0.f, 0.f, 0.f}, dpm[3] = {0.f, 0.f, 0.f};
-      so3_fwd_bwd(so3, sm, cnt, ring, warp, lane, need, p, g, dG, dg, dpm, (int)(rr * n_steps + k));
+      if (so3.prof != nullptr && tid == 0 && (n_eval == so3.prof_eval || n_eval == so3.prof_eval + 1))
+        so3.prof[blockIdx.x * 32 + 30 + (n_eval - so3.prof_eval)] = clock64();      // start of this and of the next evaluation
+      so3_fwd_bwd(so3, sm, cnt, ring, warp, lane, need, p, g, dG, dg, dpm, (int)(rr * n_steps + k), n_eval);
+      ++n_eval;
       if (need) {
         finish(p, hn, dn, dg, dpm, jx, jy, jz);
         inject(k, v);
@@ -698,6 +729,13 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
   for (int k = 0; k < 10; ++k) a.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
   a.window_dev = so3_w != nullptr ? so3_window_dev : nullptr;
   a.saved = so3_w != nullptr ? so3_saved : nullptr;
+  a.prof = nullptr; a.prof_eval = 0;
+  const char* prof_path = getenv("RNERF_SWEEP_PROF");      // development aid: synchronous, never set in production
+  if (prof_path != nullptr && so3_w != nullptr) {
+    cudaMalloc(&a.prof, 4096 * 32 * sizeof(long long));
+    cudaMemsetAsync(a.prof, 0, 4096 * 32 * sizeof(long long), (cudaStream_t)stream);
+    a.prof_eval = getenv("RNERF_SWEEP_PROF_EVAL") ? atoi(getenv("RNERF_SWEEP_PROF_EVAL")) : 40;
+  }
   RNERF_REQUIRE(a.saved == nullptr || (double)n_rays * n_steps < 2147483648.0, RNERF_E_SHAPE,
                 "rnerf_march_all_bwd: so3_saved needs n_rays * n_steps < 2^31");
   const size_t dyn = (size_t)BW_ACT_FLOATS * 4 + 64 + 8 * SO3_MAX_SLOTS + (size_t)BW_RING_SLOTS * BW_SLOT_FLOATS * 4 +
@@ -720,5 +758,22 @@ extern "C" int rnerf_march_all_bwd(const float* table, const float* bricks, cons
                                                                     n_rays, (float)near, step, n_steps, jitter, n_coarse, d_pos_c,
                                                                     d_dir_c, a, d_origins, d_viewdirs, rpc, (float4*)d_table);
   count_launch();
+  if (a.prof != nullptr) {
+    cudaStreamSynchronize(st);
+    const int nb = blocks < 4096 ? (int)blocks : 4096;
+    long long* h = (long long*)malloc((size_t)nb * 32 * sizeof(long long));
+    cudaMemcpy(h, a.prof, (size_t)nb * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(prof_path, "w")) {
+      for (int b = 0; b < nb; ++b) {
+        if (h[b * 32 + 1] == 0) continue;          // this CTA never reached the stamped evaluation
+        fprintf(f, "%d %lld", b, h[b * 32]);
+        for (int i = 1; i < 32; ++i) fprintf(f, " %lld", h[b * 32 + i]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    free(h);
+    cudaFree(a.prof);
+  }
   return check_launch("rnerf_march_all_bwd");
 }
