@@ -1,6 +1,6 @@
 // IoR grid preparation and lookup: Gaussian prefilter (a1), (n, grad n) table (a2), trilinear lookup (a3).
 #include <math.h>
-#include "common.cuh"
+#include "march_common.cuh"
 
 namespace rnerf {
 
@@ -33,51 +33,75 @@ __global__ void __launch_bounds__(256) blur_kernel(const float* __restrict__ in,
   }
 }
 
+// a / d for a divisor d that is constant over the launch: the exhaustively verified 3-instruction sequence of the march
+// (march_common.cuh, recip = recip_for(d) or 0) where it applies -- same bits as the IEEE division -- else the division.
+__device__ __forceinline__ float div_const(float a, float d, float recip) {
+  if (recip != 0.f) {
+    const float aa = fabsf(a);
+    if (aa >= 0x1p-60f && aa <= 0x1p60f) return div_by_const(a, d, recip);
+    if (a == 0.f) return d > 0.f ? a : -a;          // (most voxels: a homogeneous neighbourhood)
+  }
+  return divf(a, d);
+}
+struct TableRecips { float r[3]; };
+
 // VoxMLP._compute_grad (rnerf/ior_utils.py:165-172): central differences on the edge-padded grid / (2*ndelta).
-__global__ void __launch_bounds__(256) table_kernel(const float* __restrict__ n, float4* __restrict__ table, GridGeom g) {
-  const int64_t total = (int64_t)g.gx * g.gy * g.gz;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int z = (int)(i % g.gz);
-    int y = (int)((i / g.gz) % g.gy);
-    int x = (int)(i / ((int64_t)g.gz * g.gy));
-    const int64_t sx = (int64_t)g.gy * g.gz, sy = g.gz;
-    int xm = max(x - 1, 0), xp = min(x + 1, g.gx - 1);
-    int ym = max(y - 1, 0), yp = min(y + 1, g.gy - 1);
-    int zm = max(z - 1, 0), zp = min(z + 1, g.gz - 1);
-    float dx = divf(sub(__ldg(n + sx * xp + sy * y + z), __ldg(n + sx * xm + sy * y + z)), g.two_ndelta[0]);
-    float dy = divf(sub(__ldg(n + sx * x + sy * yp + z), __ldg(n + sx * x + sy * ym + z)), g.two_ndelta[1]);
-    float dz = divf(sub(__ldg(n + sx * x + sy * y + zp), __ldg(n + sx * x + sy * y + zm)), g.two_ndelta[2]);
-    table[i] = make_float4(__ldg(n + i), dx, dy, dz);
+// One block per (x, y) row, threads along z: 32-bit index arithmetic (the first version derived (x, y, z) from a 64-bit
+// flat index with three divisions per voxel and ran at 1.5 TB/s on a 2.5 GB pass: instruction-bound).
+__global__ void __launch_bounds__(256) table_kernel(const float* __restrict__ n, float4* __restrict__ table, GridGeom g,
+                                                    TableRecips rc) {
+  const int rows = g.gx * g.gy;
+  const int64_t sx = (int64_t)g.gy * g.gz, sy = g.gz;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int x = row / g.gy, y = row - x * g.gy;
+    const int xm = max(x - 1, 0), xp = min(x + 1, g.gx - 1), ym = max(y - 1, 0), yp = min(y + 1, g.gy - 1);
+    const float* c = n + sx * x + sy * y;
+    const float* cxp = n + sx * xp + sy * y; const float* cxm = n + sx * xm + sy * y;
+    const float* cyp = n + sx * x + sy * yp; const float* cym = n + sx * x + sy * ym;
+    float4* out = table + (int64_t)row * g.gz;
+    for (int z = threadIdx.x; z < g.gz; z += blockDim.x) {
+      const int zm = max(z - 1, 0), zp = min(z + 1, g.gz - 1);
+      const float dx = div_const(sub(__ldg(cxp + z), __ldg(cxm + z)), g.two_ndelta[0], rc.r[0]);
+      const float dy = div_const(sub(__ldg(cyp + z), __ldg(cym + z)), g.two_ndelta[1], rc.r[1]);
+      const float dz = div_const(sub(__ldg(c + zp), __ldg(c + zm)), g.two_ndelta[2], rc.r[2]);
+      out[z] = make_float4(__ldg(c + z), dx, dy, dz);
+    }
   }
 }
 
 // Adjoint of table_kernel (extension, no reference counterpart: a learned IoR grid): d_n[i] = d_table[i].n + the transposed
 // central differences, edge clamping included (n[0] and n[G-1] each enter their own boundary difference twice).
 __global__ void __launch_bounds__(256) table_bwd_kernel(const float4* __restrict__ dt, float* __restrict__ dn, GridGeom g) {
-  const int64_t total = (int64_t)g.gx * g.gy * g.gz;
+  const int rows = g.gx * g.gy;
   const int64_t sx = (int64_t)g.gy * g.gz, sy = g.gz;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int z = (int)(i % g.gz), y = (int)((i / g.gz) % g.gy), x = (int)(i / ((int64_t)g.gz * g.gy));
-    float acc = __ldg(dt + i).x;
-    float s = 0.f;
-    if (x >= 1) s += __ldg(dt + i - sx).y;
-    if (x == g.gx - 1) s += __ldg(dt + i).y;
-    if (x <= g.gx - 2) s -= __ldg(dt + i + sx).y;
-    if (x == 0) s -= __ldg(dt + i).y;
-    acc += s / g.two_ndelta[0];
-    s = 0.f;
-    if (y >= 1) s += __ldg(dt + i - sy).z;
-    if (y == g.gy - 1) s += __ldg(dt + i).z;
-    if (y <= g.gy - 2) s -= __ldg(dt + i + sy).z;
-    if (y == 0) s -= __ldg(dt + i).z;
-    acc += s / g.two_ndelta[1];
-    s = 0.f;
-    if (z >= 1) s += __ldg(dt + i - 1).w;
-    if (z == g.gz - 1) s += __ldg(dt + i).w;
-    if (z <= g.gz - 2) s -= __ldg(dt + i + 1).w;
-    if (z == 0) s -= __ldg(dt + i).w;
-    acc += s / g.two_ndelta[2];
-    dn[i] = acc;
+  const float ix = 1.f / g.two_ndelta[0], iy = 1.f / g.two_ndelta[1], iz = 1.f / g.two_ndelta[2];
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int x = row / g.gy, y = row - x * g.gy;
+    const float4* c = dt + (int64_t)row * g.gz;
+    float* o = dn + (int64_t)row * g.gz;
+    for (int z = threadIdx.x; z < g.gz; z += blockDim.x) {
+      const float4 here = __ldg(c + z);
+      float acc = here.x;
+      float s = 0.f;
+      if (x >= 1) s += __ldg(c + z - sx).y;
+      if (x == g.gx - 1) s += here.y;
+      if (x <= g.gx - 2) s -= __ldg(c + z + sx).y;
+      if (x == 0) s -= here.y;
+      acc += s * ix;
+      s = 0.f;
+      if (y >= 1) s += __ldg(c + z - sy).z;
+      if (y == g.gy - 1) s += here.z;
+      if (y <= g.gy - 2) s -= __ldg(c + z + sy).z;
+      if (y == 0) s -= here.z;
+      acc += s * iy;
+      s = 0.f;
+      if (z >= 1) s += __ldg(c + z - 1).w;
+      if (z == g.gz - 1) s += here.w;
+      if (z <= g.gz - 2) s -= __ldg(c + z + 1).w;
+      if (z == 0) s -= here.w;
+      acc += s * iz;
+      o[z] = acc;
+    }
   }
 }
 
@@ -154,8 +178,11 @@ extern "C" int rnerf_grid_table(const float* n, const int ndim[3], const double 
   RNERF_REQUIRE(ndim[0] >= 2 && ndim[1] >= 2 && ndim[2] >= 2, RNERF_E_SHAPE, "rnerf_grid_table: ndim must be >= 2");
   RNERF_REQUIRE(aligned16(table), RNERF_E_ALIGN, "rnerf_grid_table: table must be 16-byte aligned");
   GridGeom g = make_geom(ndim, nmin, nmax);
-  const int64_t total = (int64_t)ndim[0] * ndim[1] * ndim[2];
-  table_kernel<<<grid_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(n, (float4*)table, g);
+  RNERF_REQUIRE((int64_t)ndim[0] * ndim[1] < 2147483647LL, RNERF_E_SHAPE, "rnerf_grid_table: ndim[0] * ndim[1] must fit 31 bits");
+  TableRecips rc;
+  for (int i = 0; i < 3; ++i) rc.r[i] = fast_div_enabled() ? recip_for(g.two_ndelta[i], (cudaStream_t)stream) : 0.f;
+  const int rows = ndim[0] * ndim[1];
+  table_kernel<<<rows < 1048576 ? rows : 1048576, 256, 0, (cudaStream_t)stream>>>(n, (float4*)table, g, rc);
   count_launch();
   return check_launch("rnerf_grid_table");
 }
@@ -166,8 +193,9 @@ extern "C" int rnerf_grid_table_bwd(const float* d_table, const int ndim[3], con
   RNERF_REQUIRE(ndim[0] > 1 && ndim[1] > 1 && ndim[2] > 1, RNERF_E_SHAPE, "rnerf_grid_table_bwd: every grid side must be >= 2");
   RNERF_REQUIRE(aligned16(d_table), RNERF_E_ALIGN, "rnerf_grid_table_bwd: d_table must be 16-byte aligned");
   GridGeom g = make_geom(ndim, nmin, nmax);
-  const int64_t total = (int64_t)ndim[0] * ndim[1] * ndim[2];
-  table_bwd_kernel<<<grid_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_table, d_n, g);
+  RNERF_REQUIRE((int64_t)ndim[0] * ndim[1] < 2147483647LL, RNERF_E_SHAPE, "rnerf_grid_table_bwd: ndim[0] * ndim[1] must fit 31 bits");
+  const int rows = ndim[0] * ndim[1];
+  table_bwd_kernel<<<rows < 1048576 ? rows : 1048576, 256, 0, (cudaStream_t)stream>>>((const float4*)d_table, d_n, g);
   count_launch();
   return check_launch("rnerf_grid_table_bwd");
 }

@@ -45,6 +45,9 @@ float recip_for(float d, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+    return 0.f;                 // the verification synchronises: not inside a graph capture (IEEE divisions this time, not cached)
   float y = 0.f;
   if (d == d && fabsf(d) >= 0x1p-30f && fabsf(d) <= 0x1p30f) {
     const float cand = (float)(1.0 / (double)d);
@@ -1181,7 +1184,7 @@ __global__ void __launch_bounds__(256) select_kernel(const float4* __restrict__ 
 using namespace rnerf;
 
 // RNERF_MARCH_DIV=ieee forces IEEE divisions for the grid coordinates (results are identical either way)
-static bool fast_div_enabled() {
+bool rnerf::fast_div_enabled() {
   const char* e = getenv("RNERF_MARCH_DIV");      // read per call so that a test can compare both modes in one process
   return !(e != nullptr && strcmp(e, "ieee") == 0);
 }

@@ -139,6 +139,7 @@ __device__ __forceinline__ void ring_drain(So3Ring& r) {
 
 // verified reciprocal of a grid pitch for div_by_const, or 0 (march.cu)
 float recip_for(float d, cudaStream_t st);
+bool fast_div_enabled();     // RNERF_MARCH_DIV=ieee switches the verified sequence off (march.cu)
 int so3_rays_per_cta(int64_t n_rays, int n_sm);
 // geometry + verified reciprocals; returns true when the 3-instruction division may be used (march.cu)
 bool make_march_geom(const int ndim[3], const double nmin[3], const double nmax[3], cudaStream_t st, MarchGeom& mg);

@@ -22,6 +22,23 @@ def test_grid_table_bit_exact(cuda_lib, scene):
     assert torch.equal(t, scene["table"]), f"max abs diff {(t - scene['table']).abs().max()}"
 
 
+def test_grid_table_constant_division_equals_ieee(cuda_lib, monkeypatch):
+    """The (n, grad n) table divides by the constants 2 * ndelta with the exhaustively verified multiply/FMA sequence; it must
+    give the bits of the IEEE division (RNERF_MARCH_DIV=ieee) on noisy grids with non-cubic shapes and awkward pitches, and the
+    oracle's table."""
+    from samplenerfro_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    for ndim, lo, hi in (([17, 9, 33], [-1.3, -0.7, -2.1], [1.9, 0.4, 0.3]), ([40, 40, 40], [-1.5] * 3, [1.5] * 3)):
+        n = 1.0 + 0.6 * torch.rand(ndim[0] * ndim[1] * ndim[2], generator=gen)
+        n[::5] = n[1::5][: n[::5].numel()]                 # exact zeros among the differences
+        fast = ops.grid_table(n.cuda(), ndim, lo, hi).cpu()
+        monkeypatch.setenv("RNERF_MARCH_DIV", "ieee")
+        ieee = ops.grid_table(n.cuda(), ndim, lo, hi).cpu()
+        monkeypatch.delenv("RNERF_MARCH_DIV")
+        assert torch.equal(fast.view(torch.int32), ieee.view(torch.int32))
+        assert torch.equal(fast, O.build_table(n.reshape(ndim), ndim, lo, hi))
+
+
 @pytest.mark.parametrize("ws,sigma", [(3, 1.0), (5, 3.0), (9, 3.0)])
 def test_grid_blur(cuda_lib, ws, sigma):
     from samplenerfro_b200 import ops
