@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RNERF_ABI_VERSION 10
+#define RNERF_ABI_VERSION 11
 #define RNERF_PATH_STRIDE 12         /* full records */
 #define RNERF_PATH_STRIDE_COMPACT 8
 
@@ -260,6 +260,12 @@ size_t rnerf_so3_tc_packed_bytes(void);
 int rnerf_so3_tc_pack(const float* so3_w, void* so3_tc_packed, void* stream);
 int rnerf_so3_predict_tc(const void* so3_tc_packed, const float* so3_w, const double so3_window_host[10],
                          const float* so3_window_dev, const float* pts, const float* cond, int64_t n, float* pred, void* stream);
+/* a10 on the tensor pipe (render path): bkgd_mlp(pos_enc(dir, 0, 4)) (rnerf/models.py:303, rnerf/model_utils.py:93-140) with the
+ * so3 evaluator -- the two networks have the same shape (27 / 60 inputs -> 128 x 4 with the inputs re-joined before Dense_3 -> 3).
+ * bkgd_so3: the background weights zero-padded into so3_mlp's layout (rnerf_so3_weight_floats() floats); bkgd_tc_packed =
+ * rnerf_so3_tc_pack(bkgd_so3).  fp16 hi/lo split operands, fp32 accumulation: 1e-6 of rnerf_bkgd_mlp_fwd. */
+int rnerf_bkgd_mlp_fwd_tc(const void* bkgd_tc_packed, const float* bkgd_so3, const float* dirs, int64_t n_rays,
+                          int64_t dir_stride_floats, float* raw_out, void* stream);
 size_t rnerf_mlp_input_grad_packed_floats(void);
 int rnerf_mlp_input_grad_pack(const float* dense0_kernel, const float* dense5_kernel, const float* dense10_kernel,
                               float* wt, void* stream);

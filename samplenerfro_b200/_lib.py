@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RNERF_LIB") or os.path.join(_HERE, "librnerf_b200.so")
 
 _lib: Optional[C.CDLL] = None
-ABI_VERSION = 10      # include/rnerf_b200.h RNERF_ABI_VERSION
+ABI_VERSION = 11      # include/rnerf_b200.h RNERF_ABI_VERSION
 
 c_f32p = C.c_void_p
 c_i64 = C.c_int64
@@ -78,6 +78,7 @@ SIGNATURES = {
     "rnerf_so3_tc_packed_bytes": (C.c_size_t, []),
     "rnerf_so3_tc_pack": (C.c_int, [c_f32p, C.c_void_p, C.c_void_p]),
     "rnerf_so3_predict_tc": (C.c_int, [C.c_void_p, c_f32p, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_i64, c_f32p, C.c_void_p]),
+    "rnerf_bkgd_mlp_fwd_tc": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64, c_i64, c_f32p, C.c_void_p]),
     "rnerf_so3_transposed_floats": (C.c_size_t, []),
     "rnerf_so3_transpose": (C.c_int, [c_f32p, c_f32p, C.c_void_p]),
     "rnerf_march_all_bwd": (C.c_int, [c_f32p, c_f32p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), c_f32p,

@@ -111,6 +111,14 @@ def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: tor
 
 
 # ----------------------------------------------------------------------------- background MLP (a10)
+BKGD_TC_MIN_RAYS = 8192      # no-grad evaluations of at least this many rays run on the tensor pipe (fp16 hi/lo split, fp32-grade)
+
+
+def _bkgd_tc_enabled() -> bool:
+    import os
+    return os.environ.get("RNERF_BKGD_TC", "1") != "0"      # development aid: RNERF_BKGD_TC=0 keeps the fp32 CUDA-core kernel
+
+
 class _BkgdMLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sink, w, dirs, n_rays, stride, offset, *params):
@@ -143,6 +151,8 @@ def bkgd_raw(model, variables: Dict, dir_c: torch.Tensor, n_rays: int, n_coarse:
     if _needs_grad(p):
         return _BkgdMLP.apply(_sink(model, "bkgd_mlp"), w, dir_c, n_rays, stride, offset, *_mlp_param_list(p, 5))
     with torch.no_grad():
+        if n_rays >= BKGD_TC_MIN_RAYS and _bkgd_tc_enabled():     # a frame's worth of rays: the so3 evaluator on the tensor pipe
+            return ops.bkgd_mlp_fwd_tc(model._bkgd_tc(variables), dir_c, n_rays, stride, offset)
         return ops.bkgd_mlp_fwd(w, dir_c, n_rays, stride, offset)
 
 
@@ -155,7 +165,10 @@ def bkgd_color(model, variables: Dict, viewdirs: torch.Tensor) -> torch.Tensor:
         raw = _BkgdMLP.apply(_sink(model, "bkgd_mlp"), w, viewdirs, n, 3, 0, *_mlp_param_list(p, 5))
     else:
         with torch.no_grad():
-            raw = ops.bkgd_mlp_fwd(w, viewdirs, n, 3, 0)
+            if n >= BKGD_TC_MIN_RAYS and _bkgd_tc_enabled():
+                raw = ops.bkgd_mlp_fwd_tc(model._bkgd_tc(variables), viewdirs, n, 3, 0)
+            else:
+                raw = ops.bkgd_mlp_fwd(w, viewdirs, n, 3, 0)
     return torch.sigmoid(raw) * (1 + 2 * model.rgb_padding) - model.rgb_padding
 
 

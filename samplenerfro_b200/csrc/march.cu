@@ -611,9 +611,23 @@ struct TcPredictSmem {
   static constexpr uint32_t TMEM_SLOT = BAR_OFF + (2 * TCP_SLOTS + 2) * 8;
   static constexpr uint32_t BYTES = TMEM_SLOT + 16;
 };
+// pos_enc(dir, 0, 4) of the background MLP (rnerf/model_utils.py:204-214; same arithmetic as bkgd_mlp.cu): feature f < 27
+__device__ __forceinline__ float bkgd_enc_value(int f, float d0, float d1, float d2) {
+  if (f >= 27) return 0.f;
+  if (f < 3) return f == 0 ? d0 : (f == 1 ? d1 : d2);
+  const int q = (f - 3) % 12, k = q / 3, c = q - 3 * k;
+  float xb = mul(c == 0 ? d0 : (c == 1 ? d1 : d2), (float)(1 << k));
+  if (f >= 15) xb = add(xb, 1.57079632679489661923f);
+  return sinf(xb);
+}
+
+// BKGD = false: VoxMLP.wrapper_grad_mlp on free-standing points (pred = rodrigues(so3_mlp(enc(pts)), cond)).
+// BKGD = true: the background MLP (model_utils.MLP 27 -> 128 x4 (+27) -> 3: the same network shape as so3_mlp, so its weights
+// are handed over zero-padded in so3 layout) on ray directions read with a stride; pred = the 3 raw outputs.
+template <bool BKGD>
 __global__ void __launch_bounds__(TCP_THREADS, 1) so3_predict_tc_kernel(const uint8_t* __restrict__ packed, const So3Args so3,
                                                                         const float* __restrict__ pts, const float* __restrict__ cond,
-                                                                        int64_t n, float* __restrict__ pred) {
+                                                                        int64_t n, float* __restrict__ pred, int64_t pts_stride) {
   using SL = TcPredictSmem;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   const uint32_t sbase = smem_u32(tc_smem);
@@ -679,10 +693,16 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) so3_predict_tc_kernel(const ui
       workers_sync();                            // the previous pass's head has finished with P / RAW / HS
       if (wt < TC_N) {
         const int64_t i = p0 + min(wt, n_here - 1);
-        P[wt] = pts[3 * i]; P[TC_N + wt] = pts[3 * i + 1]; P[2 * TC_N + wt] = pts[3 * i + 2];
+        const float* src = pts + i * pts_stride;
+        P[wt] = src[0]; P[TC_N + wt] = src[1]; P[2 * TC_N + wt] = src[2];
       }
       workers_sync();
-      if (!(so3.dbg & 4)) {
+      if (BKGD) {
+        for (int c = warp - 2; c < TC_N; c += 4) {               // one warp per column, lane = feature (and feature + 32: zero)
+          tc_enc_store(tc_smem, c, 0, lane, bkgd_enc_value(lane, P[c], P[TC_N + c], P[2 * TC_N + c]));
+          tc_enc_store(tc_smem, c, 1, lane, 0.f);
+        }
+      } else if (!(so3.dbg & 4)) {
         const TcEncLane enc = tc_enc_lane(so3, lane);
         for (int c = warp - 2; c < TC_N; c += 4)                 // one warp per column, lane = feature (and feature + 32)
 #pragma unroll
@@ -713,9 +733,13 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) so3_predict_tc_kernel(const ui
       workers_sync();
       if (wt < n_here) {
         const int64_t i = p0 + wt;
-        float gx = cond[3 * i], gy = cond[3 * i + 1], gz = cond[3 * i + 2];
-        so3_rotate(RAW[wt], RAW[TC_N + wt], RAW[2 * TC_N + wt], gx, gy, gz);
-        pred[3 * i] = gx; pred[3 * i + 1] = gy; pred[3 * i + 2] = gz;
+        if (BKGD) {
+          pred[3 * i] = RAW[wt]; pred[3 * i + 1] = RAW[TC_N + wt]; pred[3 * i + 2] = RAW[2 * TC_N + wt];
+        } else {
+          float gx = cond[3 * i], gy = cond[3 * i + 1], gz = cond[3 * i + 2];
+          so3_rotate(RAW[wt], RAW[TC_N + wt], RAW[2 * TC_N + wt], gx, gy, gz);
+          pred[3 * i] = gx; pred[3 * i + 1] = gy; pred[3 * i + 2] = gz;
+        }
       }
     }
   }
@@ -1437,16 +1461,40 @@ extern "C" int rnerf_so3_predict_tc(const void* so3_tc_packed, const float* so3_
   for (int k = 0; k < 10; ++k) so3.window[k] = so3_window != nullptr ? (float)so3_window[k] : 0.f;
   so3.window_dev = so3_window_dev;
   { const char* d = getenv("RNERF_SO3_TC_DEBUG"); so3.dbg = d ? atoi(d) : 0; }
-  cudaError_t e = cudaFuncSetAttribute(so3_predict_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPredictSmem::BYTES);
+  cudaError_t e = cudaFuncSetAttribute(so3_predict_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPredictSmem::BYTES);
   if (e != cudaSuccess) { set_error("rnerf_so3_predict_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (n + TC_N - 1) / TC_N;
-  so3_predict_tc_kernel<<<(unsigned)(tiles < n_sm ? tiles : n_sm), TCP_THREADS, TcPredictSmem::BYTES, (cudaStream_t)stream>>>(
-      (const uint8_t*)so3_tc_packed, so3, pts, cond, n, pred);
+  so3_predict_tc_kernel<false><<<(unsigned)(tiles < n_sm ? tiles : n_sm), TCP_THREADS, TcPredictSmem::BYTES, (cudaStream_t)stream>>>(
+      (const uint8_t*)so3_tc_packed, so3, pts, cond, n, pred, 3);
   count_launch();
   return check_launch("rnerf_so3_predict_tc");
+}
+
+// The background MLP on the tensor pipe (render path: one evaluation per ray of a frame).  bkgd_so3 = the background weights
+// zero-padded into so3_mlp's layout (rnerf_so3_weight_floats() floats: Dense_0 rows 27..59 and Dense_3 rows 155..187 zero),
+// bkgd_tc_packed = rnerf_so3_tc_pack(bkgd_so3).  dirs is read with a ray stride like rnerf_bkgd_mlp_fwd.
+extern "C" int rnerf_bkgd_mlp_fwd_tc(const void* bkgd_tc_packed, const float* bkgd_so3, const float* dirs, int64_t n_rays,
+                                     int64_t dir_stride_floats, float* raw_out, void* stream) {
+  RNERF_REQUIRE(n_rays >= 0 && dir_stride_floats >= 3, RNERF_E_SHAPE, "rnerf_bkgd_mlp_fwd_tc: bad sizes");
+  if (n_rays == 0) return 0;
+  RNERF_REQUIRE_PTR(bkgd_tc_packed); RNERF_REQUIRE_PTR(bkgd_so3); RNERF_REQUIRE_PTR(dirs); RNERF_REQUIRE_PTR(raw_out);
+  RNERF_REQUIRE(aligned16(bkgd_tc_packed) && aligned16(bkgd_so3), RNERF_E_ALIGN, "rnerf_bkgd_mlp_fwd_tc: weight images must be 16-byte aligned");
+  So3Args so3;
+  memset(&so3, 0, sizeof(so3));
+  so3.w = bkgd_so3;
+  cudaError_t e = cudaFuncSetAttribute(so3_predict_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPredictSmem::BYTES);
+  if (e != cudaSuccess) { set_error("rnerf_bkgd_mlp_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (n_rays + TC_N - 1) / TC_N;
+  so3_predict_tc_kernel<true><<<(unsigned)(tiles < n_sm ? tiles : n_sm), TCP_THREADS, TcPredictSmem::BYTES, (cudaStream_t)stream>>>(
+      (const uint8_t*)bkgd_tc_packed, so3, dirs, nullptr, n_rays, raw_out, dir_stride_floats);
+  count_launch();
+  return check_launch("rnerf_bkgd_mlp_fwd_tc");
 }
 
 extern "C" int rnerf_so3_predict(const float* so3_w, const double so3_window[10], const float* so3_window_dev, const float* pts,

@@ -164,6 +164,18 @@ class NerfModel:
         self._pack_cache[name] = (sig, buf)
         return buf
 
+    def _bkgd_tc(self, variables: Dict):
+        """Tensor-pipe image of the background MLP (ops.bkgd_tc_pack) for whole-frame evaluations; rebuilt when a parameter
+        tensor changed."""
+        p = variables["params"]["bkgd_mlp"]
+        sig = tuple((id(d["kernel"]), d["kernel"]._version, id(d["bias"]), d["bias"]._version) for d in p.values())
+        hit = self._pack_cache.get("bkgd_mlp_tc")
+        if hit is None or hit[0] != sig:
+            with torch.no_grad():
+                hit = (sig, ops.bkgd_tc_pack(self._packed(variables, "bkgd_mlp")))
+            self._pack_cache["bkgd_mlp_tc"] = hit
+        return hit[1]
+
     def so3_window(self, annealed_alpha: float) -> List[float]:
         """cosine_easing_window(0, 9, 10, annealed_alpha * 10) of annealed_pos_enc (rnerf/model_utils.py:222-245), in
         fp32 like the reference evaluates it."""

@@ -383,6 +383,29 @@ def bkgd_mlp_fwd(w: torch.Tensor, dirs: torch.Tensor, n_rays: int, stride_floats
     return out
 
 
+def bkgd_tc_pack(w: torch.Tensor):
+    """Background weights (bkgd_pack layout) -> (the same zero-padded into so3_mlp's layout, its tensor-pipe image): the two
+    networks have the same shape, so the so3 evaluator runs the background MLP of a whole frame (bkgd_mlp_fwd_tc)."""
+    _chk(w, "w")
+    k0, k1, k2, k3, k4 = 27 * 128, 128 * 128, 128 * 128, 155 * 128, 128 * 3
+    o = [0, k0, k0 + k1, k0 + k1 + k2, k0 + k1 + k2 + k3, k0 + k1 + k2 + k3 + k4]
+    z = lambda rows: torch.zeros(rows * 128, device=w.device, dtype=torch.float32)
+    img = torch.cat([w[o[0]:o[1]], z(60 - 27), w[o[1]:o[2]], w[o[2]:o[3]], w[o[3]:o[4]], z(188 - 155), w[o[4]:o[5]], w[o[5]:]]).contiguous()
+    assert img.numel() == _lib.load().rnerf_so3_weight_floats()
+    return img, so3_tc_pack(img)
+
+
+def bkgd_mlp_fwd_tc(tc, dirs: torch.Tensor, n_rays: int, stride_floats: int = 3, offset_floats: int = 0):
+    """bkgd_mlp_fwd on the tensor pipe; tc = bkgd_tc_pack(w)."""
+    img, packed = tc
+    _chk(dirs, "dirs")
+    out = torch.empty(n_rays, 3, device=dirs.device, dtype=torch.float32)
+    ptr = C.c_void_p(dirs.data_ptr() + 4 * offset_floats)
+    check(_lib.load().rnerf_bkgd_mlp_fwd_tc(_p(packed), _p(img), ptr, n_rays, stride_floats, _p(out), _stream()),
+          "rnerf_bkgd_mlp_fwd_tc")
+    return out
+
+
 # ---------------------------------------------------------------- compositing (a11, a12)
 def composite_fwd(raw, t, dirs, bkgd_raw=None, mask=None, white_bkgd=False, rgb_padding=0.001, sigma_bias=-1.0,
                   want_weights=True, want_alpha=False):

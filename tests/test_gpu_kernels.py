@@ -295,6 +295,27 @@ def test_bkgd_mlp(cuda_lib):
     assert (out - ref).abs().max().item() < 2e-5, (out - ref).abs().max().item()
 
 
+@pytest.mark.parametrize("B", [1, 63, 64, 1000, 148 * 64 * 2 + 17])
+def test_bkgd_mlp_on_the_tensor_pipe(cuda_lib, B):
+    """The background MLP through the so3 evaluator (fp16 hi/lo split operands on tcgen05, fp32 accumulation): within 2e-6 of
+    the fp32 CUDA-core kernel relative to the output scale, and within the same 2e-5 of the oracle; strided directions, ragged
+    tiles, more tiles than SMs."""
+    from samplenerfro_b200 import ops
+    gen = torch.Generator().manual_seed(B)
+    p = O.init_small_mlp(gen, bias_scale=0.1)
+    Nc = 3
+    d = torch.randn(B, Nc, 3, generator=gen)
+    d = d / d.norm(dim=-1, keepdim=True)
+    w = ops.bkgd_pack(H.to_cuda_params(p))
+    dc = d.cuda().contiguous()
+    fp32 = ops.bkgd_mlp_fwd(w, dc, B, stride_floats=Nc * 3, offset_floats=(Nc - 1) * 3)
+    tc = ops.bkgd_mlp_fwd_tc(ops.bkgd_tc_pack(w), dc, B, stride_floats=Nc * 3, offset_floats=(Nc - 1) * 3)
+    scale = fp32.abs().max().item()
+    assert (tc - fp32).abs().max().item() < 2e-6 * max(scale, 1.0), ((tc - fp32).abs().max().item(), scale)
+    ref = O.small_mlp(p, O.pos_enc(d[:, -1:], 0, 4))[:, 0]
+    assert (tc.cpu() - ref).abs().max().item() < 2e-5
+
+
 @pytest.mark.parametrize("M", [128, 1000, 148 * 128 + 77, 60000, 74 * 512 * 3 + 333])
 def test_encmlp_vs_bf16_oracle(cuda_lib, M):
     """Per-layer outputs vs an oracle that rounds operands to bf16 at the same points (fp32 accumulate).
