@@ -111,7 +111,7 @@ def radiance_mlp(model, variables: Dict, name: str, pos: torch.Tensor, dirs: tor
 
 
 # ----------------------------------------------------------------------------- background MLP (a10)
-BKGD_TC_MIN_RAYS = 8192      # no-grad evaluations of at least this many rays run on the tensor pipe (fp16 hi/lo split, fp32-grade)
+BKGD_TC_MIN_RAYS = 8192      # evaluations of at least this many rays run their forward on the tensor pipe (fp16 hi/lo split, fp32-grade)
 
 
 def _bkgd_tc_enabled() -> bool:
@@ -125,6 +125,10 @@ class _BkgdMLP(torch.autograd.Function):
         ctx.geom = (n_rays, stride, offset)
         ctx.sink = sink
         ctx.save_for_backward(w, dirs, *params)
+        if n_rays >= BKGD_TC_MIN_RAYS and _bkgd_tc_enabled():
+            # (a training step's env patch: the backward kernel recomputes the forward in fp32 anyway, so only the outputs
+            # are needed here; the tensor-pipe image is rebuilt from this step's weights, two small kernels)
+            return ops.bkgd_mlp_fwd_tc(ops.bkgd_tc_pack(w), dirs, n_rays, stride, offset)
         return ops.bkgd_mlp_fwd(w, dirs, n_rays, stride, offset)
 
     @staticmethod
