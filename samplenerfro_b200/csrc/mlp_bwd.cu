@@ -330,9 +330,20 @@ __global__ void __launch_bounds__(256) mlp_head_grad_kernel(const __nv_bfloat16*
 // wgrad: G[Kx x N] += X[rows][Kx]^T  dZ[rows][N]   (MN-major operands, reduction over rows), gb[N] += colsum(dZ)
 // One CTA = one slab of rows; accumulators: Kx/128 M-blocks x N columns of TMEM.
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_ROWS = 32;                           // rows (GEMM K) per pipeline stage
-constexpr int WG_STAGES = 6;
-constexpr int WG_DEPTH = 4;                           // stages of loads kept in flight (128 KB per SM: the kernel is HBM-bound)
+// Stage geometry, measured on the 4096-ray step [r6k]: 64 rows x 3 stages, 2 in flight 6.13 ms/step; 32 x 6, 4 in flight (the
+// first version) 6.43; 48 x 4 6.28; 96 x 2 6.34; 16 x 12 7.35 -- every stage costs two named barriers and a bias pass over
+// the tile, so few large stages win as long as one whole stage is in flight behind the one being published.
+#ifndef RNERF_WG_ROWS          // (overridable for A/B builds: RNERF_NVCC_EXTRA="-DRNERF_WG_ROWS=32 -DRNERF_WG_STAGES=6 -DRNERF_WG_DEPTH=4")
+#define RNERF_WG_ROWS 64
+#define RNERF_WG_STAGES 3
+#define RNERF_WG_DEPTH 2
+#endif
+#ifndef RNERF_WG_BIG_ROWS      // rows per CTA and job above which every job gets all the SMs (see rnerf_mlp_wgrad_batched)
+#define RNERF_WG_BIG_ROWS 1024
+#endif
+constexpr int WG_ROWS = RNERF_WG_ROWS;                // rows (GEMM K) per pipeline stage
+constexpr int WG_STAGES = RNERF_WG_STAGES;
+constexpr int WG_DEPTH = RNERF_WG_DEPTH;              // stages of loads kept in flight (128 KB per SM: the kernel is HBM-bound)
 constexpr int WG_STAGE_BYTES = WG_ROWS * 256 * 2 * 2; // X tile [32 x 256] + dZ tile [32 x 256] bf16 = 32 KB
 constexpr int WG_THREADS = 64 + 256;                  // warp 0: MMA, warp 1: spare, warps 2-9: loaders/epilogue
 
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
         default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
       }
     };
-    static_assert(WG_DEPTH == 4 && WG_DEPTH <= WG_STAGES, "wait_pending covers depths up to 4");
+    static_assert(WG_DEPTH >= 2 && WG_DEPTH <= 4 && WG_DEPTH <= WG_STAGES && WG_ROWS % 16 == 0, "wait_pending covers depths up to 4");
     int stage = 0; uint32_t phase = 0;
     for (int it = 0; it < n_steps; ++it) {
       mbar_wait(bar_empty(stage), phase ^ 1);
@@ -697,14 +708,14 @@ extern "C" int rnerf_mlp_wgrad_batched(int n_jobs, const uint16_t* const* x, con
     RNERF_REQUIRE(aligned16(x[j]) && aligned16(dz[j]), RNERF_E_ALIGN, "rnerf_mlp_wgrad_batched: job %d: x/dz must be 16-byte aligned", j);
     total += (double)(x_cols[j] + n[j]);
   }
-  // CTAs per job.  Large batches (>= 32 pipeline stages per CTA even when a job is cut over every SM): every job gets all the
+  // CTAs per job.  Large batches (>= 1024 rows per CTA even when a job is cut over every SM): every job gets all the
   // SMs, jobs in sequence -- the schedule of 13 separate launches without their gaps and tails (measured: a single wave with
   // ~60 000 rows per CTA is slower, the per-stage floor of the short-row jobs unbalances it).  Small batches (a 512-ray shard
   // of an 8-GPU step): one wave, the SMs divided in proportion to the bytes each job streams, so the fixed costs (TMEM
   // allocation, the 256 KB accumulator flush) are paid once per SM instead of 13 times.
   int ctas[WG_MAX_JOBS], sum = 0;
   const int64_t max_ctas = (n_samples + WG_ROWS - 1) / WG_ROWS;
-  const bool big = n_samples >= (int64_t)n_sm * WG_ROWS * 32;
+  const bool big = n_samples >= (int64_t)n_sm * RNERF_WG_BIG_ROWS;
   for (int j = 0; j < n_jobs; ++j) {
     int c = big ? n_sm : (int)((double)n_sm * (x_cols[j] + n[j]) / total);
     if (c < 1) c = 1;
