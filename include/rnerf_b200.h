@@ -127,7 +127,7 @@ int rnerf_encmlp_fwd_debug(const void* packed, const float* pos, const float* di
  * rnerf_encmlp_fwd_train additionally saves layer_out[10][M][256] (bf16 post-activation outputs of Dense_0..7,
  * Dense_9, Dense_10), enc_out[2][M][64] (bf16 pos_enc / dir_enc rows, zero padded) and relu_masks[10][M][8] (uint32: one bit
  * per activation, set where it is positive -- all the dgrad chain needs of the activations; 32 B instead of 512 B per
- * sample and layer; bit layout: csrc/umma.cuh relu_mask_push).
+ * sample and layer; bit layout: csrc/umma.cuh relu_mask32: word g = columns 32g..32g+31, even column 2i at bit i, odd column 2i+1 at bit 16+i).
  * rnerf_mlp_dgrad: fused tcgen05 chain producing dz_out[10][M][256] (bf16 gradient wrt every layer's pre-activation)
  *   from d_raw[M][4] and relu_masks; dgrad_packed comes from rnerf_mlp_dgrad_pack (transposed weight image, rebuilt when
  *   weights change).

@@ -112,7 +112,7 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, const float* __rest
                                              uint8_t* __restrict__ a_row, uint32_t r7s, EpiOut& o,
                                              __nv_bfloat16* __restrict__ dump_row, uint32_t* __restrict__ mask_row = nullptr) {
   constexpr int NCG = (KIND == 3) ? 4 : 8;
-  uint32_t m2[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};      // ReLU bit-mask words of columns 0..127 / 128..255 (umma.cuh)
+  uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};             // ReLU bit-mask word of every 32-column group (umma.cuh)
 #pragma unroll 1
   for (int cg2 = 0; cg2 < NCG; cg2 += 2) {   // 2 x 32 accumulator columns per iteration, both TMEM loads in flight
     uint32_t v[2][32];
@@ -133,7 +133,7 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, const float* __rest
         if (KIND == 2) { pk[2 * j4] = pack_bf16(f0, f1);      pk[2 * j4 + 1] = pack_bf16(f2, f3); }
         else           { pk[2 * j4] = pack_bf16_relu(f0, f1); pk[2 * j4 + 1] = pack_bf16_relu(f2, f3); }
       }
-      if (DUMP && KIND != 2) { if (cg2 < 4) relu_mask_push(m2[0], pk); else relu_mask_push(m2[1], pk); }
+      if (DUMP && KIND != 2) relu_mask_set(mw, cg2 + half, relu_mask32(pk));
       if (KIND == 1) {  // sigma head (Dense_8) on the bf16-rounded trunk output; weights in vslot[0..255]
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -174,8 +174,8 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, const float* __rest
     }
   }
   if (DUMP && KIND != 2 && mask_row != nullptr) {
-    reinterpret_cast<uint4*>(mask_row)[0] = make_uint4(m2[0][0], m2[0][1], m2[0][2], m2[0][3]);
-    reinterpret_cast<uint4*>(mask_row)[1] = make_uint4(m2[1][0], m2[1][1], m2[1][2], m2[1][3]);
+    reinterpret_cast<uint4*>(mask_row)[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+    if (KIND != 3) reinterpret_cast<uint4*>(mask_row)[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
   }
 }
 

@@ -50,7 +50,7 @@ __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __res
                                               __nv_bfloat16* __restrict__ dump_row = nullptr /* KIND 3 in training mode */,
                                               uint32_t* __restrict__ mask_row = nullptr /* training: this row's 4 mask words */) {
   constexpr int NCG = (KIND == 3) ? 2 : 4;
-  uint32_t m2[4] = {0u, 0u, 0u, 0u};
+  uint32_t mw[4] = {0u, 0u, 0u, 0u};      // ReLU bit-mask word of each of this thread's 32-column groups (umma.cuh)
 #ifdef RNERF_PAIR_PIPELINED_LD
   // two TMEM loads in flight: group cg+1 is fetched while group cg is converted and stored
   uint32_t vv[2][32];
@@ -80,7 +80,7 @@ __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __res
       if (KIND == 2) { pk[2 * j4] = pack_bf16(f0, f1);      pk[2 * j4 + 1] = pack_bf16(f2, f3); }
       else           { pk[2 * j4] = pack_bf16_relu(f0, f1); pk[2 * j4 + 1] = pack_bf16_relu(f2, f3); }
     }
-    if (DUMP && KIND != 2) relu_mask_push(m2, pk);
+    if (DUMP && KIND != 2) relu_mask_set(mw, cg, relu_mask32(pk));
     if (KIND == 1) {  // sigma head (Dense_8): hw = w_sigma[256]
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
@@ -119,9 +119,9 @@ __device__ __forceinline__ void pair_epilogue(uint32_t taddr, const float* __res
     }
   }
   if (DUMP && KIND != 2 && mask_row != nullptr) {
-    // KIND 3: this warpgroup holds 64 of the layer's 128 columns (two groups): columns 0..63 go to bits 15..8, 64..127 to 7..0
-    const int sh = (KIND == 3 && col0 == 0) ? 8 : 0;
-    *reinterpret_cast<uint4*>(mask_row) = make_uint4(m2[0] << sh, m2[1] << sh, m2[2] << sh, m2[3] << sh);
+    // (mask_row points at this warpgroup's first word: 4 groups of 32 columns, or 2 for the condition layer's 64)
+    if (KIND == 3) *reinterpret_cast<uint2*>(mask_row) = make_uint2(mw[0], mw[1]);
+    else *reinterpret_cast<uint4*>(mask_row) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
   }
 }
 
@@ -333,7 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) enc
           tile_bar_sync(t);
           pair_epilogue<3, TRAIN>(taddr_row + half * 64, bias_s, a_scratch, a_row, r7s, half * 64, eo,
                                   (TRAIN && live) ? args.layer_out + ((size_t)9 * args.n_samples + srow) * 256 : nullptr,
-                                  (TRAIN && live && args.mask_out) ? args.mask_out + ((size_t)9 * args.n_samples + srow) * 8 + half * 4 : nullptr);
+                                  (TRAIN && live && args.mask_out) ? args.mask_out + ((size_t)9 * args.n_samples + srow) * 8 + half * 2 : nullptr);
           // combine the two column halves: half 1 parks its partial sums, half 0 adds and writes the row
           float4* part = reinterpret_cast<float4*>(a_scratch + 1024);
           if (half == 1) part[row] = make_float4(eo.r, eo.g, eo.b, eo.sigma);

@@ -20,7 +20,7 @@ constexpr size_t DG_TOTAL_BYTES = DG_PAIR_OFF + (size_t)DGP_NCHUNK * PAIR_CHUNK_
 struct DgradArgs {
   const uint8_t* packed;        // dgrad weight image (dgrad_pack_kernel)
   const float* head_w;          // w_sigma[256] then w_rgb[3][128], bf16-rounded fp32 (forward image tail)
-  const uint32_t* masks;        // [10][M][8] ReLU bit-masks written by the training forward (relu_mask_push, umma.cuh)
+  const uint32_t* masks;        // [10][M][8] ReLU bit-masks written by the training forward (relu_mask32, umma.cuh)
   const float4* d_raw;          // [M] (d rgb_raw[3], d sigma_raw)
   __nv_bfloat16* dZ;            // [10][M][256] out
   int64_t n_samples;

@@ -163,11 +163,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DGP_THREADS, 1) mlp_
       const float4 draw = live ? __ldg(args.d_raw + lrow) : make_float4(0.f, 0.f, 0.f, 0.f);
       // ---- prologue: rgb head (Dense_11) backward + ReLU of the condition layer -> dZ[9]; this half's 64 columns = k-block `half`
       {
-        uint32_t m9[4];                           // condition layer: 128 columns, the two writers' words OR-ed
+        uint32_t m9[2];                           // condition layer: this half's 64 columns = words 2 half, 2 half + 1
         {
-          const uint4* mp = reinterpret_cast<const uint4*>(args.masks + ((size_t)9 * args.n_samples + lrow) * 8);
-          const uint4 a4 = __ldg(mp), b4 = __ldg(mp + 1);
-          m9[0] = a4.x | b4.x; m9[1] = a4.y | b4.y; m9[2] = a4.z | b4.z; m9[3] = a4.w | b4.w;
+          const uint2 a2 = __ldg(reinterpret_cast<const uint2*>(args.masks + ((size_t)9 * args.n_samples + lrow) * 8) + half);
+          m9[0] = a2.x; m9[1] = a2.y;
         }
         tile_free();
         tile_bar_sync(t);                         // k-block 1 was last stored by the OTHER warpgroup (dZ[0], columns 64..127)
@@ -180,9 +179,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DGP_THREADS, 1) mlp_
             const int j0 = c8 * 8 + i * 2;
             float g0 = draw.x * w_rgb[j0] + draw.y * w_rgb[128 + j0] + draw.z * w_rgb[256 + j0];
             float g1 = draw.x * w_rgb[j0 + 1] + draw.y * w_rgb[128 + j0 + 1] + draw.z * w_rgb[256 + j0 + 1];
-            // columns 8 c8 + 2 i, + 1: word i, step c8 (relu_mask_push)
-            if (!((m9[i] >> (15 - c8)) & 1u)) g0 = 0.f;
-            if (!((m9[i] >> (31 - c8)) & 1u)) g1 = 0.f;
+            // columns 8 c8 + 2 i, + 1: pair (u & 3) * 4 + i of this half's group u >> 2 (relu_mask32)
+            const uint32_t word = (u >> 2) == 0 ? m9[0] : m9[1];
+            if (!relu_mask_even(word, (u & 3) * 4 + i)) g0 = 0.f;
+            if (!relu_mask_odd(word, (u & 3) * 4 + i)) g1 = 0.f;
             pk[i] = pack_bf16(g0, g1);
           }
           *reinterpret_cast<uint4*>(a_row + half * ABLK_BYTES + ((uint32_t)(u << 4) ^ r7s)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -210,9 +210,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DGP_THREADS, 1) mlp_
           uint32_t v[32];
           tmem_ld32(taddr_row + (uint32_t)(cg * 32), v);
           tmem_ld_wait();
-          uint32_t mk[4];                           // this group's four steps of the half's words, aligned to bit 3 / bit 19
+          uint32_t mk = 0u;                         // this 32-column group's word
 #pragma unroll
-          for (int p = 0; p < 4; ++p) mk[p] = mask[p] >> (12 - cg * 4);
+          for (int p = 0; p < 4; ++p) mk = (p == cg) ? mask[p] : mk;
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -221,9 +221,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DGP_THREADS, 1) mlp_
               f0 = fmaf(draw.w, w_sigma[half * 128 + cg * 32 + 2 * j], f0);
               f1 = fmaf(draw.w, w_sigma[half * 128 + cg * 32 + 2 * j + 1], f1);
             }
-            if (d >= 1) {                          // columns 32 cg + 2 j, + 1 of the half: word j & 3, step 4 cg + (j >> 2)
-              if (!((mk[j & 3] >> (3 - (j >> 2))) & 1u)) f0 = 0.f;
-              if (!((mk[j & 3] >> (19 - (j >> 2))) & 1u)) f1 = 0.f;
+            if (d >= 1) {                          // columns 32 cg + 2 j, + 1 of the half: bits j and 16 + j of the group's word
+              if (!relu_mask_even(mk, j)) f0 = 0.f;
+              if (!relu_mask_odd(mk, j)) f1 = 0.f;
             }
             pk[j] = pack_bf16(f0, f1);
           }

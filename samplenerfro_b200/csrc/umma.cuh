@@ -231,21 +231,30 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // The dgrad chain needs, per layer, only WHETHER an activation was positive.  Reading that back from the saved bf16
 // activations costs 512 B per sample and layer (3.7 GB of the 7.4 GB the dgrad kernel moved per 4096-ray step); the forward
 // epilogue has the values in registers, so it emits the bits: 32 B per sample and layer.
-// Format: mask [layer][row][8] uint32.  Words 0-3 cover columns 0..127, words 4-7 columns 128..255 (layer 9, 128 columns:
-// words q and 4 + q are OR-ed by the reader; one writer fills bits 15..8, the other 7..0, or one fills all).  Within a half,
-// column c sits in word q = (c >> 1) & 3 at bit 16 * (c & 1) + 15 - s with s = 4 * (c >> 5) + ((c & 31) >> 3): the writer
-// pushes its 16 packed bf16 pairs of every 32-column group in order, `m2[q] = 2 * m2[q] + nz(pair)` where nz has bit 0 / bit
-// 16 set iff the even / odd column is non-zero, i.e. positive after ReLU: (x & 0x7FFF) + 0x7FFF carries into bit 15 of its
-// half exactly when x & 0x7FFF != 0 (four integer ops per pair).
-__device__ __forceinline__ void relu_mask_push(uint32_t (&m2)[4], const uint32_t (&pk)[16]) {
+// Format: mask [layer][row][8] uint32, word g = columns 32 g .. 32 g + 31 (layer 9, 128 columns: words 0..3): the even column
+// 32 g + 2 i sits at bit i, the odd column 32 g + 2 i + 1 at bit 16 + i -- the epilogue holds a group as 16 packed bf16 pairs,
+// and one word per group costs four integer ops per pair: the values are >= 0 after ReLU, (x & 0x7FFF) + 0x7FFF carries into
+// bit 15 of its half exactly when the half is non-zero, and `acc = (t & 0x80008000) | (acc >> 1)` walks pair i's two flags
+// down to bits i and 16 + i.  (The first format interleaved four words per 128 columns at six ops per pair; the mask work
+// was a third of the training forward's instructions, profiles/r6q.)
+__device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&pk)[16]) {
+  uint32_t acc = 0u;
 #pragma unroll
-  for (int g4 = 0; g4 < 4; ++g4)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t t = (pk[4 * g4 + q] & 0x7FFF7FFFu) + 0x7FFF7FFFu;
-      m2[q] = m2[q] * 2u + ((t >> 15) & 0x00010001u);
-    }
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t t = (pk[i] & 0x7FFF7FFFu) + 0x7FFF7FFFu;
+    acc = (t & 0x80008000u) | (acc >> 1);
+  }
+  return acc;
 }
+// w[idx] = m for a loop-variant idx without sending the array to local memory (N predicated moves)
+template <int N>
+__device__ __forceinline__ void relu_mask_set(uint32_t (&w)[N], int idx, uint32_t m) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = (i == idx) ? m : w[i];
+}
+// reader: are columns 2 i / 2 i + 1 of the group positive?
+__device__ __forceinline__ bool relu_mask_even(uint32_t word, int i) { return (word >> i) & 1u; }
+__device__ __forceinline__ bool relu_mask_odd(uint32_t word, int i) { return (word >> (16 + i)) & 1u; }
 
 struct EncMlpArgs {
   const uint8_t* packed;
@@ -255,7 +264,7 @@ struct EncMlpArgs {
   float4* raw_out;
   __nv_bfloat16* layer_out;  // debug / training dump [10][M][256] or null
   __nv_bfloat16* enc_out;    // training dump of the encodings [2][M][64] (pos_enc, dir_enc) or null
-  uint32_t* mask_out;        // training dump of the ReLU bit-masks [10][M][8] (relu_mask_push) or null
+  uint32_t* mask_out;        // training dump of the ReLU bit-masks [10][M][8] (relu_mask32) or null
   long long* prof;           // development aid: clock64 stamps of CTA 0, [3][10][4], or null
   int n_groups;              // ceil(n_samples / (128*NT))
   int dbg;                   // development aid (timing experiments only; results are wrong when set)
